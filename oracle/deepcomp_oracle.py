@@ -1,0 +1,457 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference's env.step hot path.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+leg may import this module; the product path (``deepcomp_b200/``) never does and fails loudly
+when its CUDA library is missing.
+
+Parity status: **pinned against the live reference** -- ``tests/test_oracle_vs_reference.py`` runs
+this restatement in lock-step with the unmodified reference env imported from /root/reference
+(under ``oracle/ref_stubs.py``) and asserts *bit-identical* positions, masks, lost-connection
+counts, link rates, utilities, observations and rewards; ``oracle/make_golden.py`` freezes traces of
+the reference itself into ``tests/golden/*.npz`` so that the same pin travels to the GPU box.  The
+reference has no tests / golden vectors of its own; the one arithmetic piece
+that lives in an un-vendored dependency is shapely==1.7.0 (setup.py:17) ``Point.distance`` ==
+GEOS ``sqrt(dx*dx+dy*dy)``, restated in ``_dist``.
+
+The restatement keeps the reference's per-object evaluation order (dict insertion order of
+``ue.bs_dr``, list order of ``bs.conn_ues``) so that floating-point sums associate identically.
+All file:line citations are relative to /root/reference/deepcomp/.
+"""
+import math
+import random
+from fractions import Fraction
+
+import numpy as np
+
+# util/constants.py:28,34-35,40-41
+EPSILON = 1e-16
+FAIR_WEIGHT_ALPHA = 1
+FAIR_WEIGHT_BETA = 1
+MIN_UTILITY = -20
+MAX_UTILITY = 20
+# env/entities/station.py:10
+SNR_THRESHOLD = 2e-8
+# env/entities/station.py:26-30
+BW = 9e6
+FREQUENCY = 2500
+NOISE = 1e-9
+TX_POWER = 30
+BS_HEIGHT = 50
+UE_HEIGHT = 1.5
+
+SHARING_MIX = ['resource-fair', 'rate-fair', 'proportional-fair']          # util/env_setup.py:48
+SHARING_CODE = {'resource-fair': 0, 'rate-fair': 1, 'proportional-fair': 2, 'max-cap': 3}
+
+
+def sharing_for_bs(sharing, b):
+    """util/env_setup.py:40-49"""
+    return sharing if sharing != 'mixed' else SHARING_MIX[b % 3]
+
+
+def grid_layout(n_bs, pitch=100, border=10):
+    """Synthetic layout of SURVEY.md section 8d (pitch = cli.py:41 --bs-dist default, border = env_setup.py:87)."""
+    cols = int(np.ceil(np.sqrt(n_bs)))
+    rows = int(np.ceil(n_bs / cols))
+    width = max(pitch * (cols - 1) + 2 * border, 120)
+    height = max(pitch * (rows - 1) + 2 * border, 120)
+    bs_xy = [(border + pitch * (b % cols), border + pitch * (b // cols)) for b in range(n_bs)]
+    return width, height, bs_xy
+
+
+def path_loss_consts():
+    """env/entities/station.py:110-116 -- evaluated exactly as the reference does (np.log10 on scalars)."""
+    ch = 0.8 + (1.1 * np.log10(FREQUENCY) - 0.7) * UE_HEIGHT - 1.56 * np.log10(FREQUENCY)
+    const1 = 69.55 + 26.16 * np.log10(FREQUENCY) - 13.82 * np.log10(BS_HEIGHT) - ch
+    const2 = 44.9 - 6.55 * np.log10(BS_HEIGHT)
+    return const1, const2
+
+
+_CONST1, _CONST2 = path_loss_consts()
+
+
+def _dist(ax, ay, bx, by):
+    """shapely 1.7.0 Point.distance -> GEOS: sqrt(dx*dx + dy*dy) in double (station.py:124, movement.py:142)."""
+    dx = ax - bx
+    dy = ay - by
+    return math.sqrt(dx * dx + dy * dy)
+
+
+def _fma(a, b, c):
+    """Correctly rounded a*b+c (Python 3.12 has no math.fma)."""
+    return float(Fraction(a) * Fraction(b) + Fraction(c))
+
+
+def _norm2(vx, vy):
+    """
+    np.linalg.norm of a 2-vector (movement.py:151) == sqrt(x.dot(x)); the dot product goes to OpenBLAS ddot whose
+    x86 FMA3 kernels accumulate acc = fma(x_i, x_i, acc) -- i.e. sqrt(fma(vy, vy, vx*vx)).  Verified bit-identical
+    to np.linalg.norm on 1e5 random vectors in this container ("pinned arithmetic").
+    """
+    return math.sqrt(_fma(vy, vy, vx * vx))
+
+
+def snr_of_distance(distance):
+    """station.py:110-127: Okumura-Hata path loss -> received power -> SNR"""
+    pl = _CONST1 + _CONST2 * np.log10(distance + EPSILON)
+    signal = 10 ** ((TX_POWER - pl) / 10)
+    return signal / NOISE
+
+
+def log_utility(curr_dr):
+    """env/util/utility.py:36-54"""
+    if curr_dr == 0:
+        return MIN_UTILITY
+    return np.clip(10 * np.log10(curr_dr), MIN_UTILITY, MAX_UTILITY)
+
+
+def threshold_distance():
+    """Largest double d with snr(d) > SNR_THRESHOLD (station.py:224); used by fast restatements (C / CUDA)."""
+    lo, hi = 60.0, 80.0
+    assert snr_of_distance(lo) > SNR_THRESHOLD >= snr_of_distance(hi)
+    while True:
+        mid = 0.5 * (lo + hi)
+        if mid == lo or mid == hi:
+            break
+        if snr_of_distance(mid) > SNR_THRESHOLD:
+            lo = mid
+        else:
+            hi = mid
+    return lo
+
+
+class _UE:
+    __slots__ = ('idx', 'id', 'x', 'y', 'init_x', 'init_y', 'init_velocity', 'velocity', 'wx', 'wy', 'pausing',
+                 'curr_pause', 'rng', 'mrng', 'bs_dr', 'ewma_dr')
+
+
+class OracleEnv:
+    """
+    One env instance, restating MobileEnv (+ CentralRelNormEnv / MultiAgentMobileEnv) for the in-scope feature set:
+    RandomWaypoint movement, log utility, fixed UE population, the four sharing models.
+
+    kind: 'central' (multi_ue/central.py:143-152) or 'multi' (multi_ue/multi_agent.py:6-107)
+    """
+
+    def __init__(self, kind, n_ue, bs_xy, map_wh, sharing='mixed', velocities='slow', seed=None, reward='avg',
+                 episode_length=100, rand_episodes=False, init_pos=None, pause_duration=2, border_buffer=10):
+        assert kind in ('central', 'multi')
+        self.kind = kind
+        self.n_ue = n_ue
+        self.bs_xy = [(float(x), float(y)) for x, y in bs_xy]
+        self.n_bs = len(bs_xy)
+        # entities/map.py:20-21
+        self.width, self.height = int(map_wh[0]), int(map_wh[1])
+        if isinstance(sharing, str):
+            sharing = [sharing_for_bs(sharing, b) for b in range(self.n_bs)]
+        self.sharing = list(sharing)
+        if not isinstance(velocities, (list, tuple)):
+            velocities = [velocities] * n_ue
+        self.reward_agg = reward
+        self.episode_length = episode_length
+        self.rand_episodes = rand_episodes
+        self.pause_duration = pause_duration
+        self.border_buffer = border_buffer
+        self.env_seed = seed
+        self.time = 0
+        self.total_utility = 0
+        self.ues = []
+        for i in range(n_ue):
+            ue = _UE()
+            ue.idx = i
+            ue.id = str(i + 1)                                  # util/env_setup.py:148-160
+            ue.init_x, ue.init_y = ('random', 'random') if init_pos is None else init_pos[i]
+            ue.init_velocity = velocities[i]
+            ue.rng = random.Random()                            # entities/user.py:38
+            ue.mrng = random.Random()                           # util/movement.py:14
+            ue.bs_dr = {}
+            ue.ewma_dr = 0
+            ue.x = ue.y = 0.0
+            ue.pausing, ue.curr_pause = False, 0
+            self.ues.append(ue)
+        # per-BS connected-UE lists (station.py:18), in connection order
+        self.conn_ues = [[] for _ in range(self.n_bs)]
+        self.seed(seed)
+        self.last_lost_conn = [0] * n_ue
+
+    # ------------------------------------------------------------------ seeding / reset
+    def seed(self, seed=None):
+        """single_ue/base.py:132-143 (+ user.py:94-96): UE i (1-based) gets seed+100*i for BOTH of its RNGs"""
+        if seed is not None:
+            offset = 0
+            for ue in self.ues:
+                offset += 100
+                ue.rng.seed(seed + offset)
+                ue.mrng.seed(seed + offset)
+
+    def _movement_reset(self, ue):
+        """util/movement.py:110-130"""
+        if ue.init_velocity == 'slow':
+            ue.velocity = ue.mrng.randint(1, 3)
+        elif ue.init_velocity == 'fast':
+            ue.velocity = ue.mrng.randint(5, 10)
+        else:
+            ue.velocity = ue.init_velocity
+        x = ue.mrng.randint(self.border_buffer, int(self.width - self.border_buffer))
+        y = ue.mrng.randint(self.border_buffer, int(self.height - self.border_buffer))
+        ue.wx, ue.wy = float(x), float(y)
+        ue.pausing = False
+        ue.curr_pause = 0
+
+    def reset(self):
+        """single_ue/base.py:169-189; user.py:98-116; station.py:106-108"""
+        if not self.rand_episodes:
+            self.seed(self.env_seed)
+        self.time = 0
+        for ue in self.ues:
+            px = ue.init_x
+            if px == 'random':
+                px = ue.rng.randint(0, int(self.width))
+            py = ue.init_y
+            if py == 'random':
+                py = ue.rng.randint(0, int(self.height))
+            ue.x, ue.y = float(px), float(py)
+            self._movement_reset(ue)
+            ue.bs_dr = {}
+            ue.ewma_dr = 0
+        self.conn_ues = [[] for _ in range(self.n_bs)]
+        return self.get_obs()
+
+    # ------------------------------------------------------------------ radio model
+    def snr(self, b, ue):
+        """station.py:122-127"""
+        bx, by = self.bs_xy[b]
+        return snr_of_distance(_dist(bx, by, ue.x, ue.y))
+
+    def can_connect(self, b, ue):
+        """station.py:222-226"""
+        return self.snr(b, ue) > SNR_THRESHOLD
+
+    def data_rate_unshared(self, b, ue):
+        """station.py:129-138"""
+        return BW * np.log2(1 + self.snr(b, ue))
+
+    def priority(self, b, ue):
+        """station.py:140-150"""
+        return (self.data_rate_unshared(b, ue) ** FAIR_WEIGHT_ALPHA) / (ue.ewma_dr ** FAIR_WEIGHT_BETA + EPSILON)
+
+    def data_rate_shared(self, b, ue, dr_ue_unshared):
+        """station.py:152-202"""
+        conn = self.conn_ues[b]
+        already = ue in conn
+        if not already:
+            ue.bs_dr[b] = self.data_rate_unshared(b, ue)
+            conn.append(ue)
+        model = self.sharing[b]
+        if model == 'resource-fair':
+            dr = dr_ue_unshared / len(conn)
+        elif model == 'rate-fair':
+            total_inverse_dr = sum([1 / self.data_rate_unshared(b, o) for o in conn])
+            dr = 1 / total_inverse_dr
+        elif model == 'max-cap':
+            max_ue_idx = np.argmax([self.data_rate_unshared(b, o) for o in conn])
+            dr = 0
+            if conn.index(ue) == max_ue_idx:
+                dr = self.data_rate_unshared(b, ue)
+        elif model == 'proportional-fair':
+            frac = self.priority(b, ue) / (sum([self.priority(b, o) for o in conn]) + EPSILON)
+            dr = frac * dr_ue_unshared
+        else:
+            raise AssertionError(model)
+        if not already:
+            del ue.bs_dr[b]
+            conn.remove(ue)
+        return dr
+
+    def data_rate(self, b, ue):
+        """station.py:204-220"""
+        if not self.can_connect(b, ue):
+            return 0
+        return self.data_rate_shared(b, ue, self.data_rate_unshared(b, ue))
+
+    # ------------------------------------------------------------------ UE
+    @staticmethod
+    def curr_dr(ue):
+        """user.py:64-69"""
+        return sum(list(ue.bs_dr.values()))
+
+    def utility(self, ue):
+        """user.py:76-92 (log utility only)"""
+        return log_utility(self.curr_dr(ue))
+
+    def connect_to_bs(self, ue, b):
+        """user.py:190-229 with disconnect=True (the only way the env calls it, base.py:263)"""
+        if b in ue.bs_dr:
+            del ue.bs_dr[b]
+            self.conn_ues[b].remove(ue)
+            return
+        if self.can_connect(b, ue):
+            ue.bs_dr[b] = self.data_rate(b, ue)
+            self.conn_ues[b].append(ue)
+
+    def movement_step(self, ue):
+        """util/movement.py:132-181"""
+        if ue.x == ue.wx and ue.y == ue.wy:
+            ue.pausing = True
+        if ue.pausing:
+            if ue.curr_pause < self.pause_duration:
+                ue.curr_pause += 1
+                return
+            self._movement_reset(ue)
+        if _dist(ue.x, ue.y, ue.wx, ue.wy) <= ue.velocity:
+            ue.x, ue.y = ue.wx, ue.wy
+            return
+        vx = ue.wx - ue.x
+        vy = ue.wy - ue.y
+        norm = _norm2(vx, vy)
+        ue.x = ue.x + ue.velocity * (vx / norm)
+        ue.y = ue.y + ue.velocity * (vy / norm)
+
+    def move(self, ue, weight=0.9):
+        """user.py:148-188"""
+        self.movement_step(ue)
+        remove = [b for b in ue.bs_dr if not self.can_connect(b, ue)]
+        for b in remove:
+            del ue.bs_dr[b]
+            self.conn_ues[b].remove(ue)
+        ue.ewma_dr = weight * self.curr_dr(ue) + (1 - weight) * ue.ewma_dr
+        return len(remove)
+
+    # ------------------------------------------------------------------ env
+    @staticmethod
+    def calc_reward(utility, penalty):
+        """single_ue/base.py:158-167"""
+        clip_util = np.clip(utility, MIN_UTILITY, MAX_UTILITY)
+        return np.clip(clip_util + penalty, MIN_UTILITY, MAX_UTILITY) / MAX_UTILITY
+
+    def update_ue_drs_rewards(self, update_only=False):
+        """single_ue/base.py:315-335 (penalties are identically 0, base.py:257)"""
+        rewards = []
+        for ue in self.ues:
+            for b in ue.bs_dr:                                  # user.py:143-146
+                ue.bs_dr[b] = self.data_rate(b, ue)
+            rewards.append(0 if update_only else self.calc_reward(self.utility(ue), 0))
+        return rewards
+
+    def get_ue_obs(self, ue):
+        """single_ue/variants.py:271-303"""
+        bs_conn = [int(b in ue.bs_dr) for b in range(self.n_bs)]
+        bs_dr = [self.snr(b, ue) for b in range(self.n_bs)]
+        max_dr = max(bs_dr)
+        if max_dr == 0:
+            bs_norm_dr = [0 for _ in bs_dr]
+        else:
+            bs_norm_dr = [dr / max_dr for dr in bs_dr]
+        utility = [self.utility(ue) / MAX_UTILITY]
+        ues_at_bs = [len(self.conn_ues[b]) / self.n_ue for b in range(self.n_bs)]
+        avg_util = []
+        for b in range(self.n_bs):                              # station.py:71-76
+            c = self.conn_ues[b]
+            avg_util.append((np.mean([self.utility(o) for o in c]) if len(c) > 0 else 0) / MAX_UTILITY)
+        return {'connected': bs_conn, 'dr': bs_norm_dr, 'utility': utility, 'ues_at_bs': ues_at_bs,
+                'util_at_bs': avg_util}
+
+    def get_obs(self):
+        """
+        Flat observation in RLlib's Dict-flattening order (alphabetical keys).
+        central (central.py:31-57,147-152): [connected(N*M) | dr(N*M) | utility(N)]
+        multi (multi_agent.py:32-37, variants.py:255-269): per UE [connected(M) | dr(M) | ues_at_bs(M) | util_at_bs(M) | utility(1)]
+        """
+        per_ue = [self.get_ue_obs(ue) for ue in self.ues]
+        if self.kind == 'central':
+            out = []
+            for key in ('connected', 'dr', 'utility'):
+                for o in per_ue:
+                    out.extend(o[key])
+            return np.asarray(out, dtype=np.float64)
+        return np.stack([np.concatenate([np.asarray(o[k], dtype=np.float64)
+                                         for k in ('connected', 'dr', 'ues_at_bs', 'util_at_bs', 'utility')])
+                         for o in per_ue])
+
+    def step_reward(self, rewards):
+        if self.kind == 'central':
+            # multi_ue/central.py:65-73
+            if self.reward_agg == 'avg':
+                return np.float64(np.mean(rewards))
+            if self.reward_agg == 'sum':
+                return np.float64(sum(rewards))
+            if self.reward_agg == 'min':
+                return np.float64(min(rewards))
+            raise NotImplementedError(self.reward_agg)
+        # multi_ue/multi_agent.py:39-95
+        out = []
+        for ue in self.ues:
+            agg_util = self.utility(ue)
+            in_range = [b for b in range(self.n_bs) if self.can_connect(b, ue)]
+            if len(in_range) > 0:
+                if self.reward_agg == 'avg':
+                    num_neighbors = sum([len(self.conn_ues[b]) for b in in_range])
+                    if num_neighbors > 0:
+                        total = sum([sum([self.utility(o) for o in self.conn_ues[b]]) for b in in_range])
+                        if len(ue.bs_dr) == 0:
+                            agg_util = (total + self.utility(ue)) / (num_neighbors + 1)
+                        else:
+                            agg_util = total / num_neighbors
+                elif self.reward_agg == 'sum':
+                    # user.py:238-244 builds a *set* of neighbours; its iteration order is hash order in the
+                    # reference -- summed in UE-index order here (differences are O(1 ulp))
+                    neigh = set()
+                    for b in ue.bs_dr:
+                        neigh.update(o.idx for o in self.conn_ues[b])
+                    agg_util = sum([rewards[j] for j in sorted(neigh)])
+                elif self.reward_agg == 'min':
+                    mins = []
+                    for b in in_range:                          # station.py:78-83
+                        c = self.conn_ues[b]
+                        mins.append(min([self.utility(o) for o in c]) if len(c) > 0 else MAX_UTILITY)
+                    agg_util = min(mins + [self.utility(ue)])
+                else:
+                    raise NotImplementedError(self.reward_agg)
+            out.append(agg_util)
+        return np.asarray(out, dtype=np.float64)
+
+    def step(self, actions):
+        """single_ue/base.py:413-466. actions: int[N], 0 = noop, b+1 = toggle BS b"""
+        actions = np.asarray(actions)
+        assert actions.shape == (self.n_ue,) and np.all(actions >= 0) and np.all(actions <= self.n_bs)
+        for ue in self.ues:                                     # base.py:247-282
+            a = int(actions[ue.idx])
+            if a > 0:
+                self.connect_to_bs(ue, a - 1)
+        rewards_before = self.update_ue_drs_rewards()
+        self.last_lost_conn = [self.move(ue) for ue in self.ues]
+        self.update_ue_drs_rewards(update_only=True)
+        self.time += 1
+        sum_utility = sum([self.utility(ue) for ue in self.ues])
+        self.total_utility += sum_utility
+        obs = self.get_obs()
+        reward = self.step_reward(rewards_before)
+        out = self.snapshot()
+        out.update(obs=obs, reward=reward, lost_conn=np.asarray(self.last_lost_conn, dtype=np.int32),
+                   sum_utility=np.float64(sum_utility), time=self.time, done=None)
+        return out
+
+    # ------------------------------------------------------------------ snapshots (same keys as ref_loader.RefTrace)
+    def snapshot(self):
+        n, m = self.n_ue, self.n_bs
+        mask = np.zeros((n, m), dtype=np.uint8)
+        rates = np.zeros((n, m), dtype=np.float64)
+        snr = np.zeros((n, m), dtype=np.float64)
+        for ue in self.ues:
+            for b, r in ue.bs_dr.items():
+                mask[ue.idx, b] = 1
+                rates[ue.idx, b] = r
+            for b in range(m):
+                snr[ue.idx, b] = self.snr(b, ue)
+        return dict(
+            pos=np.array([[ue.x, ue.y] for ue in self.ues], dtype=np.float64), mask=mask, link_rates=rates, snr=snr,
+            curr_dr=np.array([float(self.curr_dr(ue)) for ue in self.ues]),
+            ewma=np.array([float(ue.ewma_dr) for ue in self.ues]),
+            utility=np.array([float(self.utility(ue)) for ue in self.ues]),
+            movement=np.array([[ue.velocity, ue.wx, ue.wy, float(ue.pausing), ue.curr_pause] for ue in self.ues],
+                              dtype=np.float64))
+
+    def reset_trace(self):
+        obs = self.reset()
+        out = self.snapshot()
+        out['obs'] = obs
+        return out

@@ -1,0 +1,142 @@
+"""TEST INFRASTRUCTURE ONLY -- freeze traces of the *unmodified reference env* into tests/golden/*.npz.
+
+Run in a container that has /root/reference:   python -m oracle.make_golden
+The reference (deepcomp.env.multi_ue.{central,multi_agent}) is imported under oracle/ref_stubs.py and driven with
+seeded uniform-random actions; every array the parity tests compare is recorded per step.  The fixtures are the
+pin that travels to the GPU box (where /root/reference does not exist).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+from . import ref_loader as rl
+
+OUT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+STEP_KEYS = ['pos', 'mask', 'link_rates', 'snr', 'curr_dr', 'ewma', 'utility', 'movement', 'obs', 'reward',
+             'lost_conn', 'sum_utility', 'time']
+RESET_KEYS = ['pos', 'mask', 'link_rates', 'snr', 'curr_dr', 'ewma', 'utility', 'movement', 'obs']
+
+
+def medium_map(bs_dist=100, border=10):
+    """util/env_setup.py:87-104 create_dyn_medium_map -- BASELINE.json configs[0] (3 BS)"""
+    y_dist = np.sqrt(bs_dist ** 2 - (bs_dist / 2) ** 2)
+    wh = (2 * border + bs_dist, 2 * border + y_dist)
+    bs = [(border, border), (border + bs_dist, border), (border + bs_dist / 2, border + y_dist)]
+    return wh, bs
+
+
+def scenarios():
+    wh, bs = medium_map()
+    S = []
+    for kind in ('central', 'multi'):
+        S.append(dict(name=f'medium3bs_5ue_{kind}', kind=kind, n_ue=5, bs_xy=bs, map_wh=wh, sharing='mixed',
+                      velocities='slow', seed=42, reward='avg', steps=100, action_seed=1, episodes=2))
+    W, H, gbs = rl.grid_layout(10)
+    for kind in ('central', 'multi'):
+        S.append(dict(name=f'grid10bs_50ue_{kind}', kind=kind, n_ue=50, bs_xy=gbs, map_wh=(W, H), sharing='mixed',
+                      velocities='slow', seed=1000, reward='avg', steps=25, action_seed=2, episodes=1))
+    W, H, gbs = rl.grid_layout(5)
+    vel = ['slow', 'fast', 0, 2.5] * 3
+    for sharing in ('resource-fair', 'rate-fair', 'proportional-fair', 'max-cap', 'mixed'):
+        for kind, reward in (('central', 'avg'), ('multi', 'avg'), ('multi', 'min'), ('central', 'min'),
+                             ('central', 'sum'), ('multi', 'sum')):
+            if reward != 'avg' and sharing not in ('mixed', 'max-cap'):
+                continue
+            S.append(dict(name=f'grid5bs_12ue_{kind}_{reward}_{sharing}', kind=kind, n_ue=12, bs_xy=gbs,
+                          map_wh=(W, H), sharing=sharing, velocities=vel, seed=7, reward=reward, steps=60,
+                          action_seed=3, episodes=1))
+    # fixed initial positions + long run on a tiny map: many waypoint redraws / pauses (movement.py:168-181)
+    S.append(dict(name='tiny_redraw_multi', kind='multi', n_ue=6, bs_xy=[(30, 30), (90, 90)], map_wh=(120, 120),
+                  sharing='mixed', velocities=['fast', 'fast', 'slow', 7, 'fast', 0], seed=99, reward='avg', steps=150,
+                  action_seed=4, episodes=1, init_pos=[(60, 60), ('random', 'random'), (10, 110), (0, 0),
+                                                        ('random', 5), (120, 120)]))
+    return S
+
+
+def record(sc):
+    env = rl.build_env(sc['kind'], sc['n_ue'], sc['seed'], sc['bs_xy'], sc['map_wh'], sharing=sc['sharing'],
+                       velocities=sc['velocities'], reward=sc['reward'], episode_length=sc['steps'],
+                       init_pos=sc.get('init_pos'))
+    tr = rl.RefTrace(env, sc['kind'])
+    rng = np.random.default_rng(sc['action_seed'])
+    n_bs = len(sc['bs_xy'])
+    out = {}
+    actions = []
+    steps = {k: [] for k in STEP_KEYS}
+    resets = {k: [] for k in RESET_KEYS}
+    for ep in range(sc['episodes']):
+        r = tr.reset()
+        for k in RESET_KEYS:
+            resets[k].append(r[k])
+        for t in range(sc['steps']):
+            a = rng.integers(0, n_bs + 1, sc['n_ue']).astype(np.int32)
+            s = tr.step(a)
+            # base.py:371-381: done is None; multi_agent.py:97-102: dict of None incl. '__all__'
+            if sc['kind'] == 'central':
+                assert s['done'] is None
+            else:
+                assert set(s['done'].keys()) == {str(i + 1) for i in range(sc['n_ue'])} | {'__all__'}
+                assert all(v is None for v in s['done'].values())
+            actions.append(a)
+            for k in STEP_KEYS:
+                steps[k].append(s[k])
+    out['actions'] = np.stack(actions)
+    for k in STEP_KEYS:
+        out['step_' + k] = np.stack([np.asarray(v) for v in steps[k]])
+    for k in RESET_KEYS:
+        out['reset_' + k] = np.stack([np.asarray(v) for v in resets[k]])
+    cfg = {k: v for k, v in sc.items()}
+    cfg['bs_xy'] = [[float(x), float(y)] for x, y in sc['bs_xy']]
+    cfg['map_wh'] = [float(sc['map_wh'][0]), float(sc['map_wh'][1])]
+    out['config'] = np.array(json.dumps(cfg))
+    return out
+
+
+def anchors():
+    """Known answers that exist only as comments in the reference, evaluated by the
+    reference's own functions."""
+    R = rl._import_reference()
+    from deepcomp.env.util.utility import log_utility
+    import random
+    bs = R['Basestation']('A', R['Point'](0, 0), 'resource-fair')
+    d = np.array([0.0, 1e-3, 0.5, 1, 10, 11, 12.16, 46, 68, 68.9, 68.92488308058006, 68.92488308058007, 69, 100, 250, 1000])
+    snr = np.array([float(bs.snr(R['Point'](x, 0))) for x in d])
+    ue = type('U', (), {})()
+    rate = []
+    for x in d:
+        ue.pos = R['Point'](x, 0)
+        rate.append(float(bs.data_rate_unshared(ue)))
+    dr = np.array([0, 1e-9, 0.005, 0.01, 0.5, 1, 2.5, 50, 99.9, 100, 1e4])
+    util = np.array([float(log_utility(x)) for x in dr])
+    seeds = [142, 1100, 0, 2 ** 32 + 5, 7 + 100 * 12]
+    raw = np.array([[random.Random(s).getrandbits(32)] + [0] * 7 for s in seeds], dtype=np.uint64)
+    for i, s in enumerate(seeds):
+        r = random.Random(s)
+        raw[i] = [r.getrandbits(32) for _ in range(8)]
+    ranges = [(0, 300), (0, 300), (1, 3), (10, 290), (10, 290), (5, 10), (0, 120), (10, 110)] * 8
+    ints = np.zeros((len(seeds), len(ranges)), dtype=np.int64)
+    for i, s in enumerate(seeds):
+        r = random.Random(s)
+        ints[i] = [r.randint(a, b) for a, b in ranges]
+    return dict(dist=d, snr=snr, rate_unshared=np.array(rate), dr=dr, log_utility=util,
+                path_loss_1m=np.float64(bs.path_loss(1)), rng_seeds=np.array(seeds, dtype=np.int64), rng_raw=raw,
+                rng_ranges=np.array(ranges, dtype=np.int64), rng_ints=ints)
+
+
+def main():
+    if not rl.available():
+        sys.exit('reference not found under ' + rl.REFERENCE_ROOT)
+    os.makedirs(OUT_DIR, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT_DIR, 'anchors.npz'), **anchors())
+    for sc in scenarios():
+        data = record(sc)
+        path = os.path.join(OUT_DIR, sc['name'] + '.npz')
+        np.savez_compressed(path, **data)
+        print(f"{sc['name']}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == '__main__':
+    main()

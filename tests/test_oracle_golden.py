@@ -1,0 +1,60 @@
+"""CPU: the oracle restatements (Python and C) against golden traces of the reference itself (tests/golden/)."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+from oracle import deepcomp_oracle as po
+
+from helpers import GOLDEN_DIR, check_against_golden, golden_names, load_golden, oracle_kwargs
+
+
+def test_anchor_known_answers():
+    """Comment-level known answers of the reference (station.py:9,33-35; utility.py:49)."""
+    z = np.load(f'{GOLDEN_DIR}/anchors.npz')
+    snr = np.array([float(po.snr_of_distance(d)) for d in z['dist']])
+    assert np.array_equal(snr, z['snr'])
+    rate = np.array([float(po.BW * np.log2(1 + s)) for s in snr])
+    assert np.array_equal(rate, z['rate_unshared'])
+    util = np.array([float(po.log_utility(x)) for x in z['dr']])
+    assert np.array_equal(util, z['log_utility'])
+    assert po._CONST1 + po._CONST2 * np.log10(1 + po.EPSILON) == z['path_loss_1m']
+    # "threshold corresponds roughly to a distance of 69m" (station.py:9)
+    thr = po.threshold_distance()
+    assert po.snr_of_distance(thr) > po.SNR_THRESHOLD >= po.snr_of_distance(np.nextafter(thr, 100))
+    assert 68.92 < thr < 68.93
+    # "1 Mbit range (46m)" (station.py:33)
+    assert abs(po.BW * np.log2(1 + po.snr_of_distance(46)) - 1.0175) < 1e-3
+
+
+def test_rng_known_answers():
+    """MT19937 + CPython randint of the C restatement == random.Random draws recorded from the reference RNG."""
+    z = np.load(f'{GOLDEN_DIR}/anchors.npz')
+    ranges = [tuple(r) for r in z['rng_ranges'].tolist()]
+    for i, seed in enumerate(z['rng_seeds'].tolist()):
+        raw, ints = c_oracle.rng_draws(seed, 8, ranges)
+        assert raw.tolist() == z['rng_raw'][i].tolist()
+        assert ints.tolist() == z['rng_ints'][i].tolist()
+    # env seed 42, UE "1" -> random.Random(142): start (298,249), v=3, first waypoint (259,94)
+    raw, ints = c_oracle.rng_draws(142, 4, [(0, 300), (0, 300)])
+    assert raw.tolist() == [2502198289, 2976738031, 2921394369, 2747885567] and ints.tolist() == [298, 249]
+    _, ints = c_oracle.rng_draws(142, 0, [(1, 3), (10, 290), (10, 290)])
+    assert ints.tolist() == [3, 259, 94]
+
+
+PY_CASES = [n for n in golden_names() if not n.startswith('grid10bs_50ue')] + ['grid10bs_50ue_multi']
+
+
+@pytest.mark.parametrize('name', PY_CASES)
+def test_python_oracle_bit_identical_to_reference(name):
+    cfg, z = load_golden(name)
+    env = po.OracleEnv(**oracle_kwargs(cfg))
+    # multi/'sum' sums over a Python set in hash order in the reference (user.py:238-244): O(1 ulp) freedom
+    exact = not (cfg['kind'] == 'multi' and cfg['reward'] == 'sum')
+    check_against_golden(env, cfg, z, exact_floats=exact)
+
+
+@pytest.mark.parametrize('name', golden_names())
+def test_c_oracle_matches_reference(name):
+    cfg, z = load_golden(name)
+    env = c_oracle.COracleEnv(**oracle_kwargs(cfg))
+    check_against_golden(env, cfg, z, exact_floats=False)
