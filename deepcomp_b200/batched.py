@@ -1,0 +1,301 @@
+"""Batched tensor surface of the B200 env step: K independent DeepCoMP env instances advanced by one CUDA launch.
+
+This is the layer the gym / RLlib-shaped facades (``deepcomp_b200.env``, ``deepcomp_b200.rllib``) sit on.  It mirrors
+``MobileEnv`` (reference deepcomp/env/single_ue/base.py:20-466) for K envs at once: ``reset() -> obs``,
+``step(actions) -> (obs, reward, done, info)``, ``seed``-able per env, with ``done`` always ``None``
+(base.py:371-381).  PyTorch only provides device memory and the stream; all compute is in libdeepcomp_b200.so.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DcbConfig, DcbOutputs, DcbStateHost, check
+
+KIND = {'central': 0, 'multi': 1}
+REWARD = {'avg': 0, 'sum': 1, 'min': 2}
+SHARING = {'resource-fair': 0, 'rate-fair': 1, 'proportional-fair': 2, 'max-cap': 3}
+SHARING_MIX = ['resource-fair', 'rate-fair', 'proportional-fair']   # reference util/env_setup.py:48
+VELOCITY = {'slow': -1.0, 'fast': -2.0}
+
+
+def sharing_for_bs(sharing, bs_idx):
+    """reference util/env_setup.py:40-49 get_sharing_for_bs"""
+    if sharing != 'mixed':
+        if sharing not in SHARING:
+            raise ValueError(f"sharing model {sharing!r} not supported; one of {sorted(SHARING)} or 'mixed'")
+        return sharing
+    return SHARING_MIX[bs_idx % len(SHARING_MIX)]
+
+
+def env_seeds(base_seed, num_envs, n_ue, first_env=0):
+    """
+    Seeds for a batch of envs.  UE i of an env draws from random.Random(seed + 100*i) (base.py:138-143), so consecutive
+    env seeds must be >= 100*(N+1) apart or UE streams of different envs collide.
+    `first_env` is the global index of this shard's first env, so a sharded batch reproduces the unsharded one.
+    """
+    k = np.arange(first_env, first_env + num_envs, dtype=np.int64)
+    return np.int64(base_seed) + k * np.int64(100 * (n_ue + 1))
+
+
+class BatchedMobileEnv:
+    """K env instances of one scenario (same map, BS layout and UE classes; per-env seeds) on one GPU."""
+
+    def __init__(self, num_envs, n_ue, bs_xy, map_wh, kind='multi', sharing='mixed', velocities='slow', seed=0,
+                 seeds=None, reward='avg', episode_length=100, rand_episodes=False, auto_reset=False, init_pos=None,
+                 pause_duration=2, border_buffer=10, device=None, first_env=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("deepcomp_b200 needs a CUDA device: the env step is a CUDA kernel and has no CPU "
+                               "fallback")
+        self._L = _lib.load()
+        if kind not in KIND:
+            raise ValueError(f"kind must be 'central' or 'multi', got {kind!r}")
+        if reward not in REWARD:
+            # reference raises NotImplementedError for unknown aggregations (central.py:73, multi_agent.py:92)
+            raise NotImplementedError(f"Unexpected reward aggregation: {reward}")
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        self.num_envs, self.n_ue, self.kind, self.reward_agg = int(num_envs), int(n_ue), kind, reward
+        bs = np.ascontiguousarray(np.asarray(bs_xy, dtype=np.float64).reshape(-1, 2))
+        self.n_bs = bs.shape[0]
+        self.bs_xy = bs
+        self.map_wh = (int(map_wh[0]), int(map_wh[1]))      # Map casts to int (map.py:20-21)
+        self.episode_length = int(episode_length)
+        self.rand_episodes, self.auto_reset = bool(rand_episodes), bool(auto_reset)
+        if isinstance(sharing, str):
+            sharing = [sharing_for_bs(sharing, b) for b in range(self.n_bs)]
+        for s in sharing:
+            if s not in SHARING:
+                raise ValueError(f"sharing model {s!r} not supported; one of {sorted(SHARING)}")
+        self.sharing = list(sharing)
+        if not isinstance(velocities, (list, tuple, np.ndarray)):
+            velocities = [velocities] * self.n_ue
+        if len(velocities) != self.n_ue:
+            raise ValueError("need one velocity per UE")
+        self.velocities = list(velocities)
+        vel = np.array([VELOCITY[v] if isinstance(v, str) else float(v) for v in velocities], dtype=np.float64)
+        ixy = np.full((self.n_ue, 2), np.nan, dtype=np.float64)
+        if init_pos is not None:
+            for i, (px, py) in enumerate(init_pos):
+                if px != 'random':
+                    ixy[i, 0] = float(px)
+                if py != 'random':
+                    ixy[i, 1] = float(py)
+        if seeds is None:
+            seeds = env_seeds(seed, self.num_envs, self.n_ue, first_env)
+        seeds = np.ascontiguousarray(np.asarray(seeds, dtype=np.int64))
+        if seeds.shape != (self.num_envs,):
+            raise ValueError("need one seed per env")
+        self.seeds = seeds
+        sh = np.array([SHARING[s] for s in self.sharing], dtype=np.int32)
+
+        cfg = DcbConfig(
+            abi_version=_lib.DCB_ABI_VERSION, device=self.device.index, kind=KIND[kind], reward=REWARD[reward],
+            num_envs=self.num_envs, n_ue=self.n_ue, n_bs=self.n_bs, map_width=self.map_wh[0],
+            map_height=self.map_wh[1], episode_length=self.episode_length, rand_episodes=int(self.rand_episodes),
+            auto_reset=int(self.auto_reset), pause_duration=int(pause_duration), border_buffer=int(border_buffer),
+            host_bs_xy=bs.ctypes.data, host_sharing=sh.ctypes.data, host_velocity=vel.ctypes.data,
+            host_init_xy=ixy.ctypes.data, host_seeds=seeds.ctypes.data)
+        h = ctypes.c_void_p()
+        check(self._L.dcb_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self._h = h
+        self.obs_size = int(self._L.dcb_obs_size(h))
+        self.reward_size = int(self._L.dcb_reward_size(h))
+        self.obs_shape = (self.obs_size,) if kind == 'central' else (self.n_ue, 4 * self.n_bs + 1)
+        self.reward_shape = () if kind == 'central' else (self.n_ue,)
+        self._pinned = None
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            self._L.dcb_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    @property
+    def algorithmic_bytes_per_env_step(self):
+        return int(self._L.dcb_algorithmic_bytes_per_env_step(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self._L.dcb_launch_count(self._h))
+
+    @property
+    def launch_geometry(self):
+        v = [ctypes.c_int32() for _ in range(4)]
+        check(self._L.dcb_launch_geometry(self._h, *[ctypes.byref(x) for x in v]))
+        return dict(envs_per_cta=v[0].value, threads=v[1].value, smem_bytes=v[2].value, grid=v[3].value)
+
+    def check_errors(self):
+        """Raise ValueError if an out-of-range action reached the device (reference: assert in base.py:238 /
+        central.py:61), RuntimeError if a UE ran out of pre-drawn waypoints."""
+        rc = self._L.dcb_check_errors(self._h, self._stream())
+        if rc == -4:
+            raise ValueError(self._L.dcb_last_error().decode())
+        if rc != 0:
+            raise RuntimeError(self._L.dcb_last_error().decode())
+
+    # ------------------------------------------------------------------ observation helpers
+    def split_obs(self, obs):
+        """Packed observation -> dict of views keyed like the reference's obs dicts (variants.py:302-303)."""
+        M, N = self.n_bs, self.n_ue
+        if self.kind == 'central':
+            nm = N * M
+            return {'connected': obs[..., :nm], 'dr': obs[..., nm:2 * nm], 'utility': obs[..., 2 * nm:]}
+        return {'connected': obs[..., :M], 'dr': obs[..., M:2 * M], 'ues_at_bs': obs[..., 2 * M:3 * M],
+                'util_at_bs': obs[..., 3 * M:4 * M], 'utility': obs[..., 4 * M:]}
+
+    def _outputs(self, T, obs=True, info=False, debug=False):
+        K, N, M = self.num_envs, self.n_ue, self.n_bs
+        lead = (T,) if T else ()
+        o = DcbOutputs()
+        t = {}
+        if obs:
+            t['obs'] = self._empty(lead + (K,) + self.obs_shape, torch.float32)
+            o.obs, o.obs_stride = t['obs'].data_ptr(), K * self.obs_size
+        if T != 0:
+            t['reward'] = self._empty(lead + (K,) + self.reward_shape, torch.float32)
+            o.reward, o.reward_stride = t['reward'].data_ptr(), K * self.reward_size
+            t['lost_conn'] = self._empty(lead + (K, N), torch.uint8)
+            o.lost_conn, o.lost_conn_stride = t['lost_conn'].data_ptr(), K * N
+        if info:
+            t['curr_dr'] = self._empty(lead + (K, N), torch.float32)
+            t['utility'] = self._empty(lead + (K, N), torch.float32)
+            t['sum_utility'] = self._empty(lead + (K,), torch.float32)
+            o.curr_dr, o.curr_dr_stride = t['curr_dr'].data_ptr(), K * N
+            o.utility, o.utility_stride = t['utility'].data_ptr(), K * N
+            o.sum_utility, o.sum_utility_stride = t['sum_utility'].data_ptr(), K
+        if debug:
+            f64 = torch.float64
+            t['dbg_obs'] = self._empty((K,) + self.obs_shape, f64)
+            t['dbg_snr'] = self._empty((K, N, M), f64)
+            t['dbg_link_rate'] = self._empty((K, N, M), f64)
+            t['dbg_curr_dr'] = self._empty((K, N), f64)
+            t['dbg_utility'] = self._empty((K, N), f64)
+            t['dbg_sum_utility'] = self._empty((K,), f64)
+            o.dbg_obs, o.dbg_snr = t['dbg_obs'].data_ptr(), t['dbg_snr'].data_ptr()
+            o.dbg_link_rate, o.dbg_curr_dr = t['dbg_link_rate'].data_ptr(), t['dbg_curr_dr'].data_ptr()
+            o.dbg_utility, o.dbg_sum_utility = t['dbg_utility'].data_ptr(), t['dbg_sum_utility'].data_ptr()
+            if T != 0:
+                t['dbg_reward'] = self._empty((K,) + self.reward_shape, f64)
+                o.dbg_reward = t['dbg_reward'].data_ptr()
+        return o, t
+
+    # ------------------------------------------------------------------ gym-like batched API
+    def reset(self, env_ids=None, debug=False):
+        """MobileEnv.reset (base.py:169-189) for all envs or the listed ones; returns the observation of ALL envs."""
+        if env_ids is None:
+            check(self._L.dcb_reset(self._h, None, 0, self._stream()))
+        else:
+            ids = np.ascontiguousarray(np.asarray(env_ids, dtype=np.int32))
+            check(self._L.dcb_reset(self._h, ctypes.c_void_p(ids.ctypes.data), ids.size, self._stream()))
+        return self.observe(debug=debug)
+
+    def observe(self, debug=False):
+        o, t = self._outputs(0, debug=debug, info=debug)
+        check(self._L.dcb_observe(self._h, ctypes.byref(o), self._stream()))
+        return t if debug else t['obs']
+
+    def _check_actions(self, actions, T=None):
+        shape = (self.num_envs, self.n_ue) if T is None else (T, self.num_envs, self.n_ue)
+        if not (isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dtype == torch.int32
+                and actions.is_contiguous() and tuple(actions.shape) == shape and actions.device == self.device):
+            raise ValueError(f"actions must be a contiguous int32 tensor of shape {shape} on {self.device}")
+
+    def step(self, actions, info=True, debug=False):
+        """MobileEnv.step (base.py:413-466) for all K envs.  actions: int32 [K, N] on the device."""
+        self._check_actions(actions)
+        o, t = self._outputs(None, info=info or debug, debug=debug)
+        check(self._L.dcb_step(self._h, ctypes.c_void_p(actions.data_ptr()), ctypes.byref(o), self._stream()))
+        if debug:
+            return t
+        inf = {'lost_conn': t['lost_conn']}
+        if info:
+            inf.update(curr_dr=t['curr_dr'], utility=t['utility'], sum_utility=t['sum_utility'])
+        return t['obs'], t['reward'], None, inf
+
+    def step_many(self, actions, obs=True, info=False, out=None):
+        """
+        T consecutive steps in one launch.  actions: int32 [T, K, N].  Returns dict of [T, ...] tensors
+        (obs, reward, lost_conn[, curr_dr, utility, sum_utility]); pass `out` (from a previous call) to reuse buffers.
+        """
+        T = int(actions.shape[0])
+        self._check_actions(actions, T)
+        if out is None:
+            o, t = self._outputs(T, obs=obs, info=info)
+            t['_struct'] = o
+        else:
+            o, t = out['_struct'], out
+        check(self._L.dcb_step_many(self._h, ctypes.c_void_p(actions.data_ptr()), T, ctypes.byref(o), self._stream()))
+        return t
+
+    # ------------------------------------------------------------------ host-buffer path (e2e)
+    def pinned_buffers(self):
+        """Pinned host buffers for step_host: actions int32 [K,N], obs, reward, lost_conn."""
+        if self._pinned is None:
+            K, N = self.num_envs, self.n_ue
+            self._pinned = dict(
+                actions=torch.empty((K, N), dtype=torch.int32).pin_memory(),
+                obs=torch.empty((K,) + self.obs_shape, dtype=torch.float32).pin_memory(),
+                reward=torch.empty((K,) + self.reward_shape, dtype=torch.float32).pin_memory(),
+                lost_conn=torch.empty((K, N), dtype=torch.uint8).pin_memory())
+        return self._pinned
+
+    def step_host(self, actions=None):
+        """
+        One step through host memory: H2D copy of the actions, the step, D2H copies of obs / reward / lost_conn, and a
+        stream synchronise -- all inside the C-ABI call dcb_step_host.  `actions`: None (already written into
+        pinned_buffers()['actions']) or an int array [K, N].
+        """
+        pb = self.pinned_buffers()
+        if actions is not None:
+            pb['actions'].copy_(torch.as_tensor(np.asarray(actions, dtype=np.int32)))
+        check(self._L.dcb_step_host(self._h, ctypes.c_void_p(pb['actions'].data_ptr()),
+                                    ctypes.c_void_p(pb['obs'].data_ptr()), ctypes.c_void_p(pb['reward'].data_ptr()),
+                                    ctypes.c_void_p(pb['lost_conn'].data_ptr()), self._stream()))
+        return pb['obs'], pb['reward'], None, {'lost_conn': pb['lost_conn']}
+
+    # ------------------------------------------------------------------ state snapshots
+    def get_state(self):
+        K, N = self.num_envs, self.n_ue
+        st = dict(pos=np.zeros((K, N, 2)), mask=np.zeros((K, N), dtype=np.uint64), ewma=np.zeros((K, N)),
+                  movement=np.zeros((K, N, 5)), time=np.zeros(K, dtype=np.int32))
+        s = DcbStateHost(**{k: v.ctypes.data for k, v in st.items()})
+        check(self._L.dcb_get_state(self._h, ctypes.byref(s)))
+        return st
+
+    def set_state(self, **arrays):
+        """Inject any of pos [K,N,2] f64, mask [K,N] u64, ewma [K,N] f64, movement [K,N,5] f64, time [K] i32."""
+        K, N = self.num_envs, self.n_ue
+        spec = dict(pos=((K, N, 2), np.float64), mask=((K, N), np.uint64), ewma=((K, N), np.float64),
+                    movement=((K, N, 5), np.float64), time=((K,), np.int32))
+        keep = {}
+        s = DcbStateHost()
+        for k, v in arrays.items():
+            shape, dt = spec[k]
+            a = np.ascontiguousarray(np.asarray(v, dtype=dt))
+            if a.shape != shape:
+                raise ValueError(f"{k} must have shape {shape}")
+            keep[k] = a
+            setattr(s, k, a.ctypes.data)
+        check(self._L.dcb_set_state(self._h, ctypes.byref(s)))
+
+    def mask_matrix(self, mask=None):
+        """uint64 bitmask [K,N] -> uint8 [K,N,M] connection matrix"""
+        if mask is None:
+            mask = self.get_state()['mask']
+        b = np.arange(self.n_bs, dtype=np.uint64)
+        return ((mask[..., None] >> b) & np.uint64(1)).astype(np.uint8)

@@ -1,0 +1,492 @@
+// C ABI of libdeepcomp_b200.so (include/deepcomp_b200.h): handle management, launch geometry, host-side glue.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "dcb_internal.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(DCB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                                      \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// station.py:110-127 evaluated on the host with the host libm (the one the reference's NumPy scalars use)
+double host_snr_of_d2(double c1, double c2, double d2) {
+    const double d = sqrt(d2);
+    const double pl = c1 + c2 * log10(d + DCB_EPSILON);
+    const double signal = pow(10.0, (DCB_TX_POWER - pl) / 10.0);
+    return signal / DCB_NOISE;
+}
+
+// Largest squared distance d2 with snr(sqrt(d2)) > SNR_THRESHOLD (station.py:224): the range decision becomes one
+// fp64 compare on the device and agrees with the reference's own evaluation on this side of the boundary.
+double threshold_d2(double c1, double c2) {
+    double lo = 60.0 * 60.0, hi = 80.0 * 80.0;
+    for (;;) {
+        const double mid = 0.5 * (lo + hi);
+        if (mid == lo || mid == hi) break;
+        if (host_snr_of_d2(c1, c2, mid) > DCB_SNR_THRESHOLD) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+}  // namespace
+
+struct dcb_env {
+    dcb_config cfg;   // host pointers inside are NOT retained
+    int device = 0;
+    DevParams p;
+    int threads = 0, grid = 0;
+    size_t smem = 0;
+    int64_t launches = 0;
+    // device allocations
+    double *d_bs_xy = nullptr, *d_vel = nullptr, *d_init_xy = nullptr;
+    int *d_sharing = nullptr;
+    long long *d_seeds = nullptr;
+    double2 *d_pos = nullptr, *d_init_pos = nullptr;
+    uint2 *d_mv = nullptr;
+    unsigned long long *d_mask = nullptr;
+    double *d_ewma = nullptr;
+    int *d_time = nullptr, *d_err = nullptr;
+    uint32_t *d_table = nullptr, *d_pos_skip = nullptr, *d_mv_skip = nullptr;
+    int32_t *d_env_ids = nullptr;
+    int env_ids_cap = 0;
+    // dcb_step_host staging
+    int32_t *d_h_actions = nullptr;
+    float *d_h_obs = nullptr, *d_h_reward = nullptr;
+    uint8_t *d_h_lost = nullptr;
+};
+
+namespace {
+
+// Envs per CTA: keep CTAs at <= 256 threads when N allows it, waste few lanes in the last warp and spread the
+// grid evenly over the SMs (grid sizes just above a multiple of the SM count leave most SMs half idle).
+int choose_envs_per_cta(int K, int N, int M, int kind, int num_sms, size_t smem_cap) {
+    const char *ov = getenv("DCB_ENVS_PER_CTA");
+    if (ov && atoi(ov) > 0) return atoi(ov);
+    int best_e = 1;
+    double best_score = -1.0;
+    const int max_threads = N <= 256 ? 256 : (N <= 512 ? 512 : 1024);
+    for (int E = 1; E * N <= max_threads && E <= K; E++) {
+        const size_t sm = dcb_step_smem_bytes(kind, N, M, E);
+        if (sm > smem_cap) break;
+        const int threads = (E * N + 31) / 32 * 32;
+        const double lane_util = (double)(E * N) / threads;
+        const int grid = (K + E - 1) / E;
+        int per_sm = (int)(smem_cap / sm);
+        const int by_threads = 2048 / threads;
+        if (by_threads < per_sm) per_sm = by_threads;
+        if (per_sm < 1) per_sm = 1;
+        const int waves_slots = num_sms * per_sm;
+        const int waves = (grid + waves_slots - 1) / waves_slots;
+        // fraction of SM-time doing work: total CTAs / (CTA slots occupied by the busiest SM over all waves)
+        const int busiest = (grid + num_sms - 1) / num_sms;
+        const double balance = (double)grid / ((double)busiest * num_sms);
+        const double env_util = (double)K / ((double)grid * E);
+        // mild preference for larger CTAs (fewer barriers per UE of work, better reducer utilisation)
+        const double size_bonus = 1.0 + 0.02 * (threads / 32);
+        const double score = lane_util * balance * env_util * size_bonus / (1.0 + 0.0 * waves);
+        if (score > best_score) { best_score = score; best_e = E; }
+    }
+    return best_e;
+}
+
+int launch_step(dcb_env *env, const int32_t *d_actions, int T, const dcb_outputs *out, cudaStream_t s) {
+    StepArgs a;
+    a.p = env->p;
+    a.actions = d_actions;
+    a.T = T;
+    if (out) a.out = *out;
+    else memset(&a.out, 0, sizeof(a.out));
+    if (a.out.dbg_link_rate)
+        CU(cudaMemsetAsync(a.out.dbg_link_rate, 0, sizeof(double) * (size_t)env->p.K * env->p.N * env->p.M, s));
+    CU(dcb_launch_step(a, env->threads, env->grid, env->smem, s));
+    env->launches++;
+    return DCB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dcb_abi_version(void) { return DCB_ABI_VERSION; }
+
+const char *dcb_last_error(void) { return g_err; }
+
+int64_t dcb_obs_size(const dcb_env *env) {
+    const int64_t N = env->p.N, M = env->p.M;
+    return env->p.kind == DCB_KIND_CENTRAL ? 2 * N * M + N : N * (4 * M + 1);
+}
+
+int64_t dcb_reward_size(const dcb_env *env) { return env->p.kind == DCB_KIND_CENTRAL ? 1 : env->p.N; }
+
+int64_t dcb_algorithmic_bytes_per_env_step(const dcb_env *env) {
+    // state R+W per UE 56 + 8W (W = ceil(M/32) mask words), actions 4, obs f32, reward f32
+    const int64_t N = env->p.N, M = env->p.M, W = (M + 31) / 32;
+    if (env->p.kind == DCB_KIND_CENTRAL) return N * (60 + 8 * W + 8 * M + 4) + 4;
+    return N * (64 + 8 * W + 16 * M + 4);
+}
+
+int64_t dcb_launch_count(const dcb_env *env) { return env->launches; }
+
+int dcb_launch_geometry(const dcb_env *env, int32_t *envs_per_cta, int32_t *threads, int32_t *smem_bytes,
+                        int32_t *grid) {
+    if (!env) return fail(DCB_ERR_INVALID_ARG, "null handle");
+    if (envs_per_cta) *envs_per_cta = env->p.E;
+    if (threads) *threads = env->threads;
+    if (smem_bytes) *smem_bytes = (int32_t)env->smem;
+    if (grid) *grid = env->grid;
+    return DCB_OK;
+}
+
+void dcb_destroy(dcb_env *env) {
+    if (!env) return;
+    DeviceGuard g(env->device);
+    cudaFree(env->d_bs_xy); cudaFree(env->d_vel); cudaFree(env->d_init_xy); cudaFree(env->d_sharing);
+    cudaFree(env->d_seeds); cudaFree(env->d_pos); cudaFree(env->d_init_pos); cudaFree(env->d_mv);
+    cudaFree(env->d_mask); cudaFree(env->d_ewma); cudaFree(env->d_time); cudaFree(env->d_err);
+    cudaFree(env->d_table); cudaFree(env->d_pos_skip); cudaFree(env->d_mv_skip); cudaFree(env->d_env_ids);
+    cudaFree(env->d_h_actions); cudaFree(env->d_h_obs); cudaFree(env->d_h_reward); cudaFree(env->d_h_lost);
+    delete env;
+}
+
+int dcb_create(const dcb_config *cfg, dcb_env **out) {
+    if (!cfg || !out) return fail(DCB_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != DCB_ABI_VERSION)
+        return fail(DCB_ERR_INVALID_ARG, "abi_version %d != %d", cfg->abi_version, DCB_ABI_VERSION);
+    const int K = cfg->num_envs, N = cfg->n_ue, M = cfg->n_bs;
+    if (K < 1 || N < 1 || M < 1) return fail(DCB_ERR_INVALID_ARG, "num_envs, n_ue, n_bs must be >= 1");
+    if (M > 64) return fail(DCB_ERR_UNSUPPORTED, "n_bs = %d > 64 (connection mask is one 64-bit word per UE)", M);
+    if (N > 1024) return fail(DCB_ERR_UNSUPPORTED, "n_ue = %d > 1024 (one thread per UE, one CTA per env)", N);
+    if (cfg->kind != DCB_KIND_CENTRAL && cfg->kind != DCB_KIND_MULTI) return fail(DCB_ERR_INVALID_ARG, "bad kind");
+    if (cfg->reward < DCB_REWARD_AVG || cfg->reward > DCB_REWARD_MIN)
+        return fail(DCB_ERR_INVALID_ARG, "bad reward aggregation %d", cfg->reward);   // central.py:73, multi_agent.py:92
+    if (cfg->map_width < 1 || cfg->map_height < 1 || cfg->map_width >= 16384 || cfg->map_height >= 16384)
+        return fail(DCB_ERR_UNSUPPORTED, "map %dx%d outside [1, 16383]", cfg->map_width, cfg->map_height);
+    if (cfg->border_buffer <= 0)   // movement.py:103
+        return fail(DCB_ERR_INVALID_ARG, "border_buffer must be > 0");
+    if (cfg->map_width - cfg->border_buffer < cfg->border_buffer ||
+        cfg->map_height - cfg->border_buffer < cfg->border_buffer)
+        return fail(DCB_ERR_INVALID_ARG, "map smaller than twice the border buffer");
+    if (cfg->pause_duration < 0 || cfg->pause_duration > 126)
+        return fail(DCB_ERR_UNSUPPORTED, "pause_duration outside [0, 126]");
+    if (cfg->episode_length < 1) return fail(DCB_ERR_INVALID_ARG, "episode_length must be >= 1");
+    if (cfg->auto_reset && cfg->rand_episodes)
+        return fail(DCB_ERR_UNSUPPORTED, "auto_reset replays the seeded episode; it cannot be combined with rand_episodes");
+    if (!cfg->host_bs_xy || !cfg->host_sharing || !cfg->host_velocity || !cfg->host_init_xy || !cfg->host_seeds)
+        return fail(DCB_ERR_INVALID_ARG, "null host array in config");
+    bool has_maxcap = false, has_pf = false;
+    for (int b = 0; b < M; b++) {
+        const int s = cfg->host_sharing[b];
+        if (s < 0 || s > 3) return fail(DCB_ERR_INVALID_ARG, "sharing[%d] = %d not supported", b, s);   // station.py:21
+        has_maxcap |= s == DCB_SHARE_MAX_CAP;
+        has_pf |= s == DCB_SHARE_PROPORTIONAL_FAIR;
+    }
+    for (int i = 0; i < N; i++) {
+        const double v = cfg->host_velocity[i];
+        if (!(v >= 0.0 || v == DCB_VELOCITY_SLOW || v == DCB_VELOCITY_FAST))
+            return fail(DCB_ERR_INVALID_ARG, "velocity[%d] = %g", i, v);
+    }
+
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(DCB_ERR_INVALID_ARG, "device %d of %d", cfg->device, ndev);
+    DeviceGuard guard(cfg->device);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+
+    dcb_env *env = new (std::nothrow) dcb_env();
+    if (!env) return fail(DCB_ERR_INVALID_ARG, "out of host memory");
+    env->cfg = *cfg;
+    env->cfg.host_bs_xy = nullptr; env->cfg.host_sharing = nullptr; env->cfg.host_velocity = nullptr;
+    env->cfg.host_init_xy = nullptr; env->cfg.host_seeds = nullptr;
+    env->device = cfg->device;
+
+    const size_t smem_cap = prop.sharedMemPerBlockOptin;
+    if (dcb_step_smem_bytes(cfg->kind, N, M, 1) > smem_cap) {
+        delete env;
+        return fail(DCB_ERR_UNSUPPORTED, "one env of %d UEs x %d BS needs %zu B of shared memory (> %zu)", N, M,
+                    dcb_step_smem_bytes(cfg->kind, N, M, 1), smem_cap);
+    }
+    const int E = choose_envs_per_cta(K, N, M, cfg->kind, prop.multiProcessorCount, smem_cap);
+    if (E * N > 1024 || dcb_step_smem_bytes(cfg->kind, N, M, E) > smem_cap) {
+        delete env;
+        return fail(DCB_ERR_INVALID_ARG, "DCB_ENVS_PER_CTA = %d does not fit", E);
+    }
+    env->threads = (E * N + 31) / 32 * 32;
+    env->grid = (K + E - 1) / E;
+    env->smem = dcb_step_smem_bytes(cfg->kind, N, M, E);
+    int S = 1;
+    while (S * 2 <= 32 && E * M * S * 2 <= env->threads) S *= 2;
+
+    const size_t KN = (size_t)K * N;
+    // pause_duration + 1 steps is the shortest possible redraw cycle (movement.py:168-181); +2 = entry 0 and slack
+    const int D = cfg->episode_length / (cfg->pause_duration + 1) + 3;
+
+#define ALLOC(ptr, count)                                                           \
+    do {                                                                            \
+        cudaError_t e_ = cudaMalloc((void **)&(ptr), sizeof(*(ptr)) * (count));     \
+        if (e_ != cudaSuccess) {                                                    \
+            dcb_destroy(env);                                                       \
+            return fail(DCB_ERR_CUDA, "cudaMalloc(%s): %s", #ptr, cudaGetErrorString(e_)); \
+        }                                                                           \
+    } while (0)
+    ALLOC(env->d_bs_xy, 2 * M); ALLOC(env->d_sharing, M); ALLOC(env->d_vel, N); ALLOC(env->d_init_xy, 2 * N);
+    ALLOC(env->d_seeds, K); ALLOC(env->d_pos, KN); ALLOC(env->d_init_pos, KN); ALLOC(env->d_mv, KN);
+    ALLOC(env->d_mask, KN); ALLOC(env->d_ewma, KN); ALLOC(env->d_time, K); ALLOC(env->d_err, 1);
+    ALLOC(env->d_table, KN * D);
+    if (cfg->rand_episodes) { ALLOC(env->d_pos_skip, K); ALLOC(env->d_mv_skip, KN); }
+#undef ALLOC
+    CU(cudaMemcpy(env->d_bs_xy, cfg->host_bs_xy, sizeof(double) * 2 * M, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(env->d_sharing, cfg->host_sharing, sizeof(int) * M, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(env->d_vel, cfg->host_velocity, sizeof(double) * N, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(env->d_init_xy, cfg->host_init_xy, sizeof(double) * 2 * N, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(env->d_seeds, cfg->host_seeds, sizeof(long long) * K, cudaMemcpyHostToDevice));
+    CU(cudaMemset(env->d_err, 0, sizeof(int)));
+    if (cfg->rand_episodes) {
+        CU(cudaMemset(env->d_pos_skip, 0, sizeof(uint32_t) * K));
+        CU(cudaMemset(env->d_mv_skip, 0, sizeof(uint32_t) * KN));
+    }
+
+    DevParams &p = env->p;
+    memset(&p, 0, sizeof(p));
+    p.K = K; p.N = N; p.M = M; p.kind = cfg->kind; p.reward = cfg->reward;
+    p.episode_length = cfg->episode_length; p.auto_reset = cfg->auto_reset; p.pause_duration = cfg->pause_duration;
+    p.D = D; p.E = E; p.S = S;
+    p.has_maxcap = has_maxcap; p.has_propfair = has_pf;
+    // station.py:112-114 with the host libm, exactly as the reference evaluates them
+    const double ch = 0.8 + (1.1 * log10(2500.0) - 0.7) * 1.5 - 1.56 * log10(2500.0);
+    p.c1 = 69.55 + 26.16 * log10(2500.0) - 13.82 * log10(50.0) - ch;
+    p.c2 = 44.9 - 6.55 * log10(50.0);
+    p.thr_d2 = threshold_d2(p.c1, p.c2);
+    p.bs_xy = env->d_bs_xy; p.sharing = env->d_sharing; p.vel_spec = env->d_vel;
+    p.pos = env->d_pos; p.mv = env->d_mv; p.mask = env->d_mask; p.ewma = env->d_ewma; p.time = env->d_time;
+    p.init_pos = env->d_init_pos; p.table = env->d_table; p.err = env->d_err;
+
+    cudaError_t e = dcb_step_set_smem_limit(env->threads, env->smem);
+    if (e != cudaSuccess) {
+        dcb_destroy(env);
+        return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", env->smem, cudaGetErrorString(e));
+    }
+
+    // initial tables + state (as after the first reset)
+    GenArgs g;
+    g.K = K; g.N = N; g.D = D; g.W = cfg->map_width; g.H = cfg->map_height; g.border_buffer = cfg->border_buffer;
+    g.seeds = env->d_seeds; g.vel_spec = env->d_vel; g.init_xy = env->d_init_xy;
+    g.pos_skip = nullptr; g.mv_skip = nullptr; g.env_ids = nullptr; g.n_ids = 0;
+    g.init_pos = env->d_init_pos; g.table = env->d_table;
+    ResetArgs r;
+    r.K = K; r.N = N; r.D = D; r.env_ids = nullptr; r.n_ids = 0; r.init_pos = env->d_init_pos; r.table = env->d_table;
+    r.pos = env->d_pos; r.mv = env->d_mv; r.mask = env->d_mask; r.ewma = env->d_ewma; r.time = env->d_time;
+    r.pos_skip = nullptr;
+    e = dcb_launch_generate(g, 0);
+    if (e == cudaSuccess) e = dcb_launch_reset(r, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        dcb_destroy(env);
+        return fail(DCB_ERR_CUDA, "table generation: %s", cudaGetErrorString(e));
+    }
+    env->launches += 2;
+    *out = env;
+    return DCB_OK;
+}
+
+int dcb_reset(dcb_env *env, const int32_t *host_env_ids, int32_t n, void *stream) {
+    if (!env) return fail(DCB_ERR_INVALID_ARG, "null handle");
+    DeviceGuard guard(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const DevParams &p = env->p;
+    const int32_t *d_ids = nullptr;
+    if (host_env_ids) {
+        if (n < 0) return fail(DCB_ERR_INVALID_ARG, "negative env count");
+        for (int j = 0; j < n; j++)
+            if (host_env_ids[j] < 0 || host_env_ids[j] >= p.K)
+                return fail(DCB_ERR_INVALID_ARG, "env id %d outside [0, %d)", host_env_ids[j], p.K);
+        if (n == 0) return DCB_OK;
+        if (n > env->env_ids_cap) {
+            cudaFree(env->d_env_ids);
+            env->d_env_ids = nullptr;
+            CU(cudaMalloc((void **)&env->d_env_ids, sizeof(int32_t) * n));
+            env->env_ids_cap = n;
+        }
+        CU(cudaMemcpyAsync(env->d_env_ids, host_env_ids, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+        d_ids = env->d_env_ids;
+    }
+    if (env->cfg.rand_episodes) {
+        // base.py:171-173: no re-seed -> continue every UE's stream where the last episode left it
+        CU(dcb_launch_advance_skip(p.K, p.N, d_ids, n, env->d_mv, env->d_mv_skip, env->d_pos_skip, s));
+        GenArgs g;
+        g.K = p.K; g.N = p.N; g.D = p.D; g.W = env->cfg.map_width; g.H = env->cfg.map_height;
+        g.border_buffer = env->cfg.border_buffer;
+        g.seeds = env->d_seeds; g.vel_spec = env->d_vel; g.init_xy = env->d_init_xy;
+        g.pos_skip = env->d_pos_skip; g.mv_skip = env->d_mv_skip; g.env_ids = d_ids; g.n_ids = n;
+        g.init_pos = env->d_init_pos; g.table = env->d_table;
+        CU(dcb_launch_generate(g, s));
+        env->launches += 2;
+    }
+    ResetArgs r;
+    r.K = p.K; r.N = p.N; r.D = p.D; r.env_ids = d_ids; r.n_ids = n; r.init_pos = env->d_init_pos;
+    r.table = env->d_table; r.pos = env->d_pos; r.mv = env->d_mv; r.mask = env->d_mask; r.ewma = env->d_ewma;
+    r.time = env->d_time; r.pos_skip = env->cfg.rand_episodes ? env->d_pos_skip : nullptr;
+    CU(dcb_launch_reset(r, s));
+    env->launches++;
+    if (host_env_ids) CU(cudaStreamSynchronize(s));   // the id list is reused by the next partial reset
+    return DCB_OK;
+}
+
+int dcb_observe(dcb_env *env, const dcb_outputs *out, void *stream) {
+    if (!env) return fail(DCB_ERR_INVALID_ARG, "null handle");
+    DeviceGuard guard(env->device);
+    return launch_step(env, nullptr, 0, out, (cudaStream_t)stream);
+}
+
+int dcb_step(dcb_env *env, const int32_t *d_actions, const dcb_outputs *out, void *stream) {
+    if (!env || !d_actions) return fail(DCB_ERR_INVALID_ARG, "null argument");
+    DeviceGuard guard(env->device);
+    return launch_step(env, d_actions, 1, out, (cudaStream_t)stream);
+}
+
+int dcb_step_many(dcb_env *env, const int32_t *d_actions, int32_t T, const dcb_outputs *out, void *stream) {
+    if (!env || !d_actions) return fail(DCB_ERR_INVALID_ARG, "null argument");
+    if (T < 1) return fail(DCB_ERR_INVALID_ARG, "T must be >= 1");
+    DeviceGuard guard(env->device);
+    return launch_step(env, d_actions, T, out, (cudaStream_t)stream);
+}
+
+int dcb_step_host(dcb_env *env, const int32_t *h_actions, float *h_obs, float *h_reward, uint8_t *h_lost_conn,
+                  void *stream) {
+    if (!env || !h_actions) return fail(DCB_ERR_INVALID_ARG, "null argument");
+    DeviceGuard guard(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const DevParams &p = env->p;
+    const size_t KN = (size_t)p.K * p.N;
+    const size_t n_obs = (size_t)p.K * dcb_obs_size(env), n_rew = (size_t)p.K * dcb_reward_size(env);
+    if (!env->d_h_actions) {
+        CU(cudaMalloc((void **)&env->d_h_actions, sizeof(int32_t) * KN));
+        CU(cudaMalloc((void **)&env->d_h_obs, sizeof(float) * n_obs));
+        CU(cudaMalloc((void **)&env->d_h_reward, sizeof(float) * n_rew));
+        CU(cudaMalloc((void **)&env->d_h_lost, KN));
+    }
+    CU(cudaMemcpyAsync(env->d_h_actions, h_actions, sizeof(int32_t) * KN, cudaMemcpyHostToDevice, s));
+    dcb_outputs o;
+    memset(&o, 0, sizeof(o));
+    o.obs = h_obs ? env->d_h_obs : nullptr;
+    o.reward = h_reward ? env->d_h_reward : nullptr;
+    o.lost_conn = h_lost_conn ? env->d_h_lost : nullptr;
+    const int rc = launch_step(env, env->d_h_actions, 1, &o, s);
+    if (rc != DCB_OK) return rc;
+    if (h_obs) CU(cudaMemcpyAsync(h_obs, env->d_h_obs, sizeof(float) * n_obs, cudaMemcpyDeviceToHost, s));
+    if (h_reward) CU(cudaMemcpyAsync(h_reward, env->d_h_reward, sizeof(float) * n_rew, cudaMemcpyDeviceToHost, s));
+    if (h_lost_conn) CU(cudaMemcpyAsync(h_lost_conn, env->d_h_lost, KN, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return DCB_OK;
+}
+
+int dcb_check_errors(dcb_env *env, void *stream) {
+    if (!env) return fail(DCB_ERR_INVALID_ARG, "null handle");
+    DeviceGuard guard(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int flags = 0;
+    CU(cudaMemcpyAsync(&flags, env->d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (flags) {
+        CU(cudaMemsetAsync(env->d_err, 0, sizeof(int), s));
+        if (flags & DCB_ERRBIT_ACTION)
+            return fail(DCB_ERR_ACTION_RANGE, "an action outside [0, %d] was passed to step (treated as no-op)", env->p.M);
+        return fail(DCB_ERR_TABLE_EXHAUSTED, "a UE ran out of pre-drawn waypoints (stepped past episode_length "
+                                             "without reset)");
+    }
+    return DCB_OK;
+}
+
+int dcb_get_state(dcb_env *env, dcb_state_host *st) {
+    if (!env || !st) return fail(DCB_ERR_INVALID_ARG, "null argument");
+    DeviceGuard guard(env->device);
+    const DevParams &p = env->p;
+    const size_t KN = (size_t)p.K * p.N;
+    CU(cudaDeviceSynchronize());
+    if (st->pos) CU(cudaMemcpy(st->pos, env->d_pos, sizeof(double2) * KN, cudaMemcpyDeviceToHost));
+    if (st->mask) CU(cudaMemcpy(st->mask, env->d_mask, sizeof(uint64_t) * KN, cudaMemcpyDeviceToHost));
+    if (st->ewma) CU(cudaMemcpy(st->ewma, env->d_ewma, sizeof(double) * KN, cudaMemcpyDeviceToHost));
+    if (st->time) CU(cudaMemcpy(st->time, env->d_time, sizeof(int) * p.K, cudaMemcpyDeviceToHost));
+    if (st->movement) {
+        std::vector<uint2> mv(KN);
+        std::vector<double> vel(p.N);
+        CU(cudaMemcpy(mv.data(), env->d_mv, sizeof(uint2) * KN, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(vel.data(), env->d_vel, sizeof(double) * p.N, cudaMemcpyDeviceToHost));
+        for (size_t u = 0; u < KN; u++) {
+            const double vf = vel[u % p.N];
+            double *m = st->movement + 5 * u;
+            m[0] = vf >= 0.0 ? vf : (double)(mv[u].y & 0xffu);
+            m[1] = (double)(mv[u].x & 0xffffu);
+            m[2] = (double)(mv[u].x >> 16);
+            m[3] = (double)((mv[u].y >> 15) & 1u);
+            m[4] = (double)((mv[u].y >> 8) & 0x7fu);
+        }
+    }
+    return DCB_OK;
+}
+
+int dcb_set_state(dcb_env *env, const dcb_state_host *st) {
+    if (!env || !st) return fail(DCB_ERR_INVALID_ARG, "null argument");
+    DeviceGuard guard(env->device);
+    const DevParams &p = env->p;
+    const size_t KN = (size_t)p.K * p.N;
+    CU(cudaDeviceSynchronize());
+    if (st->pos) CU(cudaMemcpy(env->d_pos, st->pos, sizeof(double2) * KN, cudaMemcpyHostToDevice));
+    if (st->mask) CU(cudaMemcpy(env->d_mask, st->mask, sizeof(uint64_t) * KN, cudaMemcpyHostToDevice));
+    if (st->ewma) CU(cudaMemcpy(env->d_ewma, st->ewma, sizeof(double) * KN, cudaMemcpyHostToDevice));
+    if (st->time) CU(cudaMemcpy(env->d_time, st->time, sizeof(int) * p.K, cudaMemcpyHostToDevice));
+    if (st->movement) {
+        // velocity / waypoint / pause state are injected; the table cursor (tidx) is kept
+        std::vector<uint2> mv(KN);
+        CU(cudaMemcpy(mv.data(), env->d_mv, sizeof(uint2) * KN, cudaMemcpyDeviceToHost));
+        for (size_t u = 0; u < KN; u++) {
+            const double *m = st->movement + 5 * u;
+            const unsigned wx = (unsigned)m[1], wy = (unsigned)m[2];
+            if (wx >= 16384u || wy >= 16384u) return fail(DCB_ERR_INVALID_ARG, "waypoint outside the map");
+            const unsigned v = (unsigned)m[0] & 0xffu;
+            const unsigned pause = ((m[3] != 0.0) ? 0x80u : 0u) | ((unsigned)m[4] & 0x7fu);
+            mv[u].x = wx | (wy << 16);
+            mv[u].y = v | (pause << 8) | (mv[u].y & 0xffff0000u);
+        }
+        CU(cudaMemcpy(env->d_mv, mv.data(), sizeof(uint2) * KN, cudaMemcpyHostToDevice));
+    }
+    return DCB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+// Internal declarations shared by the CUDA translation units of libdeepcomp_b200.so (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/deepcomp_b200.h"
+
+// Radio model constants: deepcomp/env/entities/station.py:10,26-30; deepcomp/util/constants.py:28,40-41
+#define DCB_EPSILON 1e-16
+#define DCB_BW 9e6
+#define DCB_NOISE 1e-9
+#define DCB_TX_POWER 30.0
+#define DCB_SNR_THRESHOLD 2e-8
+#define DCB_MIN_UTILITY (-20.0)
+#define DCB_MAX_UTILITY 20.0
+
+// Sticky device-side error bits (DevParams::err)
+#define DCB_ERRBIT_ACTION 1
+#define DCB_ERRBIT_TABLE 2
+
+// Packed per-UE movement state (8 bytes):  x = wx | wy << 16,  y = vel | pause << 8 | tidx << 16
+//   wx, wy : current waypoint (integers, movement.py:126-127)
+//   vel    : drawn velocity 1..10 for 'slow'/'fast' UEs (movement.py:112-115); unused for fixed-velocity UEs
+//   pause  : bit 7 = RandomWaypoint.pausing, bits 0..6 = curr_pause (movement.py:101-102)
+//   tidx   : next unread entry of this UE's waypoint table
+// Packed waypoint-table entry (4 bytes): wx | wy << 14 | vel << 28
+
+struct DevParams {
+    int K, N, M, kind, reward;
+    int episode_length, auto_reset, pause_duration;
+    int D;               // waypoint-table depth per UE
+    int E;               // envs per CTA
+    int S;               // reducer lanes per (env, BS) pair, power of two <= 32
+    int has_maxcap, has_propfair;
+    double thr_d2;       // largest squared distance that is still in range (snr > 2e-8, station.py:224)
+    double c1, c2;       // Okumura-Hata constants (station.py:112-114)
+    const double *bs_xy; // [M][2]
+    const int *sharing;  // [M]
+    const double *vel_spec;  // [N]
+    // state slabs, flat UE index u = k*N + i
+    double2 *pos;        // [K*N]
+    uint2 *mv;           // [K*N]
+    unsigned long long *mask;  // [K*N]
+    double *ewma;        // [K*N]
+    int *time;           // [K]
+    const double2 *init_pos;   // [K*N] position drawn by reset_pos (user.py:98-109)
+    const uint32_t *table;     // [K*N][D] successive movement.reset() draws (movement.py:110-130)
+    int *err;
+};
+
+struct StepArgs {
+    DevParams p;
+    const int32_t *actions;  // [T][K][N]
+    int T;                   // 0 = observe only
+    dcb_outputs out;
+};
+
+struct GenArgs {
+    int K, N, D, W, H, border_buffer;
+    const long long *seeds;     // [K]
+    const double *vel_spec;     // [N]
+    const double *init_xy;      // [N][2]
+    const uint32_t *pos_skip;   // [K] reset_pos() calls already consumed per env (rand_episodes) or NULL
+    const uint32_t *mv_skip;    // [K*N] movement.reset() calls already consumed per UE or NULL
+    const int32_t *env_ids;     // [n_ids] or NULL = all envs
+    int n_ids;
+    double2 *init_pos;          // [K*N]
+    uint32_t *table;            // [K*N][D]
+};
+
+struct ResetArgs {
+    int K, N, D;
+    const int32_t *env_ids;
+    int n_ids;
+    const double2 *init_pos;
+    const uint32_t *table;
+    double2 *pos;
+    uint2 *mv;
+    unsigned long long *mask;
+    double *ewma;
+    int *time;
+    uint32_t *pos_skip;   // rand_episodes: bumped once per reset env, else NULL
+};
+
+cudaError_t dcb_launch_generate(const GenArgs &a, cudaStream_t s);
+cudaError_t dcb_launch_reset(const ResetArgs &a, cudaStream_t s);
+cudaError_t dcb_launch_advance_skip(int K, int N, const int32_t *env_ids, int n_ids, const uint2 *mv,
+                                    uint32_t *mv_skip, const uint32_t *pos_skip, cudaStream_t s);
+cudaError_t dcb_launch_step(const StepArgs &a, int threads, int grid, size_t smem, cudaStream_t s);
+cudaError_t dcb_step_set_smem_limit(int threads, size_t smem);
+size_t dcb_step_smem_bytes(int kind, int N, int M, int E);

@@ -1,0 +1,178 @@
+// Per-UE random draws of the reference, generated on the device.
+//
+// The reference gives every UE two `random.Random` generators seeded with the SAME value seed + 100*i
+// (deepcomp/env/single_ue/base.py:132-143, deepcomp/env/entities/user.py:94-96):
+//   User.rng       -> initial position: randint(0, W), randint(0, H)            (user.py:98-109)
+//   movement.rng   -> per movement.reset(): [velocity randint] , waypoint x, y   (util/movement.py:110-130)
+// Draw TIMES are data dependent (a redraw happens when a pause ends, movement.py:172-177) but the draw SEQUENCE
+// per UE is not, so the whole sequence is materialised once per reset as a table the step kernel consumes by
+// index.  CPython's generator is MT19937 seeded through init_by_array, randint is rejection sampling on the top
+// bits of one 32-bit output (Lib/random.py _randbelow_with_getrandbits) -- restated here.
+//
+// One thread per UE; the 624-word MT state lives in local memory (2.5 KB per thread, L1/L2 backed) -- this
+// kernel runs once per episode, it is not on the per-step path.
+#include "dcb_internal.h"
+
+namespace {
+
+struct MT {
+    uint32_t mt[624];
+    int idx;
+};
+
+__device__ void mt_seed(MT &g, long long seed) {
+    // random.seed(int): key = little-endian 32-bit words of abs(seed), at least one
+    unsigned long long a = seed < 0 ? (unsigned long long)(-(seed + 1)) + 1ull : (unsigned long long)seed;
+    uint32_t key[2] = {(uint32_t)(a & 0xffffffffu), (uint32_t)(a >> 32)};
+    const int len = key[1] ? 2 : 1;
+    g.mt[0] = 19650218u;
+    for (int i = 1; i < 624; i++) g.mt[i] = 1812433253u * (g.mt[i - 1] ^ (g.mt[i - 1] >> 30)) + (uint32_t)i;
+    int i = 1, j = 0;
+    for (int k = 624; k; k--) {
+        g.mt[i] = (g.mt[i] ^ ((g.mt[i - 1] ^ (g.mt[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+        i++; j++;
+        if (i >= 624) { g.mt[0] = g.mt[623]; i = 1; }
+        if (j >= len) j = 0;
+    }
+    for (int k = 623; k; k--) {
+        g.mt[i] = (g.mt[i] ^ ((g.mt[i - 1] ^ (g.mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+        i++;
+        if (i >= 624) { g.mt[0] = g.mt[623]; i = 1; }
+    }
+    g.mt[0] = 0x80000000u;
+    g.idx = 624;
+}
+
+__device__ uint32_t mt_next(MT &g) {
+    if (g.idx >= 624) {
+        uint32_t *mt = g.mt;
+        int kk;
+        for (kk = 0; kk < 624 - 397; kk++) {
+            uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+            mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        for (; kk < 623; kk++) {
+            uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+            mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        uint32_t y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+        mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        g.idx = 0;
+    }
+    uint32_t y = g.mt[g.idx++];
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+
+__device__ int mt_randint(MT &g, int a, int b) {
+    const uint32_t n = (uint32_t)(b - a + 1);
+    const int k = 32 - __clz(n);
+    uint32_t r = mt_next(g) >> (32 - k);
+    while (r >= n) r = mt_next(g) >> (32 - k);
+    return a + (int)r;
+}
+
+__global__ void __launch_bounds__(128) dcb_generate_kernel(GenArgs a) {
+    const long long n_env = a.env_ids ? a.n_ids : a.K;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_env * a.N) return;
+    const int slot = (int)(t / a.N);
+    const int i = (int)(t % a.N);
+    const int k = a.env_ids ? a.env_ids[slot] : slot;
+    const long long u = (long long)k * a.N + i;
+    const long long seed = a.seeds[k] + 100ll * (i + 1);
+
+    MT g;
+    // ---- User.rng: initial position (user.py:98-109); earlier episodes' draws are skipped (rand_episodes)
+    const double ix = a.init_xy[2 * i], iy = a.init_xy[2 * i + 1];
+    const bool rx = isnan(ix), ry = isnan(iy);
+    double px = ix, py = iy;
+    if (rx || ry) {
+        mt_seed(g, seed);
+        const uint32_t skip = a.pos_skip ? a.pos_skip[k] : 0u;
+        for (uint32_t e = 0; e <= skip; e++) {
+            if (rx) px = (double)mt_randint(g, 0, a.W);
+            if (ry) py = (double)mt_randint(g, 0, a.H);
+        }
+    }
+    a.init_pos[u] = make_double2(px, py);
+
+    // ---- movement.rng: successive movement.reset() draws (movement.py:110-130)
+    mt_seed(g, seed);
+    const double vs = a.vel_spec[i];
+    const uint32_t skip = a.mv_skip ? a.mv_skip[u] : 0u;
+    uint32_t *row = a.table + u * a.D;
+    for (uint32_t e = 0; e < skip + (uint32_t)a.D; e++) {
+        int v = 0;
+        if (vs == DCB_VELOCITY_SLOW) v = mt_randint(g, 1, 3);
+        else if (vs == DCB_VELOCITY_FAST) v = mt_randint(g, 5, 10);
+        const int wx = mt_randint(g, a.border_buffer, a.W - a.border_buffer);
+        const int wy = mt_randint(g, a.border_buffer, a.H - a.border_buffer);
+        if (e >= skip) row[e - skip] = (uint32_t)wx | ((uint32_t)wy << 14) | ((uint32_t)v << 28);
+    }
+}
+
+// MobileEnv.reset (base.py:169-189) -> User.reset (user.py:111-116) + Basestation.reset (station.py:106-108)
+__global__ void __launch_bounds__(256) dcb_reset_kernel(ResetArgs a) {
+    const long long n_env = a.env_ids ? a.n_ids : a.K;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_env * a.N) return;
+    const int slot = (int)(t / a.N);
+    const int i = (int)(t % a.N);
+    const int k = a.env_ids ? a.env_ids[slot] : slot;
+    const long long u = (long long)k * a.N + i;
+    a.pos[u] = a.init_pos[u];
+    const uint32_t e = a.table[u * a.D];
+    const uint32_t wx = e & 0x3fffu, wy = (e >> 14) & 0x3fffu, v = e >> 28;
+    a.mv[u] = make_uint2(wx | (wy << 16), v | (1u << 16));   // pausing = 0, curr_pause = 0, tidx = 1
+    a.mask[u] = 0ull;
+    a.ewma[u] = 0.0;
+    if (i == 0) {
+        a.time[k] = 0;
+        if (a.pos_skip) a.pos_skip[k] += 1u;
+    }
+}
+
+// rand_episodes (base.py:171-173: no re-seed on reset): before regenerating, remember how many movement.reset()
+// draws each UE has consumed so far (table base + tidx) so that the next generate call continues the stream.
+// pos_skip[k] counts the resets env k has completed (= reset_pos() draws consumed); it is bumped by the reset
+// kernel AFTER generation, so the reset that follows dcb_create replays the first draws.
+__global__ void __launch_bounds__(256) dcb_advance_skip_kernel(int K, int N, const int32_t *env_ids, int n_ids,
+                                                               const uint2 *mv, uint32_t *mv_skip,
+                                                               const uint32_t *pos_skip) {
+    const long long n_env = env_ids ? n_ids : K;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_env * N) return;
+    const int slot = (int)(t / N);
+    const int i = (int)(t % N);
+    const int k = env_ids ? env_ids[slot] : slot;
+    const long long u = (long long)k * N + i;
+    if (pos_skip[k] >= 1u) mv_skip[u] += mv[u].y >> 16;
+}
+
+}  // namespace
+
+cudaError_t dcb_launch_advance_skip(int K, int N, const int32_t *env_ids, int n_ids, const uint2 *mv,
+                                    uint32_t *mv_skip, const uint32_t *pos_skip, cudaStream_t s) {
+    const long long n = (long long)(env_ids ? n_ids : K) * N;
+    if (n == 0) return cudaSuccess;
+    dcb_advance_skip_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(K, N, env_ids, n_ids, mv, mv_skip, pos_skip);
+    return cudaGetLastError();
+}
+
+cudaError_t dcb_launch_generate(const GenArgs &a, cudaStream_t s) {
+    const long long n = (long long)(a.env_ids ? a.n_ids : a.K) * a.N;
+    if (n == 0) return cudaSuccess;
+    dcb_generate_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t dcb_launch_reset(const ResetArgs &a, cudaStream_t s) {
+    const long long n = (long long)(a.env_ids ? a.n_ids : a.K) * a.N;
+    if (n == 0) return cudaSuccess;
+    dcb_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
+    return cudaGetLastError();
+}

@@ -1,0 +1,174 @@
+/*
+ * deepcomp_b200 -- C ABI of the B200-native batched DeepCoMP environment step.
+ *
+ * This is the drop-in boundary for ONE path of CN-UPB/DeepCoMP: the mobile-cellular gym env step
+ * (deepcomp/env/single_ue/base.py:413-466 `MobileEnv.step`, with the observation / reward variants
+ * deepcomp/env/multi_ue/central.py:143-152 `CentralRelNormEnv` and deepcomp/env/multi_ue/multi_agent.py:6-107
+ * `MultiAgentMobileEnv`).  The reference is pure Python and has no FFI; the entry points below are what a
+ * ctypes binding inside the reference's env classes would call (INTEGRATION.md shows that binding).
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative dcb_status, never throws;
+ *     `dcb_last_error()` returns a thread-local message for the last failure.
+ *   - one handle == one CUDA device == K independent env instances; a handle is not thread-safe, distinct
+ *     handles are.
+ *   - the caller owns every buffer it passes (device pointers unless the name says `host`); the library owns only
+ *     its handle and the state slabs allocated in dcb_create.
+ *   - all device work is enqueued on the `stream` argument (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream) and is asynchronous unless stated otherwise.
+ *
+ * Batched data layout (K envs, N UEs per env, M base stations, row-major, innermost last):
+ *   actions     int32 [T][K][N]      0 = no-op, b+1 = toggle the link to BS b   (base.py:247-282, user.py:190-229)
+ *   obs central float [T][K][2NM+N]  connected[N][M] | dr[N][M] | utility[N]    (central.py:31-57,147-152)
+ *   obs multi   float [T][K][N][4M+1] connected[M] | dr[M] | ues_at_bs[M] | util_at_bs[M] | utility[1]
+ *                                    (variants.py:271-303; alphabetical key order = RLlib's Dict flattening)
+ *   reward      float central [T][K] (central.py:65-73) / multi [T][K][N] (multi_agent.py:39-95)
+ *   lost_conn   uint8 [T][K][N]      links dropped by movement this step (user.py:175-188; returned by
+ *                                    base.py:337-348 and discarded by the reference's step, base.py:447)
+ */
+#ifndef DEEPCOMP_B200_H
+#define DEEPCOMP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCB_ABI_VERSION 1
+
+typedef struct dcb_env dcb_env;
+
+typedef enum dcb_status {
+    DCB_OK = 0,
+    DCB_ERR_INVALID_ARG = -1,
+    DCB_ERR_UNSUPPORTED = -2,   /* shape outside what the kernels handle (see dcb_create) */
+    DCB_ERR_CUDA = -3,
+    DCB_ERR_ACTION_RANGE = -4,  /* an action outside [0, M] was seen on the device (base.py:238, central.py:61) */
+    DCB_ERR_TABLE_EXHAUSTED = -5 /* waypoint table ran dry: call dcb_reset or dcb_refill_waypoints */
+} dcb_status;
+
+/* deepcomp/util/env_setup.py:23-37: 'central' -> CentralRelNormEnv, 'multi' -> MultiAgentMobileEnv */
+typedef enum dcb_kind { DCB_KIND_CENTRAL = 0, DCB_KIND_MULTI = 1 } dcb_kind;
+/* env_config['reward'] (central.py:19, multi_agent.py:19) */
+typedef enum dcb_reward { DCB_REWARD_AVG = 0, DCB_REWARD_SUM = 1, DCB_REWARD_MIN = 2 } dcb_reward;
+/* Basestation.sharing_model (station.py:152-202) */
+typedef enum dcb_sharing {
+    DCB_SHARE_RESOURCE_FAIR = 0, DCB_SHARE_RATE_FAIR = 1, DCB_SHARE_PROPORTIONAL_FAIR = 2, DCB_SHARE_MAX_CAP = 3
+} dcb_sharing;
+
+/* Velocity spec of a UE's RandomWaypoint (movement.py:112-117): a number >= 0 is used as is */
+#define DCB_VELOCITY_SLOW (-1.0) /* rng.randint(1, 3)  */
+#define DCB_VELOCITY_FAST (-2.0) /* rng.randint(5, 10) */
+
+typedef struct dcb_config {
+    int32_t abi_version;     /* DCB_ABI_VERSION */
+    int32_t device;          /* CUDA device ordinal */
+    int32_t kind;            /* dcb_kind */
+    int32_t reward;          /* dcb_reward */
+    int32_t num_envs;        /* K */
+    int32_t n_ue;            /* N (fixed population: max_ues == num_ue, base.py:80-84) */
+    int32_t n_bs;            /* M, 1..64 */
+    int32_t map_width;       /* Map.width / Map.height are ints (map.py:20-21), < 16384 */
+    int32_t map_height;
+    int32_t episode_length;  /* env_config['episode_length']; sizes the waypoint table */
+    int32_t rand_episodes;   /* env_config['rand_episodes'] (base.py:171-173): 0 = re-seed on every reset */
+    int32_t auto_reset;      /* 1: an env whose time reached episode_length resets before its next step */
+    int32_t pause_duration;  /* RandomWaypoint(pause_duration=2) movement.py:87 */
+    int32_t border_buffer;   /* RandomWaypoint(border_buffer=10) movement.py:87 */
+    const double *host_bs_xy;     /* [M][2] BS positions (Basestation.pos) */
+    const int32_t *host_sharing;  /* [M] dcb_sharing per BS (env_setup.py:40-49) */
+    const double *host_velocity;  /* [N] DCB_VELOCITY_SLOW / _FAST / fixed number (env_setup.py:145-161) */
+    const double *host_init_xy;   /* [N][2] initial position, NaN = 'random' (user.py:98-109) */
+    const int64_t *host_seeds;    /* [K] env seeds; UE i (1-based) draws from random.Random(seed + 100*i) for both
+                                     its position RNG and its movement RNG (base.py:132-143, user.py:94-96) */
+} dcb_config;
+
+/*
+ * Output buffers of one dcb_step / dcb_step_many / dcb_observe call.  Every pointer is a device pointer and may
+ * be NULL (= not wanted).  For dcb_step_many the `*_stride` fields give the distance in ELEMENTS between
+ * consecutive steps (0 = every step overwrites the same buffer, i.e. only the last step survives).
+ */
+typedef struct dcb_outputs {
+    float *obs;
+    float *reward;
+    uint8_t *lost_conn;
+    float *curr_dr;      /* [K][N] info()['vector_metrics']['dr']      (base.py:407) */
+    float *utility;      /* [K][N] info()['vector_metrics']['utility'] (base.py:408) */
+    float *sum_utility;  /* [K]    info()['scalar_metrics']['sum_utility'] (base.py:402) */
+    int64_t obs_stride, reward_stride, lost_conn_stride, curr_dr_stride, utility_stride, sum_utility_stride;
+    /* fp64 taps for parity tests (same layouts as above, double precision, last step only) */
+    double *dbg_obs;
+    double *dbg_reward;
+    double *dbg_snr;         /* [K][N][M] SNR at the post-move positions (station.py:122-127) */
+    double *dbg_link_rate;   /* [K][N][M] cached ue.bs_dr values, 0 where not connected (user.py:143-146) */
+    double *dbg_curr_dr;     /* [K][N] */
+    double *dbg_utility;     /* [K][N] */
+    double *dbg_sum_utility; /* [K] */
+} dcb_outputs;
+
+/* Host-side snapshot of the env state, for tests and checkpointing.  NULL members are skipped. */
+typedef struct dcb_state_host {
+    double *pos;        /* [K][N][2] */
+    uint64_t *mask;     /* [K][N] bit b = connected to BS b */
+    double *ewma;       /* [K][N] User.ewma_dr (user.py:148-157) */
+    double *movement;   /* [K][N][5] velocity, waypoint x, waypoint y, pausing, curr_pause (movement.py:96-104) */
+    int32_t *time;      /* [K] MobileEnv.time */
+} dcb_state_host;
+
+int dcb_abi_version(void);
+const char *dcb_last_error(void);
+
+/*
+ * Allocate the state slabs for K envs on cfg->device and generate the per-UE RNG tables.  Supported shapes:
+ * 1 <= M <= 64, N * max(16*M, 4*(4*M+1)) bytes of shared memory per env must fit one CTA (N*M <= ~13000),
+ * N <= 1024.  Synchronous.
+ */
+int dcb_create(const dcb_config *cfg, dcb_env **out);
+void dcb_destroy(dcb_env *env);
+
+/*
+ * MobileEnv.reset (base.py:169-189) for all envs (env_ids == NULL) or for the n envs listed in the HOST array
+ * env_ids.  Re-seeds when rand_episodes == 0.  Follow with dcb_observe to get the first observation.
+ */
+int dcb_reset(dcb_env *env, const int32_t *host_env_ids, int32_t n, void *stream);
+
+/* get_obs() of the current state (central.py:31-57 / multi_agent.py:32-37) without stepping; reward is not written */
+int dcb_observe(dcb_env *env, const dcb_outputs *out, void *stream);
+
+/* MobileEnv.step (base.py:413-466) for all K envs: d_actions int32 [K][N] on the device */
+int dcb_step(dcb_env *env, const int32_t *d_actions, const dcb_outputs *out, void *stream);
+
+/* T consecutive steps in ONE launch (state stays on chip between steps): d_actions int32 [T][K][N] */
+int dcb_step_many(dcb_env *env, const int32_t *d_actions, int32_t T, const dcb_outputs *out, void *stream);
+
+/*
+ * Convenience for host callers (the e2e path of bench.py and the K=1 gym facades): copies `h_actions` [K][N] to the
+ * device, steps, copies obs / reward / lost_conn back into the host buffers and synchronises the stream.  Host
+ * buffers should be pinned for full PCIe bandwidth; NULL outputs are skipped.
+ */
+int dcb_step_host(dcb_env *env, const int32_t *h_actions, float *h_obs, float *h_reward, uint8_t *h_lost_conn,
+                  void *stream);
+
+/* Sticky device-side error flags (action range, table exhaustion) since the last call; synchronises the stream. */
+int dcb_check_errors(dcb_env *env, void *stream);
+
+/* State snapshot / injection (synchronous). */
+int dcb_get_state(dcb_env *env, dcb_state_host *state);
+int dcb_set_state(dcb_env *env, const dcb_state_host *state);
+
+/* Shape helpers */
+int64_t dcb_obs_size(const dcb_env *env);     /* floats per env: 2NM+N (central) or N*(4M+1) (multi) */
+int64_t dcb_reward_size(const dcb_env *env);  /* floats per env: 1 (central) or N (multi) */
+/* Algorithmic HBM bytes of one env-step as defined in SURVEY.md section 8(d) (the roofline numerator) */
+int64_t dcb_algorithmic_bytes_per_env_step(const dcb_env *env);
+/* Kernel launches issued through this handle so far (bench.py's gpu_launches) */
+int64_t dcb_launch_count(const dcb_env *env);
+/* Launch geometry chosen for the step kernel: envs per CTA, threads per CTA, dynamic smem bytes, grid size */
+int dcb_launch_geometry(const dcb_env *env, int32_t *envs_per_cta, int32_t *threads, int32_t *smem_bytes,
+                        int32_t *grid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPCOMP_B200_H */
