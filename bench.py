@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the batched DeepCoMP env step on N B200s (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 1000 --warmup 100
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps K --warmup W      # the reference algorithm on the host cores
+
+A "step" is one batched env step: every one of the K envs of the workload advances by one MobileEnv.step.  The
+workload at N GPUs is BASELINE.json configs[1] per GPU (50 UE x 10 BS x 1024 envs, MultiAgentMobileEnv, mixed
+sharing, all-'slow' RandomWaypoint UEs, episode_length 100, reset every 100 steps) -- weak scaling, 8 GPUs = the
+north-star (50, 10, 8192) batch.  Steps are issued as rollout fragments of `--fragment` steps per launch
+(dcb_step_many), actions pre-generated on the device.
+
+One JSON line on stdout (rank 0).  Nothing here reads /root/reference; the CPU baseline / reference arm run the
+oracle port (oracle/deepcomp_oracle.py: the reference's algorithm restated, bit-identical to it on the golden traces).
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "env steps/sec (batched)"
+UNIT = "env-steps/s"
+
+
+def grid_layout(n_bs, pitch=100, border=10):
+    """Synthetic BS layout: square grid, 100 m pitch (cli.py:41), 10 m border."""
+    cols = int(np.ceil(np.sqrt(n_bs)))
+    rows = int(np.ceil(n_bs / cols))
+    width = max(pitch * (cols - 1) + 2 * border, 120)
+    height = max(pitch * (rows - 1) + 2 * border, 120)
+    return width, height, [(border + pitch * (b % cols), border + pitch * (b // cols)) for b in range(n_bs)]
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": f"{args.n_ue} UE x {args.n_bs} BS x {args.envs} envs/GPU ({args.envs * n_gpus} total), "
+                    f"{'MultiAgentMobileEnv' if args.kind == 'multi' else 'CentralRelNormEnv'}, {args.sharing} "
+                    f"sharing, slow RandomWaypoint, episode_length {args.episode_length}, reset every episode",
+        "kind": args.kind, "n_ue": args.n_ue, "n_bs": args.n_bs, "envs_per_gpu": args.envs,
+        "episode_length": args.episode_length, "fragment_steps": args.fragment, "base_seed": args.seed,
+        "actions": "uniform int in [0, M], torch.Generator(seed=0), pre-generated on device",
+    }
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def _cpu_worker(idx, n_workers, args_d, steps, warmup, barrier, q):
+    """One host process stepping its own env with the oracle port (reference algorithm)."""
+    from oracle.deepcomp_oracle import OracleEnv
+    W, H, bs = grid_layout(args_d['n_bs'])
+    env = OracleEnv(args_d['kind'], args_d['n_ue'], bs, (W, H), sharing=args_d['sharing'], velocities='slow',
+                    seed=args_d['seed'] + idx * 100 * (args_d['n_ue'] + 1), reward='avg',
+                    episode_length=args_d['episode_length'])
+    rng = np.random.default_rng(idx)
+    L = args_d['episode_length']
+    env.reset()
+    t_env = 0
+    for _ in range(warmup):
+        if t_env == L:
+            env.reset(); t_env = 0
+        env.step(rng.integers(0, args_d['n_bs'] + 1, args_d['n_ue'])); t_env += 1
+    barrier.wait()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        if t_env == L:
+            env.reset(); t_env = 0
+        env.step(rng.integers(0, args_d['n_bs'] + 1, args_d['n_ue'])); t_env += 1
+    t1 = time.perf_counter()
+    q.put((idx, t1 - t0))
+
+
+def run_cpu_port(args, steps, warmup, cores=None):
+    """P processes (P = host cores), each its own env; returns (env-steps/s aggregate, cores, seconds)."""
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context('fork')
+    barrier = ctx.Barrier(cores)
+    q = ctx.Queue()
+    args_d = dict(kind=args.kind, n_ue=args.n_ue, n_bs=args.n_bs, sharing=args.sharing, seed=args.seed,
+                  episode_length=args.episode_length)
+    procs = [ctx.Process(target=_cpu_worker, args=(i, cores, args_d, steps, warmup, barrier, q)) for i in range(cores)]
+    for p in procs:
+        p.start()
+    times = [q.get()[1] for _ in procs]
+    for p in procs:
+        p.join()
+    elapsed = max(times)
+    return cores * steps / elapsed, cores, elapsed
+
+
+def run_c_oracle(args, cores):
+    """Native C restatement (oracle/dcb_oracle.c, OpenMP): a much stronger CPU baseline than the reference's Python."""
+    try:
+        from oracle import c_oracle as co
+        W, H, bs = grid_layout(args.n_bs)
+        K = max(cores * 8, 8)
+        envs = [co.COracleEnv(args.kind, args.n_ue, bs, (W, H), sharing=args.sharing, velocities='slow',
+                              seed=args.seed + k * 100 * (args.n_ue + 1)) for k in range(K)]
+        for e in envs:
+            e.L.orc_reset(e.h)
+        rng = np.random.default_rng(0)
+        T = 100
+        acts = rng.integers(0, args.n_bs + 1, (T, K, args.n_ue)).astype(np.int32)
+        best = 0.0
+        for nt in sorted({1, cores}):
+            co.batch_run(envs, acts[:10], nthreads=nt)
+            t0 = time.perf_counter()
+            co.batch_run(envs, acts, nthreads=nt)
+            best = max(best, T * K / (time.perf_counter() - t0))
+        return {"value": best, "unit": UNIT, "cores": cores, "kind": "port-native-C",
+                "sample": f"{K} envs x {T} steps, OpenMP"}
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": str(exc)[:200]}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # each step = every worker's env advancing once: bounded sample of the workload (one env per host core)
+    value, cores, elapsed = run_cpu_port(args, args.steps, min(args.warmup, 20), cores)
+    sample = (f"{cores} envs (one per host core) x {args.steps} steps of the same (N_UE={args.n_ue}, M_BS={args.n_bs}) "
+              f"workload, oracle port of the reference's Python env")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                       '-lms', '20', '-i', str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def wait_started(self, timeout=5.0):
+        """Block until nvidia-smi has written its first sample (its start-up is longer than a short timed region)."""
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < timeout:
+            if os.path.getsize(self.f.name) > 0:
+                return
+            time.sleep(0.02)
+
+    def mark(self):
+        """Current size of the sample file: samples written after this offset were taken after this call."""
+        return os.path.getsize(self.f.name) if self.p is not None else 0
+
+    def stop(self, start=0, end=None):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.05)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        data = self.f.read()
+        window = data[start:end] if end is not None and end > start else data[start:]
+        if not window.strip():
+            window = data          # region shorter than one sampling period: fall back to the whole loaded run
+            out["window"] = "whole run (timed region shorter than the 20 ms sampling period)"
+        else:
+            out["window"] = "timed region"
+        sm, mx, reasons = [], [], set()
+        for ln in window.splitlines():
+            c = [x.strip() for x in ln.split(',')]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def measured_peak_hbm():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from deepcomp_b200 import BatchedMobileEnv
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    # CPU baseline first (forks worker processes: do it before this process owns a CUDA context)
+    cpu_baseline = None
+    extra_native = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v, cores, secs = run_cpu_port(args, args.cpu_steps, 5, cores)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{cores} envs (one per core) x {args.cpu_steps} steps of the same (N_UE, M_BS) "
+                                  f"workload, Python oracle port of the reference env ({secs:.1f} s)"}
+        extra_native = run_c_oracle(args, cores)
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            sys.exit(f"--gpus {args.gpus} needs torchrun with --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    K, N, M, L, F = args.envs, args.n_ue, args.n_bs, args.episode_length, args.fragment
+    W, H, bs = grid_layout(M)
+    env = BatchedMobileEnv(num_envs=K, n_ue=N, bs_xy=bs, map_wh=(W, H), kind=args.kind, sharing=args.sharing,
+                           velocities='slow', seed=args.seed, reward='avg', episode_length=L, device=dev,
+                           first_env=rank * K)
+    total = args.warmup + args.steps
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0 + rank)
+    actions = torch.randint(0, M + 1, (total, K, N), generator=gen, device=dev, dtype=torch.int32)
+
+    # one fragment plan for warm-up + timed steps: (first step, n steps, reset before?)
+    def plan(first, count, t_env):
+        out = []
+        s = first
+        while s < first + count:
+            reset = t_env == L
+            if reset:
+                t_env = 0
+            n = min(F, L - t_env, first + count - s)
+            out.append((s, n, reset))
+            s += n
+            t_env += n
+        return out, t_env
+
+    env.reset()
+    bufs = {}
+
+    def run(fragments, events=None):
+        for (s, n, reset) in fragments:
+            if reset:
+                env.reset()          # MobileEnv.reset incl. the first observation, as the reference loop does
+            if events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            env.step_many(actions[s:s + n], out=bufs[n])
+            if events is not None:
+                e1.record()
+                events.append((e0, e1, n))
+
+    warm, t_env = plan(0, args.warmup, 0)
+    timed, _ = plan(args.warmup, args.steps, t_env)
+    # allocate the per-fragment output buffers outside the timed region (one dry fragment per distinct length)
+    for n in sorted({n for _, n, _ in warm + timed}):
+        bufs[n] = env.step_many(actions[0:n], obs=True, info=False)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.wait_started()
+    env.reset()
+    run(warm)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    launches0 = env.launch_count
+    mark0 = sampler.mark() if sampler else 0
+    events = []
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    t_start.record()
+    run(timed, events)
+    t_end.record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop(mark0, sampler.mark()) if sampler else None
+    launches = env.launch_count - launches0
+    env.check_errors()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    kern_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in events)
+    kern_steps = sum(n for _, _, n in events)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = world * K * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (dcb_step_kernel): algorithmic bytes / launch duration, this rank
+    peak, peak_src = measured_peak_hbm()
+    bytes_per_env_step = env.algorithmic_bytes_per_env_step
+    achieved = (bytes_per_env_step * K * kern_steps) / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "dcb_step_kernel",
+                "algorithmic_bytes_per_env_step": bytes_per_env_step,
+                "kernel_share_of_step": kern_ms / elapsed_ms if elapsed_ms > 0 else None,
+                "avg_launch_ms": kern_ms / max(len(events), 1), "env_steps_per_launch": K * F}
+    tr = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tr):
+        try:
+            with open(tr) as f:
+                roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ---- e2e: host actions -> H2D -> step -> D2H obs/reward/lost_conn, every step, through dcb_step_host
+    e2e_steps = min(args.steps, args.e2e_steps)
+    pb = env.pinned_buffers()
+    host_actions = actions[:e2e_steps].cpu().numpy()
+    env.reset()
+    for s in range(min(5, e2e_steps)):
+        env.step_host(host_actions[s])
+    env.reset()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        if s > 0 and s % L == 0:
+            env.reset()
+        np.copyto(pb['actions'].numpy(), host_actions[s])
+        env.step_host(None)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": world * K * e2e_steps / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": int(pb['actions'].numel() * 4),
+           "d2h_bytes_per_step": int(pb['obs'].numel() * 4 + pb['reward'].numel() * 4 + pb['lost_conn'].numel()),
+           "steps": e2e_steps, "api": "BatchedMobileEnv.step_host -> dcb_step_host (pinned host buffers)"}
+    env.check_errors()
+
+    # ---- rollout hand-off (not in the timed region): NCCL all-gather of one fragment's rewards + obs slab
+    gather = None
+    if world > 1:
+        frag = bufs[max(bufs)]
+        obs = frag['obs']
+        part = obs[: max(1, min(obs.shape[0], 8))].contiguous()
+        out = torch.empty((world,) + tuple(part.shape), dtype=part.dtype, device=dev)
+        dist.all_gather_into_tensor(out, part)
+        torch.cuda.synchronize(dev)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        g0.record()
+        dist.all_gather_into_tensor(out, part)
+        g1.record()
+        torch.cuda.synchronize(dev)
+        gms = torch.tensor([g0.elapsed_time(g1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        gather = {"collective": "nccl all_gather_into_tensor", "bytes_per_rank": int(part.numel() * 4),
+                  "ms": float(gms.item()),
+                  "GBps_per_rank_in": float((world - 1) * part.numel() * 4 / (gms.item() * 1e-3) / 1e9)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cfg = workload_config(args, world)
+    cfg["l2"] = (f"no flush needed: each fragment streams {bufs[max(bufs)]['obs'].numel() * 4 / 1e6:.0f} MB of "
+                 f"observations + {F * K * N * 4 / 1e6:.0f} MB of actions through a 126 MB L2")
+    cfg["launch_geometry"] = env.launch_geometry
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if extra_native is not None:
+        line["cpu_native_port"] = extra_native
+    if gather is not None:
+        line["rollout_gather"] = gather
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5000)
+    ap.add_argument('--warmup', type=int, default=200)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--n-ue', type=int, default=50)
+    ap.add_argument('--n-bs', type=int, default=10)
+    ap.add_argument('--envs', type=int, default=1024, help='envs per GPU (weak scaling)')
+    ap.add_argument('--kind', default='multi', choices=['multi', 'central'])
+    ap.add_argument('--sharing', default='mixed')
+    ap.add_argument('--episode-length', type=int, default=100)
+    ap.add_argument('--fragment', type=int, default=100, help='steps per launch (rollout fragment)')
+    ap.add_argument('--seed', type=int, default=1000)
+    ap.add_argument('--e2e-steps', type=int, default=200)
+    ap.add_argument('--cpu-steps', type=int, default=300, help='steps per core for the cpu_baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == 'reference':
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == '__main__':
+    main()

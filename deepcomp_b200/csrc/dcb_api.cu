@@ -293,6 +293,8 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     p.c1 = 69.55 + 26.16 * log10(2500.0) - 13.82 * log10(50.0) - ch;
     p.c2 = 44.9 - 6.55 * log10(50.0);
     p.thr_d2 = threshold_d2(p.c1, p.c2);
+    p.snr_c0 = log2(10.0) * (DCB_TX_POWER - p.c1) / 10.0 - log2(DCB_NOISE);
+    p.snr_h = p.c2 / 20.0;
     p.bs_xy = env->d_bs_xy; p.sharing = env->d_sharing; p.vel_spec = env->d_vel;
     p.pos = env->d_pos; p.mv = env->d_mv; p.mask = env->d_mask; p.ewma = env->d_ewma; p.time = env->d_time;
     p.init_pos = env->d_init_pos; p.table = env->d_table; p.err = env->d_err;

@@ -35,6 +35,7 @@ struct DevParams {
     int has_maxcap, has_propfair;
     double thr_d2;       // largest squared distance that is still in range (snr > 2e-8, station.py:224)
     double c1, c2;       // Okumura-Hata constants (station.py:112-114)
+    double snr_c0, snr_h; // snr(d) = 2^(snr_c0 - snr_h * log2(d^2)): the same model folded for the fast path
     const double *bs_xy; // [M][2]
     const int *sharing;  // [M]
     const double *vel_spec;  // [N]

@@ -1,0 +1,87 @@
+// fp64 device math for the radio model, sized for the accuracy the path needs (<= 1e-12 relative) instead of the
+// 1-ulp general-purpose libm routines (CUDA's pow() alone is ~300 instructions; the whole SNR chain below is ~45).
+//
+// Table-driven log2 / exp2 with 16-entry tables: a 16 x 8-byte table is exactly one row of the 32 shared-memory
+// banks, so ANY per-lane index pattern is conflict-free (equal indices broadcast).  The tables are built once per
+// CTA with the libm routines (dcb_math_init) and live in shared memory.
+//
+//   log2(x)   x = 2^e * m, j = top 4 mantissa bits, c_j = 1 + (j + 1/2)/16, r = m * INV[j] - 1, |r| <= 1/32
+//             log2(x) = e + L2C[j] + log2(1 + r),   L2C[j] = -log2(INV[j]) with INV[j] = fl(1/c_j)   (consistent)
+//             log2(1 + r) = r * (a1 + a2 r + ... + a8 r^7) / 1,  truncation (1/32)^9/9/ln2 = 4.5e-15
+//   exp2(y)   k = rint(16 y), f = y - k/16, |f| <= 1/32, 2^y = 2^(k >> 4) * EXPT[k & 15] * 2^f
+//             2^f = sum_{n<=6} (f ln2)^n / n!,  truncation (ln2/32)^7/7! = 4.4e-16
+//   log1p2(s) log2(1 + s) for 0 <= s < 1/32 as the reference rounds it: t = fl(1 + s), s' = t - 1 (exact), series in s'
+#pragma once
+
+#include <cuda_runtime.h>
+
+struct MathTables {
+    double inv[16];   // fl(1 / c_j)
+    double l2c[16];   // -log2(inv[j])
+    double ex2[16];   // 2^(j/16)
+};
+
+// call from the first 16 threads of the CTA, then __syncthreads()
+__device__ __forceinline__ void dcb_math_init(MathTables *t, int tid) {
+    if (tid < 16) {
+        const double c = 1.0 + ((double)tid + 0.5) / 16.0;
+        const double inv = 1.0 / c;
+        t->inv[tid] = inv;
+        t->l2c[tid] = -log2(inv);
+        t->ex2[tid] = exp2((double)tid / 16.0);
+    }
+}
+
+#define DCB_INV_LN2 1.4426950408889634074
+#define DCB_LN2 0.69314718055994530942
+
+// log2(1 + r) for |r| <= 1/32 (Taylor series, Horner)
+__device__ __forceinline__ double dcb_log2_1p_small(double r) {
+    double p = -DCB_INV_LN2 / 8.0;
+    p = fma(p, r, DCB_INV_LN2 / 7.0);
+    p = fma(p, r, -DCB_INV_LN2 / 6.0);
+    p = fma(p, r, DCB_INV_LN2 / 5.0);
+    p = fma(p, r, -DCB_INV_LN2 / 4.0);
+    p = fma(p, r, DCB_INV_LN2 / 3.0);
+    p = fma(p, r, -DCB_INV_LN2 / 2.0);
+    p = fma(p, r, DCB_INV_LN2);
+    return p * r;
+}
+
+// log2 of a positive, normal double
+__device__ __forceinline__ double dcb_log2(const MathTables *t, double x) {
+    const int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    const int e = (hi >> 20) - 1023;
+    const int j = (hi >> 16) & 15;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    const double r = fma(m, t->inv[j], -1.0);
+    // (double)e without a conversion instruction: 2^52 + 2^31 + e, minus the same constant
+    const double ef = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;
+    return ef + (t->l2c[j] + dcb_log2_1p_small(r));
+}
+
+// 2^y for |y| < 1000 (result stays a normal double)
+__device__ __forceinline__ double dcb_exp2(const MathTables *t, double y) {
+    const double magic = 6755399441055744.0;             // 1.5 * 2^52: rint() in the low word
+    const double kd = fma(y, 16.0, magic);
+    const int k = __double2loint(kd);
+    const double f = fma(kd - magic, -0.0625, y);         // exact: |f| <= 1/32
+    const double z = f * DCB_LN2;
+    double p = 1.0 / 720.0;
+    p = fma(p, z, 1.0 / 120.0);
+    p = fma(p, z, 1.0 / 24.0);
+    p = fma(p, z, 1.0 / 6.0);
+    p = fma(p, z, 0.5);
+    p = fma(p, z, 1.0);
+    p = fma(p, z, 1.0);
+    const double v = t->ex2[k & 15] * p;
+    return __hiloint2double(__double2hiint(v) + ((k >> 4) << 20), __double2loint(v));
+}
+
+// log2(1 + s) for s >= 0 with the reference's rounding of 1 + s (station.py:137 np.log2(1 + snr))
+__device__ __forceinline__ double dcb_log2_1p(const MathTables *t, double s) {
+    const double u = 1.0 + s;
+    if (s < 0.03125) return dcb_log2_1p_small(u - 1.0);
+    return dcb_log2(t, u);
+}

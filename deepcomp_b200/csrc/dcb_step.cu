@@ -8,22 +8,26 @@
 // every [K][N] state slab, so state loads / reward stores are perfectly coalesced.  The per-UE state (position,
 // waypoint, pause counter, connection bitmask, EWMA rate) stays in registers for all T steps.  Each thread walks
 // its M UE x BS pairs serially; the per-BS reductions over UEs (connected count, sum of inverse rates, sum of
-// priorities, arg-max rate, sum of utilities) go through a dense [E*N][M] fp64 matrix in shared memory that
+// priorities, arg-max rate, sum of utilities) go through a dense [E*N][M|1] fp64 matrix in shared memory that
 // S lanes per (env, BS) pair column-sum and combine with warp shuffles, in a fixed order (deterministic results).
 // The observation tile of the CTA is staged in shared memory and written out with coalesced 16-byte stores.
 //
 // Arithmetic.  Positions and every range decision are fp64 with the reference's operation order (no FMA
 // contraction: the library is built with --fmad=false; the one FMA the reference has, inside np.linalg.norm, is
-// explicit).  SNR / rate / utility are fp64 as in the reference.
+// explicit), so trajectories, connection masks and lost-connection counts are bit-exact.  SNR / rate / utility are
+// fp64 through the table-driven log2 / exp2 of dcb_math.cuh (<= 1e-13 relative to the reference's libm chain); a
+// UE closer than 1 m to a BS -- where the reference's `distance + EPSILON` matters -- takes the libm path.
 #include <math_constants.h>
 
 #include "dcb_internal.h"
+#include "dcb_math.cuh"
 
 namespace {
 
 struct SmemLayout {
-    int off_a, off_b, off_cnt_pre, off_sum_pre, off_arg_pre, off_cnt_post, off_sum_post, off_arg_post, off_usum,
-        off_umin, off_su, off_srb, off_smask, off_env_rew, off_env_sumu, off_bsx, off_bsy, off_share, off_vel;
+    int off_tab, off_a, off_b, off_sum_pre, off_sum_post, off_usum, off_umin, off_fues, off_futil, off_su, off_srb,
+        off_smask, off_env_rew, off_env_sumu, off_bsx, off_bsy, off_vel, off_cnt_pre, off_arg_pre, off_cnt_post,
+        off_arg_post, off_share;
     int total;
 };
 
@@ -31,18 +35,25 @@ __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
 __host__ __device__ inline int obs_width(int kind, int M) { return kind == DCB_KIND_CENTRAL ? 2 * M + 1 : 4 * M + 1; }
 
+// Row stride (in doubles) of the [E*N][M] matrices: odd, so that the 16 lanes of one 64-bit shared-memory access
+// phase (consecutive UEs, same BS) hit 16 different bank pairs.
+__host__ __device__ inline int row_stride(int M) { return M | 1; }
+
 __host__ __device__ inline SmemLayout smem_layout(int kind, int N, int M, int E) {
     SmemLayout L;
     const int EN = E * N, EM = E * M;
     int o = 0;
+    L.off_tab = o;      o += (int)sizeof(MathTables);                // 3 x 128 B: one bank row per table
     const int stage = EN * obs_width(kind, M) * 4;
-    const int amat = EN * M * 8;
+    const int amat = EN * row_stride(M) * 8;
     L.off_a = o;        o += align16(stage > amat ? stage : amat);   // matrix A, later the obs staging tile
     L.off_b = o;        o += align16(amat);
     L.off_sum_pre = o;  o += align16(EM * 8);
     L.off_sum_post = o; o += align16(EM * 8);
     L.off_usum = o;     o += align16(EM * 8);
     L.off_umin = o;     o += align16(EM * 8);
+    L.off_fues = o;     o += align16(EM * 8);
+    L.off_futil = o;    o += align16(EM * 8);
     L.off_su = o;       o += align16(EN * 8);
     L.off_srb = o;      o += align16(EN * 8);
     L.off_smask = o;    o += align16(EN * 8);
@@ -67,22 +78,29 @@ __device__ __forceinline__ double dist2(double ax, double ay, double bx, double 
     return dx * dx + dy * dy;
 }
 
-__device__ __forceinline__ double snr_of_d2(const DevParams &p, double d2) {
-    // station.py:110-127: Okumura-Hata path loss -> received power -> SNR
+// station.py:110-127 verbatim with libm: used when the UE is within 1 m of the BS (distance + EPSILON matters)
+__device__ __noinline__ double snr_of_d2_libm(double c1, double c2, double d2) {
     const double d = sqrt(d2);
-    const double pl = p.c1 + p.c2 * log10(d + DCB_EPSILON);
+    const double pl = c1 + c2 * log10(d + DCB_EPSILON);
     const double signal = pow(10.0, (DCB_TX_POWER - pl) / 10.0);
     return signal / DCB_NOISE;
 }
 
-__device__ __forceinline__ double rate_unshared(double snr) {
-    return DCB_BW * log2(1.0 + snr);   // station.py:129-138
+// SNR = 10^((30 - c1 - c2 log10(d)) / 10) / 1e-9 = 2^(c0 - h log2(d^2)),  h = c2 / 20
+__device__ __forceinline__ double snr_of_d2(const DevParams &p, const MathTables *tab, double d2) {
+    if (d2 < 1.0) return snr_of_d2_libm(p.c1, p.c2, d2);
+    return dcb_exp2(tab, fma(-p.snr_h, dcb_log2(tab, d2), p.snr_c0));
 }
 
-__device__ __forceinline__ double log_utility(double dr) {
-    // env/util/utility.py:36-54
-    if (dr == 0.0) return DCB_MIN_UTILITY;
-    const double u = 10.0 * log10(dr);
+__device__ __forceinline__ double rate_unshared(const MathTables *tab, double snr) {
+    return DCB_BW * dcb_log2_1p(tab, snr);   // station.py:129-138
+}
+
+__device__ __forceinline__ double log_utility(const MathTables *tab, double dr) {
+    // env/util/utility.py:36-54: clip(10 log10(dr), -20, 20); dr <= 0.01 / >= 100 clip without evaluating the log
+    if (dr <= 0.01) return DCB_MIN_UTILITY;
+    if (dr >= 100.0) return DCB_MAX_UTILITY;
+    const double u = 3.0102999566398119521 * dcb_log2(tab, dr);   // 10 log10(2) log2(dr)
     return fmin(fmax(u, DCB_MIN_UTILITY), DCB_MAX_UTILITY);
 }
 
@@ -94,9 +112,9 @@ __device__ __forceinline__ double link_value(int model, double r0, double ewma) 
 }
 
 // ------------------------------------------------------------------------------------------------ reductions
-// Column reduction of the dense [E*N][M] matrix A: for every (env, BS) pair count the non-zero entries, sum them
+// Column reduction of the dense [E*N][MS] matrix A: for every (env, BS) pair count the non-zero entries, sum them
 // and (max-cap only) find the first arg-max.  S lanes per pair, fixed combination order.
-__device__ __forceinline__ void reduce_links(const double *A, int N, int M, int n_env, int S, bool want_arg,
+__device__ __forceinline__ void reduce_links(const double *A, int N, int M, int MS, int n_env, int S, bool want_arg,
                                              int *cnt, double *sum, int *arg) {
     const int R = n_env * M;
     const int ppp = blockDim.x / S;
@@ -111,12 +129,13 @@ __device__ __forceinline__ void reduce_links(const double *A, int N, int M, int 
             const int le = pair / M, b = pair - le * M;
             const int i0 = seg * chunk;
             const int i1 = min(N, i0 + chunk);
-            const double *col = A + (size_t)(le * N) * M + b;
+            const double *col = A + (size_t)(le * N) * MS + b;
+#pragma unroll 4
             for (int i = i0; i < i1; i++) {
-                const double v = col[(size_t)i * M];
+                const double v = col[(size_t)i * MS];
                 c += (v != 0.0);
                 s += v;
-                if (v > best) { best = v; bi = i; }
+                if (want_arg && v > best) { best = v; bi = i; }
             }
         }
         for (int off = S >> 1; off > 0; off >>= 1) {
@@ -132,10 +151,11 @@ __device__ __forceinline__ void reduce_links(const double *A, int N, int M, int 
     }
 }
 
-// Column sum only (per-BS total utility, station.py:63-69); optional masked min (station.py:78-83)
+// Per-BS total utility (station.py:63-69) -> usum, the two per-BS observation entries (variants.py:296-299,
+// station.py:71-76) -> f_ues, f_util; optional masked min (station.py:78-83).
 __device__ __forceinline__ void reduce_utility(const double *A, const unsigned long long *smask, const double *su,
-                                               int N, int M, int n_env, int S, bool want_min, double *usum,
-                                               double *umin) {
+                                               const int *cnt, int N, int M, int MS, int n_env, int S, bool want_min,
+                                               double *usum, double *umin, double *f_ues, double *f_util) {
     const int R = n_env * M;
     const int ppp = blockDim.x / S;
     const int seg = threadIdx.x & (S - 1);
@@ -148,8 +168,9 @@ __device__ __forceinline__ void reduce_utility(const double *A, const unsigned l
             const int le = pair / M, b = pair - le * M;
             const int i0 = seg * chunk;
             const int i1 = min(N, i0 + chunk);
-            const double *col = A + (size_t)(le * N) * M + b;
-            for (int i = i0; i < i1; i++) s += col[(size_t)i * M];
+            const double *col = A + (size_t)(le * N) * MS + b;
+#pragma unroll 4
+            for (int i = i0; i < i1; i++) s += col[(size_t)i * MS];
             if (want_min)
                 for (int i = i0; i < i1; i++)
                     if ((smask[le * N + i] >> b) & 1ull) mn = fmin(mn, su[le * N + i]);
@@ -158,13 +179,18 @@ __device__ __forceinline__ void reduce_utility(const double *A, const unsigned l
             s += __shfl_xor_sync(0xffffffffu, s, off);
             if (want_min) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
         }
-        if (ok && seg == 0) { usum[pair] = s; umin[pair] = mn; }
+        if (ok && seg == 0) {
+            const int c = cnt[pair];
+            usum[pair] = s;
+            umin[pair] = mn;
+            f_ues[pair] = (double)c / (double)N;
+            f_util[pair] = (c > 0 ? s / (double)c : 0.0) / DCB_MAX_UTILITY;
+        }
     }
 }
 
-// Per-env reduction of a per-UE vector: mode 0 = sum, 2 = min
+// Per-env reduction of a per-UE vector: mode 0 = sum, 2 = min (one warp per env)
 __device__ __forceinline__ void reduce_env(const double *v, int N, int n_env, int mode, double *out) {
-    // 32 lanes per env
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int chunk = (N + 31) / 32;
     for (int le = warp; le < n_env; le += nwarps) {
@@ -182,10 +208,12 @@ __device__ __forceinline__ void reduce_env(const double *v, int N, int n_env, in
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int MAXT>
 __global__ void __launch_bounds__(MAXT) dcb_step_kernel(const StepArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const DevParams &p = a.p;
     const int N = p.N, M = p.M, E = p.E, S = p.S;
+    const int MS = row_stride(M);
     const SmemLayout L = smem_layout(p.kind, N, M, E);
+    MathTables *tab = reinterpret_cast<MathTables *>(smem + L.off_tab);
     double *A = reinterpret_cast<double *>(smem + L.off_a);
     float *stage = reinterpret_cast<float *>(smem + L.off_a);
     double *B = reinterpret_cast<double *>(smem + L.off_b);
@@ -197,6 +225,8 @@ __global__ void __launch_bounds__(MAXT) dcb_step_kernel(const StepArgs a) {
     int *arg_post = reinterpret_cast<int *>(smem + L.off_arg_post);
     double *usum = reinterpret_cast<double *>(smem + L.off_usum);
     double *umin = reinterpret_cast<double *>(smem + L.off_umin);
+    double *f_ues = reinterpret_cast<double *>(smem + L.off_fues);
+    double *f_util = reinterpret_cast<double *>(smem + L.off_futil);
     double *su = reinterpret_cast<double *>(smem + L.off_su);
     double *srb = reinterpret_cast<double *>(smem + L.off_srb);
     unsigned long long *smask = reinterpret_cast<unsigned long long *>(smem + L.off_smask);
@@ -218,6 +248,7 @@ __global__ void __launch_bounds__(MAXT) dcb_step_kernel(const StepArgs a) {
     const bool central = p.kind == DCB_KIND_CENTRAL;
     const int OW = obs_width(p.kind, M);
 
+    dcb_math_init(tab, t);
     for (int b = t; b < M; b += blockDim.x) {
         bsx[b] = p.bs_xy[2 * b];
         bsy[b] = p.bs_xy[2 * b + 1];
@@ -241,12 +272,13 @@ __global__ void __launch_bounds__(MAXT) dcb_step_kernel(const StepArgs a) {
     }
     __syncthreads();
     const double vfix = valid ? velspec[i] : 0.0;
-    double *Arow = A + (size_t)t * M;
-    double *Brow = B + (size_t)t * M;
+    double *Arow = A + (size_t)t * MS;
+    double *Brow = B + (size_t)t * MS;
     const int T = a.T;
+    const int n_iter = T > 0 ? T : 1;
 
-    for (int step = 0; step < (T > 0 ? T : 1); step++) {
-        const bool last = step == (T > 0 ? T : 1) - 1;
+    for (int step = 0; step < n_iter; step++) {
+        const bool last = step == n_iter - 1;
         double rb = 0.0;      // reward before the move (base.py:446)
         int lost = 0;
         if (T > 0) {
@@ -274,13 +306,13 @@ __global__ void __launch_bounds__(MAXT) dcb_step_kernel(const StepArgs a) {
                 for (int b = 0; b < M; b++) Arow[b] = 0.0;
                 for (unsigned long long m = mask; m; m &= m - 1) {
                     const int b = __ffsll((long long)m) - 1;
-                    const double r0 = rate_unshared(snr_of_d2(p, dist2(bsx[b], bsy[b], x, y)));
+                    const double r0 = rate_unshared(tab, snr_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y)));
                     Arow[b] = link_value(share[b], r0, ewma);
                     Brow[b] = r0;
                 }
             }
             __syncthreads();
-            reduce_links(A, N, M, n_env, S, p.has_maxcap, cnt_pre, sum_pre, arg_pre);
+            reduce_links(A, N, M, MS, n_env, S, p.has_maxcap, cnt_pre, sum_pre, arg_pre);
             __syncthreads();
             if (valid) {
                 // ---- Basestation.data_rate_shared (station.py:152-202) per connected link; ue.bs_dr cache in Brow
@@ -299,8 +331,7 @@ __global__ void __launch_bounds__(MAXT) dcb_step_kernel(const StepArgs a) {
                     dr += r;                                                           // user.py:64-69
                 }
                 // ---- calc_reward (base.py:158-167), penalties are identically 0 (base.py:257)
-                const double up = log_utility(dr);
-                rb = fmin(fmax(up, DCB_MIN_UTILITY), DCB_MAX_UTILITY) / DCB_MAX_UTILITY;
+                rb = log_utility(tab, dr) / DCB_MAX_UTILITY;
                 // ---- User.move (user.py:159-173) -> RandomWaypoint.step (movement.py:158-181)
                 double wx = (double)(wxy & 0xffffu), wy = (double)(wxy >> 16);
                 unsigned pause = (vpt >> 8) & 0xffu;
@@ -351,23 +382,22 @@ __global__ void __launch_bounds__(MAXT) dcb_step_kernel(const StepArgs a) {
         double mx = 0.0;
         unsigned long long inrange = 0ull;
         if (valid) {
-            // SNR of every pair at the current position (variants.py:278) -> Brow; in-range set (multi_agent.py:60)
+            // SNR of every pair at the current position (variants.py:278) -> Brow; in-range set (multi_agent.py:60);
+            // link values at the new position for update_ue_drs_rewards(update_only=True) (base.py:451) -> Arow
+#pragma unroll 2
             for (int b = 0; b < M; b++) {
                 const double d2 = dist2(bsx[b], bsy[b], x, y);
-                const double s = snr_of_d2(p, d2);
+                const double s = snr_of_d2(p, tab, d2);
                 Brow[b] = s;
                 mx = fmax(mx, s);
                 if (d2 <= p.thr_d2) inrange |= 1ull << b;
-            }
-            // link values at the new position for update_ue_drs_rewards(update_only=True) (base.py:451)
-            for (int b = 0; b < M; b++) {
                 double v = 0.0;
-                if ((mask >> b) & 1ull) v = link_value(share[b], rate_unshared(Brow[b]), ewma);
+                if ((mask >> b) & 1ull) v = link_value(share[b], rate_unshared(tab, s), ewma);
                 Arow[b] = v;
             }
         }
         __syncthreads();
-        reduce_links(A, N, M, n_env, S, p.has_maxcap, cnt_post, sum_post, arg_post);
+        reduce_links(A, N, M, MS, n_env, S, p.has_maxcap, cnt_post, sum_post, arg_post);
         __syncthreads();
         double dr = 0.0, util = 0.0;
         if (valid) {
@@ -380,38 +410,42 @@ __global__ void __launch_bounds__(MAXT) dcb_step_kernel(const StepArgs a) {
                 if (model == DCB_SHARE_RESOURCE_FAIR) r = v / (double)cnt_post[pr];
                 else if (model == DCB_SHARE_RATE_FAIR) r = 1.0 / sum_post[pr];
                 else if (model == DCB_SHARE_MAX_CAP) r = (arg_post[pr] == i) ? v : 0.0;
-                else r = v / (sum_post[pr] + DCB_EPSILON) * rate_unshared(Brow[b]);
+                else r = v / (sum_post[pr] + DCB_EPSILON) * rate_unshared(tab, Brow[b]);
                 if (last && a.out.dbg_link_rate) a.out.dbg_link_rate[u * M + b] = r;
                 dr += r;
             }
-            util = log_utility(dr);                                                    // user.py:76-92
+            util = log_utility(tab, dr);                                               // user.py:76-92
             su[t] = util;
             srb[t] = rb;
             smask[t] = mask;
-            for (int b = 0; b < M; b++) Arow[b] = ((mask >> b) & 1ull) ? util : 0.0;
+            if (!central)
+                for (int b = 0; b < M; b++) Arow[b] = ((mask >> b) & 1ull) ? util : 0.0;
         }
         __syncthreads();
-        if (!central) reduce_utility(A, smask, su, N, M, n_env, S, p.reward == DCB_REWARD_MIN, usum, umin);
+        if (!central)
+            reduce_utility(A, smask, su, cnt_post, N, M, MS, n_env, S, p.reward == DCB_REWARD_MIN, usum, umin, f_ues,
+                           f_util);
         if (central && T > 0) reduce_env(srb, N, n_env, p.reward == DCB_REWARD_MIN ? 2 : 0, env_rew);
-        reduce_env(su, N, n_env, 0, env_sumu);
+        if (a.out.sum_utility || a.out.dbg_sum_utility) reduce_env(su, N, n_env, 0, env_sumu);
         __syncthreads();
         // ---- observation row -> staging tile (A is dead now), rewards and per-UE outputs -> global
         if (valid) {
-            const double inv_max = DCB_MAX_UTILITY;
             double *dobs = (last && a.out.dbg_obs) ? a.out.dbg_obs : nullptr;
+            const double un = util / DCB_MAX_UTILITY;                                  // variants.py:287
+            const double inv_mx = mx == 0.0 ? 0.0 : 1.0 / mx;                          // variants.py:279-284
             if (central) {
                 // central.py:31-57: [connected(N*M) | dr(N*M) | utility(N)] per env
                 float *row = stage + (size_t)le * (2 * N * M + N);
                 double *drow = dobs ? dobs + (size_t)k * (2 * N * M + N) : nullptr;
                 for (int b = 0; b < M; b++) {
                     const double c = (double)((mask >> b) & 1ull);
-                    const double r = mx == 0.0 ? 0.0 : Brow[b] / mx;                  // variants.py:279-284
+                    const double r = Brow[b] * inv_mx;
                     row[i * M + b] = (float)c;
                     row[N * M + i * M + b] = (float)r;
                     if (drow) { drow[i * M + b] = c; drow[N * M + i * M + b] = r; }
                 }
-                row[2 * N * M + i] = (float)(util / inv_max);                          // variants.py:287
-                if (drow) drow[2 * N * M + i] = util / inv_max;
+                row[2 * N * M + i] = (float)un;
+                if (drow) drow[2 * N * M + i] = un;
             } else {
                 // variants.py:271-303: [connected(M) | dr(M) | ues_at_bs(M) | util_at_bs(M) | utility(1)] per UE
                 float *row = stage + (size_t)t * OW;
@@ -419,15 +453,13 @@ __global__ void __launch_bounds__(MAXT) dcb_step_kernel(const StepArgs a) {
                 for (int b = 0; b < M; b++) {
                     const int pr = le * M + b;
                     const double c = (double)((mask >> b) & 1ull);
-                    const double r = mx == 0.0 ? 0.0 : Brow[b] / mx;
-                    const double nb = (double)cnt_post[pr];
-                    const double ab = nb / (double)N;                                  // variants.py:296
-                    const double ub = (cnt_post[pr] > 0 ? usum[pr] / nb : 0.0) / inv_max;   // station.py:71-76
+                    const double r = Brow[b] * inv_mx;
+                    const double ab = f_ues[pr], ub = f_util[pr];
                     row[b] = (float)c; row[M + b] = (float)r; row[2 * M + b] = (float)ab; row[3 * M + b] = (float)ub;
                     if (drow) { drow[b] = c; drow[M + b] = r; drow[2 * M + b] = ab; drow[3 * M + b] = ub; }
                 }
-                row[4 * M] = (float)(util / inv_max);
-                if (drow) drow[4 * M] = util / inv_max;
+                row[4 * M] = (float)un;
+                if (drow) drow[4 * M] = un;
             }
             if (last && a.out.dbg_snr)
                 for (int b = 0; b < M; b++) a.out.dbg_snr[u * M + b] = Brow[b];
@@ -489,7 +521,7 @@ __global__ void __launch_bounds__(MAXT) dcb_step_kernel(const StepArgs a) {
                 const int n4 = n >> 2;
                 const float4 *s4 = reinterpret_cast<const float4 *>(stage);
                 float4 *d4 = reinterpret_cast<float4 *>(dst);
-                for (int j = t; j < n4; j += blockDim.x) d4[j] = s4[j];
+                for (int j = t; j < n4; j += blockDim.x) __stcs(d4 + j, s4[j]);
                 for (int j = (n4 << 2) + t; j < n; j += blockDim.x) dst[j] = stage[j];
             } else {
                 for (int j = t; j < n; j += blockDim.x) dst[j] = stage[j];
