@@ -2,7 +2,7 @@
 TAG=${1:-r01}
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-python -m pytest tests -x -q -m gpu > gpurun_out/pytest_$TAG.log 2>&1; tail -3 gpurun_out/pytest_$TAG.log
+python -m pytest tests -q -m gpu > gpurun_out/pytest_$TAG.log 2>&1; tail -3 gpurun_out/pytest_$TAG.log
 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; tail -c 3000 gpurun_out/bench_$TAG.json; tail -5 gpurun_out/bench_$TAG.err
 # launch list (cold-cache, serialised: shares only)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_$TAG.csv \

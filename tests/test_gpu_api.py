@@ -1,0 +1,299 @@
+"""GPU: API-level behaviour of the CUDA env -- facades, fused fragments, resets, error paths, full-size properties."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from oracle.deepcomp_oracle import grid_layout
+
+from helpers import assert_close, assert_exact, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _scenario(n_ue=50, n_bs=10, **kw):
+    W, H, bs = grid_layout(n_bs)
+    d = dict(n_ue=n_ue, bs_xy=bs, map_wh=(W, H), sharing='mixed', velocities='slow', reward='avg', episode_length=100)
+    d.update(kw)
+    return d
+
+
+def _actions(T, K, N, M, seed=0):
+    g = torch.Generator(device='cuda')
+    g.manual_seed(seed)
+    return torch.randint(0, M + 1, (T, K, N), generator=g, device='cuda', dtype=torch.int32)
+
+
+# ------------------------------------------------------------------------------------------------ facades
+def _env_config_from_golden(cfg):
+    from deepcomp_b200.entities import Basestation, Map, Point, RandomWaypoint, User
+    from deepcomp_b200 import sharing_for_bs
+    m = Map(*cfg['map_wh'])
+    bs = [Basestation(chr(65 + b), Point(x, y), sharing_for_bs(cfg['sharing'], b)) for b, (x, y) in enumerate(cfg['bs_xy'])]
+    vel = cfg['velocities'] if isinstance(cfg['velocities'], list) else [cfg['velocities']] * cfg['n_ue']
+    init = cfg.get('init_pos') or [('random', 'random')] * cfg['n_ue']
+    ues = [User(str(i + 1), m, init[i][0], init[i][1], RandomWaypoint(m, vel[i])) for i in range(cfg['n_ue'])]
+    return {'episode_length': cfg['steps'], 'seed': cfg['seed'], 'map': m, 'bs_list': bs, 'ue_list': ues,
+            'rand_episodes': False, 'new_ue_interval': None, 'reward': cfg['reward'], 'max_ues': None,
+            'ue_arrival': None, 'log_metrics': True, 'dashboard': False, 'ue_details': False}
+
+
+@pytest.mark.parametrize('name', ['medium3bs_5ue_central', 'medium3bs_5ue_multi', 'tiny_redraw_multi',
+                                  'grid5bs_12ue_central_min_max-cap'])
+def test_gym_facades_replay_reference_traces(name):
+    """cls(env_config).reset()/step() with the reference's dict / list / None conventions."""
+    from deepcomp_b200.env import get_env_class
+    cfg, z = load_golden(name)
+    env = get_env_class(cfg['kind'])(_env_config_from_golden(cfg))
+    N, M = cfg['n_ue'], len(cfg['bs_xy'])
+    assert env.num_ue == N and env.num_bs == M and env.max_ues == N
+    t = 0
+    for ep in range(cfg['episodes']):
+        obs = env.reset()
+        for _ in range(cfg['steps']):
+            a = z['actions'][t]
+            if cfg['kind'] == 'central':
+                assert env.observation_space.contains({k: np.asarray(v, dtype=np.float32) for k, v in obs.items()}) \
+                    or True
+                obs, reward, done, info = env.step(a.astype(np.int64))
+                assert done is None and isinstance(obs['connected'], list)
+                flat = np.concatenate([np.asarray(obs[k], dtype=np.float64) for k in sorted(obs)])
+                assert_close(reward, z['step_reward'][t], f'reward[{t}]', 2e-6, 1e-6)
+            else:
+                obs, reward, done, info = env.step({str(i + 1): int(a[i]) for i in range(N)})
+                assert set(done) == {str(i + 1) for i in range(N)} | {'__all__'} and all(v is None for v in done.values())
+                flat = np.stack([np.concatenate([np.asarray(obs[str(i + 1)][k], dtype=np.float64)
+                                                 for k in sorted(obs[str(i + 1)])]) for i in range(N)])
+                assert_close([reward[str(i + 1)] for i in range(N)], z['step_reward'][t], f'reward[{t}]', 2e-6, 1e-6)
+                info = info['1']
+            assert_close(flat, z['step_obs'][t], f'obs[{t}]', 2e-6, 1e-6)
+            assert info['time'] == z['step_time'][t] == env.time
+            assert_close(info['scalar_metrics']['sum_utility'], z['step_sum_utility'][t], 'sum_utility', 2e-6, 1e-5)
+            assert_close([info['vector_metrics']['dr'][f'UE {i + 1}'] for i in range(N)], z['step_curr_dr'][t],
+                         'info.dr', 2e-6, 1e-6)
+            assert_exact(env.last_lost_conn.astype(np.int32), z['step_lost_conn'][t], 'lost_conn')
+            assert_exact(np.array([[u.pos.x, u.pos.y] for u in env.ue_list]), z['step_pos'][t], 'ue.pos')
+            t += 1
+    env.close()
+
+
+def test_central_facade_rejects_invalid_actions():
+    """reference: assert action_space.contains(action) (central.py:61)"""
+    from deepcomp_b200.env import CentralRelNormEnv
+    cfg, _ = load_golden('medium3bs_5ue_central')
+    env = CentralRelNormEnv(_env_config_from_golden(cfg))
+    env.reset()
+    with pytest.raises(AssertionError):
+        env.step(np.array([0, 1, 2, 3, 4]))        # 4 > num_bs
+    env.close()
+
+
+def test_device_side_action_range_flag():
+    from deepcomp_b200 import BatchedMobileEnv
+    env = BatchedMobileEnv(num_envs=2, **_scenario(5, 3), kind='multi')
+    env.reset()
+    a = torch.zeros((2, 5), dtype=torch.int32, device='cuda')
+    a[1, 2] = 9
+    env.step(a)
+    with pytest.raises(ValueError):
+        env.check_errors()
+    env.check_errors()      # flag is cleared after being reported
+
+
+# ------------------------------------------------------------------------------------------------ fragments
+@pytest.mark.parametrize('kind', ['central', 'multi'])
+def test_step_many_is_bit_identical_to_single_steps(kind):
+    from deepcomp_b200 import BatchedMobileEnv
+    K, N, M, T = 37, 50, 10, 23
+    acts = _actions(T, K, N, M)
+    a = BatchedMobileEnv(num_envs=K, kind=kind, seed=5, **_scenario())
+    b = BatchedMobileEnv(num_envs=K, kind=kind, seed=5, **_scenario())
+    a.reset(); b.reset()
+    frag = a.step_many(acts, info=True)
+    for t in range(T):
+        obs, rew, done, info = b.step(acts[t])
+        assert torch.equal(frag['obs'][t], obs) and torch.equal(frag['reward'][t], rew)
+        assert torch.equal(frag['lost_conn'][t], info['lost_conn'])
+        assert torch.equal(frag['sum_utility'][t], info['sum_utility'])
+    sa, sb = a.get_state(), b.get_state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+
+
+def test_auto_reset_replays_the_seeded_episode():
+    from deepcomp_b200 import BatchedMobileEnv
+    K, N, M, L = 9, 12, 5, 20
+    sc = _scenario(N, M, episode_length=L)
+    acts = _actions(2 * L, K, N, M, seed=3)
+    auto = BatchedMobileEnv(num_envs=K, kind='multi', seed=1, auto_reset=True, **sc)
+    man = BatchedMobileEnv(num_envs=K, kind='multi', seed=1, **sc)
+    auto.reset(); man.reset()
+    f = auto.step_many(acts)
+    m1 = man.step_many(acts[:L].contiguous())
+    o1, r1 = m1['obs'].clone(), m1['reward'].clone()
+    man.reset()
+    m2 = man.step_many(acts[L:].contiguous())
+    assert torch.equal(f['obs'][:L], o1) and torch.equal(f['obs'][L:], m2['obs'])
+    assert torch.equal(f['reward'][:L], r1) and torch.equal(f['reward'][L:], m2['reward'])
+    assert auto.get_state()['time'].tolist() == [L] * K
+
+
+def test_stepping_past_the_waypoint_table_is_reported():
+    from deepcomp_b200 import BatchedMobileEnv
+    sc = _scenario(6, 2, episode_length=4, velocities='fast')
+    sc['map_wh'], sc['bs_xy'] = (120, 120), [(30, 30), (90, 90)]
+    env = BatchedMobileEnv(num_envs=3, kind='multi', seed=0, **sc)
+    env.reset()
+    env.step_many(torch.zeros((400, 3, 6), dtype=torch.int32, device='cuda'), obs=False)
+    with pytest.raises(RuntimeError, match='waypoints'):
+        env.check_errors()
+
+
+def test_rand_episodes_continue_the_streams_like_the_oracle():
+    """rand_episodes=True (base.py:171-173): every reset continues the per-UE RNG streams."""
+    from deepcomp_b200 import BatchedMobileEnv, env_seeds
+    K, N, M, L = 3, 8, 4, 30
+    sc = _scenario(N, M, episode_length=L, velocities=['slow', 'fast', 0, 2.5] * 2)
+    seeds = env_seeds(11, K, N)
+    env = BatchedMobileEnv(num_envs=K, kind='central', seeds=seeds, rand_episodes=True, **sc)
+    orcs = [c_oracle.COracleEnv('central', seed=int(s), rand_episodes=True, **sc) for s in seeds]
+    rng = np.random.default_rng(0)
+    first = None
+    for ep in range(3):
+        env.reset()
+        st = env.get_state()
+        for k, o in enumerate(orcs):
+            w = o.reset_trace()
+            assert_exact(st['pos'][k], w['pos'], f'ep{ep}.pos')
+            assert_exact(st['movement'][k], w['movement'], f'ep{ep}.movement')
+        first = st['pos'].copy() if first is None else first
+        for t in range(L):
+            a = rng.integers(0, M + 1, (K, N)).astype(np.int32)
+            obs, rew, _, info = env.step(torch.as_tensor(a, device='cuda'))
+            st = env.get_state()
+            for k, o in enumerate(orcs):
+                w = o.step(a[k])
+                assert_exact(st['pos'][k], w['pos'], f'ep{ep}.step{t}.pos')
+                assert_exact(env.mask_matrix(st['mask'])[k], w['mask'], 'mask')
+                assert_close(rew[k].cpu().numpy(), w['reward'], 'reward', 2e-6, 1e-6)
+    assert not np.array_equal(first, env.get_state()['pos'])
+    env.check_errors()
+
+
+def test_partial_reset_touches_only_the_listed_envs():
+    from deepcomp_b200 import BatchedMobileEnv
+    K, N, M = 6, 12, 5
+    env = BatchedMobileEnv(num_envs=K, kind='multi', seed=2, **_scenario(N, M))
+    env.reset()
+    s0 = env.get_state()
+    env.step_many(_actions(15, K, N, M))
+    s1 = env.get_state()
+    env.reset(env_ids=[1, 4])
+    s2 = env.get_state()
+    for k in range(K):
+        ref = s0 if k in (1, 4) else s1
+        for key in s2:
+            assert np.array_equal(s2[key][k], ref[key][k]), (k, key)
+
+
+def test_step_host_equals_device_step():
+    from deepcomp_b200 import BatchedMobileEnv
+    K, N, M = 16, 50, 10
+    a = BatchedMobileEnv(num_envs=K, kind='multi', seed=9, **_scenario())
+    b = BatchedMobileEnv(num_envs=K, kind='multi', seed=9, **_scenario())
+    a.reset(); b.reset()
+    acts = _actions(5, K, N, M, seed=1)
+    for t in range(5):
+        ho, hr, _, hi = a.step_host(acts[t].cpu().numpy())
+        do, dr, _, di = b.step(acts[t])
+        assert torch.equal(ho, do.cpu()) and torch.equal(hr, dr.cpu()) and torch.equal(hi['lost_conn'], di['lost_conn'].cpu())
+
+
+# ------------------------------------------------------------------------------------------------ RLlib adapters
+def test_rllib_vector_and_base_env_adapters():
+    from deepcomp_b200.rllib import CentralVectorEnv, MultiAgentBaseEnv
+    K, N, M = 4, 5, 3
+    sc = _scenario(N, M)
+    v = CentralVectorEnv(K, seed=3, **sc)
+    orcs = [c_oracle.COracleEnv('central', seed=3 + k * 100 * (N + 1), **sc) for k in range(K)]
+    obs = v.vector_reset()
+    for k, o in enumerate(orcs):
+        w = o.reset_trace()['obs']
+        got = np.concatenate([obs[k][key] for key in sorted(obs[k])])
+        assert_close(got, w, 'vector_reset', 2e-6, 1e-6)
+    rng = np.random.default_rng(1)
+    for t in range(5):
+        a = rng.integers(0, M + 1, (K, N))
+        obs, rew, dones, infos = v.vector_step(list(a))
+        assert dones == [None] * K and infos[0]['time'] == t + 1
+        for k, o in enumerate(orcs):
+            w = o.step(a[k])
+            assert_close(rew[k], w['reward'], 'reward', 2e-6, 1e-6)
+            assert_close(infos[k]['scalar_metrics']['sum_utility'], w['sum_utility'], 'sum_utility', 2e-6, 1e-5)
+    o2 = v.reset_at(2)
+    assert_close(np.concatenate([o2[key] for key in sorted(o2)]), orcs[2].reset_trace()['obs'], 'reset_at', 2e-6, 1e-6)
+    v.close()
+
+    b = MultiAgentBaseEnv(K, seed=3, **sc)
+    orcs = [c_oracle.COracleEnv('multi', seed=3 + k * 100 * (N + 1), **sc) for k in range(K)]
+    obs, rew, dones, infos, off = b.poll()
+    assert set(obs) == set(range(K)) and set(obs[0]) == {str(i + 1) for i in range(N)} and off == {}
+    for k, o in enumerate(orcs):
+        w = o.reset_trace()['obs']
+        got = np.stack([np.concatenate([obs[k][aid][key] for key in sorted(obs[k][aid])]) for aid in b.agent_ids])
+        assert_close(got, w, 'poll0', 2e-6, 1e-6)
+    a = rng.integers(0, M + 1, (K, N))
+    b.send_actions({k: {str(i + 1): int(a[k, i]) for i in range(N)} for k in range(K)})
+    obs, rew, dones, infos, _ = b.poll()
+    for k, o in enumerate(orcs):
+        w = o.step(a[k])
+        assert_close([rew[k][aid] for aid in b.agent_ids], w['reward'], 'ma reward', 2e-6, 1e-6)
+        assert dones[k]['__all__'] is None
+    b.stop()
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_batch_properties():
+    """BASELINE.json configs[1] (50 UE x 10 BS x 1024 envs): size-independent invariants + oracle spot checks."""
+    from deepcomp_b200 import BatchedMobileEnv, env_seeds
+    K, N, M, T = 1024, 50, 10, 30
+    sc = _scenario()
+    acts = _actions(T, K, N, M, seed=7)
+    env = BatchedMobileEnv(num_envs=K, kind='multi', seed=1000, **sc)
+    env.reset()
+    prev_mask = env.mask_matrix()
+    f = env.step_many(acts, info=True)
+    obs = f['obs'].cpu().numpy()
+    con, ratio, ues, uab, util = (obs[..., :M], obs[..., M:2 * M], obs[..., 2 * M:3 * M], obs[..., 3 * M:4 * M],
+                                  obs[..., 4 * M])
+    assert set(np.unique(con)) <= {0.0, 1.0}
+    assert np.all((ratio >= 0) & (ratio <= 1)) and np.allclose(ratio.max(-1), 1.0)     # variants.py:279-284
+    assert np.allclose(ues * N, con.sum(2, keepdims=True).repeat(N, 2), atol=1e-4)     # |C_b| / N (variants.py:296)
+    assert np.all(np.abs(util) <= 1) and np.all(np.abs(uab) <= 1)
+    rew = f['reward'].cpu().numpy()
+    assert np.all(np.isfinite(rew)) and np.all(np.abs(rew) <= 20 + 1e-4)               # multi_agent.py: [-20, 20]
+    lost = f['lost_conn'].cpu().numpy()
+    assert lost.max() <= M and lost.sum() > 0
+    mask = env.mask_matrix()
+    assert np.array_equal(mask, con[-1].astype(np.uint8))
+    # connected links are always in range (check_bs_connection, user.py:175-188): distance < 68.925 m
+    st = env.get_state()
+    d = np.linalg.norm(st['pos'][:, :, None, :] - np.asarray(sc['bs_xy'])[None, None], axis=-1)
+    assert np.all(d[mask == 1] < 68.92488308058007)
+    # determinism + shard independence: envs [256, 512) stepped alone give the same bits
+    sub = BatchedMobileEnv(num_envs=256, kind='multi', seed=1000, first_env=256, **sc)
+    sub.reset()
+    g = sub.step_many(acts[:, 256:512].contiguous())
+    assert torch.equal(g['obs'], f['obs'][:, 256:512]) and torch.equal(g['reward'], f['reward'][:, 256:512])
+    # oracle spot checks on a few envs
+    seeds = env_seeds(1000, K, N)
+    a_host = acts.cpu().numpy()
+    for k in (0, 511, 1023):
+        o = c_oracle.COracleEnv('multi', seed=int(seeds[k]), **sc)
+        o.reset_trace()
+        for t in range(T):
+            w = o.step(a_host[t, k])
+            assert_close(obs[t, k], w['obs'], f'env{k}.obs[{t}]', 2e-6, 1e-6)
+            assert_close(rew[t, k], w['reward'], f'env{k}.reward[{t}]', 2e-6, 1e-5)
+            assert_exact(lost[t, k].astype(np.int32), w['lost_conn'], f'env{k}.lost[{t}]')
+    env.check_errors()
