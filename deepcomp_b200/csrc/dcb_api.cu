@@ -250,8 +250,10 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     env->threads = (E * N + 31) / 32 * 32;
     env->grid = (K + E - 1) / E;
     env->smem = dcb_step_smem_bytes(cfg->kind, N, M, E);
+    // reducer lanes per (env, BS) pair: one per 32-UE bitset word, power of two, while the pairs still fit the CTA
     int S = 1;
-    while (S * 2 <= 32 && E * M * S * 2 <= env->threads) S *= 2;
+    const int NW = (N + 31) / 32;
+    while (S < NW && S * 2 <= 32 && E * M * S * 2 <= env->threads) S *= 2;
 
     const size_t KN = (size_t)K * N;
     // pause_duration + 1 steps is the shortest possible redraw cycle (movement.py:168-181); +2 = entry 0 and slack

@@ -1,4 +1,4 @@
-// fp64 device math for the radio model, sized for the accuracy the path needs (<= 1e-12 relative) instead of the
+// fp64 device math for the radio model, sized for the accuracy the path needs (<= 1e-13 relative) instead of the
 // 1-ulp general-purpose libm routines (CUDA's pow() alone is ~300 instructions; the whole SNR chain below is ~45).
 //
 // Table-driven log2 / exp2 with 16-entry tables: a 16 x 8-byte table is exactly one row of the 32 shared-memory
@@ -7,10 +7,14 @@
 //
 //   log2(x)   x = 2^e * m, j = top 4 mantissa bits, c_j = 1 + (j + 1/2)/16, r = m * INV[j] - 1, |r| <= 1/32
 //             log2(x) = e + L2C[j] + log2(1 + r),   L2C[j] = -log2(INV[j]) with INV[j] = fl(1/c_j)   (consistent)
-//             log2(1 + r) = r * (a1 + a2 r + ... + a8 r^7) / 1,  truncation (1/32)^9/9/ln2 = 4.5e-15
+//             log2(1 + r) = r * (a1 + a2 r + ... + a8 r^7),  truncation (1/32)^9/9/ln2 = 4.5e-15
 //   exp2(y)   k = rint(16 y), f = y - k/16, |f| <= 1/32, 2^y = 2^(k >> 4) * EXPT[k & 15] * 2^f
 //             2^f = sum_{n<=6} (f ln2)^n / n!,  truncation (ln2/32)^7/7! = 4.4e-16
 //   log1p2(s) log2(1 + s) for 0 <= s < 1/32 as the reference rounds it: t = fl(1 + s), s' = t - 1 (exact), series in s'
+//   rcp(x)    MUFU.RCP64H seed + 2 Newton steps (<= 1 ulp) for the divisions that need not be IEEE-exact
+//
+// The polynomials are evaluated in Estrin form (dependency depth 4 instead of 8): the path is latency-bound at the
+// occupancy a 1024-env batch gives a B200.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -35,17 +39,27 @@ __device__ __forceinline__ void dcb_math_init(MathTables *t, int tid) {
 #define DCB_INV_LN2 1.4426950408889634074
 #define DCB_LN2 0.69314718055994530942
 
-// log2(1 + r) for |r| <= 1/32 (Taylor series, Horner)
+// 1/x for a positive normal x, <= 1 ulp
+__device__ __forceinline__ double dcb_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+// log2(1 + r) for |r| <= 1/32 (Taylor series, Estrin evaluation)
 __device__ __forceinline__ double dcb_log2_1p_small(double r) {
-    double p = -DCB_INV_LN2 / 8.0;
-    p = fma(p, r, DCB_INV_LN2 / 7.0);
-    p = fma(p, r, -DCB_INV_LN2 / 6.0);
-    p = fma(p, r, DCB_INV_LN2 / 5.0);
-    p = fma(p, r, -DCB_INV_LN2 / 4.0);
-    p = fma(p, r, DCB_INV_LN2 / 3.0);
-    p = fma(p, r, -DCB_INV_LN2 / 2.0);
-    p = fma(p, r, DCB_INV_LN2);
-    return p * r;
+    const double r2 = r * r;
+    const double r4 = r2 * r2;
+    const double p01 = fma(-DCB_INV_LN2 / 2.0, r, DCB_INV_LN2);
+    const double p23 = fma(-DCB_INV_LN2 / 4.0, r, DCB_INV_LN2 / 3.0);
+    const double p45 = fma(-DCB_INV_LN2 / 6.0, r, DCB_INV_LN2 / 5.0);
+    const double p67 = fma(-DCB_INV_LN2 / 8.0, r, DCB_INV_LN2 / 7.0);
+    const double q0 = fma(p23, r2, p01);
+    const double q1 = fma(p67, r2, p45);
+    return fma(q1, r4, q0) * r;
 }
 
 // log2 of a positive, normal double
@@ -58,7 +72,7 @@ __device__ __forceinline__ double dcb_log2(const MathTables *t, double x) {
     const double r = fma(m, t->inv[j], -1.0);
     // (double)e without a conversion instruction: 2^52 + 2^31 + e, minus the same constant
     const double ef = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;
-    return ef + (t->l2c[j] + dcb_log2_1p_small(r));
+    return (ef + t->l2c[j]) + dcb_log2_1p_small(r);
 }
 
 // 2^y for |y| < 1000 (result stays a normal double)
@@ -68,13 +82,12 @@ __device__ __forceinline__ double dcb_exp2(const MathTables *t, double y) {
     const int k = __double2loint(kd);
     const double f = fma(kd - magic, -0.0625, y);         // exact: |f| <= 1/32
     const double z = f * DCB_LN2;
-    double p = 1.0 / 720.0;
-    p = fma(p, z, 1.0 / 120.0);
-    p = fma(p, z, 1.0 / 24.0);
-    p = fma(p, z, 1.0 / 6.0);
-    p = fma(p, z, 0.5);
-    p = fma(p, z, 1.0);
-    p = fma(p, z, 1.0);
+    const double z2 = z * z;
+    const double p01 = 1.0 + z;
+    const double p23 = fma(1.0 / 6.0, z, 0.5);
+    const double p45 = fma(1.0 / 120.0, z, 1.0 / 24.0);
+    const double q1 = fma(1.0 / 720.0, z2, p45);
+    const double p = fma(fma(q1, z2, p23), z2, p01);
     const double v = t->ex2[k & 15] * p;
     return __hiloint2double(__double2hiint(v) + ((k >> 4) << 20), __double2loint(v));
 }

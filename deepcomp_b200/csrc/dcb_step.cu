@@ -6,17 +6,30 @@
 //
 // Mapping.  A CTA owns E consecutive envs; thread t owns UE slot t of the CTA's E*N UEs, which are contiguous in
 // every [K][N] state slab, so state loads / reward stores are perfectly coalesced.  The per-UE state (position,
-// waypoint, pause counter, connection bitmask, EWMA rate) stays in registers for all T steps.  Each thread walks
-// its M UE x BS pairs serially; the per-BS reductions over UEs (connected count, sum of inverse rates, sum of
-// priorities, arg-max rate, sum of utilities) go through a dense [E*N][M|1] fp64 matrix in shared memory that
-// S lanes per (env, BS) pair column-sum and combine with warp shuffles, in a fixed order (deterministic results).
-// The observation tile of the CTA is staged in shared memory and written out with coalesced 16-byte stores.
+// waypoint, pause counter, connection bitmask, EWMA rate) stays in registers for all T steps.
+//
+// Step structure (one iteration of the fused loop, after the first):
+//   1. pre-move rates from the aggregates computed during the PREVIOUS step's observe phase (the UE positions of
+//      "after move t" and "before move t+1" are the same; only the action's one toggled link differs, so the
+//      reducer produces both sets of per-BS aggregates in one pass)            base.py:446, station.py:152-220
+//   2. move, drop out-of-range links, EWMA                                     user.py:148-188, movement.py:132-181
+//   3. dense pair loop over the M base stations: squared distance, in-range bit, normalised SNR -> obs tile
+//      (fp32, see below); sparse loop over the (few) connected links: fp64 SNR -> unshared rate -> link value
+//      -> matrix X and per-(env, BS) UE bitsets                               variants.py:271-303, user.py:190-229
+//   4. reduce per (env, BS) over the CONNECTED UEs only (bitset walk): count / sum of link values / arg-max, for
+//      the current mask and for the next step's mask; fixed order (deterministic)
+//   5. post-move rates -> utility; per-BS utility sums; observation tile + rewards; coalesced tile write-out
+// The first step of a launch (and a step that starts with an episode reset) has no aggregates to inherit and
+// computes them stand-alone.
 //
 // Arithmetic.  Positions and every range decision are fp64 with the reference's operation order (no FMA
 // contraction: the library is built with --fmad=false; the one FMA the reference has, inside np.linalg.norm, is
-// explicit), so trajectories, connection masks and lost-connection counts are bit-exact.  SNR / rate / utility are
-// fp64 through the table-driven log2 / exp2 of dcb_math.cuh (<= 1e-13 relative to the reference's libm chain); a
-// UE closer than 1 m to a BS -- where the reference's `distance + EPSILON` matters -- takes the libm path.
+// explicit), so trajectories, connection masks and lost-connection counts are bit-exact.  Everything that feeds
+// rates, utilities and rewards is fp64 through the table-driven log2 / exp2 of dcb_math.cuh (<= 1e-13 relative to
+// the reference's libm chain); a UE closer than ~1 m to a BS -- where the reference's `distance + EPSILON` matters
+// -- takes the libm path.  The observation entry 'dr' = snr_b / max_b snr_b (variants.py:276-284) is a float32
+// output that feeds nothing else; it is evaluated as (d2min/d2_b)^h in fp32 (q * sqrt(q) * 2^((h - 1.5) log2 q),
+// MUFU lg2 / ex2 / rcp / sqrt), <= 1e-6 relative against the reference (north star: 1e-5).
 #include <math_constants.h>
 
 #include "dcb_internal.h"
@@ -25,9 +38,10 @@
 namespace {
 
 struct SmemLayout {
-    int off_tab, off_a, off_b, off_sum_pre, off_sum_post, off_usum, off_umin, off_fues, off_futil, off_su, off_srb,
-        off_smask, off_env_rew, off_env_sumu, off_bsx, off_bsy, off_vel, off_cnt_pre, off_arg_pre, off_cnt_post,
-        off_arg_post, off_share;
+    int off_tab, off_stage, off_x, off_sum_pre, off_sum_post, off_usum, off_umin, off_fues, off_futil, off_su,
+        off_srb, off_smask, off_env_rew, off_env_sumu, off_bsx, off_bsy, off_vel, off_cnt_pre, off_arg_pre,
+        off_cnt_post, off_arg_post, off_bits, off_share;
+    int nbits;   // words per bitset
     int total;
 };
 
@@ -35,7 +49,7 @@ __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
 __host__ __device__ inline int obs_width(int kind, int M) { return kind == DCB_KIND_CENTRAL ? 2 * M + 1 : 4 * M + 1; }
 
-// Row stride (in doubles) of the [E*N][M] matrices: odd, so that the 16 lanes of one 64-bit shared-memory access
+// Row stride (in doubles) of the [E*N][M] link matrix: odd, so that the 16 lanes of one 64-bit shared-memory access
 // phase (consecutive UEs, same BS) hit 16 different bank pairs.
 __host__ __device__ inline int row_stride(int M) { return M | 1; }
 
@@ -44,10 +58,8 @@ __host__ __device__ inline SmemLayout smem_layout(int kind, int N, int M, int E)
     const int EN = E * N, EM = E * M;
     int o = 0;
     L.off_tab = o;      o += (int)sizeof(MathTables);                // 3 x 128 B: one bank row per table
-    const int stage = EN * obs_width(kind, M) * 4;
-    const int amat = EN * row_stride(M) * 8;
-    L.off_a = o;        o += align16(stage > amat ? stage : amat);   // matrix A, later the obs staging tile
-    L.off_b = o;        o += align16(amat);
+    L.off_stage = o;    o += align16(EN * obs_width(kind, M) * 4);   // float obs tile of the CTA
+    L.off_x = o;        o += align16(EN * row_stride(M) * 8);        // link values of connected links
     L.off_sum_pre = o;  o += align16(EM * 8);
     L.off_sum_post = o; o += align16(EM * 8);
     L.off_usum = o;     o += align16(EM * 8);
@@ -66,6 +78,8 @@ __host__ __device__ inline SmemLayout smem_layout(int kind, int N, int M, int E)
     L.off_arg_pre = o;  o += align16(EM * 4);
     L.off_cnt_post = o; o += align16(EM * 4);
     L.off_arg_post = o; o += align16(EM * 4);
+    L.nbits = EM * ((N + 31) / 32);
+    L.off_bits = o;     o += align16(3 * L.nbits * 4);               // UE bitsets per (env, BS): post, pre, fresh
     L.off_share = o;    o += align16(M * 4);
     L.total = o;
     return L;
@@ -78,22 +92,30 @@ __device__ __forceinline__ double dist2(double ax, double ay, double bx, double 
     return dx * dx + dy * dy;
 }
 
-// station.py:110-127 verbatim with libm: used when the UE is within 1 m of the BS (distance + EPSILON matters)
+// station.py:110-138 verbatim with libm, for a UE within ~1 m of the BS (distance + EPSILON matters; snr > 1/32)
 __device__ __noinline__ double snr_of_d2_libm(double c1, double c2, double d2) {
     const double d = sqrt(d2);
     const double pl = c1 + c2 * log10(d + DCB_EPSILON);
     const double signal = pow(10.0, (DCB_TX_POWER - pl) / 10.0);
     return signal / DCB_NOISE;
 }
+__device__ __noinline__ double rate_of_d2_libm(double c1, double c2, double d2) {
+    return DCB_BW * log2(1.0 + snr_of_d2_libm(c1, c2, d2));
+}
 
-// SNR = 10^((30 - c1 - c2 log10(d)) / 10) / 1e-9 = 2^(c0 - h log2(d^2)),  h = c2 / 20
+#define DCB_NEAR_D2 1.1   // below this squared distance the verbatim libm path is used (snr(1.1) = 0.0275 < 1/32)
+
+// SNR = 10^((30 - c1 - c2 log10(d)) / 10) / 1e-9 = 2^(c0 - h log2(d^2)),  h = c2 / 20      (station.py:110-127)
 __device__ __forceinline__ double snr_of_d2(const DevParams &p, const MathTables *tab, double d2) {
-    if (d2 < 1.0) return snr_of_d2_libm(p.c1, p.c2, d2);
+    if (d2 < DCB_NEAR_D2) return snr_of_d2_libm(p.c1, p.c2, d2);
     return dcb_exp2(tab, fma(-p.snr_h, dcb_log2(tab, d2), p.snr_c0));
 }
 
-__device__ __forceinline__ double rate_unshared(const MathTables *tab, double snr) {
-    return DCB_BW * dcb_log2_1p(tab, snr);   // station.py:129-138
+// Unshared rate bw * log2(1 + snr) (station.py:129-138); on the fast path snr < 1/32 -> series in fl(1 + snr) - 1
+__device__ __forceinline__ double rate_of_d2(const DevParams &p, const MathTables *tab, double d2) {
+    if (d2 < DCB_NEAR_D2) return rate_of_d2_libm(p.c1, p.c2, d2);
+    const double s = dcb_exp2(tab, fma(-p.snr_h, dcb_log2(tab, d2), p.snr_c0));
+    return DCB_BW * dcb_log2_1p_small((1.0 + s) - 1.0);
 }
 
 __device__ __forceinline__ double log_utility(const MathTables *tab, double dr) {
@@ -104,76 +126,123 @@ __device__ __forceinline__ double log_utility(const MathTables *tab, double dr) 
     return fmin(fmax(u, DCB_MIN_UTILITY), DCB_MAX_UTILITY);
 }
 
-// value a connected link contributes to its BS's reduction, by sharing model (station.py:170-195)
-__device__ __forceinline__ double link_value(int model, double r0, double ewma) {
-    if (model == DCB_SHARE_RATE_FAIR) return 1.0 / r0;                               // :178
-    if (model == DCB_SHARE_PROPORTIONAL_FAIR) return r0 / (ewma + DCB_EPSILON);      // :150 (alpha = beta = 1)
-    return r0;                                                                       // resource-fair / max-cap
+// Value a connected link contributes to its BS's reduction, by sharing model (station.py:170-195):
+// resource-fair / max-cap: r0; rate-fair: 1/r0 (:178); proportional-fair: priority r0/(ewma + eps) (:150)
+__device__ __forceinline__ double link_value(int model, double r0, double inv_ewma_eps) {
+    if (model == DCB_SHARE_RATE_FAIR) return dcb_rcp(r0);
+    if (model == DCB_SHARE_PROPORTIONAL_FAIR) return r0 * inv_ewma_eps;
+    return r0;
+}
+
+// Shared rate of one link from its value and the BS aggregates (station.py:152-202)
+__device__ __forceinline__ double shared_rate(int model, double v, int cnt, double sum, int arg, int i,
+                                              double ewma_eps) {
+    if (model == DCB_SHARE_RESOURCE_FAIR) return v * dcb_rcp((double)cnt);                      // :173
+    if (model == DCB_SHARE_RATE_FAIR) return dcb_rcp(sum);                                      // :180
+    if (model == DCB_SHARE_MAX_CAP) return arg == i ? v : 0.0;                                  // :184-187
+    return v * dcb_rcp(sum + DCB_EPSILON) * (v * ewma_eps);                                     // :194-195, r0 = v (ewma + eps)
+}
+
+// fp32 normalised SNR (variants.py:276-284): (d2min / d2)^h with h = c2/20 = 1.5 + hr
+__device__ __forceinline__ float norm_snr_f32(float d2, float d2min, float hr) {
+    float rc, lg, sq, ex;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(d2));
+    const float q = d2min * rc;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(q));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(q));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(hr * lg));
+    return d2 == d2min ? 1.0f : fminf(q * sq * ex, 1.0f);   // the closest BS is exactly 1 (variants.py:284)
 }
 
 // ------------------------------------------------------------------------------------------------ reductions
-// Column reduction of the dense [E*N][MS] matrix A: for every (env, BS) pair count the non-zero entries, sum them
-// and (max-cap only) find the first arg-max.  S lanes per pair, fixed combination order.
-__device__ __forceinline__ void reduce_links(const double *A, int N, int M, int MS, int n_env, int S, bool want_arg,
-                                             int *cnt, double *sum, int *arg) {
+// For every (env, BS) pair walk the bitset of connected UEs: count, sum of link values X[ue][bs], first arg-max
+// (max-cap only).  Done for two bitsets (current masks -> *_a, next step's masks -> *_b).  S lanes per pair take the
+// 32-UE words round-robin; fixed combination order -> deterministic.
+__device__ __forceinline__ void reduce_links(const double *X, const unsigned *bits_a, const unsigned *bits_b, int N,
+                                             int M, int MS, int n_env, int S, bool want_arg, int *cnt_a, double *sum_a,
+                                             int *arg_a, int *cnt_b, double *sum_b, int *arg_b) {
     const int R = n_env * M;
+    const int NW = (N + 31) >> 5;
     const int ppp = blockDim.x / S;
     const int seg = threadIdx.x & (S - 1);
-    const int chunk = (N + S - 1) / S;
     for (int base = 0; base < R; base += ppp) {
         const int pair = base + threadIdx.x / S;
         const bool ok = pair < R;
-        int c = 0, bi = 0x7fffffff;
-        double s = 0.0, best = 0.0;
+        int c0 = 0, c1 = 0, a0 = 0x7fffffff, a1 = 0x7fffffff;
+        double s0 = 0.0, s1 = 0.0, b0 = 0.0, b1 = 0.0;
         if (ok) {
             const int le = pair / M, b = pair - le * M;
-            const int i0 = seg * chunk;
-            const int i1 = min(N, i0 + chunk);
-            const double *col = A + (size_t)(le * N) * MS + b;
-#pragma unroll 4
-            for (int i = i0; i < i1; i++) {
-                const double v = col[(size_t)i * MS];
-                c += (v != 0.0);
-                s += v;
-                if (want_arg && v > best) { best = v; bi = i; }
+            const double *col = X + (size_t)(le * N) * MS + b;
+            for (int w = seg; w < NW; w += S) {
+                unsigned wa = bits_a[pair * NW + w];
+                const unsigned wb = bits_b[pair * NW + w];
+                c0 += __popc(wa);
+                c1 += __popc(wb);
+                unsigned both = wa | wb;
+                while (both) {
+                    const int j = __ffs(both) - 1;
+                    both &= both - 1;
+                    const int i = (w << 5) + j;
+                    const double v = col[i * MS];
+                    if ((wa >> j) & 1u) {
+                        s0 += v;
+                        if (want_arg && v > b0) { b0 = v; a0 = i; }
+                    }
+                    if ((wb >> j) & 1u) {
+                        s1 += v;
+                        if (want_arg && v > b1) { b1 = v; a1 = i; }
+                    }
+                }
             }
         }
         for (int off = S >> 1; off > 0; off >>= 1) {
-            c += __shfl_xor_sync(0xffffffffu, c, off);
-            s += __shfl_xor_sync(0xffffffffu, s, off);
+            c0 += __shfl_xor_sync(0xffffffffu, c0, off);
+            c1 += __shfl_xor_sync(0xffffffffu, c1, off);
+            s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, off);
             if (want_arg) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                double ob = __shfl_xor_sync(0xffffffffu, b0, off);
+                int oi = __shfl_xor_sync(0xffffffffu, a0, off);
+                if (ob > b0 || (ob == b0 && oi < a0)) { b0 = ob; a0 = oi; }
+                ob = __shfl_xor_sync(0xffffffffu, b1, off);
+                oi = __shfl_xor_sync(0xffffffffu, a1, off);
+                if (ob > b1 || (ob == b1 && oi < a1)) { b1 = ob; a1 = oi; }
             }
         }
-        if (ok && seg == 0) { cnt[pair] = c; sum[pair] = s; arg[pair] = bi; }
+        if (ok && seg == 0) {
+            cnt_a[pair] = c0; sum_a[pair] = s0; arg_a[pair] = a0;
+            cnt_b[pair] = c1; sum_b[pair] = s1; arg_b[pair] = a1;
+        }
     }
 }
 
 // Per-BS total utility (station.py:63-69) -> usum, the two per-BS observation entries (variants.py:296-299,
-// station.py:71-76) -> f_ues, f_util; optional masked min (station.py:78-83).
-__device__ __forceinline__ void reduce_utility(const double *A, const unsigned long long *smask, const double *su,
-                                               const int *cnt, int N, int M, int MS, int n_env, int S, bool want_min,
-                                               double *usum, double *umin, double *f_ues, double *f_util) {
+// station.py:71-76) -> f_ues, f_util; min (station.py:78-83) -> umin.
+__device__ __forceinline__ void reduce_utility(const unsigned *bits, const double *su, const int *cnt, int N, int M,
+                                               int n_env, int S, bool want_min, double *usum, double *umin,
+                                               double *f_ues, double *f_util) {
     const int R = n_env * M;
+    const int NW = (N + 31) >> 5;
     const int ppp = blockDim.x / S;
     const int seg = threadIdx.x & (S - 1);
-    const int chunk = (N + S - 1) / S;
+    const double inv_n = 1.0 / (double)N;
     for (int base = 0; base < R; base += ppp) {
         const int pair = base + threadIdx.x / S;
         const bool ok = pair < R;
         double s = 0.0, mn = DCB_MAX_UTILITY;
         if (ok) {
-            const int le = pair / M, b = pair - le * M;
-            const int i0 = seg * chunk;
-            const int i1 = min(N, i0 + chunk);
-            const double *col = A + (size_t)(le * N) * MS + b;
-#pragma unroll 4
-            for (int i = i0; i < i1; i++) s += col[(size_t)i * MS];
-            if (want_min)
-                for (int i = i0; i < i1; i++)
-                    if ((smask[le * N + i] >> b) & 1ull) mn = fmin(mn, su[le * N + i]);
+            const int le = pair / M;
+            const double *sue = su + le * N;
+            for (int w = seg; w < NW; w += S) {
+                unsigned wa = bits[pair * NW + w];
+                while (wa) {
+                    const int j = __ffs(wa) - 1;
+                    wa &= wa - 1;
+                    const double uu = sue[(w << 5) + j];
+                    s += uu;
+                    if (want_min) mn = fmin(mn, uu);
+                }
+            }
         }
         for (int off = S >> 1; off > 0; off >>= 1) {
             s += __shfl_xor_sync(0xffffffffu, s, off);
@@ -183,8 +252,8 @@ __device__ __forceinline__ void reduce_utility(const double *A, const unsigned l
             const int c = cnt[pair];
             usum[pair] = s;
             umin[pair] = mn;
-            f_ues[pair] = (double)c / (double)N;
-            f_util[pair] = (c > 0 ? s / (double)c : 0.0) / DCB_MAX_UTILITY;
+            f_ues[pair] = (double)c * inv_n;                                     // |C_b| / N (variants.py:296)
+            f_util[pair] = c > 0 ? s * dcb_rcp((double)c) * (1.0 / DCB_MAX_UTILITY) : 0.0;
         }
     }
 }
@@ -212,11 +281,11 @@ __global__ void __launch_bounds__(MAXT) dcb_step_kernel(const StepArgs a) {
     const DevParams &p = a.p;
     const int N = p.N, M = p.M, E = p.E, S = p.S;
     const int MS = row_stride(M);
+    const int NW = (N + 31) >> 5;
     const SmemLayout L = smem_layout(p.kind, N, M, E);
     MathTables *tab = reinterpret_cast<MathTables *>(smem + L.off_tab);
-    double *A = reinterpret_cast<double *>(smem + L.off_a);
-    float *stage = reinterpret_cast<float *>(smem + L.off_a);
-    double *B = reinterpret_cast<double *>(smem + L.off_b);
+    float *stage = reinterpret_cast<float *>(smem + L.off_stage);
+    double *X = reinterpret_cast<double *>(smem + L.off_x);
     int *cnt_pre = reinterpret_cast<int *>(smem + L.off_cnt_pre);
     double *sum_pre = reinterpret_cast<double *>(smem + L.off_sum_pre);
     int *arg_pre = reinterpret_cast<int *>(smem + L.off_arg_pre);
@@ -236,6 +305,9 @@ __global__ void __launch_bounds__(MAXT) dcb_step_kernel(const StepArgs a) {
     double *bsy = reinterpret_cast<double *>(smem + L.off_bsy);
     int *share = reinterpret_cast<int *>(smem + L.off_share);
     double *velspec = reinterpret_cast<double *>(smem + L.off_vel);
+    unsigned *bits_post = reinterpret_cast<unsigned *>(smem + L.off_bits);
+    unsigned *bits_pre = bits_post + L.nbits;
+    unsigned *bits_fresh = bits_pre + L.nbits;
 
     const int t = threadIdx.x;
     const int env0 = blockIdx.x * E;
@@ -255,6 +327,7 @@ __global__ void __launch_bounds__(MAXT) dcb_step_kernel(const StepArgs a) {
         share[b] = p.sharing[b];
     }
     for (int j = t; j < N; j += blockDim.x) velspec[j] = p.vel_spec[j];
+    for (int j = t; j < 3 * L.nbits; j += blockDim.x) bits_post[j] = 0u;
 
     // ---- per-UE state -> registers
     double x = 0, y = 0, ewma = 0;
@@ -272,62 +345,80 @@ __global__ void __launch_bounds__(MAXT) dcb_step_kernel(const StepArgs a) {
     }
     __syncthreads();
     const double vfix = valid ? velspec[i] : 0.0;
-    double *Arow = A + (size_t)t * MS;
-    double *Brow = B + (size_t)t * MS;
+    double *Xrow = X + (size_t)t * MS;
+    // obs tile row of this UE: multi [connected(M) | dr(M) | ues_at_bs(M) | util_at_bs(M) | utility(1)] per UE
+    // (variants.py:271-303); central [connected(N*M) | dr(N*M) | utility(N)] per env (central.py:31-57)
+    float *row_conn = central ? stage + (size_t)le * (2 * N * M + N) + i * M : stage + (size_t)t * OW;
+    float *row_dr = central ? row_conn + N * M : row_conn + M;
+    // this UE's bit in the per-(env, BS) bitsets
+    const int bit_word = le * M * NW + (i >> 5);
+    const unsigned bit_val = 1u << (i & 31);
+    const float hr = (float)(p.snr_h - 1.5);
+    const bool dbg_any = a.out.dbg_obs || a.out.dbg_snr;
     const int T = a.T;
     const int n_iter = T > 0 ? T : 1;
+    // mask after the NEXT step's action, prepared during the observe phase (only meaningful when !fresh)
+    unsigned long long mask_next = 0;
 
     for (int step = 0; step < n_iter; step++) {
         const bool last = step == n_iter - 1;
         double rb = 0.0;      // reward before the move (base.py:446)
         int lost = 0;
         if (T > 0) {
-            // ---- episode boundary: MobileEnv.reset before the next step (base.py:169-189)
+            // ---- stand-alone pre phase: first step of the launch or a step that starts with an episode reset
+            bool fresh = step == 0;
             if (valid && p.auto_reset && tk >= p.episode_length) {
+                // MobileEnv.reset before the next step (base.py:169-189)
                 const double2 ps = p.init_pos[u];
                 x = ps.x; y = ps.y;
                 const uint32_t e = p.table[u * p.D];
                 wxy = (e & 0x3fffu) | (((e >> 14) & 0x3fffu) << 16);
                 vpt = (e >> 28) | (1u << 16);
                 mask = 0ull; ewma = 0.0; tk = 0;
+                fresh = true;
             }
-            // ---- apply_ue_actions (base.py:247-282) -> User.connect_to_bs(disconnect=True) (user.py:190-229)
             if (valid) {
-                const int act = a.actions[(size_t)step * p.K * N + u];
-                if (act < 0 || act > M) {
-                    atomicOr(p.err, DCB_ERRBIT_ACTION);
-                } else if (act > 0) {
-                    const int b = act - 1;
-                    const unsigned long long bit = 1ull << b;
-                    if (mask & bit) mask &= ~bit;
-                    else if (dist2(bsx[b], bsy[b], x, y) <= p.thr_d2) mask |= bit;     // can_connect, station.py:222-226
-                }
-                // ---- link values for update_ue_drs_rewards (base.py:315-335) at the pre-move position
-                for (int b = 0; b < M; b++) Arow[b] = 0.0;
-                for (unsigned long long m = mask; m; m &= m - 1) {
-                    const int b = __ffsll((long long)m) - 1;
-                    const double r0 = rate_unshared(tab, snr_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y)));
-                    Arow[b] = link_value(share[b], r0, ewma);
-                    Brow[b] = r0;
+                if (fresh) {
+                    // apply_ue_actions (base.py:247-282) -> User.connect_to_bs(disconnect=True) (user.py:190-229)
+                    const int act = a.actions[(size_t)step * p.K * N + u];
+                    if (act < 0 || act > M) {
+                        atomicOr(p.err, DCB_ERRBIT_ACTION);
+                    } else if (act > 0) {
+                        const int b = act - 1;
+                        const unsigned long long bit = 1ull << b;
+                        if (mask & bit) mask &= ~bit;
+                        else if (dist2(bsx[b], bsy[b], x, y) <= p.thr_d2) mask |= bit;   // can_connect, station.py:222-226
+                    }
+                } else {
+                    mask = mask_next;
                 }
             }
-            __syncthreads();
-            reduce_links(A, N, M, MS, n_env, S, p.has_maxcap, cnt_pre, sum_pre, arg_pre);
-            __syncthreads();
+            if (__syncthreads_or(fresh)) {
+                // some env of this CTA has no inherited aggregates: recompute link values and reduce
+                if (valid) {
+                    const double iee = dcb_rcp(ewma + DCB_EPSILON);
+                    for (unsigned long long m = mask; m; m &= m - 1) {
+                        const int b = __ffsll((long long)m) - 1;
+                        Xrow[b] = link_value(share[b], rate_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y)), iee);
+                        atomicOr(&bits_fresh[bit_word + b * NW], bit_val);
+                    }
+                }
+                __syncthreads();
+                reduce_links(X, bits_fresh, bits_fresh, N, M, MS, n_env, S, p.has_maxcap, cnt_post, sum_post, arg_post,
+                             cnt_pre, sum_pre, arg_pre);
+                __syncthreads();
+                for (int j = t; j < L.nbits; j += blockDim.x) bits_fresh[j] = 0u;
+            }
             if (valid) {
-                // ---- Basestation.data_rate_shared (station.py:152-202) per connected link; ue.bs_dr cache in Brow
+                // ---- update_ue_drs_rewards (base.py:315-335): Basestation.data_rate_shared (station.py:152-202) per
+                // connected link; the ue.bs_dr cache goes back into Xrow
+                const double ee = ewma + DCB_EPSILON;
                 double dr = 0.0;
                 for (unsigned long long m = mask; m; m &= m - 1) {
                     const int b = __ffsll((long long)m) - 1;
                     const int pr = le * M + b;
-                    const int model = share[b];
-                    const double r0 = Brow[b];
-                    double r;
-                    if (model == DCB_SHARE_RESOURCE_FAIR) r = r0 / (double)cnt_pre[pr];
-                    else if (model == DCB_SHARE_RATE_FAIR) r = 1.0 / sum_pre[pr];
-                    else if (model == DCB_SHARE_MAX_CAP) r = (arg_pre[pr] == i) ? r0 : 0.0;
-                    else r = Arow[b] / (sum_pre[pr] + DCB_EPSILON) * r0;
-                    Brow[b] = r;
+                    const double r = shared_rate(share[b], Xrow[b], cnt_pre[pr], sum_pre[pr], arg_pre[pr], i, ee);
+                    Xrow[b] = r;
                     dr += r;                                                           // user.py:64-69
                 }
                 // ---- calc_reward (base.py:158-167), penalties are identically 0 (base.py:257)
@@ -371,7 +462,7 @@ __global__ void __launch_bounds__(MAXT) dcb_step_kernel(const StepArgs a) {
                 double keep = 0.0;
                 for (unsigned long long m = mask; m; m &= m - 1) {
                     const int b = __ffsll((long long)m) - 1;
-                    if (dist2(bsx[b], bsy[b], x, y) <= p.thr_d2) keep += Brow[b];
+                    if (dist2(bsx[b], bsy[b], x, y) <= p.thr_d2) keep += Xrow[b];
                     else { mask &= ~(1ull << b); lost++; }
                 }
                 ewma = 0.9 * keep + (1 - 0.9) * ewma;
@@ -379,90 +470,112 @@ __global__ void __launch_bounds__(MAXT) dcb_step_kernel(const StepArgs a) {
             }
         }
         // =========================== observe the (post-move) state ===========================
-        double mx = 0.0;
         unsigned long long inrange = 0ull;
+        mask_next = mask;
         if (valid) {
-            // SNR of every pair at the current position (variants.py:278) -> Brow; in-range set (multi_agent.py:60);
-            // link values at the new position for update_ue_drs_rewards(update_only=True) (base.py:451) -> Arow
+            // dense pass A: squared distances (fp64, exact range decision multi_agent.py:60 / station.py:222-226),
+            // parked in the tile as float for pass B
+            double d2min = CUDART_INF;
 #pragma unroll 2
             for (int b = 0; b < M; b++) {
                 const double d2 = dist2(bsx[b], bsy[b], x, y);
-                const double s = snr_of_d2(p, tab, d2);
-                Brow[b] = s;
-                mx = fmax(mx, s);
+                d2min = fmin(d2min, d2);
                 if (d2 <= p.thr_d2) inrange |= 1ull << b;
-                double v = 0.0;
-                if ((mask >> b) & 1ull) v = link_value(share[b], rate_unshared(tab, s), ewma);
-                Arow[b] = v;
+                row_dr[b] = (float)d2;
+            }
+            // dense pass B: 'dr' = snr_b / max_b snr_b (variants.py:276-284) = (d2min / d2_b)^h
+            if (d2min >= DCB_NEAR_D2) {
+                const float d2minf = (float)d2min;
+#pragma unroll 2
+                for (int b = 0; b < M; b++) row_dr[b] = norm_snr_f32(row_dr[b], d2minf, hr);
+            } else {
+                const double inv_max = dcb_rcp(snr_of_d2(p, tab, d2min));
+                for (int b = 0; b < M; b++)
+                    row_dr[b] = (float)(snr_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y)) * inv_max);
+            }
+            // the next step's action toggles one link (user.py:190-229): known now, folded into this step's reduction
+            if (T > 0 && !last) {
+                const int act = a.actions[(size_t)(step + 1) * p.K * N + u];
+                if (act < 0 || act > M) {
+                    atomicOr(p.err, DCB_ERRBIT_ACTION);
+                } else if (act > 0) {
+                    const unsigned long long bit = 1ull << (act - 1);
+                    if ((mask & bit) || (inrange & bit)) mask_next = mask ^ bit;
+                }
+            }
+            smask[t] = mask;
+            // sparse pass: link values at the new position for update_ue_drs_rewards(update_only=True) (base.py:451)
+            // and for the next step's pre-move update -> X; UE bitsets per (env, BS)
+            const double iee = dcb_rcp(ewma + DCB_EPSILON);
+            for (unsigned long long m = mask | mask_next; m; m &= m - 1) {
+                const int b = __ffsll((long long)m) - 1;
+                Xrow[b] = link_value(share[b], rate_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y)), iee);
+                if ((mask >> b) & 1ull) atomicOr(&bits_post[bit_word + b * NW], bit_val);
+                if ((mask_next >> b) & 1ull) atomicOr(&bits_pre[bit_word + b * NW], bit_val);
+            }
+            if (last && dbg_any) {
+                // test taps: fp64 SNR of every pair (station.py:122-127); the fp64 copy of 'dr' is the fp32 value
+                double *dobs = a.out.dbg_obs ? (central ? a.out.dbg_obs + (size_t)k * (2 * N * M + N) + N * M + i * M
+                                                        : a.out.dbg_obs + (size_t)u * OW + M)
+                                             : nullptr;
+                for (int b = 0; b < M; b++) {
+                    if (dobs) dobs[b] = (double)row_dr[b];
+                    if (a.out.dbg_snr) a.out.dbg_snr[u * M + b] = snr_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y));
+                }
             }
         }
         __syncthreads();
-        reduce_links(A, N, M, MS, n_env, S, p.has_maxcap, cnt_post, sum_post, arg_post);
+        reduce_links(X, bits_post, bits_pre, N, M, MS, n_env, S, p.has_maxcap, cnt_post, sum_post, arg_post, cnt_pre,
+                     sum_pre, arg_pre);
         __syncthreads();
         double dr = 0.0, util = 0.0;
         if (valid) {
+            const double ee = ewma + DCB_EPSILON;
             for (unsigned long long m = mask; m; m &= m - 1) {
                 const int b = __ffsll((long long)m) - 1;
                 const int pr = le * M + b;
-                const int model = share[b];
-                const double v = Arow[b];
-                double r;
-                if (model == DCB_SHARE_RESOURCE_FAIR) r = v / (double)cnt_post[pr];
-                else if (model == DCB_SHARE_RATE_FAIR) r = 1.0 / sum_post[pr];
-                else if (model == DCB_SHARE_MAX_CAP) r = (arg_post[pr] == i) ? v : 0.0;
-                else r = v / (sum_post[pr] + DCB_EPSILON) * rate_unshared(tab, Brow[b]);
+                const double r = shared_rate(share[b], Xrow[b], cnt_post[pr], sum_post[pr], arg_post[pr], i, ee);
                 if (last && a.out.dbg_link_rate) a.out.dbg_link_rate[u * M + b] = r;
                 dr += r;
             }
             util = log_utility(tab, dr);                                               // user.py:76-92
             su[t] = util;
             srb[t] = rb;
-            smask[t] = mask;
-            if (!central)
-                for (int b = 0; b < M; b++) Arow[b] = ((mask >> b) & 1ull) ? util : 0.0;
         }
         __syncthreads();
         if (!central)
-            reduce_utility(A, smask, su, cnt_post, N, M, MS, n_env, S, p.reward == DCB_REWARD_MIN, usum, umin, f_ues,
+            reduce_utility(bits_post, su, cnt_post, N, M, n_env, S, p.reward == DCB_REWARD_MIN, usum, umin, f_ues,
                            f_util);
         if (central && T > 0) reduce_env(srb, N, n_env, p.reward == DCB_REWARD_MIN ? 2 : 0, env_rew);
         if (a.out.sum_utility || a.out.dbg_sum_utility) reduce_env(su, N, n_env, 0, env_sumu);
         __syncthreads();
-        // ---- observation row -> staging tile (A is dead now), rewards and per-UE outputs -> global
+        // the bitsets have been consumed: clear them for the next step (separated from the next atomics by 2 barriers)
+        for (int j = t; j < 2 * L.nbits; j += blockDim.x) bits_post[j] = 0u;
+        // ---- rest of the observation row -> tile, rewards and per-UE outputs -> global
         if (valid) {
             double *dobs = (last && a.out.dbg_obs) ? a.out.dbg_obs : nullptr;
             const double un = util / DCB_MAX_UTILITY;                                  // variants.py:287
-            const double inv_mx = mx == 0.0 ? 0.0 : 1.0 / mx;                          // variants.py:279-284
             if (central) {
-                // central.py:31-57: [connected(N*M) | dr(N*M) | utility(N)] per env
-                float *row = stage + (size_t)le * (2 * N * M + N);
                 double *drow = dobs ? dobs + (size_t)k * (2 * N * M + N) : nullptr;
                 for (int b = 0; b < M; b++) {
-                    const double c = (double)((mask >> b) & 1ull);
-                    const double r = Brow[b] * inv_mx;
-                    row[i * M + b] = (float)c;
-                    row[N * M + i * M + b] = (float)r;
-                    if (drow) { drow[i * M + b] = c; drow[N * M + i * M + b] = r; }
+                    const float c = (float)((unsigned)(mask >> b) & 1u);
+                    row_conn[b] = c;
+                    if (drow) drow[i * M + b] = c;
                 }
-                row[2 * N * M + i] = (float)un;
+                stage[(size_t)le * (2 * N * M + N) + 2 * N * M + i] = (float)un;
                 if (drow) drow[2 * N * M + i] = un;
             } else {
-                // variants.py:271-303: [connected(M) | dr(M) | ues_at_bs(M) | util_at_bs(M) | utility(1)] per UE
-                float *row = stage + (size_t)t * OW;
                 double *drow = dobs ? dobs + (size_t)u * OW : nullptr;
+                const double *fu = f_ues + le * M, *fa = f_util + le * M;
                 for (int b = 0; b < M; b++) {
-                    const int pr = le * M + b;
-                    const double c = (double)((mask >> b) & 1ull);
-                    const double r = Brow[b] * inv_mx;
-                    const double ab = f_ues[pr], ub = f_util[pr];
-                    row[b] = (float)c; row[M + b] = (float)r; row[2 * M + b] = (float)ab; row[3 * M + b] = (float)ub;
-                    if (drow) { drow[b] = c; drow[M + b] = r; drow[2 * M + b] = ab; drow[3 * M + b] = ub; }
+                    const float c = (float)((unsigned)(mask >> b) & 1u);
+                    const double ab = fu[b], ub = fa[b];
+                    row_conn[b] = c; row_conn[2 * M + b] = (float)ab; row_conn[3 * M + b] = (float)ub;
+                    if (drow) { drow[b] = c; drow[2 * M + b] = ab; drow[3 * M + b] = ub; }
                 }
-                row[4 * M] = (float)un;
+                row_conn[4 * M] = (float)un;
                 if (drow) drow[4 * M] = un;
             }
-            if (last && a.out.dbg_snr)
-                for (int b = 0; b < M; b++) a.out.dbg_snr[u * M + b] = Brow[b];
             if (a.out.curr_dr) a.out.curr_dr[(size_t)step * a.out.curr_dr_stride + u] = (float)dr;
             if (a.out.utility) a.out.utility[(size_t)step * a.out.utility_stride + u] = (float)util;
             if (last && a.out.dbg_curr_dr) a.out.dbg_curr_dr[u] = dr;
@@ -512,7 +625,7 @@ __global__ void __launch_bounds__(MAXT) dcb_step_kernel(const StepArgs a) {
             }
         }
         __syncthreads();
-        // ---- staging tile -> global observation buffer (contiguous span of this CTA, coalesced)
+        // ---- obs tile -> global observation buffer (contiguous span of this CTA, coalesced streaming stores)
         if (a.out.obs) {
             const size_t per_env = central ? (size_t)(2 * N * M + N) : (size_t)N * OW;
             float *dst = a.out.obs + (size_t)step * a.out.obs_stride + (size_t)env0 * per_env;
