@@ -92,33 +92,36 @@ struct dcb_env {
 
 namespace {
 
-// Envs per CTA: keep CTAs at <= 256 threads when N allows it, waste few lanes in the last warp and spread the
-// grid evenly over the SMs (grid sizes just above a multiple of the SM count leave most SMs half idle).
+// Envs per CTA.  The fused kernel wants every CTA resident at once (one wave), few idle lanes in the last warp of
+// each group, an even spread over the SMs, and -- when the batch is large enough to need several waves -- as many
+// resident warps as registers and shared memory allow.
 int choose_envs_per_cta(int K, int N, int M, int kind, int num_sms, size_t smem_cap) {
     const char *ov = getenv("DCB_ENVS_PER_CTA");
     if (ov && atoi(ov) > 0) return atoi(ov);
     int best_e = 1;
     double best_score = -1.0;
-    const int max_threads = N <= 256 ? 256 : (N <= 512 ? 512 : 1024);
-    for (int E = 1; E * N <= max_threads && E <= K; E++) {
+    const int max_group = N <= 256 ? 384 : 512;     // threads per warp group; the CTA has two groups
+    for (int E = 1; E * N <= max_group && E <= K; E++) {
         const size_t sm = dcb_step_smem_bytes(kind, N, M, E);
         if (sm > smem_cap) break;
-        const int threads = (E * N + 31) / 32 * 32;
-        const double lane_util = (double)(E * N) / threads;
-        const int grid = (K + E - 1) / E;
+        const int group = (E * N + 31) / 32 * 32;
+        const int threads = 2 * group;
+        const int regs = dcb_step_regs_per_thread(threads);
         int per_sm = (int)(smem_cap / sm);
-        const int by_threads = 2048 / threads;
-        if (by_threads < per_sm) per_sm = by_threads;
-        if (per_sm < 1) per_sm = 1;
-        const int waves_slots = num_sms * per_sm;
-        const int waves = (grid + waves_slots - 1) / waves_slots;
-        // fraction of SM-time doing work: total CTAs / (CTA slots occupied by the busiest SM over all waves)
-        const int busiest = (grid + num_sms - 1) / num_sms;
-        const double balance = (double)grid / ((double)busiest * num_sms);
+        if (2048 / threads < per_sm) per_sm = 2048 / threads;
+        if (65536 / (regs * threads) < per_sm) per_sm = 65536 / (regs * threads);
+        if (per_sm < 1) continue;
+        const int grid = (K + E - 1) / E;
+        const long slots = (long)num_sms * per_sm;
+        const long waves = (grid + slots - 1) / slots;
+        const double slot_eff = (double)grid / (double)(waves * slots);          // CTA slots doing work
+        const double lane_util = (double)(E * N) / group;
         const double env_util = (double)K / ((double)grid * E);
-        // mild preference for larger CTAs (fewer barriers per UE of work, better reducer utilisation)
-        const double size_bonus = 1.0 + 0.02 * (threads / 32);
-        const double score = lane_util * balance * env_util * size_bonus / (1.0 + 0.0 * waves);
+        double resident = (double)grid / num_sms;
+        if (resident > per_sm) resident = per_sm;
+        const double warps = resident * threads / 32.0;
+        const double occ = warps >= 32.0 ? 1.0 : 0.5 + 0.5 * warps / 32.0;       // latency hiding saturates
+        const double score = lane_util * env_util * slot_eff * occ;
         if (score > best_score) { best_score = score; best_e = E; }
     }
     return best_e;
@@ -191,7 +194,8 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     const int K = cfg->num_envs, N = cfg->n_ue, M = cfg->n_bs;
     if (K < 1 || N < 1 || M < 1) return fail(DCB_ERR_INVALID_ARG, "num_envs, n_ue, n_bs must be >= 1");
     if (M > 64) return fail(DCB_ERR_UNSUPPORTED, "n_bs = %d > 64 (connection mask is one 64-bit word per UE)", M);
-    if (N > 1024) return fail(DCB_ERR_UNSUPPORTED, "n_ue = %d > 1024 (one thread per UE, one CTA per env)", N);
+    if (N > 512)
+        return fail(DCB_ERR_UNSUPPORTED, "n_ue = %d > 512 (two threads per UE -- physics + observer -- one CTA per env)", N);
     if (cfg->kind != DCB_KIND_CENTRAL && cfg->kind != DCB_KIND_MULTI) return fail(DCB_ERR_INVALID_ARG, "bad kind");
     if (cfg->reward < DCB_REWARD_AVG || cfg->reward > DCB_REWARD_MIN)
         return fail(DCB_ERR_INVALID_ARG, "bad reward aggregation %d", cfg->reward);   // central.py:73, multi_agent.py:92
@@ -243,17 +247,18 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
                     dcb_step_smem_bytes(cfg->kind, N, M, 1), smem_cap);
     }
     const int E = choose_envs_per_cta(K, N, M, cfg->kind, prop.multiProcessorCount, smem_cap);
-    if (E * N > 1024 || dcb_step_smem_bytes(cfg->kind, N, M, E) > smem_cap) {
+    if (E * N > 512 || dcb_step_smem_bytes(cfg->kind, N, M, E) > smem_cap) {
         delete env;
         return fail(DCB_ERR_INVALID_ARG, "DCB_ENVS_PER_CTA = %d does not fit", E);
     }
-    env->threads = (E * N + 31) / 32 * 32;
+    const int group = (E * N + 31) / 32 * 32;      // threads per warp group (physics / observers)
+    env->threads = 2 * group;
     env->grid = (K + E - 1) / E;
     env->smem = dcb_step_smem_bytes(cfg->kind, N, M, E);
     // reducer lanes per (env, BS) pair: one per 32-UE bitset word, power of two, while the pairs still fit the CTA
     int S = 1;
     const int NW = (N + 31) / 32;
-    while (S < NW && S * 2 <= 32 && E * M * S * 2 <= env->threads) S *= 2;
+    while (S < NW && S * 2 <= 32 && E * M * S * 2 <= group) S *= 2;
 
     const size_t KN = (size_t)K * N;
     // pause_duration + 1 steps is the shortest possible redraw cycle (movement.py:168-181); +2 = entry 0 and slack

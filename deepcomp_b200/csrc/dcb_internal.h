@@ -91,3 +91,4 @@ cudaError_t dcb_launch_advance_skip(int K, int N, const int32_t *env_ids, int n_
 cudaError_t dcb_launch_step(const StepArgs &a, int threads, int grid, size_t smem, cudaStream_t s);
 cudaError_t dcb_step_set_smem_limit(int threads, size_t smem);
 size_t dcb_step_smem_bytes(int kind, int N, int M, int E);
+int dcb_step_regs_per_thread(int threads);

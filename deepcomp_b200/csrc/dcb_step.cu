@@ -4,21 +4,30 @@
 // deepcomp/env/multi_ue/central.py:143-152 and deepcomp/env/multi_ue/multi_agent.py:6-107.  All file:line
 // citations are relative to /root/reference/deepcomp/.
 //
-// Mapping.  A CTA owns E consecutive envs; thread t owns UE slot t of the CTA's E*N UEs, which are contiguous in
-// every [K][N] state slab, so state loads / reward stores are perfectly coalesced.  The per-UE state (position,
-// waypoint, pause counter, connection bitmask, EWMA rate) stays in registers for all T steps.
+// Mapping.  A CTA owns E consecutive envs and runs TWO warp groups of G = ceil32(E*N) threads each; thread t of
+// either group owns UE slot t of the CTA's E*N UEs, which are contiguous in every [K][N] state slab (coalesced
+// state loads / reward stores):
+//   * physics warps  -- carry the per-UE state (position, waypoint, pause counter, connection bitmask, EWMA rate) in
+//     registers across all T steps and run the state-changing chain of a step;
+//   * observer warps -- turn the state a step left behind into that step's observation tile, rewards and info.
+// The groups are pipelined one step apart through a double-buffered hand-off in shared memory and named barriers
+// (FULL / EMPTY per buffer parity): while the observers emit step t, the physics warps already run step t+1.  A
+// 1024-env batch gives a B200 only ~11 UE-warps per SM, so the step is latency-bound; the split halves the
+// per-warp instruction stream and doubles the warps in flight without redundant work.
 //
-// Step structure (one iteration of the fused loop, after the first):
-//   1. pre-move rates from the aggregates computed during the PREVIOUS step's observe phase (the UE positions of
-//      "after move t" and "before move t+1" are the same; only the action's one toggled link differs, so the
-//      reducer produces both sets of per-BS aggregates in one pass)            base.py:446, station.py:152-220
+// Physics, one step (after the first):
+//   1. pre-move rates from the aggregates computed during the PREVIOUS step (the UE positions of "after move t"
+//      and "before move t+1" are the same; only the action's one toggled link differs, so the reducer produces both
+//      sets of per-BS aggregates in one pass)                                  base.py:446, station.py:152-220
 //   2. move, drop out-of-range links, EWMA                                     user.py:148-188, movement.py:132-181
-//   3. dense pair loop over the M base stations: squared distance, in-range bit, normalised SNR -> obs tile
-//      (fp32, see below); sparse loop over the (few) connected links: fp64 SNR -> unshared rate -> link value
-//      -> matrix X and per-(env, BS) UE bitsets                               variants.py:271-303, user.py:190-229
+//   3. sparse loop over the (few) connected links: fp64 SNR -> unshared rate -> link value -> matrix X and
+//      per-(env, BS) UE bitsets                                               station.py:129-150
 //   4. reduce per (env, BS) over the CONNECTED UEs only (bitset walk): count / sum of link values / arg-max, for
 //      the current mask and for the next step's mask; fixed order (deterministic)
-//   5. post-move rates -> utility; per-BS utility sums; observation tile + rewards; coalesced tile write-out
+//   5. post-move rates -> utility -> hand-off                                  base.py:451, user.py:76-92
+// Observers, one step: per-BS utility sums (bitset walk), dense pair loop over the M base stations (squared
+// distance, in-range bit, normalised SNR in fp32), observation tile, rewards, info; the tile leaves through ONE
+// TMA bulk store (cp.async.bulk shared -> global) per CTA and step.           variants.py:271-303, multi_agent.py:39-95
 // The first step of a launch (and a step that starts with an episode reset) has no aggregates to inherit and
 // computes them stand-alone.
 //
@@ -38,9 +47,9 @@
 namespace {
 
 struct SmemLayout {
-    int off_tab, off_stage, off_x, off_sum_pre, off_sum_post, off_usum, off_umin, off_fues, off_futil, off_su,
-        off_srb, off_smask, off_env_rew, off_env_sumu, off_bsx, off_bsy, off_vel, off_cnt_pre, off_arg_pre,
-        off_cnt_post, off_arg_post, off_bits, off_share;
+    int off_tab, off_stage, off_x, off_sum_pre, off_sum_post, off_usum, off_umin, off_fues, off_futil, off_hx, off_hy,
+        off_hmask, off_hutil, off_hrb, off_hdr, off_hlost, off_env_rew, off_env_sumu, off_bsx, off_bsy, off_vel,
+        off_cnt_pre, off_arg_pre, off_cnt_post, off_arg_post, off_cnt_obs, off_bits, off_share;
     int nbits;   // words per bitset
     int total;
 };
@@ -64,11 +73,16 @@ __host__ __device__ inline SmemLayout smem_layout(int kind, int N, int M, int E)
     L.off_sum_post = o; o += align16(EM * 8);
     L.off_usum = o;     o += align16(EM * 8);
     L.off_umin = o;     o += align16(EM * 8);
-    L.off_fues = o;     o += align16(EM * 8);
-    L.off_futil = o;    o += align16(EM * 8);
-    L.off_su = o;       o += align16(EN * 8);
-    L.off_srb = o;      o += align16(EN * 8);
-    L.off_smask = o;    o += align16(EN * 8);
+    L.off_fues = o;     o += align16(EM * 4);
+    L.off_futil = o;    o += align16(EM * 4);
+    // physics -> observer hand-off, two parities: position, mask, utility, pre-move reward, rate, lost links
+    L.off_hx = o;       o += align16(2 * EN * 8);
+    L.off_hy = o;       o += align16(2 * EN * 8);
+    L.off_hmask = o;    o += align16(2 * EN * 8);
+    L.off_hutil = o;    o += align16(2 * EN * 8);
+    L.off_hrb = o;      o += align16(2 * EN * 8);
+    L.off_hdr = o;      o += align16(2 * EN * 8);
+    L.off_hlost = o;    o += align16(2 * EN * 4);
     L.off_env_rew = o;  o += align16(E * 8);
     L.off_env_sumu = o; o += align16(E * 8);
     L.off_bsx = o;      o += align16(M * 8);
@@ -78,8 +92,9 @@ __host__ __device__ inline SmemLayout smem_layout(int kind, int N, int M, int E)
     L.off_arg_pre = o;  o += align16(EM * 4);
     L.off_cnt_post = o; o += align16(EM * 4);
     L.off_arg_post = o; o += align16(EM * 4);
+    L.off_cnt_obs = o;  o += align16(EM * 4);
     L.nbits = EM * ((N + 31) / 32);
-    L.off_bits = o;     o += align16(3 * L.nbits * 4);               // UE bitsets per (env, BS): post, pre, fresh
+    L.off_bits = o;     o += align16(5 * L.nbits * 4);               // UE bitsets per (env, BS): post[2], pre[2], fresh
     L.off_share = o;    o += align16(M * 4);
     L.total = o;
     return L;
@@ -154,19 +169,38 @@ __device__ __forceinline__ float norm_snr_f32(float d2, float d2min, float hr) {
     return d2 == d2min ? 1.0f : fminf(q * sq * ex, 1.0f);   // the closest BS is exactly 1 (variants.py:284)
 }
 
+// ------------------------------------------------------------------------------------------------ named barriers
+// Barrier 0 is __syncthreads (set-up only).  Each warp group has a private barrier; FULL[parity] / EMPTY[parity]
+// hand a buffer from the physics warps to the observer warps and back (arrive on one side, sync on the other).
+enum { BAR_PHYS = 1, BAR_OBS = 2, BAR_FULL = 3, BAR_EMPTY = 5 };
+
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ bool bar_or(int id, int n, bool pred) {
+    int r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %3, 0;\n\tbar.red.or.pred p, %1, %2, q;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(r) : "r"(id), "r"(n), "r"((int)pred) : "memory");
+    return r != 0;
+}
+
 // ------------------------------------------------------------------------------------------------ reductions
+// (tid, gsize: thread index within / size of the calling warp group)
 // For every (env, BS) pair walk the bitset of connected UEs: count, sum of link values X[ue][bs], first arg-max
 // (max-cap only).  Done for two bitsets (current masks -> *_a, next step's masks -> *_b).  S lanes per pair take the
 // 32-UE words round-robin; fixed combination order -> deterministic.
-__device__ __forceinline__ void reduce_links(const double *X, const unsigned *bits_a, const unsigned *bits_b, int N,
-                                             int M, int MS, int n_env, int S, bool want_arg, int *cnt_a, double *sum_a,
-                                             int *arg_a, int *cnt_b, double *sum_b, int *arg_b) {
+__device__ __forceinline__ void reduce_links(int tid, int gsize, const double *X, const unsigned *bits_a,
+                                             const unsigned *bits_b, int N, int M, int MS, int n_env, int S,
+                                             bool want_arg, int *cnt_a, double *sum_a, int *arg_a, int *cnt_b,
+                                             double *sum_b, int *arg_b) {
     const int R = n_env * M;
     const int NW = (N + 31) >> 5;
-    const int ppp = blockDim.x / S;
-    const int seg = threadIdx.x & (S - 1);
+    const int ppp = gsize / S;
+    const int seg = tid & (S - 1);
     for (int base = 0; base < R; base += ppp) {
-        const int pair = base + threadIdx.x / S;
+        const int pair = base + tid / S;
         const bool ok = pair < R;
         int c0 = 0, c1 = 0, a0 = 0x7fffffff, a1 = 0x7fffffff;
         double s0 = 0.0, s1 = 0.0, b0 = 0.0, b1 = 0.0;
@@ -174,7 +208,7 @@ __device__ __forceinline__ void reduce_links(const double *X, const unsigned *bi
             const int le = pair / M, b = pair - le * M;
             const double *col = X + (size_t)(le * N) * MS + b;
             for (int w = seg; w < NW; w += S) {
-                unsigned wa = bits_a[pair * NW + w];
+                const unsigned wa = bits_a[pair * NW + w];
                 const unsigned wb = bits_b[pair * NW + w];
                 c0 += __popc(wa);
                 c1 += __popc(wb);
@@ -216,25 +250,27 @@ __device__ __forceinline__ void reduce_links(const double *X, const unsigned *bi
     }
 }
 
-// Per-BS total utility (station.py:63-69) -> usum, the two per-BS observation entries (variants.py:296-299,
-// station.py:71-76) -> f_ues, f_util; min (station.py:78-83) -> umin.
-__device__ __forceinline__ void reduce_utility(const unsigned *bits, const double *su, const int *cnt, int N, int M,
-                                               int n_env, int S, bool want_min, double *usum, double *umin,
-                                               double *f_ues, double *f_util) {
+// Per-BS connected count -> cnt, total utility (station.py:63-69) -> usum, the two per-BS observation entries
+// (variants.py:296-299, station.py:71-76) -> f_ues, f_util; min (station.py:78-83) -> umin.
+__device__ __forceinline__ void reduce_utility(int tid, int gsize, const unsigned *bits, const double *su, int N,
+                                               int M, int n_env, int S, bool want_min, int *cnt, double *usum,
+                                               double *umin, float *f_ues, float *f_util) {
     const int R = n_env * M;
     const int NW = (N + 31) >> 5;
-    const int ppp = blockDim.x / S;
-    const int seg = threadIdx.x & (S - 1);
+    const int ppp = gsize / S;
+    const int seg = tid & (S - 1);
     const double inv_n = 1.0 / (double)N;
     for (int base = 0; base < R; base += ppp) {
-        const int pair = base + threadIdx.x / S;
+        const int pair = base + tid / S;
         const bool ok = pair < R;
         double s = 0.0, mn = DCB_MAX_UTILITY;
+        int c = 0;
         if (ok) {
             const int le = pair / M;
             const double *sue = su + le * N;
             for (int w = seg; w < NW; w += S) {
                 unsigned wa = bits[pair * NW + w];
+                c += __popc(wa);
                 while (wa) {
                     const int j = __ffs(wa) - 1;
                     wa &= wa - 1;
@@ -245,22 +281,24 @@ __device__ __forceinline__ void reduce_utility(const unsigned *bits, const doubl
             }
         }
         for (int off = S >> 1; off > 0; off >>= 1) {
+            c += __shfl_xor_sync(0xffffffffu, c, off);
             s += __shfl_xor_sync(0xffffffffu, s, off);
             if (want_min) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
         }
         if (ok && seg == 0) {
-            const int c = cnt[pair];
+            cnt[pair] = c;
             usum[pair] = s;
             umin[pair] = mn;
-            f_ues[pair] = (double)c * inv_n;                                     // |C_b| / N (variants.py:296)
-            f_util[pair] = c > 0 ? s * dcb_rcp((double)c) * (1.0 / DCB_MAX_UTILITY) : 0.0;
+            f_ues[pair] = (float)((double)c * inv_n);                                          // |C_b| / N (variants.py:296)
+            f_util[pair] = c > 0 ? (float)(s * dcb_rcp((double)c) * (1.0 / DCB_MAX_UTILITY)) : 0.0f;
         }
     }
 }
 
 // Per-env reduction of a per-UE vector: mode 0 = sum, 2 = min (one warp per env)
-__device__ __forceinline__ void reduce_env(const double *v, int N, int n_env, int mode, double *out) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+__device__ __forceinline__ void reduce_env(int tid, int gsize, const double *v, int N, int n_env, int mode,
+                                           double *out) {
+    const int lane = tid & 31, warp = tid >> 5, nwarps = gsize >> 5;
     const int chunk = (N + 31) / 32;
     for (int le = warp; le < n_env; le += nwarps) {
         const int i0 = lane * chunk, i1 = min(N, i0 + chunk);
@@ -276,7 +314,7 @@ __device__ __forceinline__ void reduce_env(const double *v, int N, int n_env, in
 
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT) dcb_step_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(const StepArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const DevParams &p = a.p;
     const int N = p.N, M = p.M, E = p.E, S = p.S;
@@ -292,26 +330,34 @@ __global__ void __launch_bounds__(MAXT) dcb_step_kernel(const StepArgs a) {
     int *cnt_post = reinterpret_cast<int *>(smem + L.off_cnt_post);
     double *sum_post = reinterpret_cast<double *>(smem + L.off_sum_post);
     int *arg_post = reinterpret_cast<int *>(smem + L.off_arg_post);
+    int *cnt_obs = reinterpret_cast<int *>(smem + L.off_cnt_obs);
     double *usum = reinterpret_cast<double *>(smem + L.off_usum);
     double *umin = reinterpret_cast<double *>(smem + L.off_umin);
-    double *f_ues = reinterpret_cast<double *>(smem + L.off_fues);
-    double *f_util = reinterpret_cast<double *>(smem + L.off_futil);
-    double *su = reinterpret_cast<double *>(smem + L.off_su);
-    double *srb = reinterpret_cast<double *>(smem + L.off_srb);
-    unsigned long long *smask = reinterpret_cast<unsigned long long *>(smem + L.off_smask);
+    float *f_ues = reinterpret_cast<float *>(smem + L.off_fues);
+    float *f_util = reinterpret_cast<float *>(smem + L.off_futil);
+    double *hx = reinterpret_cast<double *>(smem + L.off_hx);
+    double *hy = reinterpret_cast<double *>(smem + L.off_hy);
+    unsigned long long *hmask = reinterpret_cast<unsigned long long *>(smem + L.off_hmask);
+    double *hutil = reinterpret_cast<double *>(smem + L.off_hutil);
+    double *hrb = reinterpret_cast<double *>(smem + L.off_hrb);
+    double *hdr = reinterpret_cast<double *>(smem + L.off_hdr);
+    int *hlost = reinterpret_cast<int *>(smem + L.off_hlost);
     double *env_rew = reinterpret_cast<double *>(smem + L.off_env_rew);
     double *env_sumu = reinterpret_cast<double *>(smem + L.off_env_sumu);
     double *bsx = reinterpret_cast<double *>(smem + L.off_bsx);
     double *bsy = reinterpret_cast<double *>(smem + L.off_bsy);
     int *share = reinterpret_cast<int *>(smem + L.off_share);
     double *velspec = reinterpret_cast<double *>(smem + L.off_vel);
-    unsigned *bits_post = reinterpret_cast<unsigned *>(smem + L.off_bits);
-    unsigned *bits_pre = bits_post + L.nbits;
-    unsigned *bits_fresh = bits_pre + L.nbits;
+    unsigned *bits_post2 = reinterpret_cast<unsigned *>(smem + L.off_bits);   // [2][nbits]
+    unsigned *bits_pre2 = bits_post2 + 2 * L.nbits;                            // [2][nbits]
+    unsigned *bits_fresh = bits_pre2 + 2 * L.nbits;                            // [nbits]
 
-    const int t = threadIdx.x;
+    const int G = blockDim.x >> 1;                  // threads per warp group
+    const bool is_obs = (int)threadIdx.x >= G;
+    const int t = (int)threadIdx.x - (is_obs ? G : 0);
     const int env0 = blockIdx.x * E;
     const int n_env = min(E, p.K - env0);
+    const int EN = E * N;
     const bool valid = t < n_env * N;
     const int le = valid ? t / N : 0;
     const int i = valid ? t - le * N : 0;
@@ -319,337 +365,385 @@ __global__ void __launch_bounds__(MAXT) dcb_step_kernel(const StepArgs a) {
     const long long u = (long long)k * N + i;
     const bool central = p.kind == DCB_KIND_CENTRAL;
     const int OW = obs_width(p.kind, M);
+    const int T = a.T;
+    const int n_iter = T > 0 ? T : 1;
 
-    dcb_math_init(tab, t);
-    for (int b = t; b < M; b += blockDim.x) {
+    dcb_math_init(tab, threadIdx.x);
+    for (int b = threadIdx.x; b < M; b += blockDim.x) {
         bsx[b] = p.bs_xy[2 * b];
         bsy[b] = p.bs_xy[2 * b + 1];
         share[b] = p.sharing[b];
     }
-    for (int j = t; j < N; j += blockDim.x) velspec[j] = p.vel_spec[j];
-    for (int j = t; j < 3 * L.nbits; j += blockDim.x) bits_post[j] = 0u;
-
-    // ---- per-UE state -> registers
-    double x = 0, y = 0, ewma = 0;
-    unsigned long long mask = 0;
-    unsigned wxy = 0, vpt = 0;
-    int tk = 0;
-    if (valid) {
-        const double2 ps = p.pos[u];
-        x = ps.x; y = ps.y;
-        const uint2 mv = p.mv[u];
-        wxy = mv.x; vpt = mv.y;
-        mask = p.mask[u];
-        ewma = p.ewma[u];
-        tk = p.time[k];
-    }
+    for (int j = threadIdx.x; j < N; j += blockDim.x) velspec[j] = p.vel_spec[j];
+    for (int j = threadIdx.x; j < 5 * L.nbits; j += blockDim.x) bits_post2[j] = 0u;
     __syncthreads();
-    const double vfix = valid ? velspec[i] : 0.0;
-    double *Xrow = X + (size_t)t * MS;
-    // obs tile row of this UE: multi [connected(M) | dr(M) | ues_at_bs(M) | util_at_bs(M) | utility(1)] per UE
-    // (variants.py:271-303); central [connected(N*M) | dr(N*M) | utility(N)] per env (central.py:31-57)
-    float *row_conn = central ? stage + (size_t)le * (2 * N * M + N) + i * M : stage + (size_t)t * OW;
-    float *row_dr = central ? row_conn + N * M : row_conn + M;
-    // this UE's bit in the per-(env, BS) bitsets
-    const int bit_word = le * M * NW + (i >> 5);
-    const unsigned bit_val = 1u << (i & 31);
-    const float hr = (float)(p.snr_h - 1.5);
-    const bool dbg_any = a.out.dbg_obs || a.out.dbg_snr;
-    const int T = a.T;
-    const int n_iter = T > 0 ? T : 1;
-    // mask after the NEXT step's action, prepared during the observe phase (only meaningful when !fresh)
-    unsigned long long mask_next = 0;
 
-    for (int step = 0; step < n_iter; step++) {
-        const bool last = step == n_iter - 1;
-        double rb = 0.0;      // reward before the move (base.py:446)
-        int lost = 0;
-        if (T > 0) {
-            // ---- stand-alone pre phase: first step of the launch or a step that starts with an episode reset
-            bool fresh = step == 0;
-            if (valid && p.auto_reset && tk >= p.episode_length) {
-                // MobileEnv.reset before the next step (base.py:169-189)
-                const double2 ps = p.init_pos[u];
-                x = ps.x; y = ps.y;
-                const uint32_t e = p.table[u * p.D];
-                wxy = (e & 0x3fffu) | (((e >> 14) & 0x3fffu) << 16);
-                vpt = (e >> 28) | (1u << 16);
-                mask = 0ull; ewma = 0.0; tk = 0;
-                fresh = true;
+    if (!is_obs) {
+        // ===================================================================== physics warps
+        double x = 0, y = 0, ewma = 0;
+        unsigned long long mask = 0;
+        unsigned wxy = 0, vpt = 0;
+        int tk = 0;
+        if (valid) {
+            const double2 ps = p.pos[u];
+            x = ps.x; y = ps.y;
+            const uint2 mv = p.mv[u];
+            wxy = mv.x; vpt = mv.y;
+            mask = p.mask[u];
+            ewma = p.ewma[u];
+            tk = p.time[k];
+        }
+        const double vfix = valid ? velspec[i] : 0.0;
+        double *Xrow = X + (size_t)t * MS;
+        // this UE's bit in the per-(env, BS) UE bitsets
+        const int bit_word = le * M * NW + (i >> 5);
+        const unsigned bit_val = 1u << (i & 31);
+        // mask after the NEXT step's action, prepared at the end of a step (only meaningful when !fresh)
+        unsigned long long mask_next = 0;
+
+        for (int step = 0; step < n_iter; step++) {
+            const bool last = step == n_iter - 1;
+            const int par = step & 1;
+            unsigned *bits_post = bits_post2 + par * L.nbits;
+            unsigned *bits_pre = bits_pre2 + par * L.nbits;
+            double rb = 0.0;      // reward before the move (base.py:446)
+            int lost = 0;
+            // the observers must be done with this parity's hand-off buffers (step - 2)
+            if (step >= 2) bar_sync(BAR_EMPTY + par, 2 * G);
+            if (T > 0) {
+                // ---- stand-alone pre phase: first step of the launch or a step that starts with an episode reset
+                bool fresh = step == 0;
+                if (valid && p.auto_reset && tk >= p.episode_length) {
+                    // MobileEnv.reset before the next step (base.py:169-189)
+                    const double2 ps = p.init_pos[u];
+                    x = ps.x; y = ps.y;
+                    const uint32_t e = p.table[u * p.D];
+                    wxy = (e & 0x3fffu) | (((e >> 14) & 0x3fffu) << 16);
+                    vpt = (e >> 28) | (1u << 16);
+                    mask = 0ull; ewma = 0.0; tk = 0;
+                    fresh = true;
+                }
+                if (valid) {
+                    if (fresh) {
+                        // apply_ue_actions (base.py:247-282) -> User.connect_to_bs(disconnect=True) (user.py:190-229)
+                        const int act = a.actions[(size_t)step * p.K * N + u];
+                        if (act < 0 || act > M) {
+                            atomicOr(p.err, DCB_ERRBIT_ACTION);
+                        } else if (act > 0) {
+                            const int b = act - 1;
+                            const unsigned long long bit = 1ull << b;
+                            if (mask & bit) mask &= ~bit;
+                            else if (dist2(bsx[b], bsy[b], x, y) <= p.thr_d2) mask |= bit;   // can_connect, station.py:222-226
+                        }
+                    } else {
+                        mask = mask_next;
+                    }
+                }
+                if (bar_or(BAR_PHYS, G, fresh)) {
+                    // some env of this CTA has no inherited aggregates: recompute link values and reduce
+                    if (valid) {
+                        const double iee = dcb_rcp(ewma + DCB_EPSILON);
+                        for (unsigned long long m = mask; m; m &= m - 1) {
+                            const int b = __ffsll((long long)m) - 1;
+                            Xrow[b] = link_value(share[b], rate_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y)), iee);
+                            atomicOr(&bits_fresh[bit_word + b * NW], bit_val);
+                        }
+                    }
+                    bar_sync(BAR_PHYS, G);
+                    reduce_links(t, G, X, bits_fresh, bits_fresh, N, M, MS, n_env, S, p.has_maxcap, cnt_post, sum_post,
+                                 arg_post, cnt_pre, sum_pre, arg_pre);
+                    bar_sync(BAR_PHYS, G);
+                    for (int j = t; j < L.nbits; j += G) bits_fresh[j] = 0u;
+                }
+                if (valid) {
+                    // ---- update_ue_drs_rewards (base.py:315-335): Basestation.data_rate_shared (station.py:152-202)
+                    // per connected link; the ue.bs_dr cache goes back into Xrow
+                    const double ee = ewma + DCB_EPSILON;
+                    double dr = 0.0;
+                    for (unsigned long long m = mask; m; m &= m - 1) {
+                        const int b = __ffsll((long long)m) - 1;
+                        const int pr = le * M + b;
+                        const double r = shared_rate(share[b], Xrow[b], cnt_pre[pr], sum_pre[pr], arg_pre[pr], i, ee);
+                        Xrow[b] = r;
+                        dr += r;                                                       // user.py:64-69
+                    }
+                    // ---- calc_reward (base.py:158-167), penalties are identically 0 (base.py:257)
+                    rb = log_utility(tab, dr) / DCB_MAX_UTILITY;
+                    // ---- User.move (user.py:159-173) -> RandomWaypoint.step (movement.py:158-181)
+                    double wx = (double)(wxy & 0xffffu), wy = (double)(wxy >> 16);
+                    unsigned pause = (vpt >> 8) & 0xffu;
+                    bool moving = true;
+                    if (x == wx && y == wy) pause |= 0x80u;                            // movement.py:169-170
+                    if (pause & 0x80u) {
+                        if ((int)(pause & 0x7fu) < p.pause_duration) {                 // movement.py:174-176
+                            pause++;
+                            moving = false;
+                        } else {                                                       // movement.py:177 -> reset()
+                            unsigned tidx = vpt >> 16;
+                            if ((int)tidx >= p.D) {
+                                atomicOr(p.err, DCB_ERRBIT_TABLE);
+                                tidx = p.D - 1;
+                            }
+                            const uint32_t e = p.table[u * p.D + tidx];
+                            wxy = (e & 0x3fffu) | (((e >> 14) & 0x3fffu) << 16);
+                            vpt = (e >> 28) | ((tidx + 1) << 16);
+                            wx = (double)(wxy & 0xffffu); wy = (double)(wxy >> 16);
+                            pause = 0;
+                        }
+                    }
+                    vpt = (vpt & 0xffff00ffu) | (pause << 8);
+                    if (moving) {
+                        // movement.py:132-156
+                        const double vel = vfix >= 0.0 ? vfix : (double)(vpt & 0xffu);
+                        if (sqrt(dist2(x, y, wx, wy)) <= vel) {
+                            x = wx; y = wy;
+                        } else {
+                            const double vx = wx - x, vy = wy - y;
+                            const double norm = sqrt(fma(vy, vy, vx * vx));   // np.linalg.norm -> FMA-accumulating ddot
+                            x = x + vel * (vx / norm);
+                            y = y + vel * (vy / norm);
+                        }
+                    }
+                    // ---- check_bs_connection (user.py:175-188) + update_ewma_dr (user.py:148-157)
+                    double keep = 0.0;
+                    for (unsigned long long m = mask; m; m &= m - 1) {
+                        const int b = __ffsll((long long)m) - 1;
+                        if (dist2(bsx[b], bsy[b], x, y) <= p.thr_d2) keep += Xrow[b];
+                        else { mask &= ~(1ull << b); lost++; }
+                    }
+                    ewma = 0.9 * keep + (1 - 0.9) * ewma;
+                    tk += 1;                                                           // base.py:454
+                }
             }
+            // ---- link values at the new position for update_ue_drs_rewards(update_only=True) (base.py:451) and for
+            // the next step's pre-move update (its action toggles one link, user.py:190-229: known now)
+            mask_next = mask;
             if (valid) {
-                if (fresh) {
-                    // apply_ue_actions (base.py:247-282) -> User.connect_to_bs(disconnect=True) (user.py:190-229)
-                    const int act = a.actions[(size_t)step * p.K * N + u];
+                if (T > 0 && !last) {
+                    const int act = a.actions[(size_t)(step + 1) * p.K * N + u];
                     if (act < 0 || act > M) {
                         atomicOr(p.err, DCB_ERRBIT_ACTION);
                     } else if (act > 0) {
                         const int b = act - 1;
                         const unsigned long long bit = 1ull << b;
-                        if (mask & bit) mask &= ~bit;
-                        else if (dist2(bsx[b], bsy[b], x, y) <= p.thr_d2) mask |= bit;   // can_connect, station.py:222-226
-                    }
-                } else {
-                    mask = mask_next;
-                }
-            }
-            if (__syncthreads_or(fresh)) {
-                // some env of this CTA has no inherited aggregates: recompute link values and reduce
-                if (valid) {
-                    const double iee = dcb_rcp(ewma + DCB_EPSILON);
-                    for (unsigned long long m = mask; m; m &= m - 1) {
-                        const int b = __ffsll((long long)m) - 1;
-                        Xrow[b] = link_value(share[b], rate_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y)), iee);
-                        atomicOr(&bits_fresh[bit_word + b * NW], bit_val);
+                        if ((mask & bit) || dist2(bsx[b], bsy[b], x, y) <= p.thr_d2) mask_next = mask ^ bit;
                     }
                 }
-                __syncthreads();
-                reduce_links(X, bits_fresh, bits_fresh, N, M, MS, n_env, S, p.has_maxcap, cnt_post, sum_post, arg_post,
-                             cnt_pre, sum_pre, arg_pre);
-                __syncthreads();
-                for (int j = t; j < L.nbits; j += blockDim.x) bits_fresh[j] = 0u;
+                const double iee = dcb_rcp(ewma + DCB_EPSILON);
+                for (unsigned long long m = mask | mask_next; m; m &= m - 1) {
+                    const int b = __ffsll((long long)m) - 1;
+                    Xrow[b] = link_value(share[b], rate_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y)), iee);
+                    if ((mask >> b) & 1ull) atomicOr(&bits_post[bit_word + b * NW], bit_val);
+                    if ((mask_next >> b) & 1ull) atomicOr(&bits_pre[bit_word + b * NW], bit_val);
+                }
             }
+            bar_sync(BAR_PHYS, G);
+            reduce_links(t, G, X, bits_post, bits_pre, N, M, MS, n_env, S, p.has_maxcap, cnt_post, sum_post, arg_post,
+                         cnt_pre, sum_pre, arg_pre);
+            bar_sync(BAR_PHYS, G);
+            // bits_pre of this parity is consumed; its next use is two steps (>= 2 group barriers) away
+            for (int j = t; j < L.nbits; j += G) bits_pre[j] = 0u;
             if (valid) {
-                // ---- update_ue_drs_rewards (base.py:315-335): Basestation.data_rate_shared (station.py:152-202) per
-                // connected link; the ue.bs_dr cache goes back into Xrow
+                // ---- post-move rates -> utility (user.py:76-92) -> hand-off
                 const double ee = ewma + DCB_EPSILON;
                 double dr = 0.0;
                 for (unsigned long long m = mask; m; m &= m - 1) {
                     const int b = __ffsll((long long)m) - 1;
                     const int pr = le * M + b;
-                    const double r = shared_rate(share[b], Xrow[b], cnt_pre[pr], sum_pre[pr], arg_pre[pr], i, ee);
-                    Xrow[b] = r;
-                    dr += r;                                                           // user.py:64-69
+                    const double r = shared_rate(share[b], Xrow[b], cnt_post[pr], sum_post[pr], arg_post[pr], i, ee);
+                    if (last && a.out.dbg_link_rate) a.out.dbg_link_rate[u * M + b] = r;
+                    dr += r;
                 }
-                // ---- calc_reward (base.py:158-167), penalties are identically 0 (base.py:257)
-                rb = log_utility(tab, dr) / DCB_MAX_UTILITY;
-                // ---- User.move (user.py:159-173) -> RandomWaypoint.step (movement.py:158-181)
-                double wx = (double)(wxy & 0xffffu), wy = (double)(wxy >> 16);
-                unsigned pause = (vpt >> 8) & 0xffu;
-                bool moving = true;
-                if (x == wx && y == wy) pause |= 0x80u;                                // movement.py:169-170
-                if (pause & 0x80u) {
-                    if ((int)(pause & 0x7fu) < p.pause_duration) {                     // movement.py:174-176
-                        pause++;
-                        moving = false;
-                    } else {                                                           // movement.py:177 -> reset()
-                        unsigned tidx = vpt >> 16;
-                        if ((int)tidx >= p.D) {
-                            atomicOr(p.err, DCB_ERRBIT_TABLE);
-                            tidx = p.D - 1;
-                        }
-                        const uint32_t e = p.table[u * p.D + tidx];
-                        wxy = (e & 0x3fffu) | (((e >> 14) & 0x3fffu) << 16);
-                        vpt = (e >> 28) | ((tidx + 1) << 16);
-                        wx = (double)(wxy & 0xffffu); wy = (double)(wxy >> 16);
-                        pause = 0;
-                    }
-                }
-                vpt = (vpt & 0xffff00ffu) | (pause << 8);
-                if (moving) {
-                    // movement.py:132-156
-                    const double vel = vfix >= 0.0 ? vfix : (double)(vpt & 0xffu);
-                    if (sqrt(dist2(x, y, wx, wy)) <= vel) {
-                        x = wx; y = wy;
-                    } else {
-                        const double vx = wx - x, vy = wy - y;
-                        const double norm = sqrt(fma(vy, vy, vx * vx));   // np.linalg.norm -> FMA-accumulating ddot
-                        x = x + vel * (vx / norm);
-                        y = y + vel * (vy / norm);
-                    }
-                }
-                // ---- check_bs_connection (user.py:175-188) + update_ewma_dr (user.py:148-157)
-                double keep = 0.0;
-                for (unsigned long long m = mask; m; m &= m - 1) {
-                    const int b = __ffsll((long long)m) - 1;
-                    if (dist2(bsx[b], bsy[b], x, y) <= p.thr_d2) keep += Xrow[b];
-                    else { mask &= ~(1ull << b); lost++; }
-                }
-                ewma = 0.9 * keep + (1 - 0.9) * ewma;
-                tk += 1;                                                               // base.py:454
+                const int h = par * EN + t;
+                hx[h] = x; hy[h] = y; hmask[h] = mask;
+                hutil[h] = log_utility(tab, dr);
+                hrb[h] = rb; hdr[h] = dr; hlost[h] = lost;
             }
+            bar_arrive(BAR_FULL + par, 2 * G);
         }
-        // =========================== observe the (post-move) state ===========================
-        unsigned long long inrange = 0ull;
-        mask_next = mask;
-        if (valid) {
-            // dense pass A: squared distances (fp64, exact range decision multi_agent.py:60 / station.py:222-226),
-            // parked in the tile as float for pass B
-            double d2min = CUDART_INF;
+        // drain: the observers' last (up to two) EMPTY arrivals
+        if (n_iter >= 2) bar_sync(BAR_EMPTY + (n_iter & 1), 2 * G);
+        bar_sync(BAR_EMPTY + ((n_iter - 1) & 1), 2 * G);
+
+        // ---- registers -> state slabs
+        if (valid && T > 0) {
+            p.pos[u] = make_double2(x, y);
+            p.mv[u] = make_uint2(wxy, vpt);
+            p.mask[u] = mask;
+            p.ewma[u] = ewma;
+            if (i == 0) p.time[k] = tk;
+        }
+    } else {
+        // ===================================================================== observer warps
+        // obs tile row of this UE: multi [connected(M) | dr(M) | ues_at_bs(M) | util_at_bs(M) | utility(1)] per UE
+        // (variants.py:271-303); central [connected(N*M) | dr(N*M) | utility(N)] per env (central.py:31-57)
+        float *row_conn = central ? stage + (size_t)le * (2 * N * M + N) + i * M : stage + (size_t)t * OW;
+        float *row_dr = central ? row_conn + N * M : row_conn + M;
+        const float hr = (float)(p.snr_h - 1.5);
+        const bool dbg_any = a.out.dbg_obs || a.out.dbg_snr;
+        // obs tile -> global: one TMA bulk store per step when the CTA's span is 16-byte aligned (else a copy loop)
+        const size_t per_env = central ? (size_t)(2 * N * M + N) : (size_t)N * OW;
+        const unsigned tile_bytes = (unsigned)(per_env * n_env * 4);
+        const bool use_tma = a.out.obs && (tile_bytes & 15u) == 0 &&
+                             ((((size_t)a.out.obs) + (size_t)env0 * per_env * 4) & 15) == 0 &&
+                             ((a.out.obs_stride * 4) & 15) == 0;
+
+        for (int step = 0; step < n_iter; step++) {
+            const bool last = step == n_iter - 1;
+            const int par = step & 1;
+            unsigned *bits_post = bits_post2 + par * L.nbits;
+            const int hbase = par * EN;
+            bar_sync(BAR_FULL + par, 2 * G);
+            // the previous step's TMA store must have finished reading the tile before anyone rewrites it
+            if (t == 0 && use_tma && step > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (!central)
+                reduce_utility(t, G, bits_post, hutil + hbase, N, M, n_env, S, p.reward == DCB_REWARD_MIN, cnt_obs, usum,
+                               umin, f_ues, f_util);
+            if (central && T > 0) reduce_env(t, G, hrb + hbase, N, n_env, p.reward == DCB_REWARD_MIN ? 2 : 0, env_rew);
+            if (a.out.sum_utility || a.out.dbg_sum_utility) reduce_env(t, G, hutil + hbase, N, n_env, 0, env_sumu);
+            bar_sync(BAR_OBS, G);
+            // the UE bitsets of this parity are consumed
+            for (int j = t; j < L.nbits; j += G) bits_post[j] = 0u;
+            if (valid) {
+                const int h = hbase + t;
+                const double x = hx[h], y = hy[h], util = hutil[h], dr = hdr[h];
+                const unsigned long long mask = hmask[h];
+                // ---- dense pass A: squared distances (fp64, exact range decision multi_agent.py:60 /
+                // station.py:222-226), parked in the tile as float for pass B
+                unsigned long long inrange = 0ull;
+                double d2min = CUDART_INF;
 #pragma unroll 2
-            for (int b = 0; b < M; b++) {
-                const double d2 = dist2(bsx[b], bsy[b], x, y);
-                d2min = fmin(d2min, d2);
-                if (d2 <= p.thr_d2) inrange |= 1ull << b;
-                row_dr[b] = (float)d2;
-            }
-            // dense pass B: 'dr' = snr_b / max_b snr_b (variants.py:276-284) = (d2min / d2_b)^h
-            if (d2min >= DCB_NEAR_D2) {
-                const float d2minf = (float)d2min;
+                for (int b = 0; b < M; b++) {
+                    const double d2 = dist2(bsx[b], bsy[b], x, y);
+                    d2min = fmin(d2min, d2);
+                    if (d2 <= p.thr_d2) inrange |= 1ull << b;
+                    row_dr[b] = (float)d2;
+                }
+                // ---- dense pass B: 'dr' = snr_b / max_b snr_b (variants.py:276-284) = (d2min / d2_b)^h
+                if (d2min >= DCB_NEAR_D2) {
+                    const float d2minf = (float)d2min;
 #pragma unroll 2
-                for (int b = 0; b < M; b++) row_dr[b] = norm_snr_f32(row_dr[b], d2minf, hr);
-            } else {
-                const double inv_max = dcb_rcp(snr_of_d2(p, tab, d2min));
-                for (int b = 0; b < M; b++)
-                    row_dr[b] = (float)(snr_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y)) * inv_max);
-            }
-            // the next step's action toggles one link (user.py:190-229): known now, folded into this step's reduction
-            if (T > 0 && !last) {
-                const int act = a.actions[(size_t)(step + 1) * p.K * N + u];
-                if (act < 0 || act > M) {
-                    atomicOr(p.err, DCB_ERRBIT_ACTION);
-                } else if (act > 0) {
-                    const unsigned long long bit = 1ull << (act - 1);
-                    if ((mask & bit) || (inrange & bit)) mask_next = mask ^ bit;
+                    for (int b = 0; b < M; b++) row_dr[b] = norm_snr_f32(row_dr[b], d2minf, hr);
+                } else {
+                    const double inv_max = dcb_rcp(snr_of_d2(p, tab, d2min));
+                    for (int b = 0; b < M; b++)
+                        row_dr[b] = (float)(snr_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y)) * inv_max);
                 }
-            }
-            smask[t] = mask;
-            // sparse pass: link values at the new position for update_ue_drs_rewards(update_only=True) (base.py:451)
-            // and for the next step's pre-move update -> X; UE bitsets per (env, BS)
-            const double iee = dcb_rcp(ewma + DCB_EPSILON);
-            for (unsigned long long m = mask | mask_next; m; m &= m - 1) {
-                const int b = __ffsll((long long)m) - 1;
-                Xrow[b] = link_value(share[b], rate_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y)), iee);
-                if ((mask >> b) & 1ull) atomicOr(&bits_post[bit_word + b * NW], bit_val);
-                if ((mask_next >> b) & 1ull) atomicOr(&bits_pre[bit_word + b * NW], bit_val);
-            }
-            if (last && dbg_any) {
-                // test taps: fp64 SNR of every pair (station.py:122-127); the fp64 copy of 'dr' is the fp32 value
-                double *dobs = a.out.dbg_obs ? (central ? a.out.dbg_obs + (size_t)k * (2 * N * M + N) + N * M + i * M
-                                                        : a.out.dbg_obs + (size_t)u * OW + M)
-                                             : nullptr;
-                for (int b = 0; b < M; b++) {
-                    if (dobs) dobs[b] = (double)row_dr[b];
-                    if (a.out.dbg_snr) a.out.dbg_snr[u * M + b] = snr_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y));
-                }
-            }
-        }
-        __syncthreads();
-        reduce_links(X, bits_post, bits_pre, N, M, MS, n_env, S, p.has_maxcap, cnt_post, sum_post, arg_post, cnt_pre,
-                     sum_pre, arg_pre);
-        __syncthreads();
-        double dr = 0.0, util = 0.0;
-        if (valid) {
-            const double ee = ewma + DCB_EPSILON;
-            for (unsigned long long m = mask; m; m &= m - 1) {
-                const int b = __ffsll((long long)m) - 1;
-                const int pr = le * M + b;
-                const double r = shared_rate(share[b], Xrow[b], cnt_post[pr], sum_post[pr], arg_post[pr], i, ee);
-                if (last && a.out.dbg_link_rate) a.out.dbg_link_rate[u * M + b] = r;
-                dr += r;
-            }
-            util = log_utility(tab, dr);                                               // user.py:76-92
-            su[t] = util;
-            srb[t] = rb;
-        }
-        __syncthreads();
-        if (!central)
-            reduce_utility(bits_post, su, cnt_post, N, M, n_env, S, p.reward == DCB_REWARD_MIN, usum, umin, f_ues,
-                           f_util);
-        if (central && T > 0) reduce_env(srb, N, n_env, p.reward == DCB_REWARD_MIN ? 2 : 0, env_rew);
-        if (a.out.sum_utility || a.out.dbg_sum_utility) reduce_env(su, N, n_env, 0, env_sumu);
-        __syncthreads();
-        // the bitsets have been consumed: clear them for the next step (separated from the next atomics by 2 barriers)
-        for (int j = t; j < 2 * L.nbits; j += blockDim.x) bits_post[j] = 0u;
-        // ---- rest of the observation row -> tile, rewards and per-UE outputs -> global
-        if (valid) {
-            double *dobs = (last && a.out.dbg_obs) ? a.out.dbg_obs : nullptr;
-            const double un = util / DCB_MAX_UTILITY;                                  // variants.py:287
-            if (central) {
-                double *drow = dobs ? dobs + (size_t)k * (2 * N * M + N) : nullptr;
-                for (int b = 0; b < M; b++) {
-                    const float c = (float)((unsigned)(mask >> b) & 1u);
-                    row_conn[b] = c;
-                    if (drow) drow[i * M + b] = c;
-                }
-                stage[(size_t)le * (2 * N * M + N) + 2 * N * M + i] = (float)un;
-                if (drow) drow[2 * N * M + i] = un;
-            } else {
-                double *drow = dobs ? dobs + (size_t)u * OW : nullptr;
-                const double *fu = f_ues + le * M, *fa = f_util + le * M;
-                for (int b = 0; b < M; b++) {
-                    const float c = (float)((unsigned)(mask >> b) & 1u);
-                    const double ab = fu[b], ub = fa[b];
-                    row_conn[b] = c; row_conn[2 * M + b] = (float)ab; row_conn[3 * M + b] = (float)ub;
-                    if (drow) { drow[b] = c; drow[2 * M + b] = ab; drow[3 * M + b] = ub; }
-                }
-                row_conn[4 * M] = (float)un;
-                if (drow) drow[4 * M] = un;
-            }
-            if (a.out.curr_dr) a.out.curr_dr[(size_t)step * a.out.curr_dr_stride + u] = (float)dr;
-            if (a.out.utility) a.out.utility[(size_t)step * a.out.utility_stride + u] = (float)util;
-            if (last && a.out.dbg_curr_dr) a.out.dbg_curr_dr[u] = dr;
-            if (last && a.out.dbg_utility) a.out.dbg_utility[u] = util;
-            if (i == 0) {
-                if (a.out.sum_utility) a.out.sum_utility[(size_t)step * a.out.sum_utility_stride + k] = (float)env_sumu[le];
-                if (last && a.out.dbg_sum_utility) a.out.dbg_sum_utility[k] = env_sumu[le];
-            }
-            if (T > 0) {
-                if (a.out.lost_conn) a.out.lost_conn[(size_t)step * a.out.lost_conn_stride + u] = (uint8_t)lost;
+                // ---- rest of the observation row
+                const double un = util / DCB_MAX_UTILITY;                              // variants.py:287
                 if (central) {
-                    if (i == 0) {
-                        // central.py:65-73 over the PRE-move rewards
-                        double r = env_rew[le];
-                        if (p.reward == DCB_REWARD_AVG) r = r / (double)N;
-                        if (a.out.reward) a.out.reward[(size_t)step * a.out.reward_stride + k] = (float)r;
-                        if (last && a.out.dbg_reward) a.out.dbg_reward[k] = r;
+                    for (int b = 0; b < M; b++) row_conn[b] = (float)((unsigned)(mask >> b) & 1u);
+                    stage[(size_t)le * (2 * N * M + N) + 2 * N * M + i] = (float)un;
+                } else {
+                    const float *fu = f_ues + le * M, *fa = f_util + le * M;
+                    for (int b = 0; b < M; b++) {
+                        row_conn[b] = (float)((unsigned)(mask >> b) & 1u);
+                        row_conn[2 * M + b] = fu[b];
+                        row_conn[3 * M + b] = fa[b];
+                    }
+                    row_conn[4 * M] = (float)un;
+                }
+                if (last && dbg_any) {
+                    // test taps: fp64 copy of the observation (the 'dr' entries are the fp32 values) and the fp64
+                    // SNR of every pair (station.py:122-127)
+                    if (a.out.dbg_obs) {
+                        if (central) {
+                            double *drow = a.out.dbg_obs + (size_t)k * (2 * N * M + N);
+                            for (int b = 0; b < M; b++) {
+                                drow[i * M + b] = (double)((unsigned)(mask >> b) & 1u);
+                                drow[N * M + i * M + b] = (double)row_dr[b];
+                            }
+                            drow[2 * N * M + i] = un;
+                        } else {
+                            double *drow = a.out.dbg_obs + (size_t)u * OW;
+                            for (int b = 0; b < M; b++) {
+                                const int c = cnt_obs[le * M + b];
+                                drow[b] = (double)((unsigned)(mask >> b) & 1u);
+                                drow[M + b] = (double)row_dr[b];
+                                drow[2 * M + b] = (double)c / (double)N;
+                                drow[3 * M + b] = (c > 0 ? usum[le * M + b] / (double)c : 0.0) / DCB_MAX_UTILITY;
+                            }
+                            drow[4 * M] = un;
+                        }
+                    }
+                    if (a.out.dbg_snr)
+                        for (int b = 0; b < M; b++)
+                            a.out.dbg_snr[u * M + b] = snr_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y));
+                }
+                // ---- per-UE outputs and rewards -> global
+                if (a.out.curr_dr) a.out.curr_dr[(size_t)step * a.out.curr_dr_stride + u] = (float)dr;
+                if (a.out.utility) a.out.utility[(size_t)step * a.out.utility_stride + u] = (float)util;
+                if (last && a.out.dbg_curr_dr) a.out.dbg_curr_dr[u] = dr;
+                if (last && a.out.dbg_utility) a.out.dbg_utility[u] = util;
+                if (i == 0) {
+                    if (a.out.sum_utility)
+                        a.out.sum_utility[(size_t)step * a.out.sum_utility_stride + k] = (float)env_sumu[le];
+                    if (last && a.out.dbg_sum_utility) a.out.dbg_sum_utility[k] = env_sumu[le];
+                }
+                if (T > 0) {
+                    if (a.out.lost_conn) a.out.lost_conn[(size_t)step * a.out.lost_conn_stride + u] = (uint8_t)hlost[h];
+                    if (central) {
+                        if (i == 0) {
+                            // central.py:65-73 over the PRE-move rewards
+                            double r = env_rew[le];
+                            if (p.reward == DCB_REWARD_AVG) r = r / (double)N;
+                            if (a.out.reward) a.out.reward[(size_t)step * a.out.reward_stride + k] = (float)r;
+                            if (last && a.out.dbg_reward) a.out.dbg_reward[k] = r;
+                        }
+                    } else {
+                        // multi_agent.py:39-95 on the POST-move state
+                        double agg = util;
+                        if (inrange) {
+                            if (p.reward == DCB_REWARD_AVG) {
+                                int nn = 0;
+                                double tot = 0.0;
+                                for (unsigned long long m = inrange; m; m &= m - 1) {
+                                    const int b = __ffsll((long long)m) - 1;
+                                    nn += cnt_obs[le * M + b];
+                                    tot += usum[le * M + b];
+                                }
+                                if (nn > 0) agg = mask == 0ull ? (tot + util) / (double)(nn + 1) : tot / (double)nn;
+                            } else if (p.reward == DCB_REWARD_SUM) {
+                                // user.py:238-244: UEs sharing any BS with this UE; their PRE-move rewards
+                                agg = 0.0;
+                                for (int j = 0; j < N; j++)
+                                    if (hmask[hbase + le * N + j] & mask) agg += hrb[hbase + le * N + j];
+                            } else {
+                                for (unsigned long long m = inrange; m; m &= m - 1) {
+                                    const int b = __ffsll((long long)m) - 1;
+                                    agg = fmin(agg, umin[le * M + b]);
+                                }
+                            }
+                        }
+                        if (a.out.reward) a.out.reward[(size_t)step * a.out.reward_stride + u] = (float)agg;
+                        if (last && a.out.dbg_reward) a.out.dbg_reward[u] = agg;
+                    }
+                }
+            }
+            // ---- obs tile -> global observation buffer (contiguous span of this CTA)
+            if (a.out.obs) {
+                float *dst = a.out.obs + (size_t)step * a.out.obs_stride + (size_t)env0 * per_env;
+                if (use_tma) {
+                    // generic-proxy writes of the tile -> visible to the async proxy, then one elected thread issues
+                    // the bulk copy shared -> global (TMA, UBLKCP); its completion is awaited before the next rewrite
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    bar_sync(BAR_OBS, G);
+                    if (t == 0) {
+                        const unsigned src = (unsigned)__cvta_generic_to_shared(stage);
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     :: "l"(dst), "r"(src), "r"(tile_bytes) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 } else {
-                    // multi_agent.py:39-95 on the POST-move state
-                    double agg = util;
-                    if (inrange) {
-                        if (p.reward == DCB_REWARD_AVG) {
-                            int nn = 0;
-                            double tot = 0.0;
-                            for (unsigned long long m = inrange; m; m &= m - 1) {
-                                const int b = __ffsll((long long)m) - 1;
-                                nn += cnt_post[le * M + b];
-                                tot += usum[le * M + b];
-                            }
-                            if (nn > 0) agg = mask == 0ull ? (tot + util) / (double)(nn + 1) : tot / (double)nn;
-                        } else if (p.reward == DCB_REWARD_SUM) {
-                            // user.py:238-244: UEs sharing any BS with this UE; their PRE-move rewards
-                            agg = 0.0;
-                            for (int j = 0; j < N; j++)
-                                if (smask[le * N + j] & mask) agg += srb[le * N + j];
-                        } else {
-                            for (unsigned long long m = inrange; m; m &= m - 1) {
-                                const int b = __ffsll((long long)m) - 1;
-                                agg = fmin(agg, umin[le * M + b]);
-                            }
-                        }
-                    }
-                    if (a.out.reward) a.out.reward[(size_t)step * a.out.reward_stride + u] = (float)agg;
-                    if (last && a.out.dbg_reward) a.out.dbg_reward[u] = agg;
+                    bar_sync(BAR_OBS, G);
+                    const int n = (int)(per_env * n_env);
+                    for (int j = t; j < n; j += G) dst[j] = stage[j];
                 }
             }
+            // hand the parity's buffers back to the physics warps
+            bar_arrive(BAR_EMPTY + par, 2 * G);
         }
-        __syncthreads();
-        // ---- obs tile -> global observation buffer (contiguous span of this CTA, coalesced streaming stores)
-        if (a.out.obs) {
-            const size_t per_env = central ? (size_t)(2 * N * M + N) : (size_t)N * OW;
-            float *dst = a.out.obs + (size_t)step * a.out.obs_stride + (size_t)env0 * per_env;
-            const int n = (int)(per_env * n_env);
-            if ((((size_t)dst) & 15) == 0) {
-                const int n4 = n >> 2;
-                const float4 *s4 = reinterpret_cast<const float4 *>(stage);
-                float4 *d4 = reinterpret_cast<float4 *>(dst);
-                for (int j = t; j < n4; j += blockDim.x) __stcs(d4 + j, s4[j]);
-                for (int j = (n4 << 2) + t; j < n; j += blockDim.x) dst[j] = stage[j];
-            } else {
-                for (int j = t; j < n; j += blockDim.x) dst[j] = stage[j];
-            }
-        }
-        __syncthreads();
-    }
-
-    // ---- registers -> state slabs
-    if (valid && T > 0) {
-        p.pos[u] = make_double2(x, y);
-        p.mv[u] = make_uint2(wxy, vpt);
-        p.mask[u] = mask;
-        p.ewma[u] = ewma;
-        if (i == 0) p.time[k] = tk;
+        if (t == 0 && use_tma) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
 }
 
@@ -657,17 +751,30 @@ __global__ void __launch_bounds__(MAXT) dcb_step_kernel(const StepArgs a) {
 
 size_t dcb_step_smem_bytes(int kind, int N, int M, int E) { return (size_t)smem_layout(kind, N, M, E).total; }
 
+// One instantiation per CTA-size class: __launch_bounds__ caps the registers at 65536 / MAXT so that a CTA of that
+// size is always resident.
 cudaError_t dcb_step_set_smem_limit(int threads, size_t smem) {
-    if (threads <= 256)
-        return cudaFuncSetAttribute(dcb_step_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (threads <= 512)
-        return cudaFuncSetAttribute(dcb_step_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    return cudaFuncSetAttribute(dcb_step_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int sm = (int)smem;
+    if (threads <= 256) return cudaFuncSetAttribute(dcb_step_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    if (threads <= 512) return cudaFuncSetAttribute(dcb_step_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    if (threads <= 768) return cudaFuncSetAttribute(dcb_step_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    return cudaFuncSetAttribute(dcb_step_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+}
+
+int dcb_step_regs_per_thread(int threads) {
+    cudaFuncAttributes at;
+    cudaError_t e;
+    if (threads <= 256) e = cudaFuncGetAttributes(&at, dcb_step_kernel<256>);
+    else if (threads <= 512) e = cudaFuncGetAttributes(&at, dcb_step_kernel<512>);
+    else if (threads <= 768) e = cudaFuncGetAttributes(&at, dcb_step_kernel<768>);
+    else e = cudaFuncGetAttributes(&at, dcb_step_kernel<1024>);
+    return e == cudaSuccess ? at.numRegs : 128;
 }
 
 cudaError_t dcb_launch_step(const StepArgs &a, int threads, int grid, size_t smem, cudaStream_t s) {
     if (threads <= 256) dcb_step_kernel<256><<<grid, threads, smem, s>>>(a);
     else if (threads <= 512) dcb_step_kernel<512><<<grid, threads, smem, s>>>(a);
+    else if (threads <= 768) dcb_step_kernel<768><<<grid, threads, smem, s>>>(a);
     else dcb_step_kernel<1024><<<grid, threads, smem, s>>>(a);
     return cudaGetLastError();
 }

@@ -121,8 +121,8 @@ const char *dcb_last_error(void);
 
 /*
  * Allocate the state slabs for K envs on cfg->device and generate the per-UE RNG tables.  Supported shapes:
- * 1 <= M <= 64, N * max(16*M, 4*(4*M+1)) bytes of shared memory per env must fit one CTA (N*M <= ~13000),
- * N <= 1024.  Synchronous.
+ * 1 <= M <= 64, N <= 512, and one env's working set (obs tile 4*(4M+1) + link values 8*(M|1) + ~70 bytes per UE)
+ * must fit the 227 KB of shared memory of one CTA.  Synchronous.
  */
 int dcb_create(const dcb_config *cfg, dcb_env **out);
 void dcb_destroy(dcb_env *env);
