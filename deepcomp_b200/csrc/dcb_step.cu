@@ -67,7 +67,7 @@ __host__ __device__ inline SmemLayout smem_layout(int kind, int N, int M, int E)
     const int EN = E * N, EM = E * M;
     int o = 0;
     L.off_tab = o;      o += (int)sizeof(MathTables);                // 3 x 128 B: one bank row per table
-    L.off_stage = o;    o += align16(EN * obs_width(kind, M) * 4);   // float obs tile of the CTA
+    L.off_stage = o;    o += align16(EN * obs_width(kind, M) * 4) + 16;   // float obs tile of the CTA (+ alignment shift)
     L.off_x = o;        o += align16(EN * row_stride(M) * 8);        // link values of connected links
     L.off_sum_pre = o;  o += align16(EM * 8);
     L.off_sum_post = o; o += align16(EM * 8);
@@ -577,25 +577,29 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
         // ===================================================================== observer warps
         // obs tile row of this UE: multi [connected(M) | dr(M) | ues_at_bs(M) | util_at_bs(M) | utility(1)] per UE
         // (variants.py:271-303); central [connected(N*M) | dr(N*M) | utility(N)] per env (central.py:31-57)
-        float *row_conn = central ? stage + (size_t)le * (2 * N * M + N) + i * M : stage + (size_t)t * OW;
-        float *row_dr = central ? row_conn + N * M : row_conn + M;
+        const int row_off = central ? le * (2 * N * M + N) + i * M : t * OW;
         const float hr = (float)(p.snr_h - 1.5);
         const bool dbg_any = a.out.dbg_obs || a.out.dbg_snr;
-        // obs tile -> global: one TMA bulk store per step when the CTA's span is 16-byte aligned (else a copy loop)
+        // obs tile -> global: ONE TMA bulk store (cp.async.bulk shared -> global) per CTA and step.  TMA wants 16-byte
+        // aligned addresses and sizes; the CTA's span of the observation buffer starts at an arbitrary multiple of 4
+        // bytes, so the tile is built in shared memory at the same offset modulo 16 and the (< 16 byte) head and tail
+        // are written with scalar stores.
         const size_t per_env = central ? (size_t)(2 * N * M + N) : (size_t)N * OW;
         const unsigned tile_bytes = (unsigned)(per_env * n_env * 4);
-        const bool use_tma = a.out.obs && (tile_bytes & 15u) == 0 &&
-                             ((((size_t)a.out.obs) + (size_t)env0 * per_env * 4) & 15) == 0 &&
-                             ((a.out.obs_stride * 4) & 15) == 0;
 
         for (int step = 0; step < n_iter; step++) {
             const bool last = step == n_iter - 1;
             const int par = step & 1;
             unsigned *bits_post = bits_post2 + par * L.nbits;
             const int hbase = par * EN;
+            float *dst = a.out.obs ? a.out.obs + (size_t)step * a.out.obs_stride + (size_t)env0 * per_env : nullptr;
+            const unsigned mis = (unsigned)((size_t)dst & 15);
+            float *tile = stage + (mis >> 2);
+            float *row_conn = tile + row_off;
+            float *row_dr = central ? row_conn + N * M : row_conn + M;
             bar_sync(BAR_FULL + par, 2 * G);
             // the previous step's TMA store must have finished reading the tile before anyone rewrites it
-            if (t == 0 && use_tma && step > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (t == 0 && step > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             if (!central)
                 reduce_utility(t, G, bits_post, hutil + hbase, N, M, n_env, S, p.reward == DCB_REWARD_MIN, cnt_obs, usum,
                                umin, f_ues, f_util);
@@ -633,7 +637,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                 const double un = util / DCB_MAX_UTILITY;                              // variants.py:287
                 if (central) {
                     for (int b = 0; b < M; b++) row_conn[b] = (float)((unsigned)(mask >> b) & 1u);
-                    stage[(size_t)le * (2 * N * M + N) + 2 * N * M + i] = (float)un;
+                    tile[(size_t)le * (2 * N * M + N) + 2 * N * M + i] = (float)un;
                 } else {
                     const float *fu = f_ues + le * M, *fa = f_util + le * M;
                     for (int b = 0; b < M; b++) {
@@ -721,29 +725,32 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                 }
             }
             // ---- obs tile -> global observation buffer (contiguous span of this CTA)
-            if (a.out.obs) {
-                float *dst = a.out.obs + (size_t)step * a.out.obs_stride + (size_t)env0 * per_env;
-                if (use_tma) {
-                    // generic-proxy writes of the tile -> visible to the async proxy, then one elected thread issues
-                    // the bulk copy shared -> global (TMA, UBLKCP); its completion is awaited before the next rewrite
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    bar_sync(BAR_OBS, G);
-                    if (t == 0) {
-                        const unsigned src = (unsigned)__cvta_generic_to_shared(stage);
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                     :: "l"(dst), "r"(src), "r"(tile_bytes) : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
+            if (dst) {
+                // generic-proxy writes of the tile -> visible to the async proxy; then one elected thread issues the
+                // bulk copy (TMA, UBLKCP); its read completion is awaited before the tile is rewritten next step
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                bar_sync(BAR_OBS, G);
+                const unsigned head = (16u - mis) & 15u;                       // bytes up to the first 16-byte boundary
+                const unsigned bulk = tile_bytes > head ? (tile_bytes - head) & ~15u : 0u;
+                if (t == 0 && bulk) {
+                    const unsigned src = (unsigned)__cvta_generic_to_shared(tile) + head;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(reinterpret_cast<char *>(dst) + head), "r"(src), "r"(bulk) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                const int nf = (int)(tile_bytes >> 2);
+                if (bulk) {
+                    const int hf = (int)(head >> 2), tail0 = (int)((head + bulk) >> 2);   // <= 3 floats on either side
+                    if (t >= 1 && t <= 3 && t - 1 < hf) dst[t - 1] = tile[t - 1];
+                    if (t >= 4 && t <= 6 && tail0 + t - 4 < nf) dst[tail0 + t - 4] = tile[tail0 + t - 4];
                 } else {
-                    bar_sync(BAR_OBS, G);
-                    const int n = (int)(per_env * n_env);
-                    for (int j = t; j < n; j += G) dst[j] = stage[j];
+                    for (int j = t; j < nf; j += G) dst[j] = tile[j];
                 }
             }
             // hand the parity's buffers back to the physics warps
             bar_arrive(BAR_EMPTY + par, 2 * G);
         }
-        if (t == 0 && use_tma) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
 }
 
