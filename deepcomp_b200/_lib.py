@@ -53,7 +53,8 @@ class DcbError(RuntimeError):
 
 
 def lib_path():
-    return _build.LIB
+    """In-tree library; DCB_LIB_PATH overrides it (A/B experiments with an alternative build)."""
+    return os.environ.get('DCB_LIB_PATH') or _build.LIB
 
 
 def load():
@@ -62,7 +63,7 @@ def load():
     if _LIB is not None:
         return _LIB
     path = lib_path()
-    if _build.needs_build():
+    if path == _build.LIB and _build.needs_build():
         try:
             _build.build()
         except (OSError, Exception) as exc:  # noqa: BLE001 -- nvcc missing / compile error

@@ -100,6 +100,7 @@ __host__ __device__ inline SmemLayout smem_layout(int kind, int N, int M, int E)
     return L;
 }
 
+// [region:helpers.radio]
 // ------------------------------------------------------------------------------------------------ radio model
 __device__ __forceinline__ double dist2(double ax, double ay, double bx, double by) {
     // shapely/GEOS Point.distance = sqrt(dx*dx + dy*dy) (station.py:124); the square is compared / rooted later
@@ -169,6 +170,7 @@ __device__ __forceinline__ float norm_snr_f32(float d2, float d2min, float hr) {
     return d2 == d2min ? 1.0f : fminf(q * sq * ex, 1.0f);   // the closest BS is exactly 1 (variants.py:284)
 }
 
+// [region:helpers.barriers]
 // ------------------------------------------------------------------------------------------------ named barriers
 // Barrier 0 is __syncthreads (set-up only).  Each warp group has a private barrier; FULL[parity] / EMPTY[parity]
 // hand a buffer from the physics warps to the observer warps and back (arrive on one side, sync on the other).
@@ -188,6 +190,7 @@ __device__ __forceinline__ bool bar_or(int id, int n, bool pred) {
 
 // ------------------------------------------------------------------------------------------------ reductions
 // (tid, gsize: thread index within / size of the calling warp group)
+// [region:reduce_links]
 // For every (env, BS) pair walk the bitset of connected UEs: count, sum of link values X[ue][bs], first arg-max
 // (max-cap only).  Done for two bitsets (current masks -> *_a, next step's masks -> *_b).  S lanes per pair take the
 // 32-UE words round-robin; fixed combination order -> deterministic.
@@ -250,6 +253,7 @@ __device__ __forceinline__ void reduce_links(int tid, int gsize, const double *X
     }
 }
 
+// [region:reduce_utility]
 // Per-BS connected count -> cnt, total utility (station.py:63-69) -> usum, the two per-BS observation entries
 // (variants.py:296-299, station.py:71-76) -> f_ues, f_util; min (station.py:78-83) -> umin.
 __device__ __forceinline__ void reduce_utility(int tid, int gsize, const unsigned *bits, const double *su, int N,
@@ -295,6 +299,7 @@ __device__ __forceinline__ void reduce_utility(int tid, int gsize, const unsigne
     }
 }
 
+// [region:reduce_env]
 // Per-env reduction of a per-UE vector: mode 0 = sum, 2 = min (one warp per env)
 __device__ __forceinline__ void reduce_env(int tid, int gsize, const double *v, int N, int n_env, int mode,
                                            double *out) {
@@ -312,6 +317,7 @@ __device__ __forceinline__ void reduce_env(int tid, int gsize, const double *v, 
     }
 }
 
+// [region:kernel.setup]
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int MAXT>
 __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(const StepArgs a) {
@@ -379,6 +385,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
     __syncthreads();
 
     if (!is_obs) {
+// [region:P.load]
         // ===================================================================== physics warps
         double x = 0, y = 0, ewma = 0;
         unsigned long long mask = 0;
@@ -408,6 +415,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
             unsigned *bits_pre = bits_pre2 + par * L.nbits;
             double rb = 0.0;      // reward before the move (base.py:446)
             int lost = 0;
+// [region:P.top+fresh]
             // the observers must be done with this parity's hand-off buffers (step - 2)
             if (step >= 2) bar_sync(BAR_EMPTY + par, 2 * G);
             if (T > 0) {
@@ -455,6 +463,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                     bar_sync(BAR_PHYS, G);
                     for (int j = t; j < L.nbits; j += G) bits_fresh[j] = 0u;
                 }
+// [region:P.pre_rates]
                 if (valid) {
                     // ---- update_ue_drs_rewards (base.py:315-335): Basestation.data_rate_shared (station.py:152-202)
                     // per connected link; the ue.bs_dr cache goes back into Xrow
@@ -469,6 +478,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                     }
                     // ---- calc_reward (base.py:158-167), penalties are identically 0 (base.py:257)
                     rb = log_utility(tab, dr) / DCB_MAX_UTILITY;
+// [region:P.move]
                     // ---- User.move (user.py:159-173) -> RandomWaypoint.step (movement.py:158-181)
                     double wx = (double)(wxy & 0xffffu), wy = (double)(wxy >> 16);
                     unsigned pause = (vpt >> 8) & 0xffu;
@@ -504,6 +514,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                             y = y + vel * (vy / norm);
                         }
                     }
+// [region:P.drop+ewma]
                     // ---- check_bs_connection (user.py:175-188) + update_ewma_dr (user.py:148-157)
                     double keep = 0.0;
                     for (unsigned long long m = mask; m; m &= m - 1) {
@@ -515,6 +526,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                     tk += 1;                                                           // base.py:454
                 }
             }
+// [region:P.prefetch+sparse]
             // ---- link values at the new position for update_ue_drs_rewards(update_only=True) (base.py:451) and for
             // the next step's pre-move update (its action toggles one link, user.py:190-229: known now)
             mask_next = mask;
@@ -537,6 +549,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                     if ((mask_next >> b) & 1ull) atomicOr(&bits_pre[bit_word + b * NW], bit_val);
                 }
             }
+// [region:P.reduce_phase]
             bar_sync(BAR_PHYS, G);
             reduce_links(t, G, X, bits_post, bits_pre, N, M, MS, n_env, S, p.has_maxcap, cnt_post, sum_post, arg_post,
                          cnt_pre, sum_pre, arg_pre);
@@ -544,6 +557,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
             // bits_pre of this parity is consumed; its next use is two steps (>= 2 group barriers) away
             for (int j = t; j < L.nbits; j += G) bits_pre[j] = 0u;
             if (valid) {
+// [region:P.post_rates+handoff]
                 // ---- post-move rates -> utility (user.py:76-92) -> hand-off
                 const double ee = ewma + DCB_EPSILON;
                 double dr = 0.0;
@@ -561,6 +575,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
             }
             bar_arrive(BAR_FULL + par, 2 * G);
         }
+// [region:P.drain+store]
         // drain: the observers' last (up to two) EMPTY arrivals
         if (n_iter >= 2) bar_sync(BAR_EMPTY + (n_iter & 1), 2 * G);
         bar_sync(BAR_EMPTY + ((n_iter - 1) & 1), 2 * G);
@@ -574,6 +589,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
             if (i == 0) p.time[k] = tk;
         }
     } else {
+// [region:O.setup]
         // ===================================================================== observer warps
         // obs tile row of this UE: multi [connected(M) | dr(M) | ues_at_bs(M) | util_at_bs(M) | utility(1)] per UE
         // (variants.py:271-303); central [connected(N*M) | dr(N*M) | utility(N)] per env (central.py:31-57)
@@ -597,6 +613,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
             float *tile = stage + (mis >> 2);
             float *row_conn = tile + row_off;
             float *row_dr = central ? row_conn + N * M : row_conn + M;
+// [region:O.full_wait+util_reduce]
             bar_sync(BAR_FULL + par, 2 * G);
             // the previous step's TMA store must have finished reading the tile before anyone rewrites it
             if (t == 0 && step > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -612,6 +629,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                 const int h = hbase + t;
                 const double x = hx[h], y = hy[h], util = hutil[h], dr = hdr[h];
                 const unsigned long long mask = hmask[h];
+// [region:O.dense]
                 // ---- dense pass A: squared distances (fp64, exact range decision multi_agent.py:60 /
                 // station.py:222-226), parked in the tile as float for pass B
                 unsigned long long inrange = 0ull;
@@ -633,6 +651,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                     for (int b = 0; b < M; b++)
                         row_dr[b] = (float)(snr_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y)) * inv_max);
                 }
+// [region:O.staging]
                 // ---- rest of the observation row
                 const double un = util / DCB_MAX_UTILITY;                              // variants.py:287
                 if (central) {
@@ -674,6 +693,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                         for (int b = 0; b < M; b++)
                             a.out.dbg_snr[u * M + b] = snr_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y));
                 }
+// [region:O.outputs+reward]
                 // ---- per-UE outputs and rewards -> global
                 if (a.out.curr_dr) a.out.curr_dr[(size_t)step * a.out.curr_dr_stride + u] = (float)dr;
                 if (a.out.utility) a.out.utility[(size_t)step * a.out.utility_stride + u] = (float)util;
@@ -724,6 +744,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                     }
                 }
             }
+// [region:O.tile_out]
             // ---- obs tile -> global observation buffer (contiguous span of this CTA)
             if (dst) {
                 // generic-proxy writes of the tile -> visible to the async proxy; then one elected thread issues the
