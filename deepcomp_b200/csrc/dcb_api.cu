@@ -106,7 +106,7 @@ int choose_envs_per_cta(int K, int N, int M, int kind, int num_sms, size_t smem_
         if (sm > smem_cap) break;
         const int group = (E * N + 31) / 32 * 32;
         const int threads = 2 * group;
-        const int regs = dcb_step_regs_per_thread(threads);
+        const int regs = dcb_step_regs_per_thread(threads, M);
         int per_sm = (int)(smem_cap / sm);
         if (2048 / threads < per_sm) per_sm = 2048 / threads;
         if (65536 / (regs * threads) < per_sm) per_sm = 65536 / (regs * threads);
@@ -130,6 +130,7 @@ int choose_envs_per_cta(int K, int N, int M, int kind, int num_sms, size_t smem_
 int launch_step(dcb_env *env, const int32_t *d_actions, int T, const dcb_outputs *out, cudaStream_t s) {
     StepArgs a;
     a.p = env->p;
+    a.L = dcb_smem_layout(env->p.kind, env->p.N, env->p.M, env->p.E);
     a.actions = d_actions;
     a.T = T;
     if (out) a.out = *out;
@@ -306,7 +307,7 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     p.pos = env->d_pos; p.mv = env->d_mv; p.mask = env->d_mask; p.ewma = env->d_ewma; p.time = env->d_time;
     p.init_pos = env->d_init_pos; p.table = env->d_table; p.err = env->d_err;
 
-    cudaError_t e = dcb_step_set_smem_limit(env->threads, env->smem);
+    cudaError_t e = dcb_step_set_smem_limit(env->threads, M, env->smem);
     if (e != cudaSuccess) {
         dcb_destroy(env);
         return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", env->smem, cudaGetErrorString(e));

@@ -50,8 +50,64 @@ struct DevParams {
     int *err;
 };
 
+// ---- shared-memory layout of the step kernel (byte offsets), computed once on the host
+struct SmemLayout {
+    int off_tab, off_stage, off_x, off_sum_pre, off_sum_post, off_usum, off_umin, off_fues, off_futil, off_hx, off_hy,
+        off_hmask, off_hutil, off_hrb, off_hdr, off_hlost, off_env_rew, off_env_sumu, off_bsx, off_bsy, off_vel,
+        off_cnt_pre, off_arg_pre, off_cnt_post, off_arg_post, off_cnt_obs, off_bits, off_share;
+    int nbits;   // words per bitset
+    int total;
+};
+
+__host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
+
+__host__ __device__ inline int obs_width(int kind, int M) { return kind == DCB_KIND_CENTRAL ? 2 * M + 1 : 4 * M + 1; }
+
+// Row stride (in doubles) of the [E*N][M] link matrix: odd, so that the 16 lanes of one 64-bit shared-memory access
+// phase (consecutive UEs, same BS) hit 16 different bank pairs.
+__host__ __device__ inline int row_stride(int M) { return M | 1; }
+
+__host__ __device__ inline SmemLayout dcb_smem_layout(int kind, int N, int M, int E) {
+    SmemLayout L;
+    const int EN = E * N, EM = E * M;
+    int o = 0;
+    L.off_tab = o;      o += 3 * 16 * 8;                             // 3 x 128 B: one bank row per table
+    L.off_stage = o;    o += align16(EN * obs_width(kind, M) * 4) + 16;   // float obs tile of the CTA (+ alignment shift)
+    L.off_x = o;        o += align16(EN * row_stride(M) * 8);        // link values of connected links
+    L.off_sum_pre = o;  o += align16(EM * 8);
+    L.off_sum_post = o; o += align16(EM * 8);
+    L.off_usum = o;     o += align16(EM * 8);
+    L.off_umin = o;     o += align16(EM * 8);
+    L.off_fues = o;     o += align16(EM * 4);
+    L.off_futil = o;    o += align16(EM * 4);
+    // physics -> observer hand-off, two parities: position, mask, utility, pre-move reward, rate, lost links
+    L.off_hx = o;       o += align16(2 * EN * 8);
+    L.off_hy = o;       o += align16(2 * EN * 8);
+    L.off_hmask = o;    o += align16(2 * EN * 8);
+    L.off_hutil = o;    o += align16(2 * EN * 8);
+    L.off_hrb = o;      o += align16(2 * EN * 8);
+    L.off_hdr = o;      o += align16(2 * EN * 8);
+    L.off_hlost = o;    o += align16(2 * EN * 4);
+    L.off_env_rew = o;  o += align16(E * 8);
+    L.off_env_sumu = o; o += align16(E * 8);
+    L.off_bsx = o;      o += align16(M * 8);
+    L.off_bsy = o;      o += align16(M * 8);
+    L.off_vel = o;      o += align16(N * 8);
+    L.off_cnt_pre = o;  o += align16(EM * 4);
+    L.off_arg_pre = o;  o += align16(EM * 4);
+    L.off_cnt_post = o; o += align16(EM * 4);
+    L.off_arg_post = o; o += align16(EM * 4);
+    L.off_cnt_obs = o;  o += align16(EM * 4);
+    L.nbits = EM * ((N + 31) / 32);
+    L.off_bits = o;     o += align16(5 * L.nbits * 4);               // UE bitsets per (env, BS): post[2], pre[2], fresh
+    L.off_share = o;    o += align16(M * 4);
+    L.total = o;
+    return L;
+}
+
 struct StepArgs {
     DevParams p;
+    SmemLayout L;
     const int32_t *actions;  // [T][K][N]
     int T;                   // 0 = observe only
     dcb_outputs out;
@@ -89,6 +145,6 @@ cudaError_t dcb_launch_reset(const ResetArgs &a, cudaStream_t s);
 cudaError_t dcb_launch_advance_skip(int K, int N, const int32_t *env_ids, int n_ids, const uint2 *mv,
                                     uint32_t *mv_skip, const uint32_t *pos_skip, cudaStream_t s);
 cudaError_t dcb_launch_step(const StepArgs &a, int threads, int grid, size_t smem, cudaStream_t s);
-cudaError_t dcb_step_set_smem_limit(int threads, size_t smem);
+cudaError_t dcb_step_set_smem_limit(int threads, int n_bs, size_t smem);
 size_t dcb_step_smem_bytes(int kind, int N, int M, int E);
-int dcb_step_regs_per_thread(int threads);
+int dcb_step_regs_per_thread(int threads, int n_bs);

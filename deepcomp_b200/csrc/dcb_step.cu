@@ -44,61 +44,9 @@
 #include "dcb_internal.h"
 #include "dcb_math.cuh"
 
+static_assert(sizeof(MathTables) == 3 * 16 * 8, "SmemLayout reserves 3 x 128 B for the math tables");
+
 namespace {
-
-struct SmemLayout {
-    int off_tab, off_stage, off_x, off_sum_pre, off_sum_post, off_usum, off_umin, off_fues, off_futil, off_hx, off_hy,
-        off_hmask, off_hutil, off_hrb, off_hdr, off_hlost, off_env_rew, off_env_sumu, off_bsx, off_bsy, off_vel,
-        off_cnt_pre, off_arg_pre, off_cnt_post, off_arg_post, off_cnt_obs, off_bits, off_share;
-    int nbits;   // words per bitset
-    int total;
-};
-
-__host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
-
-__host__ __device__ inline int obs_width(int kind, int M) { return kind == DCB_KIND_CENTRAL ? 2 * M + 1 : 4 * M + 1; }
-
-// Row stride (in doubles) of the [E*N][M] link matrix: odd, so that the 16 lanes of one 64-bit shared-memory access
-// phase (consecutive UEs, same BS) hit 16 different bank pairs.
-__host__ __device__ inline int row_stride(int M) { return M | 1; }
-
-__host__ __device__ inline SmemLayout smem_layout(int kind, int N, int M, int E) {
-    SmemLayout L;
-    const int EN = E * N, EM = E * M;
-    int o = 0;
-    L.off_tab = o;      o += (int)sizeof(MathTables);                // 3 x 128 B: one bank row per table
-    L.off_stage = o;    o += align16(EN * obs_width(kind, M) * 4) + 16;   // float obs tile of the CTA (+ alignment shift)
-    L.off_x = o;        o += align16(EN * row_stride(M) * 8);        // link values of connected links
-    L.off_sum_pre = o;  o += align16(EM * 8);
-    L.off_sum_post = o; o += align16(EM * 8);
-    L.off_usum = o;     o += align16(EM * 8);
-    L.off_umin = o;     o += align16(EM * 8);
-    L.off_fues = o;     o += align16(EM * 4);
-    L.off_futil = o;    o += align16(EM * 4);
-    // physics -> observer hand-off, two parities: position, mask, utility, pre-move reward, rate, lost links
-    L.off_hx = o;       o += align16(2 * EN * 8);
-    L.off_hy = o;       o += align16(2 * EN * 8);
-    L.off_hmask = o;    o += align16(2 * EN * 8);
-    L.off_hutil = o;    o += align16(2 * EN * 8);
-    L.off_hrb = o;      o += align16(2 * EN * 8);
-    L.off_hdr = o;      o += align16(2 * EN * 8);
-    L.off_hlost = o;    o += align16(2 * EN * 4);
-    L.off_env_rew = o;  o += align16(E * 8);
-    L.off_env_sumu = o; o += align16(E * 8);
-    L.off_bsx = o;      o += align16(M * 8);
-    L.off_bsy = o;      o += align16(M * 8);
-    L.off_vel = o;      o += align16(N * 8);
-    L.off_cnt_pre = o;  o += align16(EM * 4);
-    L.off_arg_pre = o;  o += align16(EM * 4);
-    L.off_cnt_post = o; o += align16(EM * 4);
-    L.off_arg_post = o; o += align16(EM * 4);
-    L.off_cnt_obs = o;  o += align16(EM * 4);
-    L.nbits = EM * ((N + 31) / 32);
-    L.off_bits = o;     o += align16(5 * L.nbits * 4);               // UE bitsets per (env, BS): post[2], pre[2], fresh
-    L.off_share = o;    o += align16(M * 4);
-    L.total = o;
-    return L;
-}
 
 // [region:helpers.radio]
 // ------------------------------------------------------------------------------------------------ radio model
@@ -169,6 +117,11 @@ __device__ __forceinline__ float norm_snr_f32(float d2, float d2min, float hr) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(hr * lg));
     return d2 == d2min ? 1.0f : fminf(q * sq * ex, 1.0f);   // the closest BS is exactly 1 (variants.py:284)
 }
+
+template <bool M32> struct MaskType { typedef unsigned long long type; };
+template <> struct MaskType<true> { typedef unsigned type; };
+__device__ __forceinline__ int mask_ffs(unsigned m) { return __ffs((int)m); }
+__device__ __forceinline__ int mask_ffs(unsigned long long m) { return __ffsll((long long)m); }
 
 // [region:helpers.barriers]
 // ------------------------------------------------------------------------------------------------ named barriers
@@ -319,14 +272,16 @@ __device__ __forceinline__ void reduce_env(int tid, int gsize, const double *v, 
 
 // [region:kernel.setup]
 // ------------------------------------------------------------------------------------------------ the kernel
-template <int MAXT>
+// M32: all connection / in-range masks fit 32 bits (n_bs <= 32) -- halves the integer work on the mask paths
+template <int MAXT, bool M32>
 __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(const StepArgs a) {
+    using mask_t = typename MaskType<M32>::type;
     extern __shared__ __align__(128) unsigned char smem[];
     const DevParams &p = a.p;
     const int N = p.N, M = p.M, E = p.E, S = p.S;
     const int MS = row_stride(M);
     const int NW = (N + 31) >> 5;
-    const SmemLayout L = smem_layout(p.kind, N, M, E);
+    const SmemLayout &L = a.L;      // computed on the host: offsets come straight from the constant bank
     MathTables *tab = reinterpret_cast<MathTables *>(smem + L.off_tab);
     float *stage = reinterpret_cast<float *>(smem + L.off_stage);
     double *X = reinterpret_cast<double *>(smem + L.off_x);
@@ -388,7 +343,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
 // [region:P.load]
         // ===================================================================== physics warps
         double x = 0, y = 0, ewma = 0;
-        unsigned long long mask = 0;
+        mask_t mask = 0;
         unsigned wxy = 0, vpt = 0;
         int tk = 0;
         if (valid) {
@@ -396,7 +351,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
             x = ps.x; y = ps.y;
             const uint2 mv = p.mv[u];
             wxy = mv.x; vpt = mv.y;
-            mask = p.mask[u];
+            mask = (mask_t)p.mask[u];
             ewma = p.ewma[u];
             tk = p.time[k];
         }
@@ -406,7 +361,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
         const int bit_word = le * M * NW + (i >> 5);
         const unsigned bit_val = 1u << (i & 31);
         // mask after the NEXT step's action, prepared at the end of a step (only meaningful when !fresh)
-        unsigned long long mask_next = 0;
+        mask_t mask_next = 0;
 
         for (int step = 0; step < n_iter; step++) {
             const bool last = step == n_iter - 1;
@@ -428,7 +383,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                     const uint32_t e = p.table[u * p.D];
                     wxy = (e & 0x3fffu) | (((e >> 14) & 0x3fffu) << 16);
                     vpt = (e >> 28) | (1u << 16);
-                    mask = 0ull; ewma = 0.0; tk = 0;
+                    mask = 0; ewma = 0.0; tk = 0;
                     fresh = true;
                 }
                 if (valid) {
@@ -439,7 +394,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                             atomicOr(p.err, DCB_ERRBIT_ACTION);
                         } else if (act > 0) {
                             const int b = act - 1;
-                            const unsigned long long bit = 1ull << b;
+                            const mask_t bit = (mask_t)1 << b;
                             if (mask & bit) mask &= ~bit;
                             else if (dist2(bsx[b], bsy[b], x, y) <= p.thr_d2) mask |= bit;   // can_connect, station.py:222-226
                         }
@@ -451,8 +406,8 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                     // some env of this CTA has no inherited aggregates: recompute link values and reduce
                     if (valid) {
                         const double iee = dcb_rcp(ewma + DCB_EPSILON);
-                        for (unsigned long long m = mask; m; m &= m - 1) {
-                            const int b = __ffsll((long long)m) - 1;
+                        for (mask_t m = mask; m; m &= m - 1) {
+                            const int b = mask_ffs(m) - 1;
                             Xrow[b] = link_value(share[b], rate_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y)), iee);
                             atomicOr(&bits_fresh[bit_word + b * NW], bit_val);
                         }
@@ -469,8 +424,8 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                     // per connected link; the ue.bs_dr cache goes back into Xrow
                     const double ee = ewma + DCB_EPSILON;
                     double dr = 0.0;
-                    for (unsigned long long m = mask; m; m &= m - 1) {
-                        const int b = __ffsll((long long)m) - 1;
+                    for (mask_t m = mask; m; m &= m - 1) {
+                        const int b = mask_ffs(m) - 1;
                         const int pr = le * M + b;
                         const double r = shared_rate(share[b], Xrow[b], cnt_pre[pr], sum_pre[pr], arg_pre[pr], i, ee);
                         Xrow[b] = r;
@@ -517,10 +472,10 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
 // [region:P.drop+ewma]
                     // ---- check_bs_connection (user.py:175-188) + update_ewma_dr (user.py:148-157)
                     double keep = 0.0;
-                    for (unsigned long long m = mask; m; m &= m - 1) {
-                        const int b = __ffsll((long long)m) - 1;
+                    for (mask_t m = mask; m; m &= m - 1) {
+                        const int b = mask_ffs(m) - 1;
                         if (dist2(bsx[b], bsy[b], x, y) <= p.thr_d2) keep += Xrow[b];
-                        else { mask &= ~(1ull << b); lost++; }
+                        else { mask &= ~((mask_t)1 << b); lost++; }
                     }
                     ewma = 0.9 * keep + (1 - 0.9) * ewma;
                     tk += 1;                                                           // base.py:454
@@ -537,16 +492,16 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                         atomicOr(p.err, DCB_ERRBIT_ACTION);
                     } else if (act > 0) {
                         const int b = act - 1;
-                        const unsigned long long bit = 1ull << b;
+                        const mask_t bit = (mask_t)1 << b;
                         if ((mask & bit) || dist2(bsx[b], bsy[b], x, y) <= p.thr_d2) mask_next = mask ^ bit;
                     }
                 }
                 const double iee = dcb_rcp(ewma + DCB_EPSILON);
-                for (unsigned long long m = mask | mask_next; m; m &= m - 1) {
-                    const int b = __ffsll((long long)m) - 1;
+                for (mask_t m = mask | mask_next; m; m &= m - 1) {
+                    const int b = mask_ffs(m) - 1;
                     Xrow[b] = link_value(share[b], rate_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y)), iee);
-                    if ((mask >> b) & 1ull) atomicOr(&bits_post[bit_word + b * NW], bit_val);
-                    if ((mask_next >> b) & 1ull) atomicOr(&bits_pre[bit_word + b * NW], bit_val);
+                    if ((mask >> b) & 1) atomicOr(&bits_post[bit_word + b * NW], bit_val);
+                    if ((mask_next >> b) & 1) atomicOr(&bits_pre[bit_word + b * NW], bit_val);
                 }
             }
 // [region:P.reduce_phase]
@@ -561,8 +516,8 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                 // ---- post-move rates -> utility (user.py:76-92) -> hand-off
                 const double ee = ewma + DCB_EPSILON;
                 double dr = 0.0;
-                for (unsigned long long m = mask; m; m &= m - 1) {
-                    const int b = __ffsll((long long)m) - 1;
+                for (mask_t m = mask; m; m &= m - 1) {
+                    const int b = mask_ffs(m) - 1;
                     const int pr = le * M + b;
                     const double r = shared_rate(share[b], Xrow[b], cnt_post[pr], sum_post[pr], arg_post[pr], i, ee);
                     if (last && a.out.dbg_link_rate) a.out.dbg_link_rate[u * M + b] = r;
@@ -584,7 +539,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
         if (valid && T > 0) {
             p.pos[u] = make_double2(x, y);
             p.mv[u] = make_uint2(wxy, vpt);
-            p.mask[u] = mask;
+            p.mask[u] = (unsigned long long)mask;
             p.ewma[u] = ewma;
             if (i == 0) p.time[k] = tk;
         }
@@ -628,17 +583,17 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
             if (valid) {
                 const int h = hbase + t;
                 const double x = hx[h], y = hy[h], util = hutil[h], dr = hdr[h];
-                const unsigned long long mask = hmask[h];
+                const mask_t mask = (mask_t)hmask[h];
 // [region:O.dense]
                 // ---- dense pass A: squared distances (fp64, exact range decision multi_agent.py:60 /
                 // station.py:222-226), parked in the tile as float for pass B
-                unsigned long long inrange = 0ull;
+                mask_t inrange = 0;
                 double d2min = CUDART_INF;
 #pragma unroll 2
                 for (int b = 0; b < M; b++) {
                     const double d2 = dist2(bsx[b], bsy[b], x, y);
                     d2min = fmin(d2min, d2);
-                    if (d2 <= p.thr_d2) inrange |= 1ull << b;
+                    if (d2 <= p.thr_d2) inrange |= (mask_t)1 << b;
                     row_dr[b] = (float)d2;
                 }
                 // ---- dense pass B: 'dr' = snr_b / max_b snr_b (variants.py:276-284) = (d2min / d2_b)^h
@@ -721,20 +676,20 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                             if (p.reward == DCB_REWARD_AVG) {
                                 int nn = 0;
                                 double tot = 0.0;
-                                for (unsigned long long m = inrange; m; m &= m - 1) {
-                                    const int b = __ffsll((long long)m) - 1;
+                                for (mask_t m = inrange; m; m &= m - 1) {
+                                    const int b = mask_ffs(m) - 1;
                                     nn += cnt_obs[le * M + b];
                                     tot += usum[le * M + b];
                                 }
-                                if (nn > 0) agg = mask == 0ull ? (tot + util) / (double)(nn + 1) : tot / (double)nn;
+                                if (nn > 0) agg = mask == 0 ? (tot + util) / (double)(nn + 1) : tot / (double)nn;
                             } else if (p.reward == DCB_REWARD_SUM) {
                                 // user.py:238-244: UEs sharing any BS with this UE; their PRE-move rewards
                                 agg = 0.0;
                                 for (int j = 0; j < N; j++)
-                                    if (hmask[hbase + le * N + j] & mask) agg += hrb[hbase + le * N + j];
+                                    if ((mask_t)hmask[hbase + le * N + j] & mask) agg += hrb[hbase + le * N + j];
                             } else {
-                                for (unsigned long long m = inrange; m; m &= m - 1) {
-                                    const int b = __ffsll((long long)m) - 1;
+                                for (mask_t m = inrange; m; m &= m - 1) {
+                                    const int b = mask_ffs(m) - 1;
                                     agg = fmin(agg, umin[le * M + b]);
                                 }
                             }
@@ -777,32 +732,39 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
 
 }  // namespace
 
-size_t dcb_step_smem_bytes(int kind, int N, int M, int E) { return (size_t)smem_layout(kind, N, M, E).total; }
+size_t dcb_step_smem_bytes(int kind, int N, int M, int E) { return (size_t)dcb_smem_layout(kind, N, M, E).total; }
 
-// One instantiation per CTA-size class: __launch_bounds__ caps the registers at 65536 / MAXT so that a CTA of that
-// size is always resident.
-cudaError_t dcb_step_set_smem_limit(int threads, size_t smem) {
-    const int sm = (int)smem;
-    if (threads <= 256) return cudaFuncSetAttribute(dcb_step_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-    if (threads <= 512) return cudaFuncSetAttribute(dcb_step_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-    if (threads <= 768) return cudaFuncSetAttribute(dcb_step_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-    return cudaFuncSetAttribute(dcb_step_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+// One instantiation per CTA-size class and mask width: __launch_bounds__ caps the registers at 65536 / MAXT so that a
+// CTA of that size is always resident.
+#define DCB_DISPATCH(threads, m32, EXPR)                                                  \
+    do {                                                                                  \
+        if (m32) {                                                                        \
+            if ((threads) <= 256) { auto kern = dcb_step_kernel<256, true>; EXPR; }       \
+            else if ((threads) <= 512) { auto kern = dcb_step_kernel<512, true>; EXPR; }  \
+            else if ((threads) <= 768) { auto kern = dcb_step_kernel<768, true>; EXPR; }  \
+            else { auto kern = dcb_step_kernel<1024, true>; EXPR; }                       \
+        } else {                                                                          \
+            if ((threads) <= 256) { auto kern = dcb_step_kernel<256, false>; EXPR; }      \
+            else if ((threads) <= 512) { auto kern = dcb_step_kernel<512, false>; EXPR; } \
+            else if ((threads) <= 768) { auto kern = dcb_step_kernel<768, false>; EXPR; } \
+            else { auto kern = dcb_step_kernel<1024, false>; EXPR; }                      \
+        }                                                                                 \
+    } while (0)
+
+cudaError_t dcb_step_set_smem_limit(int threads, int n_bs, size_t smem) {
+    cudaError_t e = cudaSuccess;
+    DCB_DISPATCH(threads, n_bs <= 32, e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return e;
 }
 
-int dcb_step_regs_per_thread(int threads) {
+int dcb_step_regs_per_thread(int threads, int n_bs) {
     cudaFuncAttributes at;
-    cudaError_t e;
-    if (threads <= 256) e = cudaFuncGetAttributes(&at, dcb_step_kernel<256>);
-    else if (threads <= 512) e = cudaFuncGetAttributes(&at, dcb_step_kernel<512>);
-    else if (threads <= 768) e = cudaFuncGetAttributes(&at, dcb_step_kernel<768>);
-    else e = cudaFuncGetAttributes(&at, dcb_step_kernel<1024>);
+    cudaError_t e = cudaSuccess;
+    DCB_DISPATCH(threads, n_bs <= 32, e = cudaFuncGetAttributes(&at, kern));
     return e == cudaSuccess ? at.numRegs : 128;
 }
 
 cudaError_t dcb_launch_step(const StepArgs &a, int threads, int grid, size_t smem, cudaStream_t s) {
-    if (threads <= 256) dcb_step_kernel<256><<<grid, threads, smem, s>>>(a);
-    else if (threads <= 512) dcb_step_kernel<512><<<grid, threads, smem, s>>>(a);
-    else if (threads <= 768) dcb_step_kernel<768><<<grid, threads, smem, s>>>(a);
-    else dcb_step_kernel<1024><<<grid, threads, smem, s>>>(a);
+    DCB_DISPATCH(threads, a.p.M <= 32, (kern<<<grid, threads, smem, s>>>(a)));
     return cudaGetLastError();
 }
