@@ -153,15 +153,17 @@ __device__ __forceinline__ void reduce_links(int tid, int gsize, const double *X
                                              double *sum_b, int *arg_b) {
     const int R = n_env * M;
     const int NW = (N + 31) >> 5;
-    const int ppp = gsize / S;
+    const int ls = 31 - __clz(S);                 // S is a power of two
+    const int ppp = gsize >> ls;
     const int seg = tid & (S - 1);
+    const float inv_m = 1.0f / (float)M;
     for (int base = 0; base < R; base += ppp) {
-        const int pair = base + tid / S;
+        const int pair = base + (tid >> ls);
         const bool ok = pair < R;
         int c0 = 0, c1 = 0, a0 = 0x7fffffff, a1 = 0x7fffffff;
         double s0 = 0.0, s1 = 0.0, b0 = 0.0, b1 = 0.0;
         if (ok) {
-            const int le = pair / M, b = pair - le * M;
+            const int le = __float2int_rz(((float)pair + 0.5f) * inv_m), b = pair - le * M;   // exact: pair < 2^16
             const double *col = X + (size_t)(le * N) * MS + b;
             for (int w = seg; w < NW; w += S) {
                 const unsigned wa = bits_a[pair * NW + w];
@@ -174,13 +176,12 @@ __device__ __forceinline__ void reduce_links(int tid, int gsize, const double *X
                     both &= both - 1;
                     const int i = (w << 5) + j;
                     const double v = col[i * MS];
-                    if ((wa >> j) & 1u) {
-                        s0 += v;
-                        if (want_arg && v > b0) { b0 = v; a0 = i; }
-                    }
-                    if ((wb >> j) & 1u) {
-                        s1 += v;
-                        if (want_arg && v > b1) { b1 = v; a1 = i; }
+                    const bool ina = (wa >> j) & 1u, inb = (wb >> j) & 1u;
+                    if (ina) s0 += v;
+                    if (inb) s1 += v;
+                    if (want_arg) {               // max-cap only (station.py:184): first arg-max
+                        if (ina && v > b0) { b0 = v; a0 = i; }
+                        if (inb && v > b1) { b1 = v; a1 = i; }
                     }
                 }
             }
@@ -214,16 +215,18 @@ __device__ __forceinline__ void reduce_utility(int tid, int gsize, const unsigne
                                                double *umin, float *f_ues, float *f_util) {
     const int R = n_env * M;
     const int NW = (N + 31) >> 5;
-    const int ppp = gsize / S;
+    const int ls = 31 - __clz(S);
+    const int ppp = gsize >> ls;
     const int seg = tid & (S - 1);
     const double inv_n = 1.0 / (double)N;
+    const float inv_m = 1.0f / (float)M;
     for (int base = 0; base < R; base += ppp) {
-        const int pair = base + tid / S;
+        const int pair = base + (tid >> ls);
         const bool ok = pair < R;
         double s = 0.0, mn = DCB_MAX_UTILITY;
         int c = 0;
         if (ok) {
-            const int le = pair / M;
+            const int le = __float2int_rz(((float)pair + 0.5f) * inv_m);
             const double *sue = su + le * N;
             for (int w = seg; w < NW; w += S) {
                 unsigned wa = bits[pair * NW + w];
@@ -370,6 +373,9 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
             unsigned *bits_pre = bits_pre2 + par * L.nbits;
             double rb = 0.0;      // reward before the move (base.py:446)
             int lost = 0;
+            // next step's action: issued now so that the global-load latency hides behind this step's work
+            int act_next = 0;
+            if (valid && T > 0 && !last) act_next = a.actions[(size_t)(step + 1) * p.K * N + u];
 // [region:P.top+fresh]
             // the observers must be done with this parity's hand-off buffers (step - 2)
             if (step >= 2) bar_sync(BAR_EMPTY + par, 2 * G);
@@ -487,7 +493,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
             mask_next = mask;
             if (valid) {
                 if (T > 0 && !last) {
-                    const int act = a.actions[(size_t)(step + 1) * p.K * N + u];
+                    const int act = act_next;
                     if (act < 0 || act > M) {
                         atomicOr(p.err, DCB_ERRBIT_ACTION);
                     } else if (act > 0) {
@@ -741,11 +747,13 @@ size_t dcb_step_smem_bytes(int kind, int N, int M, int E) { return (size_t)dcb_s
         if (m32) {                                                                        \
             if ((threads) <= 256) { auto kern = dcb_step_kernel<256, true>; EXPR; }       \
             else if ((threads) <= 512) { auto kern = dcb_step_kernel<512, true>; EXPR; }  \
+            else if ((threads) <= 704) { auto kern = dcb_step_kernel<704, true>; EXPR; }  \
             else if ((threads) <= 768) { auto kern = dcb_step_kernel<768, true>; EXPR; }  \
             else { auto kern = dcb_step_kernel<1024, true>; EXPR; }                       \
         } else {                                                                          \
             if ((threads) <= 256) { auto kern = dcb_step_kernel<256, false>; EXPR; }      \
             else if ((threads) <= 512) { auto kern = dcb_step_kernel<512, false>; EXPR; } \
+            else if ((threads) <= 704) { auto kern = dcb_step_kernel<704, false>; EXPR; } \
             else if ((threads) <= 768) { auto kern = dcb_step_kernel<768, false>; EXPR; } \
             else { auto kern = dcb_step_kernel<1024, false>; EXPR; }                      \
         }                                                                                 \
