@@ -13,8 +13,8 @@
 //   log1p2(s) log2(1 + s) for 0 <= s < 1/32 as the reference rounds it: t = fl(1 + s), s' = t - 1 (exact), series in s'
 //   rcp(x)    MUFU.RCP64H seed + 2 Newton steps (<= 1 ulp) for the divisions that need not be IEEE-exact
 //
-// The polynomials are evaluated in Estrin form (dependency depth 4 instead of 8): the path is latency-bound at the
-// occupancy a 1024-env batch gives a B200.
+// The polynomials are evaluated as two independent even / odd Horner chains (dependency depth ~5 instead of 8, one
+// literal per FMA): the path is issue- and latency-bound at the occupancy a 1024-env batch gives a B200.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -49,17 +49,20 @@ __device__ __forceinline__ double dcb_rcp(double x) {
     return fma(y, e, y);
 }
 
-// log2(1 + r) for |r| <= 1/32 (Taylor series, Estrin evaluation)
+// log2(1 + r) for |r| <= 1/32: Taylor series r (c1 + c2 r + ... + c8 r^7), c_k = (-1)^(k+1) / (k ln 2), split into
+// even and odd halves, each a Horner chain in r^2.  One literal per FMA (a second one would cost two MOVs), two
+// independent chains of depth 3.
 __device__ __forceinline__ double dcb_log2_1p_small(double r) {
     const double r2 = r * r;
-    const double r4 = r2 * r2;
-    const double p01 = fma(-DCB_INV_LN2 / 2.0, r, DCB_INV_LN2);
-    const double p23 = fma(-DCB_INV_LN2 / 4.0, r, DCB_INV_LN2 / 3.0);
-    const double p45 = fma(-DCB_INV_LN2 / 6.0, r, DCB_INV_LN2 / 5.0);
-    const double p67 = fma(-DCB_INV_LN2 / 8.0, r, DCB_INV_LN2 / 7.0);
-    const double q0 = fma(p23, r2, p01);
-    const double q1 = fma(p67, r2, p45);
-    return fma(q1, r4, q0) * r;
+    double pa = DCB_INV_LN2 / 7.0;                  // c1 + c3 r^2 + c5 r^4 + c7 r^6
+    pa = fma(pa, r2, DCB_INV_LN2 / 5.0);
+    pa = fma(pa, r2, DCB_INV_LN2 / 3.0);
+    pa = fma(pa, r2, DCB_INV_LN2);
+    double pb = -DCB_INV_LN2 / 8.0;                 // c2 + c4 r^2 + c6 r^4 + c8 r^6
+    pb = fma(pb, r2, -DCB_INV_LN2 / 6.0);
+    pb = fma(pb, r2, -DCB_INV_LN2 / 4.0);
+    pb = fma(pb, r2, -DCB_INV_LN2 / 2.0);
+    return fma(pb, r, pa) * r;
 }
 
 // log2 of a positive, normal double
@@ -83,11 +86,14 @@ __device__ __forceinline__ double dcb_exp2(const MathTables *t, double y) {
     const double f = fma(kd - magic, -0.0625, y);         // exact: |f| <= 1/32
     const double z = f * DCB_LN2;
     const double z2 = z * z;
-    const double p01 = 1.0 + z;
-    const double p23 = fma(1.0 / 6.0, z, 0.5);
-    const double p45 = fma(1.0 / 120.0, z, 1.0 / 24.0);
-    const double q1 = fma(1.0 / 720.0, z2, p45);
-    const double p = fma(fma(q1, z2, p23), z2, p01);
+    double pe = 1.0 / 720.0;                        // 1 + z^2/2 + z^4/24 + z^6/720
+    pe = fma(pe, z2, 1.0 / 24.0);
+    pe = fma(pe, z2, 0.5);
+    pe = fma(pe, z2, 1.0);
+    double po = 1.0 / 120.0;                        // 1 + z^2/6 + z^4/120
+    po = fma(po, z2, 1.0 / 6.0);
+    po = fma(po, z2, 1.0);
+    const double p = fma(po, z, pe);
     const double v = t->ex2[k & 15] * p;
     return __hiloint2double(__double2hiint(v) + ((k >> 4) << 20), __double2loint(v));
 }

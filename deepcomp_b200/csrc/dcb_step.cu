@@ -50,6 +50,10 @@ namespace {
 
 // [region:helpers.radio]
 // ------------------------------------------------------------------------------------------------ radio model
+__device__ __forceinline__ double dist2(double2 a, double bx, double by) {   // BS (one 16-byte load) to UE
+    const double dx = a.x - bx, dy = a.y - by;
+    return dx * dx + dy * dy;
+}
 __device__ __forceinline__ double dist2(double ax, double ay, double bx, double by) {
     // shapely/GEOS Point.distance = sqrt(dx*dx + dy*dy) (station.py:124); the square is compared / rooted later
     const double dx = ax - bx, dy = ay - by;
@@ -308,8 +312,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
     int *hlost = reinterpret_cast<int *>(smem + L.off_hlost);
     double *env_rew = reinterpret_cast<double *>(smem + L.off_env_rew);
     double *env_sumu = reinterpret_cast<double *>(smem + L.off_env_sumu);
-    double *bsx = reinterpret_cast<double *>(smem + L.off_bsx);
-    double *bsy = reinterpret_cast<double *>(smem + L.off_bsy);
+    double2 *bsxy = reinterpret_cast<double2 *>(smem + L.off_bsx);   // [M] interleaved (off_bsx, off_bsy are adjacent)
     int *share = reinterpret_cast<int *>(smem + L.off_share);
     double *velspec = reinterpret_cast<double *>(smem + L.off_vel);
     unsigned *bits_post2 = reinterpret_cast<unsigned *>(smem + L.off_bits);   // [2][nbits]
@@ -334,8 +337,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
 
     dcb_math_init(tab, threadIdx.x);
     for (int b = threadIdx.x; b < M; b += blockDim.x) {
-        bsx[b] = p.bs_xy[2 * b];
-        bsy[b] = p.bs_xy[2 * b + 1];
+        bsxy[b] = make_double2(p.bs_xy[2 * b], p.bs_xy[2 * b + 1]);
         share[b] = p.sharing[b];
     }
     for (int j = threadIdx.x; j < N; j += blockDim.x) velspec[j] = p.vel_spec[j];
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                             const int b = act - 1;
                             const mask_t bit = (mask_t)1 << b;
                             if (mask & bit) mask &= ~bit;
-                            else if (dist2(bsx[b], bsy[b], x, y) <= p.thr_d2) mask |= bit;   // can_connect, station.py:222-226
+                            else if (dist2(bsxy[b], x, y) <= p.thr_d2) mask |= bit;   // can_connect, station.py:222-226
                         }
                     } else {
                         mask = mask_next;
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                         const double iee = dcb_rcp(ewma + DCB_EPSILON);
                         for (mask_t m = mask; m; m &= m - 1) {
                             const int b = mask_ffs(m) - 1;
-                            Xrow[b] = link_value(share[b], rate_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y)), iee);
+                            Xrow[b] = link_value(share[b], rate_of_d2(p, tab, dist2(bsxy[b], x, y)), iee);
                             atomicOr(&bits_fresh[bit_word + b * NW], bit_val);
                         }
                     }
@@ -480,7 +482,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                     double keep = 0.0;
                     for (mask_t m = mask; m; m &= m - 1) {
                         const int b = mask_ffs(m) - 1;
-                        if (dist2(bsx[b], bsy[b], x, y) <= p.thr_d2) keep += Xrow[b];
+                        if (dist2(bsxy[b], x, y) <= p.thr_d2) keep += Xrow[b];
                         else { mask &= ~((mask_t)1 << b); lost++; }
                     }
                     ewma = 0.9 * keep + (1 - 0.9) * ewma;
@@ -499,13 +501,13 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                     } else if (act > 0) {
                         const int b = act - 1;
                         const mask_t bit = (mask_t)1 << b;
-                        if ((mask & bit) || dist2(bsx[b], bsy[b], x, y) <= p.thr_d2) mask_next = mask ^ bit;
+                        if ((mask & bit) || dist2(bsxy[b], x, y) <= p.thr_d2) mask_next = mask ^ bit;
                     }
                 }
                 const double iee = dcb_rcp(ewma + DCB_EPSILON);
                 for (mask_t m = mask | mask_next; m; m &= m - 1) {
                     const int b = mask_ffs(m) - 1;
-                    Xrow[b] = link_value(share[b], rate_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y)), iee);
+                    Xrow[b] = link_value(share[b], rate_of_d2(p, tab, dist2(bsxy[b], x, y)), iee);
                     if ((mask >> b) & 1) atomicOr(&bits_post[bit_word + b * NW], bit_val);
                     if ((mask_next >> b) & 1) atomicOr(&bits_pre[bit_word + b * NW], bit_val);
                 }
@@ -597,7 +599,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                 double d2min = CUDART_INF;
 #pragma unroll 2
                 for (int b = 0; b < M; b++) {
-                    const double d2 = dist2(bsx[b], bsy[b], x, y);
+                    const double d2 = dist2(bsxy[b], x, y);
                     d2min = fmin(d2min, d2);
                     if (d2 <= p.thr_d2) inrange |= (mask_t)1 << b;
                     row_dr[b] = (float)d2;
@@ -610,7 +612,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                 } else {
                     const double inv_max = dcb_rcp(snr_of_d2(p, tab, d2min));
                     for (int b = 0; b < M; b++)
-                        row_dr[b] = (float)(snr_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y)) * inv_max);
+                        row_dr[b] = (float)(snr_of_d2(p, tab, dist2(bsxy[b], x, y)) * inv_max);
                 }
 // [region:O.staging]
                 // ---- rest of the observation row
@@ -652,7 +654,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                     }
                     if (a.out.dbg_snr)
                         for (int b = 0; b < M; b++)
-                            a.out.dbg_snr[u * M + b] = snr_of_d2(p, tab, dist2(bsx[b], bsy[b], x, y));
+                            a.out.dbg_snr[u * M + b] = snr_of_d2(p, tab, dist2(bsxy[b], x, y));
                 }
 // [region:O.outputs+reward]
                 // ---- per-UE outputs and rewards -> global
