@@ -278,7 +278,10 @@ def gpu_arm(args):
             if events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            env.step_many(actions[s:s + n], out=bufs[n])
+            if args.policy:
+                env.rollout(policy_spec, n, out=bufs[n])          # closed loop on the device, no actions tensor
+            else:
+                env.step_many(actions[s:s + n], out=bufs[n])
             if events is not None:
                 e1.record()
                 events.append((e0, e1, n))
@@ -286,8 +289,13 @@ def gpu_arm(args):
     warm, t_env = plan(0, args.warmup, 0)
     timed, _ = plan(args.warmup, args.steps, t_env)
     # allocate the per-fragment output buffers outside the timed region (one dry fragment per distinct length)
+    policy_spec = None
+    if args.policy:
+        policy_spec = {'3gpp': dict(kind='3gpp'), 'fullcomp': dict(kind='fullcomp'),
+                       'dynamic': dict(kind='dynamic', epsilon=0.5), 'random': dict(kind='random', seed=0)}[args.policy]
     for n in sorted({n for _, n, _ in warm + timed}):
-        bufs[n] = env.step_many(actions[0:n], obs=True, info=False)
+        bufs[n] = (env.rollout(policy_spec, n, obs=True, info=False, return_actions=False) if args.policy
+                   else env.step_many(actions[0:n], obs=True, info=False))
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.wait_started()
@@ -395,6 +403,8 @@ def gpu_arm(args):
     cfg["l2"] = (f"no flush needed: each fragment streams {bufs[max(bufs)]['obs'].numel() * 4 / 1e6:.0f} MB of "
                  f"observations + {F * K * N * 4 / 1e6:.0f} MB of actions through a 126 MB L2")
     cfg["launch_geometry"] = env.launch_geometry
+    if args.policy:
+        cfg["actions"] = f"on-device scripted policy '{args.policy}' (dcb_rollout), closed loop"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -427,6 +437,8 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=200)
     ap.add_argument('--cpu-steps', type=int, default=300, help='steps per core for the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--policy', default=None, choices=['3gpp', 'fullcomp', 'dynamic', 'random'],
+                    help='drive the envs with an on-device baseline policy instead of pre-generated random actions')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

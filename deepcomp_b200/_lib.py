@@ -31,6 +31,12 @@ class DcbOutputs(ctypes.Structure):
     ]
 
 
+class DcbPolicy(ctypes.Structure):
+    _fields_ = [('kind', ctypes.c_int32), ('noop_interval', ctypes.c_int32), ('epsilon', ctypes.c_double),
+                ('host_cluster_masks', ctypes.c_void_p), ('host_fixed_action', ctypes.c_void_p),
+                ('seed', ctypes.c_uint64)]
+
+
 class DcbStateHost(ctypes.Structure):
     _fields_ = [('pos', ctypes.c_void_p), ('mask', ctypes.c_void_p), ('ewma', ctypes.c_void_p),
                 ('movement', ctypes.c_void_p), ('time', ctypes.c_void_p)]
@@ -39,7 +45,7 @@ class DcbStateHost(ctypes.Structure):
 # every symbol include/deepcomp_b200.h declares (tests/test_abi.py checks the library exports all of them)
 SYMBOLS = [
     'dcb_abi_version', 'dcb_last_error', 'dcb_create', 'dcb_destroy', 'dcb_reset', 'dcb_observe', 'dcb_step',
-    'dcb_step_many', 'dcb_step_host', 'dcb_check_errors', 'dcb_get_state', 'dcb_set_state', 'dcb_obs_size',
+    'dcb_step_many', 'dcb_rollout', 'dcb_step_host', 'dcb_check_errors', 'dcb_get_state', 'dcb_set_state', 'dcb_obs_size',
     'dcb_reward_size', 'dcb_algorithmic_bytes_per_env_step', 'dcb_launch_count', 'dcb_launch_geometry',
 ]
 
@@ -82,6 +88,7 @@ def load():
     L.dcb_observe.argtypes = [vp, ctypes.POINTER(DcbOutputs), vp]
     L.dcb_step.argtypes = [vp, vp, ctypes.POINTER(DcbOutputs), vp]
     L.dcb_step_many.argtypes = [vp, vp, i32, ctypes.POINTER(DcbOutputs), vp]
+    L.dcb_rollout.argtypes = [vp, ctypes.POINTER(DcbPolicy), i32, vp, ctypes.POINTER(DcbOutputs), vp]
     L.dcb_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     L.dcb_check_errors.argtypes = [vp, vp]
     L.dcb_get_state.argtypes = [vp, ctypes.POINTER(DcbStateHost)]

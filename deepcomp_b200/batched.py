@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import DcbConfig, DcbOutputs, DcbStateHost, check
+from ._lib import DcbConfig, DcbOutputs, DcbPolicy, DcbStateHost, check
 
 KIND = {'central': 0, 'multi': 1}
 REWARD = {'avg': 0, 'sum': 1, 'min': 2}
@@ -240,6 +240,41 @@ class BatchedMobileEnv:
         else:
             o, t = out['_struct'], out
         check(self._L.dcb_step_many(self._h, ctypes.c_void_p(actions.data_ptr()), T, ctypes.byref(o), self._stream()))
+        return t
+
+    def rollout(self, policy, T, obs=True, info=False, out=None, return_actions=True):
+        """
+        T consecutive steps driven by a scripted baseline policy ON THE DEVICE (no host round trip per step).
+        `policy`: an agent from deepcomp_b200.agents (anything with .device_policy()) or the dict it returns.
+        Returns the same dict as step_many plus 'actions' int32 [T, K, N] (the actions the policy took).
+        """
+        from .agents import POLICY_KIND
+        spec = policy.device_policy(self) if hasattr(policy, 'device_policy') else dict(policy)
+        pol = DcbPolicy(kind=POLICY_KIND[spec['kind']], noop_interval=int(spec.get('noop_interval', 0)),
+                        epsilon=float(spec.get('epsilon', 0.0)), seed=int(spec.get('seed', 0)))
+        keep = []
+        if spec['kind'] == 'static':
+            cm = np.ascontiguousarray(np.asarray(spec['cluster_masks'], dtype=np.uint64))
+            if cm.shape != (self.n_bs,):
+                raise ValueError("need one cluster mask per BS")
+            keep.append(cm)
+            pol.host_cluster_masks = cm.ctypes.data
+        if spec['kind'] == 'fixed':
+            fa = np.ascontiguousarray(np.asarray(spec['fixed_action'], dtype=np.int32))
+            if fa.shape != (self.n_ue,):
+                raise ValueError("need one fixed action per UE")
+            keep.append(fa)
+            pol.host_fixed_action = fa.ctypes.data
+        T = int(T)
+        if out is None:
+            o, t = self._outputs(T, obs=obs, info=info)
+            t['_struct'] = o
+            if return_actions:
+                t['actions'] = self._empty((T, self.num_envs, self.n_ue), torch.int32)
+        else:
+            o, t = out['_struct'], out
+        aptr = ctypes.c_void_p(t['actions'].data_ptr()) if 'actions' in t else None
+        check(self._L.dcb_rollout(self._h, ctypes.byref(pol), T, aptr, ctypes.byref(o), self._stream()))
         return t
 
     # ------------------------------------------------------------------ host-buffer path (e2e)

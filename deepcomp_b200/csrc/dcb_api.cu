@@ -84,6 +84,10 @@ struct dcb_env {
     uint32_t *d_table = nullptr, *d_pos_skip = nullptr, *d_mv_skip = nullptr;
     int32_t *d_env_ids = nullptr;
     int env_ids_cap = 0;
+    // scripted policies (dcb_rollout)
+    unsigned long long *d_cluster = nullptr;
+    int32_t *d_fixed = nullptr;
+    long long policy_calls = 0;
     // dcb_step_host staging
     int32_t *d_h_actions = nullptr;
     float *d_h_obs = nullptr, *d_h_reward = nullptr;
@@ -127,8 +131,12 @@ int choose_envs_per_cta(int K, int N, int M, int kind, int num_sms, size_t smem_
     return best_e;
 }
 
-int launch_step(dcb_env *env, const int32_t *d_actions, int T, const dcb_outputs *out, cudaStream_t s) {
+int launch_step(dcb_env *env, const int32_t *d_actions, int T, const dcb_outputs *out, cudaStream_t s,
+                const PolicyParams *pol = nullptr, int32_t *d_actions_out = nullptr) {
     StepArgs a;
+    memset(&a.pol, 0, sizeof(a.pol));
+    if (pol) a.pol = *pol;
+    a.actions_out = d_actions_out;
     a.p = env->p;
     a.L = dcb_smem_layout(env->p.kind, env->p.N, env->p.M, env->p.E);
     a.actions = d_actions;
@@ -183,6 +191,7 @@ void dcb_destroy(dcb_env *env) {
     cudaFree(env->d_seeds); cudaFree(env->d_pos); cudaFree(env->d_init_pos); cudaFree(env->d_mv);
     cudaFree(env->d_mask); cudaFree(env->d_ewma); cudaFree(env->d_time); cudaFree(env->d_err);
     cudaFree(env->d_table); cudaFree(env->d_pos_skip); cudaFree(env->d_mv_skip); cudaFree(env->d_env_ids);
+    cudaFree(env->d_cluster); cudaFree(env->d_fixed);
     cudaFree(env->d_h_actions); cudaFree(env->d_h_obs); cudaFree(env->d_h_reward); cudaFree(env->d_h_lost);
     delete env;
 }
@@ -395,6 +404,52 @@ int dcb_step_many(dcb_env *env, const int32_t *d_actions, int32_t T, const dcb_o
     if (T < 1) return fail(DCB_ERR_INVALID_ARG, "T must be >= 1");
     DeviceGuard guard(env->device);
     return launch_step(env, d_actions, T, out, (cudaStream_t)stream);
+}
+
+int dcb_rollout(dcb_env *env, const dcb_policy *policy, int32_t T, int32_t *d_actions_out, const dcb_outputs *out,
+                void *stream) {
+    if (!env || !policy) return fail(DCB_ERR_INVALID_ARG, "null argument");
+    if (T < 1) return fail(DCB_ERR_INVALID_ARG, "T must be >= 1");
+    if (policy->kind < DCB_POLICY_3GPP || policy->kind > DCB_POLICY_RANDOM)
+        return fail(DCB_ERR_INVALID_ARG, "unknown policy kind %d", policy->kind);
+    DeviceGuard guard(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const DevParams &p = env->p;
+    PolicyParams q;
+    memset(&q, 0, sizeof(q));
+    q.kind = policy->kind;
+    q.call0 = env->policy_calls;
+    q.seed = policy->seed;
+    if (policy->kind == DCB_POLICY_DYNAMIC) {
+        // heuristics.py:86-91: selected = {b: snr_b >= epsilon * best_snr}; snr ~ (d^2)^-h  =>  d2_b <= d2min * epsilon^(-1/h)
+        if (!(policy->epsilon >= 0.0 && policy->epsilon <= 1.0))   // cli.py:100
+            return fail(DCB_ERR_INVALID_ARG, "epsilon must be within [0, 1] but is %g", policy->epsilon);
+        q.gain = policy->epsilon > 0.0 ? pow(policy->epsilon, -1.0 / p.snr_h) : INFINITY;
+    }
+    if (policy->kind == DCB_POLICY_STATIC) {
+        if (!policy->host_cluster_masks) return fail(DCB_ERR_INVALID_ARG, "static clustering needs host_cluster_masks");
+        if (!env->d_cluster) CU(cudaMalloc((void **)&env->d_cluster, sizeof(unsigned long long) * p.M));
+        CU(cudaMemcpyAsync(env->d_cluster, policy->host_cluster_masks, sizeof(unsigned long long) * p.M,
+                           cudaMemcpyHostToDevice, s));
+        q.cluster = env->d_cluster;
+    }
+    if (policy->kind == DCB_POLICY_FIXED) {
+        if (!policy->host_fixed_action) return fail(DCB_ERR_INVALID_ARG, "fixed agent needs host_fixed_action");
+        if (policy->noop_interval < 0) return fail(DCB_ERR_INVALID_ARG, "noop_interval must be >= 0");
+        for (int i = 0; i < p.N; i++)
+            if (policy->host_fixed_action[i] < 0 || policy->host_fixed_action[i] > p.M)
+                return fail(DCB_ERR_ACTION_RANGE, "fixed action %d of UE %d outside [0, %d]", policy->host_fixed_action[i], i, p.M);
+        if (!env->d_fixed) CU(cudaMalloc((void **)&env->d_fixed, sizeof(int32_t) * p.N));
+        CU(cudaMemcpyAsync(env->d_fixed, policy->host_fixed_action, sizeof(int32_t) * p.N, cudaMemcpyHostToDevice, s));
+        q.fixed = env->d_fixed;
+        q.noop_interval = policy->noop_interval;
+    }
+    const int rc = launch_step(env, nullptr, T, out, s, &q, d_actions_out);
+    if (rc != DCB_OK) return rc;
+    env->policy_calls += T;
+    if (policy->kind == DCB_POLICY_STATIC || policy->kind == DCB_POLICY_FIXED)
+        CU(cudaStreamSynchronize(s));   // the host arrays of the policy may be reused by the caller
+    return DCB_OK;
 }
 
 int dcb_step_host(dcb_env *env, const int32_t *h_actions, float *h_obs, float *h_reward, uint8_t *h_lost_conn,

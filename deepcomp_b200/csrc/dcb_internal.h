@@ -105,11 +105,25 @@ __host__ __device__ inline SmemLayout dcb_smem_layout(int kind, int N, int M, in
     return L;
 }
 
+// Scripted per-UE policy evaluated on the device (reference deepcomp/agent/heuristics.py, dummy.py); kind 0 = none:
+// actions come from StepArgs::actions.
+struct PolicyParams {
+    int kind;                          // dcb_policy_kind
+    int noop_interval;                 // FixedAgent(noop_interval)
+    double gain;                       // DynamicSelection: epsilon^(-20/c2) -- "snr >= eps * best" as a d^2 ratio
+    const unsigned long long *cluster; // StaticClustering: [M] bitmask of the cluster of each BS
+    const int32_t *fixed;              // FixedAgent: [N] action per UE
+    long long call0;                   // compute_action calls made before this launch (FixedAgent interval, RNG stream)
+    unsigned long long seed;           // RandomAgent
+};
+
 struct StepArgs {
     DevParams p;
     SmemLayout L;
-    const int32_t *actions;  // [T][K][N]
+    const int32_t *actions;  // [T][K][N], or NULL when a policy drives the envs
     int T;                   // 0 = observe only
+    PolicyParams pol;
+    int32_t *actions_out;    // [T][K][N] actions the policy took, or NULL
     dcb_outputs out;
 };
 

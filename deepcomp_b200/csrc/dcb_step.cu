@@ -127,6 +127,64 @@ template <> struct MaskType<true> { typedef unsigned type; };
 __device__ __forceinline__ int mask_ffs(unsigned m) { return __ffs((int)m); }
 __device__ __forceinline__ int mask_ffs(unsigned long long m) { return __ffsll((long long)m); }
 
+// ------------------------------------------------------------------------------------------------ scripted policies
+// The reference's baseline agents (deepcomp/agent/heuristics.py:13-187, dummy.py:6-50) act per UE on obs['connected'] and
+// obs['dr'] = snr_b / max snr.  SNR is a decreasing function of the distance, so "highest dr" is "smallest squared
+// distance" (first index on ties, as np.argmax / the agents' loops do) and "dr_b >= eps" is "d2_b <= d2min * gain"
+// with gain = eps^(-1/h): the physics warps evaluate the policies exactly, from the state they already hold, one
+// step ahead of the observation that the host would have needed.
+template <typename mask_t>
+__device__ __forceinline__ int policy_action(const PolicyParams &q, mask_t mask, double x, double y, const double2 *bsxy,
+                                             int M, int i, long long call_idx, long long u) {
+    if (q.kind == DCB_POLICY_FIXED) {                    // dummy.py:25-50
+        const long long period = (long long)q.noop_interval + 1;
+        return (call_idx % period) == 0 ? q.fixed[i] : 0;
+    }
+    if (q.kind == DCB_POLICY_RANDOM) {                   // dummy.py:6-22 (uniform over Discrete(M + 1); own counter-based RNG)
+        unsigned long long z = q.seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(u + 1) +
+                               0xD1B54A32D192ED03ull * (unsigned long long)(call_idx + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        return (int)(((z >> 32) * (unsigned long long)(M + 1)) >> 32);
+    }
+    // closest BS overall and closest BS this UE is not linked to (first index on ties)
+    double d2min = CUDART_INF, d2free = CUDART_INF;
+    int best = 0, best_free = -1;
+    for (int b = 0; b < M; b++) {
+        const double d2 = dist2(bsxy[b], x, y);
+        if (d2 < d2min) { d2min = d2; best = b; }
+        if (!((mask >> b) & 1) && d2 < d2free) { d2free = d2; best_free = b; }
+    }
+    if (q.kind == DCB_POLICY_3GPP) {                     // heuristics.py:19-38
+        if ((mask >> best) & 1) return 0;
+        if (mask) return mask_ffs(mask);                 // disconnect from the (first) other BS first
+        return best + 1;
+    }
+    if (q.kind == DCB_POLICY_FULLCOMP)                   // heuristics.py:44-65
+        return best_free + 1;                            // -1 + 1 = 0 = noop when linked to every BS
+    mask_t selected = 0;
+    if (q.kind == DCB_POLICY_DYNAMIC) {                  // heuristics.py:86-108: strongest BS and all within eps of it
+        const double thr = d2min * q.gain;
+        for (int b = 0; b < M; b++)
+            if (dist2(bsxy[b], x, y) <= thr) selected |= (mask_t)1 << b;
+    } else {                                             // heuristics.py:169-187: the static cluster of the strongest BS
+        selected = (mask_t)q.cluster[best];
+    }
+    const mask_t drop = mask & ~selected;
+    if (drop) return mask_ffs(drop);                     // leave BS outside the set, lowest index first
+    const mask_t want = selected & ~mask;
+    if (!want) return 0;
+    double d2w = CUDART_INF;                             // join the set, strongest first
+    int bw = 0;
+    for (mask_t m = want; m; m &= m - 1) {
+        const int b = mask_ffs(m) - 1;
+        const double d2 = dist2(bsxy[b], x, y);
+        if (d2 < d2w) { d2w = d2; bw = b; }
+    }
+    return bw + 1;
+}
+
 // [region:helpers.barriers]
 // ------------------------------------------------------------------------------------------------ named barriers
 // Barrier 0 is __syncthreads (set-up only).  Each warp group has a private barrier; FULL[parity] / EMPTY[parity]
@@ -377,7 +435,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
             int lost = 0;
             // next step's action: issued now so that the global-load latency hides behind this step's work
             int act_next = 0;
-            if (valid && T > 0 && !last) act_next = a.actions[(size_t)(step + 1) * p.K * N + u];
+            if (valid && T > 0 && !last && !a.pol.kind) act_next = a.actions[(size_t)(step + 1) * p.K * N + u];
 // [region:P.top+fresh]
             // the observers must be done with this parity's hand-off buffers (step - 2)
             if (step >= 2) bar_sync(BAR_EMPTY + par, 2 * G);
@@ -397,7 +455,13 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                 if (valid) {
                     if (fresh) {
                         // apply_ue_actions (base.py:247-282) -> User.connect_to_bs(disconnect=True) (user.py:190-229)
-                        const int act = a.actions[(size_t)step * p.K * N + u];
+                        int act;
+                        if (a.pol.kind) {
+                            act = policy_action<mask_t>(a.pol, mask, x, y, bsxy, M, i, a.pol.call0 + step, u);
+                            if (a.actions_out) a.actions_out[(size_t)step * p.K * N + u] = act;
+                        } else {
+                            act = a.actions[(size_t)step * p.K * N + u];
+                        }
                         if (act < 0 || act > M) {
                             atomicOr(p.err, DCB_ERRBIT_ACTION);
                         } else if (act > 0) {
@@ -495,7 +559,11 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
             mask_next = mask;
             if (valid) {
                 if (T > 0 && !last) {
-                    const int act = act_next;
+                    int act = act_next;
+                    if (a.pol.kind) {
+                        act = policy_action<mask_t>(a.pol, mask, x, y, bsxy, M, i, a.pol.call0 + step + 1, u);
+                        if (a.actions_out) a.actions_out[(size_t)(step + 1) * p.K * N + u] = act;
+                    }
                     if (act < 0 || act > M) {
                         atomicOr(p.err, DCB_ERRBIT_ACTION);
                     } else if (act > 0) {

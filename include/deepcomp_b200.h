@@ -57,6 +57,25 @@ typedef enum dcb_sharing {
     DCB_SHARE_RESOURCE_FAIR = 0, DCB_SHARE_RATE_FAIR = 1, DCB_SHARE_PROPORTIONAL_FAIR = 2, DCB_SHARE_MAX_CAP = 3
 } dcb_sharing;
 
+/*
+ * Scripted baseline policies evaluated on the device (closed rollout loop, no host round trip per step):
+ * deepcomp/agent/heuristics.py:13-187 (Heuristic3GPP, FullCoMP, DynamicSelection, StaticClustering) and
+ * deepcomp/agent/dummy.py:6-50 (RandomAgent, FixedAgent).
+ */
+typedef enum dcb_policy_kind {
+    DCB_POLICY_NONE = 0, DCB_POLICY_3GPP = 1, DCB_POLICY_FULLCOMP = 2, DCB_POLICY_DYNAMIC = 3, DCB_POLICY_STATIC = 4,
+    DCB_POLICY_FIXED = 5, DCB_POLICY_RANDOM = 6
+} dcb_policy_kind;
+
+typedef struct dcb_policy {
+    int32_t kind;                       /* dcb_policy_kind */
+    int32_t noop_interval;              /* FIXED: no-op steps between repetitions (dummy.py:29-45) */
+    double epsilon;                     /* DYNAMIC: scaling factor in [0, 1] (heuristics.py:79-91) */
+    const uint64_t *host_cluster_masks; /* STATIC: [M] bitmask of the cluster each BS belongs to (heuristics.py:127-167) */
+    const int32_t *host_fixed_action;   /* FIXED: [N] action per UE */
+    uint64_t seed;                      /* RANDOM */
+} dcb_policy;
+
 /* Velocity spec of a UE's RandomWaypoint (movement.py:112-117): a number >= 0 is used as is */
 #define DCB_VELOCITY_SLOW (-1.0) /* rng.randint(1, 3)  */
 #define DCB_VELOCITY_FAST (-2.0) /* rng.randint(5, 10) */
@@ -141,6 +160,14 @@ int dcb_step(dcb_env *env, const int32_t *d_actions, const dcb_outputs *out, voi
 
 /* T consecutive steps in ONE launch (state stays on chip between steps): d_actions int32 [T][K][N] */
 int dcb_step_many(dcb_env *env, const int32_t *d_actions, int32_t T, const dcb_outputs *out, void *stream);
+
+/*
+ * T consecutive steps driven by a scripted policy: action(t+1) = policy(state after step t), the first action of a
+ * launch from the current state (e.g. right after dcb_reset).  d_actions_out (int32 [T][K][N], may be NULL) receives
+ * the actions taken.  The policy's call counter (FixedAgent interval, RandomAgent stream) persists in the handle.
+ */
+int dcb_rollout(dcb_env *env, const dcb_policy *policy, int32_t T, int32_t *d_actions_out, const dcb_outputs *out,
+                void *stream);
 
 /*
  * Convenience for host callers (the e2e path of bench.py and the K=1 gym facades): copies `h_actions` [K][N] to the

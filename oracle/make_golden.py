@@ -56,6 +56,51 @@ def scenarios():
     return S
 
 
+def policy_scenarios():
+    """Closed loops of the reference's baseline agents (deepcomp/agent/heuristics.py, dummy.py) on the reference env."""
+    S = []
+    W, H, gbs = rl.grid_layout(5)
+    vel = ['slow', 'fast', 0, 2.5] * 3
+    base = dict(kind='multi', n_ue=12, bs_xy=gbs, map_wh=(W, H), sharing='mixed', velocities=vel, seed=21, reward='avg',
+                steps=60, action_seed=0, episodes=2)
+    S.append(dict(base, name='policy_3gpp', policy=dict(kind='3gpp')))
+    S.append(dict(base, name='policy_fullcomp', policy=dict(kind='fullcomp')))
+    S.append(dict(base, name='policy_dynamic_eps05', policy=dict(kind='dynamic', epsilon=0.5)))
+    S.append(dict(base, name='policy_dynamic_eps001', policy=dict(kind='dynamic', epsilon=0.01)))
+    S.append(dict(base, name='policy_static_c2', policy=dict(kind='static', cluster_size=2, seed=5)))
+    W, H, gbs = rl.grid_layout(10)
+    big = dict(kind='multi', n_ue=50, bs_xy=gbs, map_wh=(W, H), sharing='mixed', velocities='slow', seed=1000,
+               reward='avg', steps=25, action_seed=0, episodes=1)
+    S.append(dict(big, name='policy_3gpp_grid10', policy=dict(kind='3gpp')))
+    # StaticClustering ranks the cells of a cluster with a stable sort over a Python set of Basestation objects
+    # (heuristics.py:171-183): equal-dr ties resolve in hash (= memory address) order, i.e. nondeterministically.  Integer
+    # start positions on a regular grid produce such ties, so this trace starts the UEs at non-integer positions.
+    frac = np.random.default_rng(3)
+    init = [(round(float(frac.uniform(0, W)), 3), round(float(frac.uniform(0, H)), 3)) for _ in range(50)]
+    S.append(dict(big, name='policy_static_c3_grid10', policy=dict(kind='static', cluster_size=3, seed=1),
+                  init_pos=init))
+    S.append(dict(base, name='policy_fixed', kind='central', policy=dict(kind='fixed', action=[1, 2, 3, 4, 5, 0] * 2,
+                                                                        noop_interval=2)))
+    return S
+
+
+def make_reference_agent(sc, env):
+    from deepcomp.agent.heuristics import Heuristic3GPP, FullCoMP, DynamicSelection, StaticClustering
+    from deepcomp.agent.dummy import FixedAgent
+    pol = sc['policy']
+    if pol['kind'] == '3gpp':
+        return Heuristic3GPP()
+    if pol['kind'] == 'fullcomp':
+        return FullCoMP()
+    if pol['kind'] == 'dynamic':
+        return DynamicSelection(epsilon=pol['epsilon'])
+    if pol['kind'] == 'static':
+        return StaticClustering(cluster_size=pol['cluster_size'], bs_list=env.bs_list, seed=pol['seed'])
+    if pol['kind'] == 'fixed':
+        return FixedAgent(action=np.array(pol['action']), noop_interval=pol['noop_interval'])
+    raise ValueError(pol)
+
+
 def record(sc):
     env = rl.build_env(sc['kind'], sc['n_ue'], sc['seed'], sc['bs_xy'], sc['map_wh'], sharing=sc['sharing'],
                        velocities=sc['velocities'], reward=sc['reward'], episode_length=sc['steps'],
@@ -67,13 +112,24 @@ def record(sc):
     actions = []
     steps = {k: [] for k in STEP_KEYS}
     resets = {k: [] for k in RESET_KEYS}
+    agent = make_reference_agent(sc, env) if 'policy' in sc else None
     for ep in range(sc['episodes']):
-        r = tr.reset()
+        raw_obs = env.reset()
+        r = tr.snapshot()
+        r['obs'] = tr.flat_obs(raw_obs)
         for k in RESET_KEYS:
             resets[k].append(r[k])
         for t in range(sc['steps']):
-            a = rng.integers(0, n_bs + 1, sc['n_ue']).astype(np.int32)
+            if agent is None:
+                a = rng.integers(0, n_bs + 1, sc['n_ue']).astype(np.int32)
+            elif getattr(agent, 'central_agent', False):      # StaticClustering never calls super().__init__()
+                a = np.asarray(agent.compute_action(raw_obs), dtype=np.int32)           # simulation.py:327-349
+            else:
+                # simulation.py:351-380: one compute_action call per agent id
+                a = np.array([agent.compute_action(raw_obs[ue.id], policy_id='ue') for ue in env.ue_list],
+                             dtype=np.int32)
             s = tr.step(a)
+            raw_obs = tr.last_obs
             # base.py:371-381: done is None; multi_agent.py:97-102: dict of None incl. '__all__'
             if sc['kind'] == 'central':
                 assert s['done'] is None
@@ -88,6 +144,12 @@ def record(sc):
         out['step_' + k] = np.stack([np.asarray(v) for v in steps[k]])
     for k in RESET_KEYS:
         out['reset_' + k] = np.stack([np.asarray(v) for v in resets[k]])
+    if agent is not None and sc['policy']['kind'] == 'static':
+        masks = np.zeros(n_bs, dtype=np.uint64)
+        for bs, members in agent.clusters.items():
+            for m in members:
+                masks[env.bs_list.index(bs)] |= np.uint64(1) << np.uint64(env.bs_list.index(m))
+        out['cluster_masks'] = masks
     cfg = {k: v for k, v in sc.items()}
     cfg['bs_xy'] = [[float(x), float(y)] for x, y in sc['bs_xy']]
     cfg['map_wh'] = [float(sc['map_wh'][0]), float(sc['map_wh'][1])]
@@ -130,8 +192,12 @@ def main():
     if not rl.available():
         sys.exit('reference not found under ' + rl.REFERENCE_ROOT)
     os.makedirs(OUT_DIR, exist_ok=True)
-    np.savez_compressed(os.path.join(OUT_DIR, 'anchors.npz'), **anchors())
-    for sc in scenarios():
+    only = sys.argv[1] if len(sys.argv) > 1 else ''     # optional name prefix: regenerate a subset only
+    if not only:
+        np.savez_compressed(os.path.join(OUT_DIR, 'anchors.npz'), **anchors())
+    for sc in scenarios() + policy_scenarios():
+        if not sc['name'].startswith(only):
+            continue
         data = record(sc)
         path = os.path.join(OUT_DIR, sc['name'] + '.npz')
         np.savez_compressed(path, **data)

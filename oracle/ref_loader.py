@@ -163,6 +163,7 @@ class RefTrace:
 
     def step(self, a):
         obs, reward, done, info = self.env.step(self.to_action(a))
+        self.last_obs = obs
         out = self.snapshot()
         out['obs'] = self.flat_obs(obs)
         out['reward'] = self.flat_reward(reward)

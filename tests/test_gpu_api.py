@@ -297,3 +297,67 @@ def test_full_size_batch_properties():
             assert_close(rew[t, k], w['reward'], f'env{k}.reward[{t}]', 2e-6, 1e-5)
             assert_exact(lost[t, k].astype(np.int32), w['lost_conn'], f'env{k}.lost[{t}]')
     env.check_errors()
+
+
+# ------------------------------------------------------------------------------------------------ on-device policies
+@pytest.mark.parametrize('name', [n for n in __import__('helpers').golden_names() if n.startswith('policy_')])
+def test_device_policies_reproduce_reference_agents(name):
+    """Closed loop on the device: the kernel's scripted policy takes exactly the actions the reference's agent took on
+    the reference env, and the env follows the same trajectory (deepcomp/agent/heuristics.py, dummy.py)."""
+    from deepcomp_b200 import BatchedMobileEnv
+    from helpers import oracle_kwargs
+    from test_agents import make_agent
+    cfg, z = load_golden(name)
+    kw = oracle_kwargs(cfg)
+    seed = kw.pop('seed')
+    env = BatchedMobileEnv(num_envs=1, seeds=[seed], **kw)
+    agent = make_agent(cfg)
+    T = cfg['steps']
+    for ep in range(cfg['episodes']):
+        env.reset()
+        r = env.rollout(agent, T, info=True)
+        sl = slice(ep * T, (ep + 1) * T)
+        assert_exact(r['actions'][:, 0].cpu().numpy(), z['actions'][sl], f'{name}.actions')
+        assert_exact(r['lost_conn'][:, 0].cpu().numpy().astype(np.int32), z['step_lost_conn'][sl], f'{name}.lost_conn')
+        assert_close(r['reward'][:, 0].cpu().numpy(), z['step_reward'][sl], f'{name}.reward', 2e-6, 1e-5)
+        assert_close(r['obs'][:, 0].cpu().numpy(), z['step_obs'][sl], f'{name}.obs', 2e-6, 1e-6)
+        assert_close(r['sum_utility'][:, 0].cpu().numpy(), z['step_sum_utility'][sl], f'{name}.sum_utility', 2e-6, 1e-4)
+        st = env.get_state()
+        assert_exact(st['pos'][0], z['step_pos'][(ep + 1) * T - 1], f'{name}.pos')
+    env.check_errors()
+
+
+def test_rollout_equals_host_loop_with_the_same_policy():
+    """K envs: device rollout == stepping the same envs from the host with the host form of the agent."""
+    from deepcomp_b200 import BatchedMobileEnv, agents
+    K, N, M, T = 19, 50, 10, 15
+    a = BatchedMobileEnv(num_envs=K, kind='multi', seed=4, **_scenario())
+    b = BatchedMobileEnv(num_envs=K, kind='multi', seed=4, **_scenario())
+    agent = agents.DynamicSelection(0.3)
+    a.reset()
+    obs = b.reset().cpu().numpy()
+    r = a.rollout(agent, T)
+    for t in range(T):
+        acts = np.zeros((K, N), dtype=np.int32)
+        for k in range(K):
+            for i in range(N):
+                row = obs[k, i]
+                acts[k, i] = agent.compute_action({'connected': [int(v) for v in row[:M]], 'dr': list(row[M:2 * M])}, 'ue')
+        assert np.array_equal(acts, r['actions'][t].cpu().numpy()), t
+        o, rew, _, _ = b.step(torch.as_tensor(acts, device='cuda'))
+        assert torch.equal(o, r['obs'][t]) and torch.equal(rew, r['reward'][t])
+        obs = o.cpu().numpy()
+
+
+def test_random_policy_is_uniform_and_reproducible():
+    from deepcomp_b200 import BatchedMobileEnv
+    K, N, M, T = 64, 50, 10, 40
+    env = BatchedMobileEnv(num_envs=K, kind='multi', seed=4, **_scenario())
+    env.reset()
+    r1 = env.rollout(dict(kind='random', seed=7), T, obs=False)['actions'].clone()
+    env2 = BatchedMobileEnv(num_envs=K, kind='multi', seed=4, **_scenario())
+    env2.reset()
+    r2 = env2.rollout(dict(kind='random', seed=7), T, obs=False)['actions']
+    assert torch.equal(r1, r2)
+    hist = torch.bincount(r1.flatten().long(), minlength=M + 1).float()
+    assert hist.numel() == M + 1 and (hist / hist.sum() - 1 / (M + 1)).abs().max() < 0.01
