@@ -52,10 +52,11 @@ struct DevParams {
 
 // ---- shared-memory layout of the step kernel (byte offsets), computed once on the host
 struct SmemLayout {
-    int off_tab, off_stage, off_x, off_sum_pre, off_sum_post, off_usum, off_umin, off_fues, off_futil, off_hx, off_hy,
+    int off_tab, off_stage, off_x, off_fac_pre, off_fac_post, off_usum, off_umin, off_fues, off_futil, off_hx, off_hy,
         off_hmask, off_hutil, off_hrb, off_hdr, off_hlost, off_env_rew, off_env_sumu, off_bsx, off_bsy, off_vel,
-        off_cnt_pre, off_arg_pre, off_cnt_post, off_arg_post, off_cnt_obs, off_bits, off_share;
+        off_arg_pre, off_arg_post, off_cnt_obs, off_bits, off_share, off_links, off_vthr;
     int nbits;   // words per bitset
+    int links_per_warp;   // capacity (entries) of one physics warp's link list
     int total;
 };
 
@@ -74,8 +75,8 @@ __host__ __device__ inline SmemLayout dcb_smem_layout(int kind, int N, int M, in
     L.off_tab = o;      o += 3 * 16 * 8;                             // 3 x 128 B: one bank row per table
     L.off_stage = o;    o += align16(EN * obs_width(kind, M) * 4) + 16;   // float obs tile of the CTA (+ alignment shift)
     L.off_x = o;        o += align16(EN * row_stride(M) * 8);        // link values of connected links
-    L.off_sum_pre = o;  o += align16(EM * 8);
-    L.off_sum_post = o; o += align16(EM * 8);
+    L.off_fac_pre = o;  o += align16(EM * 8);                        // per-(env, BS) sharing factor, next step's masks
+    L.off_fac_post = o; o += align16(EM * 8);                        // ... current masks
     L.off_usum = o;     o += align16(EM * 8);
     L.off_umin = o;     o += align16(EM * 8);
     L.off_fues = o;     o += align16(EM * 4);
@@ -93,14 +94,17 @@ __host__ __device__ inline SmemLayout dcb_smem_layout(int kind, int N, int M, in
     L.off_bsx = o;      o += align16(M * 8);
     L.off_bsy = o;      o += align16(M * 8);
     L.off_vel = o;      o += align16(N * 8);
-    L.off_cnt_pre = o;  o += align16(EM * 4);
     L.off_arg_pre = o;  o += align16(EM * 4);
-    L.off_cnt_post = o; o += align16(EM * 4);
     L.off_arg_post = o; o += align16(EM * 4);
     L.off_cnt_obs = o;  o += align16(EM * 4);
     L.nbits = EM * ((N + 31) / 32);
     L.off_bits = o;     o += align16(5 * L.nbits * 4);               // UE bitsets per (env, BS): post[2], pre[2], fresh
     L.off_share = o;    o += align16(M * 4);
+    // per physics warp: compacted list of the warp's links (owner lane, BS, membership flags), 2 bytes per entry;
+    // worst case every UE of the warp is linked to every BS
+    L.links_per_warp = 32 * M;
+    L.off_links = o;    o += align16(((EN + 31) / 32) * L.links_per_warp * 2);
+    L.off_vthr = o;     o += align16(16 * 8);                        // snap thresholds for drawn velocities 0..15
     L.total = o;
     return L;
 }

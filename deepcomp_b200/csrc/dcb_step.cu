@@ -54,11 +54,6 @@ __device__ __forceinline__ double dist2(double2 a, double bx, double by) {   // 
     const double dx = a.x - bx, dy = a.y - by;
     return dx * dx + dy * dy;
 }
-__device__ __forceinline__ double dist2(double ax, double ay, double bx, double by) {
-    // shapely/GEOS Point.distance = sqrt(dx*dx + dy*dy) (station.py:124); the square is compared / rooted later
-    const double dx = ax - bx, dy = ay - by;
-    return dx * dx + dy * dy;
-}
 
 // station.py:110-138 verbatim with libm, for a UE within ~1 m of the BS (distance + EPSILON matters; snr > 1/32)
 __device__ __noinline__ double snr_of_d2_libm(double c1, double c2, double d2) {
@@ -80,18 +75,21 @@ __device__ __forceinline__ double snr_of_d2(const DevParams &p, const MathTables
 }
 
 // Unshared rate bw * log2(1 + snr) (station.py:129-138); on the fast path snr < 1/32 -> series in fl(1 + snr) - 1
-__device__ __forceinline__ double rate_of_d2(const DevParams &p, const MathTables *tab, double d2) {
-    if (d2 < DCB_NEAR_D2) return rate_of_d2_libm(p.c1, p.c2, d2);
+__device__ __forceinline__ double rate_of_d2_fast(const DevParams &p, const MathTables *tab, double d2) {
     const double s = dcb_exp2(tab, fma(-p.snr_h, dcb_log2(tab, d2), p.snr_c0));
     return DCB_BW * dcb_log2_1p_small((1.0 + s) - 1.0);
 }
+__device__ __forceinline__ double rate_of_d2(const DevParams &p, const MathTables *tab, double d2) {
+    if (d2 < DCB_NEAR_D2) return rate_of_d2_libm(p.c1, p.c2, d2);
+    return rate_of_d2_fast(p, tab, d2);
+}
 
 __device__ __forceinline__ double log_utility(const MathTables *tab, double dr) {
-    // env/util/utility.py:36-54: clip(10 log10(dr), -20, 20); dr <= 0.01 / >= 100 clip without evaluating the log
-    if (dr <= 0.01) return DCB_MIN_UTILITY;
-    if (dr >= 100.0) return DCB_MAX_UTILITY;
-    const double u = 3.0102999566398119521 * dcb_log2(tab, dr);   // 10 log10(2) log2(dr)
-    return fmin(fmax(u, DCB_MIN_UTILITY), DCB_MAX_UTILITY);
+    // env/util/utility.py:36-54: clip(10 log10(dr), -20, 20); dr <= 0.01 / >= 100 clip without evaluating the log.
+    // Branch-free (selects): two utilities of one UE are evaluated back to back and should share a basic block.
+    const double u = 3.0102999566398119521 * dcb_log2(tab, dr);   // 10 log10(2) log2(dr); unused (finite garbage) for dr <= 0.01
+    const double c = u > DCB_MAX_UTILITY ? DCB_MAX_UTILITY : (u < DCB_MIN_UTILITY ? DCB_MIN_UTILITY : u);
+    return dr <= 0.01 ? DCB_MIN_UTILITY : (dr >= 100.0 ? DCB_MAX_UTILITY : c);
 }
 
 // Value a connected link contributes to its BS's reduction, by sharing model (station.py:170-195):
@@ -101,14 +99,40 @@ __device__ __forceinline__ double link_value(int model, double r0, double inv_ew
     if (model == DCB_SHARE_PROPORTIONAL_FAIR) return r0 * inv_ewma_eps;
     return r0;
 }
+// branch-free form for the balanced link loop (both candidates are cheap; selects keep two links in one basic block)
+__device__ __forceinline__ double link_value_sel(int model, double r0, double inv_ewma_eps) {
+    const double a = dcb_rcp(r0), b = r0 * inv_ewma_eps;
+    return model == DCB_SHARE_RATE_FAIR ? a : (model == DCB_SHARE_PROPORTIONAL_FAIR ? b : r0);
+}
 
-// Shared rate of one link from its value and the BS aggregates (station.py:152-202)
-__device__ __forceinline__ double shared_rate(int model, double v, int cnt, double sum, int arg, int i,
-                                              double ewma_eps) {
-    if (model == DCB_SHARE_RESOURCE_FAIR) return v * dcb_rcp((double)cnt);                      // :173
-    if (model == DCB_SHARE_RATE_FAIR) return dcb_rcp(sum);                                      // :180
+// Per-(env, BS) factor the reducer leaves behind so that a link's shared rate is a couple of multiplies:
+// resource-fair 1/|C_b| (station.py:173), rate-fair 1/sum(1/r0) (:180), proportional-fair 1/(sum(priority) + eps) (:194)
+__device__ __forceinline__ double share_factor(int model, int cnt, double sum) {
+    const double d = model == DCB_SHARE_RESOURCE_FAIR ? (double)cnt
+                                                      : (model == DCB_SHARE_PROPORTIONAL_FAIR ? sum + DCB_EPSILON : sum);
+    return dcb_rcp(d);
+}
+
+// Shared rate of one link from its value and the BS factor (station.py:152-202)
+__device__ __forceinline__ double shared_rate(int model, double v, double fac, int arg, int i, double ewma_eps) {
+    if (model == DCB_SHARE_RESOURCE_FAIR) return v * fac;                                       // :173
+    if (model == DCB_SHARE_RATE_FAIR) return fac;                                               // :180
     if (model == DCB_SHARE_MAX_CAP) return arg == i ? v : 0.0;                                  // :184-187
-    return v * dcb_rcp(sum + DCB_EPSILON) * (v * ewma_eps);                                     // :194-195, r0 = v (ewma + eps)
+    return v * fac * (v * ewma_eps);                                                            // :194-195, r0 = v (ewma + eps)
+}
+
+// Largest squared distance d2 with fl(sqrt(d2)) <= vel: `curr_pos.distance(waypoint) <= velocity` (movement.py:142-145)
+// becomes one compare.  fl(sqrt) is monotone, so the set is a down-set and the boundary sits within a few ulps of vel^2.
+__device__ __noinline__ double snap_threshold(double vel) {
+    if (!(vel > 0.0)) return 0.0;            // sqrt(d2) <= 0  <=>  d2 == 0
+    double c = vel * vel;
+    for (int it = 0; it < 64 && sqrt(c) > vel; it++) c = __longlong_as_double(__double_as_longlong(c) - 1);
+    for (int it = 0; it < 64; it++) {
+        const double n = __longlong_as_double(__double_as_longlong(c) + 1);
+        if (!(sqrt(n) <= vel)) break;
+        c = n;
+    }
+    return c;
 }
 
 // fp32 normalised SNR (variants.py:276-284): (d2min / d2)^h with h = c2/20 = 1.5 + hr
@@ -207,12 +231,13 @@ __device__ __forceinline__ bool bar_or(int id, int n, bool pred) {
 // (tid, gsize: thread index within / size of the calling warp group)
 // [region:reduce_links]
 // For every (env, BS) pair walk the bitset of connected UEs: count, sum of link values X[ue][bs], first arg-max
-// (max-cap only).  Done for two bitsets (current masks -> *_a, next step's masks -> *_b).  S lanes per pair take the
-// 32-UE words round-robin; fixed combination order -> deterministic.
+// (max-cap only), folded into the pair's sharing factor (share_factor).  Done for two bitsets (current masks -> *_a,
+// next step's masks -> *_b).  S lanes per pair take the 32-UE words round-robin; fixed combination order ->
+// deterministic.
 __device__ __forceinline__ void reduce_links(int tid, int gsize, const double *X, const unsigned *bits_a,
                                              const unsigned *bits_b, int N, int M, int MS, int n_env, int S,
-                                             bool want_arg, int *cnt_a, double *sum_a, int *arg_a, int *cnt_b,
-                                             double *sum_b, int *arg_b) {
+                                             bool want_arg, const int *share, double *fac_a, int *arg_a,
+                                             double *fac_b, int *arg_b) {
     const int R = n_env * M;
     const int NW = (N + 31) >> 5;
     const int ls = 31 - __clz(S);                 // S is a power of two
@@ -222,10 +247,11 @@ __device__ __forceinline__ void reduce_links(int tid, int gsize, const double *X
     for (int base = 0; base < R; base += ppp) {
         const int pair = base + (tid >> ls);
         const bool ok = pair < R;
-        int c0 = 0, c1 = 0, a0 = 0x7fffffff, a1 = 0x7fffffff;
+        int c0 = 0, c1 = 0, a0 = 0x7fffffff, a1 = 0x7fffffff, model = 0;
         double s0 = 0.0, s1 = 0.0, b0 = 0.0, b1 = 0.0;
         if (ok) {
             const int le = __float2int_rz(((float)pair + 0.5f) * inv_m), b = pair - le * M;   // exact: pair < 2^16
+            model = share[b];
             const double *col = X + (size_t)(le * N) * MS + b;
             for (int w = seg; w < NW; w += S) {
                 const unsigned wa = bits_a[pair * NW + w];
@@ -263,8 +289,9 @@ __device__ __forceinline__ void reduce_links(int tid, int gsize, const double *X
             }
         }
         if (ok && seg == 0) {
-            cnt_a[pair] = c0; sum_a[pair] = s0; arg_a[pair] = a0;
-            cnt_b[pair] = c1; sum_b[pair] = s1; arg_b[pair] = a1;
+            fac_a[pair] = share_factor(model, c0, s0);
+            fac_b[pair] = share_factor(model, c1, s1);
+            if (want_arg) { arg_a[pair] = a0; arg_b[pair] = a1; }
         }
     }
 }
@@ -350,11 +377,9 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
     MathTables *tab = reinterpret_cast<MathTables *>(smem + L.off_tab);
     float *stage = reinterpret_cast<float *>(smem + L.off_stage);
     double *X = reinterpret_cast<double *>(smem + L.off_x);
-    int *cnt_pre = reinterpret_cast<int *>(smem + L.off_cnt_pre);
-    double *sum_pre = reinterpret_cast<double *>(smem + L.off_sum_pre);
+    double *fac_pre = reinterpret_cast<double *>(smem + L.off_fac_pre);
     int *arg_pre = reinterpret_cast<int *>(smem + L.off_arg_pre);
-    int *cnt_post = reinterpret_cast<int *>(smem + L.off_cnt_post);
-    double *sum_post = reinterpret_cast<double *>(smem + L.off_sum_post);
+    double *fac_post = reinterpret_cast<double *>(smem + L.off_fac_post);
     int *arg_post = reinterpret_cast<int *>(smem + L.off_arg_post);
     int *cnt_obs = reinterpret_cast<int *>(smem + L.off_cnt_obs);
     double *usum = reinterpret_cast<double *>(smem + L.off_usum);
@@ -376,6 +401,8 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
     unsigned *bits_post2 = reinterpret_cast<unsigned *>(smem + L.off_bits);   // [2][nbits]
     unsigned *bits_pre2 = bits_post2 + 2 * L.nbits;                            // [2][nbits]
     unsigned *bits_fresh = bits_pre2 + 2 * L.nbits;                            // [nbits]
+    unsigned short *links = reinterpret_cast<unsigned short *>(smem + L.off_links);
+    double *vthr = reinterpret_cast<double *>(smem + L.off_vthr);
 
     const int G = blockDim.x >> 1;                  // threads per warp group
     const bool is_obs = (int)threadIdx.x >= G;
@@ -400,6 +427,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
     }
     for (int j = threadIdx.x; j < N; j += blockDim.x) velspec[j] = p.vel_spec[j];
     for (int j = threadIdx.x; j < 5 * L.nbits; j += blockDim.x) bits_post2[j] = 0u;
+    if (threadIdx.x >= 32 && threadIdx.x < 48) vthr[threadIdx.x - 32] = snap_threshold((double)(threadIdx.x - 32));
     __syncthreads();
 
     if (!is_obs) {
@@ -419,19 +447,25 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
             tk = p.time[k];
         }
         const double vfix = valid ? velspec[i] : 0.0;
+        const double vfix_thr = vfix >= 0.0 ? snap_threshold(vfix) : 0.0;
         double *Xrow = X + (size_t)t * MS;
-        // this UE's bit in the per-(env, BS) UE bitsets
+        // this UE's bit in the per-(env, BS) UE bitsets: word index (low 24 bits) and bit number (high 8 bits)
         const int bit_word = le * M * NW + (i >> 5);
-        const unsigned bit_val = 1u << (i & 31);
-        // mask after the NEXT step's action, prepared at the end of a step (only meaningful when !fresh)
-        mask_t mask_next = 0;
+        const int bit_info = bit_word | ((i & 31) << 24);
+        const int lane = t & 31;
+        unsigned short *wl = links + (t >> 5) * L.links_per_warp;   // this warp's link list
+        double *Xwarp = X + (size_t)(t & ~31) * MS;
+        // carried from the end of one step to the next (only meaningful when the next step is not fresh):
+        mask_t mask_next = 0;     // mask after the next step's action
+        double rb_next = 0.0;     // the next step's reward before the move (base.py:446)
+        bool any_fresh = true;    // some env of this CTA starts the step without inherited aggregates (CTA-uniform)
 
         for (int step = 0; step < n_iter; step++) {
             const bool last = step == n_iter - 1;
             const int par = step & 1;
             unsigned *bits_post = bits_post2 + par * L.nbits;
             unsigned *bits_pre = bits_pre2 + par * L.nbits;
-            double rb = 0.0;      // reward before the move (base.py:446)
+            double rb = rb_next;
             int lost = 0;
             // next step's action: issued now so that the global-load latency hides behind this step's work
             int act_next = 0;
@@ -440,72 +474,73 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
             // the observers must be done with this parity's hand-off buffers (step - 2)
             if (step >= 2) bar_sync(BAR_EMPTY + par, 2 * G);
             if (T > 0) {
-                // ---- stand-alone pre phase: first step of the launch or a step that starts with an episode reset
-                bool fresh = step == 0;
-                if (valid && p.auto_reset && tk >= p.episode_length) {
-                    // MobileEnv.reset before the next step (base.py:169-189)
-                    const double2 ps = p.init_pos[u];
-                    x = ps.x; y = ps.y;
-                    const uint32_t e = p.table[u * p.D];
-                    wxy = (e & 0x3fffu) | (((e >> 14) & 0x3fffu) << 16);
-                    vpt = (e >> 28) | (1u << 16);
-                    mask = 0; ewma = 0.0; tk = 0;
-                    fresh = true;
-                }
-                if (valid) {
-                    if (fresh) {
-                        // apply_ue_actions (base.py:247-282) -> User.connect_to_bs(disconnect=True) (user.py:190-229)
-                        int act;
-                        if (a.pol.kind) {
-                            act = policy_action<mask_t>(a.pol, mask, x, y, bsxy, M, i, a.pol.call0 + step, u);
-                            if (a.actions_out) a.actions_out[(size_t)step * p.K * N + u] = act;
-                        } else {
-                            act = a.actions[(size_t)step * p.K * N + u];
-                        }
-                        if (act < 0 || act > M) {
-                            atomicOr(p.err, DCB_ERRBIT_ACTION);
-                        } else if (act > 0) {
-                            const int b = act - 1;
-                            const mask_t bit = (mask_t)1 << b;
-                            if (mask & bit) mask &= ~bit;
-                            else if (dist2(bsxy[b], x, y) <= p.thr_d2) mask |= bit;   // can_connect, station.py:222-226
-                        }
-                    } else {
-                        mask = mask_next;
+                if (any_fresh) {
+                    // ---- stand-alone pre phase: first step of the launch or a step that starts with an episode
+                    // reset in some env of this CTA (every env of the CTA recomputes; same arithmetic, same values)
+                    bool fresh = step == 0;
+                    if (valid && p.auto_reset && tk >= p.episode_length) {
+                        // MobileEnv.reset before the next step (base.py:169-189)
+                        const double2 ps = p.init_pos[u];
+                        x = ps.x; y = ps.y;
+                        const uint32_t e = p.table[u * p.D];
+                        wxy = (e & 0x3fffu) | (((e >> 14) & 0x3fffu) << 16);
+                        vpt = (e >> 28) | (1u << 16);
+                        mask = 0; ewma = 0.0; tk = 0;
+                        fresh = true;
                     }
-                }
-                if (bar_or(BAR_PHYS, G, fresh)) {
-                    // some env of this CTA has no inherited aggregates: recompute link values and reduce
                     if (valid) {
+                        if (fresh) {
+                            // apply_ue_actions (base.py:247-282) -> User.connect_to_bs(disconnect=True) (user.py:190-229)
+                            int act;
+                            if (a.pol.kind) {
+                                act = policy_action<mask_t>(a.pol, mask, x, y, bsxy, M, i, a.pol.call0 + step, u);
+                                if (a.actions_out) a.actions_out[(size_t)step * p.K * N + u] = act;
+                            } else {
+                                act = a.actions[(size_t)step * p.K * N + u];
+                            }
+                            if (act < 0 || act > M) {
+                                atomicOr(p.err, DCB_ERRBIT_ACTION);
+                            } else if (act > 0) {
+                                const int b = act - 1;
+                                const mask_t bit = (mask_t)1 << b;
+                                if (mask & bit) mask &= ~bit;
+                                else if (dist2(bsxy[b], x, y) <= p.thr_d2) mask |= bit;   // can_connect, station.py:222-226
+                            }
+                        } else {
+                            mask = mask_next;
+                        }
                         const double iee = dcb_rcp(ewma + DCB_EPSILON);
                         for (mask_t m = mask; m; m &= m - 1) {
                             const int b = mask_ffs(m) - 1;
                             Xrow[b] = link_value(share[b], rate_of_d2(p, tab, dist2(bsxy[b], x, y)), iee);
-                            atomicOr(&bits_fresh[bit_word + b * NW], bit_val);
+                            atomicOr(&bits_fresh[bit_word + b * NW], 1u << (i & 31));
                         }
                     }
                     bar_sync(BAR_PHYS, G);
-                    reduce_links(t, G, X, bits_fresh, bits_fresh, N, M, MS, n_env, S, p.has_maxcap, cnt_post, sum_post,
-                                 arg_post, cnt_pre, sum_pre, arg_pre);
+                    reduce_links(t, G, X, bits_fresh, bits_fresh, N, M, MS, n_env, S, p.has_maxcap, share, fac_post,
+                                 arg_post, fac_pre, arg_pre);
                     bar_sync(BAR_PHYS, G);
                     for (int j = t; j < L.nbits; j += G) bits_fresh[j] = 0u;
-                }
-// [region:P.pre_rates]
-                if (valid) {
-                    // ---- update_ue_drs_rewards (base.py:315-335): Basestation.data_rate_shared (station.py:152-202)
-                    // per connected link; the ue.bs_dr cache goes back into Xrow
-                    const double ee = ewma + DCB_EPSILON;
-                    double dr = 0.0;
-                    for (mask_t m = mask; m; m &= m - 1) {
-                        const int b = mask_ffs(m) - 1;
-                        const int pr = le * M + b;
-                        const double r = shared_rate(share[b], Xrow[b], cnt_pre[pr], sum_pre[pr], arg_pre[pr], i, ee);
-                        Xrow[b] = r;
-                        dr += r;                                                       // user.py:64-69
+                    if (valid) {
+                        // ---- update_ue_drs_rewards (base.py:315-335): Basestation.data_rate_shared (station.py:152-202)
+                        // per connected link; the ue.bs_dr cache goes back into Xrow; calc_reward (base.py:158-167),
+                        // penalties are identically 0 (base.py:257)
+                        const double ee = ewma + DCB_EPSILON;
+                        double dr = 0.0;
+                        for (mask_t m = mask; m; m &= m - 1) {
+                            const int b = mask_ffs(m) - 1;
+                            const int pr = le * M + b;
+                            const double r = shared_rate(share[b], Xrow[b], fac_pre[pr], arg_pre[pr], i, ee);
+                            Xrow[b] = r;
+                            dr += r;                                                   // user.py:64-69
+                        }
+                        rb = log_utility(tab, dr) * (1.0 / DCB_MAX_UTILITY);
                     }
-                    // ---- calc_reward (base.py:158-167), penalties are identically 0 (base.py:257)
-                    rb = log_utility(tab, dr) / DCB_MAX_UTILITY;
+                } else {
+                    mask = mask_next;
+                }
 // [region:P.move]
+                if (valid) {
                     // ---- User.move (user.py:159-173) -> RandomWaypoint.step (movement.py:158-181)
                     double wx = (double)(wxy & 0xffffu), wy = (double)(wxy >> 16);
                     unsigned pause = (vpt >> 8) & 0xffu;
@@ -530,19 +565,22 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                     }
                     vpt = (vpt & 0xffff00ffu) | (pause << 8);
                     if (moving) {
-                        // movement.py:132-156
-                        const double vel = vfix >= 0.0 ? vfix : (double)(vpt & 0xffu);
-                        if (sqrt(dist2(x, y, wx, wy)) <= vel) {
+                        // movement.py:132-156; `distance <= velocity` as a compare of the squared distance (snap_threshold)
+                        const bool drawn = vfix < 0.0;
+                        const double vel = drawn ? (double)(vpt & 0xffu) : vfix;
+                        const double snap = drawn ? vthr[vpt & 0xfu] : vfix_thr;
+                        const double vx = wx - x, vy = wy - y;
+                        if (vx * vx + vy * vy <= snap) {
                             x = wx; y = wy;
                         } else {
-                            const double vx = wx - x, vy = wy - y;
                             const double norm = sqrt(fma(vy, vy, vx * vx));   // np.linalg.norm -> FMA-accumulating ddot
                             x = x + vel * (vx / norm);
                             y = y + vel * (vy / norm);
                         }
                     }
 // [region:P.drop+ewma]
-                    // ---- check_bs_connection (user.py:175-188) + update_ewma_dr (user.py:148-157)
+                    // ---- check_bs_connection (user.py:175-188) + update_ewma_dr (user.py:148-157); Xrow holds the
+                    // pre-move shared rates (ue.bs_dr)
                     double keep = 0.0;
                     for (mask_t m = mask; m; m &= m - 1) {
                         const int b = mask_ffs(m) - 1;
@@ -553,55 +591,113 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                     tk += 1;                                                           // base.py:454
                 }
             }
-// [region:P.prefetch+sparse]
-            // ---- link values at the new position for update_ue_drs_rewards(update_only=True) (base.py:451) and for
-            // the next step's pre-move update (its action toggles one link, user.py:190-229: known now)
+// [region:P.next_action]
+            // ---- the next step's action toggles one link (user.py:190-229): known now, so the link values and the
+            // reduction below serve update_ue_drs_rewards(update_only=True) of this step (base.py:451) AND the
+            // pre-move update of the next step (base.py:446)
             mask_next = mask;
-            if (valid) {
-                if (T > 0 && !last) {
-                    int act = act_next;
-                    if (a.pol.kind) {
-                        act = policy_action<mask_t>(a.pol, mask, x, y, bsxy, M, i, a.pol.call0 + step + 1, u);
-                        if (a.actions_out) a.actions_out[(size_t)(step + 1) * p.K * N + u] = act;
-                    }
-                    if (act < 0 || act > M) {
-                        atomicOr(p.err, DCB_ERRBIT_ACTION);
-                    } else if (act > 0) {
-                        const int b = act - 1;
-                        const mask_t bit = (mask_t)1 << b;
-                        if ((mask & bit) || dist2(bsxy[b], x, y) <= p.thr_d2) mask_next = mask ^ bit;
-                    }
+            if (valid && T > 0 && !last) {
+                int act = act_next;
+                if (a.pol.kind) {
+                    act = policy_action<mask_t>(a.pol, mask, x, y, bsxy, M, i, a.pol.call0 + step + 1, u);
+                    if (a.actions_out) a.actions_out[(size_t)(step + 1) * p.K * N + u] = act;
                 }
-                const double iee = dcb_rcp(ewma + DCB_EPSILON);
-                for (mask_t m = mask | mask_next; m; m &= m - 1) {
+                if (act < 0 || act > M) {
+                    atomicOr(p.err, DCB_ERRBIT_ACTION);
+                } else if (act > 0) {
+                    const int b = act - 1;
+                    const mask_t bit = (mask_t)1 << b;
+                    if ((mask & bit) || dist2(bsxy[b], x, y) <= p.thr_d2) mask_next = mask ^ bit;
+                }
+            }
+// [region:P.links]
+            // ---- link values at the new position, balanced over the warp: the lanes' links (1.6 on average, up to M)
+            // are compacted into a per-warp list and dealt out round-robin, LW per lane and trip in one basic block
+            {
+                const mask_t un = valid ? (mask | mask_next) : (mask_t)0;
+                const int n = M32 ? __popc((unsigned)un) : __popcll((unsigned long long)un);
+                int incl = n;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += o;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                int pos = incl - n;
+                for (mask_t m = un; m; m &= m - 1) {
                     const int b = mask_ffs(m) - 1;
-                    Xrow[b] = link_value(share[b], rate_of_d2(p, tab, dist2(bsxy[b], x, y)), iee);
-                    if ((mask >> b) & 1) atomicOr(&bits_post[bit_word + b * NW], bit_val);
-                    if ((mask_next >> b) & 1) atomicOr(&bits_pre[bit_word + b * NW], bit_val);
+                    const unsigned fl = ((unsigned)(mask >> b) & 1u) | (((unsigned)(mask_next >> b) & 1u) << 1);
+                    wl[pos++] = (unsigned short)(lane | (b << 5) | (fl << 11));
+                }
+                __syncwarp();
+                const double iee = dcb_rcp(ewma + DCB_EPSILON);
+                constexpr int LW = 2;
+                for (int base = 0; base < total; base += 32 * LW) {
+                    unsigned e[LW];
+                    double d2[LW], v[LW], oi[LW];
+                    int ow[LW], bi[LW];
+#pragma unroll
+                    for (int q = 0; q < LW; q++) {
+                        const int idx = base + q * 32 + lane;
+                        e[q] = idx < total ? (unsigned)wl[idx] | 0x8000u : (unsigned)lane;
+                        ow[q] = e[q] & 31;
+                        const double ox = __shfl_sync(0xffffffffu, x, ow[q]);
+                        const double oy = __shfl_sync(0xffffffffu, y, ow[q]);
+                        oi[q] = __shfl_sync(0xffffffffu, iee, ow[q]);
+                        bi[q] = __shfl_sync(0xffffffffu, bit_info, ow[q]);
+                        const int b = (e[q] >> 5) & 63;
+                        d2[q] = dist2(bsxy[b], ox, oy);
+                        v[q] = link_value_sel(share[b], rate_of_d2_fast(p, tab, d2[q]), oi[q]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < LW; q++) {
+                        if (e[q] & 0x8000u) {
+                            const int b = (e[q] >> 5) & 63;
+                            double val = v[q];
+                            if (d2[q] < DCB_NEAR_D2)        // within ~1 m of the BS: the verbatim libm chain
+                                val = link_value(share[b], rate_of_d2_libm(p.c1, p.c2, d2[q]), oi[q]);
+                            Xwarp[(size_t)ow[q] * MS + b] = val;
+                            const int bw = (bi[q] & 0xffffff) + b * NW;
+                            const unsigned bv = 1u << ((unsigned)bi[q] >> 24);
+                            if (e[q] & (1u << 11)) atomicOr(&bits_post[bw], bv);
+                            if (e[q] & (1u << 12)) atomicOr(&bits_pre[bw], bv);
+                        }
+                    }
                 }
             }
 // [region:P.reduce_phase]
-            bar_sync(BAR_PHYS, G);
-            reduce_links(t, G, X, bits_post, bits_pre, N, M, MS, n_env, S, p.has_maxcap, cnt_post, sum_post, arg_post,
-                         cnt_pre, sum_pre, arg_pre);
+            // barrier + "does any env of this CTA reset before the next step?" in one bar.red
+            any_fresh = bar_or(BAR_PHYS, G, valid && T > 0 && p.auto_reset && tk >= p.episode_length);
+            reduce_links(t, G, X, bits_post, bits_pre, N, M, MS, n_env, S, p.has_maxcap, share, fac_post, arg_post,
+                         fac_pre, arg_pre);
             bar_sync(BAR_PHYS, G);
             // bits_pre of this parity is consumed; its next use is two steps (>= 2 group barriers) away
             for (int j = t; j < L.nbits; j += G) bits_pre[j] = 0u;
             if (valid) {
-// [region:P.post_rates+handoff]
-                // ---- post-move rates -> utility (user.py:76-92) -> hand-off
+// [region:P.rates+handoff]
+                // ---- post-move rates of this step and pre-move rates of the next one in ONE pass over the links;
+                // the next step's ue.bs_dr cache goes back into Xrow.  utility (user.py:76-92), reward (base.py:158-167)
                 const double ee = ewma + DCB_EPSILON;
-                double dr = 0.0;
-                for (mask_t m = mask; m; m &= m - 1) {
+                double dr = 0.0, dr_pre = 0.0;
+                for (mask_t m = mask | mask_next; m; m &= m - 1) {
                     const int b = mask_ffs(m) - 1;
                     const int pr = le * M + b;
-                    const double r = shared_rate(share[b], Xrow[b], cnt_post[pr], sum_post[pr], arg_post[pr], i, ee);
-                    if (last && a.out.dbg_link_rate) a.out.dbg_link_rate[u * M + b] = r;
-                    dr += r;
+                    const int model = share[b];
+                    const double v = Xrow[b];
+                    const double r_post = shared_rate(model, v, fac_post[pr], arg_post[pr], i, ee);
+                    const double r_pre = shared_rate(model, v, fac_pre[pr], arg_pre[pr], i, ee);
+                    if ((mask >> b) & 1) {
+                        if (last && a.out.dbg_link_rate) a.out.dbg_link_rate[u * M + b] = r_post;
+                        dr += r_post;
+                    }
+                    if ((mask_next >> b) & 1) dr_pre += r_pre;                         // user.py:64-69
+                    Xrow[b] = r_pre;
                 }
+                const double util = log_utility(tab, dr);
+                rb_next = log_utility(tab, dr_pre) * (1.0 / DCB_MAX_UTILITY);
                 const int h = par * EN + t;
                 hx[h] = x; hy[h] = y; hmask[h] = mask;
-                hutil[h] = log_utility(tab, dr);
+                hutil[h] = util;
                 hrb[h] = rb; hdr[h] = dr; hlost[h] = lost;
             }
             bar_arrive(BAR_FULL + par, 2 * G);
@@ -664,27 +760,32 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                 // ---- dense pass A: squared distances (fp64, exact range decision multi_agent.py:60 /
                 // station.py:222-226), parked in the tile as float for pass B
                 mask_t inrange = 0;
-                double d2min = CUDART_INF;
+                float d2minf = CUDART_INF_F;
 #pragma unroll 2
                 for (int b = 0; b < M; b++) {
                     const double d2 = dist2(bsxy[b], x, y);
-                    d2min = fmin(d2min, d2);
+                    const float d2f = (float)d2;
+                    d2minf = fminf(d2minf, d2f);            // float conversion is monotone: the min commutes with it
                     if (d2 <= p.thr_d2) inrange |= (mask_t)1 << b;
-                    row_dr[b] = (float)d2;
+                    row_dr[b] = d2f;
                 }
                 // ---- dense pass B: 'dr' = snr_b / max_b snr_b (variants.py:276-284) = (d2min / d2_b)^h
-                if (d2min >= DCB_NEAR_D2) {
-                    const float d2minf = (float)d2min;
+                if (d2minf >= (float)DCB_NEAR_D2) {
 #pragma unroll 2
                     for (int b = 0; b < M; b++) row_dr[b] = norm_snr_f32(row_dr[b], d2minf, hr);
                 } else {
+                    double d2min = CUDART_INF;
+                    for (int b = 0; b < M; b++) {
+                        const double d2 = dist2(bsxy[b], x, y);
+                        d2min = d2 < d2min ? d2 : d2min;
+                    }
                     const double inv_max = dcb_rcp(snr_of_d2(p, tab, d2min));
                     for (int b = 0; b < M; b++)
                         row_dr[b] = (float)(snr_of_d2(p, tab, dist2(bsxy[b], x, y)) * inv_max);
                 }
 // [region:O.staging]
                 // ---- rest of the observation row
-                const double un = util / DCB_MAX_UTILITY;                              // variants.py:287
+                const double un = util * (1.0 / DCB_MAX_UTILITY);                      // variants.py:287
                 if (central) {
                     for (int b = 0; b < M; b++) row_conn[b] = (float)((unsigned)(mask >> b) & 1u);
                     tile[(size_t)le * (2 * N * M + N) + 2 * N * M + i] = (float)un;
@@ -757,7 +858,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                                     nn += cnt_obs[le * M + b];
                                     tot += usum[le * M + b];
                                 }
-                                if (nn > 0) agg = mask == 0 ? (tot + util) / (double)(nn + 1) : tot / (double)nn;
+                                if (nn > 0) agg = (mask == 0 ? tot + util : tot) * dcb_rcp((double)(mask == 0 ? nn + 1 : nn));
                             } else if (p.reward == DCB_REWARD_SUM) {
                                 // user.py:238-244: UEs sharing any BS with this UE; their PRE-move rewards
                                 agg = 0.0;
