@@ -266,9 +266,11 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     env->grid = (K + E - 1) / E;
     env->smem = dcb_step_smem_bytes(cfg->kind, N, M, E);
     // reducer lanes per (env, BS) pair: one per 32-UE bitset word, power of two, while the pairs still fit the CTA
-    int S = 1;
+    // (more lanes than words: the words are cut into 16- or 8-bit chunks)
+    int S = 1, CS = 0;
     const int NW = (N + 31) / 32;
-    while (S < NW && S * 2 <= 32 && E * M * S * 2 <= group) S *= 2;
+    while (S < 4 * NW && S * 2 <= 32 && E * M * S * 2 <= group) S *= 2;
+    while ((NW << CS) < S && CS < 2) CS++;
 
     const size_t KN = (size_t)K * N;
     // pause_duration + 1 steps is the shortest possible redraw cycle (movement.py:168-181); +2 = entry 0 and slack
@@ -303,7 +305,7 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     memset(&p, 0, sizeof(p));
     p.K = K; p.N = N; p.M = M; p.kind = cfg->kind; p.reward = cfg->reward;
     p.episode_length = cfg->episode_length; p.auto_reset = cfg->auto_reset; p.pause_duration = cfg->pause_duration;
-    p.D = D; p.E = E; p.S = S;
+    p.D = D; p.E = E; p.S = S; p.CS = CS;
     p.has_maxcap = has_maxcap; p.has_propfair = has_pf;
     // station.py:112-114 with the host libm, exactly as the reference evaluates them
     const double ch = 0.8 + (1.1 * log10(2500.0) - 0.7) * 1.5 - 1.56 * log10(2500.0);
@@ -312,6 +314,9 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     p.thr_d2 = threshold_d2(p.c1, p.c2);
     p.snr_c0 = log2(10.0) * (DCB_TX_POWER - p.c1) / 10.0 - log2(DCB_NOISE);
     p.snr_h = p.c2 / 20.0;
+    // (1 + r)^(-h) = sum_k binom(-h, k) r^k
+    p.pw[0] = 1.0;
+    for (int k = 1; k < 10; k++) p.pw[k] = p.pw[k - 1] * (-p.snr_h - (double)(k - 1)) / (double)k;
     p.bs_xy = env->d_bs_xy; p.sharing = env->d_sharing; p.vel_spec = env->d_vel;
     p.pos = env->d_pos; p.mv = env->d_mv; p.mask = env->d_mask; p.ewma = env->d_ewma; p.time = env->d_time;
     p.init_pos = env->d_init_pos; p.table = env->d_table; p.err = env->d_err;

@@ -32,10 +32,12 @@ struct DevParams {
     int D;               // waypoint-table depth per UE
     int E;               // envs per CTA
     int S;               // reducer lanes per (env, BS) pair, power of two <= 32
+    int CS;              // log2 of the bitset chunks per 32-UE word the reducer lanes deal out (0: whole words)
     int has_maxcap, has_propfair;
     double thr_d2;       // largest squared distance that is still in range (snr > 2e-8, station.py:224)
     double c1, c2;       // Okumura-Hata constants (station.py:112-114)
     double snr_c0, snr_h; // snr(d) = 2^(snr_c0 - snr_h * log2(d^2)): the same model folded for the fast path
+    double pw[10];       // binomial series of (1 + r)^(-snr_h): coefficients of r^0 .. r^9 (dcb_snr_inrange)
     const double *bs_xy; // [M][2]
     const int *sharing;  // [M]
     const double *vel_spec;  // [N]
@@ -52,11 +54,13 @@ struct DevParams {
 
 // ---- shared-memory layout of the step kernel (byte offsets), computed once on the host
 struct SmemLayout {
-    int off_tab, off_stage, off_x, off_fac_pre, off_fac_post, off_usum, off_umin, off_fues, off_futil, off_hx, off_hy,
-        off_hmask, off_hutil, off_hrb, off_hdr, off_hlost, off_env_rew, off_env_sumu, off_bsx, off_bsy, off_vel,
-        off_arg_pre, off_arg_post, off_cnt_obs, off_bits, off_share, off_links, off_vthr;
+    int off_tab, off_stage, off_x, off_fac_pre, off_fac_post, off_hx, off_hy,
+        off_hmask, off_hutil, off_hrb, off_hdr, off_hlost, off_bsx, off_bsy, off_vel,
+        off_arg_pre, off_arg_post, off_bits, off_share, off_links, off_vthr, off_wagg;
     int nbits;   // words per bitset
     int links_per_warp;   // capacity (entries) of one physics warp's link list
+    int wagg_pairs;       // (env, BS) pairs one observer warp aggregates for itself: the envs its 32 rows touch x M
+    int wagg_stride;      // bytes of one observer warp's aggregate block
     int total;
 };
 
@@ -72,15 +76,12 @@ __host__ __device__ inline SmemLayout dcb_smem_layout(int kind, int N, int M, in
     SmemLayout L;
     const int EN = E * N, EM = E * M;
     int o = 0;
-    L.off_tab = o;      o += 3 * 16 * 8;                             // 3 x 128 B: one bank row per table
+    L.off_tab = o;      o += 5 * 16 * 8;                             // 5 x 128 B: one bank row per table
     L.off_stage = o;    o += align16(EN * obs_width(kind, M) * 4) + 16;   // float obs tile of the CTA (+ alignment shift)
     L.off_x = o;        o += align16(EN * row_stride(M) * 8);        // link values of connected links
     L.off_fac_pre = o;  o += align16(EM * 8);                        // per-(env, BS) sharing factor, next step's masks
     L.off_fac_post = o; o += align16(EM * 8);                        // ... current masks
-    L.off_usum = o;     o += align16(EM * 8);
-    L.off_umin = o;     o += align16(EM * 8);
-    L.off_fues = o;     o += align16(EM * 4);
-    L.off_futil = o;    o += align16(EM * 4);
+    // per-(env, BS) utility aggregates and per-env sums the physics warps hand to the observers, two parities
     // physics -> observer hand-off, two parities: position, mask, utility, pre-move reward, rate, lost links
     L.off_hx = o;       o += align16(2 * EN * 8);
     L.off_hy = o;       o += align16(2 * EN * 8);
@@ -89,22 +90,24 @@ __host__ __device__ inline SmemLayout dcb_smem_layout(int kind, int N, int M, in
     L.off_hrb = o;      o += align16(2 * EN * 8);
     L.off_hdr = o;      o += align16(2 * EN * 8);
     L.off_hlost = o;    o += align16(2 * EN * 4);
-    L.off_env_rew = o;  o += align16(E * 8);
-    L.off_env_sumu = o; o += align16(E * 8);
     L.off_bsx = o;      o += align16(M * 8);
     L.off_bsy = o;      o += align16(M * 8);
     L.off_vel = o;      o += align16(N * 8);
     L.off_arg_pre = o;  o += align16(EM * 4);
     L.off_arg_post = o; o += align16(EM * 4);
-    L.off_cnt_obs = o;  o += align16(EM * 4);
     L.nbits = EM * ((N + 31) / 32);
-    L.off_bits = o;     o += align16(5 * L.nbits * 4);               // UE bitsets per (env, BS): post[2], pre[2], fresh
+    L.off_bits = o;     o += align16(6 * L.nbits * 4);               // UE bitsets per (env, BS): post[3], pre[2], fresh
     L.off_share = o;    o += align16(M * 4);
     // per physics warp: compacted list of the warp's links (owner lane, BS, membership flags), 2 bytes per entry;
     // worst case every UE of the warp is linked to every BS
     L.links_per_warp = 32 * M;
     L.off_links = o;    o += align16(((EN + 31) / 32) * L.links_per_warp * 2);
     L.off_vthr = o;     o += align16(16 * 8);                        // snap thresholds for drawn velocities 0..15
+    // per observer warp: utility aggregates of the (env, BS) pairs its rows need -- usum, umin (double), cnt (int),
+    // f_ues, f_util (float) -- computed by the warp itself so that observer warps never synchronise with each other
+    L.wagg_pairs = ((31 / N + 2) * M + 1) & ~1;
+    L.wagg_stride = align16(L.wagg_pairs * 28);
+    L.off_wagg = o;     o += ((EN + 31) / 32) * L.wagg_stride;
     L.total = o;
     return L;
 }

@@ -44,7 +44,7 @@
 #include "dcb_internal.h"
 #include "dcb_math.cuh"
 
-static_assert(sizeof(MathTables) == 3 * 16 * 8, "SmemLayout reserves 3 x 128 B for the math tables");
+static_assert(sizeof(MathTables) == 5 * 16 * 8, "SmemLayout reserves 5 x 128 B for the math tables");
 
 namespace {
 
@@ -55,33 +55,30 @@ __device__ __forceinline__ double dist2(double2 a, double bx, double by) {   // 
     return dx * dx + dy * dy;
 }
 
-// station.py:110-138 verbatim with libm, for a UE within ~1 m of the BS (distance + EPSILON matters; snr > 1/32)
-__device__ __noinline__ double snr_of_d2_libm(double c1, double c2, double d2) {
-    const double d = sqrt(d2);
-    const double pl = c1 + c2 * log10(d + DCB_EPSILON);
-    const double signal = pow(10.0, (DCB_TX_POWER - pl) / 10.0);
-    return signal / DCB_NOISE;
-}
-__device__ __noinline__ double rate_of_d2_libm(double c1, double c2, double d2) {
-    return DCB_BW * log2(1.0 + snr_of_d2_libm(c1, c2, d2));
-}
+// SNR = 10^((30 - c1 - c2 log10(d + EPSILON)) / 10) / 1e-9 = 2^(c0 - 2 h log2(d + EPSILON)),  h = c2 / 20  (station.py:110-127).
+// EPSILON = 1e-16 changes d by less than half an ulp for d >= 1 m, so from 1 m on the SNR is a power law in d^2.
+#define DCB_NEAR_D2 1.1        // below this squared distance snr can exceed 1/32: general log2(1 + snr)
+#define DCB_FAR_D2 65536.0     // dcb_snr_inrange covers binary exponents 0..15 of d^2
 
-#define DCB_NEAR_D2 1.1   // below this squared distance the verbatim libm path is used (snr(1.1) = 0.0275 < 1/32)
-
-// SNR = 10^((30 - c1 - c2 log10(d)) / 10) / 1e-9 = 2^(c0 - h log2(d^2)),  h = c2 / 20      (station.py:110-127)
+// any distance, including d = 0 (a UE that snapped onto a waypoint at a BS position): ~3x the cost of the table form
+__device__ __noinline__ double snr_of_d2_general(double c0, double h, const MathTables *tab, double d2) {
+    const double d = sqrt(d2) + DCB_EPSILON;
+    return dcb_exp2(tab, fma(-2.0 * h, dcb_log2(tab, d), c0));
+}
 __device__ __forceinline__ double snr_of_d2(const DevParams &p, const MathTables *tab, double d2) {
-    if (d2 < DCB_NEAR_D2) return snr_of_d2_libm(p.c1, p.c2, d2);
-    return dcb_exp2(tab, fma(-p.snr_h, dcb_log2(tab, d2), p.snr_c0));
+    if (d2 >= 1.0 && d2 < DCB_FAR_D2) return dcb_snr_inrange(tab, p.pw, d2);
+    return snr_of_d2_general(p.snr_c0, p.snr_h, tab, d2);
 }
 
-// Unshared rate bw * log2(1 + snr) (station.py:129-138); on the fast path snr < 1/32 -> series in fl(1 + snr) - 1
-__device__ __forceinline__ double rate_of_d2_fast(const DevParams &p, const MathTables *tab, double d2) {
-    const double s = dcb_exp2(tab, fma(-p.snr_h, dcb_log2(tab, d2), p.snr_c0));
+// Unshared rate bw * log2(1 + snr) (station.py:129-138).  In range and not within ~1 m of the BS (every link but a
+// handful): table form of the power law, snr < 1/32 -> series in fl(1 + snr) - 1
+__device__ __forceinline__ double rate_of_d2_inrange(const DevParams &p, const MathTables *tab, double d2) {
+    const double s = dcb_snr_inrange(tab, p.pw, d2);
     return DCB_BW * dcb_log2_1p_small((1.0 + s) - 1.0);
 }
 __device__ __forceinline__ double rate_of_d2(const DevParams &p, const MathTables *tab, double d2) {
-    if (d2 < DCB_NEAR_D2) return rate_of_d2_libm(p.c1, p.c2, d2);
-    return rate_of_d2_fast(p, tab, d2);
+    if (d2 >= DCB_NEAR_D2 && d2 < DCB_FAR_D2) return rate_of_d2_inrange(p, tab, d2);
+    return DCB_BW * dcb_log2_1p(tab, snr_of_d2(p, tab, d2));
 }
 
 __device__ __forceinline__ double log_utility(const MathTables *tab, double dr) {
@@ -232,10 +229,11 @@ __device__ __forceinline__ bool bar_or(int id, int n, bool pred) {
 // [region:reduce_links]
 // For every (env, BS) pair walk the bitset of connected UEs: count, sum of link values X[ue][bs], first arg-max
 // (max-cap only), folded into the pair's sharing factor (share_factor).  Done for two bitsets (current masks -> *_a,
-// next step's masks -> *_b).  S lanes per pair take the 32-UE words round-robin; fixed combination order ->
-// deterministic.
+// next step's masks -> *_b).  S lanes per pair take the pair's chunks round-robin -- a chunk is a 32-UE bitset word
+// or, when there are more lanes than words, a 16- / 8-bit piece of one (CS = log2 chunks per word); fixed
+// combination order -> deterministic.
 __device__ __forceinline__ void reduce_links(int tid, int gsize, const double *X, const unsigned *bits_a,
-                                             const unsigned *bits_b, int N, int M, int MS, int n_env, int S,
+                                             const unsigned *bits_b, int N, int M, int MS, int n_env, int S, int CS,
                                              bool want_arg, const int *share, double *fac_a, int *arg_a,
                                              double *fac_b, int *arg_b) {
     const int R = n_env * M;
@@ -253,16 +251,19 @@ __device__ __forceinline__ void reduce_links(int tid, int gsize, const double *X
             const int le = __float2int_rz(((float)pair + 0.5f) * inv_m), b = pair - le * M;   // exact: pair < 2^16
             model = share[b];
             const double *col = X + (size_t)(le * N) * MS + b;
-            for (int w = seg; w < NW; w += S) {
-                const unsigned wa = bits_a[pair * NW + w];
-                const unsigned wb = bits_b[pair * NW + w];
+            const int cb = 32 >> CS;                                   // bits per chunk
+            const unsigned cmask = 0xffffffffu >> (32 - cb);
+            for (int c = seg; c < (NW << CS); c += S) {
+                const int w = c >> CS, sh = (c & ((1 << CS) - 1)) * cb;
+                const unsigned wa = (bits_a[pair * NW + w] >> sh) & cmask;
+                const unsigned wb = (bits_b[pair * NW + w] >> sh) & cmask;
                 c0 += __popc(wa);
                 c1 += __popc(wb);
                 unsigned both = wa | wb;
                 while (both) {
                     const int j = __ffs(both) - 1;
                     both &= both - 1;
-                    const int i = (w << 5) + j;
+                    const int i = (w << 5) + sh + j;
                     const double v = col[i * MS];
                     const bool ina = (wa >> j) & 1u, inb = (wb >> j) & 1u;
                     if (ina) s0 += v;
@@ -297,69 +298,56 @@ __device__ __forceinline__ void reduce_links(int tid, int gsize, const double *X
 }
 
 // [region:reduce_utility]
-// Per-BS connected count -> cnt, total utility (station.py:63-69) -> usum, the two per-BS observation entries
-// (variants.py:296-299, station.py:71-76) -> f_ues, f_util; min (station.py:78-83) -> umin.
-__device__ __forceinline__ void reduce_utility(int tid, int gsize, const unsigned *bits, const double *su, int N,
-                                               int M, int n_env, int S, bool want_min, int *cnt, double *usum,
-                                               double *umin, float *f_ues, float *f_util) {
-    const int R = n_env * M;
+// Observer-side aggregates, computed by every observer warp for itself (no barrier between observer warps): for the
+// n_le envs [le0, le0 + n_le) that the warp's 32 rows belong to and every BS -- connected count -> cnt, total utility
+// (station.py:63-69) -> usum, min (station.py:78-83) -> umin, and the two per-BS observation entries (variants.py:296-299,
+// station.py:71-76) -> f_ues, f_util.  Lane q walks the UE bitset of pair q in UE order; warps that share an env
+// compute bit-identical values.
+__device__ __forceinline__ void warp_reduce_utility(int lane, const unsigned *bits, const double *su, int N, int M,
+                                                    int le0, int n_le, bool want_min, int *cnt, double *usum,
+                                                    double *umin, float *f_ues, float *f_util) {
     const int NW = (N + 31) >> 5;
-    const int ls = 31 - __clz(S);
-    const int ppp = gsize >> ls;
-    const int seg = tid & (S - 1);
+    const int PW = n_le * M;
     const double inv_n = 1.0 / (double)N;
     const float inv_m = 1.0f / (float)M;
-    for (int base = 0; base < R; base += ppp) {
-        const int pair = base + (tid >> ls);
-        const bool ok = pair < R;
+    for (int q = lane; q < PW; q += 32) {
+        const int ll = __float2int_rz(((float)q + 0.5f) * inv_m), b = q - ll * M;   // exact: q < 2^16
+        const int le = le0 + ll;
+        const unsigned *pb = bits + (le * M + b) * NW;
+        const double *sue = su + le * N;
         double s = 0.0, mn = DCB_MAX_UTILITY;
         int c = 0;
-        if (ok) {
-            const int le = __float2int_rz(((float)pair + 0.5f) * inv_m);
-            const double *sue = su + le * N;
-            for (int w = seg; w < NW; w += S) {
-                unsigned wa = bits[pair * NW + w];
-                c += __popc(wa);
-                while (wa) {
-                    const int j = __ffs(wa) - 1;
-                    wa &= wa - 1;
-                    const double uu = sue[(w << 5) + j];
-                    s += uu;
-                    if (want_min) mn = fmin(mn, uu);
-                }
+        for (int w = 0; w < NW; w++) {
+            unsigned wa = pb[w];
+            c += __popc(wa);
+            while (wa) {
+                const int j = __ffs(wa) - 1;
+                wa &= wa - 1;
+                const double uu = sue[(w << 5) + j];
+                s += uu;
+                if (want_min) mn = uu < mn ? uu : mn;
             }
         }
-        for (int off = S >> 1; off > 0; off >>= 1) {
-            c += __shfl_xor_sync(0xffffffffu, c, off);
-            s += __shfl_xor_sync(0xffffffffu, s, off);
-            if (want_min) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
-        }
-        if (ok && seg == 0) {
-            cnt[pair] = c;
-            usum[pair] = s;
-            umin[pair] = mn;
-            f_ues[pair] = (float)((double)c * inv_n);                                          // |C_b| / N (variants.py:296)
-            f_util[pair] = c > 0 ? (float)(s * dcb_rcp((double)c) * (1.0 / DCB_MAX_UTILITY)) : 0.0f;
-        }
+        cnt[q] = c;
+        usum[q] = s;
+        umin[q] = mn;
+        f_ues[q] = (float)((double)c * inv_n);                                             // |C_b| / N (variants.py:296)
+        f_util[q] = c > 0 ? (float)(s * dcb_rcp((double)c) * (1.0 / DCB_MAX_UTILITY)) : 0.0f;
     }
 }
 
 // [region:reduce_env]
-// Per-env reduction of a per-UE vector: mode 0 = sum, 2 = min (one warp per env)
-__device__ __forceinline__ void reduce_env(int tid, int gsize, const double *v, int N, int n_env, int mode,
-                                           double *out) {
-    const int lane = tid & 31, warp = tid >> 5, nwarps = gsize >> 5;
+// Reduction of one env's per-UE vector by one warp: mode 0 = sum, 2 = min; every lane gets the result
+__device__ __forceinline__ double warp_reduce_env(int lane, const double *v, int N, int mode) {
     const int chunk = (N + 31) / 32;
-    for (int le = warp; le < n_env; le += nwarps) {
-        const int i0 = lane * chunk, i1 = min(N, i0 + chunk);
-        double s = mode == 2 ? CUDART_INF : 0.0;
-        for (int i = i0; i < i1; i++) s = mode == 2 ? fmin(s, v[le * N + i]) : s + v[le * N + i];
-        for (int off = 16; off > 0; off >>= 1) {
-            const double o = __shfl_xor_sync(0xffffffffu, s, off);
-            s = mode == 2 ? fmin(s, o) : s + o;
-        }
-        if (lane == 0) out[le] = s;
+    const int i0 = lane * chunk, i1 = min(N, i0 + chunk);
+    double s = mode == 2 ? CUDART_INF : 0.0;
+    for (int i = i0; i < i1; i++) s = mode == 2 ? fmin(s, v[i]) : s + v[i];
+    for (int off = 16; off > 0; off >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, s, off);
+        s = mode == 2 ? fmin(s, o) : s + o;
     }
+    return s;
 }
 
 // [region:kernel.setup]
@@ -381,11 +369,6 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
     int *arg_pre = reinterpret_cast<int *>(smem + L.off_arg_pre);
     double *fac_post = reinterpret_cast<double *>(smem + L.off_fac_post);
     int *arg_post = reinterpret_cast<int *>(smem + L.off_arg_post);
-    int *cnt_obs = reinterpret_cast<int *>(smem + L.off_cnt_obs);
-    double *usum = reinterpret_cast<double *>(smem + L.off_usum);
-    double *umin = reinterpret_cast<double *>(smem + L.off_umin);
-    float *f_ues = reinterpret_cast<float *>(smem + L.off_fues);
-    float *f_util = reinterpret_cast<float *>(smem + L.off_futil);
     double *hx = reinterpret_cast<double *>(smem + L.off_hx);
     double *hy = reinterpret_cast<double *>(smem + L.off_hy);
     unsigned long long *hmask = reinterpret_cast<unsigned long long *>(smem + L.off_hmask);
@@ -393,13 +376,11 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
     double *hrb = reinterpret_cast<double *>(smem + L.off_hrb);
     double *hdr = reinterpret_cast<double *>(smem + L.off_hdr);
     int *hlost = reinterpret_cast<int *>(smem + L.off_hlost);
-    double *env_rew = reinterpret_cast<double *>(smem + L.off_env_rew);
-    double *env_sumu = reinterpret_cast<double *>(smem + L.off_env_sumu);
     double2 *bsxy = reinterpret_cast<double2 *>(smem + L.off_bsx);   // [M] interleaved (off_bsx, off_bsy are adjacent)
     int *share = reinterpret_cast<int *>(smem + L.off_share);
     double *velspec = reinterpret_cast<double *>(smem + L.off_vel);
-    unsigned *bits_post2 = reinterpret_cast<unsigned *>(smem + L.off_bits);   // [2][nbits]
-    unsigned *bits_pre2 = bits_post2 + 2 * L.nbits;                            // [2][nbits]
+    unsigned *bits_post3 = reinterpret_cast<unsigned *>(smem + L.off_bits);   // [3][nbits]
+    unsigned *bits_pre2 = bits_post3 + 3 * L.nbits;                            // [2][nbits]
     unsigned *bits_fresh = bits_pre2 + 2 * L.nbits;                            // [nbits]
     unsigned short *links = reinterpret_cast<unsigned short *>(smem + L.off_links);
     double *vthr = reinterpret_cast<double *>(smem + L.off_vthr);
@@ -420,13 +401,13 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
     const int T = a.T;
     const int n_iter = T > 0 ? T : 1;
 
-    dcb_math_init(tab, threadIdx.x);
+    dcb_math_init(tab, threadIdx.x, p.snr_h, p.snr_c0);
     for (int b = threadIdx.x; b < M; b += blockDim.x) {
         bsxy[b] = make_double2(p.bs_xy[2 * b], p.bs_xy[2 * b + 1]);
         share[b] = p.sharing[b];
     }
     for (int j = threadIdx.x; j < N; j += blockDim.x) velspec[j] = p.vel_spec[j];
-    for (int j = threadIdx.x; j < 5 * L.nbits; j += blockDim.x) bits_post2[j] = 0u;
+    for (int j = threadIdx.x; j < 6 * L.nbits; j += blockDim.x) bits_post3[j] = 0u;
     if (threadIdx.x >= 32 && threadIdx.x < 48) vthr[threadIdx.x - 32] = snap_threshold((double)(threadIdx.x - 32));
     __syncthreads();
 
@@ -459,12 +440,14 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
         mask_t mask_next = 0;     // mask after the next step's action
         double rb_next = 0.0;     // the next step's reward before the move (base.py:446)
         bool any_fresh = true;    // some env of this CTA starts the step without inherited aggregates (CTA-uniform)
+        int rot = 0;              // step % 3: the post-move UE bitsets rotate over three buffers (see the clear below)
 
         for (int step = 0; step < n_iter; step++) {
             const bool last = step == n_iter - 1;
             const int par = step & 1;
-            unsigned *bits_post = bits_post2 + par * L.nbits;
+            unsigned *bits_post = bits_post3 + rot * L.nbits;
             unsigned *bits_pre = bits_pre2 + par * L.nbits;
+            rot = rot == 2 ? 0 : rot + 1;              // now (step + 1) % 3
             double rb = rb_next;
             int lost = 0;
             // next step's action: issued now so that the global-load latency hides behind this step's work
@@ -517,7 +500,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                         }
                     }
                     bar_sync(BAR_PHYS, G);
-                    reduce_links(t, G, X, bits_fresh, bits_fresh, N, M, MS, n_env, S, p.has_maxcap, share, fac_post,
+                    reduce_links(t, G, X, bits_fresh, bits_fresh, N, M, MS, n_env, S, p.CS, p.has_maxcap, share, fac_post,
                                  arg_post, fac_pre, arg_pre);
                     bar_sync(BAR_PHYS, G);
                     for (int j = t; j < L.nbits; j += G) bits_fresh[j] = 0u;
@@ -647,15 +630,15 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                         bi[q] = __shfl_sync(0xffffffffu, bit_info, ow[q]);
                         const int b = (e[q] >> 5) & 63;
                         d2[q] = dist2(bsxy[b], ox, oy);
-                        v[q] = link_value_sel(share[b], rate_of_d2_fast(p, tab, d2[q]), oi[q]);
+                        v[q] = link_value_sel(share[b], rate_of_d2_inrange(p, tab, d2[q]), oi[q]);
                     }
 #pragma unroll
                     for (int q = 0; q < LW; q++) {
                         if (e[q] & 0x8000u) {
                             const int b = (e[q] >> 5) & 63;
                             double val = v[q];
-                            if (d2[q] < DCB_NEAR_D2)        // within ~1 m of the BS: the verbatim libm chain
-                                val = link_value(share[b], rate_of_d2_libm(p.c1, p.c2, d2[q]), oi[q]);
+                            if (d2[q] < DCB_NEAR_D2 || d2[q] >= DCB_FAR_D2)   // within ~1 m of the BS (far: never in range)
+                                val = link_value(share[b], rate_of_d2(p, tab, d2[q]), oi[q]);
                             Xwarp[(size_t)ow[q] * MS + b] = val;
                             const int bw = (bi[q] & 0xffffff) + b * NW;
                             const unsigned bv = 1u << ((unsigned)bi[q] >> 24);
@@ -668,11 +651,16 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
 // [region:P.reduce_phase]
             // barrier + "does any env of this CTA reset before the next step?" in one bar.red
             any_fresh = bar_or(BAR_PHYS, G, valid && T > 0 && p.auto_reset && tk >= p.episode_length);
-            reduce_links(t, G, X, bits_post, bits_pre, N, M, MS, n_env, S, p.has_maxcap, share, fac_post, arg_post,
+            reduce_links(t, G, X, bits_post, bits_pre, N, M, MS, n_env, S, p.CS, p.has_maxcap, share, fac_post, arg_post,
                          fac_pre, arg_pre);
             bar_sync(BAR_PHYS, G);
-            // bits_pre of this parity is consumed; its next use is two steps (>= 2 group barriers) away
-            for (int j = t; j < L.nbits; j += G) bits_pre[j] = 0u;
+            // bits_pre of this parity is consumed; its next use is two steps (>= 2 group barriers) away.  The post
+            // bitsets of step - 2 were read by the observers, who are done with that step (EMPTY wait above); that
+            // buffer, (step + 1) % 3, is the one the next step fills
+            for (int j = t; j < L.nbits; j += G) {
+                bits_pre[j] = 0u;
+                if (step >= 2) bits_post3[rot * L.nbits + j] = 0u;
+            }
             if (valid) {
 // [region:P.rates+handoff]
                 // ---- post-move rates of this step and pre-move rates of the next one in ONE pass over the links;
@@ -729,29 +717,61 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
         // are written with scalar stores.
         const size_t per_env = central ? (size_t)(2 * N * M + N) : (size_t)N * OW;
         const unsigned tile_bytes = (unsigned)(per_env * n_env * 4);
+        // multi: a warp's 32 rows are one contiguous span of 128 * OW bytes (a multiple of 16 from the tile start), so
+        // every warp stores its own span and the observer warps never wait for each other
+        const bool warp_store = !central;
+        const int lane = t & 31;
+        const int w0 = t & ~31;
+        const int wrows = max(0, min(32, n_env * N - w0));
+        // envs this warp's rows belong to, and its private aggregate block (warp_reduce_utility)
+        const int le0 = w0 / N;
+        const int n_le = wrows > 0 ? (w0 + wrows - 1) / N - le0 + 1 : 0;
+        const int le_s0 = (w0 + N - 1) / N;          // first env whose UE 0 is one of this warp's rows
+        unsigned char *wagg = smem + L.off_wagg + (t >> 5) * L.wagg_stride;
+        double *usum_o = reinterpret_cast<double *>(wagg);
+        double *umin_o = usum_o + L.wagg_pairs;
+        int *cnt_o = reinterpret_cast<int *>(umin_o + L.wagg_pairs);
+        float *f_ues = reinterpret_cast<float *>(cnt_o + L.wagg_pairs);
+        float *f_util = f_ues + L.wagg_pairs;
+        const int lq = (le - le0) * M;               // this UE's env within the block
+        const bool want_env_rew = central && T > 0;
+        const bool want_env_sumu = a.out.sum_utility || a.out.dbg_sum_utility;
+        int orot = 0;                                 // step % 3 (the physics warps' rotating post bitsets)
 
         for (int step = 0; step < n_iter; step++) {
             const bool last = step == n_iter - 1;
             const int par = step & 1;
-            unsigned *bits_post = bits_post2 + par * L.nbits;
             const int hbase = par * EN;
             float *dst = a.out.obs ? a.out.obs + (size_t)step * a.out.obs_stride + (size_t)env0 * per_env : nullptr;
             const unsigned mis = (unsigned)((size_t)dst & 15);
             float *tile = stage + (mis >> 2);
             float *row_conn = tile + row_off;
             float *row_dr = central ? row_conn + N * M : row_conn + M;
-// [region:O.full_wait+util_reduce]
+// [region:O.full_wait]
             bar_sync(BAR_FULL + par, 2 * G);
-            // the previous step's TMA store must have finished reading the tile before anyone rewrites it
-            if (t == 0 && step > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            // the previous step's TMA store(s) must have finished reading the tile before anyone rewrites it
+            if (warp_store) {
+                if (lane == 0 && step > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            } else {
+                if (t == 0 && step > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                bar_sync(BAR_OBS, G);
+            }
+// [region:O.util_reduce]
+            const unsigned *bits_post = bits_post3 + orot * L.nbits;
+            orot = orot == 2 ? 0 : orot + 1;
             if (!central)
-                reduce_utility(t, G, bits_post, hutil + hbase, N, M, n_env, S, p.reward == DCB_REWARD_MIN, cnt_obs, usum,
-                               umin, f_ues, f_util);
-            if (central && T > 0) reduce_env(t, G, hrb + hbase, N, n_env, p.reward == DCB_REWARD_MIN ? 2 : 0, env_rew);
-            if (a.out.sum_utility || a.out.dbg_sum_utility) reduce_env(t, G, hutil + hbase, N, n_env, 0, env_sumu);
-            bar_sync(BAR_OBS, G);
-            // the UE bitsets of this parity are consumed
-            for (int j = t; j < L.nbits; j += G) bits_post[j] = 0u;
+                warp_reduce_utility(lane, bits_post, hutil + hbase, N, M, le0, n_le, p.reward == DCB_REWARD_MIN, cnt_o,
+                                    usum_o, umin_o, f_ues, f_util);
+            double env_rew_v = 0.0, env_sumu_v = 0.0;          // of the env whose UE 0 this thread is
+            if (want_env_rew || want_env_sumu) {
+                for (int es = le_s0; es < n_env && es * N < w0 + 32; es++) {
+                    double r1 = 0.0, r2 = 0.0;
+                    if (want_env_rew) r1 = warp_reduce_env(lane, hrb + hbase + es * N, N, p.reward == DCB_REWARD_MIN ? 2 : 0);
+                    if (want_env_sumu) r2 = warp_reduce_env(lane, hutil + hbase + es * N, N, 0);
+                    if (valid && le == es && i == 0) { env_rew_v = r1; env_sumu_v = r2; }
+                }
+            }
+            __syncwarp();
             if (valid) {
                 const int h = hbase + t;
                 const double x = hx[h], y = hy[h], util = hutil[h], dr = hdr[h];
@@ -770,7 +790,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                     row_dr[b] = d2f;
                 }
                 // ---- dense pass B: 'dr' = snr_b / max_b snr_b (variants.py:276-284) = (d2min / d2_b)^h
-                if (d2minf >= (float)DCB_NEAR_D2) {
+                if (d2minf >= 1e-6f) {        // below: d + EPSILON matters (in practice d = 0 exactly)
 #pragma unroll 2
                     for (int b = 0; b < M; b++) row_dr[b] = norm_snr_f32(row_dr[b], d2minf, hr);
                 } else {
@@ -790,7 +810,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                     for (int b = 0; b < M; b++) row_conn[b] = (float)((unsigned)(mask >> b) & 1u);
                     tile[(size_t)le * (2 * N * M + N) + 2 * N * M + i] = (float)un;
                 } else {
-                    const float *fu = f_ues + le * M, *fa = f_util + le * M;
+                    const float *fu = f_ues + lq, *fa = f_util + lq;
                     for (int b = 0; b < M; b++) {
                         row_conn[b] = (float)((unsigned)(mask >> b) & 1u);
                         row_conn[2 * M + b] = fu[b];
@@ -812,11 +832,11 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                         } else {
                             double *drow = a.out.dbg_obs + (size_t)u * OW;
                             for (int b = 0; b < M; b++) {
-                                const int c = cnt_obs[le * M + b];
+                                const int c = cnt_o[lq + b];
                                 drow[b] = (double)((unsigned)(mask >> b) & 1u);
                                 drow[M + b] = (double)row_dr[b];
                                 drow[2 * M + b] = (double)c / (double)N;
-                                drow[3 * M + b] = (c > 0 ? usum[le * M + b] / (double)c : 0.0) / DCB_MAX_UTILITY;
+                                drow[3 * M + b] = (c > 0 ? usum_o[lq + b] / (double)c : 0.0) / DCB_MAX_UTILITY;
                             }
                             drow[4 * M] = un;
                         }
@@ -833,15 +853,15 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                 if (last && a.out.dbg_utility) a.out.dbg_utility[u] = util;
                 if (i == 0) {
                     if (a.out.sum_utility)
-                        a.out.sum_utility[(size_t)step * a.out.sum_utility_stride + k] = (float)env_sumu[le];
-                    if (last && a.out.dbg_sum_utility) a.out.dbg_sum_utility[k] = env_sumu[le];
+                        a.out.sum_utility[(size_t)step * a.out.sum_utility_stride + k] = (float)env_sumu_v;
+                    if (last && a.out.dbg_sum_utility) a.out.dbg_sum_utility[k] = env_sumu_v;
                 }
                 if (T > 0) {
                     if (a.out.lost_conn) a.out.lost_conn[(size_t)step * a.out.lost_conn_stride + u] = (uint8_t)hlost[h];
                     if (central) {
                         if (i == 0) {
                             // central.py:65-73 over the PRE-move rewards
-                            double r = env_rew[le];
+                            double r = env_rew_v;
                             if (p.reward == DCB_REWARD_AVG) r = r / (double)N;
                             if (a.out.reward) a.out.reward[(size_t)step * a.out.reward_stride + k] = (float)r;
                             if (last && a.out.dbg_reward) a.out.dbg_reward[k] = r;
@@ -855,8 +875,8 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                                 double tot = 0.0;
                                 for (mask_t m = inrange; m; m &= m - 1) {
                                     const int b = mask_ffs(m) - 1;
-                                    nn += cnt_obs[le * M + b];
-                                    tot += usum[le * M + b];
+                                    nn += cnt_o[lq + b];
+                                    tot += usum_o[lq + b];
                                 }
                                 if (nn > 0) agg = (mask == 0 ? tot + util : tot) * dcb_rcp((double)(mask == 0 ? nn + 1 : nn));
                             } else if (p.reward == DCB_REWARD_SUM) {
@@ -867,7 +887,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                             } else {
                                 for (mask_t m = inrange; m; m &= m - 1) {
                                     const int b = mask_ffs(m) - 1;
-                                    agg = fmin(agg, umin[le * M + b]);
+                                    agg = fmin(agg, umin_o[lq + b]);
                                 }
                             }
                         }
@@ -877,13 +897,37 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                 }
             }
 // [region:O.tile_out]
-            // ---- obs tile -> global observation buffer (contiguous span of this CTA)
-            if (dst) {
-                // generic-proxy writes of the tile -> visible to the async proxy; then one elected thread issues the
-                // bulk copy (TMA, UBLKCP); its read completion is awaited before the tile is rewritten next step
+            // ---- obs tile -> global observation buffer (contiguous span of this CTA): generic-proxy writes of the
+            // tile -> visible to the async proxy; then an elected thread issues the bulk copy (TMA, UBLKCP); its read
+            // completion is awaited before the tile is rewritten next step
+            if (dst && warp_store) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (wrows > 0) {
+                    const unsigned wbytes = (unsigned)(wrows * OW * 4);
+                    const float *sp = tile + (size_t)w0 * OW;
+                    float *gp = dst + (size_t)w0 * OW;
+                    const unsigned head = (16u - mis) & 15u;                   // bytes up to the first 16-byte boundary
+                    const unsigned bulk = wbytes > head ? (wbytes - head) & ~15u : 0u;
+                    if (lane == 0 && bulk) {
+                        const unsigned src = (unsigned)__cvta_generic_to_shared(sp) + head;
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     :: "l"(reinterpret_cast<char *>(gp) + head), "r"(src), "r"(bulk) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    const int nf = (int)(wbytes >> 2);
+                    if (bulk) {
+                        const int hf = (int)(head >> 2), tail0 = (int)((head + bulk) >> 2);   // <= 3 floats on either side
+                        if (lane >= 1 && lane <= 3 && lane - 1 < hf) gp[lane - 1] = sp[lane - 1];
+                        if (lane >= 4 && lane <= 6 && tail0 + lane - 4 < nf) gp[tail0 + lane - 4] = sp[tail0 + lane - 4];
+                    } else {
+                        for (int j = lane; j < nf; j += 32) gp[j] = sp[j];
+                    }
+                }
+            } else if (dst) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 bar_sync(BAR_OBS, G);
-                const unsigned head = (16u - mis) & 15u;                       // bytes up to the first 16-byte boundary
+                const unsigned head = (16u - mis) & 15u;
                 const unsigned bulk = tile_bytes > head ? (tile_bytes - head) & ~15u : 0u;
                 if (t == 0 && bulk) {
                     const unsigned src = (unsigned)__cvta_generic_to_shared(tile) + head;
@@ -893,7 +937,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
                 }
                 const int nf = (int)(tile_bytes >> 2);
                 if (bulk) {
-                    const int hf = (int)(head >> 2), tail0 = (int)((head + bulk) >> 2);   // <= 3 floats on either side
+                    const int hf = (int)(head >> 2), tail0 = (int)((head + bulk) >> 2);
                     if (t >= 1 && t <= 3 && t - 1 < hf) dst[t - 1] = tile[t - 1];
                     if (t >= 4 && t <= 6 && tail0 + t - 4 < nf) dst[tail0 + t - 4] = tile[tail0 + t - 4];
                 } else {
@@ -903,7 +947,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
             // hand the parity's buffers back to the physics warps
             bar_arrive(BAR_EMPTY + par, 2 * G);
         }
-        if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (warp_store ? lane == 0 : t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
 }
 
