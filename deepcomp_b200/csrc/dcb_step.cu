@@ -354,7 +354,7 @@ __device__ __forceinline__ double warp_reduce_env(int lane, const double *v, int
 // ------------------------------------------------------------------------------------------------ the kernel
 // M32: all connection / in-range masks fit 32 bits (n_bs <= 32) -- halves the integer work on the mask paths
 template <int MAXT, bool M32>
-__global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(const StepArgs a) {
+__device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
     using mask_t = typename MaskType<M32>::type;
     extern __shared__ __align__(128) unsigned char smem[];
     const DevParams &p = a.p;
@@ -951,6 +951,19 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 3 : 1) dcb_step_kernel(con
     }
 }
 
+// Register budget per CTA-size class so that one CTA of that size (three of the smallest) is always resident:
+// 65536 registers / (warps rounded up to a multiple of 4 x 32), in the allocation granule of 8 registers per thread
+// (88 registers x 704 threads does not launch: warps are allocated in fours).
+#define DCB_STEP_KERNEL(MAXT, REGS)                                                                         \
+    template <bool M32> __global__ void __maxnreg__(REGS) dcb_step_kernel_##MAXT(const __grid_constant__ StepArgs a) { \
+        dcb_step_body<MAXT, M32>(a);                                                                        \
+    }
+DCB_STEP_KERNEL(256, 80)
+DCB_STEP_KERNEL(512, 128)
+DCB_STEP_KERNEL(704, 80)
+DCB_STEP_KERNEL(768, 80)
+DCB_STEP_KERNEL(1024, 64)
+
 }  // namespace
 
 size_t dcb_step_smem_bytes(int kind, int N, int M, int E) { return (size_t)dcb_smem_layout(kind, N, M, E).total; }
@@ -960,17 +973,17 @@ size_t dcb_step_smem_bytes(int kind, int N, int M, int E) { return (size_t)dcb_s
 #define DCB_DISPATCH(threads, m32, EXPR)                                                  \
     do {                                                                                  \
         if (m32) {                                                                        \
-            if ((threads) <= 256) { auto kern = dcb_step_kernel<256, true>; EXPR; }       \
-            else if ((threads) <= 512) { auto kern = dcb_step_kernel<512, true>; EXPR; }  \
-            else if ((threads) <= 704) { auto kern = dcb_step_kernel<704, true>; EXPR; }  \
-            else if ((threads) <= 768) { auto kern = dcb_step_kernel<768, true>; EXPR; }  \
-            else { auto kern = dcb_step_kernel<1024, true>; EXPR; }                       \
+            if ((threads) <= 256) { auto kern = dcb_step_kernel_256<true>; EXPR; }       \
+            else if ((threads) <= 512) { auto kern = dcb_step_kernel_512<true>; EXPR; }  \
+            else if ((threads) <= 704) { auto kern = dcb_step_kernel_704<true>; EXPR; }  \
+            else if ((threads) <= 768) { auto kern = dcb_step_kernel_768<true>; EXPR; }  \
+            else { auto kern = dcb_step_kernel_1024<true>; EXPR; }                       \
         } else {                                                                          \
-            if ((threads) <= 256) { auto kern = dcb_step_kernel<256, false>; EXPR; }      \
-            else if ((threads) <= 512) { auto kern = dcb_step_kernel<512, false>; EXPR; } \
-            else if ((threads) <= 704) { auto kern = dcb_step_kernel<704, false>; EXPR; } \
-            else if ((threads) <= 768) { auto kern = dcb_step_kernel<768, false>; EXPR; } \
-            else { auto kern = dcb_step_kernel<1024, false>; EXPR; }                      \
+            if ((threads) <= 256) { auto kern = dcb_step_kernel_256<false>; EXPR; }      \
+            else if ((threads) <= 512) { auto kern = dcb_step_kernel_512<false>; EXPR; } \
+            else if ((threads) <= 704) { auto kern = dcb_step_kernel_704<false>; EXPR; } \
+            else if ((threads) <= 768) { auto kern = dcb_step_kernel_768<false>; EXPR; } \
+            else { auto kern = dcb_step_kernel_1024<false>; EXPR; }                      \
         }                                                                                 \
     } while (0)
 
