@@ -71,6 +71,7 @@ struct dcb_env {
     DevParams p;
     int threads = 0, grid = 0;
     size_t smem = 0;
+    bool wide = false;   // one CTA per env (dcb_wide.cu) instead of the fused kernel (dcb_step.cu)
     int64_t launches = 0;
     // device allocations
     double *d_bs_xy = nullptr, *d_vel = nullptr, *d_init_xy = nullptr;
@@ -139,13 +140,15 @@ int launch_step(dcb_env *env, const int32_t *d_actions, int T, const dcb_outputs
     a.actions_out = d_actions_out;
     a.p = env->p;
     a.L = dcb_smem_layout(env->p.kind, env->p.N, env->p.M, env->p.E);
+    a.W = dcb_wide_layout(env->p.N, env->p.M, env->p.LC);
     a.actions = d_actions;
     a.T = T;
     if (out) a.out = *out;
     else memset(&a.out, 0, sizeof(a.out));
     if (a.out.dbg_link_rate)
         CU(cudaMemsetAsync(a.out.dbg_link_rate, 0, sizeof(double) * (size_t)env->p.K * env->p.N * env->p.M, s));
-    CU(dcb_launch_step(a, env->threads, env->grid, env->smem, s));
+    if (env->wide) CU(dcb_launch_wide(a, env->threads, env->grid, env->smem, s));
+    else CU(dcb_launch_step(a, env->threads, env->grid, env->smem, s));
     env->launches++;
     return DCB_OK;
 }
@@ -204,8 +207,8 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     const int K = cfg->num_envs, N = cfg->n_ue, M = cfg->n_bs;
     if (K < 1 || N < 1 || M < 1) return fail(DCB_ERR_INVALID_ARG, "num_envs, n_ue, n_bs must be >= 1");
     if (M > 64) return fail(DCB_ERR_UNSUPPORTED, "n_bs = %d > 64 (connection mask is one 64-bit word per UE)", M);
-    if (N > 512)
-        return fail(DCB_ERR_UNSUPPORTED, "n_ue = %d > 512 (two threads per UE -- physics + observer -- one CTA per env)", N);
+    if (N > 1024)
+        return fail(DCB_ERR_UNSUPPORTED, "n_ue = %d > 1024 (one thread per UE, one CTA per env)", N);
     if (cfg->kind != DCB_KIND_CENTRAL && cfg->kind != DCB_KIND_MULTI) return fail(DCB_ERR_INVALID_ARG, "bad kind");
     if (cfg->reward < DCB_REWARD_AVG || cfg->reward > DCB_REWARD_MIN)
         return fail(DCB_ERR_INVALID_ARG, "bad reward aggregation %d", cfg->reward);   // central.py:73, multi_agent.py:92
@@ -251,20 +254,52 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     env->device = cfg->device;
 
     const size_t smem_cap = prop.sharedMemPerBlockOptin;
-    if (dcb_step_smem_bytes(cfg->kind, N, M, 1) > smem_cap) {
-        delete env;
-        return fail(DCB_ERR_UNSUPPORTED, "one env of %d UEs x %d BS needs %zu B of shared memory (> %zu)", N, M,
-                    dcb_step_smem_bytes(cfg->kind, N, M, 1), smem_cap);
+    // Kernel choice: the fused, pipelined kernel (several envs per CTA, two threads per UE) when one env fits it, else
+    // the wide kernel (one CTA per env, one thread per UE).  DCB_FORCE_WIDE=1 selects the wide kernel for any shape.
+    const char *fw = getenv("DCB_FORCE_WIDE");
+    env->wide = (fw && atoi(fw) > 0) || N > 512 || dcb_step_smem_bytes(cfg->kind, N, M, 1) > smem_cap;
+    // link slots per UE of the wide kernel: every BS a UE is linked to is within range r of the UE, so those BS are
+    // within 2r of each other: max_b #{b' : |b - b'| <= 2r} bounds the links any reachable state can hold
+    // station.py:112-114 with the host libm, exactly as the reference evaluates them
+    const double ch = 0.8 + (1.1 * log10(2500.0) - 0.7) * 1.5 - 1.56 * log10(2500.0);
+    const double c1 = 69.55 + 26.16 * log10(2500.0) - 13.82 * log10(50.0) - ch;
+    const double c2 = 44.9 - 6.55 * log10(50.0);
+    const double thr_d2 = threshold_d2(c1, c2);
+    int LC = 1;
+    for (int b = 0; b < M; b++) {
+        int c = 0;
+        for (int b2 = 0; b2 < M; b2++) {
+            const double dx = cfg->host_bs_xy[2 * b] - cfg->host_bs_xy[2 * b2];
+            const double dy = cfg->host_bs_xy[2 * b + 1] - cfg->host_bs_xy[2 * b2 + 1];
+            if (dx * dx + dy * dy <= 4.0 * thr_d2 * (1.0 + 1e-9)) c++;
+        }
+        if (c > LC) LC = c;
     }
-    const int E = choose_envs_per_cta(K, N, M, cfg->kind, prop.multiProcessorCount, smem_cap);
-    if (E * N > 512 || dcb_step_smem_bytes(cfg->kind, N, M, E) > smem_cap) {
-        delete env;
-        return fail(DCB_ERR_INVALID_ARG, "DCB_ENVS_PER_CTA = %d does not fit", E);
+    int E = 1, group = 0;
+    if (env->wide) {
+        const WideLayout W = dcb_wide_layout(N, M, LC);
+        if ((size_t)W.total > smem_cap) {
+            delete env;
+            return fail(DCB_ERR_UNSUPPORTED, "one env of %d UEs x %d BS (%d link slots) needs %d B of shared memory (> %zu)",
+                        N, M, LC, W.total, smem_cap);
+        }
+        int threads = (N + 31) / 32 * 32;
+        if (threads < 128) threads = 128;
+        env->threads = threads;
+        env->grid = K;
+        env->smem = (size_t)W.total;
+        group = threads;
+    } else {
+        E = choose_envs_per_cta(K, N, M, cfg->kind, prop.multiProcessorCount, smem_cap);
+        if (E * N > 512 || dcb_step_smem_bytes(cfg->kind, N, M, E) > smem_cap) {
+            delete env;
+            return fail(DCB_ERR_INVALID_ARG, "DCB_ENVS_PER_CTA = %d does not fit", E);
+        }
+        group = (E * N + 31) / 32 * 32;      // threads per warp group (physics / observers)
+        env->threads = 2 * group;
+        env->grid = (K + E - 1) / E;
+        env->smem = dcb_step_smem_bytes(cfg->kind, N, M, E);
     }
-    const int group = (E * N + 31) / 32 * 32;      // threads per warp group (physics / observers)
-    env->threads = 2 * group;
-    env->grid = (K + E - 1) / E;
-    env->smem = dcb_step_smem_bytes(cfg->kind, N, M, E);
     // reducer lanes per (env, BS) pair: one per 32-UE bitset word, power of two, while the pairs still fit the CTA
     // (more lanes than words: the words are cut into 16- or 8-bit chunks)
     int S = 1, CS = 0;
@@ -305,13 +340,11 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     memset(&p, 0, sizeof(p));
     p.K = K; p.N = N; p.M = M; p.kind = cfg->kind; p.reward = cfg->reward;
     p.episode_length = cfg->episode_length; p.auto_reset = cfg->auto_reset; p.pause_duration = cfg->pause_duration;
-    p.D = D; p.E = E; p.S = S; p.CS = CS;
+    p.D = D; p.E = E; p.S = S; p.CS = CS; p.LC = LC;
     p.has_maxcap = has_maxcap; p.has_propfair = has_pf;
-    // station.py:112-114 with the host libm, exactly as the reference evaluates them
-    const double ch = 0.8 + (1.1 * log10(2500.0) - 0.7) * 1.5 - 1.56 * log10(2500.0);
-    p.c1 = 69.55 + 26.16 * log10(2500.0) - 13.82 * log10(50.0) - ch;
-    p.c2 = 44.9 - 6.55 * log10(50.0);
-    p.thr_d2 = threshold_d2(p.c1, p.c2);
+    p.c1 = c1;
+    p.c2 = c2;
+    p.thr_d2 = thr_d2;
     p.snr_c0 = log2(10.0) * (DCB_TX_POWER - p.c1) / 10.0 - log2(DCB_NOISE);
     p.snr_h = p.c2 / 20.0;
     // (1 + r)^(-h) = sum_k binom(-h, k) r^k
@@ -321,7 +354,7 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     p.pos = env->d_pos; p.mv = env->d_mv; p.mask = env->d_mask; p.ewma = env->d_ewma; p.time = env->d_time;
     p.init_pos = env->d_init_pos; p.table = env->d_table; p.err = env->d_err;
 
-    cudaError_t e = dcb_step_set_smem_limit(env->threads, M, env->smem);
+    cudaError_t e = env->wide ? dcb_wide_set_smem_limit(env->smem) : dcb_step_set_smem_limit(env->threads, M, env->smem);
     if (e != cudaSuccess) {
         dcb_destroy(env);
         return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", env->smem, cudaGetErrorString(e));
@@ -495,6 +528,9 @@ int dcb_check_errors(dcb_env *env, void *stream) {
     CU(cudaStreamSynchronize(s));
     if (flags) {
         CU(cudaMemsetAsync(env->d_err, 0, sizeof(int), s));
+        if (flags & DCB_ERRBIT_LINKS)
+            return fail(DCB_ERR_UNSUPPORTED, "a UE held more than %d links (an unreachable state was injected); the excess "
+                                             "links were dropped", env->p.LC);
         if (flags & DCB_ERRBIT_ACTION)
             return fail(DCB_ERR_ACTION_RANGE, "an action outside [0, %d] was passed to step (treated as no-op)", env->p.M);
         return fail(DCB_ERR_TABLE_EXHAUSTED, "a UE ran out of pre-drawn waypoints (stepped past episode_length "

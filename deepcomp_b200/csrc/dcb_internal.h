@@ -18,6 +18,7 @@
 // Sticky device-side error bits (DevParams::err)
 #define DCB_ERRBIT_ACTION 1
 #define DCB_ERRBIT_TABLE 2
+#define DCB_ERRBIT_LINKS 4    // a UE held more links than the wide kernel's slot capacity (unreachable state injected)
 
 // Packed per-UE movement state (8 bytes):  x = wx | wy << 16,  y = vel | pause << 8 | tidx << 16
 //   wx, wy : current waypoint (integers, movement.py:126-127)
@@ -34,6 +35,7 @@ struct DevParams {
     int S;               // reducer lanes per (env, BS) pair, power of two <= 32
     int CS;              // log2 of the bitset chunks per 32-UE word the reducer lanes deal out (0: whole words)
     int has_maxcap, has_propfair;
+    int LC;              // wide kernel: link slots per UE (bound on the base stations any point can be in range of)
     double thr_d2;       // largest squared distance that is still in range (snr > 2e-8, station.py:224)
     double c1, c2;       // Okumura-Hata constants (station.py:112-114)
     double snr_c0, snr_h; // snr(d) = 2^(snr_c0 - snr_h * log2(d^2)): the same model folded for the fast path
@@ -112,6 +114,40 @@ __host__ __device__ inline SmemLayout dcb_smem_layout(int kind, int N, int M, in
     return L;
 }
 
+// ---- shared-memory layout of the wide-env kernel (dcb_wide.cu: one CTA per env)
+struct WideLayout {
+    int off_tab, off_bsxy, off_share, off_vthr, off_xs, off_sx, off_sy, off_smask, off_su, off_srb, off_bits, off_fac,
+        off_arg, off_cnt, off_usum, off_umin, off_fues, off_futil, off_env;
+    int total;
+};
+
+__host__ __device__ inline WideLayout dcb_wide_layout(int N, int M, int LC) {
+    WideLayout L;
+    const int NW = (N + 31) / 32;
+    int o = 0;
+    L.off_tab = o;   o += 5 * 16 * 8;
+    L.off_bsxy = o;  o += align16(M * 16);
+    L.off_vthr = o;  o += align16(16 * 8);
+    L.off_xs = o;    o += align16(N * LC * 8);
+    L.off_sx = o;    o += align16(N * 8);
+    L.off_sy = o;    o += align16(N * 8);
+    L.off_smask = o; o += align16(N * 8);
+    L.off_su = o;    o += align16(N * 8);
+    L.off_srb = o;   o += align16(N * 8);
+    L.off_fac = o;   o += align16(M * 8);
+    L.off_usum = o;  o += align16(M * 8);
+    L.off_umin = o;  o += align16(M * 8);
+    L.off_env = o;   o += 16;
+    L.off_bits = o;  o += align16(M * NW * 4);
+    L.off_share = o; o += align16(M * 4);
+    L.off_arg = o;   o += align16(M * 4);
+    L.off_cnt = o;   o += align16(M * 4);
+    L.off_fues = o;  o += align16(M * 4);
+    L.off_futil = o; o += align16(M * 4);
+    L.total = o;
+    return L;
+}
+
 // Scripted per-UE policy evaluated on the device (reference deepcomp/agent/heuristics.py, dummy.py); kind 0 = none:
 // actions come from StepArgs::actions.
 struct PolicyParams {
@@ -127,6 +163,7 @@ struct PolicyParams {
 struct StepArgs {
     DevParams p;
     SmemLayout L;
+    WideLayout W;            // used by the wide kernel instead of L
     const int32_t *actions;  // [T][K][N], or NULL when a policy drives the envs
     int T;                   // 0 = observe only
     PolicyParams pol;
@@ -167,5 +204,7 @@ cudaError_t dcb_launch_advance_skip(int K, int N, const int32_t *env_ids, int n_
                                     uint32_t *mv_skip, const uint32_t *pos_skip, cudaStream_t s);
 cudaError_t dcb_launch_step(const StepArgs &a, int threads, int grid, size_t smem, cudaStream_t s);
 cudaError_t dcb_step_set_smem_limit(int threads, int n_bs, size_t smem);
+cudaError_t dcb_launch_wide(const StepArgs &a, int threads, int grid, size_t smem, cudaStream_t s);
+cudaError_t dcb_wide_set_smem_limit(size_t smem);
 size_t dcb_step_smem_bytes(int kind, int N, int M, int E);
 int dcb_step_regs_per_thread(int threads, int n_bs);

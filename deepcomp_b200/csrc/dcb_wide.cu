@@ -1,0 +1,464 @@
+// Wide-env step kernel: ONE CTA PER ENV, for envs too large for the fused kernel of dcb_step.cu (n_ue > 512, or an
+// observation tile + link matrix that do not fit a CTA's shared memory; BASELINE config 4: 1000 UE x 50 BS).
+//
+// Same path, same state slabs, same outputs as dcb_step.cu (MobileEnv.step, deepcomp/env/single_ue/base.py:413-466); all
+// file:line citations are relative to /root/reference/deepcomp/.  Mapping:
+//   * per-UE phases  -- thread u < N owns UE u and carries its state in registers across the T steps of a launch:
+//     action, rates before the move, reward, move, link drop, EWMA, rates after the move, utility;
+//   * per-BS phases  -- one warp per base station walks the bitset of the UEs linked to it, one 32-UE word per lane, and
+//     folds count / sum / arg-max (sharing models, station.py:152-202) or count / utility sum / min (station.py:63-83)
+//     with warp shuffles;
+//   * per-row phase  -- one warp per UE row of the observation, lanes over the base stations: squared distances, the
+//     closest BS by a shuffle min-reduction, the in-range set by ballot, normalised SNR, and the row leaves as coalesced
+//     128-byte segments straight to the observation buffer (no staging tile: one env's observation is up to 804 KB).
+// A UE's link values live in a compact per-UE slot list (slot = rank of the BS in the UE's mask) instead of the dense
+// [N][M] matrix of the fused kernel; the slot capacity LC is the largest number of base stations any point of the map
+// can be in range of (host-computed bound, dcb_api.cu).
+// Unlike the fused kernel there is no pipelining between steps and no inheritance of aggregates: every step evaluates the
+// link rates twice (before / after the move) exactly as the reference does.
+#include "dcb_device.cuh"
+
+namespace {
+
+typedef unsigned long long u64;
+
+struct WideSmem {
+    MathTables *tab;
+    double2 *bsxy;
+    int *share;
+    double *vthr;
+    double *Xs;        // [N][LC] link values / cached shared rates
+    double *sx, *sy;   // [N] positions after the move
+    u64 *smask;        // [N]
+    double *su;        // [N] utility after the move
+    double *srb;       // [N] reward before the move
+    unsigned *bits;    // [M][NW] UEs linked to each BS
+    double *fac;       // [M]
+    int *arg;          // [M]
+    int *cnt_obs;      // [M]
+    double *usum, *umin;   // [M]
+    float *f_ues, *f_util; // [M]
+    double *env_red;   // [2] per-env reward / utility sum
+};
+
+__device__ __forceinline__ int rank_of(u64 mask, int b) { return __popcll(mask & (((u64)1 << b) - 1)); }
+
+// per-BS reduction over the linked UEs: count, sum of link values, first arg-max -> sharing factor (one warp per BS)
+__device__ __forceinline__ void wide_reduce_links(const WideSmem &S, int N, int M, int NW, int LC, bool want_arg,
+                                                  int warp, int lane, int nwarps) {
+    for (int b = warp; b < M; b += nwarps) {
+        int c = 0, a0 = 0x7fffffff;
+        double s = 0.0, best = 0.0;
+        for (int w = lane; w < NW; w += 32) {
+            unsigned wa = S.bits[b * NW + w];
+            c += __popc(wa);
+            while (wa) {
+                const int j = __ffs(wa) - 1;
+                wa &= wa - 1;
+                const int i = (w << 5) + j;
+                const double v = S.Xs[(size_t)i * LC + rank_of(S.smask[i], b)];
+                s += v;
+                if (want_arg && v > best) { best = v; a0 = i; }      // station.py:184: first arg-max
+            }
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            c += __shfl_xor_sync(0xffffffffu, c, off);
+            s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (want_arg) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, a0, off);
+                if (ob > best || (ob == best && oi < a0)) { best = ob; a0 = oi; }
+            }
+        }
+        if (lane == 0) {
+            S.fac[b] = share_factor(S.share[b], c, s);
+            S.arg[b] = a0;
+        }
+    }
+}
+
+// per-BS utility aggregates for the observation / multi-agent reward (one warp per BS)
+__device__ __forceinline__ void wide_reduce_utility(const WideSmem &S, int N, int M, int NW, bool want_min, int warp,
+                                                    int lane, int nwarps) {
+    const double inv_n = 1.0 / (double)N;
+    for (int b = warp; b < M; b += nwarps) {
+        int c = 0;
+        double s = 0.0, mn = DCB_MAX_UTILITY;
+        for (int w = lane; w < NW; w += 32) {
+            unsigned wa = S.bits[b * NW + w];
+            c += __popc(wa);
+            while (wa) {
+                const int j = __ffs(wa) - 1;
+                wa &= wa - 1;
+                const double uu = S.su[(w << 5) + j];
+                s += uu;
+                if (want_min) mn = uu < mn ? uu : mn;
+            }
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            c += __shfl_xor_sync(0xffffffffu, c, off);
+            s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (want_min) {
+                const double o = __shfl_xor_sync(0xffffffffu, mn, off);
+                mn = o < mn ? o : mn;
+            }
+        }
+        if (lane == 0) {
+            S.cnt_obs[b] = c;
+            S.usum[b] = s;
+            S.umin[b] = mn;
+            S.f_ues[b] = (float)((double)c * inv_n);                                               // variants.py:296
+            S.f_util[b] = c > 0 ? (float)(s * dcb_rcp((double)c) * (1.0 / DCB_MAX_UTILITY)) : 0.0f; // station.py:71-76
+        }
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+    for (int off = 16; off > 0; off >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, v, off);
+        v = o < v ? o : v;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant__ StepArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const DevParams &p = a.p;
+    const WideLayout &L = a.W;
+    const int N = p.N, M = p.M, LC = p.LC;
+    const int NW = (N + 31) >> 5;
+    WideSmem S;
+    S.tab = reinterpret_cast<MathTables *>(smem + L.off_tab);
+    S.bsxy = reinterpret_cast<double2 *>(smem + L.off_bsxy);
+    S.share = reinterpret_cast<int *>(smem + L.off_share);
+    S.vthr = reinterpret_cast<double *>(smem + L.off_vthr);
+    S.Xs = reinterpret_cast<double *>(smem + L.off_xs);
+    S.sx = reinterpret_cast<double *>(smem + L.off_sx);
+    S.sy = reinterpret_cast<double *>(smem + L.off_sy);
+    S.smask = reinterpret_cast<u64 *>(smem + L.off_smask);
+    S.su = reinterpret_cast<double *>(smem + L.off_su);
+    S.srb = reinterpret_cast<double *>(smem + L.off_srb);
+    S.bits = reinterpret_cast<unsigned *>(smem + L.off_bits);
+    S.fac = reinterpret_cast<double *>(smem + L.off_fac);
+    S.arg = reinterpret_cast<int *>(smem + L.off_arg);
+    S.cnt_obs = reinterpret_cast<int *>(smem + L.off_cnt);
+    S.usum = reinterpret_cast<double *>(smem + L.off_usum);
+    S.umin = reinterpret_cast<double *>(smem + L.off_umin);
+    S.f_ues = reinterpret_cast<float *>(smem + L.off_fues);
+    S.f_util = reinterpret_cast<float *>(smem + L.off_futil);
+    S.env_red = reinterpret_cast<double *>(smem + L.off_env);
+    const MathTables *tab = S.tab;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int k = blockIdx.x;
+    const bool valid = tid < N;
+    const int i = valid ? tid : 0;
+    const long long u = (long long)k * N + i;
+    const bool central = p.kind == DCB_KIND_CENTRAL;
+    const int OW = obs_width(p.kind, M);
+    const size_t per_env = central ? (size_t)(2 * N * M + N) : (size_t)N * OW;
+    const int T = a.T;
+    const int n_iter = T > 0 ? T : 1;
+    const float hr = (float)(p.snr_h - 1.5);
+
+    dcb_math_init(S.tab, tid, p.snr_h, p.snr_c0);
+    for (int b = tid; b < M; b += blockDim.x) {
+        S.bsxy[b] = make_double2(p.bs_xy[2 * b], p.bs_xy[2 * b + 1]);
+        S.share[b] = p.sharing[b];
+    }
+    for (int j = tid; j < M * NW; j += blockDim.x) S.bits[j] = 0u;
+    if (tid >= 32 && tid < 48) S.vthr[tid - 32] = snap_threshold((double)(tid - 32));
+
+    // ---- per-UE state -> registers
+    double x = 0, y = 0, ewma = 0;
+    u64 mask = 0;
+    unsigned wxy = 0, vpt = 0;
+    int tk = p.time[k];
+    if (valid) {
+        const double2 ps = p.pos[u];
+        x = ps.x; y = ps.y;
+        const uint2 mv = p.mv[u];
+        wxy = mv.x; vpt = mv.y;
+        mask = p.mask[u];
+        ewma = p.ewma[u];
+    }
+    const double vfix = valid ? p.vel_spec[i] : 0.0;
+    const double vfix_thr = vfix >= 0.0 ? snap_threshold(vfix) : 0.0;
+    double *Xrow = S.Xs + (size_t)i * LC;
+    __syncthreads();
+
+    for (int step = 0; step < n_iter; step++) {
+        const bool last = step == n_iter - 1;
+        double rb = 0.0, dr = 0.0, util = DCB_MIN_UTILITY;
+        int lost = 0;
+        if (T > 0) {
+            // ---- MobileEnv.reset before the step of an env that reached its episode length (base.py:169-189)
+            if (p.auto_reset && tk >= p.episode_length) {
+                if (valid) {
+                    ue_reset(p, u, x, y, wxy, vpt);
+                    mask = 0; ewma = 0.0;
+                }
+                tk = 0;
+            }
+            if (valid) {
+                // ---- apply_ue_actions (base.py:247-282) -> User.connect_to_bs(disconnect=True) (user.py:190-229)
+                int act;
+                if (a.pol.kind) {
+                    act = policy_action<u64>(a.pol, mask, x, y, S.bsxy, M, i, a.pol.call0 + step, u);
+                    if (a.actions_out) a.actions_out[(size_t)step * p.K * N + u] = act;
+                } else {
+                    act = a.actions[(size_t)step * p.K * N + u];
+                }
+                if (act < 0 || act > M) {
+                    atomicOr(p.err, DCB_ERRBIT_ACTION);
+                } else if (act > 0) {
+                    const int b = act - 1;
+                    const u64 bit = (u64)1 << b;
+                    if (mask & bit) mask &= ~bit;
+                    else if (dist2(S.bsxy[b], x, y) <= p.thr_d2) mask |= bit;   // can_connect, station.py:222-226
+                }
+                if (__popcll(mask) > LC) {          // cannot happen on a reachable state (LC bounds the BS in range)
+                    atomicOr(p.err, DCB_ERRBIT_LINKS);
+                    while (__popcll(mask) > LC) mask &= mask - 1;
+                }
+                // ---- link values at the pre-move position (station.py:129-150)
+                const double iee = dcb_rcp(ewma + DCB_EPSILON);
+                int slot = 0;
+                for (u64 m = mask; m; m &= m - 1, slot++) {
+                    const int b = __ffsll((long long)m) - 1;
+                    Xrow[slot] = link_value(S.share[b], rate_of_d2(p, tab, dist2(S.bsxy[b], x, y)), iee);
+                    atomicOr(&S.bits[b * NW + (i >> 5)], 1u << (i & 31));
+                }
+                S.smask[i] = mask;
+            }
+            __syncthreads();
+            wide_reduce_links(S, N, M, NW, LC, p.has_maxcap, warp, lane, nwarps);
+            __syncthreads();
+            for (int j = tid; j < M * NW; j += blockDim.x) S.bits[j] = 0u;
+            if (valid) {
+                // ---- update_ue_drs_rewards (base.py:315-335): shared rate of every connected link -> ue.bs_dr cache
+                // (back into the slots), calc_reward (base.py:158-167; penalties are identically 0, base.py:257)
+                const double ee = ewma + DCB_EPSILON;
+                double dr0 = 0.0;
+                int slot = 0;
+                for (u64 m = mask; m; m &= m - 1, slot++) {
+                    const int b = __ffsll((long long)m) - 1;
+                    const double r = shared_rate(S.share[b], Xrow[slot], S.fac[b], S.arg[b], i, ee);
+                    Xrow[slot] = r;
+                    dr0 += r;                                                          // user.py:64-69
+                }
+                rb = log_utility(tab, dr0) * (1.0 / DCB_MAX_UTILITY);
+                // ---- User.move (user.py:159-173), check_bs_connection (user.py:175-188), update_ewma_dr (user.py:148-157)
+                ue_move(p, u, vfix, vfix_thr, S.vthr, x, y, wxy, vpt);
+                double keep = 0.0;
+                slot = 0;
+                for (u64 m = mask; m; m &= m - 1, slot++) {
+                    const int b = __ffsll((long long)m) - 1;
+                    if (dist2(S.bsxy[b], x, y) <= p.thr_d2) keep += Xrow[slot];
+                    else { mask &= ~((u64)1 << b); lost++; }
+                }
+                ewma = 0.9 * keep + (1 - 0.9) * ewma;
+            }
+            tk += 1;                                                                   // base.py:454
+            __syncthreads();      // bits cleared, slots of the pre-move pass consumed
+        }
+        // ---- link values at the new position for update_ue_drs_rewards(update_only=True) (base.py:451)
+        if (valid) {
+            const double iee = dcb_rcp(ewma + DCB_EPSILON);
+            int slot = 0;
+            for (u64 m = mask; m; m &= m - 1, slot++) {
+                const int b = __ffsll((long long)m) - 1;
+                if (slot < LC) {
+                    Xrow[slot] = link_value(S.share[b], rate_of_d2(p, tab, dist2(S.bsxy[b], x, y)), iee);
+                    atomicOr(&S.bits[b * NW + (i >> 5)], 1u << (i & 31));
+                } else {
+                    atomicOr(p.err, DCB_ERRBIT_LINKS);     // observe-only launch on an injected state with too many links
+                    mask &= ~((u64)1 << b);
+                }
+            }
+            S.smask[i] = mask;
+            S.sx[i] = x; S.sy[i] = y;
+        }
+        __syncthreads();
+        wide_reduce_links(S, N, M, NW, LC, p.has_maxcap, warp, lane, nwarps);
+        __syncthreads();
+        if (valid) {
+            // ---- post-move rates -> utility (user.py:76-92)
+            const double ee = ewma + DCB_EPSILON;
+            int slot = 0;
+            for (u64 m = mask; m; m &= m - 1, slot++) {
+                const int b = __ffsll((long long)m) - 1;
+                const double r = shared_rate(S.share[b], Xrow[slot], S.fac[b], S.arg[b], i, ee);
+                if (last && a.out.dbg_link_rate) a.out.dbg_link_rate[u * M + b] = r;
+                dr += r;
+            }
+            util = log_utility(tab, dr);
+            S.su[i] = util;
+            S.srb[i] = rb;
+            // ---- per-UE info outputs (base.py:383-411)
+            if (a.out.curr_dr) a.out.curr_dr[(size_t)step * a.out.curr_dr_stride + u] = (float)dr;
+            if (a.out.utility) a.out.utility[(size_t)step * a.out.utility_stride + u] = (float)util;
+            if (last && a.out.dbg_curr_dr) a.out.dbg_curr_dr[u] = dr;
+            if (last && a.out.dbg_utility) a.out.dbg_utility[u] = util;
+            if (T > 0 && a.out.lost_conn) a.out.lost_conn[(size_t)step * a.out.lost_conn_stride + u] = (uint8_t)lost;
+        }
+        __syncthreads();
+        if (!central) wide_reduce_utility(S, N, M, NW, p.reward == DCB_REWARD_MIN, warp, lane, nwarps);
+        if (warp == nwarps - 1) {
+            // per-env sums: utility (base.py:402) and the central reward over the PRE-move rewards (central.py:65-73)
+            double s_u = 0.0, s_r = p.reward == DCB_REWARD_MIN ? CUDART_INF : 0.0;
+            for (int j = lane; j < N; j += 32) {
+                s_u += S.su[j];
+                const double r = S.srb[j];
+                s_r = p.reward == DCB_REWARD_MIN ? (r < s_r ? r : s_r) : s_r + r;
+            }
+            s_u = warp_sum(s_u);
+            s_r = p.reward == DCB_REWARD_MIN ? warp_min(s_r) : warp_sum(s_r);
+            if (lane == 0) { S.env_red[0] = s_u; S.env_red[1] = s_r; }
+        }
+        __syncthreads();
+        // ---- clear the bitsets for the next step (all reducers are past them)
+        for (int j = tid; j < M * NW; j += blockDim.x) S.bits[j] = 0u;
+        if (tid == 0) {
+            if (a.out.sum_utility) a.out.sum_utility[(size_t)step * a.out.sum_utility_stride + k] = (float)S.env_red[0];
+            if (last && a.out.dbg_sum_utility) a.out.dbg_sum_utility[k] = S.env_red[0];
+            if (central && T > 0) {
+                double r = S.env_red[1];
+                if (p.reward == DCB_REWARD_AVG) r = r / (double)N;
+                if (a.out.reward) a.out.reward[(size_t)step * a.out.reward_stride + k] = (float)r;
+                if (last && a.out.dbg_reward) a.out.dbg_reward[k] = r;
+            }
+        }
+        // ---- observation rows and per-UE rewards: one warp per row, lanes over the base stations (two passes cover
+        // M <= 64).  variants.py:271-303, central.py:31-57, multi_agent.py:32-95
+        float *obs_env = a.out.obs ? a.out.obs + (size_t)step * a.out.obs_stride + (size_t)k * per_env : nullptr;
+        const bool want_dbg = last && (a.out.dbg_obs || a.out.dbg_snr);
+        for (int r = warp; r < N; r += nwarps) {
+            const double rx = S.sx[r], ry = S.sy[r], rutil = S.su[r];
+            const u64 rmask = S.smask[r];
+            const int b0 = lane, b1 = lane + 32;
+            const bool ok0 = b0 < M, ok1 = b1 < M;
+            const double d20 = ok0 ? dist2(S.bsxy[b0], rx, ry) : CUDART_INF;
+            const double d21 = ok1 ? dist2(S.bsxy[b1], rx, ry) : CUDART_INF;
+            const float f0 = (float)d20, f1 = (float)d21;
+            float d2minf = fminf(f0, f1);
+            for (int off = 16; off > 0; off >>= 1) d2minf = fminf(d2minf, __shfl_xor_sync(0xffffffffu, d2minf, off));
+            // in-range set (multi_agent.py:60 / station.py:222-226): exact fp64 decision, gathered by ballot
+            const unsigned in0 = __ballot_sync(0xffffffffu, ok0 && d20 <= p.thr_d2);
+            const unsigned in1 = __ballot_sync(0xffffffffu, ok1 && d21 <= p.thr_d2);
+            float dr0, dr1;
+            if (d2minf >= 1e-6f) {       // 'dr' = snr_b / max_b snr_b (variants.py:276-284) = (d2min / d2_b)^h in fp32
+                dr0 = norm_snr_f32(f0, d2minf, hr);
+                dr1 = norm_snr_f32(f1, d2minf, hr);
+            } else {                     // a UE sitting on a BS: d + EPSILON matters
+                double d2min = d20 < d21 ? d20 : d21;
+                d2min = warp_min(d2min);
+                const double inv_max = dcb_rcp(snr_of_d2(p, tab, d2min));
+                dr0 = ok0 ? (float)(snr_of_d2(p, tab, d20) * inv_max) : 0.0f;
+                dr1 = ok1 ? (float)(snr_of_d2(p, tab, d21) * inv_max) : 0.0f;
+            }
+            const float c0 = (float)((unsigned)(rmask >> b0) & 1u), c1 = ok1 ? (float)((unsigned)(rmask >> b1) & 1u) : 0.0f;
+            const double un = rutil * (1.0 / DCB_MAX_UTILITY);                              // variants.py:287
+            const long long ru = (long long)k * N + r;
+            if (obs_env) {
+                if (central) {
+                    float *oc = obs_env + (size_t)r * M, *od = obs_env + (size_t)N * M + (size_t)r * M;
+                    if (ok0) { oc[b0] = c0; od[b0] = dr0; }
+                    if (ok1) { oc[b1] = c1; od[b1] = dr1; }
+                    if (lane == 0) obs_env[(size_t)2 * N * M + r] = (float)un;
+                } else {
+                    float *orow = obs_env + (size_t)r * OW;
+                    if (ok0) { orow[b0] = c0; orow[M + b0] = dr0; orow[2 * M + b0] = S.f_ues[b0]; orow[3 * M + b0] = S.f_util[b0]; }
+                    if (ok1) { orow[b1] = c1; orow[M + b1] = dr1; orow[2 * M + b1] = S.f_ues[b1]; orow[3 * M + b1] = S.f_util[b1]; }
+                    if (lane == 0) orow[4 * M] = (float)un;
+                }
+            }
+            if (want_dbg) {
+                // test taps: fp64 copy of the observation (the 'dr' entries are the fp32 values) and the fp64 SNR
+                if (a.out.dbg_obs) {
+                    if (central) {
+                        double *drow = a.out.dbg_obs + (size_t)k * (2 * N * M + N);
+                        if (ok0) { drow[r * M + b0] = (double)c0; drow[N * M + r * M + b0] = (double)dr0; }
+                        if (ok1) { drow[r * M + b1] = (double)c1; drow[N * M + r * M + b1] = (double)dr1; }
+                        if (lane == 0) drow[2 * N * M + r] = un;
+                    } else {
+                        double *drow = a.out.dbg_obs + (size_t)ru * OW;
+#pragma unroll
+                        for (int q = 0; q < 2; q++) {
+                            const int b = q ? b1 : b0;
+                            if (b < M) {
+                                const int c = S.cnt_obs[b];
+                                drow[b] = (double)(q ? c1 : c0);
+                                drow[M + b] = (double)(q ? dr1 : dr0);
+                                drow[2 * M + b] = (double)c / (double)N;
+                                drow[3 * M + b] = (c > 0 ? S.usum[b] / (double)c : 0.0) / DCB_MAX_UTILITY;
+                            }
+                        }
+                        if (lane == 0) drow[4 * M] = un;
+                    }
+                }
+                if (a.out.dbg_snr) {
+                    if (ok0) a.out.dbg_snr[ru * M + b0] = snr_of_d2(p, tab, d20);
+                    if (ok1) a.out.dbg_snr[ru * M + b1] = snr_of_d2(p, tab, d21);
+                }
+            }
+            if (!central && T > 0) {
+                // ---- multi_agent.py:39-95 on the POST-move state
+                double agg = rutil;
+                if (in0 | in1) {
+                    if (p.reward == DCB_REWARD_AVG) {
+                        const bool i0 = (in0 >> lane) & 1u, i1 = (in1 >> lane) & 1u;
+                        int nn = (i0 ? S.cnt_obs[b0] : 0) + (i1 ? S.cnt_obs[b1] : 0);
+                        double tot = (i0 ? S.usum[b0] : 0.0) + (i1 ? S.usum[b1] : 0.0);
+                        for (int off = 16; off > 0; off >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, off);
+                        tot = warp_sum(tot);
+                        if (nn > 0) agg = (rmask == 0 ? tot + rutil : tot) * dcb_rcp((double)(rmask == 0 ? nn + 1 : nn));
+                    } else if (p.reward == DCB_REWARD_SUM) {
+                        // user.py:238-244: UEs sharing any BS with this UE; their PRE-move rewards
+                        double s = 0.0;
+                        for (int j = lane; j < N; j += 32)
+                            if (S.smask[j] & rmask) s += S.srb[j];
+                        agg = warp_sum(s);
+                    } else {
+                        const bool i0 = (in0 >> lane) & 1u, i1 = (in1 >> lane) & 1u;
+                        double mn = i0 ? S.umin[b0] : CUDART_INF;
+                        if (i1) mn = S.umin[b1] < mn ? S.umin[b1] : mn;
+                        mn = warp_min(mn);
+                        agg = mn < agg ? mn : agg;
+                    }
+                }
+                if (lane == 0) {
+                    if (a.out.reward) a.out.reward[(size_t)step * a.out.reward_stride + ru] = (float)agg;
+                    if (last && a.out.dbg_reward) a.out.dbg_reward[ru] = agg;
+                }
+            }
+        }
+        __syncthreads();      // rows done: sx / su / smask / aggregates may be overwritten by the next step
+    }
+
+    // ---- registers -> state slabs
+    if (T > 0) {
+        if (valid) {
+            p.pos[u] = make_double2(x, y);
+            p.mv[u] = make_uint2(wxy, vpt);
+            p.mask[u] = mask;
+            p.ewma[u] = ewma;
+        }
+        if (tid == 0) p.time[k] = tk;
+    }
+}
+
+}  // namespace
+
+cudaError_t dcb_wide_set_smem_limit(size_t smem) {
+    return cudaFuncSetAttribute(dcb_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+cudaError_t dcb_launch_wide(const StepArgs &a, int threads, int grid, size_t smem, cudaStream_t s) {
+    dcb_wide_kernel<<<grid, threads, smem, s>>>(a);
+    return cudaGetLastError();
+}

@@ -64,9 +64,13 @@ def compare_step(env, dbg, want, k, what, step=True):
         assert_close(dbg['dbg_sum_utility'][k].cpu().numpy(), want['sum_utility'], f'{what}.sum_utility', RTOL, ATOL)
 
 
+@pytest.mark.parametrize('wide', [False, True], ids=['fused', 'wide'])
 @pytest.mark.parametrize('name', golden_names())
-def test_cuda_step_matches_reference_golden(name):
-    """K=1, one launch per step, every recorded array of the reference trace."""
+def test_cuda_step_matches_reference_golden(name, wide, monkeypatch):
+    """K=1, one launch per step, every recorded array of the reference trace; through the fused kernel (dcb_step.cu)
+    and through the one-CTA-per-env kernel for large envs (dcb_wide.cu, forced here for the small golden shapes)."""
+    if wide:
+        monkeypatch.setenv('DCB_FORCE_WIDE', '1')
     cfg, z = load_golden(name)
     env = make_env(oracle_kwargs(cfg))
     t = 0
@@ -106,6 +110,56 @@ def test_cuda_batch_matches_c_oracle(kind, n_ue, n_bs, K):
         for k, o in enumerate(orcs):
             compare_step(env, dbg, o.step(a[k]), k, f'step[{t}].env{k}')
     env.check_errors()
+
+
+@pytest.mark.parametrize('kind', ['central', 'multi'])
+@pytest.mark.parametrize('n_ue,n_bs,K,steps,force', [(1000, 50, 2, 12, False), (600, 33, 2, 12, False),
+                                                     (50, 10, 9, 40, True), (5, 3, 7, 40, True), (33, 64, 3, 40, True),
+                                                     (1, 1, 3, 20, True)])
+def test_wide_kernel_matches_c_oracle(kind, n_ue, n_bs, K, steps, force, monkeypatch):
+    """BASELINE config 4 shape (1000 UE x 50 BS) and other shapes through dcb_wide.cu, every step against the C oracle."""
+    from deepcomp_b200 import env_seeds
+    if force:
+        monkeypatch.setenv('DCB_FORCE_WIDE', '1')
+    W, H, bs = c_oracle_grid(n_bs)
+    seeds = env_seeds(1000, K, n_ue)
+    kw = dict(kind=kind, n_ue=n_ue, bs_xy=bs, map_wh=(W, H), sharing='mixed', velocities='slow', reward='avg',
+              episode_length=steps)
+    env = make_env(dict(kw, seed=0), num_envs=K, seeds=seeds)
+    assert env.launch_geometry['grid'] == K              # one CTA per env
+    orcs = [c_oracle.COracleEnv(seed=int(s), **kw) for s in seeds]
+    dbg = env.reset(debug=True)
+    for k, o in enumerate(orcs):
+        compare_step(env, dbg, o.reset_trace(), k, f'reset.env{k}', step=False)
+    rng = np.random.default_rng(11)
+    for t in range(steps):
+        a = rng.integers(0, n_bs + 1, (K, n_ue)).astype(np.int32)
+        dbg = env.step(torch.as_tensor(a, device='cuda'), debug=True)
+        for k, o in enumerate(orcs):
+            compare_step(env, dbg, o.step(a[k]), k, f'step[{t}].env{k}')
+    env.check_errors()
+
+
+def test_wide_fragment_equals_single_steps():
+    """T fused steps in one launch of the wide kernel == T single-step launches (state carried in registers vs slabs),
+    with an on-device episode reset in the middle."""
+    from deepcomp_b200 import BatchedMobileEnv, env_seeds
+    n_ue, n_bs, K, T = 520, 12, 3, 30
+    W, H, bs = c_oracle_grid(n_bs)
+    kw = dict(num_envs=K, n_ue=n_ue, bs_xy=bs, map_wh=(W, H), kind='multi', seeds=env_seeds(7, K, n_ue),
+              episode_length=20, auto_reset=True)
+    a = torch.randint(0, n_bs + 1, (T, K, n_ue), dtype=torch.int32, device='cuda',
+                      generator=torch.Generator('cuda').manual_seed(3))
+    e1, e2 = BatchedMobileEnv(**kw), BatchedMobileEnv(**kw)
+    e1.reset(); e2.reset()
+    f = e1.step_many(a)
+    for t in range(T):
+        obs, rew, _, info = e2.step(a[t])
+        assert torch.equal(obs, f['obs'][t]) and torch.equal(rew, f['reward'][t])
+        assert torch.equal(info['lost_conn'], f['lost_conn'][t])
+    s1, s2 = e1.get_state(), e2.get_state()
+    for key in ('pos', 'mask', 'ewma', 'movement', 'time'):
+        assert np.array_equal(s1[key], s2[key]), key
 
 
 def c_oracle_grid(n_bs):
