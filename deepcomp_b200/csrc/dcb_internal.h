@@ -116,7 +116,8 @@ __host__ __device__ inline SmemLayout dcb_smem_layout(int kind, int N, int M, in
 
 // ---- shared-memory layout of the wide-env kernel (dcb_wide.cu: one CTA per env)
 struct WideLayout {
-    int off_tab, off_bsxy, off_share, off_vthr, off_xs, off_sx, off_sy, off_smask, off_su, off_srb, off_bits, off_fac,
+    int off_tab, off_bsxy, off_share, off_vthr, off_xs, off_sx, off_sy, off_smask, off_su, off_srb, off_sew, off_smv,
+        off_bits, off_fac,
         off_arg, off_cnt, off_usum, off_umin, off_fues, off_futil, off_env;
     int total;
 };
@@ -134,6 +135,8 @@ __host__ __device__ inline WideLayout dcb_wide_layout(int N, int M, int LC) {
     L.off_smask = o; o += align16(N * 8);
     L.off_su = o;    o += align16(N * 8);
     L.off_srb = o;   o += align16(N * 8);
+    L.off_sew = o;   o += align16(N * 8);
+    L.off_smv = o;   o += align16(N * 8);
     L.off_fac = o;   o += align16(M * 8);
     L.off_usum = o;  o += align16(M * 8);
     L.off_umin = o;  o += align16(M * 8);

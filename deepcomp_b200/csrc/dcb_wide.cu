@@ -32,6 +32,8 @@ struct WideSmem {
     u64 *smask;        // [N]
     double *su;        // [N] utility after the move
     double *srb;       // [N] reward before the move
+    double *sew;       // [N] EWMA rate
+    uint2 *smv;        // [N] packed movement state
     unsigned *bits;    // [M][NW] UEs linked to each BS
     double *fac;       // [M]
     int *arg;          // [M]
@@ -142,6 +144,8 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
     S.smask = reinterpret_cast<u64 *>(smem + L.off_smask);
     S.su = reinterpret_cast<double *>(smem + L.off_su);
     S.srb = reinterpret_cast<double *>(smem + L.off_srb);
+    S.sew = reinterpret_cast<double *>(smem + L.off_sew);
+    S.smv = reinterpret_cast<uint2 *>(smem + L.off_smv);
     S.bits = reinterpret_cast<unsigned *>(smem + L.off_bits);
     S.fac = reinterpret_cast<double *>(smem + L.off_fac);
     S.arg = reinterpret_cast<int *>(smem + L.off_arg);
@@ -173,18 +177,15 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
     for (int j = tid; j < M * NW; j += blockDim.x) S.bits[j] = 0u;
     if (tid >= 32 && tid < 48) S.vthr[tid - 32] = snap_threshold((double)(tid - 32));
 
-    // ---- per-UE state -> registers
-    double x = 0, y = 0, ewma = 0;
-    u64 mask = 0;
-    unsigned wxy = 0, vpt = 0;
+    // ---- per-UE state: global slabs -> shared memory for the launch.  A UE's thread pulls it into registers for the
+    // per-UE phases of a step only, so the row-parallel phase (most of the instructions) has the registers to itself
     int tk = p.time[k];
     if (valid) {
         const double2 ps = p.pos[u];
-        x = ps.x; y = ps.y;
-        const uint2 mv = p.mv[u];
-        wxy = mv.x; vpt = mv.y;
-        mask = p.mask[u];
-        ewma = p.ewma[u];
+        S.sx[i] = ps.x; S.sy[i] = ps.y;
+        S.smv[i] = p.mv[u];
+        S.smask[i] = p.mask[u];
+        S.sew[i] = p.ewma[u];
     }
     const double vfix = valid ? p.vel_spec[i] : 0.0;
     const double vfix_thr = vfix >= 0.0 ? snap_threshold(vfix) : 0.0;
@@ -195,6 +196,14 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
         const bool last = step == n_iter - 1;
         double rb = 0.0, dr = 0.0, util = DCB_MIN_UTILITY;
         int lost = 0;
+        double x = 0, y = 0, ewma = 0;
+        u64 mask = 0;
+        unsigned wxy = 0, vpt = 0;
+        if (valid) {
+            x = S.sx[i]; y = S.sy[i]; ewma = S.sew[i]; mask = S.smask[i];
+            const uint2 mv = S.smv[i];
+            wxy = mv.x; vpt = mv.y;
+        }
         if (T > 0) {
             // ---- MobileEnv.reset before the step of an env that reached its episode length (base.py:169-189)
             if (p.auto_reset && tk >= p.episode_length) {
@@ -282,6 +291,8 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
             }
             S.smask[i] = mask;
             S.sx[i] = x; S.sy[i] = y;
+            S.sew[i] = ewma;
+            S.smv[i] = make_uint2(wxy, vpt);
         }
         __syncthreads();
         wide_reduce_links(S, N, M, NW, LC, p.has_maxcap, warp, lane, nwarps);
@@ -337,13 +348,22 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
         // M <= 64).  variants.py:271-303, central.py:31-57, multi_agent.py:32-95
         float *obs_env = a.out.obs ? a.out.obs + (size_t)step * a.out.obs_stride + (size_t)k * per_env : nullptr;
         const bool want_dbg = last && (a.out.dbg_obs || a.out.dbg_snr);
+        // this lane's two base stations: everything that does not depend on the row stays in registers
+        const int b0 = lane, b1 = lane + 32;
+        const bool ok0 = b0 < M, ok1 = b1 < M;
+        const double2 bs0 = ok0 ? S.bsxy[b0] : make_double2(0.0, 0.0), bs1 = ok1 ? S.bsxy[b1] : make_double2(0.0, 0.0);
+        float fu0 = 0.0f, fu1 = 0.0f, fa0 = 0.0f, fa1 = 0.0f;
+        int cn0 = 0, cn1 = 0;
+        double us0 = 0.0, us1 = 0.0, um0 = CUDART_INF, um1 = CUDART_INF;
+        if (!central) {
+            if (ok0) { fu0 = S.f_ues[b0]; fa0 = S.f_util[b0]; cn0 = S.cnt_obs[b0]; us0 = S.usum[b0]; um0 = S.umin[b0]; }
+            if (ok1) { fu1 = S.f_ues[b1]; fa1 = S.f_util[b1]; cn1 = S.cnt_obs[b1]; us1 = S.usum[b1]; um1 = S.umin[b1]; }
+        }
         for (int r = warp; r < N; r += nwarps) {
             const double rx = S.sx[r], ry = S.sy[r], rutil = S.su[r];
             const u64 rmask = S.smask[r];
-            const int b0 = lane, b1 = lane + 32;
-            const bool ok0 = b0 < M, ok1 = b1 < M;
-            const double d20 = ok0 ? dist2(S.bsxy[b0], rx, ry) : CUDART_INF;
-            const double d21 = ok1 ? dist2(S.bsxy[b1], rx, ry) : CUDART_INF;
+            const double d20 = ok0 ? dist2(bs0, rx, ry) : CUDART_INF;
+            const double d21 = ok1 ? dist2(bs1, rx, ry) : CUDART_INF;
             const float f0 = (float)d20, f1 = (float)d21;
             float d2minf = fminf(f0, f1);
             for (int off = 16; off > 0; off >>= 1) d2minf = fminf(d2minf, __shfl_xor_sync(0xffffffffu, d2minf, off));
@@ -372,8 +392,8 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                     if (lane == 0) obs_env[(size_t)2 * N * M + r] = (float)un;
                 } else {
                     float *orow = obs_env + (size_t)r * OW;
-                    if (ok0) { orow[b0] = c0; orow[M + b0] = dr0; orow[2 * M + b0] = S.f_ues[b0]; orow[3 * M + b0] = S.f_util[b0]; }
-                    if (ok1) { orow[b1] = c1; orow[M + b1] = dr1; orow[2 * M + b1] = S.f_ues[b1]; orow[3 * M + b1] = S.f_util[b1]; }
+                    if (ok0) { orow[b0] = c0; orow[M + b0] = dr0; orow[2 * M + b0] = fu0; orow[3 * M + b0] = fa0; }
+                    if (ok1) { orow[b1] = c1; orow[M + b1] = dr1; orow[2 * M + b1] = fu1; orow[3 * M + b1] = fa1; }
                     if (lane == 0) orow[4 * M] = (float)un;
                 }
             }
@@ -412,8 +432,8 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                 if (in0 | in1) {
                     if (p.reward == DCB_REWARD_AVG) {
                         const bool i0 = (in0 >> lane) & 1u, i1 = (in1 >> lane) & 1u;
-                        int nn = (i0 ? S.cnt_obs[b0] : 0) + (i1 ? S.cnt_obs[b1] : 0);
-                        double tot = (i0 ? S.usum[b0] : 0.0) + (i1 ? S.usum[b1] : 0.0);
+                        int nn = (i0 ? cn0 : 0) + (i1 ? cn1 : 0);
+                        double tot = (i0 ? us0 : 0.0) + (i1 ? us1 : 0.0);
                         for (int off = 16; off > 0; off >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, off);
                         tot = warp_sum(tot);
                         if (nn > 0) agg = (rmask == 0 ? tot + rutil : tot) * dcb_rcp((double)(rmask == 0 ? nn + 1 : nn));
@@ -425,8 +445,8 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                         agg = warp_sum(s);
                     } else {
                         const bool i0 = (in0 >> lane) & 1u, i1 = (in1 >> lane) & 1u;
-                        double mn = i0 ? S.umin[b0] : CUDART_INF;
-                        if (i1) mn = S.umin[b1] < mn ? S.umin[b1] : mn;
+                        double mn = i0 ? um0 : CUDART_INF;
+                        if (i1) mn = um1 < mn ? um1 : mn;
                         mn = warp_min(mn);
                         agg = mn < agg ? mn : agg;
                     }
@@ -440,13 +460,13 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
         __syncthreads();      // rows done: sx / su / smask / aggregates may be overwritten by the next step
     }
 
-    // ---- registers -> state slabs
+    // ---- shared memory -> state slabs
     if (T > 0) {
         if (valid) {
-            p.pos[u] = make_double2(x, y);
-            p.mv[u] = make_uint2(wxy, vpt);
-            p.mask[u] = mask;
-            p.ewma[u] = ewma;
+            p.pos[u] = make_double2(S.sx[i], S.sy[i]);
+            p.mv[u] = S.smv[i];
+            p.mask[u] = S.smask[i];
+            p.ewma[u] = S.sew[i];
         }
         if (tid == 0) p.time[k] = tk;
     }

@@ -1,0 +1,6 @@
+# full ncu capture of one wide-kernel launch at BASELINE config 4.  usage: bash scripts/gpu_prof_wide.sh <tag>
+TAG=${1:-x}
+cd $GRAFT_REPO_ROOT
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:dcb_wide_kernel -s 4 -c 1 -o gpurun_out/prof_wide_$TAG -f \
+    python bench.py --n-ue 1000 --n-bs 50 --envs 1024 --fragment 4 --steps 12 --warmup 4 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_wide_$TAG.log 2>&1
+ls -la gpurun_out/prof_wide_$TAG.ncu-rep
