@@ -359,6 +359,12 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
             if (ok0) { fu0 = S.f_ues[b0]; fa0 = S.f_util[b0]; cn0 = S.cnt_obs[b0]; us0 = S.usum[b0]; um0 = S.umin[b0]; }
             if (ok1) { fu1 = S.f_ues[b1]; fa1 = S.f_util[b1]; cn1 = S.cnt_obs[b1]; us1 = S.usum[b1]; um1 = S.umin[b1]; }
         }
+        // this lane's output cursor: column b0 of the env's first row; the four (multi) / two (central) segments of a
+        // row are fixed byte offsets from it, the second pass (b1 = b0 + 32) is +128 bytes on the same addresses
+        float *obs_lane = obs_env ? obs_env + b0 : nullptr;
+        const int seg1 = central ? N * M : M, seg2 = 2 * M, seg3 = 3 * M;      // in floats
+        const int row_stride_f = central ? M : OW;
+        const long long kN = (long long)k * N;
         for (int r = warp; r < N; r += nwarps) {
             const double rx = S.sx[r], ry = S.sy[r], rutil = S.su[r];
             const u64 rmask = S.smask[r];
@@ -381,20 +387,21 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                 dr0 = ok0 ? (float)(snr_of_d2(p, tab, d20) * inv_max) : 0.0f;
                 dr1 = ok1 ? (float)(snr_of_d2(p, tab, d21) * inv_max) : 0.0f;
             }
-            const float c0 = (float)((unsigned)(rmask >> b0) & 1u), c1 = ok1 ? (float)((unsigned)(rmask >> b1) & 1u) : 0.0f;
+            // 'connected' (variants.py:272): bit b0 of the low word / bit b0 of the high word (b1 = b0 + 32)
+            const float c0 = (((unsigned)rmask >> lane) & 1u) ? 1.0f : 0.0f;
+            const float c1 = (((unsigned)(rmask >> 32) >> lane) & 1u) ? 1.0f : 0.0f;
             const double un = rutil * (1.0 / DCB_MAX_UTILITY);                              // variants.py:287
-            const long long ru = (long long)k * N + r;
-            if (obs_env) {
+            const long long ru = kN + r;
+            if (obs_lane) {
+                float *o = obs_lane + r * row_stride_f;
                 if (central) {
-                    float *oc = obs_env + (size_t)r * M, *od = obs_env + (size_t)N * M + (size_t)r * M;
-                    if (ok0) { oc[b0] = c0; od[b0] = dr0; }
-                    if (ok1) { oc[b1] = c1; od[b1] = dr1; }
+                    if (ok0) { o[0] = c0; o[seg1] = dr0; }
+                    if (ok1) { o[32] = c1; o[seg1 + 32] = dr1; }
                     if (lane == 0) obs_env[(size_t)2 * N * M + r] = (float)un;
                 } else {
-                    float *orow = obs_env + (size_t)r * OW;
-                    if (ok0) { orow[b0] = c0; orow[M + b0] = dr0; orow[2 * M + b0] = fu0; orow[3 * M + b0] = fa0; }
-                    if (ok1) { orow[b1] = c1; orow[M + b1] = dr1; orow[2 * M + b1] = fu1; orow[3 * M + b1] = fa1; }
-                    if (lane == 0) orow[4 * M] = (float)un;
+                    if (ok0) { o[0] = c0; o[seg1] = dr0; o[seg2] = fu0; o[seg3] = fa0; }
+                    if (ok1) { o[32] = c1; o[seg1 + 32] = dr1; o[seg2 + 32] = fu1; o[seg3 + 32] = fa1; }
+                    if (lane == 0) o[4 * M] = (float)un;
                 }
             }
             if (want_dbg) {
