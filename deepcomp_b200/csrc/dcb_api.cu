@@ -143,6 +143,7 @@ int launch_step(dcb_env *env, const int32_t *d_actions, int T, const dcb_outputs
     a.W = dcb_wide_layout(env->p.N, env->p.M, env->p.LC);
     a.actions = d_actions;
     a.T = T;
+    a.threads = env->threads;
     if (out) a.out = *out;
     else memset(&a.out, 0, sizeof(a.out));
     if (a.out.dbg_link_rate)

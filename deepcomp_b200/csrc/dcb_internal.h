@@ -169,6 +169,7 @@ struct StepArgs {
     WideLayout W;            // used by the wide kernel instead of L
     const int32_t *actions;  // [T][K][N], or NULL when a policy drives the envs
     int T;                   // 0 = observe only
+    int threads;             // CTA size of the launch
     PolicyParams pol;
     int32_t *actions_out;    // [T][K][N] actions the policy took, or NULL
     dcb_outputs out;

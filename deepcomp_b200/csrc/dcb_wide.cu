@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
     S.env_red = reinterpret_cast<double *>(smem + L.off_env);
     const MathTables *tab = S.tab;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = a.threads >> 5;   // a.threads == blockDim.x
     const int k = blockIdx.x;
     const bool valid = tid < N;
     const int i = valid ? tid : 0;
@@ -365,6 +365,9 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
         const int seg1 = central ? N * M : M, seg2 = 2 * M, seg3 = 3 * M;      // in floats
         const int row_stride_f = central ? M : OW;
         const long long kN = (long long)k * N;
+        float *reward_env = (a.out.reward && !central && T > 0)
+                                ? a.out.reward + (size_t)step * a.out.reward_stride + kN : nullptr;
+        double *dbg_reward_env = (last && a.out.dbg_reward && !central && T > 0) ? a.out.dbg_reward + kN : nullptr;
         for (int r = warp; r < N; r += nwarps) {
             const double rx = S.sx[r], ry = S.sy[r], rutil = S.su[r];
             const u64 rmask = S.smask[r];
@@ -459,8 +462,8 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                     }
                 }
                 if (lane == 0) {
-                    if (a.out.reward) a.out.reward[(size_t)step * a.out.reward_stride + ru] = (float)agg;
-                    if (last && a.out.dbg_reward) a.out.dbg_reward[ru] = agg;
+                    if (reward_env) reward_env[r] = (float)agg;
+                    if (dbg_reward_env) dbg_reward_env[r] = agg;
                 }
             }
         }
