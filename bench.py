@@ -332,15 +332,20 @@ def gpu_arm(args):
     bytes_per_env_step = env.algorithmic_bytes_per_env_step
     achieved = (bytes_per_env_step * K * kern_steps) / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "dcb_step_kernel",
+                "traffic": None, "peak_source": peak_src, "kernel": env.kernel_name,
                 "algorithmic_bytes_per_env_step": bytes_per_env_step,
                 "kernel_share_of_step": kern_ms / elapsed_ms if elapsed_ms > 0 else None,
                 "avg_launch_ms": kern_ms / max(len(events), 1), "env_steps_per_launch": K * F}
+    # measured DRAM bytes of one launch of this workload (ncu --set full capture, profiles/traffic.json), if one exists
     tr = os.path.join(ROOT, 'profiles', 'traffic.json')
+    wl_key = f"{args.kind}:{N}x{M}x{K}:F{F}"
     if os.path.exists(tr):
         try:
             with open(tr) as f:
-                roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+                rec = json.load(f).get(wl_key)
+            if rec:
+                roofline["traffic"] = rec["dram_bytes_per_launch"]
+                roofline["traffic_source"] = rec["source"]
         except Exception:  # noqa: BLE001
             pass
 

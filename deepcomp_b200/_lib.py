@@ -47,6 +47,7 @@ SYMBOLS = [
     'dcb_abi_version', 'dcb_last_error', 'dcb_create', 'dcb_destroy', 'dcb_reset', 'dcb_observe', 'dcb_step',
     'dcb_step_many', 'dcb_rollout', 'dcb_step_host', 'dcb_check_errors', 'dcb_get_state', 'dcb_set_state', 'dcb_obs_size',
     'dcb_reward_size', 'dcb_algorithmic_bytes_per_env_step', 'dcb_launch_count', 'dcb_launch_geometry',
+    'dcb_kernel_name',
 ]
 
 DCB_ABI_VERSION = 1
@@ -102,6 +103,8 @@ def load():
     L.dcb_launch_count.argtypes = [vp]
     L.dcb_launch_count.restype = i64
     L.dcb_launch_geometry.argtypes = [vp] + [ctypes.POINTER(i32)] * 4
+    L.dcb_kernel_name.argtypes = [vp]
+    L.dcb_kernel_name.restype = ctypes.c_char_p
     if L.dcb_abi_version() != DCB_ABI_VERSION:
         raise ImportError(f"libdeepcomp_b200.so ABI {L.dcb_abi_version()} != {DCB_ABI_VERSION}; rebuild")
     _LIB = L

@@ -134,6 +134,11 @@ class BatchedMobileEnv:
         return int(self._L.dcb_launch_count(self._h))
 
     @property
+    def kernel_name(self):
+        """'dcb_step_kernel' (fused, several envs per CTA) or 'dcb_wide_kernel' (one CTA per env, large envs)"""
+        return self._L.dcb_kernel_name(self._h).decode()
+
+    @property
     def launch_geometry(self):
         v = [ctypes.c_int32() for _ in range(4)]
         check(self._L.dcb_launch_geometry(self._h, *[ctypes.byref(x) for x in v]))

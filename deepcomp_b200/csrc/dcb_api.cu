@@ -178,6 +178,8 @@ int64_t dcb_algorithmic_bytes_per_env_step(const dcb_env *env) {
 
 int64_t dcb_launch_count(const dcb_env *env) { return env->launches; }
 
+const char *dcb_kernel_name(const dcb_env *env) { return env && env->wide ? "dcb_wide_kernel" : "dcb_step_kernel"; }
+
 int dcb_launch_geometry(const dcb_env *env, int32_t *envs_per_cta, int32_t *threads, int32_t *smem_bytes,
                         int32_t *grid) {
     if (!env) return fail(DCB_ERR_INVALID_ARG, "null handle");

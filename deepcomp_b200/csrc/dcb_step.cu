@@ -278,6 +278,8 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
         // carried from the end of one step to the next (only meaningful when the next step is not fresh):
         mask_t mask_next = 0;     // mask after the next step's action
         double rb_next = 0.0;     // the next step's reward before the move (base.py:446)
+        // ... which only the central reward (central.py:65-73) and the multi-agent 'sum' reward (multi_agent.py:79-86) read
+        const bool need_rb = central || p.reward == DCB_REWARD_SUM;
         bool any_fresh = true;    // some env of this CTA starts the step without inherited aggregates (CTA-uniform)
         int rot = 0;              // step % 3: the post-move UE bitsets rotate over three buffers (see the clear below)
 
@@ -352,7 +354,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                             Xrow[b] = r;
                             dr += r;                                                   // user.py:64-69
                         }
-                        rb = log_utility(tab, dr) * (1.0 / DCB_MAX_UTILITY);
+                        if (need_rb) rb = log_utility(tab, dr) * (1.0 / DCB_MAX_UTILITY);
                     }
                 } else {
                     mask = mask_next;
@@ -481,7 +483,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                     Xrow[b] = r_pre;
                 }
                 const double util = log_utility(tab, dr);
-                rb_next = log_utility(tab, dr_pre) * (1.0 / DCB_MAX_UTILITY);
+                if (need_rb) rb_next = log_utility(tab, dr_pre) * (1.0 / DCB_MAX_UTILITY);
                 const int h = par * EN + t;
                 hx[h] = x; hy[h] = y; hmask[h] = mask;
                 hutil[h] = util;

@@ -140,8 +140,10 @@ const char *dcb_last_error(void);
 
 /*
  * Allocate the state slabs for K envs on cfg->device and generate the per-UE RNG tables.  Supported shapes:
- * 1 <= M <= 64, N <= 512, and one env's working set (obs tile 4*(4M+1) + link values 8*(M|1) + ~70 bytes per UE)
- * must fit the 227 KB of shared memory of one CTA.  Synchronous.
+ * 1 <= M <= 64, N <= 1024.  Envs of up to 512 UEs whose working set (obs tile 4*(4M+1) + link values 8*(M|1) +
+ * ~100 bytes per UE) fits the 227 KB of shared memory of one CTA run on the fused, pipelined kernel (several envs per
+ * CTA); larger envs (BASELINE config 4: 1000 UE x 50 BS) run on the wide kernel, one CTA per env (dcb_kernel_name
+ * tells which; the environment variable DCB_FORCE_WIDE=1 selects the wide kernel for any shape).  Synchronous.
  */
 int dcb_create(const dcb_config *cfg, dcb_env **out);
 void dcb_destroy(dcb_env *env);
@@ -191,6 +193,8 @@ int64_t dcb_reward_size(const dcb_env *env);  /* floats per env: 1 (central) or 
 int64_t dcb_algorithmic_bytes_per_env_step(const dcb_env *env);
 /* Kernel launches issued through this handle so far (bench.py's gpu_launches) */
 int64_t dcb_launch_count(const dcb_env *env);
+/* Name of the CUDA kernel that steps this handle: "dcb_step_kernel" (fused) or "dcb_wide_kernel" (one CTA per env) */
+const char *dcb_kernel_name(const dcb_env *env);
 /* Launch geometry chosen for the step kernel: envs per CTA, threads per CTA, dynamic smem bytes, grid size */
 int dcb_launch_geometry(const dcb_env *env, int32_t *envs_per_cta, int32_t *threads, int32_t *smem_bytes,
                         int32_t *grid);
