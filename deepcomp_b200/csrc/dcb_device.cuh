@@ -172,8 +172,12 @@ __device__ __forceinline__ int policy_action(const PolicyParams &q, mask_t mask,
 // User.move (user.py:159-173) -> RandomWaypoint.step (movement.py:158-181) for one UE.  State: position (x, y), packed
 // waypoint wxy and velocity / pause / table cursor vpt (dcb_internal.h).  vfix >= 0: fixed velocity with snap threshold
 // vfix_thr, else the drawn velocity in vpt with its threshold from vthr[] (snap_threshold).
+// PREFETCH: `next_e` holds the table entry under the cursor, loaded when the previous one was consumed -- a redraw
+// happens about once per 50 steps and UE, and a warp that waits ~1 us for the table in global memory holds up every
+// warp of its group at the next barrier.
+template <bool PREFETCH>
 __device__ __forceinline__ void ue_move(const DevParams &p, long long u, double vfix, double vfix_thr, const double *vthr,
-                                        double &x, double &y, unsigned &wxy, unsigned &vpt) {
+                                        double &x, double &y, unsigned &wxy, unsigned &vpt, uint32_t &next_e) {
     double wx = (double)(wxy & 0xffffu), wy = (double)(wxy >> 16);
     unsigned pause = (vpt >> 8) & 0xffu;
     bool moving = true;
@@ -184,11 +188,15 @@ __device__ __forceinline__ void ue_move(const DevParams &p, long long u, double 
             moving = false;
         } else {                                                       // movement.py:177 -> reset()
             unsigned tidx = vpt >> 16;
+            uint32_t e;
             if ((int)tidx >= p.D) {
                 atomicOr(p.err, DCB_ERRBIT_TABLE);
                 tidx = p.D - 1;
+                e = p.table[u * p.D + tidx];
+            } else {
+                e = PREFETCH ? next_e : p.table[u * p.D + tidx];
             }
-            const uint32_t e = p.table[u * p.D + tidx];
+            if (PREFETCH) next_e = (int)(tidx + 1) < p.D ? p.table[u * p.D + tidx + 1] : 0u;
             wxy = (e & 0x3fffu) | (((e >> 14) & 0x3fffu) << 16);
             vpt = (e >> 28) | ((tidx + 1) << 16);
             wx = (double)(wxy & 0xffffu); wy = (double)(wxy >> 16);

@@ -43,6 +43,19 @@
 
 static_assert(sizeof(MathTables) == 5 * 16 * 8, "SmemLayout reserves 5 x 128 B for the math tables");
 
+#ifdef DCB_TRACE
+// Phase timeline of CTA 0 (A/B builds only, -DDCB_TRACE): clock64 of lane 0 of every warp at the phase boundaries of
+// steps 40..47 of a launch: [role][warp][step - 40][point]
+__device__ long long dcb_trace_buf[2 * 16 * 8 * 8];
+#define DCB_TRACE_PT(role, pt)                                                                              \
+    do {                                                                                                    \
+        if (blockIdx.x == 0 && (t & 31) == 0 && step >= 40 && step < 48)                                    \
+            dcb_trace_buf[(((role) * 16 + (t >> 5)) * 8 + (step - 40)) * 8 + (pt)] = clock64();             \
+    } while (0)
+#else
+#define DCB_TRACE_PT(role, pt) do { } while (0)
+#endif
+
 namespace {
 
 // [region:helpers.barriers]
@@ -266,6 +279,8 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
             ewma = p.ewma[u];
             tk = p.time[k];
         }
+        // the waypoint-table entry under the cursor, fetched ahead of its use (ue_move)
+        uint32_t next_e = valid && (int)(vpt >> 16) < p.D ? p.table[u * p.D + (vpt >> 16)] : 0u;
         const double vfix = valid ? velspec[i] : 0.0;
         const double vfix_thr = vfix >= 0.0 ? snap_threshold(vfix) : 0.0;
         double *Xrow = X + (size_t)t * MS;
@@ -297,6 +312,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
 // [region:P.top+fresh]
             // the observers must be done with this parity's hand-off buffers (step - 2)
             if (step >= 2) bar_sync(BAR_EMPTY + par, 2 * G);
+            DCB_TRACE_PT(0, 0);
             if (T > 0) {
                 if (any_fresh) {
                     // ---- stand-alone pre phase: first step of the launch or a step that starts with an episode
@@ -305,6 +321,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                     if (valid && p.auto_reset && tk >= p.episode_length) {
                         // MobileEnv.reset before the next step (base.py:169-189)
                         ue_reset(p, u, x, y, wxy, vpt);
+                        next_e = p.table[u * p.D + 1];      // cursor is 1 after a reset; D >= 3
                         mask = 0; ewma = 0.0; tk = 0;
                         fresh = true;
                     }
@@ -361,7 +378,8 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                 }
 // [region:P.move]
                 if (valid) {
-                    ue_move(p, u, vfix, vfix_thr, vthr, x, y, wxy, vpt);
+                    DCB_TRACE_PT(0, 1);
+                    ue_move<true>(p, u, vfix, vfix_thr, vthr, x, y, wxy, vpt, next_e);
 // [region:P.drop+ewma]
                     // ---- check_bs_connection (user.py:175-188) + update_ewma_dr (user.py:148-157); Xrow holds the
                     // pre-move shared rates (ue.bs_dr)
@@ -394,6 +412,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                     if ((mask & bit) || dist2(bsxy[b], x, y) <= p.thr_d2) mask_next = mask ^ bit;
                 }
             }
+            DCB_TRACE_PT(0, 2);
 // [region:P.links]
             // ---- link values at the new position, balanced over the warp: the lanes' links (1.6 on average, up to M)
             // are compacted into a per-warp list and dealt out round-robin, LW per lane and trip in one basic block
@@ -451,10 +470,13 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
             }
 // [region:P.reduce_phase]
             // barrier + "does any env of this CTA reset before the next step?" in one bar.red
+            DCB_TRACE_PT(0, 3);
             any_fresh = bar_or(BAR_PHYS, G, valid && T > 0 && p.auto_reset && tk >= p.episode_length);
+            DCB_TRACE_PT(0, 4);
             reduce_links(t, G, X, bits_post, bits_pre, N, M, MS, n_env, S, p.CS, p.has_maxcap, share, fac_post, arg_post,
                          fac_pre, arg_pre);
             bar_sync(BAR_PHYS, G);
+            DCB_TRACE_PT(0, 5);
             // bits_pre of this parity is consumed; its next use is two steps (>= 2 group barriers) away.  The post
             // bitsets of step - 2 were read by the observers, who are done with that step (EMPTY wait above); that
             // buffer, (step + 1) % 3, is the one the next step fills
@@ -490,6 +512,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                 hrb[h] = rb; hdr[h] = dr; hlost[h] = lost;
             }
             bar_arrive(BAR_FULL + par, 2 * G);
+            DCB_TRACE_PT(0, 7);
         }
 // [region:P.drain+store]
         // drain: the observers' last (up to two) EMPTY arrivals
@@ -550,6 +573,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
             float *row_dr = central ? row_conn + N * M : row_conn + M;
 // [region:O.full_wait]
             bar_sync(BAR_FULL + par, 2 * G);
+            DCB_TRACE_PT(1, 0);
             // the previous step's TMA store(s) must have finished reading the tile before anyone rewrites it
             if (warp_store) {
                 if (lane == 0 && step > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -573,6 +597,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                 }
             }
             __syncwarp();
+            DCB_TRACE_PT(1, 1);
             if (valid) {
                 const int h = hbase + t;
                 const double x = hx[h], y = hy[h], util = hutil[h], dr = hdr[h];
@@ -604,6 +629,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                     for (int b = 0; b < M; b++)
                         row_dr[b] = (float)(snr_of_d2(p, tab, dist2(bsxy[b], x, y)) * inv_max);
                 }
+                DCB_TRACE_PT(1, 2);
 // [region:O.staging]
                 // ---- rest of the observation row
                 const double un = util * (1.0 / DCB_MAX_UTILITY);                      // variants.py:287
@@ -646,6 +672,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                         for (int b = 0; b < M; b++)
                             a.out.dbg_snr[u * M + b] = snr_of_d2(p, tab, dist2(bsxy[b], x, y));
                 }
+                DCB_TRACE_PT(1, 3);
 // [region:O.outputs+reward]
                 // ---- per-UE outputs and rewards -> global
                 if (a.out.curr_dr) a.out.curr_dr[(size_t)step * a.out.curr_dr_stride + u] = (float)dr;
@@ -697,6 +724,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                     }
                 }
             }
+            DCB_TRACE_PT(1, 4);
 // [region:O.tile_out]
             // ---- obs tile -> global observation buffer (contiguous span of this CTA): generic-proxy writes of the
             // tile -> visible to the async proxy; then an elected thread issues the bulk copy (TMA, UBLKCP); its read
@@ -747,6 +775,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
             }
             // hand the parity's buffers back to the physics warps
             bar_arrive(BAR_EMPTY + par, 2 * G);
+            DCB_TRACE_PT(1, 5);
         }
         if (warp_store ? lane == 0 : t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
@@ -766,6 +795,12 @@ DCB_STEP_KERNEL(768, 80)
 DCB_STEP_KERNEL(1024, 64)
 
 }  // namespace
+
+#ifdef DCB_TRACE
+extern "C" int dcb_trace_read(long long *out) {
+    return (int)cudaMemcpyFromSymbol(out, dcb_trace_buf, sizeof(dcb_trace_buf));
+}
+#endif
 
 size_t dcb_step_smem_bytes(int kind, int N, int M, int E) { return (size_t)dcb_smem_layout(kind, N, M, E).total; }
 
