@@ -308,6 +308,10 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     int S = 1, CS = 0;
     const int NW = (N + 31) / 32;
     while (S < 4 * NW && S * 2 <= 32 && E * M * S * 2 <= group) S *= 2;
+    if (const char *ov = getenv("DCB_REDUCE_LANES")) {       // experiments: 1, 2, 4, 8, ...
+        const int v = atoi(ov);
+        if (v >= 1 && v <= 32 && (v & (v - 1)) == 0 && v <= 4 * NW) S = v;
+    }
     while ((NW << CS) < S && CS < 2) CS++;
 
     const size_t KN = (size_t)K * N;
