@@ -781,6 +781,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
     }
 }
 
+// [region:wrappers]
 // Register budget per CTA-size class so that one CTA of that size (three of the smallest) is always resident:
 // 65536 registers / (warps rounded up to a multiple of 4 x 32), in the allocation granule of 8 registers per thread
 // (88 registers x 704 threads does not launch: warps are allocated in fours).
