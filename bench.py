@@ -242,6 +242,8 @@ def gpu_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO on some boxes) off it
+        os.environ['NCCL_DEBUG'] = os.environ.get('DCB_NCCL_DEBUG', 'WARN')
         dist.init_process_group('nccl', device_id=dev)
 
     K, N, M, L, F = args.envs, args.n_ue, args.n_bs, args.episode_length, args.fragment
