@@ -300,11 +300,15 @@ def test_full_size_batch_properties():
 
 
 # ------------------------------------------------------------------------------------------------ on-device policies
+@pytest.mark.parametrize('wide', [False, True], ids=['fused', 'wide'])
 @pytest.mark.parametrize('name', [n for n in __import__('helpers').golden_names() if n.startswith('policy_')])
-def test_device_policies_reproduce_reference_agents(name):
+def test_device_policies_reproduce_reference_agents(name, wide, monkeypatch):
     """Closed loop on the device: the kernel's scripted policy takes exactly the actions the reference's agent took on
-    the reference env, and the env follows the same trajectory (deepcomp/agent/heuristics.py, dummy.py)."""
+    the reference env, and the env follows the same trajectory (deepcomp/agent/heuristics.py, dummy.py); through the
+    fused kernel and through the wide (one CTA per env) kernel."""
     from deepcomp_b200 import BatchedMobileEnv
+    if wide:
+        monkeypatch.setenv('DCB_FORCE_WIDE', '1')
     from helpers import oracle_kwargs
     from test_agents import make_agent
     cfg, z = load_golden(name)
@@ -327,9 +331,12 @@ def test_device_policies_reproduce_reference_agents(name):
     env.check_errors()
 
 
-def test_rollout_equals_host_loop_with_the_same_policy():
+@pytest.mark.parametrize('wide', [False, True], ids=['fused', 'wide'])
+def test_rollout_equals_host_loop_with_the_same_policy(wide, monkeypatch):
     """K envs: device rollout == stepping the same envs from the host with the host form of the agent."""
     from deepcomp_b200 import BatchedMobileEnv, agents
+    if wide:
+        monkeypatch.setenv('DCB_FORCE_WIDE', '1')
     K, N, M, T = 19, 50, 10, 15
     a = BatchedMobileEnv(num_envs=K, kind='multi', seed=4, **_scenario())
     b = BatchedMobileEnv(num_envs=K, kind='multi', seed=4, **_scenario())
