@@ -172,12 +172,19 @@ __device__ __forceinline__ int policy_action(const PolicyParams &q, mask_t mask,
 // User.move (user.py:159-173) -> RandomWaypoint.step (movement.py:158-181) for one UE.  State: position (x, y), packed
 // waypoint wxy and velocity / pause / table cursor vpt (dcb_internal.h).  vfix >= 0: fixed velocity with snap threshold
 // vfix_thr, else the drawn velocity in vpt with its threshold from vthr[] (snap_threshold).
-// PREFETCH: `next_e` holds the table entry under the cursor, loaded when the previous one was consumed -- a redraw
-// happens about once per 50 steps and UE, and a warp that waits ~1 us for the table in global memory holds up every
-// warp of its group at the next barrier.
+// PREFETCH: `*next_slot` (shared memory) receives the table entry under the cursor by an asynchronous copy (cp.async,
+// SASS LDGSTS) issued when the previous entry was consumed -- a redraw happens about once per 50 steps and UE, and a warp
+// that waits ~1 us for the table in global memory holds up every warp of its group at the next barrier.  A load into a
+// register would do the same on paper, but its scoreboard is shared with later shared-memory loads and stalls them.
+__device__ __forceinline__ void prefetch_table_entry(uint32_t *slot, const uint32_t *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(slot)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <bool PREFETCH>
 __device__ __forceinline__ void ue_move(const DevParams &p, long long u, double vfix, double vfix_thr, const double *vthr,
-                                        double &x, double &y, unsigned &wxy, unsigned &vpt, uint32_t &next_e) {
+                                        double &x, double &y, unsigned &wxy, unsigned &vpt, uint32_t *next_slot) {
     double wx = (double)(wxy & 0xffffu), wy = (double)(wxy >> 16);
     unsigned pause = (vpt >> 8) & 0xffu;
     bool moving = true;
@@ -193,10 +200,13 @@ __device__ __forceinline__ void ue_move(const DevParams &p, long long u, double 
                 atomicOr(p.err, DCB_ERRBIT_TABLE);
                 tidx = p.D - 1;
                 e = p.table[u * p.D + tidx];
+            } else if (PREFETCH) {
+                prefetch_wait();
+                e = *next_slot;
             } else {
-                e = PREFETCH ? next_e : p.table[u * p.D + tidx];
+                e = p.table[u * p.D + tidx];
             }
-            if (PREFETCH) next_e = (int)(tidx + 1) < p.D ? p.table[u * p.D + tidx + 1] : 0u;
+            if (PREFETCH && (int)(tidx + 1) < p.D) prefetch_table_entry(next_slot, p.table + u * p.D + tidx + 1);
             wxy = (e & 0x3fffu) | (((e >> 14) & 0x3fffu) << 16);
             vpt = (e >> 28) | ((tidx + 1) << 16);
             wx = (double)(wxy & 0xffffu); wy = (double)(wxy >> 16);

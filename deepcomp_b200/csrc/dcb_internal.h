@@ -58,7 +58,7 @@ struct DevParams {
 struct SmemLayout {
     int off_tab, off_stage, off_x, off_fac_pre, off_fac_post, off_hx, off_hy,
         off_hmask, off_hutil, off_hrb, off_hdr, off_hlost, off_bsx, off_bsy, off_vel,
-        off_arg_pre, off_arg_post, off_bits, off_share, off_links, off_vthr, off_wagg;
+        off_arg_pre, off_arg_post, off_bits, off_share, off_links, off_vthr, off_wagg, off_snext;
     int nbits;   // words per bitset
     int links_per_warp;   // capacity (entries) of one physics warp's link list
     int wagg_pairs;       // (env, BS) pairs one observer warp aggregates for itself: the envs its 32 rows touch x M
@@ -105,6 +105,7 @@ __host__ __device__ inline SmemLayout dcb_smem_layout(int kind, int N, int M, in
     L.links_per_warp = 32 * M;
     L.off_links = o;    o += align16(((EN + 31) / 32) * L.links_per_warp * 2);
     L.off_vthr = o;     o += align16(16 * 8);                        // snap thresholds for drawn velocities 0..15
+    L.off_snext = o;    o += align16(EN * 4);                        // per UE: prefetched waypoint-table entry
     // per observer warp: utility aggregates of the (env, BS) pairs its rows need -- usum, umin (double), cnt (int),
     // f_ues, f_util (float) -- computed by the warp itself so that observer warps never synchronise with each other
     L.wagg_pairs = ((31 / N + 2) * M + 1) & ~1;

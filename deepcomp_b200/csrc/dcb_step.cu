@@ -47,6 +47,17 @@ static_assert(sizeof(MathTables) == 5 * 16 * 8, "SmemLayout reserves 5 x 128 B f
 // Phase timeline of CTA 0 (A/B builds only, -DDCB_TRACE): clock64 of lane 0 of every warp at the phase boundaries of
 // steps 40..47 of a launch: [role][warp][step - 40][point]
 __device__ long long dcb_trace_buf[2 * 16 * 8 * 8];
+__device__ long long dcb_trace_cta[3 * 4096];     // per CTA: globaltimer (ns) at entry / exit, SM id
+__device__ __forceinline__ long long dcb_globaltimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned dcb_smid() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
 #define DCB_TRACE_PT(role, pt)                                                                              \
     do {                                                                                                    \
         if (blockIdx.x == 0 && (t & 31) == 0 && step >= 40 && step < 48)                                    \
@@ -236,6 +247,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
     unsigned *bits_fresh = bits_pre2 + 2 * L.nbits;                            // [nbits]
     unsigned short *links = reinterpret_cast<unsigned short *>(smem + L.off_links);
     double *vthr = reinterpret_cast<double *>(smem + L.off_vthr);
+    uint32_t *snext = reinterpret_cast<uint32_t *>(smem + L.off_snext);
 
     const int G = blockDim.x >> 1;                  // threads per warp group
     const bool is_obs = (int)threadIdx.x >= G;
@@ -263,6 +275,9 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
     if (threadIdx.x >= 32 && threadIdx.x < 48) vthr[threadIdx.x - 32] = snap_threshold((double)(threadIdx.x - 32));
     __syncthreads();
 
+#ifdef DCB_TRACE
+    if (threadIdx.x == 0 && blockIdx.x < 4096) dcb_trace_cta[3 * blockIdx.x] = dcb_globaltimer();
+#endif
     if (!is_obs) {
 // [region:P.load]
         // ===================================================================== physics warps
@@ -280,7 +295,8 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
             tk = p.time[k];
         }
         // the waypoint-table entry under the cursor, fetched ahead of its use (ue_move)
-        uint32_t next_e = valid && (int)(vpt >> 16) < p.D ? p.table[u * p.D + (vpt >> 16)] : 0u;
+        uint32_t *next_slot = snext + t;
+        if (valid && (int)(vpt >> 16) < p.D) prefetch_table_entry(next_slot, p.table + u * p.D + (vpt >> 16));
         const double vfix = valid ? velspec[i] : 0.0;
         const double vfix_thr = vfix >= 0.0 ? snap_threshold(vfix) : 0.0;
         double *Xrow = X + (size_t)t * MS;
@@ -321,7 +337,8 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                     if (valid && p.auto_reset && tk >= p.episode_length) {
                         // MobileEnv.reset before the next step (base.py:169-189)
                         ue_reset(p, u, x, y, wxy, vpt);
-                        next_e = p.table[u * p.D + 1];      // cursor is 1 after a reset; D >= 3
+                        prefetch_wait();                    // (an older copy into the slot must land first)
+                        prefetch_table_entry(next_slot, p.table + u * p.D + 1);   // cursor is 1 after a reset; D >= 3
                         mask = 0; ewma = 0.0; tk = 0;
                         fresh = true;
                     }
@@ -379,7 +396,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
 // [region:P.move]
                 if (valid) {
                     DCB_TRACE_PT(0, 1);
-                    ue_move<true>(p, u, vfix, vfix_thr, vthr, x, y, wxy, vpt, next_e);
+                    ue_move<true>(p, u, vfix, vfix_thr, vthr, x, y, wxy, vpt, next_slot);
 // [region:P.drop+ewma]
                     // ---- check_bs_connection (user.py:175-188) + update_ewma_dr (user.py:148-157); Xrow holds the
                     // pre-move shared rates (ue.bs_dr)
@@ -527,6 +544,12 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
             p.ewma[u] = ewma;
             if (i == 0) p.time[k] = tk;
         }
+#ifdef DCB_TRACE
+        if (threadIdx.x == 0 && blockIdx.x < 4096) {
+            dcb_trace_cta[3 * blockIdx.x + 1] = dcb_globaltimer();
+            dcb_trace_cta[3 * blockIdx.x + 2] = dcb_smid();
+        }
+#endif
     } else {
 // [region:O.setup]
         // ===================================================================== observer warps
@@ -800,6 +823,9 @@ DCB_STEP_KERNEL(1024, 64)
 #ifdef DCB_TRACE
 extern "C" int dcb_trace_read(long long *out) {
     return (int)cudaMemcpyFromSymbol(out, dcb_trace_buf, sizeof(dcb_trace_buf));
+}
+extern "C" int dcb_trace_read_cta(long long *out) {
+    return (int)cudaMemcpyFromSymbol(out, dcb_trace_cta, sizeof(dcb_trace_cta));
 }
 #endif
 

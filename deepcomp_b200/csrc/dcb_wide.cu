@@ -262,8 +262,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                 }
                 rb = log_utility(tab, dr0) * (1.0 / DCB_MAX_UTILITY);
                 // ---- User.move (user.py:159-173), check_bs_connection (user.py:175-188), update_ewma_dr (user.py:148-157)
-                uint32_t no_prefetch = 0;
-                ue_move<false>(p, u, vfix, vfix_thr, S.vthr, x, y, wxy, vpt, no_prefetch);
+                ue_move<false>(p, u, vfix, vfix_thr, S.vthr, x, y, wxy, vpt, nullptr);
                 double keep = 0.0;
                 slot = 0;
                 for (u64 m = mask; m; m &= m - 1, slot++) {

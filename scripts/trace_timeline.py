@@ -40,3 +40,18 @@ for role, pts in ((0, [0, 1, 2, 3, 4, 6, 7]), (1, [0, 1, 2, 3, 4, 5])):
             print('          ' + ' '.join(f'{tr[role, w, step, p if p != 6 else 5] - t0:10d}' for p in pts))
 per_step = (tr[0, :nw, 7, 0] - tr[0, :nw, 0, 0]) / 7.0
 print('cycles per step (physics top to top):', per_step.mean())
+
+# ---- per-CTA wall time of the traced launch (globaltimer): the kernel ends with its slowest CTA
+cta = np.zeros(3 * 4096, dtype=np.int64)
+L.dcb_trace_read_cta.argtypes = [ctypes.c_void_p]
+assert L.dcb_trace_read_cta(cta.ctypes.data) == 0
+g = env.launch_geometry['grid']
+t0 = cta[0:3 * g:3]
+t1 = cta[1:3 * g:3]
+sm = cta[2:3 * g:3]
+dur = (t1 - t0) / 1e3
+order = np.argsort(dur)
+print(f'per-CTA duration of one 100-step launch (us): min {dur.min():.1f} median {np.median(dur):.1f} '
+      f'p90 {np.percentile(dur, 90):.1f} max {dur.max():.1f}; launch span {(t1.max() - t0.min()) / 1e3:.1f}')
+print('slowest CTAs (cta, sm, us):', [(int(c), int(sm[c]), round(float(dur[c]), 1)) for c in order[-8:]])
+print('fastest CTAs (cta, sm, us):', [(int(c), int(sm[c]), round(float(dur[c]), 1)) for c in order[:8]])
