@@ -134,6 +134,15 @@ class BatchedMobileEnv:
         return int(self._L.dcb_launch_count(self._h))
 
     @property
+    def active_ues(self):
+        """UEs present per env: slots [0, active_ues) of the n_ue = max_ues slots (reference base.py:80-84)"""
+        return int(self._L.dcb_get_active_ues(self._h))
+
+    @active_ues.setter
+    def active_ues(self, n):
+        check(self._L.dcb_set_active_ues(self._h, int(n)))
+
+    @property
     def kernel_name(self):
         """'dcb_step_kernel' (fused, several envs per CTA) or 'dcb_wide_kernel' (one CTA per env, large envs)"""
         return self._L.dcb_kernel_name(self._h).decode()

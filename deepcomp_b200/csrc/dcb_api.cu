@@ -345,7 +345,7 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
 
     DevParams &p = env->p;
     memset(&p, 0, sizeof(p));
-    p.K = K; p.N = N; p.M = M; p.kind = cfg->kind; p.reward = cfg->reward;
+    p.K = K; p.N = N; p.NA = N; p.M = M; p.kind = cfg->kind; p.reward = cfg->reward;
     p.episode_length = cfg->episode_length; p.auto_reset = cfg->auto_reset; p.pause_duration = cfg->pause_duration;
     p.D = D; p.E = E; p.S = S; p.CS = CS; p.LC = LC;
     p.has_maxcap = has_maxcap; p.has_propfair = has_pf;
@@ -361,7 +361,9 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     p.pos = env->d_pos; p.mv = env->d_mv; p.mask = env->d_mask; p.ewma = env->d_ewma; p.time = env->d_time;
     p.init_pos = env->d_init_pos; p.table = env->d_table; p.err = env->d_err;
 
-    cudaError_t e = env->wide ? dcb_wide_set_smem_limit(env->smem) : dcb_step_set_smem_limit(env->threads, M, env->smem);
+    // the attribute is per kernel, not per handle: always raise it to the device limit so that a later, smaller handle
+    // of the same kernel class cannot lower it under an earlier one
+    cudaError_t e = env->wide ? dcb_wide_set_smem_limit(smem_cap) : dcb_step_set_smem_limit(env->threads, M, smem_cap);
     if (e != cudaSuccess) {
         dcb_destroy(env);
         return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", env->smem, cudaGetErrorString(e));
@@ -431,6 +433,16 @@ int dcb_reset(dcb_env *env, const int32_t *host_env_ids, int32_t n, void *stream
     if (host_env_ids) CU(cudaStreamSynchronize(s));   // the id list is reused by the next partial reset
     return DCB_OK;
 }
+
+int dcb_set_active_ues(dcb_env *env, int32_t n_active) {
+    if (!env) return fail(DCB_ERR_INVALID_ARG, "null handle");
+    if (n_active < 1 || n_active > env->p.N)
+        return fail(DCB_ERR_INVALID_ARG, "n_active = %d outside [1, n_ue = %d]", n_active, env->p.N);
+    env->p.NA = n_active;
+    return DCB_OK;
+}
+
+int32_t dcb_get_active_ues(const dcb_env *env) { return env ? env->p.NA : 0; }
 
 int dcb_observe(dcb_env *env, const dcb_outputs *out, void *stream) {
     if (!env) return fail(DCB_ERR_INVALID_ARG, "null handle");

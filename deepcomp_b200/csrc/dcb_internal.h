@@ -29,6 +29,7 @@
 
 struct DevParams {
     int K, N, M, kind, reward;
+    int NA;              // active UEs per env: slots [0, NA) of the N = max_ues slots exist (base.py:80-84, central.py:46-55)
     int episode_length, auto_reset, pause_duration;
     int D;               // waypoint-table depth per UE
     int E;               // envs per CTA

@@ -166,12 +166,12 @@ __device__ __forceinline__ void reduce_links(int tid, int gsize, const double *X
 // (station.py:63-69) -> usum, min (station.py:78-83) -> umin, and the two per-BS observation entries (variants.py:296-299,
 // station.py:71-76) -> f_ues, f_util.  Lane q walks the UE bitset of pair q in UE order; warps that share an env
 // compute bit-identical values.
-__device__ __forceinline__ void warp_reduce_utility(int lane, const unsigned *bits, const double *su, int N, int M,
-                                                    int le0, int n_le, bool want_min, int *cnt, double *usum,
+__device__ __forceinline__ void warp_reduce_utility(int lane, const unsigned *bits, const double *su, int N, int NA,
+                                                    int M, int le0, int n_le, bool want_min, int *cnt, double *usum,
                                                     double *umin, float *f_ues, float *f_util) {
     const int NW = (N + 31) >> 5;
     const int PW = n_le * M;
-    const double inv_n = 1.0 / (double)N;
+    const double inv_n = 1.0 / (double)NA;       // self.num_ue = UEs present (variants.py:296)
     const float inv_m = 1.0f / (float)M;
     for (int q = lane; q < PW; q += 32) {
         const int ll = __float2int_rz(((float)q + 0.5f) * inv_m), b = q - ll * M;   // exact: q < 2^16
@@ -255,9 +255,11 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
     const int env0 = blockIdx.x * E;
     const int n_env = min(E, p.K - env0);
     const int EN = E * N;
-    const bool valid = t < n_env * N;
-    const int le = valid ? t / N : 0;
-    const int i = valid ? t - le * N : 0;
+    const bool in_cta = t < n_env * N;              // a UE slot of one of this CTA's envs
+    const int le = in_cta ? t / N : 0;
+    const int i = in_cta ? t - le * N : 0;
+    const int NA = p.NA;                            // slots [0, NA) hold UEs, the rest is padding (max_ues > num_ue)
+    const bool valid = in_cta && i < NA;
     const int k = env0 + le;
     const long long u = (long long)k * N + i;
     const bool central = p.kind == DCB_KIND_CENTRAL;
@@ -608,14 +610,14 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
             const unsigned *bits_post = bits_post3 + orot * L.nbits;
             orot = orot == 2 ? 0 : orot + 1;
             if (!central)
-                warp_reduce_utility(lane, bits_post, hutil + hbase, N, M, le0, n_le, p.reward == DCB_REWARD_MIN, cnt_o,
+                warp_reduce_utility(lane, bits_post, hutil + hbase, N, NA, M, le0, n_le, p.reward == DCB_REWARD_MIN, cnt_o,
                                     usum_o, umin_o, f_ues, f_util);
             double env_rew_v = 0.0, env_sumu_v = 0.0;          // of the env whose UE 0 this thread is
             if (want_env_rew || want_env_sumu) {
                 for (int es = le_s0; es < n_env && es * N < w0 + 32; es++) {
                     double r1 = 0.0, r2 = 0.0;
-                    if (want_env_rew) r1 = warp_reduce_env(lane, hrb + hbase + es * N, N, p.reward == DCB_REWARD_MIN ? 2 : 0);
-                    if (want_env_sumu) r2 = warp_reduce_env(lane, hutil + hbase + es * N, N, 0);
+                    if (want_env_rew) r1 = warp_reduce_env(lane, hrb + hbase + es * N, NA, p.reward == DCB_REWARD_MIN ? 2 : 0);
+                    if (want_env_sumu) r2 = warp_reduce_env(lane, hutil + hbase + es * N, NA, 0);
                     if (valid && le == es && i == 0) { env_rew_v = r1; env_sumu_v = r2; }
                 }
             }
@@ -685,7 +687,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                                 const int c = cnt_o[lq + b];
                                 drow[b] = (double)((unsigned)(mask >> b) & 1u);
                                 drow[M + b] = (double)row_dr[b];
-                                drow[2 * M + b] = (double)c / (double)N;
+                                drow[2 * M + b] = (double)c / (double)NA;
                                 drow[3 * M + b] = (c > 0 ? usum_o[lq + b] / (double)c : 0.0) / DCB_MAX_UTILITY;
                             }
                             drow[4 * M] = un;
@@ -713,7 +715,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                         if (i == 0) {
                             // central.py:65-73 over the PRE-move rewards
                             double r = env_rew_v;
-                            if (p.reward == DCB_REWARD_AVG) r = r / (double)N;
+                            if (p.reward == DCB_REWARD_AVG) r = r / (double)NA;
                             if (a.out.reward) a.out.reward[(size_t)step * a.out.reward_stride + k] = (float)r;
                             if (last && a.out.dbg_reward) a.out.dbg_reward[k] = r;
                         }
@@ -733,7 +735,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                             } else if (p.reward == DCB_REWARD_SUM) {
                                 // user.py:238-244: UEs sharing any BS with this UE; their PRE-move rewards
                                 agg = 0.0;
-                                for (int j = 0; j < N; j++)
+                                for (int j = 0; j < NA; j++)
                                     if ((mask_t)hmask[hbase + le * N + j] & mask) agg += hrb[hbase + le * N + j];
                             } else {
                                 for (mask_t m = inrange; m; m &= m - 1) {
@@ -745,6 +747,38 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                         if (a.out.reward) a.out.reward[(size_t)step * a.out.reward_stride + u] = (float)agg;
                         if (last && a.out.dbg_reward) a.out.dbg_reward[u] = agg;
                     }
+                }
+            } else if (in_cta) {
+                // ---- padding slot (no UE there: max_ues > num_ue): zeros, as central.py:46-55 pads the observation
+                for (int b = 0; b < M; b++) {
+                    row_conn[b] = 0.0f;
+                    row_dr[b] = 0.0f;
+                    if (!central) { row_conn[2 * M + b] = 0.0f; row_conn[3 * M + b] = 0.0f; }
+                }
+                if (central) tile[(size_t)le * (2 * N * M + N) + 2 * N * M + i] = 0.0f;
+                else row_conn[4 * M] = 0.0f;
+                if (a.out.curr_dr) a.out.curr_dr[(size_t)step * a.out.curr_dr_stride + u] = 0.0f;
+                if (a.out.utility) a.out.utility[(size_t)step * a.out.utility_stride + u] = 0.0f;
+                if (T > 0) {
+                    if (a.out.lost_conn) a.out.lost_conn[(size_t)step * a.out.lost_conn_stride + u] = 0;
+                    if (!central && a.out.reward) a.out.reward[(size_t)step * a.out.reward_stride + u] = 0.0f;
+                }
+                if (last) {
+                    if (a.out.dbg_curr_dr) a.out.dbg_curr_dr[u] = 0.0;
+                    if (a.out.dbg_utility) a.out.dbg_utility[u] = 0.0;
+                    if (!central && T > 0 && a.out.dbg_reward) a.out.dbg_reward[u] = 0.0;
+                    if (a.out.dbg_obs) {
+                        if (central) {
+                            double *drow = a.out.dbg_obs + (size_t)k * (2 * N * M + N);
+                            for (int b = 0; b < M; b++) { drow[i * M + b] = 0.0; drow[N * M + i * M + b] = 0.0; }
+                            drow[2 * N * M + i] = 0.0;
+                        } else {
+                            double *drow = a.out.dbg_obs + (size_t)u * OW;
+                            for (int b = 0; b <= 4 * M; b++) drow[b] = 0.0;
+                        }
+                    }
+                    if (a.out.dbg_snr)
+                        for (int b = 0; b < M; b++) a.out.dbg_snr[u * M + b] = 0.0;
                 }
             }
             DCB_TRACE_PT(1, 4);

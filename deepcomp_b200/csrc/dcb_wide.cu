@@ -80,9 +80,9 @@ __device__ __forceinline__ void wide_reduce_links(const WideSmem &S, int N, int 
 }
 
 // per-BS utility aggregates for the observation / multi-agent reward (one warp per BS)
-__device__ __forceinline__ void wide_reduce_utility(const WideSmem &S, int N, int M, int NW, bool want_min, int warp,
+__device__ __forceinline__ void wide_reduce_utility(const WideSmem &S, int NA, int M, int NW, bool want_min, int warp,
                                                     int lane, int nwarps) {
-    const double inv_n = 1.0 / (double)N;
+    const double inv_n = 1.0 / (double)NA;      // self.num_ue = UEs present (variants.py:296)
     for (int b = warp; b < M; b += nwarps) {
         int c = 0;
         double s = 0.0, mn = DCB_MAX_UTILITY;
@@ -159,7 +159,8 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = a.threads >> 5;   // a.threads == blockDim.x
     const int k = blockIdx.x;
-    const bool valid = tid < N;
+    const int NA = p.NA;                   // slots [0, NA) hold UEs, the rest is padding (max_ues > num_ue)
+    const bool valid = tid < NA;
     const int i = valid ? tid : 0;
     const long long u = (long long)k * N + i;
     const bool central = p.kind == DCB_KIND_CENTRAL;
@@ -318,11 +319,11 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
             if (T > 0 && a.out.lost_conn) a.out.lost_conn[(size_t)step * a.out.lost_conn_stride + u] = (uint8_t)lost;
         }
         __syncthreads();
-        if (!central) wide_reduce_utility(S, N, M, NW, p.reward == DCB_REWARD_MIN, warp, lane, nwarps);
+        if (!central) wide_reduce_utility(S, NA, M, NW, p.reward == DCB_REWARD_MIN, warp, lane, nwarps);
         if (warp == nwarps - 1) {
             // per-env sums: utility (base.py:402) and the central reward over the PRE-move rewards (central.py:65-73)
             double s_u = 0.0, s_r = p.reward == DCB_REWARD_MIN ? CUDART_INF : 0.0;
-            for (int j = lane; j < N; j += 32) {
+            for (int j = lane; j < NA; j += 32) {
                 s_u += S.su[j];
                 const double r = S.srb[j];
                 s_r = p.reward == DCB_REWARD_MIN ? (r < s_r ? r : s_r) : s_r + r;
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
             if (last && a.out.dbg_sum_utility) a.out.dbg_sum_utility[k] = S.env_red[0];
             if (central && T > 0) {
                 double r = S.env_red[1];
-                if (p.reward == DCB_REWARD_AVG) r = r / (double)N;
+                if (p.reward == DCB_REWARD_AVG) r = r / (double)NA;
                 if (a.out.reward) a.out.reward[(size_t)step * a.out.reward_stride + k] = (float)r;
                 if (last && a.out.dbg_reward) a.out.dbg_reward[k] = r;
             }
@@ -369,6 +370,47 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                                 ? a.out.reward + (size_t)step * a.out.reward_stride + kN : nullptr;
         double *dbg_reward_env = (last && a.out.dbg_reward && !central && T > 0) ? a.out.dbg_reward + kN : nullptr;
         for (int r = warp; r < N; r += nwarps) {
+            if (r >= NA) {
+                // ---- padding slot (no UE there: max_ues > num_ue): zeros, as central.py:46-55 pads the observation
+                const long long ru = kN + r;
+                if (obs_lane) {
+                    float *o = obs_lane + r * row_stride_f;
+                    if (central) {
+                        if (ok0) { o[0] = 0.0f; o[seg1] = 0.0f; }
+                        if (ok1) { o[32] = 0.0f; o[seg1 + 32] = 0.0f; }
+                        if (lane == 0) obs_env[(size_t)2 * N * M + r] = 0.0f;
+                    } else {
+                        if (ok0) { o[0] = 0.0f; o[seg1] = 0.0f; o[seg2] = 0.0f; o[seg3] = 0.0f; }
+                        if (ok1) { o[32] = 0.0f; o[seg1 + 32] = 0.0f; o[seg2 + 32] = 0.0f; o[seg3 + 32] = 0.0f; }
+                        if (lane == 0) o[4 * M] = 0.0f;
+                    }
+                }
+                if (lane == 0) {
+                    if (a.out.curr_dr) a.out.curr_dr[(size_t)step * a.out.curr_dr_stride + ru] = 0.0f;
+                    if (a.out.utility) a.out.utility[(size_t)step * a.out.utility_stride + ru] = 0.0f;
+                    if (T > 0 && a.out.lost_conn) a.out.lost_conn[(size_t)step * a.out.lost_conn_stride + ru] = 0;
+                    if (reward_env) reward_env[r] = 0.0f;
+                    if (dbg_reward_env) dbg_reward_env[r] = 0.0;
+                    if (last && a.out.dbg_curr_dr) a.out.dbg_curr_dr[ru] = 0.0;
+                    if (last && a.out.dbg_utility) a.out.dbg_utility[ru] = 0.0;
+                }
+                if (last && a.out.dbg_obs) {
+                    if (central) {
+                        double *drow = a.out.dbg_obs + (size_t)k * (2 * N * M + N);
+                        if (ok0) { drow[r * M + b0] = 0.0; drow[N * M + r * M + b0] = 0.0; }
+                        if (ok1) { drow[r * M + b1] = 0.0; drow[N * M + r * M + b1] = 0.0; }
+                        if (lane == 0) drow[2 * N * M + r] = 0.0;
+                    } else {
+                        double *drow = a.out.dbg_obs + (size_t)ru * OW;
+                        for (int c = lane; c < OW; c += 32) drow[c] = 0.0;
+                    }
+                }
+                if (last && a.out.dbg_snr) {
+                    if (ok0) a.out.dbg_snr[ru * M + b0] = 0.0;
+                    if (ok1) a.out.dbg_snr[ru * M + b1] = 0.0;
+                }
+                continue;
+            }
             const double rx = S.sx[r], ry = S.sy[r], rutil = S.su[r];
             const u64 rmask = S.smask[r];
             const double d20 = ok0 ? dist2(bs0, rx, ry) : CUDART_INF;
@@ -424,7 +466,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                                 const int c = S.cnt_obs[b];
                                 drow[b] = (double)(q ? c1 : c0);
                                 drow[M + b] = (double)(q ? dr1 : dr0);
-                                drow[2 * M + b] = (double)c / (double)N;
+                                drow[2 * M + b] = (double)c / (double)NA;
                                 drow[3 * M + b] = (c > 0 ? S.usum[b] / (double)c : 0.0) / DCB_MAX_UTILITY;
                             }
                         }
@@ -450,7 +492,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                     } else if (p.reward == DCB_REWARD_SUM) {
                         // user.py:238-244: UEs sharing any BS with this UE; their PRE-move rewards
                         double s = 0.0;
-                        for (int j = lane; j < N; j += 32)
+                        for (int j = lane; j < NA; j += 32)
                             if (S.smask[j] & rmask) s += S.srb[j];
                         agg = warp_sum(s);
                     } else {

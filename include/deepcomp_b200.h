@@ -154,6 +154,16 @@ void dcb_destroy(dcb_env *env);
  */
 int dcb_reset(dcb_env *env, const int32_t *host_env_ids, int32_t n, void *stream);
 
+/*
+ * Variable UE population (base.py:80-84 `max_ues`, central.py:46-55 zero padding): of the n_ue = max_ues slots of every
+ * env only slots [0, n_active) hold UEs.  Padding slots ignore their actions, keep their state, and read as zeros in
+ * every output (observation rows / entries, reward, lost_conn, curr_dr, utility); per-env quantities (`ues_at_bs` =
+ * |C_b| / num_ue variants.py:296, the central 'avg' reward central.py:65-73, sum_utility) count the UEs present.
+ * Takes effect with the next launch; all envs of the handle share the count (they step in lockstep).  Default: n_ue.
+ */
+int dcb_set_active_ues(dcb_env *env, int32_t n_active);
+int32_t dcb_get_active_ues(const dcb_env *env);
+
 /* get_obs() of the current state (central.py:31-57 / multi_agent.py:32-37) without stepping; reward is not written */
 int dcb_observe(dcb_env *env, const dcb_outputs *out, void *stream);
 

@@ -368,3 +368,51 @@ def test_random_policy_is_uniform_and_reproducible():
     assert torch.equal(r1, r2)
     hist = torch.bincount(r1.flatten().long(), minlength=M + 1).float()
     assert hist.numel() == M + 1 and (hist / hist.sum() - 1 / (M + 1)).abs().max() < 0.01
+
+
+# ------------------------------------------------------------------------------------------------ variable population
+@pytest.mark.parametrize('wide', [False, True], ids=['fused', 'wide'])
+@pytest.mark.parametrize('reward', ['avg', 'sum', 'min'])
+@pytest.mark.parametrize('kind', ['central', 'multi'])
+def test_padding_slots_match_a_smaller_population(kind, reward, wide, monkeypatch):
+    """max_ues > num_ue (base.py:80-84): an env with 9 slots of which 6 hold UEs behaves like a 6-UE env on those slots
+    and reads as zeros on the padding (central.py:46-55), through both kernels."""
+    from deepcomp_b200 import BatchedMobileEnv, env_seeds
+    if wide:
+        monkeypatch.setenv('DCB_FORCE_WIDE', '1')
+    K, slots, act, M, T = 6, 9, 6, 5, 30
+    seeds = env_seeds(77, K, slots)
+    a = BatchedMobileEnv(num_envs=K, kind=kind, seeds=seeds, **_scenario(n_ue=slots, n_bs=M, reward=reward))
+    b = BatchedMobileEnv(num_envs=K, kind=kind, seeds=seeds, **_scenario(n_ue=act, n_bs=M, reward=reward))
+    a.active_ues = act
+    assert a.active_ues == act
+    acts = _actions(T, K, slots, M, seed=3)
+
+    def check(oa, ob, what):
+        oa, ob = oa.cpu().numpy(), ob.cpu().numpy()
+        if kind == 'central':            # connected[slots*M] | dr[slots*M] | utility[slots]
+            ca, da, ua = oa[:, :slots * M], oa[:, slots * M:2 * slots * M], oa[:, 2 * slots * M:]
+            cb, db, ub = ob[:, :act * M], ob[:, act * M:2 * act * M], ob[:, 2 * act * M:]
+            for xa, xb, w in ((ca, cb, M), (da, db, M), (ua, ub, 1)):
+                assert_close(xa[:, :act * w], xb, what, 2e-6, 1e-6)
+                assert not xa[:, act * w:].any(), what
+        else:
+            assert_close(oa[:, :act], ob, what, 2e-6, 1e-6)
+            assert not oa[:, act:].any(), what
+
+    check(a.reset(), b.reset(), 'reset.obs')
+    for t in range(T):
+        oa, ra, _, ia = a.step(acts[t])
+        ob, rb, _, ib = b.step(acts[t][:, :act].contiguous())
+        check(oa, ob, f'obs[{t}]')
+        if kind == 'central':
+            assert_close(ra.cpu().numpy(), rb.cpu().numpy(), f'reward[{t}]', 2e-6, 1e-6)
+        else:
+            assert_close(ra[:, :act].cpu().numpy(), rb.cpu().numpy(), f'reward[{t}]', 2e-6, 1e-5)
+            assert not ra[:, act:].any()
+        assert torch.equal(ia['lost_conn'][:, :act], ib['lost_conn']) and not ia['lost_conn'][:, act:].any()
+        assert_close(ia['sum_utility'].cpu().numpy(), ib['sum_utility'].cpu().numpy(), f'sum_utility[{t}]', 2e-6, 1e-4)
+    sa, sb = a.get_state(), b.get_state()
+    assert_exact(sa['pos'][:, :act], sb['pos'], 'pos')
+    assert_exact(a.mask_matrix(sa['mask'])[:, :act], b.mask_matrix(sb['mask']), 'mask')
+    a.check_errors(); b.check_errors()
