@@ -216,7 +216,9 @@ __device__ __forceinline__ double warp_reduce_env(int lane, const double *v, int
 // [region:kernel.setup]
 // ------------------------------------------------------------------------------------------------ the kernel
 // M32: all connection / in-range masks fit 32 bits (n_bs <= 32) -- halves the integer work on the mask paths
-template <int MAXT, bool M32>
+// PAD: the envs have padding slots (NA < N, variable UE population); the common fixed-population case compiles without
+// the extra compares and the padding branch of the observers
+template <int MAXT, bool M32, bool PAD>
 __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
     using mask_t = typename MaskType<M32>::type;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -258,8 +260,8 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
     const bool in_cta = t < n_env * N;              // a UE slot of one of this CTA's envs
     const int le = in_cta ? t / N : 0;
     const int i = in_cta ? t - le * N : 0;
-    const int NA = p.NA;                            // slots [0, NA) hold UEs, the rest is padding (max_ues > num_ue)
-    const bool valid = in_cta && i < NA;
+    const int NA = PAD ? p.NA : N;                  // slots [0, NA) hold UEs, the rest is padding (max_ues > num_ue)
+    const bool valid = PAD ? (in_cta && i < NA) : in_cta;
     const int k = env0 + le;
     const long long u = (long long)k * N + i;
     const bool central = p.kind == DCB_KIND_CENTRAL;
@@ -748,7 +750,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                         if (last && a.out.dbg_reward) a.out.dbg_reward[u] = agg;
                     }
                 }
-            } else if (in_cta) {
+            } else if (PAD && in_cta) {
                 // ---- padding slot (no UE there: max_ues > num_ue): zeros, as central.py:46-55 pads the observation
                 for (int b = 0; b < M; b++) {
                     row_conn[b] = 0.0f;
@@ -843,8 +845,9 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
 // 65536 registers / (warps rounded up to a multiple of 4 x 32), in the allocation granule of 8 registers per thread
 // (88 registers x 704 threads does not launch: warps are allocated in fours).
 #define DCB_STEP_KERNEL(MAXT, REGS)                                                                         \
-    template <bool M32> __global__ void __maxnreg__(REGS) dcb_step_kernel_##MAXT(const __grid_constant__ StepArgs a) { \
-        dcb_step_body<MAXT, M32>(a);                                                                        \
+    template <bool M32, bool PAD>                                                                           \
+    __global__ void __maxnreg__(REGS) dcb_step_kernel_##MAXT(const __grid_constant__ StepArgs a) {          \
+        dcb_step_body<MAXT, M32, PAD>(a);                                                                   \
     }
 DCB_STEP_KERNEL(256, 80)
 DCB_STEP_KERNEL(512, 128)
@@ -867,37 +870,36 @@ size_t dcb_step_smem_bytes(int kind, int N, int M, int E) { return (size_t)dcb_s
 
 // One instantiation per CTA-size class and mask width: __launch_bounds__ caps the registers at 65536 / MAXT so that a
 // CTA of that size is always resident.
-#define DCB_DISPATCH(threads, m32, EXPR)                                                  \
-    do {                                                                                  \
-        if (m32) {                                                                        \
-            if ((threads) <= 256) { auto kern = dcb_step_kernel_256<true>; EXPR; }       \
-            else if ((threads) <= 512) { auto kern = dcb_step_kernel_512<true>; EXPR; }  \
-            else if ((threads) <= 704) { auto kern = dcb_step_kernel_704<true>; EXPR; }  \
-            else if ((threads) <= 768) { auto kern = dcb_step_kernel_768<true>; EXPR; }  \
-            else { auto kern = dcb_step_kernel_1024<true>; EXPR; }                       \
-        } else {                                                                          \
-            if ((threads) <= 256) { auto kern = dcb_step_kernel_256<false>; EXPR; }      \
-            else if ((threads) <= 512) { auto kern = dcb_step_kernel_512<false>; EXPR; } \
-            else if ((threads) <= 704) { auto kern = dcb_step_kernel_704<false>; EXPR; } \
-            else if ((threads) <= 768) { auto kern = dcb_step_kernel_768<false>; EXPR; } \
-            else { auto kern = dcb_step_kernel_1024<false>; EXPR; }                      \
-        }                                                                                 \
+#define DCB_DISPATCH_T(threads, M32V, PADV, EXPR)                                                   \
+    do {                                                                                            \
+        if ((threads) <= 256) { auto kern = dcb_step_kernel_256<M32V, PADV>; EXPR; }                \
+        else if ((threads) <= 512) { auto kern = dcb_step_kernel_512<M32V, PADV>; EXPR; }           \
+        else if ((threads) <= 704) { auto kern = dcb_step_kernel_704<M32V, PADV>; EXPR; }           \
+        else if ((threads) <= 768) { auto kern = dcb_step_kernel_768<M32V, PADV>; EXPR; }           \
+        else { auto kern = dcb_step_kernel_1024<M32V, PADV>; EXPR; }                                \
+    } while (0)
+#define DCB_DISPATCH(threads, m32, pad, EXPR)                                                       \
+    do {                                                                                            \
+        if (m32) { if (pad) DCB_DISPATCH_T(threads, true, true, EXPR); else DCB_DISPATCH_T(threads, true, false, EXPR); }      \
+        else { if (pad) DCB_DISPATCH_T(threads, false, true, EXPR); else DCB_DISPATCH_T(threads, false, false, EXPR); }        \
     } while (0)
 
 cudaError_t dcb_step_set_smem_limit(int threads, int n_bs, size_t smem) {
     cudaError_t e = cudaSuccess;
-    DCB_DISPATCH(threads, n_bs <= 32, e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int pad = 0; pad < 2 && e == cudaSuccess; pad++)
+        DCB_DISPATCH(threads, n_bs <= 32, pad,
+                     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return e;
 }
 
 int dcb_step_regs_per_thread(int threads, int n_bs) {
     cudaFuncAttributes at;
     cudaError_t e = cudaSuccess;
-    DCB_DISPATCH(threads, n_bs <= 32, e = cudaFuncGetAttributes(&at, kern));
+    DCB_DISPATCH(threads, n_bs <= 32, false, e = cudaFuncGetAttributes(&at, kern));
     return e == cudaSuccess ? at.numRegs : 128;
 }
 
 cudaError_t dcb_launch_step(const StepArgs &a, int threads, int grid, size_t smem, cudaStream_t s) {
-    DCB_DISPATCH(threads, a.p.M <= 32, (kern<<<grid, threads, smem, s>>>(a)));
+    DCB_DISPATCH(threads, a.p.M <= 32, a.p.NA < a.p.N, (kern<<<grid, threads, smem, s>>>(a)));
     return cudaGetLastError();
 }
