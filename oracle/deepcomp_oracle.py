@@ -127,16 +127,32 @@ class _UE:
 class OracleEnv:
     """
     One env instance, restating MobileEnv (+ CentralRelNormEnv / MultiAgentMobileEnv) for the in-scope feature set:
-    RandomWaypoint movement, log utility, fixed UE population, the four sharing models.
+    RandomWaypoint movement, log utility, the four sharing models, fixed or variable UE population (`max_ues`,
+    `ue_arrival`, `new_ue_interval`: base.py:80-84, 433-443, 592-617; per-UE arrays are padded to max_ues).
+
+    Variable population, documented divergence: the reference's reset() re-seeds the UEs of the *current* list by their
+    current list position before it restores the original list (base.py:132-143, 169-189), so after removals an original
+    UE can come back with another UE's seed, and an original UE that was removed keeps drawing from its old streams.
+    This restatement (like the CUDA path) resets to the state a fresh env would have: originals re-seeded by their
+    original index.  The first episode is bit-identical to the reference; later episodes only if no original UE
+    changed its list position.
 
     kind: 'central' (multi_ue/central.py:143-152) or 'multi' (multi_ue/multi_agent.py:6-107)
     """
 
     def __init__(self, kind, n_ue, bs_xy, map_wh, sharing='mixed', velocities='slow', seed=None, reward='avg',
-                 episode_length=100, rand_episodes=False, init_pos=None, pause_duration=2, border_buffer=10):
+                 episode_length=100, rand_episodes=False, init_pos=None, pause_duration=2, border_buffer=10,
+                 max_ues=None, ue_arrival=None, new_ue_interval=None):
         assert kind in ('central', 'multi')
         self.kind = kind
         self.n_ue = n_ue
+        # variable population (base.py:80-84): per-UE arrays have max_ues rows, the UEs present come first
+        self.max_ues = n_ue if max_ues is None else int(max_ues)
+        assert self.max_ues >= n_ue
+        self.ue_arrival = None if ue_arrival is None else {int(t): int(n) for t, n in ue_arrival.items()}
+        self.new_ue_interval = new_ue_interval
+        self.map_rng = random.Random()                          # entities/map.py:30
+        self.glob_rng = random.Random()                         # the `random` module itself (base.py:134, 612)
         self.bs_xy = [(float(x), float(y)) for x, y in bs_xy]
         self.n_bs = len(bs_xy)
         # entities/map.py:20-21
@@ -168,6 +184,7 @@ class OracleEnv:
             ue.x = ue.y = 0.0
             ue.pausing, ue.curr_pause = False, 0
             self.ues.append(ue)
+        self.original_ues = list(self.ues)                      # base.py:52 original_ue_list
         # per-BS connected-UE lists (station.py:18), in connection order
         self.conn_ues = [[] for _ in range(self.n_bs)]
         self.seed(seed)
@@ -177,6 +194,8 @@ class OracleEnv:
     def seed(self, seed=None):
         """single_ue/base.py:132-143 (+ user.py:94-96): UE i (1-based) gets seed+100*i for BOTH of its RNGs"""
         if seed is not None:
+            self.glob_rng.seed(seed)                            # base.py:134 random.seed(seed)
+            self.map_rng.seed(seed)                             # base.py:136 -> map.py:49-50
             offset = 0
             for ue in self.ues:
                 offset += 100
@@ -199,7 +218,8 @@ class OracleEnv:
 
     def reset(self):
         """single_ue/base.py:169-189; user.py:98-116; station.py:106-108"""
-        if not self.rand_episodes:
+        self.ues = list(self.original_ues)                      # base.py:176-182 (see the class docstring: restored
+        if not self.rand_episodes:                              # BEFORE seeding here)
             self.seed(self.env_seed)
         self.time = 0
         for ue in self.ues:
@@ -342,7 +362,7 @@ class OracleEnv:
         else:
             bs_norm_dr = [dr / max_dr for dr in bs_dr]
         utility = [self.utility(ue) / MAX_UTILITY]
-        ues_at_bs = [len(self.conn_ues[b]) / self.n_ue for b in range(self.n_bs)]
+        ues_at_bs = [len(self.conn_ues[b]) / len(self.ues) for b in range(self.n_bs)]    # self.num_ue, variants.py:296
         avg_util = []
         for b in range(self.n_bs):                              # station.py:71-76
             c = self.conn_ues[b]
@@ -357,15 +377,18 @@ class OracleEnv:
         multi (multi_agent.py:32-37, variants.py:255-269): per UE [connected(M) | dr(M) | ues_at_bs(M) | util_at_bs(M) | utility(1)]
         """
         per_ue = [self.get_ue_obs(ue) for ue in self.ues]
+        missing = self.max_ues - len(self.ues)
         if self.kind == 'central':
             out = []
-            for key in ('connected', 'dr', 'utility'):
+            for key, width in (('connected', self.n_bs), ('dr', self.n_bs), ('utility', 1)):
                 for o in per_ue:
                     out.extend(o[key])
+                out.extend([0] * (missing * width))             # central.py:46-55: zeros for the UEs not there
             return np.asarray(out, dtype=np.float64)
-        return np.stack([np.concatenate([np.asarray(o[k], dtype=np.float64)
+        rows = np.stack([np.concatenate([np.asarray(o[k], dtype=np.float64)
                                          for k in ('connected', 'dr', 'ues_at_bs', 'util_at_bs', 'utility')])
                          for o in per_ue])
+        return self._pad(rows)
 
     def step_reward(self, rewards):
         if self.kind == 'central':
@@ -394,9 +417,10 @@ class OracleEnv:
                 elif self.reward_agg == 'sum':
                     # user.py:238-244 builds a *set* of neighbours; its iteration order is hash order in the
                     # reference -- summed in UE-index order here (differences are O(1 ulp))
+                    where = {id(o): j for j, o in enumerate(self.ues)}
                     neigh = set()
                     for b in ue.bs_dr:
-                        neigh.update(o.idx for o in self.conn_ues[b])
+                        neigh.update(where[id(o)] for o in self.conn_ues[b])
                     agg_util = sum([rewards[j] for j in sorted(neigh)])
                 elif self.reward_agg == 'min':
                     mins = []
@@ -407,16 +431,67 @@ class OracleEnv:
                 else:
                     raise NotImplementedError(self.reward_agg)
             out.append(agg_util)
-        return np.asarray(out, dtype=np.float64)
+        return self._pad(np.asarray(out, dtype=np.float64))
+
+    # ------------------------------------------------------------------ variable population
+    def _pad(self, a):
+        a = np.asarray(a)
+        missing = self.max_ues - a.shape[0]
+        if missing <= 0:
+            return a
+        return np.concatenate([a, np.zeros((missing,) + a.shape[1:], dtype=a.dtype)])
+
+    def rand_border_point(self):
+        """entities/map.py:52-65 (min_x = min_y = 0)"""
+        x = self.map_rng.randint(0, self.width)
+        y = self.map_rng.randint(0, self.height)
+        border = self.map_rng.choice(['left', 'right', 'top', 'bottom'])
+        return {'left': (0, y), 'right': (self.width - 1, y), 'top': (x, self.height - 1), 'bottom': (x, 0)}[border]
+
+    def add_new_ue(self):
+        """single_ue/base.py:592-608"""
+        new_id = int(self.ues[-1].id) + 1
+        px, py = self.rand_border_point()
+        ue = _UE()
+        ue.idx = None
+        ue.id = str(new_id)
+        ue.init_x, ue.init_y = px, py
+        ue.init_velocity = 'slow'
+        ue.rng = random.Random()
+        ue.mrng = random.Random()
+        seed = new_id * 100 if self.env_seed is None else self.env_seed + new_id * 100
+        ue.rng.seed(seed)
+        ue.mrng.seed(seed)
+        ue.x, ue.y = float(px), float(py)                       # user.py:111-116 reset(): fixed position, then
+        self._movement_reset(ue)                                # movement.reset()
+        ue.bs_dr = {}
+        ue.ewma_dr = 0
+        self.ues.append(ue)
+
+    def remove_ue(self):
+        """single_ue/base.py:610-617: a uniformly random UE of the list, drawn from the global `random` module"""
+        idx = self.glob_rng.randint(0, len(self.ues) - 1)
+        ue = self.ues.pop(idx)
+        for b in list(ue.bs_dr):                                # user.py:231-236 disconnect_from_all
+            del ue.bs_dr[b]
+            self.conn_ues[b].remove(ue)
 
     def step(self, actions):
-        """single_ue/base.py:413-466. actions: int[N], 0 = noop, b+1 = toggle BS b"""
+        """single_ue/base.py:413-466. actions: int[max_ues], 0 = noop, b+1 = toggle BS b (entry i = i-th UE present)"""
         actions = np.asarray(actions)
-        assert actions.shape == (self.n_ue,) and np.all(actions >= 0) and np.all(actions <= self.n_bs)
-        for ue in self.ues:                                     # base.py:247-282
-            a = int(actions[ue.idx])
+        assert actions.shape == (self.max_ues,) and np.all(actions >= 0) and np.all(actions <= self.n_bs)
+        for pos, ue in enumerate(self.ues):                     # base.py:247-282
+            a = int(actions[pos])
             if a > 0:
                 self.connect_to_bs(ue, a - 1)
+        # base.py:429-443: arrivals / departures after the actions, before the rates and rewards
+        if self.new_ue_interval is not None and self.time > 0 and self.time % self.new_ue_interval == 0:
+            self.add_new_ue()
+        if self.ue_arrival is not None and self.time in self.ue_arrival:
+            n = self.ue_arrival[self.time]
+            for _ in range(abs(n)):
+                self.add_new_ue() if n > 0 else self.remove_ue()
+            assert len(self.ues) <= self.max_ues
         rewards_before = self.update_ue_drs_rewards()
         self.last_lost_conn = [self.move(ue) for ue in self.ues]
         self.update_ue_drs_rewards(update_only=True)
@@ -426,29 +501,32 @@ class OracleEnv:
         obs = self.get_obs()
         reward = self.step_reward(rewards_before)
         out = self.snapshot()
-        out.update(obs=obs, reward=reward, lost_conn=np.asarray(self.last_lost_conn, dtype=np.int32),
+        out.update(obs=obs, reward=reward, lost_conn=self._pad(np.asarray(self.last_lost_conn, dtype=np.int32)),
                    sum_utility=np.float64(sum_utility), time=self.time, done=None)
         return out
 
     # ------------------------------------------------------------------ snapshots (same keys as ref_loader.RefTrace)
     def snapshot(self):
-        n, m = self.n_ue, self.n_bs
+        n, m = len(self.ues), self.n_bs
         mask = np.zeros((n, m), dtype=np.uint8)
         rates = np.zeros((n, m), dtype=np.float64)
         snr = np.zeros((n, m), dtype=np.float64)
-        for ue in self.ues:
+        for j, ue in enumerate(self.ues):
             for b, r in ue.bs_dr.items():
-                mask[ue.idx, b] = 1
-                rates[ue.idx, b] = r
+                mask[j, b] = 1
+                rates[j, b] = r
             for b in range(m):
-                snr[ue.idx, b] = self.snr(b, ue)
-        return dict(
+                snr[j, b] = self.snr(b, ue)
+        d = dict(
             pos=np.array([[ue.x, ue.y] for ue in self.ues], dtype=np.float64), mask=mask, link_rates=rates, snr=snr,
             curr_dr=np.array([float(self.curr_dr(ue)) for ue in self.ues]),
             ewma=np.array([float(ue.ewma_dr) for ue in self.ues]),
             utility=np.array([float(self.utility(ue)) for ue in self.ues]),
             movement=np.array([[ue.velocity, ue.wx, ue.wy, float(ue.pausing), ue.curr_pause] for ue in self.ues],
                               dtype=np.float64))
+        d = {k: self._pad(v) for k, v in d.items()}
+        d['num_ue'] = n
+        return d
 
     def reset_trace(self):
         obs = self.reset()

@@ -16,8 +16,8 @@ from . import ref_loader as rl
 OUT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
 
 STEP_KEYS = ['pos', 'mask', 'link_rates', 'snr', 'curr_dr', 'ewma', 'utility', 'movement', 'obs', 'reward',
-             'lost_conn', 'sum_utility', 'time']
-RESET_KEYS = ['pos', 'mask', 'link_rates', 'snr', 'curr_dr', 'ewma', 'utility', 'movement', 'obs']
+             'lost_conn', 'sum_utility', 'time', 'num_ue']
+RESET_KEYS = ['pos', 'mask', 'link_rates', 'snr', 'curr_dr', 'ewma', 'utility', 'movement', 'obs', 'num_ue']
 
 
 def medium_map(bs_dist=100, border=10):
@@ -53,6 +53,25 @@ def scenarios():
                   sharing='mixed', velocities=['fast', 'fast', 'slow', 7, 'fast', 0], seed=99, reward='avg', steps=150,
                   action_seed=4, episodes=1, init_pos=[(60, 60), ('random', 'random'), (10, 110), (0, 0),
                                                         ('random', 5), (120, 120)]))
+    return S
+
+
+def population_scenarios():
+    """Variable UE population: `ue_arrival` sequences of util/env_setup.py:205-226 and `new_ue_interval`
+    (single_ue/base.py:433-443, 592-617) on envs with `max_ues` > `num_ue` (zero padding, multi_ue/central.py:46-55)."""
+    S = []
+    W, H, gbs = rl.grid_layout(5)
+    base = dict(n_ue=3, bs_xy=gbs, map_wh=(W, H), sharing='mixed', velocities='slow', seed=33, steps=100,
+                action_seed=9, episodes=2)
+    largeupdown = {20: 1, 30: -1, 40: 1, 45: 1, 50: 1, 55: 2, 60: 3, 65: 2, 70: 1, 75: -1, 80: -2, 85: -3, 90: -3, 95: -2}
+    for kind, reward in (('central', 'avg'), ('multi', 'avg'), ('multi', 'sum'), ('central', 'min')):
+        S.append(dict(base, name=f'pop_largeupdown_{kind}_{reward}', kind=kind, reward=reward, max_ues=14,
+                      ue_arrival=largeupdown))
+    S.append(dict(base, name='pop_updown_multi_min', kind='multi', reward='min', max_ues=8,
+                  ue_arrival={10: 1, 15: 1, 20: 1, 40: 1, 50: -1, 60: -1}))
+    S.append(dict(base, name='pop_3up2down_central_sum', kind='central', reward='sum', max_ues=6, n_ue=2,
+                  ue_arrival={10: 3, 30: -2}, sharing='proportional-fair'))
+    S.append(dict(base, name='pop_interval25_multi_avg', kind='multi', reward='avg', max_ues=6, new_ue_interval=25))
     return S
 
 
@@ -104,7 +123,10 @@ def make_reference_agent(sc, env):
 def record(sc):
     env = rl.build_env(sc['kind'], sc['n_ue'], sc['seed'], sc['bs_xy'], sc['map_wh'], sharing=sc['sharing'],
                        velocities=sc['velocities'], reward=sc['reward'], episode_length=sc['steps'],
-                       init_pos=sc.get('init_pos'))
+                       init_pos=sc.get('init_pos'), max_ues=sc.get('max_ues'), ue_arrival=sc.get('ue_arrival'),
+                       new_ue_interval=sc.get('new_ue_interval'))
+    pop = 'max_ues' in sc
+    n_act = sc.get('max_ues', sc['n_ue'])                # length of the action vector (central.py:28)
     tr = rl.RefTrace(env, sc['kind'])
     rng = np.random.default_rng(sc['action_seed'])
     n_bs = len(sc['bs_xy'])
@@ -121,7 +143,7 @@ def record(sc):
             resets[k].append(r[k])
         for t in range(sc['steps']):
             if agent is None:
-                a = rng.integers(0, n_bs + 1, sc['n_ue']).astype(np.int32)
+                a = rng.integers(0, n_bs + 1, n_act).astype(np.int32)
             elif getattr(agent, 'central_agent', False):      # StaticClustering never calls super().__init__()
                 a = np.asarray(agent.compute_action(raw_obs), dtype=np.int32)           # simulation.py:327-349
             else:
@@ -133,6 +155,8 @@ def record(sc):
             # base.py:371-381: done is None; multi_agent.py:97-102: dict of None incl. '__all__'
             if sc['kind'] == 'central':
                 assert s['done'] is None
+            elif pop:
+                assert all(v is None for v in s['done'].values())
             else:
                 assert set(s['done'].keys()) == {str(i + 1) for i in range(sc['n_ue'])} | {'__all__'}
                 assert all(v is None for v in s['done'].values())
@@ -151,6 +175,8 @@ def record(sc):
                 masks[env.bs_list.index(bs)] |= np.uint64(1) << np.uint64(env.bs_list.index(m))
         out['cluster_masks'] = masks
     cfg = {k: v for k, v in sc.items()}
+    if cfg.get('ue_arrival') is not None:
+        cfg['ue_arrival'] = {str(t): int(n) for t, n in cfg['ue_arrival'].items()}
     cfg['bs_xy'] = [[float(x), float(y)] for x, y in sc['bs_xy']]
     cfg['map_wh'] = [float(sc['map_wh'][0]), float(sc['map_wh'][1])]
     out['config'] = np.array(json.dumps(cfg))
@@ -195,7 +221,7 @@ def main():
     only = sys.argv[1] if len(sys.argv) > 1 else ''     # optional name prefix: regenerate a subset only
     if not only:
         np.savez_compressed(os.path.join(OUT_DIR, 'anchors.npz'), **anchors())
-    for sc in scenarios() + policy_scenarios():
+    for sc in scenarios() + policy_scenarios() + population_scenarios():
         if not sc['name'].startswith(only):
             continue
         data = record(sc)

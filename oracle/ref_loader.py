@@ -55,13 +55,15 @@ def grid_layout(n_bs, pitch=100, border=10):
 
 
 def build_env(kind, n_ue, seed, bs_xy, map_wh, sharing='mixed', velocities='slow', reward='avg',
-              episode_length=100, rand_episodes=False, init_pos=None):
+              episode_length=100, rand_episodes=False, init_pos=None, max_ues=None, ue_arrival=None,
+              new_ue_interval=None):
     """
     Build a reference env.
 
     :param kind: 'central' (CentralRelNormEnv) or 'multi' (MultiAgentMobileEnv)
     :param velocities: 'slow' | 'fast' | number, or a list of those per UE
     :param init_pos: None (all 'random') or list of (x, y) per UE with numbers or 'random'
+    :param max_ues, ue_arrival, new_ue_interval: variable UE population (base.py:80-84,433-443; env_setup.py:205-226)
     """
     R = _import_reference()
     m = R['Map'](width=map_wh[0], height=map_wh[1])
@@ -77,8 +79,9 @@ def build_env(kind, n_ue, seed, bs_xy, map_wh, sharing='mixed', velocities='slow
                                  movement=R['RandomWaypoint'](m, velocity=velocities[i]), util_func='log'))
     env_config = {
         'episode_length': episode_length, 'seed': seed, 'map': m, 'bs_list': bs_list, 'ue_list': ue_list,
-        'rand_episodes': rand_episodes, 'new_ue_interval': None, 'reward': reward, 'max_ues': None,
-        'ue_arrival': None, 'log_metrics': True, 'dashboard': False, 'ue_details': False,
+        'rand_episodes': rand_episodes, 'new_ue_interval': new_ue_interval, 'reward': reward, 'max_ues': max_ues,
+        'ue_arrival': None if ue_arrival is None else {int(t): int(n) for t, n in ue_arrival.items()},
+        'log_metrics': True, 'dashboard': False, 'ue_details': False,
     }
     cls = R['CentralRelNormEnv'] if kind == 'central' else R['MultiAgentMobileEnv']
     return cls(env_config)
@@ -138,22 +141,33 @@ class RefTrace:
         for ue in e.ue_list:
             o = obs[ue.id]
             rows.append(np.concatenate([np.asarray(o[k], dtype=np.float64).ravel() for k in sorted(o.keys())]))
-        return np.stack(rows)
+        return self._pad(np.stack(rows))
 
     def flat_reward(self, reward):
         if self.kind == 'central':
             return np.float64(reward)
-        return np.array([float(reward[ue.id]) for ue in self.env.ue_list], dtype=np.float64)
+        return self._pad(np.array([float(reward[ue.id]) for ue in self.env.ue_list], dtype=np.float64))
 
     def to_action(self, a):
         """a: int array [N] -> the action object the env class expects"""
         if self.kind == 'central':
-            return np.asarray(a, dtype=np.int64)
+            return np.asarray(a, dtype=np.int64)          # length max_ues; entries beyond the UEs present are ignored
         return {ue.id: int(a[i]) for i, ue in enumerate(self.env.ue_list)}
 
+    def _pad(self, a):
+        """rows of the UEs present (list order) first, zero rows up to max_ues (variable population)"""
+        a = np.asarray(a)
+        missing = self.env.max_ues - a.shape[0]
+        if missing <= 0:
+            return a
+        return np.concatenate([a, np.zeros((missing,) + a.shape[1:], dtype=a.dtype)])
+
     def snapshot(self):
-        return dict(pos=self.positions(), mask=self.mask(), link_rates=self.link_rates(), snr=self.snr(),
-                    curr_dr=self.curr_dr(), ewma=self.ewma(), utility=self.utility(), movement=self.movement())
+        d = dict(pos=self.positions(), mask=self.mask(), link_rates=self.link_rates(), snr=self.snr(),
+                 curr_dr=self.curr_dr(), ewma=self.ewma(), utility=self.utility(), movement=self.movement())
+        d = {k: self._pad(v) for k, v in d.items()}
+        d['num_ue'] = len(self.env.ue_list)
+        return d
 
     def reset(self):
         obs = self.env.reset()
@@ -167,7 +181,7 @@ class RefTrace:
         out = self.snapshot()
         out['obs'] = self.flat_obs(obs)
         out['reward'] = self.flat_reward(reward)
-        out['lost_conn'] = np.array(self._lost, dtype=np.int32)
+        out['lost_conn'] = self._pad(np.array(self._lost, dtype=np.int32))
         out['done'] = done
         out['info'] = info
         if self.kind == 'multi':

@@ -19,15 +19,32 @@ RTOL = 1e-9
 ATOL = 1e-9
 
 
-def golden_names():
+def _names():
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz'))
                   if not p.endswith('anchors.npz'))
+
+
+def golden_names():
+    """fixed-population traces (every test that replays a trace step by step)"""
+    return [n for n in _names() if not n.startswith('pop_')]
+
+
+def population_names():
+    """variable-population traces: ue_arrival / new_ue_interval on envs with max_ues > num_ue, arrays padded to max_ues"""
+    return [n for n in _names() if n.startswith('pop_')]
 
 
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + '.npz'), allow_pickle=False)
     cfg = json.loads(str(z['config']))
     return cfg, z
+
+
+def population_kwargs(cfg):
+    """extra constructor arguments of a variable-population trace (oracle and CUDA env take the same ones)"""
+    arr = cfg.get('ue_arrival')
+    return dict(max_ues=cfg['max_ues'], ue_arrival=None if arr is None else {int(t): int(n) for t, n in arr.items()},
+                new_ue_interval=cfg.get('new_ue_interval'))
 
 
 def oracle_kwargs(cfg):
@@ -60,9 +77,9 @@ def assert_exact(a, b, what):
                              f"got {a[tuple(bad[0])]!r} want {b[tuple(bad[0])]!r}")
 
 
-def check_against_golden(env, cfg, z, exact_floats=False, skip_float=()):
+def check_against_golden(env, cfg, z, exact_floats=False, skip_float=(), episodes=None):
     """Replay the golden action sequence through `env` (reset_trace()/step()) and compare every recorded array."""
-    steps, eps = cfg['steps'], cfg['episodes']
+    steps, eps = cfg['steps'], cfg['episodes'] if episodes is None else episodes
     t = 0
     for ep in range(eps):
         r = env.reset_trace()
