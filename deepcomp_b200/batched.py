@@ -44,7 +44,14 @@ class BatchedMobileEnv:
 
     def __init__(self, num_envs, n_ue, bs_xy, map_wh, kind='multi', sharing='mixed', velocities='slow', seed=0,
                  seeds=None, reward='avg', episode_length=100, rand_episodes=False, auto_reset=False, init_pos=None,
-                 pause_duration=2, border_buffer=10, device=None, first_env=0):
+                 pause_duration=2, border_buffer=10, device=None, first_env=0, max_ues=None, ue_arrival=None,
+                 new_ue_interval=None):
+        """
+        Variable UE population (reference env_config keys of the same names, base.py:80-84, 429-443): `n_ue` UEs at
+        reset, `max_ues` slots per env (every per-UE array has max_ues rows; rows of UEs that are not there read as
+        zeros, central.py:46-55), `ue_arrival` = {time: +n arrivals / -n departures} (env_setup.py:205-226),
+        `new_ue_interval` = one arrival every so many steps.  All envs of the batch step in lockstep.
+        """
         if not torch.cuda.is_available():
             raise RuntimeError("deepcomp_b200 needs a CUDA device: the env step is a CUDA kernel and has no CPU "
                                "fallback")
@@ -57,6 +64,22 @@ class BatchedMobileEnv:
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         if self.device.index is None:
             self.device = torch.device('cuda', torch.cuda.current_device())
+        self.num_ue_initial = int(n_ue)
+        if max_ues is not None and int(max_ues) < int(n_ue):
+            raise ValueError(f"max_ues = {max_ues} < n_ue = {n_ue}")             # base.py:84
+        n_slots = int(n_ue) if max_ues is None else int(max_ues)
+        self.ue_arrival = None if ue_arrival is None else {int(t): int(n) for t, n in dict(ue_arrival).items()}
+        self.new_ue_interval = None if new_ue_interval is None else int(new_ue_interval)
+        self._dynamic = self.ue_arrival is not None or self.new_ue_interval is not None
+        if self._dynamic and (rand_episodes or auto_reset):
+            raise NotImplementedError("variable UE population needs rand_episodes=False and auto_reset=False")
+        self._t = 0                                          # MobileEnv.time of the lockstep batch (events key on it)
+        if not isinstance(velocities, (list, tuple, np.ndarray)):
+            velocities = [velocities] * int(n_ue)
+        velocities = list(velocities) + ['slow'] * (n_slots - len(velocities))   # add_new_ue(velocity='slow')
+        if init_pos is not None:
+            init_pos = list(init_pos) + [('random', 'random')] * (n_slots - len(init_pos))
+        n_ue = n_slots                                       # from here on n_ue counts SLOTS (= max_ues)
         self.num_envs, self.n_ue, self.kind, self.reward_agg = int(num_envs), int(n_ue), kind, reward
         bs = np.ascontiguousarray(np.asarray(bs_xy, dtype=np.float64).reshape(-1, 2))
         self.n_bs = bs.shape[0]
@@ -84,7 +107,10 @@ class BatchedMobileEnv:
                 if py != 'random':
                     ixy[i, 1] = float(py)
         if seeds is None:
-            seeds = env_seeds(seed, self.num_envs, self.n_ue, first_env)
+            # arriving UEs get ids (and seeds 100 * id apart) beyond the slots: keep the env seeds further apart
+            n_ids = self.n_ue + (sum(max(n, 0) for n in self.ue_arrival.values()) if self.ue_arrival else 0) + \
+                (self.episode_length // self.new_ue_interval if self.new_ue_interval else 0)
+            seeds = env_seeds(seed, self.num_envs, n_ids, first_env)
         seeds = np.ascontiguousarray(np.asarray(seeds, dtype=np.int64))
         if seeds.shape != (self.num_envs,):
             raise ValueError("need one seed per env")
@@ -106,6 +132,8 @@ class BatchedMobileEnv:
         self.obs_shape = (self.obs_size,) if kind == 'central' else (self.n_ue, 4 * self.n_bs + 1)
         self.reward_shape = () if kind == 'central' else (self.n_ue,)
         self._pinned = None
+        if self.num_ue_initial != self.n_ue:
+            self.active_ues = self.num_ue_initial
 
     # ------------------------------------------------------------------ plumbing
     def close(self):
@@ -209,8 +237,27 @@ class BatchedMobileEnv:
         return o, t
 
     # ------------------------------------------------------------------ gym-like batched API
+    def _population_events(self, t, actions):
+        """base.py:429-443 at MobileEnv.time == t: arrivals / departures between the actions and the rate update.
+        Returns the action tensor to step with (a copy, edited on the device, if something happened)."""
+        ev = []
+        if self.new_ue_interval is not None and t > 0 and t % self.new_ue_interval == 0:
+            ev.append((1, 0))
+        if self.ue_arrival is not None and t in self.ue_arrival:
+            n = self.ue_arrival[t]
+            ev.append((n, 0) if n > 0 else (0, -n))
+        if ev:
+            actions = actions.clone()
+            for n_add, n_rem in ev:
+                check(self._L.dcb_population_event(self._h, n_add, n_rem, ctypes.c_void_p(actions.data_ptr()),
+                                                   self._stream()))
+        return actions
+
     def reset(self, env_ids=None, debug=False):
         """MobileEnv.reset (base.py:169-189) for all envs or the listed ones; returns the observation of ALL envs."""
+        if self._dynamic and env_ids is not None:
+            raise NotImplementedError("a batch with a variable UE population resets as a whole (lockstep)")
+        self._t = 0
         if env_ids is None:
             check(self._L.dcb_reset(self._h, None, 0, self._stream()))
         else:
@@ -232,6 +279,9 @@ class BatchedMobileEnv:
     def step(self, actions, info=True, debug=False):
         """MobileEnv.step (base.py:413-466) for all K envs.  actions: int32 [K, N] on the device."""
         self._check_actions(actions)
+        if self._dynamic:
+            actions = self._population_events(self._t, actions)
+        self._t += 1
         o, t = self._outputs(None, info=info or debug, debug=debug)
         check(self._L.dcb_step(self._h, ctypes.c_void_p(actions.data_ptr()), ctypes.byref(o), self._stream()))
         if debug:
@@ -253,8 +303,39 @@ class BatchedMobileEnv:
             t['_struct'] = o
         else:
             o, t = out['_struct'], out
+        if self._dynamic:
+            # arrivals / departures cut the fragment: one launch per stretch of steps without an event
+            t0 = 0
+            while t0 < T:
+                a0 = self._population_events(self._t, actions[t0])
+                t1 = t0 + 1
+                while t1 < T and not self._has_event(self._t + (t1 - t0)):
+                    t1 += 1
+                acts = actions[t0:t1] if a0.data_ptr() == actions[t0].data_ptr() else \
+                    torch.cat([a0[None], actions[t0 + 1:t1]]).contiguous()
+                check(self._L.dcb_step_many(self._h, ctypes.c_void_p(acts.data_ptr()), t1 - t0,
+                                            ctypes.byref(self._offset_outputs(o, t0)), self._stream()))
+                self._t += t1 - t0
+                t0 = t1
+            return t
+        self._t += T
         check(self._L.dcb_step_many(self._h, ctypes.c_void_p(actions.data_ptr()), T, ctypes.byref(o), self._stream()))
         return t
+
+    def _has_event(self, t):
+        return (self.new_ue_interval is not None and t > 0 and t % self.new_ue_interval == 0) or \
+            (self.ue_arrival is not None and self.ue_arrival.get(t, 0) != 0)
+
+    @staticmethod
+    def _offset_outputs(o, t0):
+        """the outputs struct of a [T, ...] buffer set, advanced to step t0"""
+        q = DcbOutputs()
+        ctypes.memmove(ctypes.byref(q), ctypes.byref(o), ctypes.sizeof(DcbOutputs))
+        for name, size in (('obs', 4), ('reward', 4), ('lost_conn', 1), ('curr_dr', 4), ('utility', 4), ('sum_utility', 4)):
+            ptr = getattr(q, name)
+            if ptr:
+                setattr(q, name, ptr + t0 * getattr(q, name + '_stride') * size)
+        return q
 
     def rollout(self, policy, T, obs=True, info=False, out=None, return_actions=True):
         """
@@ -263,6 +344,9 @@ class BatchedMobileEnv:
         Returns the same dict as step_many plus 'actions' int32 [T, K, N] (the actions the policy took).
         """
         from .agents import POLICY_KIND
+        if self._dynamic:
+            raise NotImplementedError("device-side policies with a variable UE population")
+        self._t += T
         spec = policy.device_policy(self) if hasattr(policy, 'device_policy') else dict(policy)
         pol = DcbPolicy(kind=POLICY_KIND[spec['kind']], noop_interval=int(spec.get('noop_interval', 0)),
                         epsilon=float(spec.get('epsilon', 0.0)), seed=int(spec.get('seed', 0)))
@@ -309,6 +393,9 @@ class BatchedMobileEnv:
         stream synchronise -- all inside the C-ABI call dcb_step_host.  `actions`: None (already written into
         pinned_buffers()['actions']) or an int array [K, N].
         """
+        if self._dynamic:
+            raise NotImplementedError("step_host with a variable UE population (use step with device tensors)")
+        self._t += 1
         pb = self.pinned_buffers()
         if actions is not None:
             pb['actions'].copy_(torch.as_tensor(np.asarray(actions, dtype=np.int32)))

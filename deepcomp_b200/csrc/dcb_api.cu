@@ -83,6 +83,11 @@ struct dcb_env {
     double *d_ewma = nullptr;
     int *d_time = nullptr, *d_err = nullptr;
     uint32_t *d_table = nullptr, *d_pos_skip = nullptr, *d_mv_skip = nullptr;
+    // variable UE population (dcb_population_event)
+    int32_t *d_uid = nullptr;
+    uint32_t *d_map_draws = nullptr, *d_glob_draws = nullptr;
+    int na_reset = 0;        // UEs present after a reset (the original ue_list, base.py:176-182)
+    bool pop_dirty = false;  // slots were shifted / filled since the last reset: the next reset regenerates the tables
     int32_t *d_env_ids = nullptr;
     int env_ids_cap = 0;
     // scripted policies (dcb_rollout)
@@ -198,6 +203,7 @@ void dcb_destroy(dcb_env *env) {
     cudaFree(env->d_mask); cudaFree(env->d_ewma); cudaFree(env->d_time); cudaFree(env->d_err);
     cudaFree(env->d_table); cudaFree(env->d_pos_skip); cudaFree(env->d_mv_skip); cudaFree(env->d_env_ids);
     cudaFree(env->d_cluster); cudaFree(env->d_fixed);
+    cudaFree(env->d_uid); cudaFree(env->d_map_draws); cudaFree(env->d_glob_draws);
     cudaFree(env->d_h_actions); cudaFree(env->d_h_obs); cudaFree(env->d_h_reward); cudaFree(env->d_h_lost);
     delete env;
 }
@@ -330,6 +336,7 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     ALLOC(env->d_seeds, K); ALLOC(env->d_pos, KN); ALLOC(env->d_init_pos, KN); ALLOC(env->d_mv, KN);
     ALLOC(env->d_mask, KN); ALLOC(env->d_ewma, KN); ALLOC(env->d_time, K); ALLOC(env->d_err, 1);
     ALLOC(env->d_table, KN * D);
+    ALLOC(env->d_uid, KN); ALLOC(env->d_map_draws, K); ALLOC(env->d_glob_draws, K);
     if (cfg->rand_episodes) { ALLOC(env->d_pos_skip, K); ALLOC(env->d_mv_skip, KN); }
 #undef ALLOC
     CU(cudaMemcpy(env->d_bs_xy, cfg->host_bs_xy, sizeof(double) * 2 * M, cudaMemcpyHostToDevice));
@@ -338,6 +345,10 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     CU(cudaMemcpy(env->d_init_xy, cfg->host_init_xy, sizeof(double) * 2 * N, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(env->d_seeds, cfg->host_seeds, sizeof(long long) * K, cudaMemcpyHostToDevice));
     CU(cudaMemset(env->d_err, 0, sizeof(int)));
+    CU(cudaMemset(env->d_map_draws, 0, sizeof(uint32_t) * K));
+    CU(cudaMemset(env->d_glob_draws, 0, sizeof(uint32_t) * K));
+    CU(dcb_launch_iota_uid(env->d_uid, K, N, 0));
+    env->na_reset = N;
     if (cfg->rand_episodes) {
         CU(cudaMemset(env->d_pos_skip, 0, sizeof(uint32_t) * K));
         CU(cudaMemset(env->d_mv_skip, 0, sizeof(uint32_t) * KN));
@@ -412,6 +423,25 @@ int dcb_reset(dcb_env *env, const int32_t *host_env_ids, int32_t n, void *stream
         CU(cudaMemcpyAsync(env->d_env_ids, host_env_ids, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
         d_ids = env->d_env_ids;
     }
+    if (env->pop_dirty) {
+        // base.py:176-182: back to the original ue_list; slots were shifted / overwritten by arrivals and departures, so
+        // the tables of the original UEs are drawn again (documented divergence: the originals are re-seeded by their
+        // ORIGINAL index), and map.rng / the global `random` module restart with the env seed (base.py:134-136)
+        if (host_env_ids) return fail(DCB_ERR_UNSUPPORTED, "partial reset of a batch whose UE population changed");
+        GenArgs g;
+        g.K = p.K; g.N = p.N; g.D = p.D; g.W = env->cfg.map_width; g.H = env->cfg.map_height;
+        g.border_buffer = env->cfg.border_buffer;
+        g.seeds = env->d_seeds; g.vel_spec = env->d_vel; g.init_xy = env->d_init_xy;
+        g.pos_skip = nullptr; g.mv_skip = nullptr; g.env_ids = nullptr; g.n_ids = 0;
+        g.init_pos = env->d_init_pos; g.table = env->d_table;
+        CU(dcb_launch_generate(g, s));
+        CU(dcb_launch_iota_uid(env->d_uid, p.K, p.N, s));
+        CU(cudaMemsetAsync(env->d_map_draws, 0, sizeof(uint32_t) * p.K, s));
+        CU(cudaMemsetAsync(env->d_glob_draws, 0, sizeof(uint32_t) * p.K, s));
+        env->launches += 2;
+        env->pop_dirty = false;
+    }
+    env->p.NA = env->na_reset;
     if (env->cfg.rand_episodes) {
         // base.py:171-173: no re-seed -> continue every UE's stream where the last episode left it
         CU(dcb_launch_advance_skip(p.K, p.N, d_ids, n, env->d_mv, env->d_mv_skip, env->d_pos_skip, s));
@@ -439,10 +469,44 @@ int dcb_set_active_ues(dcb_env *env, int32_t n_active) {
     if (n_active < 1 || n_active > env->p.N)
         return fail(DCB_ERR_INVALID_ARG, "n_active = %d outside [1, n_ue = %d]", n_active, env->p.N);
     env->p.NA = n_active;
+    env->na_reset = n_active;      // the original ue_list: what dcb_reset goes back to after arrivals / departures
     return DCB_OK;
 }
 
 int32_t dcb_get_active_ues(const dcb_env *env) { return env ? env->p.NA : 0; }
+
+int dcb_population_event(dcb_env *env, int32_t n_add, int32_t n_remove, int32_t *d_actions, void *stream) {
+    if (!env) return fail(DCB_ERR_INVALID_ARG, "null handle");
+    if (n_add < 0 || n_remove < 0) return fail(DCB_ERR_INVALID_ARG, "negative UE count");
+    if (n_add == 0 && n_remove == 0) return DCB_OK;
+    const DevParams &p = env->p;
+    if (p.NA - n_remove < 1) return fail(DCB_ERR_INVALID_ARG, "cannot remove %d of %d UEs", n_remove, p.NA);
+    if (p.NA - n_remove + n_add > p.N)
+        return fail(DCB_ERR_INVALID_ARG, "%d UEs would exceed max_ues = %d (base.py:84)", p.NA - n_remove + n_add, p.N);
+    if (env->cfg.rand_episodes)
+        return fail(DCB_ERR_UNSUPPORTED, "variable UE population needs rand_episodes = 0 (streams restart at reset)");
+    DeviceGuard guard(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    // slots change owners: every slot must describe the same kind of UE (arrivals are 'slow', base.py:592)
+    std::vector<double> vel(p.N);
+    CU(cudaMemcpyAsync(vel.data(), env->d_vel, sizeof(double) * p.N, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (int i = 0; i < p.N; i++)
+        if (vel[i] != DCB_VELOCITY_SLOW)
+            return fail(DCB_ERR_UNSUPPORTED, "variable UE population needs 'slow' UEs in every slot (slot %d is not)", i);
+    PopArgs a;
+    a.K = p.K; a.N = p.N; a.D = p.D; a.W = env->cfg.map_width; a.H = env->cfg.map_height;
+    a.border_buffer = env->cfg.border_buffer;
+    a.NA = p.NA; a.n_add = n_add; a.n_rem = n_remove;
+    a.seeds = env->d_seeds; a.map_draws = env->d_map_draws; a.glob_draws = env->d_glob_draws; a.uid = env->d_uid;
+    a.pos = env->d_pos; a.mv = env->d_mv; a.mask = env->d_mask; a.ewma = env->d_ewma; a.table = env->d_table;
+    a.actions = d_actions;
+    CU(dcb_launch_population(a, s));
+    env->launches++;
+    env->p.NA = p.NA - n_remove + n_add;
+    env->pop_dirty = true;
+    return DCB_OK;
+}
 
 int dcb_observe(dcb_env *env, const dcb_outputs *out, void *stream) {
     if (!env) return fail(DCB_ERR_INVALID_ARG, "null handle");

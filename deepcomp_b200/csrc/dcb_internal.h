@@ -204,7 +204,26 @@ struct ResetArgs {
     uint32_t *pos_skip;   // rand_episodes: bumped once per reset env, else NULL
 };
 
+// Arrival / departure of UEs (single_ue/base.py:433-443, 592-617), one thread per env
+struct PopArgs {
+    int K, N, D, W, H, border_buffer;
+    int NA;                     // UEs present before the event (the same in every env)
+    int n_add, n_rem;           // removals first, then arrivals
+    const long long *seeds;     // [K] env seeds: map.rng and the global `random` module are both seeded with them
+    uint32_t *map_draws;        // [K] 32-bit outputs consumed from map.rng since the last seeding
+    uint32_t *glob_draws;       // [K] ... from the global `random` module
+    int32_t *uid;               // [K*N] UE id per slot (ids of arriving UEs continue after the last UE's id)
+    double2 *pos;
+    uint2 *mv;
+    unsigned long long *mask;
+    double *ewma;
+    uint32_t *table;            // [K*N][D]
+    int32_t *actions;           // [K][N] this step's actions (follow their UEs when slots shift) or NULL
+};
+
 cudaError_t dcb_launch_generate(const GenArgs &a, cudaStream_t s);
+cudaError_t dcb_launch_population(const PopArgs &a, cudaStream_t s);
+cudaError_t dcb_launch_iota_uid(int32_t *uid, int K, int N, cudaStream_t s);
 cudaError_t dcb_launch_reset(const ResetArgs &a, cudaStream_t s);
 cudaError_t dcb_launch_advance_skip(int K, int N, const int32_t *env_ids, int n_ids, const uint2 *mv,
                                     uint32_t *mv_skip, const uint32_t *pos_skip, cudaStream_t s);

@@ -18,6 +18,7 @@ namespace {
 struct MT {
     uint32_t mt[624];
     int idx;
+    uint32_t drawn;     // 32-bit outputs produced since mt_seed
 };
 
 __device__ void mt_seed(MT &g, long long seed) {
@@ -41,6 +42,7 @@ __device__ void mt_seed(MT &g, long long seed) {
     }
     g.mt[0] = 0x80000000u;
     g.idx = 624;
+    g.drawn = 0u;
 }
 
 __device__ uint32_t mt_next(MT &g) {
@@ -60,6 +62,7 @@ __device__ uint32_t mt_next(MT &g) {
         g.idx = 0;
     }
     uint32_t y = g.mt[g.idx++];
+    g.drawn++;
     y ^= (y >> 11);
     y ^= (y << 7) & 0x9d2c5680u;
     y ^= (y << 15) & 0xefc60000u;
@@ -153,7 +156,88 @@ __global__ void __launch_bounds__(256) dcb_advance_skip_kernel(int K, int N, con
     if (pos_skip[k] >= 1u) mv_skip[u] += mv[u].y >> 16;
 }
 
+// ---------------------------------------------------------------------------------------------- variable population
+// add_new_ue / remove_ue (single_ue/base.py:592-617) for every env of a lockstep batch.  The two generators involved --
+// Map.rng (entities/map.py:30,49-65: rand_border_point) and the global `random` module (base.py:134,612) -- are both
+// seeded with the env seed at reset; their position is kept as "outputs consumed so far" and the stream is re-derived
+// from the seed for each event (events are rare: a handful per episode).
+__global__ void __launch_bounds__(64) dcb_population_kernel(PopArgs a) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.K) return;
+    const long long base = (long long)k * a.N;
+    int na = a.NA;
+    MT g;
+    // ---- remove_ue (base.py:610-617): idx = random.randint(0, num_ue - 1); ue_list.pop(idx): later UEs move up one
+    // list position -- and so does everything indexed by list position, including this step's actions (they were
+    // assigned by position BEFORE the removal, base.py:426-427 / central.py:59-63)
+    for (int r = 0; r < a.n_rem; r++) {
+        mt_seed(g, a.seeds[k]);
+        for (uint32_t s = a.glob_draws[k]; s; s--) mt_next(g);
+        const int idx = mt_randint(g, 0, na - 1);
+        a.glob_draws[k] = g.drawn;
+        for (int j = idx; j < na - 1; j++) {
+            const long long d = base + j, s = d + 1;
+            a.pos[d] = a.pos[s]; a.mv[d] = a.mv[s]; a.mask[d] = a.mask[s]; a.ewma[d] = a.ewma[s]; a.uid[d] = a.uid[s];
+            for (int e = 0; e < a.D; e++) a.table[d * a.D + e] = a.table[s * a.D + e];
+            if (a.actions) a.actions[d] = a.actions[s];
+        }
+        na--;
+        a.mask[base + na] = 0ull;
+        if (a.actions) a.actions[base + na] = 0;
+    }
+    // ---- add_new_ue (base.py:592-608): id = last id + 1, position = map.rand_border_point(), 'slow' RandomWaypoint,
+    // both of the UE's generators seeded with env_seed + 100 * id, then User.reset() (fixed position -> no draw from
+    // User.rng; movement.reset() -> velocity, waypoint).  The UE is not in the action dict of this step.
+    for (int r = 0; r < a.n_add; r++) {
+        mt_seed(g, a.seeds[k]);
+        for (uint32_t s = a.map_draws[k]; s; s--) mt_next(g);
+        const int x = mt_randint(g, 0, a.W);                    // map.py:54-55 (min_x = min_y = 0)
+        const int y = mt_randint(g, 0, a.H);
+        const int side = mt_randint(g, 0, 3);                   // rng.choice(['left', 'right', 'top', 'bottom'])
+        a.map_draws[k] = g.drawn;
+        double px, py;
+        if (side == 0) { px = 0.0; py = (double)y; }
+        else if (side == 1) { px = (double)(a.W - 1); py = (double)y; }
+        else if (side == 2) { px = (double)x; py = (double)(a.H - 1); }
+        else { px = (double)x; py = 0.0; }
+        const long long d = base + na;
+        const int new_id = a.uid[d - 1] + 1;
+        mt_seed(g, a.seeds[k] + 100ll * new_id);
+        uint32_t *row = a.table + d * a.D;
+        for (int e = 0; e < a.D; e++) {
+            const int v = mt_randint(g, 1, 3);                  // add_new_ue(velocity='slow'), movement.py:112-113
+            const int wx = mt_randint(g, a.border_buffer, a.W - a.border_buffer);
+            const int wy = mt_randint(g, a.border_buffer, a.H - a.border_buffer);
+            row[e] = (uint32_t)wx | ((uint32_t)wy << 14) | ((uint32_t)v << 28);
+        }
+        const uint32_t e0 = row[0];
+        a.pos[d] = make_double2(px, py);
+        a.mv[d] = make_uint2((e0 & 0x3fffu) | (((e0 >> 14) & 0x3fffu) << 16), (e0 >> 28) | (1u << 16));
+        a.mask[d] = 0ull;
+        a.ewma[d] = 0.0;
+        a.uid[d] = new_id;
+        if (a.actions) a.actions[d] = 0;
+        na++;
+    }
+}
+
+__global__ void dcb_iota_uid_kernel(int32_t *uid, long long n, int N) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) uid[t] = (int32_t)(t % N) + 1;                   // ids "1".."N" (env_setup.py:148-160)
+}
+
 }  // namespace
+
+cudaError_t dcb_launch_population(const PopArgs &a, cudaStream_t s) {
+    dcb_population_kernel<<<(a.K + 63) / 64, 64, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t dcb_launch_iota_uid(int32_t *uid, int K, int N, cudaStream_t s) {
+    const long long n = (long long)K * N;
+    dcb_iota_uid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(uid, n, N);
+    return cudaGetLastError();
+}
 
 cudaError_t dcb_launch_advance_skip(int K, int N, const int32_t *env_ids, int n_ids, const uint2 *mv,
                                     uint32_t *mv_skip, const uint32_t *pos_skip, cudaStream_t s) {

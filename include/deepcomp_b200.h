@@ -160,9 +160,22 @@ int dcb_reset(dcb_env *env, const int32_t *host_env_ids, int32_t n, void *stream
  * every output (observation rows / entries, reward, lost_conn, curr_dr, utility); per-env quantities (`ues_at_bs` =
  * |C_b| / num_ue variants.py:296, the central 'avg' reward central.py:65-73, sum_utility) count the UEs present.
  * Takes effect with the next launch; all envs of the handle share the count (they step in lockstep).  Default: n_ue.
+ * This is the ORIGINAL population (base.py:52 original_ue_list): dcb_reset goes back to it after arrivals / departures.
  */
 int dcb_set_active_ues(dcb_env *env, int32_t n_active);
 int32_t dcb_get_active_ues(const dcb_env *env);
+
+/*
+ * Arrival / departure of UEs between the application of a step's actions and its rate update (base.py:429-443):
+ * n_remove times `remove_ue` (base.py:610-617: a uniformly random UE, drawn from the global `random` module that
+ * MobileEnv.seed seeded with the env seed; later UEs move up one slot), then n_add times `add_new_ue` (base.py:592-608:
+ * id = last id + 1, position = Map.rand_border_point map.py:52-65, 'slow' RandomWaypoint seeded with env_seed + 100 id).
+ * Call it right BEFORE the dcb_step of the step the event belongs to, with that step's device action buffer
+ * (int32 [K][n_ue], edited in place: actions follow their UEs, arriving UEs get a no-op; may be NULL).  Every env of
+ * the handle sees the same event (lockstep batch); needs rand_episodes = 0 and 'slow' UEs in every slot.  dcb_reset
+ * restores the original population.
+ */
+int dcb_population_event(dcb_env *env, int32_t n_add, int32_t n_remove, int32_t *d_actions, void *stream);
 
 /* get_obs() of the current state (central.py:31-57 / multi_agent.py:32-37) without stepping; reward is not written */
 int dcb_observe(dcb_env *env, const dcb_outputs *out, void *stream);

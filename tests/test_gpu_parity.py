@@ -5,7 +5,8 @@ import torch
 
 from oracle import c_oracle
 
-from helpers import (assert_close, assert_exact, golden_names, load_golden, oracle_kwargs)
+from helpers import (assert_close, assert_exact, golden_names, load_golden, oracle_kwargs, population_kwargs,
+                     population_names)
 
 pytestmark = pytest.mark.gpu
 
@@ -37,13 +38,15 @@ def make_env(cfg_kwargs, num_envs=1, seeds=None, **extra):
     return BatchedMobileEnv(num_envs=num_envs, seeds=seeds, **kw)
 
 
-def compare_step(env, dbg, want, k, what, step=True):
-    """dbg: debug dict of the CUDA env (all K envs); want: oracle trace of env k."""
+def compare_step(env, dbg, want, k, what, step=True, num_ue=None):
+    """dbg: debug dict of the CUDA env (all K envs); want: oracle trace of env k.  num_ue: UEs present (variable
+    population): the state slabs are compared on those slots only, every output on all max_ues rows (padding = 0)."""
     st = env.get_state()
-    assert_exact(st['pos'][k], want['pos'], f'{what}.pos')
-    assert_exact(env.mask_matrix(st['mask'])[k], want['mask'], f'{what}.mask')
-    assert_exact(st['movement'][k], want['movement'], f'{what}.movement')
-    assert_close(st['ewma'][k], want['ewma'], f'{what}.ewma', RTOL, ATOL)
+    n = want['mask'].shape[0] if num_ue is None else num_ue
+    assert_exact(st['pos'][k][:n], want['pos'][:n], f'{what}.pos')
+    assert_exact(env.mask_matrix(st['mask'])[k][:n], want['mask'][:n], f'{what}.mask')
+    assert_exact(st['movement'][k][:n], want['movement'][:n], f'{what}.movement')
+    assert_close(st['ewma'][k][:n], want['ewma'][:n], f'{what}.ewma', RTOL, ATOL)
     assert_close(dbg['dbg_snr'][k].cpu().numpy(), want['snr'], f'{what}.snr', RTOL, 0)
     assert_close(dbg['dbg_link_rate'][k].cpu().numpy(), want['link_rates'], f'{what}.link_rates', RTOL, ATOL)
     assert_close(dbg['dbg_curr_dr'][k].cpu().numpy(), want['curr_dr'], f'{what}.curr_dr', RTOL, ATOL)
@@ -87,6 +90,58 @@ def test_cuda_step_matches_reference_golden(name, wide, monkeypatch):
             compare_step(env, dbg, want, 0, f'{name}.step[{t}]')
             t += 1
     env.check_errors()
+
+
+@pytest.mark.parametrize('wide', [False, True], ids=['fused', 'wide'])
+@pytest.mark.parametrize('name', population_names())
+def test_cuda_variable_population_matches_reference_golden(name, wide, monkeypatch):
+    """ue_arrival / new_ue_interval (base.py:429-443, 592-617) on envs with max_ues > num_ue: the first episode of the
+    reference's trace, every recorded array, through both kernels; then a reset brings the original population back
+    and replays the same episode (the reference re-seeds by list position there: documented divergence)."""
+    if wide:
+        monkeypatch.setenv('DCB_FORCE_WIDE', '1')
+    cfg, z = load_golden(name)
+    env = make_env(dict(oracle_kwargs(cfg), **population_kwargs(cfg)))
+    step_keys = ('pos', 'mask', 'movement', 'ewma', 'snr', 'link_rates', 'curr_dr', 'utility', 'obs', 'lost_conn',
+                 'time', 'reward', 'sum_utility')
+    first_obs = None
+    for ep in range(2):
+        dbg = env.reset(debug=True)
+        want = {k: z['reset_' + k][0] for k in ('pos', 'mask', 'movement', 'ewma', 'snr', 'link_rates', 'curr_dr',
+                                                'utility', 'obs')}
+        assert env.active_ues == int(z['reset_num_ue'][0])
+        compare_step(env, dbg, want, 0, f'{name}.reset[{ep}]', step=False, num_ue=env.active_ues)
+        for t in range(cfg['steps']):
+            a = torch.as_tensor(z['actions'][t][None, :].astype(np.int32), device='cuda')
+            dbg = env.step(a, debug=True)
+            assert env.active_ues == int(z['step_num_ue'][t]), (name, t)
+            compare_step(env, dbg, {k: z['step_' + k][t] for k in step_keys}, 0, f'{name}.ep{ep}.step[{t}]',
+                         num_ue=env.active_ues)
+    env.check_errors()
+
+
+def test_variable_population_fragments_equal_single_steps():
+    """step_many across arrivals / departures (one launch per stretch without an event) == single steps, K envs."""
+    from deepcomp_b200 import BatchedMobileEnv
+    W, H, bs = c_oracle_grid(5)
+    arrival = {5: 2, 6: 1, 20: -2, 21: 3, 40: -4}
+    kw = dict(num_envs=5, n_ue=3, max_ues=10, bs_xy=bs, map_wh=(W, H), kind='multi', seed=11, episode_length=60,
+              ue_arrival=arrival, new_ue_interval=17)
+    e1, e2 = BatchedMobileEnv(**kw), BatchedMobileEnv(**kw)
+    a = torch.randint(0, 6, (60, 5, 10), dtype=torch.int32, device='cuda', generator=torch.Generator('cuda').manual_seed(1))
+    e1.reset(); e2.reset()
+    f = e1.step_many(a, info=True)
+    for t in range(60):
+        obs, rew, _, info = e2.step(a[t])
+        assert torch.equal(obs, f['obs'][t]) and torch.equal(rew, f['reward'][t]), t
+        assert torch.equal(info['lost_conn'], f['lost_conn'][t]) and torch.equal(info['sum_utility'], f['sum_utility'][t])
+    want = 3 + sum(arrival.values()) + 3                       # + the interval arrivals at 17, 34, 51
+    assert e1.active_ues == e2.active_ues == want
+    s1, s2 = e1.get_state(), e2.get_state()
+    n = e1.active_ues
+    assert np.array_equal(s1['pos'][:, :n], s2['pos'][:, :n]) and np.array_equal(s1['mask'][:, :n], s2['mask'][:, :n])
+    # envs differ in WHO left (per-env draws of the global `random` module) and where the newcomers appeared
+    assert len({tuple(p.ravel()) for p in s1['pos'][:, :n]}) == 5
 
 
 @pytest.mark.parametrize('kind', ['central', 'multi'])
