@@ -170,6 +170,12 @@ class BatchedMobileEnv:
     def active_ues(self, n):
         check(self._L.dcb_set_active_ues(self._h, int(n)))
 
+    def ue_ids(self):
+        """User.id (as integers) of the UEs present, int32 [K, active_ues]; ids of arrivals continue after the last id"""
+        ids = np.zeros((self.num_envs, self.n_ue), dtype=np.int32)
+        check(self._L.dcb_get_ue_ids(self._h, ctypes.c_void_p(ids.ctypes.data)))
+        return ids[:, :self.active_ues]
+
     @property
     def kernel_name(self):
         """'dcb_step_kernel' (fused, several envs per CTA) or 'dcb_wide_kernel' (one CTA per env, large envs)"""

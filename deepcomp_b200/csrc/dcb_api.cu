@@ -475,6 +475,14 @@ int dcb_set_active_ues(dcb_env *env, int32_t n_active) {
 
 int32_t dcb_get_active_ues(const dcb_env *env) { return env ? env->p.NA : 0; }
 
+int dcb_get_ue_ids(dcb_env *env, int32_t *host_ids) {
+    if (!env || !host_ids) return fail(DCB_ERR_INVALID_ARG, "null argument");
+    DeviceGuard guard(env->device);
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(host_ids, env->d_uid, sizeof(int32_t) * (size_t)env->p.K * env->p.N, cudaMemcpyDeviceToHost));
+    return DCB_OK;
+}
+
 int dcb_population_event(dcb_env *env, int32_t n_add, int32_t n_remove, int32_t *d_actions, void *stream) {
     if (!env) return fail(DCB_ERR_INVALID_ARG, "null handle");
     if (n_add < 0 || n_remove < 0) return fail(DCB_ERR_INVALID_ARG, "negative UE count");

@@ -26,12 +26,20 @@ def _parse_env_config(env_config):
     for k in required:
         if k not in env_config:
             raise KeyError(f"env_config is missing {k!r} (reference MobileEnv.__init__, base.py:27-84)")
-    if env_config['new_ue_interval'] is not None or env_config['ue_arrival'] is not None:
-        raise NotImplementedError("UE arrival / departure (base.py:433-443, 592-617) is outside the B200 hot path "
-                                  "(SURVEY.md section 8f)")
     m, bs_list, ue_list = env_config['map'], env_config['bs_list'], env_config['ue_list']
-    if env_config['max_ues'] is not None and env_config['max_ues'] != len(ue_list):
-        raise NotImplementedError("max_ues != num_ue needs the variable-population path (SURVEY.md section 8f)")
+    max_ues = env_config['max_ues']
+    if max_ues is None:
+        # base.py:191-209 get_max_num_ue
+        max_ues = len(ue_list)
+        if env_config['new_ue_interval'] is not None:
+            # "eps_length - 1 because time is increased before checking done and t=eps_length is never reached"
+            max_ues += int((env_config['episode_length'] - 1) / env_config['new_ue_interval'])
+        if env_config['ue_arrival'] is not None:
+            curr = max_ues                      # running number of UEs over the arrival / departure sequence
+            for arrival in env_config['ue_arrival'].values():
+                curr += arrival
+                max_ues = max(max_ues, curr)
+    assert max_ues >= len(ue_list)                                                        # base.py:84
     velocities, init_pos, pauses, borders = [], [], set(), set()
     for ue in ue_list:
         if getattr(ue, 'util_func', 'log') != 'log':
@@ -48,7 +56,8 @@ def _parse_env_config(env_config):
     return dict(n_ue=len(ue_list), bs_xy=[(float(bs.pos.x), float(bs.pos.y)) for bs in bs_list],
                 map_wh=(int(m.width), int(m.height)), sharing=[bs.sharing_model for bs in bs_list],
                 velocities=velocities, init_pos=init_pos, pause_duration=pauses.pop(), border_buffer=borders.pop(),
-                episode_length=env_config['episode_length'], rand_episodes=bool(env_config['rand_episodes']))
+                episode_length=env_config['episode_length'], rand_episodes=bool(env_config['rand_episodes']),
+                max_ues=int(max_ues), ue_arrival=env_config['ue_arrival'], new_ue_interval=env_config['new_ue_interval'])
 
 
 class _MobileEnvFacade:
@@ -62,13 +71,14 @@ class _MobileEnvFacade:
         self.episode_length = sc['episode_length']
         self.map, self.bs_list, self.ue_list = env_config['map'], env_config['bs_list'], env_config['ue_list']
         self.original_ue_list = list(self.ue_list)
-        self.new_ue_interval, self.ue_arrival = None, None
+        self.new_ue_interval, self.ue_arrival = sc['new_ue_interval'], sc['ue_arrival']
         self.env_seed = env_config['seed']
         self.rand_episodes = sc['rand_episodes']
         self.log_metrics = env_config['log_metrics']
         self.dashboard = env_config.get('dashboard', False)
         self.ue_details = env_config.get('ue_details', False)
-        self.max_ues = len(self.ue_list)
+        self.max_ues = sc['max_ues']
+        self._ue_by_id = {int(ue.id): ue for ue in self.ue_list}
         self.reward_agg = env_config['reward']                      # central.py:19 / multi_agent.py:19
         self.time = 0
         self.total_utility = 0
@@ -98,7 +108,8 @@ class _MobileEnvFacade:
             num_envs=1, n_ue=sc['n_ue'], bs_xy=sc['bs_xy'], map_wh=sc['map_wh'], kind=self._kind,
             sharing=sc['sharing'], velocities=sc['velocities'], seeds=[seed], reward=self.reward_agg,
             episode_length=sc['episode_length'], rand_episodes=sc['rand_episodes'], init_pos=sc['init_pos'],
-            pause_duration=sc['pause_duration'], border_buffer=sc['border_buffer'], device=self._device)
+            pause_duration=sc['pause_duration'], border_buffer=sc['border_buffer'], device=self._device,
+            max_ues=sc['max_ues'], ue_arrival=sc['ue_arrival'], new_ue_interval=sc['new_ue_interval'])
 
     # ---- MobileEnv attributes
     @property
@@ -169,12 +180,30 @@ class _MobileEnvFacade:
         }
 
     def _device_actions(self, per_ue):
-        a = np.zeros((1, self.num_ue), dtype=np.int32)
-        a[0, :] = per_ue
+        a = np.zeros((1, self.max_ues), dtype=np.int32)
+        a[0, :len(per_ue)] = per_ue
         return torch.as_tensor(a, device=self._batch.device)
+
+    def _sync_ue_list(self):
+        """arrivals / departures (base.py:592-617): rebuild ue_list from the ids the device holds per slot"""
+        from .entities import RandomWaypoint, User
+        ids = self._batch.ue_ids()[0]
+        if [int(ue.id) for ue in self.ue_list] == ids.tolist():
+            return
+        ues = []
+        for uid in ids.tolist():
+            if uid not in self._ue_by_id:          # add_new_ue: 'slow' RandomWaypoint UE appearing on the map border
+                self._ue_by_id[uid] = User(str(uid), self.map, None, None, movement=RandomWaypoint(self.map, velocity='slow'))
+            ues.append(self._ue_by_id[uid])
+        self.ue_list = ues
+
+    def _reset_ue_list(self):
+        self.ue_list = list(self.original_ue_list)                   # base.py:176-182
 
     def _step_batch(self, per_ue_actions):
         obs, reward, _, info = self._batch.step(self._device_actions(per_ue_actions), info=True)
+        if self._batch._dynamic:
+            self._sync_ue_list()
         self.time += 1
         sum_utility = float(info['sum_utility'][0])
         self.total_utility += sum_utility
@@ -199,7 +228,7 @@ class CentralRelNormEnv(_MobileEnvFacade):
 
     def _obs_dict(self, flat):
         """central.py:31-57: values are Python lists in the reference"""
-        nm = self.num_ue * self.num_bs
+        nm = self.max_ues * self.num_bs                     # zero-padded to max_ues (central.py:46-55)
         return {'connected': [int(v) for v in flat[:nm]], 'dr': [float(v) for v in flat[nm:2 * nm]],
                 'utility': [float(v) for v in flat[2 * nm:]]}
 
@@ -211,6 +240,7 @@ class CentralRelNormEnv(_MobileEnvFacade):
 
     def reset(self):
         self.time = 0
+        self._reset_ue_list()
         flat = self._batch.reset()[0].cpu().numpy()
         self.obs = self._obs_dict(flat)
         return self.obs
@@ -218,7 +248,7 @@ class CentralRelNormEnv(_MobileEnvFacade):
     def step(self, action):
         action = np.asarray(action)
         assert self.action_space.contains(action), f"Action {action} does not fit action space {self.action_space}"
-        flat, reward, curr_dr, utility, sum_utility = self._step_batch(action.astype(np.int32))
+        flat, reward, curr_dr, utility, sum_utility = self._step_batch(action.astype(np.int32)[:self.num_ue])
         self._sync_entities(curr_dr, utility)
         self.obs = self._obs_dict(flat)
         return self.obs, float(reward), self.done(), self._info(curr_dr, utility, sum_utility)
@@ -249,6 +279,7 @@ class MultiAgentMobileEnv(_MobileEnvFacade):
 
     def reset(self):
         self.time = 0
+        self._reset_ue_list()
         packed = self._batch.reset()[0].cpu().numpy()
         self.obs = self._obs_dict(packed)
         return self.obs

@@ -176,6 +176,8 @@ int32_t dcb_get_active_ues(const dcb_env *env);
  * restores the original population.
  */
 int dcb_population_event(dcb_env *env, int32_t n_add, int32_t n_remove, int32_t *d_actions, void *stream);
+/* UE ids per slot, host int32 [K][n_ue] (User.id as an integer; slots >= dcb_get_active_ues are stale).  Synchronous. */
+int dcb_get_ue_ids(dcb_env *env, int32_t *host_ids);
 
 /* get_obs() of the current state (central.py:31-57 / multi_agent.py:32-37) without stepping; reward is not written */
 int dcb_observe(dcb_env *env, const dcb_outputs *out, void *stream);

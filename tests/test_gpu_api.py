@@ -77,6 +77,55 @@ def test_gym_facades_replay_reference_traces(name):
     env.close()
 
 
+@pytest.mark.parametrize('name', ['pop_largeupdown_central_avg', 'pop_largeupdown_multi_avg', 'pop_interval25_multi_avg',
+                                  'pop_3up2down_central_sum'])
+def test_gym_facades_with_arriving_and_departing_ues(name):
+    """env_config['ue_arrival'] / ['new_ue_interval'] / ['max_ues'] through the reference-shaped classes: the agent ids
+    in the obs / reward / done dicts follow the reference (arrivals get id = last id + 1), central obs are zero-padded."""
+    from deepcomp_b200.env import get_env_class
+    cfg, z = load_golden(name)
+    ec = _env_config_from_golden(cfg)
+    ec['max_ues'] = cfg['max_ues']
+    ec['new_ue_interval'] = cfg.get('new_ue_interval')
+    ec['ue_arrival'] = None if cfg.get('ue_arrival') is None else {int(t): n for t, n in cfg['ue_arrival'].items()}
+    env = get_env_class(cfg['kind'])(ec)
+    M, S = len(cfg['bs_xy']), cfg['max_ues']
+    assert env.max_ues == S and env.num_ue == cfg['n_ue']
+    obs = env.reset()
+    for t in range(cfg['steps']):
+        a = z['actions'][t]
+        before = list(env.ue_list)
+        if cfg['kind'] == 'central':
+            obs, reward, done, info = env.step(a.astype(np.int64))
+            flat = np.concatenate([np.asarray(obs[k], dtype=np.float64) for k in sorted(obs)])
+            assert len(obs['connected']) == S * M and len(obs['utility']) == S
+            assert_close(reward, z['step_reward'][t], f'reward[{t}]', 2e-6, 1e-6)
+        else:
+            obs, reward, done, info = env.step({ue.id: int(a[i]) for i, ue in enumerate(before)})
+            ids = [ue.id for ue in env.ue_list]
+            assert set(obs) == set(reward) == set(ids) and set(done) == set(ids) | {'__all__'}
+            flat = np.zeros((S, 4 * M + 1))
+            rew = np.zeros(S)
+            for i, uid in enumerate(ids):
+                flat[i] = np.concatenate([np.asarray(obs[uid][k], dtype=np.float64) for k in sorted(obs[uid])])
+                rew[i] = reward[uid]
+            assert_close(rew, z['step_reward'][t], f'reward[{t}]', 2e-6, 1e-5)
+            info = info[ids[0]]
+        n = int(z['step_num_ue'][t])
+        assert env.num_ue == n and info['time'] == env.time == z['step_time'][t]
+        assert_close(flat, z['step_obs'][t], f'obs[{t}]', 2e-6, 1e-6)
+        assert_close(info['scalar_metrics']['sum_utility'], z['step_sum_utility'][t], 'sum_utility', 2e-6, 1e-5)
+        assert_exact(np.array([[u.pos.x, u.pos.y] for u in env.ue_list]), z['step_pos'][t][:n], 'ue.pos')
+        # ids: departures keep the others' ids, arrivals continue after the last id of the list (base.py:595)
+        if n > len(before):
+            assert [u.id for u in env.ue_list[:len(before)]] == [u.id for u in before]
+            assert int(env.ue_list[len(before)].id) == int(before[-1].id) + 1
+    assert [u.id for u in env.ue_list] != [u.id for u in env.original_ue_list] or cfg.get('new_ue_interval') is None
+    env.reset()
+    assert env.ue_list == env.original_ue_list and env.num_ue == cfg['n_ue']
+    env.close()
+
+
 def test_central_facade_rejects_invalid_actions():
     """reference: assert action_space.contains(action) (central.py:61)"""
     from deepcomp_b200.env import CentralRelNormEnv

@@ -57,13 +57,20 @@ def test_env_config_parsing_matches_reference_fields():
     assert [ue.id for ue in _config()['ue_list']] == ['1', '2', '3', '4']
 
 
+def test_env_config_variable_population_fields():
+    """max_ues as the reference derives it when None (base.py:80-84, 191-203): initial UEs + every arrival"""
+    assert _parse_env_config(_config())['max_ues'] == 4
+    assert _parse_env_config(_config(max_ues=7))['max_ues'] == 7
+    sc = _parse_env_config(_config(new_ue_interval=10))
+    assert sc['max_ues'] == 4 + 9 and sc['new_ue_interval'] == 10        # int((100 - 1) / 10)
+    sc = _parse_env_config(_config(ue_arrival={10: 3, 30: -2}))
+    assert sc['max_ues'] == 4 + 3 and sc['ue_arrival'] == {10: 3, 30: -2}
+    assert _parse_env_config(_config(ue_arrival={10: 1, 20: -1, 30: 1, 40: -1}))['max_ues'] == 5
+    with pytest.raises(AssertionError):
+        _parse_env_config(_config(max_ues=3))                        # base.py:84
+
+
 def test_env_config_out_of_scope_features_fail_loudly():
-    with pytest.raises(NotImplementedError):
-        _parse_env_config(_config(new_ue_interval=10))
-    with pytest.raises(NotImplementedError):
-        _parse_env_config(_config(ue_arrival={'10': 1}))
-    with pytest.raises(NotImplementedError):
-        _parse_env_config(_config(max_ues=7))
     cfg = _config()
     cfg['ue_list'][0].util_func = 'step'
     with pytest.raises(NotImplementedError):
