@@ -127,6 +127,8 @@ __device__ __forceinline__ double warp_min(double v) {
     return v;
 }
 
+// PAD: the envs have padding slots (NA < N, variable UE population)
+template <bool PAD>
 __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const DevParams &p = a.p;
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = a.threads >> 5;   // a.threads == blockDim.x
     const int k = blockIdx.x;
-    const int NA = p.NA;                   // slots [0, NA) hold UEs, the rest is padding (max_ues > num_ue)
+    const int NA = PAD ? p.NA : N;         // slots [0, NA) hold UEs, the rest is padding (max_ues > num_ue)
     const bool valid = tid < NA;
     const int i = valid ? tid : 0;
     const long long u = (long long)k * N + i;
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                                 ? a.out.reward + (size_t)step * a.out.reward_stride + kN : nullptr;
         double *dbg_reward_env = (last && a.out.dbg_reward && !central && T > 0) ? a.out.dbg_reward + kN : nullptr;
         for (int r = warp; r < N; r += nwarps) {
-            if (r >= NA) {
+            if (PAD && r >= NA) {
                 // ---- padding slot (no UE there: max_ues > num_ue): zeros, as central.py:46-55 pads the observation
                 const long long ru = kN + r;
                 if (obs_lane) {
@@ -527,10 +529,14 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
 }  // namespace
 
 cudaError_t dcb_wide_set_smem_limit(size_t smem) {
-    return cudaFuncSetAttribute(dcb_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(dcb_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(dcb_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return e;
 }
 
 cudaError_t dcb_launch_wide(const StepArgs &a, int threads, int grid, size_t smem, cudaStream_t s) {
-    dcb_wide_kernel<<<grid, threads, smem, s>>>(a);
+    if (a.p.NA < a.p.N) dcb_wide_kernel<true><<<grid, threads, smem, s>>>(a);
+    else dcb_wide_kernel<false><<<grid, threads, smem, s>>>(a);
     return cudaGetLastError();
 }
