@@ -67,6 +67,12 @@ __device__ __forceinline__ unsigned dcb_smid() {
 #define DCB_TRACE_PT(role, pt) do { } while (0)
 #endif
 
+#ifndef DCB_OBS_UNROLL
+#define DCB_OBS_UNROLL 2   // unroll factor of the observers' pair loops
+#endif
+#define DCB_PRAGMA(x) _Pragma(#x)
+#define DCB_UNROLL(n) DCB_PRAGMA(unroll n)
+
 namespace {
 
 // [region:helpers.barriers]
@@ -455,7 +461,10 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                 }
                 __syncwarp();
                 const double iee = dcb_rcp(ewma + DCB_EPSILON);
-                constexpr int LW = 2;
+#ifndef DCB_LW
+#define DCB_LW 1     // links per lane and trip of the balanced link loop (2 and 3 measured slower: 1.66e8 / 1.53e8 vs 1.81e8)
+#endif
+                constexpr int LW = DCB_LW;
                 for (int base = 0; base < total; base += 32 * LW) {
                     unsigned e[LW];
                     double d2[LW], v[LW], oi[LW];
@@ -634,7 +643,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                 // station.py:222-226), parked in the tile as float for pass B
                 mask_t inrange = 0;
                 float d2minf = CUDART_INF_F;
-#pragma unroll 2
+                DCB_UNROLL(DCB_OBS_UNROLL)
                 for (int b = 0; b < M; b++) {
                     const double d2 = dist2(bsxy[b], x, y);
                     const float d2f = (float)d2;
@@ -644,7 +653,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                 }
                 // ---- dense pass B: 'dr' = snr_b / max_b snr_b (variants.py:276-284) = (d2min / d2_b)^h
                 if (d2minf >= 1e-6f) {        // below: d + EPSILON matters (in practice d = 0 exactly)
-#pragma unroll 2
+                DCB_UNROLL(DCB_OBS_UNROLL)
                     for (int b = 0; b < M; b++) row_dr[b] = norm_snr_f32(row_dr[b], d2minf, hr);
                 } else {
                     double d2min = CUDART_INF;
