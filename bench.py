@@ -242,9 +242,20 @@ def gpu_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO on some boxes) off it
+        # stdout carries exactly one JSON line: NCCL writes its version banner there when the communicator is created, so
+        # file descriptor 1 points at stderr while that happens
         os.environ['NCCL_DEBUG'] = os.environ.get('DCB_NCCL_DEBUG', 'WARN')
-        dist.init_process_group('nccl', device_id=dev)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     K, N, M, L, F = args.envs, args.n_ue, args.n_bs, args.episode_length, args.fragment
     W, H, bs = grid_layout(M)
