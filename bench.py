@@ -241,21 +241,16 @@ def gpu_arm(args):
             sys.exit(f"--gpus {args.gpus} needs torchrun with --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    real_stdout = None
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL writes its version banner there when the communicator is created, so
-        # file descriptor 1 points at stderr while that happens
+        # stdout carries exactly one JSON line, but NCCL writes its version banner to the C stdout whenever it pleases
+        # (buffered, so it can surface long after communicator creation): file descriptor 1 points at stderr for the
+        # whole run and the JSON line goes to the saved descriptor at the end
         os.environ['NCCL_DEBUG'] = os.environ.get('DCB_NCCL_DEBUG', 'WARN')
         sys.stdout.flush()
-        saved = os.dup(1)
+        real_stdout = os.dup(1)
         os.dup2(2, 1)
-        try:
-            dist.init_process_group('nccl', device_id=dev)
-            dist.barrier()
-            torch.cuda.synchronize(dev)
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+        dist.init_process_group('nccl', device_id=dev)
 
     K, N, M, L, F = args.envs, args.n_ue, args.n_bs, args.episode_length, args.fragment
     W, H, bs = grid_layout(M)
@@ -433,7 +428,10 @@ def gpu_arm(args):
         line["cpu_native_port"] = extra_native
     if gather is not None:
         line["rollout_gather"] = gather
-    print(json.dumps(line), flush=True)
+    if real_stdout is None:
+        print(json.dumps(line), flush=True)
+    else:
+        os.write(real_stdout, (json.dumps(line) + '\n').encode())
     if world > 1:
         dist.destroy_process_group()
 
