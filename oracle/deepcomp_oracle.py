@@ -505,6 +505,40 @@ class OracleEnv:
                    sum_utility=np.float64(sum_utility), time=self.time, done=None)
         return out
 
+    # ------------------------------------------------------------------ brute force (agent/brute_force.py)
+    def test_ue_actions(self, actions):
+        """single_ue/base.py:284-313: rewards of a joint action tried on the current state, then reverted"""
+        original_ewma = [ue.ewma_dr for ue in self.ues]
+
+        def apply():                                            # base.py:247-282
+            for pos, ue in enumerate(self.ues):
+                if int(actions[pos]) > 0:
+                    self.connect_to_bs(ue, int(actions[pos]) - 1)
+        apply()
+        self.update_ue_drs_rewards(update_only=True)
+        for ue in self.ues:                                     # user.py:148-157 update_ewma_dr
+            ue.ewma_dr = 0.9 * self.curr_dr(ue) + (1 - 0.9) * ue.ewma_dr
+        rewards = self.update_ue_drs_rewards()
+        apply()                                                 # "to revert the action, apply it again"
+        for ue, e in zip(self.ues, original_ewma):
+            ue.ewma_dr = e
+        self.update_ue_drs_rewards(update_only=True)
+        return rewards
+
+    def candidate_action(self, c):
+        """brute_force.py:26-62: the c-th action = digits of c in base M + 1, most significant digit = first UE"""
+        digits = []
+        for _ in range(self.max_ues):
+            digits.append(c % (self.n_bs + 1))
+            c //= self.n_bs + 1
+        return digits[::-1]
+
+    def brute_force_rewards(self):
+        """brute_force.py:64-94: central step reward of every joint action; the agent takes np.argmax (first maximum)"""
+        assert self.kind == 'central'
+        n_cand = (self.n_bs + 1) ** self.max_ues
+        return np.array([float(self.step_reward(self.test_ue_actions(self.candidate_action(c)))) for c in range(n_cand)])
+
     # ------------------------------------------------------------------ snapshots (same keys as ref_loader.RefTrace)
     def snapshot(self):
         n, m = len(self.ues), self.n_bs

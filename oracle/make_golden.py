@@ -75,6 +75,55 @@ def population_scenarios():
     return S
 
 
+def brute_scenarios():
+    """BruteForceAgent (deepcomp/agent/brute_force.py:59-94): all (M+1)^N joint actions tested with
+    MobileEnv.test_ue_actions (single_ue/base.py:284-313) on the central env, the best one taken."""
+    S = []
+    wh, bs = medium_map()
+    for sharing, reward, n_ue in (('mixed', 'avg', 4), ('proportional-fair', 'sum', 3), ('max-cap', 'min', 3),
+                                  ('rate-fair', 'avg', 5)):
+        S.append(dict(name=f'brute_{sharing}_{reward}_{n_ue}ue', kind='central', n_ue=n_ue, bs_xy=bs, map_wh=wh,
+                      sharing=sharing, velocities='slow', seed=5, reward=reward, steps=12, action_seed=0, episodes=1))
+    return S
+
+
+def record_brute(sc):
+    """Per step: the reward of EVERY candidate action (brute_force.py:64-77) from the state before the step, then the
+    step with the best one (np.argmax: first maximum, brute_force.py:90-92)."""
+    env = rl.build_env(sc['kind'], sc['n_ue'], sc['seed'], sc['bs_xy'], sc['map_wh'], sharing=sc['sharing'],
+                       velocities=sc['velocities'], reward=sc['reward'], episode_length=sc['steps'])
+    tr = rl.RefTrace(env, sc['kind'])
+    n, m = sc['n_ue'], len(sc['bs_xy'])
+    n_cand = (m + 1) ** n
+    cand_rewards, actions, steps = [], [], {k: [] for k in STEP_KEYS}
+    env.reset()
+    reset = tr.snapshot()
+    for t in range(sc['steps']):
+        rew = np.zeros(n_cand)
+        for c in range(n_cand):
+            digits = np.base_repr(c, base=m + 1).zfill(n)                      # == number_to_base(c, m + 1, n)
+            act = [int(ch, m + 1) for ch in digits]
+            rewards = env.test_ue_actions(env.get_ue_actions(act))
+            rew[c] = float(env.step_reward(rewards))
+        best = int(np.argmax(rew))
+        a = np.array([int(ch, m + 1) for ch in np.base_repr(best, base=m + 1).zfill(n)], dtype=np.int32)
+        cand_rewards.append(rew)
+        actions.append(a)
+        s = tr.step(a)
+        for k in STEP_KEYS:
+            steps[k].append(s[k])
+    out = {'cand_rewards': np.stack(cand_rewards), 'actions': np.stack(actions)}
+    for k in STEP_KEYS:
+        out['step_' + k] = np.stack([np.asarray(v) for v in steps[k]])
+    for k in ('pos', 'mask', 'ewma'):
+        out['reset_' + k] = reset[k]
+    cfg = dict(sc)
+    cfg['bs_xy'] = [[float(x), float(y)] for x, y in sc['bs_xy']]
+    cfg['map_wh'] = [float(sc['map_wh'][0]), float(sc['map_wh'][1])]
+    out['config'] = np.array(json.dumps(cfg))
+    return out
+
+
 def policy_scenarios():
     """Closed loops of the reference's baseline agents (deepcomp/agent/heuristics.py, dummy.py) on the reference env."""
     S = []
@@ -221,10 +270,10 @@ def main():
     only = sys.argv[1] if len(sys.argv) > 1 else ''     # optional name prefix: regenerate a subset only
     if not only:
         np.savez_compressed(os.path.join(OUT_DIR, 'anchors.npz'), **anchors())
-    for sc in scenarios() + policy_scenarios() + population_scenarios():
+    for sc in scenarios() + policy_scenarios() + population_scenarios() + brute_scenarios():
         if not sc['name'].startswith(only):
             continue
-        data = record(sc)
+        data = record_brute(sc) if sc['name'].startswith('brute_') else record(sc)
         path = os.path.join(OUT_DIR, sc['name'] + '.npz')
         np.savez_compressed(path, **data)
         print(f"{sc['name']}: {os.path.getsize(path) / 1024:.0f} KiB")

@@ -26,7 +26,12 @@ def _names():
 
 def golden_names():
     """fixed-population traces (every test that replays a trace step by step)"""
-    return [n for n in _names() if not n.startswith('pop_')]
+    return [n for n in _names() if not n.startswith(('pop_', 'brute_'))]
+
+
+def brute_names():
+    """brute-force traces: the reward of every joint action per step (agent/brute_force.py, base.py:284-313)"""
+    return [n for n in _names() if n.startswith('brute_')]
 
 
 def population_names():

@@ -5,7 +5,7 @@ import pytest
 from oracle import c_oracle
 from oracle import deepcomp_oracle as po
 
-from helpers import (GOLDEN_DIR, check_against_golden, golden_names, load_golden, oracle_kwargs, population_kwargs,
+from helpers import (GOLDEN_DIR, assert_close, assert_exact, brute_names, check_against_golden, golden_names, load_golden, oracle_kwargs, population_kwargs,
                      population_names)
 
 
@@ -70,3 +70,21 @@ def test_python_oracle_variable_population_matches_reference(name):
     exact = not (cfg['kind'] == 'multi' and cfg['reward'] == 'sum')
     check_against_golden(env, cfg, z, exact_floats=exact, episodes=1)
     assert env.snapshot()['num_ue'] == int(z['step_num_ue'][cfg['steps'] - 1])
+
+
+@pytest.mark.parametrize('name', brute_names())
+def test_python_oracle_brute_force_matches_reference(name):
+    """BruteForceAgent (agent/brute_force.py:59-94) over MobileEnv.test_ue_actions (base.py:284-313): the reward of every
+    joint action and the action taken, step by step."""
+    cfg, z = load_golden(name)
+    env = po.OracleEnv(**oracle_kwargs(cfg))
+    env.reset()
+    for t in range(cfg['steps']):
+        rew = env.brute_force_rewards()
+        assert_close(rew, z['cand_rewards'][t], f'{name}.cand_rewards[{t}]', 1e-12, 1e-12)
+        a = env.candidate_action(int(np.argmax(rew)))
+        assert_exact(np.asarray(a), z['actions'][t], f'{name}.action[{t}]')
+        s = env.step(a)
+        assert_exact(s['pos'], z['step_pos'][t], f'{name}.pos[{t}]')
+        assert_exact(s['mask'], z['step_mask'][t], f'{name}.mask[{t}]')
+        assert_close(s['reward'], z['step_reward'][t], f'{name}.reward[{t}]', 1e-12, 1e-12)
