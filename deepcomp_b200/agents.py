@@ -184,3 +184,31 @@ class FixedAgent(CentralAgent):
     def device_policy(self, batch=None):
         return dict(kind='fixed', fixed_action=np.asarray(self.action, dtype=np.int32),
                     noop_interval=int(self.noop_interval))
+
+
+class BruteForceAgent(CentralAgent):
+    """
+    Reference deepcomp/agent/brute_force.py:10-94: tests every joint action on the env and takes the best one (first
+    maximum).  The reference walks the (M + 1)^N candidates one by one through MobileEnv.test_ue_actions
+    (base.py:284-313); here they are evaluated in one launch (`dcb_test_actions`), so `num_workers` has no meaning.
+    `env` is a CentralRelNormEnv facade (its K = 1 batch is used) or a BatchedMobileEnv (+ `env_index`).
+    """
+
+    def __init__(self, num_workers=1, env=None, env_index=0):
+        super().__init__()
+        self.num_workers = num_workers
+        self.env = env
+        self.env_index = env_index
+
+    def _batch(self):
+        assert self.env is not None, "Set agent's env before computing actions."       # brute_force.py:81
+        return getattr(self.env, '_batch', self.env)
+
+    def get_ith_action(self, i):
+        """brute_force.py:59-62"""
+        return self._batch().candidate_action(i)
+
+    def compute_action(self, observation):
+        """brute_force.py:79-94"""
+        action, _ = self._batch().best_joint_action(self.env_index)
+        return action

@@ -170,6 +170,42 @@ class BatchedMobileEnv:
     def active_ues(self, n):
         check(self._L.dcb_set_active_ues(self._h, int(n)))
 
+    # ------------------------------------------------------------------ brute force (reference agent/brute_force.py)
+    @property
+    def num_joint_actions(self):
+        """(M + 1)^num_ue candidates of BruteForceAgent (brute_force.py:86-88)"""
+        return int(self._L.dcb_num_joint_actions(self._h))
+
+    def candidate_action(self, c):
+        """brute_force.py:26-62: digits of c in base M + 1, most significant digit = first UE; zeros on padding slots"""
+        digits = []
+        for _ in range(self.active_ues):
+            digits.append(c % (self.n_bs + 1))
+            c //= self.n_bs + 1
+        return digits[::-1] + [0] * (self.n_ue - self.active_ues)
+
+    def test_actions(self, env_index=0, first=0, count=None):
+        """
+        MobileEnv.test_ue_actions (base.py:284-313) + central step_reward (central.py:65-73) for the joint actions
+        [first, first + count) of one env, all at once on the device; the env state is not changed.  float64 [count].
+        """
+        if count is None:
+            count = self.num_joint_actions - first
+        out = self._empty((int(count),), torch.float64)
+        check(self._L.dcb_test_actions(self._h, int(env_index), int(first), int(count), ctypes.c_void_p(out.data_ptr()),
+                                       self._stream()))
+        return out
+
+    def best_joint_action(self, env_index=0, chunk=1 << 24):
+        """BruteForceAgent.compute_action (brute_force.py:79-94): the first maximum over all joint actions"""
+        best, best_c = -float('inf'), 0
+        for first in range(0, self.num_joint_actions, chunk):
+            r = self.test_actions(env_index, first, min(chunk, self.num_joint_actions - first))
+            mx = float(r.max())
+            if mx > best:
+                best, best_c = mx, first + int((r == mx).nonzero()[0, 0])
+        return self.candidate_action(best_c), best
+
     def ue_ids(self):
         """User.id (as integers) of the UEs present, int32 [K, active_ues]; ids of arrivals continue after the last id"""
         ids = np.zeros((self.num_envs, self.n_ue), dtype=np.int32)

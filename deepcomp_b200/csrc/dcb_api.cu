@@ -475,6 +475,31 @@ int dcb_set_active_ues(dcb_env *env, int32_t n_active) {
 
 int32_t dcb_get_active_ues(const dcb_env *env) { return env ? env->p.NA : 0; }
 
+int64_t dcb_num_joint_actions(const dcb_env *env) {
+    if (!env) return 0;
+    double n = pow((double)(env->p.M + 1), (double)env->p.NA);
+    return n < 9.0e18 ? (int64_t)llround(n) : -1;
+}
+
+int dcb_test_actions(dcb_env *env, int32_t env_index, int64_t first, int64_t count, double *d_rewards, void *stream) {
+    if (!env || !d_rewards) return fail(DCB_ERR_INVALID_ARG, "null argument");
+    const DevParams &p = env->p;
+    if (env_index < 0 || env_index >= p.K) return fail(DCB_ERR_INVALID_ARG, "env %d outside [0, %d)", env_index, p.K);
+    if (p.NA > 16) return fail(DCB_ERR_UNSUPPORTED, "brute force over %d UEs (at most 16)", p.NA);
+    const int64_t total = dcb_num_joint_actions(env);
+    if (total < 0) return fail(DCB_ERR_UNSUPPORTED, "(%d + 1)^%d joint actions do not fit 63 bits", p.M, p.NA);
+    if (first < 0 || count < 0 || first + count > total)
+        return fail(DCB_ERR_INVALID_ARG, "candidates [%lld, %lld) outside [0, %lld)", (long long)first,
+                    (long long)(first + count), (long long)total);
+    if (count == 0) return DCB_OK;
+    DeviceGuard guard(env->device);
+    BruteArgs a;
+    a.p = p; a.env = env_index; a.first = first; a.count = count; a.rewards = d_rewards;
+    CU(dcb_launch_brute(a, (cudaStream_t)stream));
+    env->launches++;
+    return DCB_OK;
+}
+
 int dcb_get_ue_ids(dcb_env *env, int32_t *host_ids) {
     if (!env || !host_ids) return fail(DCB_ERR_INVALID_ARG, "null argument");
     DeviceGuard guard(env->device);

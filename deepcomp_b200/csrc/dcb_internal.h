@@ -221,6 +221,15 @@ struct PopArgs {
     int32_t *actions;           // [K][N] this step's actions (follow their UEs when slots shift) or NULL
 };
 
+// Brute-force candidate evaluation (dcb_brute.cu)
+struct BruteArgs {
+    DevParams p;
+    int env;                 // which env of the batch
+    long long first, count;  // candidates [first, first + count) in the reference's enumeration (brute_force.py:59-62)
+    double *rewards;         // [count] central step reward of each candidate
+};
+cudaError_t dcb_launch_brute(const BruteArgs &a, cudaStream_t s);
+
 cudaError_t dcb_launch_generate(const GenArgs &a, cudaStream_t s);
 cudaError_t dcb_launch_population(const PopArgs &a, cudaStream_t s);
 cudaError_t dcb_launch_iota_uid(int32_t *uid, int K, int N, cudaStream_t s);

@@ -207,6 +207,17 @@ int dcb_step_host(dcb_env *env, const int32_t *h_actions, float *h_obs, float *h
 /* Sticky device-side error flags (action range, table exhaustion) since the last call; synchronises the stream. */
 int dcb_check_errors(dcb_env *env, void *stream);
 
+/*
+ * Brute-force search support: the central step reward (central.py:65-73, the handle's `reward` aggregation) of the joint
+ * actions [first, first + count) of env `env_index`, each tried on the env's current state as MobileEnv.test_ue_actions
+ * does (base.py:284-313: apply, rates, EWMA update, rates and rewards; the state itself is left untouched).  Candidate c
+ * is the action vector whose entries are the digits of c in base M + 1, first UE = most significant digit
+ * (agent/brute_force.py:26-62); BruteForceAgent takes the first maximum (brute_force.py:90-92).  d_rewards: device
+ * double [count].  At most 16 UEs; dcb_num_joint_actions = (M + 1)^num_ue or -1 if it does not fit 63 bits.
+ */
+int64_t dcb_num_joint_actions(const dcb_env *env);
+int dcb_test_actions(dcb_env *env, int32_t env_index, int64_t first, int64_t count, double *d_rewards, void *stream);
+
 /* State snapshot / injection (synchronous). */
 int dcb_get_state(dcb_env *env, dcb_state_host *state);
 int dcb_set_state(dcb_env *env, const dcb_state_host *state);

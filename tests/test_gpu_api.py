@@ -465,3 +465,60 @@ def test_padding_slots_match_a_smaller_population(kind, reward, wide, monkeypatc
     assert_exact(sa['pos'][:, :act], sb['pos'], 'pos')
     assert_exact(a.mask_matrix(sa['mask'])[:, :act], b.mask_matrix(sb['mask']), 'mask')
     a.check_errors(); b.check_errors()
+
+
+# ------------------------------------------------------------------------------------------------ brute force
+@pytest.mark.parametrize('name', __import__('helpers').brute_names())
+def test_brute_force_matches_reference(name):
+    """dcb_test_actions: the reward of EVERY joint action as the reference's BruteForceAgent measures it with
+    MobileEnv.test_ue_actions (agent/brute_force.py:59-94, base.py:284-313), the action it takes, and the trajectory
+    that follows -- through the CentralRelNormEnv facade."""
+    from deepcomp_b200.agents import BruteForceAgent
+    from deepcomp_b200.env import get_env_class
+    cfg, z = load_golden(name)
+    env = get_env_class('central')(_env_config_from_golden(cfg))
+    agent = BruteForceAgent(env=env)
+    M = len(cfg['bs_xy'])
+    assert env._batch.num_joint_actions == (M + 1) ** cfg['n_ue'] == z['cand_rewards'].shape[1]
+    obs = env.reset()
+    for t in range(cfg['steps']):
+        before = env._batch.get_state()
+        rew = env._batch.test_actions().cpu().numpy()
+        assert_close(rew, z['cand_rewards'][t], f'{name}.cand_rewards[{t}]', 1e-9, 1e-9)
+        after = env._batch.get_state()
+        for k in before:                                    # testing does not touch the env
+            assert np.array_equal(before[k], after[k]), k
+        a = agent.compute_action(obs)
+        assert_exact(np.asarray(a), z['actions'][t], f'{name}.action[{t}]')
+        assert agent.get_ith_action(int(np.argmax(z['cand_rewards'][t]))) == list(a)
+        obs, reward, done, info = env.step(np.asarray(a, dtype=np.int64))
+        assert_close(reward, z['step_reward'][t], f'{name}.reward[{t}]', 2e-6, 1e-6)
+        assert_exact(np.array([[u.pos.x, u.pos.y] for u in env.ue_list]), z['step_pos'][t], 'ue.pos')
+    env.close()
+
+
+def test_brute_force_over_a_million_joint_actions():
+    """4^10 candidates of a 10-UE, 3-BS env in one call; chunked evaluation gives the same rewards and the same best."""
+    from deepcomp_b200 import BatchedMobileEnv
+    from oracle.deepcomp_oracle import OracleEnv
+    bs, wh = [(10, 10), (110, 10), (60, 96.60254037844386)], (120, 106)
+    env = BatchedMobileEnv(num_envs=3, n_ue=10, bs_xy=bs, map_wh=wh, kind='central', seeds=[5, 2000, 4000], reward='avg')
+    env.reset()
+    a = torch.randint(0, 4, (8, 3, 10), dtype=torch.int32, device='cuda', generator=torch.Generator('cuda').manual_seed(2))
+    env.step_many(a)
+    n = env.num_joint_actions
+    assert n == 4 ** 10
+    full = env.test_actions(env_index=1)
+    parts = torch.cat([env.test_actions(1, f, min(300000, n - f)) for f in range(0, n, 300000)])
+    assert torch.equal(full, parts)
+    act, best = env.best_joint_action(1, chunk=1 << 18)
+    assert best == float(full.max()) and act == env.candidate_action(int((full == full.max()).nonzero()[0, 0]))
+    # spot check against the oracle's test_ue_actions on the same state
+    orc = OracleEnv('central', 10, bs, wh, seed=2000, reward='avg')
+    orc.reset()
+    for t in range(8):
+        orc.step(a[t, 1].cpu().numpy())
+    rng = np.random.default_rng(0)
+    for c in [0, n - 1, int(np.argmax(full.cpu().numpy()))] + rng.integers(0, n, 20).tolist():
+        want = float(orc.step_reward(orc.test_ue_actions(orc.candidate_action(c))))
+        assert abs(float(full[c]) - want) <= 1e-9 + 1e-9 * abs(want), c
