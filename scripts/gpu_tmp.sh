@@ -1,6 +1,12 @@
 cd $GRAFT_REPO_ROOT
-run() { timeout 120 python bench.py --steps 3000 --warmup 300 --no-cpu-baseline --e2e-steps 5 "$@" | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('env-steps/s %.4e'%d['value'], 'us/step %.2f'%(1e3*d['ms_per_step']), d['config']['launch_geometry'])"; }
-for s in 2 4 8; do echo "S=$s"; DCB_REDUCE_LANES=$s run; done
-echo central; run --kind central
-echo cfg3; run --n-ue 200 --n-bs 20 --envs 512 --fragment 50 --steps 1000 --warmup 100
-echo k16384; run --envs 16384 --fragment 25 --steps 200 --warmup 50
+python - <<'PY'
+import time, torch, numpy as np
+from deepcomp_b200 import BatchedMobileEnv
+bs, wh = [(10, 10), (110, 10), (60, 96.60254037844386)], (120, 106)
+for n_ue in (10, 12):
+    env = BatchedMobileEnv(num_envs=1, n_ue=n_ue, bs_xy=bs, map_wh=wh, kind='central', seeds=[5], reward='avg')
+    env.reset()
+    env.test_actions(0, 0, 1000); torch.cuda.synchronize()
+    t0 = time.perf_counter(); r = env.test_actions(); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    print(f'{n_ue} UEs x 3 BS: {env.num_joint_actions} joint actions in {dt*1e3:.2f} ms = {env.num_joint_actions/dt:.3e} candidates/s')
+PY
