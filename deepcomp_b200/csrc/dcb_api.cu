@@ -124,14 +124,19 @@ int choose_envs_per_cta(int K, int N, int M, int kind, int num_sms, size_t smem_
         const int grid = (K + E - 1) / E;
         const long slots = (long)num_sms * per_sm;
         const long waves = (grid + slots - 1) / slots;
-        const double slot_eff = (double)grid / (double)(waves * slots);          // CTA slots doing work
+        // SMs that get work at all, and -- over several waves -- how full the last wave is (free CTA slots of a
+        // single wave cost nothing)
+        const double sm_cover = (double)(grid < num_sms ? grid : num_sms) / num_sms;
+        const double tail = waves > 1 ? (double)grid / (double)(waves * slots) : 1.0;
+        // CTAs per SM are whole numbers: the busiest SM sets the time of a single wave
+        const double balance = waves > 1 ? 1.0 : ((double)grid / num_sms) / (double)((grid + num_sms - 1) / num_sms);
         const double lane_util = (double)(E * N) / group;
         const double env_util = (double)K / ((double)grid * E);
         double resident = (double)grid / num_sms;
         if (resident > per_sm) resident = per_sm;
         const double warps = resident * threads / 32.0;
         const double occ = warps >= 32.0 ? 1.0 : 0.5 + 0.5 * warps / 32.0;       // latency hiding saturates
-        const double score = lane_util * env_util * slot_eff * occ;
+        const double score = lane_util * env_util * sm_cover * tail * (grid >= num_sms ? balance : 1.0) * occ;
         if (score > best_score) { best_score = score; best_e = E; }
     }
     return best_e;
