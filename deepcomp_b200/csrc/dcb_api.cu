@@ -87,7 +87,9 @@ struct dcb_env {
     int32_t *d_uid = nullptr;
     uint32_t *d_map_draws = nullptr, *d_glob_draws = nullptr;
     int na_reset = 0;        // UEs present after a reset (the original ue_list, base.py:176-182)
-    bool pop_dirty = false;  // slots were shifted / filled since the last reset: the next reset regenerates the tables
+    bool pop_used = false;   // the population has changed at least once: resets go through the re-seeding path from then on
+    long long *d_ue_seed = nullptr;                      // per original UE: seed / draws consumed since that seeding
+    uint32_t *d_ue_pos_used = nullptr, *d_ue_mv_used = nullptr;
     int32_t *d_env_ids = nullptr;
     int env_ids_cap = 0;
     // scripted policies (dcb_rollout)
@@ -209,6 +211,7 @@ void dcb_destroy(dcb_env *env) {
     cudaFree(env->d_table); cudaFree(env->d_pos_skip); cudaFree(env->d_mv_skip); cudaFree(env->d_env_ids);
     cudaFree(env->d_cluster); cudaFree(env->d_fixed);
     cudaFree(env->d_uid); cudaFree(env->d_map_draws); cudaFree(env->d_glob_draws);
+    cudaFree(env->d_ue_seed); cudaFree(env->d_ue_pos_used); cudaFree(env->d_ue_mv_used);
     cudaFree(env->d_h_actions); cudaFree(env->d_h_obs); cudaFree(env->d_h_reward); cudaFree(env->d_h_lost);
     delete env;
 }
@@ -390,6 +393,7 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     g.K = K; g.N = N; g.D = D; g.W = cfg->map_width; g.H = cfg->map_height; g.border_buffer = cfg->border_buffer;
     g.seeds = env->d_seeds; g.vel_spec = env->d_vel; g.init_xy = env->d_init_xy;
     g.pos_skip = nullptr; g.mv_skip = nullptr; g.env_ids = nullptr; g.n_ids = 0;
+    g.ue_seed = nullptr; g.ue_pos_skip = nullptr;
     g.init_pos = env->d_init_pos; g.table = env->d_table;
     ResetArgs r;
     r.K = K; r.N = N; r.D = D; r.env_ids = nullptr; r.n_ids = 0; r.init_pos = env->d_init_pos; r.table = env->d_table;
@@ -428,23 +432,30 @@ int dcb_reset(dcb_env *env, const int32_t *host_env_ids, int32_t n, void *stream
         CU(cudaMemcpyAsync(env->d_env_ids, host_env_ids, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
         d_ids = env->d_env_ids;
     }
-    if (env->pop_dirty) {
-        // base.py:176-182: back to the original ue_list; slots were shifted / overwritten by arrivals and departures, so
-        // the tables of the original UEs are drawn again (documented divergence: the originals are re-seeded by their
-        // ORIGINAL index), and map.rng / the global `random` module restart with the env seed (base.py:134-136)
+    if (env->pop_used) {
+        // Reset of a batch whose population has changed (base.py:169-189).  MobileEnv.seed runs FIRST and walks the
+        // current list -- the UE at list position p gets seed + 100 (p + 1), whoever it is; original UEs that left the
+        // list keep their generators and continue their streams -- then the original list comes back and every UE of
+        // it draws its position and first waypoint.  map.rng / the global `random` module restart (base.py:134-136).
         if (host_env_ids) return fail(DCB_ERR_UNSUPPORTED, "partial reset of a batch whose UE population changed");
+        const size_t KN = (size_t)p.K * p.N;
+        ReseedArgs r;
+        r.K = p.K; r.N = p.N; r.NA = p.NA; r.n_orig = env->na_reset; r.seeds = env->d_seeds; r.uid = env->d_uid;
+        r.ue_seed = env->d_ue_seed; r.ue_pos_used = env->d_ue_pos_used; r.ue_mv_used = env->d_ue_mv_used;
+        CU(dcb_launch_pop_reseed(r, s));
         GenArgs g;
         g.K = p.K; g.N = p.N; g.D = p.D; g.W = env->cfg.map_width; g.H = env->cfg.map_height;
         g.border_buffer = env->cfg.border_buffer;
         g.seeds = env->d_seeds; g.vel_spec = env->d_vel; g.init_xy = env->d_init_xy;
-        g.pos_skip = nullptr; g.mv_skip = nullptr; g.env_ids = nullptr; g.n_ids = 0;
+        g.pos_skip = nullptr; g.mv_skip = env->d_ue_mv_used; g.env_ids = nullptr; g.n_ids = 0;
+        g.ue_seed = env->d_ue_seed; g.ue_pos_skip = env->d_ue_pos_used;
         g.init_pos = env->d_init_pos; g.table = env->d_table;
         CU(dcb_launch_generate(g, s));
+        CU(dcb_launch_add_u32(env->d_ue_pos_used, (long long)KN, 1u, s));      // this reset's reset_pos() draw
         CU(dcb_launch_iota_uid(env->d_uid, p.K, p.N, s));
         CU(cudaMemsetAsync(env->d_map_draws, 0, sizeof(uint32_t) * p.K, s));
         CU(cudaMemsetAsync(env->d_glob_draws, 0, sizeof(uint32_t) * p.K, s));
-        env->launches += 2;
-        env->pop_dirty = false;
+        env->launches += 4;
     }
     env->p.NA = env->na_reset;
     if (env->cfg.rand_episodes) {
@@ -455,6 +466,7 @@ int dcb_reset(dcb_env *env, const int32_t *host_env_ids, int32_t n, void *stream
         g.border_buffer = env->cfg.border_buffer;
         g.seeds = env->d_seeds; g.vel_spec = env->d_vel; g.init_xy = env->d_init_xy;
         g.pos_skip = env->d_pos_skip; g.mv_skip = env->d_mv_skip; g.env_ids = d_ids; g.n_ids = n;
+        g.ue_seed = nullptr; g.ue_pos_skip = nullptr;
         g.init_pos = env->d_init_pos; g.table = env->d_table;
         CU(dcb_launch_generate(g, s));
         env->launches += 2;
@@ -509,7 +521,9 @@ int dcb_get_ue_ids(dcb_env *env, int32_t *host_ids) {
     if (!env || !host_ids) return fail(DCB_ERR_INVALID_ARG, "null argument");
     DeviceGuard guard(env->device);
     CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(host_ids, env->d_uid, sizeof(int32_t) * (size_t)env->p.K * env->p.N, cudaMemcpyDeviceToHost));
+    const size_t n = (size_t)env->p.K * env->p.N;
+    CU(cudaMemcpy(host_ids, env->d_uid, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+    for (size_t j = 0; j < n; j++) host_ids[j] &= ~DCB_UID_ARRIVED;
     return DCB_OK;
 }
 
@@ -532,6 +546,17 @@ int dcb_population_event(dcb_env *env, int32_t n_add, int32_t n_remove, int32_t 
     for (int i = 0; i < p.N; i++)
         if (vel[i] != DCB_VELOCITY_SLOW)
             return fail(DCB_ERR_UNSUPPORTED, "variable UE population needs 'slow' UEs in every slot (slot %d is not)", i);
+    if (!env->pop_used) {
+        // per original UE: the seed of its generators and how far its two streams got (all as after a plain reset:
+        // seed + 100 (i + 1), one reset_pos() draw, table row starting at the stream's first entry)
+        const size_t KN = (size_t)p.K * p.N;
+        CU(cudaMalloc((void **)&env->d_ue_seed, sizeof(long long) * KN));
+        CU(cudaMalloc((void **)&env->d_ue_pos_used, sizeof(uint32_t) * KN));
+        CU(cudaMalloc((void **)&env->d_ue_mv_used, sizeof(uint32_t) * KN));
+        CU(dcb_launch_pop_seed_init(env->d_ue_seed, env->d_ue_pos_used, env->d_ue_mv_used, env->d_seeds, p.K, p.N, s));
+        CU(dcb_launch_add_u32(env->d_ue_pos_used, (long long)KN, 1u, s));
+        env->pop_used = true;
+    }
     PopArgs a;
     a.K = p.K; a.N = p.N; a.D = p.D; a.W = env->cfg.map_width; a.H = env->cfg.map_height;
     a.border_buffer = env->cfg.border_buffer;
@@ -539,10 +564,10 @@ int dcb_population_event(dcb_env *env, int32_t n_add, int32_t n_remove, int32_t 
     a.seeds = env->d_seeds; a.map_draws = env->d_map_draws; a.glob_draws = env->d_glob_draws; a.uid = env->d_uid;
     a.pos = env->d_pos; a.mv = env->d_mv; a.mask = env->d_mask; a.ewma = env->d_ewma; a.table = env->d_table;
     a.actions = d_actions;
+    a.n_orig = env->na_reset; a.ue_mv_used = env->d_ue_mv_used;
     CU(dcb_launch_population(a, s));
     env->launches++;
     env->p.NA = p.NA - n_remove + n_add;
-    env->pop_dirty = true;
     return DCB_OK;
 }
 

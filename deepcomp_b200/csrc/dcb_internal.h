@@ -184,6 +184,8 @@ struct GenArgs {
     const double *init_xy;      // [N][2]
     const uint32_t *pos_skip;   // [K] reset_pos() calls already consumed per env (rand_episodes) or NULL
     const uint32_t *mv_skip;    // [K*N] movement.reset() calls already consumed per UE or NULL
+    const long long *ue_seed;   // [K*N] seed per UE instead of seeds[k] + 100 (i + 1), or NULL (variable population)
+    const uint32_t *ue_pos_skip; // [K*N] reset_pos() calls already consumed per UE (instead of pos_skip[k]) or NULL
     const int32_t *env_ids;     // [n_ids] or NULL = all envs
     int n_ids;
     double2 *init_pos;          // [K*N]
@@ -204,6 +206,10 @@ struct ResetArgs {
     uint32_t *pos_skip;   // rand_episodes: bumped once per reset env, else NULL
 };
 
+// uid slab: User.id as an integer; arrivals carry this flag (an arrival's id is the last id + 1 and can repeat the id of
+// an original UE that has left -- they are different UEs with different generators)
+#define DCB_UID_ARRIVED 0x40000000
+
 // Arrival / departure of UEs (single_ue/base.py:433-443, 592-617), one thread per env
 struct PopArgs {
     int K, N, D, W, H, border_buffer;
@@ -219,7 +225,24 @@ struct PopArgs {
     double *ewma;
     uint32_t *table;            // [K*N][D]
     int32_t *actions;           // [K][N] this step's actions (follow their UEs when slots shift) or NULL
+    int n_orig;                 // UEs of the original list (ids 1..n_orig)
+    uint32_t *ue_mv_used;       // [K*N] movement.reset() draws an ORIGINAL UE has consumed since its last seeding
 };
+
+// reset() of a batch whose population changed (single_ue/base.py:169-189): MobileEnv.seed first re-seeds the UEs of the
+// CURRENT list by list position, then the original list comes back
+struct ReseedArgs {
+    int K, N, NA, n_orig;
+    const long long *seeds;     // [K]
+    const int32_t *uid;         // [K*N] current list (ids per slot)
+    long long *ue_seed;         // [K*N] per ORIGINAL UE: seed of its generators
+    uint32_t *ue_pos_used;      // [K*N] ... reset_pos() draws since that seeding
+    uint32_t *ue_mv_used;       // [K*N] ... movement.reset() draws since that seeding
+};
+cudaError_t dcb_launch_pop_reseed(const ReseedArgs &a, cudaStream_t s);
+cudaError_t dcb_launch_pop_seed_init(long long *ue_seed, uint32_t *pos_used, uint32_t *mv_used, const long long *seeds,
+                                     int K, int N, cudaStream_t s);
+cudaError_t dcb_launch_add_u32(uint32_t *a, long long n, uint32_t v, cudaStream_t s);
 
 // Brute-force candidate evaluation (dcb_brute.cu)
 struct BruteArgs {

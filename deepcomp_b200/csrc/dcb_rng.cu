@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(128) dcb_generate_kernel(GenArgs a) {
     const int i = (int)(t % a.N);
     const int k = a.env_ids ? a.env_ids[slot] : slot;
     const long long u = (long long)k * a.N + i;
-    const long long seed = a.seeds[k] + 100ll * (i + 1);
+    const long long seed = a.ue_seed ? a.ue_seed[u] : a.seeds[k] + 100ll * (i + 1);
 
     MT g;
     // ---- User.rng: initial position (user.py:98-109); earlier episodes' draws are skipped (rand_episodes)
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(128) dcb_generate_kernel(GenArgs a) {
     double px = ix, py = iy;
     if (rx || ry) {
         mt_seed(g, seed);
-        const uint32_t skip = a.pos_skip ? a.pos_skip[k] : 0u;
+        const uint32_t skip = a.ue_pos_skip ? a.ue_pos_skip[u] : (a.pos_skip ? a.pos_skip[k] : 0u);
         for (uint32_t e = 0; e <= skip; e++) {
             if (rx) px = (double)mt_randint(g, 0, a.W);
             if (ry) py = (double)mt_randint(g, 0, a.H);
@@ -175,6 +175,9 @@ __global__ void __launch_bounds__(64) dcb_population_kernel(PopArgs a) {
         for (uint32_t s = a.glob_draws[k]; s; s--) mt_next(g);
         const int idx = mt_randint(g, 0, na - 1);
         a.glob_draws[k] = g.drawn;
+        // an original UE that leaves keeps its generators (it is not in the list MobileEnv.seed walks at the next
+        // reset, base.py:138-143): remember how far its movement stream got
+        if (!(a.uid[base + idx] & DCB_UID_ARRIVED)) a.ue_mv_used[base + a.uid[base + idx] - 1] += a.mv[base + idx].y >> 16;
         for (int j = idx; j < na - 1; j++) {
             const long long d = base + j, s = d + 1;
             a.pos[d] = a.pos[s]; a.mv[d] = a.mv[s]; a.mask[d] = a.mask[s]; a.ewma[d] = a.ewma[s]; a.uid[d] = a.uid[s];
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(64) dcb_population_kernel(PopArgs a) {
         else if (side == 2) { px = (double)x; py = (double)(a.H - 1); }
         else { px = (double)x; py = 0.0; }
         const long long d = base + na;
-        const int new_id = a.uid[d - 1] + 1;
+        const int new_id = (a.uid[d - 1] & ~DCB_UID_ARRIVED) + 1;     // may repeat the id of an original UE that left
         mt_seed(g, a.seeds[k] + 100ll * new_id);
         uint32_t *row = a.table + d * a.D;
         for (int e = 0; e < a.D; e++) {
@@ -215,10 +218,40 @@ __global__ void __launch_bounds__(64) dcb_population_kernel(PopArgs a) {
         a.mv[d] = make_uint2((e0 & 0x3fffu) | (((e0 >> 14) & 0x3fffu) << 16), (e0 >> 28) | (1u << 16));
         a.mask[d] = 0ull;
         a.ewma[d] = 0.0;
-        a.uid[d] = new_id;
+        a.uid[d] = new_id | DCB_UID_ARRIVED;
         if (a.actions) a.actions[d] = 0;
         na++;
     }
+}
+
+// MobileEnv.seed at reset (base.py:132-143, 171-173) walks the CURRENT list: the UE at list position p gets seed + 100 (p + 1)
+// for both of its generators.  Original UEs that left the list are not touched and continue their streams.
+__global__ void dcb_pop_reseed_kernel(ReseedArgs a) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.K) return;
+    const long long base = (long long)k * a.N;
+    for (int p = 0; p < a.NA; p++) {
+        const int id = a.uid[base + p];
+        if (!(id & DCB_UID_ARRIVED)) {       // an original UE (ids of arrivals can repeat those of originals that left)
+            a.ue_seed[base + id - 1] = a.seeds[k] + 100ll * (p + 1);
+            a.ue_pos_used[base + id - 1] = 0u;
+            a.ue_mv_used[base + id - 1] = 0u;
+        }
+    }
+}
+
+__global__ void dcb_pop_seed_init_kernel(long long *ue_seed, uint32_t *pos_used, uint32_t *mv_used, const long long *seeds,
+                                         long long n, int N) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    ue_seed[t] = seeds[t / N] + 100ll * ((t % N) + 1);
+    pos_used[t] = 0u;
+    mv_used[t] = 0u;
+}
+
+__global__ void dcb_add_u32_kernel(uint32_t *a, long long n, uint32_t v) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) a[t] += v;
 }
 
 __global__ void dcb_iota_uid_kernel(int32_t *uid, long long n, int N) {
@@ -230,6 +263,23 @@ __global__ void dcb_iota_uid_kernel(int32_t *uid, long long n, int N) {
 
 cudaError_t dcb_launch_population(const PopArgs &a, cudaStream_t s) {
     dcb_population_kernel<<<(a.K + 63) / 64, 64, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t dcb_launch_pop_reseed(const ReseedArgs &a, cudaStream_t s) {
+    dcb_pop_reseed_kernel<<<(a.K + 63) / 64, 64, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t dcb_launch_pop_seed_init(long long *ue_seed, uint32_t *pos_used, uint32_t *mv_used, const long long *seeds,
+                                     int K, int N, cudaStream_t s) {
+    const long long n = (long long)K * N;
+    dcb_pop_seed_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ue_seed, pos_used, mv_used, seeds, n, N);
+    return cudaGetLastError();
+}
+
+cudaError_t dcb_launch_add_u32(uint32_t *a, long long n, uint32_t v, cudaStream_t s) {
+    dcb_add_u32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, n, v);
     return cudaGetLastError();
 }
 

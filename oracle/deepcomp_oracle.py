@@ -130,12 +130,9 @@ class OracleEnv:
     RandomWaypoint movement, log utility, the four sharing models, fixed or variable UE population (`max_ues`,
     `ue_arrival`, `new_ue_interval`: base.py:80-84, 433-443, 592-617; per-UE arrays are padded to max_ues).
 
-    Variable population, documented divergence: the reference's reset() re-seeds the UEs of the *current* list by their
-    current list position before it restores the original list (base.py:132-143, 169-189), so after removals an original
-    UE can come back with another UE's seed, and an original UE that was removed keeps drawing from its old streams.
-    This restatement (like the CUDA path) resets to the state a fresh env would have: originals re-seeded by their
-    original index.  The first episode is bit-identical to the reference; later episodes only if no original UE
-    changed its list position.
+    Variable population: as in the reference, reset() re-seeds the UEs of the *current* list by their current list
+    position before it restores the original list (base.py:132-143, 169-189) -- after departures an original UE can
+    come back with another UE's seed, and an original UE that was removed keeps drawing from its old streams.
 
     kind: 'central' (multi_ue/central.py:143-152) or 'multi' (multi_ue/multi_agent.py:6-107)
     """
@@ -218,9 +215,9 @@ class OracleEnv:
 
     def reset(self):
         """single_ue/base.py:169-189; user.py:98-116; station.py:106-108"""
-        self.ues = list(self.original_ues)                      # base.py:176-182 (see the class docstring: restored
-        if not self.rand_episodes:                              # BEFORE seeding here)
-            self.seed(self.env_seed)
+        if not self.rand_episodes:
+            self.seed(self.env_seed)                            # base.py:171-173: seeds the CURRENT list by position ...
+        self.ues = list(self.original_ues)                      # base.py:176-182: ... then restores the original list
         self.time = 0
         for ue in self.ues:
             px = ue.init_x

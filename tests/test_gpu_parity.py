@@ -95,28 +95,30 @@ def test_cuda_step_matches_reference_golden(name, wide, monkeypatch):
 @pytest.mark.parametrize('wide', [False, True], ids=['fused', 'wide'])
 @pytest.mark.parametrize('name', population_names())
 def test_cuda_variable_population_matches_reference_golden(name, wide, monkeypatch):
-    """ue_arrival / new_ue_interval (base.py:429-443, 592-617) on envs with max_ues > num_ue: the first episode of the
-    reference's trace, every recorded array, through both kernels; then a reset brings the original population back
-    and replays the same episode (the reference re-seeds by list position there: documented divergence)."""
+    """ue_arrival / new_ue_interval (base.py:429-443, 592-617) on envs with max_ues > num_ue: both episodes of the
+    reference's trace, every recorded array, through both kernels.  The reset in between re-seeds the UEs of the list as
+    it stands by list position and then restores the original list (base.py:132-143, 169-189): originals that moved up
+    come back with another seed, originals that left continue their streams -- the second episode differs from the first."""
     if wide:
         monkeypatch.setenv('DCB_FORCE_WIDE', '1')
     cfg, z = load_golden(name)
     env = make_env(dict(oracle_kwargs(cfg), **population_kwargs(cfg)))
     step_keys = ('pos', 'mask', 'movement', 'ewma', 'snr', 'link_rates', 'curr_dr', 'utility', 'obs', 'lost_conn',
                  'time', 'reward', 'sum_utility')
-    first_obs = None
-    for ep in range(2):
+    t = 0
+    for ep in range(cfg['episodes']):
         dbg = env.reset(debug=True)
-        want = {k: z['reset_' + k][0] for k in ('pos', 'mask', 'movement', 'ewma', 'snr', 'link_rates', 'curr_dr',
-                                                'utility', 'obs')}
-        assert env.active_ues == int(z['reset_num_ue'][0])
+        want = {k: z['reset_' + k][ep] for k in ('pos', 'mask', 'movement', 'ewma', 'snr', 'link_rates', 'curr_dr',
+                                                 'utility', 'obs')}
+        assert env.active_ues == int(z['reset_num_ue'][ep])
         compare_step(env, dbg, want, 0, f'{name}.reset[{ep}]', step=False, num_ue=env.active_ues)
-        for t in range(cfg['steps']):
+        for _ in range(cfg['steps']):
             a = torch.as_tensor(z['actions'][t][None, :].astype(np.int32), device='cuda')
             dbg = env.step(a, debug=True)
             assert env.active_ues == int(z['step_num_ue'][t]), (name, t)
-            compare_step(env, dbg, {k: z['step_' + k][t] for k in step_keys}, 0, f'{name}.ep{ep}.step[{t}]',
+            compare_step(env, dbg, {k: z['step_' + k][t] for k in step_keys}, 0, f'{name}.step[{t}]',
                          num_ue=env.active_ues)
+            t += 1
     env.check_errors()
 
 
