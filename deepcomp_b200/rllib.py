@@ -28,6 +28,10 @@ class _BatchAdapter:
         scenario = dict(scenario)
         scenario['kind'] = self.kind
         self.batch = BatchedMobileEnv(num_envs=num_envs, **scenario)
+        if self.batch._dynamic:
+            # agent ids differ per env once UEs arrive / leave (per-env draws of who leaves): use the K = 1 classes of
+            # deepcomp_b200.env, which track them, or BatchedMobileEnv with ue_ids() directly
+            raise NotImplementedError("batch adapters with a variable UE population")
         self.num_envs = num_envs
         self.n_ue, self.n_bs = self.batch.n_ue, self.batch.n_bs
         self.agent_ids = [str(i + 1) for i in range(self.n_ue)]
