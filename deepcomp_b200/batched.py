@@ -45,7 +45,7 @@ class BatchedMobileEnv:
     def __init__(self, num_envs, n_ue, bs_xy, map_wh, kind='multi', sharing='mixed', velocities='slow', seed=0,
                  seeds=None, reward='avg', episode_length=100, rand_episodes=False, auto_reset=False, init_pos=None,
                  pause_duration=2, border_buffer=10, device=None, first_env=0, max_ues=None, ue_arrival=None,
-                 new_ue_interval=None):
+                 new_ue_interval=None, util_func='log', dr_req=1):
         """
         Variable UE population (reference env_config keys of the same names, base.py:80-84, 429-443): `n_ue` UEs at
         reset, `max_ues` slots per env (every per-UE array has max_ues rows; rows of UEs that are not there read as
@@ -134,6 +134,12 @@ class BatchedMobileEnv:
         self._pinned = None
         if self.num_ue_initial != self.n_ue:
             self.active_ues = self.num_ue_initial
+        if util_func not in ('log', 'step'):
+            # the reference's 'linear' utility asserts MIN_UTILITY == 0 (utility.py:18): unusable with its own constants
+            raise NotImplementedError(f"Utility function {util_func} not implemented!")           # user.py:92
+        self.util_func = util_func
+        if util_func != 'log':
+            check(self._L.dcb_set_utility(self._h, 1, float(dr_req)))
 
     # ------------------------------------------------------------------ plumbing
     def close(self):

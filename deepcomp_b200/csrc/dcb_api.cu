@@ -368,6 +368,7 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     p.episode_length = cfg->episode_length; p.auto_reset = cfg->auto_reset; p.pause_duration = cfg->pause_duration;
     p.D = D; p.E = E; p.S = S; p.CS = CS; p.LC = LC;
     p.has_maxcap = has_maxcap; p.has_propfair = has_pf;
+    p.util_step = 0; p.dr_req = 1.0;
     p.c1 = c1;
     p.c2 = c2;
     p.thr_d2 = thr_d2;
@@ -491,6 +492,15 @@ int dcb_set_active_ues(dcb_env *env, int32_t n_active) {
 }
 
 int32_t dcb_get_active_ues(const dcb_env *env) { return env ? env->p.NA : 0; }
+
+int dcb_set_utility(dcb_env *env, int32_t kind, double dr_req) {
+    if (!env) return fail(DCB_ERR_INVALID_ARG, "null handle");
+    if (kind != DCB_UTILITY_LOG && kind != DCB_UTILITY_STEP)
+        return fail(DCB_ERR_UNSUPPORTED, "Utility function %d not implemented!", kind);      // user.py:92
+    env->p.util_step = kind == DCB_UTILITY_STEP;
+    env->p.dr_req = dr_req;
+    return DCB_OK;
+}
 
 int64_t dcb_num_joint_actions(const dcb_env *env) {
     if (!env) return 0;

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) dcb_brute_kernel(BruteArgs a) {
     // ---- calc_reward (base.py:158-167) per UE, central step_reward (central.py:65-73)
     double agg = p.reward == DCB_REWARD_MIN ? CUDART_INF : 0.0;
     for (int i = 0; i < N; i++) {
-        const double r = log_utility(tab, dr[i]) / DCB_MAX_UTILITY;
+        const double r = ue_utility(p, tab, dr[i]) / DCB_MAX_UTILITY;
         agg = p.reward == DCB_REWARD_MIN ? (r < agg ? r : agg) : agg + r;
     }
     if (p.reward == DCB_REWARD_AVG) agg = agg / (double)N;

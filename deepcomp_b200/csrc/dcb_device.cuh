@@ -51,6 +51,13 @@ __device__ __forceinline__ double log_utility(const MathTables *tab, double dr) 
     return dr <= 0.01 ? DCB_MIN_UTILITY : (dr >= 100.0 ? DCB_MAX_UTILITY : c);
 }
 
+// User.dr_to_utility (user.py:81-92): 'log' or 'step' (+-20 around the required rate, utility.py:23-33); 'linear' cannot be
+// used with the reference's MIN/MAX_UTILITY = -20/20 (its assert, utility.py:18)
+__device__ __forceinline__ double ue_utility(const DevParams &p, const MathTables *tab, double dr) {
+    if (p.util_step) return dr >= p.dr_req ? DCB_MAX_UTILITY : DCB_MIN_UTILITY;
+    return log_utility(tab, dr);
+}
+
 // Value a connected link contributes to its BS's reduction, by sharing model (station.py:170-195):
 // resource-fair / max-cap: r0; rate-fair: 1/r0 (:178); proportional-fair: priority r0/(ewma + eps) (:150)
 __device__ __forceinline__ double link_value(int model, double r0, double inv_ewma_eps) {

@@ -36,6 +36,8 @@ struct DevParams {
     int S;               // reducer lanes per (env, BS) pair, power of two <= 32
     int CS;              // log2 of the bitset chunks per 32-UE word the reducer lanes deal out (0: whole words)
     int has_maxcap, has_propfair;
+    int util_step;       // 0: log utility (utility.py:36-54); 1: step utility (utility.py:23-33) at dr_req
+    double dr_req;       // User.dr_req (user.py:17-30)
     int LC;              // wide kernel: link slots per UE (bound on the base stations any point can be in range of)
     double thr_d2;       // largest squared distance that is still in range (snr > 2e-8, station.py:224)
     double c1, c2;       // Okumura-Hata constants (station.py:112-114)

@@ -398,7 +398,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                             Xrow[b] = r;
                             dr += r;                                                   // user.py:64-69
                         }
-                        if (need_rb) rb = log_utility(tab, dr) * (1.0 / DCB_MAX_UTILITY);
+                        if (need_rb) rb = ue_utility(p, tab, dr) * (1.0 / DCB_MAX_UTILITY);
                     }
                 } else {
                     mask = mask_next;
@@ -534,8 +534,8 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                     if ((mask_next >> b) & 1) dr_pre += r_pre;                         // user.py:64-69
                     Xrow[b] = r_pre;
                 }
-                const double util = log_utility(tab, dr);
-                if (need_rb) rb_next = log_utility(tab, dr_pre) * (1.0 / DCB_MAX_UTILITY);
+                const double util = ue_utility(p, tab, dr);
+                if (need_rb) rb_next = ue_utility(p, tab, dr_pre) * (1.0 / DCB_MAX_UTILITY);
                 const int h = par * EN + t;
                 hx[h] = x; hy[h] = y; hmask[h] = mask;
                 hutil[h] = util;

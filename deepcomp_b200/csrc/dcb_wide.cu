@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                     Xrow[slot] = r;
                     dr0 += r;                                                          // user.py:64-69
                 }
-                rb = log_utility(tab, dr0) * (1.0 / DCB_MAX_UTILITY);
+                rb = ue_utility(p, tab, dr0) * (1.0 / DCB_MAX_UTILITY);
                 // ---- User.move (user.py:159-173), check_bs_connection (user.py:175-188), update_ewma_dr (user.py:148-157)
                 ue_move<false>(p, u, vfix, vfix_thr, S.vthr, x, y, wxy, vpt, nullptr);
                 double keep = 0.0;
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                 if (last && a.out.dbg_link_rate) a.out.dbg_link_rate[u * M + b] = r;
                 dr += r;
             }
-            util = log_utility(tab, dr);
+            util = ue_utility(p, tab, dr);
             S.su[i] = util;
             S.srb[i] = rb;
             // ---- per-UE info outputs (base.py:383-411)

@@ -40,10 +40,11 @@ def _parse_env_config(env_config):
                 curr += arrival
                 max_ues = max(max_ues, curr)
     assert max_ues >= len(ue_list)                                                        # base.py:84
-    velocities, init_pos, pauses, borders = [], [], set(), set()
+    velocities, init_pos, pauses, borders, utils = [], [], set(), set(), set()
     for ue in ue_list:
-        if getattr(ue, 'util_func', 'log') != 'log':
+        if getattr(ue, 'util_func', 'log') not in ('log', 'step'):
             raise NotImplementedError(f"Utility function {ue.util_func} not implemented!")   # user.py:92
+        utils.add((getattr(ue, 'util_func', 'log'), getattr(ue, 'dr_req', 1)))
         mv = ue.movement
         if not hasattr(mv, 'init_velocity'):
             raise NotImplementedError("only RandomWaypoint movement is in scope (movement.py:82-181)")
@@ -53,11 +54,15 @@ def _parse_env_config(env_config):
         borders.add(mv.border_buffer)
     if len(pauses) != 1 or len(borders) != 1:
         raise NotImplementedError("per-UE pause_duration / border_buffer are not supported")
+    if len(utils) != 1:
+        raise NotImplementedError("per-UE utility functions / required rates are not supported")
+    util_func, dr_req = utils.pop()
     return dict(n_ue=len(ue_list), bs_xy=[(float(bs.pos.x), float(bs.pos.y)) for bs in bs_list],
                 map_wh=(int(m.width), int(m.height)), sharing=[bs.sharing_model for bs in bs_list],
                 velocities=velocities, init_pos=init_pos, pause_duration=pauses.pop(), border_buffer=borders.pop(),
                 episode_length=env_config['episode_length'], rand_episodes=bool(env_config['rand_episodes']),
-                max_ues=int(max_ues), ue_arrival=env_config['ue_arrival'], new_ue_interval=env_config['new_ue_interval'])
+                max_ues=int(max_ues), ue_arrival=env_config['ue_arrival'], new_ue_interval=env_config['new_ue_interval'],
+                util_func=util_func, dr_req=dr_req)
 
 
 class _MobileEnvFacade:
@@ -109,7 +114,8 @@ class _MobileEnvFacade:
             sharing=sc['sharing'], velocities=sc['velocities'], seeds=[seed], reward=self.reward_agg,
             episode_length=sc['episode_length'], rand_episodes=sc['rand_episodes'], init_pos=sc['init_pos'],
             pause_duration=sc['pause_duration'], border_buffer=sc['border_buffer'], device=self._device,
-            max_ues=sc['max_ues'], ue_arrival=sc['ue_arrival'], new_ue_interval=sc['new_ue_interval'])
+            max_ues=sc['max_ues'], ue_arrival=sc['ue_arrival'], new_ue_interval=sc['new_ue_interval'],
+            util_func=sc['util_func'], dr_req=sc['dr_req'])
 
     # ---- MobileEnv attributes
     @property

@@ -179,6 +179,15 @@ int dcb_population_event(dcb_env *env, int32_t n_add, int32_t n_remove, int32_t 
 /* UE ids per slot, host int32 [K][n_ue] (User.id as an integer; slots >= dcb_get_active_ues are stale).  Synchronous. */
 int dcb_get_ue_ids(dcb_env *env, int32_t *host_ids);
 
+/*
+ * User.util_func (user.py:81-92; CLI --util): DCB_UTILITY_LOG (default, utility.py:36-54) or DCB_UTILITY_STEP
+ * (utility.py:23-33: MAX_UTILITY when the UE's rate reaches dr_req, else MIN_UTILITY; User.dr_req defaults to 1).  One
+ * setting per handle; takes effect with the next launch.  'linear' is not offered: the reference's own assert
+ * (utility.py:18) rules it out for MIN/MAX_UTILITY = -20/20.
+ */
+typedef enum dcb_utility { DCB_UTILITY_LOG = 0, DCB_UTILITY_STEP = 1 } dcb_utility;
+int dcb_set_utility(dcb_env *env, int32_t kind, double dr_req);
+
 /* get_obs() of the current state (central.py:31-57 / multi_agent.py:32-37) without stepping; reward is not written */
 int dcb_observe(dcb_env *env, const dcb_outputs *out, void *stream);
 

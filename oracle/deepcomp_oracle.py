@@ -139,8 +139,10 @@ class OracleEnv:
 
     def __init__(self, kind, n_ue, bs_xy, map_wh, sharing='mixed', velocities='slow', seed=None, reward='avg',
                  episode_length=100, rand_episodes=False, init_pos=None, pause_duration=2, border_buffer=10,
-                 max_ues=None, ue_arrival=None, new_ue_interval=None):
+                 max_ues=None, ue_arrival=None, new_ue_interval=None, util_func='log', dr_req=1):
         assert kind in ('central', 'multi')
+        assert util_func in ('log', 'step')                     # 'linear' fails the reference's own assert (utility.py:18)
+        self.util_func, self.dr_req = util_func, dr_req
         self.kind = kind
         self.n_ue = n_ue
         # variable population (base.py:80-84): per-UE arrays have max_ues rows, the UEs present come first
@@ -292,7 +294,9 @@ class OracleEnv:
         return sum(list(ue.bs_dr.values()))
 
     def utility(self, ue):
-        """user.py:76-92 (log utility only)"""
+        """user.py:76-92; env/util/utility.py:23-33 (step), 36-54 (log)"""
+        if self.util_func == 'step':
+            return MAX_UTILITY if self.curr_dr(ue) >= self.dr_req else MIN_UTILITY
         return log_utility(self.curr_dr(ue))
 
     def connect_to_bs(self, ue, b):

@@ -75,6 +75,16 @@ def population_scenarios():
     return S
 
 
+def utility_scenarios():
+    """User.util_func = 'step' (CLI --util step; user.py:81-92, env/util/utility.py:23-33)"""
+    S = []
+    W, H, gbs = rl.grid_layout(5)
+    for kind, reward in (('central', 'avg'), ('multi', 'avg'), ('multi', 'min'), ('multi', 'sum')):
+        S.append(dict(name=f'utilstep_{kind}_{reward}', kind=kind, n_ue=12, bs_xy=gbs, map_wh=(W, H), sharing='mixed',
+                      velocities='slow', seed=17, reward=reward, steps=50, action_seed=6, episodes=1, util_func='step'))
+    return S
+
+
 def brute_scenarios():
     """BruteForceAgent (deepcomp/agent/brute_force.py:59-94): all (M+1)^N joint actions tested with
     MobileEnv.test_ue_actions (single_ue/base.py:284-313) on the central env, the best one taken."""
@@ -173,7 +183,7 @@ def record(sc):
     env = rl.build_env(sc['kind'], sc['n_ue'], sc['seed'], sc['bs_xy'], sc['map_wh'], sharing=sc['sharing'],
                        velocities=sc['velocities'], reward=sc['reward'], episode_length=sc['steps'],
                        init_pos=sc.get('init_pos'), max_ues=sc.get('max_ues'), ue_arrival=sc.get('ue_arrival'),
-                       new_ue_interval=sc.get('new_ue_interval'))
+                       new_ue_interval=sc.get('new_ue_interval'), util_func=sc.get('util_func', 'log'))
     pop = 'max_ues' in sc
     n_act = sc.get('max_ues', sc['n_ue'])                # length of the action vector (central.py:28)
     tr = rl.RefTrace(env, sc['kind'])
@@ -270,7 +280,7 @@ def main():
     only = sys.argv[1] if len(sys.argv) > 1 else ''     # optional name prefix: regenerate a subset only
     if not only:
         np.savez_compressed(os.path.join(OUT_DIR, 'anchors.npz'), **anchors())
-    for sc in scenarios() + policy_scenarios() + population_scenarios() + brute_scenarios():
+    for sc in scenarios() + policy_scenarios() + population_scenarios() + brute_scenarios() + utility_scenarios():
         if not sc['name'].startswith(only):
             continue
         data = record_brute(sc) if sc['name'].startswith('brute_') else record(sc)

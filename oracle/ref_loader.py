@@ -56,7 +56,7 @@ def grid_layout(n_bs, pitch=100, border=10):
 
 def build_env(kind, n_ue, seed, bs_xy, map_wh, sharing='mixed', velocities='slow', reward='avg',
               episode_length=100, rand_episodes=False, init_pos=None, max_ues=None, ue_arrival=None,
-              new_ue_interval=None):
+              new_ue_interval=None, util_func='log'):
     """
     Build a reference env.
 
@@ -76,7 +76,7 @@ def build_env(kind, n_ue, seed, bs_xy, map_wh, sharing='mixed', velocities='slow
     for i in range(n_ue):
         px, py = ('random', 'random') if init_pos is None else init_pos[i]
         ue_list.append(R['User'](str(i + 1), m, pos_x=px, pos_y=py,
-                                 movement=R['RandomWaypoint'](m, velocity=velocities[i]), util_func='log'))
+                                 movement=R['RandomWaypoint'](m, velocity=velocities[i]), util_func=util_func))
     env_config = {
         'episode_length': episode_length, 'seed': seed, 'map': m, 'bs_list': bs_list, 'ue_list': ue_list,
         'rand_episodes': rand_episodes, 'new_ue_interval': new_ue_interval, 'reward': reward, 'max_ues': max_ues,

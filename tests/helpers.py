@@ -26,7 +26,12 @@ def _names():
 
 def golden_names():
     """fixed-population traces (every test that replays a trace step by step)"""
-    return [n for n in _names() if not n.startswith(('pop_', 'brute_'))]
+    return [n for n in _names() if not n.startswith(('pop_', 'brute_', 'utilstep_'))]
+
+
+def utility_names():
+    """traces with User.util_func = 'step' (CLI --util step)"""
+    return [n for n in _names() if n.startswith('utilstep_')]
 
 
 def brute_names():
@@ -58,7 +63,7 @@ def oracle_kwargs(cfg):
         init_pos = [tuple(p) for p in init_pos]
     return dict(kind=cfg['kind'], n_ue=cfg['n_ue'], bs_xy=[tuple(p) for p in cfg['bs_xy']], map_wh=tuple(cfg['map_wh']),
                 sharing=cfg['sharing'], velocities=cfg['velocities'], seed=cfg['seed'], reward=cfg['reward'],
-                episode_length=cfg['steps'], init_pos=init_pos)
+                episode_length=cfg['steps'], init_pos=init_pos, **({'util_func': cfg['util_func']} if 'util_func' in cfg else {}))
 
 
 def assert_close(a, b, what, rtol=RTOL, atol=ATOL):

@@ -6,7 +6,7 @@ import torch
 from oracle import c_oracle
 
 from helpers import (assert_close, assert_exact, golden_names, load_golden, oracle_kwargs, population_kwargs,
-                     population_names)
+                     population_names, utility_names)
 
 pytestmark = pytest.mark.gpu
 
@@ -68,7 +68,7 @@ def compare_step(env, dbg, want, k, what, step=True, num_ue=None):
 
 
 @pytest.mark.parametrize('wide', [False, True], ids=['fused', 'wide'])
-@pytest.mark.parametrize('name', golden_names())
+@pytest.mark.parametrize('name', golden_names() + utility_names())
 def test_cuda_step_matches_reference_golden(name, wide, monkeypatch):
     """K=1, one launch per step, every recorded array of the reference trace; through the fused kernel (dcb_step.cu)
     and through the one-CTA-per-env kernel for large envs (dcb_wide.cu, forced here for the small golden shapes)."""

@@ -6,7 +6,7 @@ from oracle import c_oracle
 from oracle import deepcomp_oracle as po
 
 from helpers import (GOLDEN_DIR, assert_close, assert_exact, brute_names, check_against_golden, golden_names, load_golden, oracle_kwargs, population_kwargs,
-                     population_names)
+                     population_names, utility_names)
 
 
 def test_anchor_known_answers():
@@ -88,3 +88,12 @@ def test_python_oracle_brute_force_matches_reference(name):
         assert_exact(s['pos'], z['step_pos'][t], f'{name}.pos[{t}]')
         assert_exact(s['mask'], z['step_mask'][t], f'{name}.mask[{t}]')
         assert_close(s['reward'], z['step_reward'][t], f'{name}.reward[{t}]', 1e-12, 1e-12)
+
+
+@pytest.mark.parametrize('name', utility_names())
+def test_python_oracle_step_utility_matches_reference(name):
+    """User.util_func = 'step' (CLI --util step; user.py:81-92, env/util/utility.py:23-33)"""
+    cfg, z = load_golden(name)
+    env = po.OracleEnv(**oracle_kwargs(cfg))
+    exact = not (cfg['kind'] == 'multi' and cfg['reward'] == 'sum')
+    check_against_golden(env, cfg, z, exact_floats=exact)
