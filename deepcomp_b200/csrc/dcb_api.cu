@@ -90,6 +90,7 @@ struct dcb_env {
     bool pop_used = false;   // the population has changed at least once: resets go through the re-seeding path from then on
     long long *d_ue_seed = nullptr;                      // per original UE: seed / draws consumed since that seeding
     uint32_t *d_ue_pos_used = nullptr, *d_ue_mv_used = nullptr;
+    double *d_vel_u = nullptr;                           // velocity spec per env and slot (slots change owners)
     int32_t *d_env_ids = nullptr;
     int env_ids_cap = 0;
     // scripted policies (dcb_rollout)
@@ -211,7 +212,7 @@ void dcb_destroy(dcb_env *env) {
     cudaFree(env->d_table); cudaFree(env->d_pos_skip); cudaFree(env->d_mv_skip); cudaFree(env->d_env_ids);
     cudaFree(env->d_cluster); cudaFree(env->d_fixed);
     cudaFree(env->d_uid); cudaFree(env->d_map_draws); cudaFree(env->d_glob_draws);
-    cudaFree(env->d_ue_seed); cudaFree(env->d_ue_pos_used); cudaFree(env->d_ue_mv_used);
+    cudaFree(env->d_ue_seed); cudaFree(env->d_ue_pos_used); cudaFree(env->d_ue_mv_used); cudaFree(env->d_vel_u);
     cudaFree(env->d_h_actions); cudaFree(env->d_h_obs); cudaFree(env->d_h_reward); cudaFree(env->d_h_lost);
     delete env;
 }
@@ -444,6 +445,7 @@ int dcb_reset(dcb_env *env, const int32_t *host_env_ids, int32_t n, void *stream
         r.K = p.K; r.N = p.N; r.NA = p.NA; r.n_orig = env->na_reset; r.seeds = env->d_seeds; r.uid = env->d_uid;
         r.ue_seed = env->d_ue_seed; r.ue_pos_used = env->d_ue_pos_used; r.ue_mv_used = env->d_ue_mv_used;
         CU(dcb_launch_pop_reseed(r, s));
+        CU(dcb_launch_broadcast_vel(env->d_vel_u, env->d_vel, p.K, p.N, s));    // every original UE is back in its slot
         GenArgs g;
         g.K = p.K; g.N = p.N; g.D = p.D; g.W = env->cfg.map_width; g.H = env->cfg.map_height;
         g.border_buffer = env->cfg.border_buffer;
@@ -549,13 +551,6 @@ int dcb_population_event(dcb_env *env, int32_t n_add, int32_t n_remove, int32_t 
         return fail(DCB_ERR_UNSUPPORTED, "variable UE population needs rand_episodes = 0 (streams restart at reset)");
     DeviceGuard guard(env->device);
     cudaStream_t s = (cudaStream_t)stream;
-    // slots change owners: every slot must describe the same kind of UE (arrivals are 'slow', base.py:592)
-    std::vector<double> vel(p.N);
-    CU(cudaMemcpyAsync(vel.data(), env->d_vel, sizeof(double) * p.N, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    for (int i = 0; i < p.N; i++)
-        if (vel[i] != DCB_VELOCITY_SLOW)
-            return fail(DCB_ERR_UNSUPPORTED, "variable UE population needs 'slow' UEs in every slot (slot %d is not)", i);
     if (!env->pop_used) {
         // per original UE: the seed of its generators and how far its two streams got (all as after a plain reset:
         // seed + 100 (i + 1), one reset_pos() draw, table row starting at the stream's first entry)
@@ -563,6 +558,9 @@ int dcb_population_event(dcb_env *env, int32_t n_add, int32_t n_remove, int32_t 
         CU(cudaMalloc((void **)&env->d_ue_seed, sizeof(long long) * KN));
         CU(cudaMalloc((void **)&env->d_ue_pos_used, sizeof(uint32_t) * KN));
         CU(cudaMalloc((void **)&env->d_ue_mv_used, sizeof(uint32_t) * KN));
+        CU(cudaMalloc((void **)&env->d_vel_u, sizeof(double) * KN));
+        CU(dcb_launch_broadcast_vel(env->d_vel_u, env->d_vel, p.K, p.N, s));
+        env->p.vel_u = env->d_vel_u;
         CU(dcb_launch_pop_seed_init(env->d_ue_seed, env->d_ue_pos_used, env->d_ue_mv_used, env->d_seeds, p.K, p.N, s));
         CU(dcb_launch_add_u32(env->d_ue_pos_used, (long long)KN, 1u, s));
         env->pop_used = true;
@@ -574,7 +572,7 @@ int dcb_population_event(dcb_env *env, int32_t n_add, int32_t n_remove, int32_t 
     a.seeds = env->d_seeds; a.map_draws = env->d_map_draws; a.glob_draws = env->d_glob_draws; a.uid = env->d_uid;
     a.pos = env->d_pos; a.mv = env->d_mv; a.mask = env->d_mask; a.ewma = env->d_ewma; a.table = env->d_table;
     a.actions = d_actions;
-    a.n_orig = env->na_reset; a.ue_mv_used = env->d_ue_mv_used;
+    a.n_orig = env->na_reset; a.ue_mv_used = env->d_ue_mv_used; a.vel_u = env->d_vel_u;
     CU(dcb_launch_population(a, s));
     env->launches++;
     env->p.NA = p.NA - n_remove + n_add;
@@ -707,11 +705,11 @@ int dcb_get_state(dcb_env *env, dcb_state_host *st) {
     if (st->time) CU(cudaMemcpy(st->time, env->d_time, sizeof(int) * p.K, cudaMemcpyDeviceToHost));
     if (st->movement) {
         std::vector<uint2> mv(KN);
-        std::vector<double> vel(p.N);
+        std::vector<double> vel(env->d_vel_u ? KN : (size_t)p.N);
         CU(cudaMemcpy(mv.data(), env->d_mv, sizeof(uint2) * KN, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(vel.data(), env->d_vel, sizeof(double) * p.N, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(vel.data(), env->d_vel_u ? env->d_vel_u : env->d_vel, sizeof(double) * vel.size(), cudaMemcpyDeviceToHost));
         for (size_t u = 0; u < KN; u++) {
-            const double vf = vel[u % p.N];
+            const double vf = env->d_vel_u ? vel[u] : vel[u % p.N];
             double *m = st->movement + 5 * u;
             m[0] = vf >= 0.0 ? vf : (double)(mv[u].y & 0xffu);
             m[1] = (double)(mv[u].x & 0xffffu);

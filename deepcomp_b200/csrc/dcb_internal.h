@@ -45,7 +45,8 @@ struct DevParams {
     double pw[10];       // binomial series of (1 + r)^(-snr_h): coefficients of r^0 .. r^9 (dcb_snr_inrange)
     const double *bs_xy; // [M][2]
     const int *sharing;  // [M]
-    const double *vel_spec;  // [N]
+    const double *vel_spec;  // [N] velocity spec per slot (the same in every env) ...
+    const double *vel_u;     // ... or [K*N] per env and slot once UEs have changed slots (variable population), else NULL
     // state slabs, flat UE index u = k*N + i
     double2 *pos;        // [K*N]
     uint2 *mv;           // [K*N]
@@ -229,6 +230,7 @@ struct PopArgs {
     int32_t *actions;           // [K][N] this step's actions (follow their UEs when slots shift) or NULL
     int n_orig;                 // UEs of the original list (ids 1..n_orig)
     uint32_t *ue_mv_used;       // [K*N] movement.reset() draws an ORIGINAL UE has consumed since its last seeding
+    double *vel_u;              // [K*N] velocity spec per env and slot (moves with its UE; arrivals are 'slow')
 };
 
 // reset() of a batch whose population changed (single_ue/base.py:169-189): MobileEnv.seed first re-seeds the UEs of the
@@ -245,6 +247,7 @@ cudaError_t dcb_launch_pop_reseed(const ReseedArgs &a, cudaStream_t s);
 cudaError_t dcb_launch_pop_seed_init(long long *ue_seed, uint32_t *pos_used, uint32_t *mv_used, const long long *seeds,
                                      int K, int N, cudaStream_t s);
 cudaError_t dcb_launch_add_u32(uint32_t *a, long long n, uint32_t v, cudaStream_t s);
+cudaError_t dcb_launch_broadcast_vel(double *vel_u, const double *vel_spec, int K, int N, cudaStream_t s);
 
 // Brute-force candidate evaluation (dcb_brute.cu)
 struct BruteArgs {

@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(64) dcb_population_kernel(PopArgs a) {
         for (int j = idx; j < na - 1; j++) {
             const long long d = base + j, s = d + 1;
             a.pos[d] = a.pos[s]; a.mv[d] = a.mv[s]; a.mask[d] = a.mask[s]; a.ewma[d] = a.ewma[s]; a.uid[d] = a.uid[s];
+            a.vel_u[d] = a.vel_u[s];
             for (int e = 0; e < a.D; e++) a.table[d * a.D + e] = a.table[s * a.D + e];
             if (a.actions) a.actions[d] = a.actions[s];
         }
@@ -219,6 +220,7 @@ __global__ void __launch_bounds__(64) dcb_population_kernel(PopArgs a) {
         a.mask[d] = 0ull;
         a.ewma[d] = 0.0;
         a.uid[d] = new_id | DCB_UID_ARRIVED;
+        a.vel_u[d] = DCB_VELOCITY_SLOW;
         if (a.actions) a.actions[d] = 0;
         na++;
     }
@@ -249,6 +251,11 @@ __global__ void dcb_pop_seed_init_kernel(long long *ue_seed, uint32_t *pos_used,
     mv_used[t] = 0u;
 }
 
+__global__ void dcb_broadcast_vel_kernel(double *vel_u, const double *vel_spec, long long n, int N) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) vel_u[t] = vel_spec[t % N];
+}
+
 __global__ void dcb_add_u32_kernel(uint32_t *a, long long n, uint32_t v) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) a[t] += v;
@@ -275,6 +282,12 @@ cudaError_t dcb_launch_pop_seed_init(long long *ue_seed, uint32_t *pos_used, uin
                                      int K, int N, cudaStream_t s) {
     const long long n = (long long)K * N;
     dcb_pop_seed_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ue_seed, pos_used, mv_used, seeds, n, N);
+    return cudaGetLastError();
+}
+
+cudaError_t dcb_launch_broadcast_vel(double *vel_u, const double *vel_spec, int K, int N, cudaStream_t s) {
+    const long long n = (long long)K * N;
+    dcb_broadcast_vel_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(vel_u, vel_spec, n, N);
     return cudaGetLastError();
 }
 

@@ -307,7 +307,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
         // the waypoint-table entry under the cursor, fetched ahead of its use (ue_move)
         uint32_t *next_slot = snext + t;
         if (valid && (int)(vpt >> 16) < p.D) prefetch_table_entry(next_slot, p.table + u * p.D + (vpt >> 16));
-        const double vfix = valid ? velspec[i] : 0.0;
+        const double vfix = valid ? (p.vel_u ? p.vel_u[u] : velspec[i]) : 0.0;
         const double vfix_thr = vfix >= 0.0 ? snap_threshold(vfix) : 0.0;
         double *Xrow = X + (size_t)t * MS;
         // this UE's bit in the per-(env, BS) UE bitsets: word index (low 24 bits) and bit number (high 8 bits)

@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
         S.smask[i] = p.mask[u];
         S.sew[i] = p.ewma[u];
     }
-    const double vfix = valid ? p.vel_spec[i] : 0.0;
+    const double vfix = valid ? (p.vel_u ? p.vel_u[u] : p.vel_spec[i]) : 0.0;
     const double vfix_thr = vfix >= 0.0 ? snap_threshold(vfix) : 0.0;
     double *Xrow = S.Xs + (size_t)i * LC;
     __syncthreads();

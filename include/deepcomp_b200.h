@@ -172,8 +172,8 @@ int32_t dcb_get_active_ues(const dcb_env *env);
  * id = last id + 1, position = Map.rand_border_point map.py:52-65, 'slow' RandomWaypoint seeded with env_seed + 100 id).
  * Call it right BEFORE the dcb_step of the step the event belongs to, with that step's device action buffer
  * (int32 [K][n_ue], edited in place: actions follow their UEs, arriving UEs get a no-op; may be NULL).  Every env of
- * the handle sees the same event (lockstep batch); needs rand_episodes = 0 and 'slow' UEs in every slot.  dcb_reset
- * restores the original population.
+ * the handle sees the same event (lockstep batch); needs rand_episodes = 0.  dcb_reset restores the original population
+ * the way the reference does (MobileEnv.seed walks the list as it stands first, base.py:132-143, 169-189).
  */
 int dcb_population_event(dcb_env *env, int32_t n_add, int32_t n_remove, int32_t *d_actions, void *stream);
 /* UE ids per slot, host int32 [K][n_ue] (User.id as an integer; slots >= dcb_get_active_ues are stale).  Synchronous. */

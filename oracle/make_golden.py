@@ -72,6 +72,11 @@ def population_scenarios():
     S.append(dict(base, name='pop_3up2down_central_sum', kind='central', reward='sum', max_ues=6, n_ue=2,
                   ue_arrival={10: 3, 30: -2}, sharing='proportional-fair'))
     S.append(dict(base, name='pop_interval25_multi_avg', kind='multi', reward='avg', max_ues=6, new_ue_interval=25))
+    # UEs of different velocity classes change list positions when others leave (the arrivals are always 'slow')
+    S.append(dict(base, name='pop_mixedvel_multi_avg', kind='multi', reward='avg', n_ue=4, max_ues=6,
+                  velocities=['fast', 0, 'slow', 2.5], ue_arrival={8: 2, 20: -3, 30: 2, 45: -2}))
+    S.append(dict(base, name='pop_mixedvel_central_avg', kind='central', reward='avg', n_ue=4, max_ues=6,
+                  velocities=['fast', 0, 'slow', 2.5], ue_arrival={8: 2, 20: -3, 30: 2, 45: -2}))
     return S
 
 
