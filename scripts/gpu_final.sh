@@ -14,8 +14,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:dcb_
     python bench.py --steps 300 --warmup 100 --no-cpu-baseline --e2e-steps 3 > $O/ncu_full_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:dcb_wide_kernel -s 4 -c 1 -o $O/prof_wide_$TAG -f \
     python bench.py --n-ue 1000 --n-bs 50 --envs 1024 --fragment 4 --steps 12 --warmup 4 --no-cpu-baseline --e2e-steps 1 > $O/ncu_wide_$TAG.log 2>&1
-# phase timeline of CTA 0 (instrumented build)
-DCB_LIB_PATH=$GRAFT_REPO_ROOT/gpurun_exp_TRACE.so timeout 300 python scripts/trace_timeline.py > $O/timeline_$TAG.txt 2>&1
+# phase timeline of CTA 0 (instrumented build: scripts/build_trace_lib.sh)
+[ -f gpurun_exp_TRACE.so ] && DCB_LIB_PATH=$GRAFT_REPO_ROOT/gpurun_exp_TRACE.so timeout 300 python scripts/trace_timeline.py > $O/timeline_$TAG.txt 2>&1
 # racecheck: both kernels, small shapes, multi-step fragments
 timeout 900 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_api.py -q -x -k "step_many or auto_reset or rollout_equals" > $O/racecheck_$TAG.log 2>&1; tail -3 $O/racecheck_$TAG.log
 DCB_FORCE_WIDE=1 timeout 900 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_api.py -q -x -k "step_many or auto_reset" > $O/racecheck_wide_$TAG.log 2>&1; tail -3 $O/racecheck_wide_$TAG.log
