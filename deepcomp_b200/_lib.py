@@ -48,6 +48,7 @@ SYMBOLS = [
     'dcb_step_many', 'dcb_rollout', 'dcb_step_host', 'dcb_check_errors', 'dcb_get_state', 'dcb_set_state', 'dcb_obs_size',
     'dcb_reward_size', 'dcb_algorithmic_bytes_per_env_step', 'dcb_launch_count', 'dcb_launch_geometry',
     'dcb_kernel_name', 'dcb_set_active_ues', 'dcb_get_active_ues', 'dcb_population_event', 'dcb_get_ue_ids', 'dcb_num_joint_actions', 'dcb_test_actions', 'dcb_set_utility',
+    'dcb_set_obs_norm',
 ]
 
 DCB_ABI_VERSION = 1
@@ -108,6 +109,7 @@ def load():
     L.dcb_population_event.argtypes = [vp, i32, i32, vp, vp]
     L.dcb_get_ue_ids.argtypes = [vp, vp]
     L.dcb_set_utility.argtypes = [vp, i32, ctypes.c_double]
+    L.dcb_set_obs_norm.argtypes = [vp, i32]
     L.dcb_num_joint_actions.argtypes = [vp]
     L.dcb_num_joint_actions.restype = i64
     L.dcb_test_actions.argtypes = [vp, i32, i64, i64, vp, vp]

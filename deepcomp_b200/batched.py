@@ -45,8 +45,11 @@ class BatchedMobileEnv:
     def __init__(self, num_envs, n_ue, bs_xy, map_wh, kind='multi', sharing='mixed', velocities='slow', seed=0,
                  seeds=None, reward='avg', episode_length=100, rand_episodes=False, auto_reset=False, init_pos=None,
                  pause_duration=2, border_buffer=10, device=None, first_env=0, max_ues=None, ue_arrival=None,
-                 new_ue_interval=None, util_func='log', dr_req=1):
+                 new_ue_interval=None, util_func='log', dr_req=1, obs_norm='rel'):
         """
+        `obs_norm`: 'rel' = the observation entry 'dr' is snr / max snr (RelNormEnv, variants.py:276-284; default);
+        'max' = (min(snr, 7e-6) - 2e-8) / (7e-6 - 2e-8) (MaxNormEnv, variants.py:308-332; CentralMaxNormEnv).
+
         Variable UE population (reference env_config keys of the same names, base.py:80-84, 429-443): `n_ue` UEs at
         reset, `max_ues` slots per env (every per-UE array has max_ues rows; rows of UEs that are not there read as
         zeros, central.py:46-55), `ue_arrival` = {time: +n arrivals / -n departures} (env_setup.py:205-226),
@@ -140,6 +143,11 @@ class BatchedMobileEnv:
         self.util_func = util_func
         if util_func != 'log':
             check(self._L.dcb_set_utility(self._h, 1, float(dr_req)))
+        if obs_norm not in ('rel', 'max'):
+            raise ValueError(f"obs_norm must be 'rel' (RelNormEnv) or 'max' (MaxNormEnv), got {obs_norm!r}")
+        self.obs_norm = obs_norm
+        if obs_norm == 'max':
+            check(self._L.dcb_set_obs_norm(self._h, 1))
 
     # ------------------------------------------------------------------ plumbing
     def close(self):

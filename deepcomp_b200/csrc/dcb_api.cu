@@ -370,6 +370,7 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     p.D = D; p.E = E; p.S = S; p.CS = CS; p.LC = LC;
     p.has_maxcap = has_maxcap; p.has_propfair = has_pf;
     p.util_step = 0; p.dr_req = 1.0;
+    p.obs_maxnorm = 0;
     p.c1 = c1;
     p.c2 = c2;
     p.thr_d2 = thr_d2;
@@ -504,6 +505,14 @@ int dcb_set_utility(dcb_env *env, int32_t kind, double dr_req) {
     return DCB_OK;
 }
 
+int dcb_set_obs_norm(dcb_env *env, int32_t kind) {
+    if (!env) return fail(DCB_ERR_INVALID_ARG, "null handle");
+    if (kind != DCB_OBS_RELNORM && kind != DCB_OBS_MAXNORM)
+        return fail(DCB_ERR_INVALID_ARG, "unknown observation normalisation %d", kind);
+    env->p.obs_maxnorm = kind == DCB_OBS_MAXNORM;
+    return DCB_OK;
+}
+
 int64_t dcb_num_joint_actions(const dcb_env *env) {
     if (!env) return 0;
     double n = pow((double)(env->p.M + 1), (double)env->p.NA);
@@ -604,6 +613,8 @@ int dcb_rollout(dcb_env *env, const dcb_policy *policy, int32_t T, int32_t *d_ac
     if (T < 1) return fail(DCB_ERR_INVALID_ARG, "T must be >= 1");
     if (policy->kind < DCB_POLICY_3GPP || policy->kind > DCB_POLICY_RANDOM)
         return fail(DCB_ERR_INVALID_ARG, "unknown policy kind %d", policy->kind);
+    if (env->p.obs_maxnorm)   // the agents pick by 'dr' (heuristics.py:19-38,44-65,86-108); MaxNorm caps it at 7e-6
+        return fail(DCB_ERR_UNSUPPORTED, "the scripted device policies read the RelNorm observation; this handle is MaxNorm");
     DeviceGuard guard(env->device);
     cudaStream_t s = (cudaStream_t)stream;
     const DevParams &p = env->p;

@@ -112,6 +112,13 @@ __device__ __forceinline__ float norm_snr_f32(float d2, float d2min, float hr) {
     return d2 == d2min ? 1.0f : fminf(q * sq * ex, 1.0f);   // the closest BS is exactly 1 (variants.py:284)
 }
 
+// MaxNormEnv.get_ue_obs (variants.py:322-330): SNR capped at MAX_SNR_THRESHOLD, minus the connection threshold, scaled so
+// that the cap maps to 1 (out-of-range base stations come out slightly negative).  fp64 throughout, rounded once.
+__device__ __forceinline__ float max_norm_snr(double snr) {
+    const double s = snr < DCB_MAX_SNR_THRESHOLD ? snr : DCB_MAX_SNR_THRESHOLD;
+    return (float)((s - DCB_SNR_THRESHOLD) / (DCB_MAX_SNR_THRESHOLD - DCB_SNR_THRESHOLD));
+}
+
 template <bool M32> struct MaskType { typedef unsigned long long type; };
 template <> struct MaskType<true> { typedef unsigned type; };
 __device__ __forceinline__ int mask_ffs(unsigned m) { return __ffs((int)m); }

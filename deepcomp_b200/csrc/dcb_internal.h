@@ -14,6 +14,7 @@
 #define DCB_SNR_THRESHOLD 2e-8
 #define DCB_MIN_UTILITY (-20.0)
 #define DCB_MAX_UTILITY 20.0
+#define DCB_MAX_SNR_THRESHOLD 7e-6   // MaxNormEnv.MAX_SNR_THRESHOLD (single_ue/variants.py:311)
 
 // Sticky device-side error bits (DevParams::err)
 #define DCB_ERRBIT_ACTION 1
@@ -38,6 +39,7 @@ struct DevParams {
     int has_maxcap, has_propfair;
     int util_step;       // 0: log utility (utility.py:36-54); 1: step utility (utility.py:23-33) at dr_req
     double dr_req;       // User.dr_req (user.py:17-30)
+    int obs_maxnorm;     // observation 'dr': 0 = snr / max snr (variants.py:276-284); 1 = MaxNormEnv (variants.py:308-332)
     int LC;              // wide kernel: link slots per UE (bound on the base stations any point can be in range of)
     double thr_d2;       // largest squared distance that is still in range (snr > 2e-8, station.py:224)
     double c1, c2;       // Okumura-Hata constants (station.py:112-114)

@@ -652,7 +652,10 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                     row_dr[b] = d2f;
                 }
                 // ---- dense pass B: 'dr' = snr_b / max_b snr_b (variants.py:276-284) = (d2min / d2_b)^h
-                if (d2minf >= 1e-6f) {        // below: d + EPSILON matters (in practice d = 0 exactly)
+                if (p.obs_maxnorm) {          // MaxNormEnv (variants.py:308-332): per-handle variant, out-of-line fp64 SNR
+                    for (int b = 0; b < M; b++)
+                        row_dr[b] = max_norm_snr(snr_of_d2_general(p.snr_c0, p.snr_h, tab, dist2(bsxy[b], x, y)));
+                } else if (d2minf >= 1e-6f) {        // below: d + EPSILON matters (in practice d = 0 exactly)
                 DCB_UNROLL(DCB_OBS_UNROLL)
                     for (int b = 0; b < M; b++) row_dr[b] = norm_snr_f32(row_dr[b], d2minf, hr);
                 } else {

@@ -424,7 +424,10 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
             const unsigned in0 = __ballot_sync(0xffffffffu, ok0 && d20 <= p.thr_d2);
             const unsigned in1 = __ballot_sync(0xffffffffu, ok1 && d21 <= p.thr_d2);
             float dr0, dr1;
-            if (d2minf >= 1e-6f) {       // 'dr' = snr_b / max_b snr_b (variants.py:276-284) = (d2min / d2_b)^h in fp32
+            if (p.obs_maxnorm) {         // MaxNormEnv (variants.py:308-332): per-handle variant
+                dr0 = ok0 ? max_norm_snr(snr_of_d2_general(p.snr_c0, p.snr_h, tab, d20)) : 0.0f;
+                dr1 = ok1 ? max_norm_snr(snr_of_d2_general(p.snr_c0, p.snr_h, tab, d21)) : 0.0f;
+            } else if (d2minf >= 1e-6f) {       // 'dr' = snr_b / max_b snr_b (variants.py:276-284) = (d2min / d2_b)^h in fp32
                 dr0 = norm_snr_f32(f0, d2minf, hr);
                 dr1 = norm_snr_f32(f1, d2minf, hr);
             } else {                     // a UE sitting on a BS: d + EPSILON matters

@@ -69,6 +69,7 @@ class _MobileEnvFacade:
     """Common part of the two facades: the attributes and helpers of MobileEnv (base.py:20-143, 383-411)."""
     metadata = {'render.modes': ['human']}
     _kind = None
+    _obs_norm = 'rel'           # 'dr' normalisation: RelNormEnv (variants.py:276-284) / 'max' = MaxNormEnv (:308-332)
 
     def __init__(self, env_config):
         self.env_config = env_config
@@ -115,7 +116,7 @@ class _MobileEnvFacade:
             episode_length=sc['episode_length'], rand_episodes=sc['rand_episodes'], init_pos=sc['init_pos'],
             pause_duration=sc['pause_duration'], border_buffer=sc['border_buffer'], device=self._device,
             max_ues=sc['max_ues'], ue_arrival=sc['ue_arrival'], new_ue_interval=sc['new_ue_interval'],
-            util_func=sc['util_func'], dr_req=sc['dr_req'])
+            util_func=sc['util_func'], dr_req=sc['dr_req'], obs_norm=self._obs_norm)
 
     # ---- MobileEnv attributes
     @property
@@ -258,6 +259,22 @@ class CentralRelNormEnv(_MobileEnvFacade):
         self._sync_entities(curr_dr, utility)
         self.obs = self._obs_dict(flat)
         return self.obs, float(reward), self.done(), self._info(curr_dr, utility, sum_utility)
+
+
+class CentralMaxNormEnv(CentralRelNormEnv):
+    """CentralRelNormEnv with MaxNormEnv's SNR normalisation (reference central.py:155-164, variants.py:308-332; the
+    alternative named in env_setup.py:35): obs['dr'] = (min(snr, 7e-6) - 2e-8) / (7e-6 - 2e-8), negative out of range."""
+    _obs_norm = 'max'
+
+    def __init__(self, env_config):
+        super().__init__(env_config)
+        n, m = self.max_ues, self.num_bs
+        self.obs_space_dict['dr'] = spaces.Box(low=-1, high=1, shape=(m,))              # variants.py:313-317
+        self.observation_space = spaces.Dict({                                          # central.py:159-164
+            'connected': spaces.MultiBinary(n * m),
+            'dr': spaces.Box(low=-1, high=1, shape=(n * m,)),
+            'utility': spaces.Box(low=-1, high=1, shape=(n,)),
+        })
 
 
 class MultiAgentMobileEnv(_MobileEnvFacade):

@@ -188,6 +188,17 @@ int dcb_get_ue_ids(dcb_env *env, int32_t *host_ids);
 typedef enum dcb_utility { DCB_UTILITY_LOG = 0, DCB_UTILITY_STEP = 1 } dcb_utility;
 int dcb_set_utility(dcb_env *env, int32_t kind, double dr_req);
 
+/*
+ * Normalisation of the observation entry 'dr' (one setting per handle; takes effect with the next launch):
+ * DCB_OBS_RELNORM (default): snr_b / max_b snr_b, RelNormEnv.get_ue_obs (single_ue/variants.py:276-284);
+ * DCB_OBS_MAXNORM: (min(snr_b, 7e-6) - 2e-8) / (7e-6 - 2e-8), MaxNormEnv.get_ue_obs (single_ue/variants.py:308-332;
+ * CentralMaxNormEnv multi_ue/central.py:155-164, the alternative named in util/env_setup.py:35) -- range [-0.0029, 1],
+ * negative where the BS is out of range.  Everything else in the observation is unchanged.  The scripted device
+ * policies (dcb_rollout) read the RelNorm observation and refuse a MaxNorm handle.
+ */
+typedef enum dcb_obs_norm { DCB_OBS_RELNORM = 0, DCB_OBS_MAXNORM = 1 } dcb_obs_norm;
+int dcb_set_obs_norm(dcb_env *env, int32_t kind);
+
 /* get_obs() of the current state (central.py:31-57 / multi_agent.py:32-37) without stepping; reward is not written */
 int dcb_observe(dcb_env *env, const dcb_outputs *out, void *stream);
 

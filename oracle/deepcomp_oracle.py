@@ -31,6 +31,7 @@ MIN_UTILITY = -20
 MAX_UTILITY = 20
 # env/entities/station.py:10
 SNR_THRESHOLD = 2e-8
+MAX_SNR_THRESHOLD = 7e-6                    # MaxNormEnv.MAX_SNR_THRESHOLD (single_ue/variants.py:311)
 # env/entities/station.py:26-30
 BW = 9e6
 FREQUENCY = 2500
@@ -139,8 +140,10 @@ class OracleEnv:
 
     def __init__(self, kind, n_ue, bs_xy, map_wh, sharing='mixed', velocities='slow', seed=None, reward='avg',
                  episode_length=100, rand_episodes=False, init_pos=None, pause_duration=2, border_buffer=10,
-                 max_ues=None, ue_arrival=None, new_ue_interval=None, util_func='log', dr_req=1):
+                 max_ues=None, ue_arrival=None, new_ue_interval=None, util_func='log', dr_req=1, obs_norm='rel'):
         assert kind in ('central', 'multi')
+        assert obs_norm in ('rel', 'max')                       # RelNormEnv / MaxNormEnv (variants.py:271-303 / 308-332)
+        self.obs_norm = obs_norm
         assert util_func in ('log', 'step')                     # 'linear' fails the reference's own assert (utility.py:18)
         self.util_func, self.dr_req = util_func, dr_req
         self.kind = kind
@@ -362,6 +365,10 @@ class OracleEnv:
             bs_norm_dr = [0 for _ in bs_dr]
         else:
             bs_norm_dr = [dr / max_dr for dr in bs_dr]
+        if self.obs_norm == 'max':
+            # MaxNormEnv.get_ue_obs (variants.py:319-332): cap at MAX_SNR_THRESHOLD, subtract the required SNR, normalise
+            bs_norm_dr = [(min(self.snr(b, ue), MAX_SNR_THRESHOLD) - SNR_THRESHOLD) / (MAX_SNR_THRESHOLD - SNR_THRESHOLD)
+                          for b in range(self.n_bs)]
         utility = [self.utility(ue) / MAX_UTILITY]
         ues_at_bs = [len(self.conn_ues[b]) / len(self.ues) for b in range(self.n_bs)]    # self.num_ue, variants.py:296
         avg_util = []

@@ -90,6 +90,24 @@ def utility_scenarios():
     return S
 
 
+def obs_variant_scenarios():
+    """MaxNormEnv observation (single_ue/variants.py:308-332): CentralMaxNormEnv (multi_ue/central.py:155-164) and the
+    same composition over MultiAgentMobileEnv (oracle/ref_loader.py:build_env).  UE 12 starts on top of BS 0 (d = 0:
+    SNR far above the cap), UE 11 in the far corner (every BS out of range: all entries negative)."""
+    S = []
+    W, H, gbs = rl.grid_layout(5)
+    vel = ['slow', 'fast', 0, 2.5] * 3
+    init = [('random', 'random')] * 10 + [(W, H), gbs[0]]
+    for kind, reward in (('central', 'avg'), ('multi', 'avg')):
+        S.append(dict(name=f'maxnorm_{kind}_{reward}', kind=kind, n_ue=12, bs_xy=gbs, map_wh=(W, H), sharing='mixed',
+                      velocities=vel, seed=23, reward=reward, steps=50, action_seed=8, episodes=1, obs_norm='max',
+                      init_pos=init))
+    S.append(dict(name='pop_maxnorm_central_sum', kind='central', reward='sum', n_ue=2, max_ues=6, bs_xy=gbs,
+                  map_wh=(W, H), sharing='mixed', velocities='slow', seed=33, steps=60, action_seed=9, episodes=1,
+                  ue_arrival={10: 3, 30: -2}, obs_norm='max'))
+    return S
+
+
 def brute_scenarios():
     """BruteForceAgent (deepcomp/agent/brute_force.py:59-94): all (M+1)^N joint actions tested with
     MobileEnv.test_ue_actions (single_ue/base.py:284-313) on the central env, the best one taken."""
@@ -188,7 +206,8 @@ def record(sc):
     env = rl.build_env(sc['kind'], sc['n_ue'], sc['seed'], sc['bs_xy'], sc['map_wh'], sharing=sc['sharing'],
                        velocities=sc['velocities'], reward=sc['reward'], episode_length=sc['steps'],
                        init_pos=sc.get('init_pos'), max_ues=sc.get('max_ues'), ue_arrival=sc.get('ue_arrival'),
-                       new_ue_interval=sc.get('new_ue_interval'), util_func=sc.get('util_func', 'log'))
+                       new_ue_interval=sc.get('new_ue_interval'), util_func=sc.get('util_func', 'log'),
+                       obs_norm=sc.get('obs_norm', 'rel'))
     pop = 'max_ues' in sc
     n_act = sc.get('max_ues', sc['n_ue'])                # length of the action vector (central.py:28)
     tr = rl.RefTrace(env, sc['kind'])
@@ -285,7 +304,8 @@ def main():
     only = sys.argv[1] if len(sys.argv) > 1 else ''     # optional name prefix: regenerate a subset only
     if not only:
         np.savez_compressed(os.path.join(OUT_DIR, 'anchors.npz'), **anchors())
-    for sc in scenarios() + policy_scenarios() + population_scenarios() + brute_scenarios() + utility_scenarios():
+    for sc in scenarios() + policy_scenarios() + population_scenarios() + brute_scenarios() + utility_scenarios() + \
+            obs_variant_scenarios():
         if not sc['name'].startswith(only):
             continue
         data = record_brute(sc) if sc['name'].startswith('brute_') else record(sc)

@@ -32,11 +32,13 @@ def _import_reference():
     from deepcomp.env.entities.station import Basestation
     from deepcomp.env.entities.user import User
     from deepcomp.env.util.movement import RandomWaypoint
-    from deepcomp.env.multi_ue.central import CentralRelNormEnv
+    from deepcomp.env.multi_ue.central import CentralRelNormEnv, CentralMaxNormEnv
     from deepcomp.env.multi_ue.multi_agent import MultiAgentMobileEnv
+    from deepcomp.env.single_ue.variants import MaxNormEnv
     from shapely.geometry import Point
     return dict(Map=Map, Basestation=Basestation, User=User, RandomWaypoint=RandomWaypoint,
-                CentralRelNormEnv=CentralRelNormEnv, MultiAgentMobileEnv=MultiAgentMobileEnv, Point=Point)
+                CentralRelNormEnv=CentralRelNormEnv, MultiAgentMobileEnv=MultiAgentMobileEnv, Point=Point,
+                CentralMaxNormEnv=CentralMaxNormEnv, MaxNormEnv=MaxNormEnv)
 
 
 def sharing_for_bs(sharing, b):
@@ -56,9 +58,14 @@ def grid_layout(n_bs, pitch=100, border=10):
 
 def build_env(kind, n_ue, seed, bs_xy, map_wh, sharing='mixed', velocities='slow', reward='avg',
               episode_length=100, rand_episodes=False, init_pos=None, max_ues=None, ue_arrival=None,
-              new_ue_interval=None, util_func='log'):
+              new_ue_interval=None, util_func='log', obs_norm='rel'):
     """
     Build a reference env.
+
+    :param obs_norm: 'rel' (RelNormEnv observation) or 'max' (MaxNormEnv, variants.py:308-332): central =
+        CentralMaxNormEnv (central.py:155-164); multi = MultiAgentMobileEnv composed with MaxNormEnv the way the
+        reference composes its central variant (class X(MultiAgentMobileEnv, MaxNormEnv): get_ue_obs resolves to
+        MaxNormEnv's, everything else to MultiAgentMobileEnv's; both classes unmodified)
 
     :param kind: 'central' (CentralRelNormEnv) or 'multi' (MultiAgentMobileEnv)
     :param velocities: 'slow' | 'fast' | number, or a list of those per UE
@@ -83,7 +90,11 @@ def build_env(kind, n_ue, seed, bs_xy, map_wh, sharing='mixed', velocities='slow
         'ue_arrival': None if ue_arrival is None else {int(t): int(n) for t, n in ue_arrival.items()},
         'log_metrics': True, 'dashboard': False, 'ue_details': False,
     }
-    cls = R['CentralRelNormEnv'] if kind == 'central' else R['MultiAgentMobileEnv']
+    if obs_norm == 'max':
+        cls = R['CentralMaxNormEnv'] if kind == 'central' else \
+            type('MultiAgentMaxNormEnv', (R['MultiAgentMobileEnv'], R['MaxNormEnv']), {})
+    else:
+        cls = R['CentralRelNormEnv'] if kind == 'central' else R['MultiAgentMobileEnv']
     return cls(env_config)
 
 

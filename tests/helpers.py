@@ -26,7 +26,13 @@ def _names():
 
 def golden_names():
     """fixed-population traces (every test that replays a trace step by step)"""
-    return [n for n in _names() if not n.startswith(('pop_', 'brute_', 'utilstep_'))]
+    return [n for n in _names() if not n.startswith(('pop_', 'brute_', 'utilstep_', 'maxnorm_'))]
+
+
+def obs_variant_names():
+    """fixed-population traces of the MaxNormEnv observation (variants.py:308-332; a variable-population one rides with
+    population_names() as pop_maxnorm_*)"""
+    return [n for n in _names() if n.startswith('maxnorm_')]
 
 
 def utility_names():
@@ -63,7 +69,7 @@ def oracle_kwargs(cfg):
         init_pos = [tuple(p) for p in init_pos]
     return dict(kind=cfg['kind'], n_ue=cfg['n_ue'], bs_xy=[tuple(p) for p in cfg['bs_xy']], map_wh=tuple(cfg['map_wh']),
                 sharing=cfg['sharing'], velocities=cfg['velocities'], seed=cfg['seed'], reward=cfg['reward'],
-                episode_length=cfg['steps'], init_pos=init_pos, **({'util_func': cfg['util_func']} if 'util_func' in cfg else {}))
+                episode_length=cfg['steps'], init_pos=init_pos, **{k: cfg[k] for k in ('util_func', 'obs_norm') if k in cfg})
 
 
 def assert_close(a, b, what, rtol=RTOL, atol=ATOL):

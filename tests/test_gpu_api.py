@@ -126,6 +126,67 @@ def test_gym_facades_with_arriving_and_departing_ues(name):
     env.close()
 
 
+def test_central_maxnorm_facade_replays_reference_trace():
+    """CentralMaxNormEnv (multi_ue/central.py:155-164 over MaxNormEnv, single_ue/variants.py:308-332): same step, the
+    observation entry 'dr' is the capped, threshold-shifted SNR -- Box(-1, 1), negative where the BS is out of range."""
+    from deepcomp_b200.env import CentralMaxNormEnv, CentralRelNormEnv
+    cfg, z = load_golden('maxnorm_central_avg')
+    env = CentralMaxNormEnv(_env_config_from_golden(cfg))
+    assert isinstance(env, CentralRelNormEnv)
+    N, M = cfg['n_ue'], len(cfg['bs_xy'])
+    assert env.observation_space.spaces['dr'].low.min() == -1 and env.observation_space.spaces['dr'].shape == (N * M,)
+    obs = env.reset()
+    flat = np.concatenate([np.asarray(obs[k], dtype=np.float64) for k in sorted(obs)])
+    assert_close(flat, z['reset_obs'][0], 'reset obs', 2e-6, 1e-6)
+    assert obs['dr'][11 * M] == 1.0 and max(obs['dr'][10 * M:11 * M]) < 0       # on top of BS 0 / out of every range
+    for t in range(cfg['steps']):
+        obs, reward, done, info = env.step(z['actions'][t].astype(np.int64))
+        assert done is None
+        assert env.observation_space.contains({k: np.asarray(v, dtype=np.float32) for k, v in obs.items()})
+        flat = np.concatenate([np.asarray(obs[k], dtype=np.float64) for k in sorted(obs)])
+        assert_close(flat, z['step_obs'][t], f'obs[{t}]', 2e-6, 1e-6)
+        assert_close(reward, z['step_reward'][t], f'reward[{t}]', 2e-6, 1e-6)
+        assert_exact(np.array([[u.pos.x, u.pos.y] for u in env.ue_list]), z['step_pos'][t], 'ue.pos')
+    env.close()
+
+
+def test_maxnorm_batch_differs_only_in_dr_and_refuses_device_policies():
+    """obs_norm='max' on a K-env batch: state, rewards and every other observation entry equal the RelNorm batch bit for
+    bit; through both kernels; the scripted device policies (which read the RelNorm 'dr') refuse such a handle."""
+    import os
+    from deepcomp_b200 import BatchedMobileEnv
+    from deepcomp_b200._lib import DcbError
+    sc = _scenario(n_ue=20, n_bs=7)
+    K, N, M = 9, 20, 7
+    a = _actions(12, K, N, M, seed=3)
+    for wide in (False, True):
+        if wide:
+            os.environ['DCB_FORCE_WIDE'] = '1'
+        try:
+            e_rel = BatchedMobileEnv(num_envs=K, kind='multi', seed=5, **sc)
+            e_max = BatchedMobileEnv(num_envs=K, kind='multi', seed=5, obs_norm='max', **sc)
+        finally:
+            os.environ.pop('DCB_FORCE_WIDE', None)
+        o_rel, o_max = e_rel.reset(), e_max.reset()
+        for t in range(12):
+            o_rel, r_rel, _, _ = e_rel.step(a[t])
+            o_max, r_max, _, _ = e_max.step(a[t])
+            assert torch.equal(r_rel, r_max)
+            keep = [c for c in range(4 * M + 1) if not M <= c < 2 * M]
+            assert torch.equal(o_rel[..., keep], o_max[..., keep])
+            dr = o_max[..., M:2 * M].double()
+            assert float(dr.max()) <= 1.0 and float(dr.min()) >= -2e-8 / (7e-6 - 2e-8) - 1e-9
+            # a link that survived the move is in range (user.py:175-188): snr > 2e-8 <=> positive entry
+            assert bool((dr[o_max[..., :M] == 1] > 0).all())
+        s_rel, s_max = e_rel.get_state(), e_max.get_state()
+        assert np.array_equal(s_rel['pos'], s_max['pos']) and np.array_equal(s_rel['mask'], s_max['mask'])
+        if not wide:
+            from deepcomp_b200.agents import Heuristic3GPP
+            with pytest.raises(DcbError):
+                e_max.rollout(Heuristic3GPP().device_policy(e_max), 3)
+        e_rel.close(); e_max.close()
+
+
 def test_central_facade_rejects_invalid_actions():
     """reference: assert action_space.contains(action) (central.py:61)"""
     from deepcomp_b200.env import CentralRelNormEnv

@@ -5,7 +5,7 @@ import pytest
 from oracle import c_oracle
 from oracle import deepcomp_oracle as po
 
-from helpers import (GOLDEN_DIR, assert_close, assert_exact, brute_names, check_against_golden, golden_names, load_golden, oracle_kwargs, population_kwargs,
+from helpers import (GOLDEN_DIR, assert_close, assert_exact, brute_names, check_against_golden, golden_names, load_golden, obs_variant_names, oracle_kwargs, population_kwargs,
                      population_names, utility_names)
 
 
@@ -97,3 +97,15 @@ def test_python_oracle_step_utility_matches_reference(name):
     env = po.OracleEnv(**oracle_kwargs(cfg))
     exact = not (cfg['kind'] == 'multi' and cfg['reward'] == 'sum')
     check_against_golden(env, cfg, z, exact_floats=exact)
+
+
+@pytest.mark.parametrize('name', obs_variant_names())
+def test_python_oracle_maxnorm_observation_matches_reference(name):
+    """MaxNormEnv.get_ue_obs (single_ue/variants.py:308-332): CentralMaxNormEnv (multi_ue/central.py:155-164) and the same
+    composition over MultiAgentMobileEnv; incl. a UE on top of a BS (capped at 1) and one out of every BS's range."""
+    cfg, z = load_golden(name)
+    env = po.OracleEnv(**oracle_kwargs(cfg))
+    check_against_golden(env, cfg, z, exact_floats=True)
+    n, m = cfg['n_ue'], len(cfg['bs_xy'])
+    dr = z['reset_obs'][0][n * m:2 * n * m].reshape(n, m) if cfg['kind'] == 'central' else z['reset_obs'][0][:, m:2 * m]
+    assert dr[11, 0] == 1.0 and (dr[10] < 0).all()
