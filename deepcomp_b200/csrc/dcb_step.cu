@@ -222,8 +222,9 @@ __device__ __forceinline__ double warp_reduce_env(int lane, const double *v, int
 // [region:kernel.setup]
 // ------------------------------------------------------------------------------------------------ the kernel
 // M32: all connection / in-range masks fit 32 bits (n_bs <= 32) -- halves the integer work on the mask paths
-// PAD: the envs have padding slots (NA < N, variable UE population); the common fixed-population case compiles without
-// the extra compares and the padding branch of the observers
+// PAD: the general instance -- the envs may have padding slots (NA < N, variable UE population) and the observation may be
+// a per-handle variant (MaxNorm); the common fixed-population RelNorm case compiles without the extra compares, the
+// padding branch of the observers and the variant branch
 template <int MAXT, bool M32, bool PAD>
 __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
     using mask_t = typename MaskType<M32>::type;
@@ -652,7 +653,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                     row_dr[b] = d2f;
                 }
                 // ---- dense pass B: 'dr' = snr_b / max_b snr_b (variants.py:276-284) = (d2min / d2_b)^h
-                if (p.obs_maxnorm) {          // MaxNormEnv (variants.py:308-332): per-handle variant, out-of-line fp64 SNR
+                if (PAD && p.obs_maxnorm) {   // MaxNormEnv (variants.py:308-332): per-handle variant (general instance only), out-of-line fp64 SNR
                     for (int b = 0; b < M; b++)
                         row_dr[b] = max_norm_snr(snr_of_d2_general(p.snr_c0, p.snr_h, tab, dist2(bsxy[b], x, y)));
                 } else if (d2minf >= 1e-6f) {        // below: d + EPSILON matters (in practice d = 0 exactly)
@@ -912,6 +913,8 @@ int dcb_step_regs_per_thread(int threads, int n_bs) {
 }
 
 cudaError_t dcb_launch_step(const StepArgs &a, int threads, int grid, size_t smem, cudaStream_t s) {
-    DCB_DISPATCH(threads, a.p.M <= 32, a.p.NA < a.p.N, (kern<<<grid, threads, smem, s>>>(a)));
+    // the general instance (PAD) also carries the per-handle observation variants; the fixed-population RelNorm case -- the
+    // measured path -- compiles without either
+    DCB_DISPATCH(threads, a.p.M <= 32, a.p.NA < a.p.N || a.p.obs_maxnorm, (kern<<<grid, threads, smem, s>>>(a)));
     return cudaGetLastError();
 }
