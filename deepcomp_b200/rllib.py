@@ -36,6 +36,8 @@ class _BatchAdapter:
         self.n_ue, self.n_bs = self.batch.n_ue, self.batch.n_bs
         self.agent_ids = [str(i + 1) for i in range(self.n_ue)]
         self._obs = None
+        # 'dr' is Box(0, 1) for the RelNorm observation, Box(-1, 1) for MaxNorm (variants.py:259, 313-317)
+        self._dr_low = -1 if self.batch.obs_norm == 'max' else 0
 
     def _central_obs(self, flat):
         nm = self.n_ue * self.n_bs
@@ -62,7 +64,7 @@ class CentralVectorEnv(_BatchAdapter):
         n, m = self.n_ue, self.n_bs
         self.action_space = spaces.MultiDiscrete([m + 1] * n)
         self.observation_space = spaces.Dict({
-            'connected': spaces.MultiBinary(n * m), 'dr': spaces.Box(low=0, high=1, shape=(n * m,)),
+            'connected': spaces.MultiBinary(n * m), 'dr': spaces.Box(low=self._dr_low, high=1, shape=(n * m,)),
             'utility': spaces.Box(low=-1, high=1, shape=(n,))})
         self._time = np.zeros(num_envs, dtype=np.int64)
 
@@ -103,7 +105,7 @@ class MultiAgentBaseEnv(_BatchAdapter):
         m = self.n_bs
         self.action_space = spaces.Discrete(m + 1)
         self.observation_space = spaces.Dict({
-            'connected': spaces.MultiBinary(m), 'dr': spaces.Box(low=0, high=1, shape=(m,)),
+            'connected': spaces.MultiBinary(m), 'dr': spaces.Box(low=self._dr_low, high=1, shape=(m,)),
             'utility': spaces.Box(low=-1, high=1, shape=(1,)), 'ues_at_bs': spaces.Box(low=0, high=1, shape=(m,)),
             'util_at_bs': spaces.Box(low=-1, high=1, shape=(m,))})
         self._time = np.zeros(num_envs, dtype=np.int64)
