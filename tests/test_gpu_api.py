@@ -7,6 +7,7 @@ from oracle import c_oracle
 from oracle.deepcomp_oracle import grid_layout
 
 from helpers import assert_close, assert_exact, load_golden
+from helpers import oracle_kwargs as helpers_oracle_kwargs
 
 pytestmark = pytest.mark.gpu
 
@@ -228,6 +229,41 @@ def test_step_many_is_bit_identical_to_single_steps(kind):
     sa, sb = a.get_state(), b.get_state()
     for k in sa:
         assert np.array_equal(sa[k], sb[k]), k
+
+
+def test_fragment_metrics_in_the_reference_result_layout():
+    """deepcomp_b200.metrics over a device fragment == the same summary over the per-step infos of the reference-shaped
+    facade (what Simulation.run_episode collects, simulation.py:472-554): env 0 of the batch is the facade's episode."""
+    from deepcomp_b200 import BatchedMobileEnv, metrics
+    from deepcomp_b200.env import MultiAgentMobileEnv
+    cfg, z = load_golden('medium3bs_5ue_multi')
+    T, N = cfg['steps'], cfg['n_ue']
+    env = MultiAgentMobileEnv(_env_config_from_golden(cfg))
+    env.reset()
+    rewards, su, dr = [], [], []
+    for t in range(T):
+        _, r, _, info = env.step({str(i + 1): int(z['actions'][t][i]) for i in range(N)})
+        rewards.append(sum(r.values()))                                                   # simulation.py:380
+        su.append(info['1']['scalar_metrics']['sum_utility'])
+        dr.append([info['1']['vector_metrics']['dr'][f'UE {i + 1}'] for i in range(N)])
+    env.close()
+    kw = helpers_oracle_kwargs(cfg)
+    seed = kw.pop('seed')
+    batch = BatchedMobileEnv(num_envs=2, seeds=[seed, seed + 1000], **kw)
+    batch.reset()
+    acts = torch.as_tensor(np.repeat(z['actions'][:T, None, :], 2, axis=1).astype(np.int32), device='cuda')
+    frag = batch.step_many(acts.contiguous(), info=True)
+    res = metrics.summarize_scalar_results([frag])
+    assert res['episode'] == [0, 1]
+    assert_close(res['step_reward_mean'][0], np.mean(rewards), 'step_reward_mean', 1e-6, 1e-6)
+    assert_close(res['step_reward_std'][0], np.std(rewards), 'step_reward_std', 1e-6, 1e-6)
+    assert_close(res['sum_utility_mean'][0], np.mean(su), 'sum_utility_mean', 1e-6, 1e-5)
+    assert res['step_reward_mean'][1] != res['step_reward_mean'][0]
+    df = metrics.vector_results([frag])['dr']
+    assert list(df.columns) == ['episode', 'time_step'] + [f'UE {i + 1}' for i in range(N)] and len(df) == 2 * T
+    assert_close(df[df['episode'] == 0][[f'UE {i + 1}' for i in range(N)]].to_numpy(dtype=np.float64), np.array(dr),
+                 'vector dr', 2e-6, 1e-6)
+    batch.close()
 
 
 def test_auto_reset_replays_the_seeded_episode():
