@@ -65,6 +65,9 @@ struct SmemLayout {
     int off_tab, off_stage, off_x, off_fac_pre, off_fac_post, off_hx, off_hy,
         off_hmask, off_hutil, off_hrb, off_hdr, off_hlost, off_bsx, off_bsy, off_vel,
         off_arg_pre, off_arg_post, off_bits, off_share, off_links, off_vthr, off_wagg, off_snext;
+#ifdef DCB_FX_AGG
+    int off_fxagg;   // experiment: per-(env, BS) fixed-point utility sums, [3][E*M][2] int32 (lo, hi)
+#endif
     int nbits;   // words per bitset
     int links_per_warp;   // capacity (entries) of one physics warp's link list
     int wagg_pairs;       // (env, BS) pairs one observer warp aggregates for itself: the envs its 32 rows touch x M
@@ -117,6 +120,9 @@ __host__ __device__ inline SmemLayout dcb_smem_layout(int kind, int N, int M, in
     L.wagg_pairs = ((31 / N + 2) * M + 1) & ~1;
     L.wagg_stride = align16(L.wagg_pairs * 28);
     L.off_wagg = o;     o += ((EN + 31) / 32) * L.wagg_stride;
+#ifdef DCB_FX_AGG
+    L.off_fxagg = o;    o += align16(3 * EM * 2 * 4);
+#endif
     L.total = o;
     return L;
 }

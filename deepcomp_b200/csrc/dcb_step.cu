@@ -205,6 +205,43 @@ __device__ __forceinline__ void warp_reduce_utility(int lane, const unsigned *bi
     }
 }
 
+#ifdef DCB_FX_AGG
+// Experiment (not in the default build): the physics threads add their utility, as a 2^-36 fixed-point number
+// split into two native 32-bit shared-memory atomics (64-bit shared atomics are CAS loops on sm_100a), to the sums of the
+// base stations they are linked to; integer sums are order-independent, so the result is deterministic and within
+// |C_b| * 2^-37 of the exact sum.  The observers then only count bits and convert -- no walk over the UEs.  The 'min'
+// aggregation (multi_agent.py:88-90) still needs the walk (warp_reduce_utility).
+#define DCB_FX_SCALE 68719476736.0          // 2^36
+#define DCB_FX_INV_SCALE 1.4551915228366852e-11
+__device__ __forceinline__ void fx_add_utility(int *fa, double util) {
+    const long long fx = __double2ll_rn(util * DCB_FX_SCALE);      // |util| <= 20: |fx| < 2^41
+    atomicAdd(fa, (int)(fx & 0xfffff));                             // low 20 bits, >= 0: 512 UEs stay below 2^29
+    atomicAdd(fa + 1, (int)(fx >> 20));                             // high part, signed: |.| < 2^21 per UE
+}
+__device__ __forceinline__ void warp_read_utility_fx(int lane, const unsigned *bits, const int *fx, int N, int NA, int M,
+                                                     int le0, int n_le, int *cnt, double *usum, double *umin,
+                                                     float *f_ues, float *f_util) {
+    const int NW = (N + 31) >> 5;
+    const int PW = n_le * M;
+    const double inv_n = 1.0 / (double)NA;
+    const float inv_m = 1.0f / (float)M;
+    for (int q = lane; q < PW; q += 32) {
+        const int ll = __float2int_rz(((float)q + 0.5f) * inv_m), b = q - ll * M;
+        const int le = le0 + ll;
+        const unsigned *pb = bits + (le * M + b) * NW;
+        int c = 0;
+        for (int w = 0; w < NW; w++) c += __popc(pb[w]);
+        const int *fa = fx + (le * M + b) * 2;
+        const double s = (double)(((long long)fa[1] << 20) + (long long)fa[0]) * DCB_FX_INV_SCALE;
+        cnt[q] = c;
+        usum[q] = s;
+        umin[q] = DCB_MAX_UTILITY;
+        f_ues[q] = (float)((double)c * inv_n);                                             // |C_b| / N (variants.py:296)
+        f_util[q] = c > 0 ? (float)(s * dcb_rcp((double)c) * (1.0 / DCB_MAX_UTILITY)) : 0.0f;
+    }
+}
+#endif
+
 // [region:reduce_env]
 // Reduction of one env's per-UE vector by one warp: mode 0 = sum, 2 = min; every lane gets the result
 __device__ __forceinline__ double warp_reduce_env(int lane, const double *v, int N, int mode) {
@@ -254,6 +291,9 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
     unsigned *bits_post3 = reinterpret_cast<unsigned *>(smem + L.off_bits);   // [3][nbits]
     unsigned *bits_pre2 = bits_post3 + 3 * L.nbits;                            // [2][nbits]
     unsigned *bits_fresh = bits_pre2 + 2 * L.nbits;                            // [nbits]
+#ifdef DCB_FX_AGG
+    int *fxagg3 = reinterpret_cast<int *>(smem + L.off_fxagg);                 // [3][E*M][2], rotates with bits_post3
+#endif
     unsigned short *links = reinterpret_cast<unsigned short *>(smem + L.off_links);
     double *vthr = reinterpret_cast<double *>(smem + L.off_vthr);
     uint32_t *snext = reinterpret_cast<uint32_t *>(smem + L.off_snext);
@@ -283,6 +323,9 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
     }
     for (int j = threadIdx.x; j < N; j += blockDim.x) velspec[j] = p.vel_spec[j];
     for (int j = threadIdx.x; j < 6 * L.nbits; j += blockDim.x) bits_post3[j] = 0u;
+#ifdef DCB_FX_AGG
+    for (int j = threadIdx.x; j < 6 * E * M; j += blockDim.x) fxagg3[j] = 0;
+#endif
     if (threadIdx.x >= 32 && threadIdx.x < 48) vthr[threadIdx.x - 32] = snap_threshold((double)(threadIdx.x - 32));
     __syncthreads();
 
@@ -330,6 +373,9 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
             const int par = step & 1;
             unsigned *bits_post = bits_post3 + rot * L.nbits;
             unsigned *bits_pre = bits_pre2 + par * L.nbits;
+#ifdef DCB_FX_AGG
+            int *fx_post = fxagg3 + rot * 2 * E * M;
+#endif
             rot = rot == 2 ? 0 : rot + 1;              // now (step + 1) % 3
             double rb = rb_next;
             int lost = 0;
@@ -515,6 +561,9 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                 bits_pre[j] = 0u;
                 if (step >= 2) bits_post3[rot * L.nbits + j] = 0u;
             }
+#ifdef DCB_FX_AGG
+            if (step >= 2) for (int j = t; j < 2 * E * M; j += G) fxagg3[rot * 2 * E * M + j] = 0;
+#endif
             if (valid) {
 // [region:P.rates+handoff]
                 // ---- post-move rates of this step and pre-move rates of the next one in ONE pass over the links;
@@ -541,6 +590,10 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                 hx[h] = x; hy[h] = y; hmask[h] = mask;
                 hutil[h] = util;
                 hrb[h] = rb; hdr[h] = dr; hlost[h] = lost;
+#ifdef DCB_FX_AGG
+                if (!central && p.reward != DCB_REWARD_MIN)
+                    for (mask_t m = mask; m; m &= m - 1) fx_add_utility(fx_post + (le * M + mask_ffs(m) - 1) * 2, util);
+#endif
             }
             bar_arrive(BAR_FULL + par, 2 * G);
             DCB_TRACE_PT(0, 7);
@@ -620,7 +673,15 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
             }
 // [region:O.util_reduce]
             const unsigned *bits_post = bits_post3 + orot * L.nbits;
+#ifdef DCB_FX_AGG
+            const int *fx_post = fxagg3 + orot * 2 * E * M;
+#endif
             orot = orot == 2 ? 0 : orot + 1;
+#ifdef DCB_FX_AGG
+            if (!central && p.reward != DCB_REWARD_MIN)
+                warp_read_utility_fx(lane, bits_post, fx_post, N, NA, M, le0, n_le, cnt_o, usum_o, umin_o, f_ues, f_util);
+            else
+#endif
             if (!central)
                 warp_reduce_utility(lane, bits_post, hutil + hbase, N, NA, M, le0, n_le, p.reward == DCB_REWARD_MIN, cnt_o,
                                     usum_o, umin_o, f_ues, f_util);
