@@ -122,7 +122,7 @@ def threshold_distance():
 
 class _UE:
     __slots__ = ('idx', 'id', 'x', 'y', 'init_x', 'init_y', 'init_velocity', 'velocity', 'wx', 'wy', 'pausing',
-                 'curr_pause', 'rng', 'mrng', 'bs_dr', 'ewma_dr')
+                 'curr_pause', 'rng', 'mrng', 'bs_dr', 'ewma_dr', 'uniform', 'move_x', 'move_y')
 
 
 class OracleEnv:
@@ -140,10 +140,32 @@ class OracleEnv:
 
     def __init__(self, kind, n_ue, bs_xy, map_wh, sharing='mixed', velocities='slow', seed=None, reward='avg',
                  episode_length=100, rand_episodes=False, init_pos=None, pause_duration=2, border_buffer=10,
-                 max_ues=None, ue_arrival=None, new_ue_interval=None, util_func='log', dr_req=1, obs_norm='rel'):
+                 max_ues=None, ue_arrival=None, new_ue_interval=None, util_func='log', dr_req=1, obs_norm='rel',
+                 obs_variant=None, obs_opts=None, uniform_moves=None, sequential=False):
         assert kind in ('central', 'multi')
+        # sequential: SeqMultiAgentMobileEnv (multi_ue/multi_agent.py:110-179; restated for the next round, no CUDA path
+        # yet): one UE acts per call, the UEs move and time advances after the last one; obs / reward of the next UE only
+        assert not sequential or kind == 'multi'
+        self.sequential = sequential
+        self.ue_order_idx = 0                                   # multi_agent.py:119 (never reset, not even by reset())
+        # uniform_moves: None, or per UE None (RandomWaypoint) / (move_x, move_y) with numbers or 'slow' / 'fast' =
+        # UniformMovement (util/movement.py:26-80; restated for the next round's kernels, no CUDA path yet)
+        self.uniform_moves = uniform_moves
         assert obs_norm in ('rel', 'max')                       # RelNormEnv / MaxNormEnv (variants.py:271-303 / 308-332)
         self.obs_norm = obs_norm
+        # other observation classes of the reference (restated for the next round's kernels; no CUDA path yet):
+        # 'normdr' = NormDrMobileEnv / CentralNormDrEnv (variants.py:173-250, central.py:107-140),
+        # 'datarate' = DatarateMobileEnv / CentralDrEnv (variants.py:42-170, central.py:75-104) with its env_config options
+        assert obs_variant in (None, 'normdr', 'datarate')
+        self.obs_variant = obs_variant
+        self.obs_opts = dict(dr_cutoff='auto', sub_req_dr=True, curr_dr_obs=False, ues_at_bs_obs=False, dist_obs=False,
+                             next_dist_obs=False)
+        self.obs_opts.update(obs_opts or {})
+        if obs_variant == 'datarate':                           # variants.py:75-79
+            o = self.obs_opts
+            assert not (o['dr_cutoff'] == 'auto' and not o['sub_req_dr'])
+            assert (not o['curr_dr_obs']) or (o['dr_cutoff'] == 'auto' and o['sub_req_dr'])
+            assert o['dist_obs'] or not o['next_dist_obs']
         assert util_func in ('log', 'step')                     # 'linear' fails the reference's own assert (utility.py:18)
         self.util_func, self.dr_req = util_func, dr_req
         self.kind = kind
@@ -179,6 +201,7 @@ class OracleEnv:
             ue.id = str(i + 1)                                  # util/env_setup.py:148-160
             ue.init_x, ue.init_y = ('random', 'random') if init_pos is None else init_pos[i]
             ue.init_velocity = velocities[i]
+            ue.uniform = None if uniform_moves is None else uniform_moves[i]
             ue.rng = random.Random()                            # entities/user.py:38
             ue.mrng = random.Random()                           # util/movement.py:14
             ue.bs_dr = {}
@@ -205,7 +228,19 @@ class OracleEnv:
                 ue.mrng.seed(seed + offset)
 
     def _movement_reset(self, ue):
-        """util/movement.py:110-130"""
+        """util/movement.py:110-130 (RandomWaypoint.reset); :47-64 (UniformMovement.reset)"""
+        if getattr(ue, 'uniform', None) is not None:
+            mv = []
+            for init in ue.uniform:                             # move_x first, then move_y
+                if init == 'slow':
+                    mv.append(ue.mrng.randint(1, 5))
+                elif init == 'fast':
+                    mv.append(ue.mrng.randint(10, 20))
+                else:
+                    mv.append(init)
+            ue.move_x, ue.move_y = mv
+            ue.velocity, ue.wx, ue.wy, ue.pausing, ue.curr_pause = 0, 0.0, 0.0, False, 0
+            return
         if ue.init_velocity == 'slow':
             ue.velocity = ue.mrng.randint(1, 3)
         elif ue.init_velocity == 'fast':
@@ -313,7 +348,15 @@ class OracleEnv:
             self.conn_ues[b].append(ue)
 
     def movement_step(self, ue):
-        """util/movement.py:132-181"""
+        """util/movement.py:132-181 (RandomWaypoint.step); :66-80 (UniformMovement.step)"""
+        if getattr(ue, 'uniform', None) is not None:
+            nx, ny = ue.x + ue.move_x, ue.y + ue.move_y
+            # Point.within(map.shape): strictly inside the rectangle (a point on the border is not within)
+            if not (0 < nx < self.width and 0 < ny < self.height):
+                ue.move_x, ue.move_y = -ue.move_x, -ue.move_y   # bounce: BOTH components flip, no second check
+                nx, ny = ue.x + ue.move_x, ue.y + ue.move_y
+            ue.x, ue.y = float(nx), float(ny)
+            return
         if ue.x == ue.wx and ue.y == ue.wy:
             ue.pausing = True
         if ue.pausing:
@@ -321,14 +364,17 @@ class OracleEnv:
                 ue.curr_pause += 1
                 return
             self._movement_reset(ue)
+        ue.x, ue.y = self.step_towards_waypoint(ue)
+
+    @staticmethod
+    def step_towards_waypoint(ue):
+        """util/movement.py:132-156: the position one step closer to the waypoint (the UE itself is not moved)"""
         if _dist(ue.x, ue.y, ue.wx, ue.wy) <= ue.velocity:
-            ue.x, ue.y = ue.wx, ue.wy
-            return
+            return ue.wx, ue.wy
         vx = ue.wx - ue.x
         vy = ue.wy - ue.y
         norm = _norm2(vx, vy)
-        ue.x = ue.x + ue.velocity * (vx / norm)
-        ue.y = ue.y + ue.velocity * (vy / norm)
+        return ue.x + ue.velocity * (vx / norm), ue.y + ue.velocity * (vy / norm)
 
     def move(self, ue, weight=0.9):
         """user.py:148-188"""
@@ -356,8 +402,46 @@ class OracleEnv:
             rewards.append(0 if update_only else self.calc_reward(self.utility(ue), 0))
         return rewards
 
+    def get_ue_obs_normdr(self, ue):
+        """NormDrMobileEnv.get_ue_obs (single_ue/variants.py:198-250): the *shared* rate the UE gets or would get from every
+        BS (station.py:204-220: 0 out of range; a UE that is not connected is counted in temporarily), cut at 100"""
+        cutoff = 100
+        bs_dr = [min(self.data_rate(b, ue), cutoff) / cutoff for b in range(self.n_bs)]
+        bs_conn = [int(b in ue.bs_dr) for b in range(self.n_bs)]
+        return {'dr': bs_dr, 'connected': bs_conn, 'dr_total': [min(self.curr_dr(ue), cutoff) / cutoff]}
+
+    def get_ue_obs_datarate(self, ue):
+        """DatarateMobileEnv.get_ue_obs (single_ue/variants.py:127-170)"""
+        o, req = self.obs_opts, self.dr_req
+        obs = {}
+        if o['dr_cutoff'] == 'auto':
+            obs['dr'] = [min(self.data_rate(b, ue) - req, req) / req for b in range(self.n_bs)]
+        elif o['sub_req_dr']:
+            obs['dr'] = [min(self.data_rate(b, ue) - req, o['dr_cutoff']) for b in range(self.n_bs)]
+        else:
+            obs['dr'] = [min(self.data_rate(b, ue), o['dr_cutoff']) for b in range(self.n_bs)]
+        obs['connected'] = [int(b in ue.bs_dr) for b in range(self.n_bs)]
+        if o['curr_dr_obs']:
+            total = self.curr_dr(ue)
+            total -= req
+            total = min(total, req)
+            obs['dr_total'] = [total / req]
+        if o['ues_at_bs_obs']:
+            obs['ues_at_bs'] = [len(self.conn_ues[b]) for b in range(self.n_bs)]
+        diagonal = np.sqrt(self.width ** 2 + self.height ** 2)                           # entities/map.py:26
+        if o['dist_obs']:
+            obs['dist'] = [_dist(ue.x, ue.y, bx, by) / diagonal for bx, by in self.bs_xy]
+        if o['next_dist_obs']:
+            nx, ny = self.step_towards_waypoint(ue)
+            obs['next_dist'] = [_dist(nx, ny, bx, by) / diagonal for bx, by in self.bs_xy]
+        return obs
+
     def get_ue_obs(self, ue):
         """single_ue/variants.py:271-303"""
+        if self.obs_variant == 'normdr':
+            return self.get_ue_obs_normdr(ue)
+        if self.obs_variant == 'datarate':
+            return self.get_ue_obs_datarate(ue)
         bs_conn = [int(b in ue.bs_dr) for b in range(self.n_bs)]
         bs_dr = [self.snr(b, ue) for b in range(self.n_bs)]
         max_dr = max(bs_dr)
@@ -387,15 +471,19 @@ class OracleEnv:
         per_ue = [self.get_ue_obs(ue) for ue in self.ues]
         missing = self.max_ues - len(self.ues)
         if self.kind == 'central':
+            keys = ('connected', 'dr', 'utility')
+            if self.obs_variant is not None:
+                # CentralNormDrEnv / CentralDrEnv (central.py:75-140): the keys of the class's Dict space, sorted
+                keys = sorted(per_ue[0].keys())
             out = []
-            for key, width in (('connected', self.n_bs), ('dr', self.n_bs), ('utility', 1)):
+            for key in keys:
                 for o in per_ue:
                     out.extend(o[key])
-                out.extend([0] * (missing * width))             # central.py:46-55: zeros for the UEs not there
+                out.extend([0] * (missing * len(per_ue[0][key])))   # central.py:46-55: zeros for the UEs not there
             return np.asarray(out, dtype=np.float64)
-        rows = np.stack([np.concatenate([np.asarray(o[k], dtype=np.float64)
-                                         for k in ('connected', 'dr', 'ues_at_bs', 'util_at_bs', 'utility')])
-                         for o in per_ue])
+        keys = ('connected', 'dr', 'ues_at_bs', 'util_at_bs', 'utility') if self.obs_variant is None \
+            else sorted(per_ue[0].keys())
+        rows = np.stack([np.concatenate([np.asarray(o[k], dtype=np.float64) for k in keys]) for o in per_ue])
         return self._pad(rows)
 
     def step_reward(self, rewards):
@@ -484,10 +572,42 @@ class OracleEnv:
             del ue.bs_dr[b]
             self.conn_ues[b].remove(ue)
 
+    def step_sequential(self, actions):
+        """SeqMultiAgentMobileEnv.step (multi_ue/multi_agent.py:149-179): only the current UE's entry of `actions` is
+        applied (the agent dict holds that id only, multi_agent.py:21-30); rates and rewards are updated; after the last
+        UE of the order the UEs move, the rates are updated again and time advances; then the NEXT UE becomes current and
+        its observation row and its multi-agent reward are returned."""
+        actions = np.asarray(actions)
+        cur = self.ues[self.ue_order_idx]
+        a = int(actions[self.ue_order_idx])
+        if a > 0:
+            self.connect_to_bs(cur, a - 1)
+        rewards_before = self.update_ue_drs_rewards()
+        moved = False
+        if self.ue_order_idx + 1 < len(self.ues):
+            self.ue_order_idx += 1
+        else:
+            self.ue_order_idx = 0
+            self.last_lost_conn = [self.move(ue) for ue in self.ues]
+            self.update_ue_drs_rewards(update_only=True)
+            self.time += 1
+            moved = True
+        nxt = self.ue_order_idx
+        o = self.get_ue_obs(self.ues[nxt])
+        obs = np.concatenate([np.asarray(o[k], dtype=np.float64) for k in sorted(o.keys())])
+        reward = self.step_reward(rewards_before)[nxt]
+        out = self.snapshot()
+        lost = self.last_lost_conn if moved else [0] * len(self.ues)
+        out.update(obs=obs, reward=np.float64(reward), lost_conn=self._pad(np.asarray(lost, dtype=np.int32)),
+                   sum_utility=np.float64(sum([self.utility(ue) for ue in self.ues])), time=self.time, done=None)
+        return out
+
     def step(self, actions):
         """single_ue/base.py:413-466. actions: int[max_ues], 0 = noop, b+1 = toggle BS b (entry i = i-th UE present)"""
         actions = np.asarray(actions)
         assert actions.shape == (self.max_ues,) and np.all(actions >= 0) and np.all(actions <= self.n_bs)
+        if self.sequential:
+            return self.step_sequential(actions)
         for pos, ue in enumerate(self.ues):                     # base.py:247-282
             a = int(actions[pos])
             if a > 0:
@@ -564,7 +684,9 @@ class OracleEnv:
             curr_dr=np.array([float(self.curr_dr(ue)) for ue in self.ues]),
             ewma=np.array([float(ue.ewma_dr) for ue in self.ues]),
             utility=np.array([float(self.utility(ue)) for ue in self.ues]),
-            movement=np.array([[ue.velocity, ue.wx, ue.wy, float(ue.pausing), ue.curr_pause] for ue in self.ues],
+            # RandomWaypoint: velocity, waypoint, pausing, curr_pause; UniformMovement: move_x, move_y, -1, 0, 0
+            movement=np.array([[ue.move_x, ue.move_y, -1.0, 0.0, 0.0] if getattr(ue, 'uniform', None) is not None else
+                               [ue.velocity, ue.wx, ue.wy, float(ue.pausing), ue.curr_pause] for ue in self.ues],
                               dtype=np.float64))
         d = {k: self._pad(v) for k, v in d.items()}
         d['num_ue'] = n
@@ -573,5 +695,7 @@ class OracleEnv:
     def reset_trace(self):
         obs = self.reset()
         out = self.snapshot()
+        if self.sequential:                                     # multi_agent.py:122-124: the current UE's row only
+            obs = obs[self.ue_order_idx]
         out['obs'] = obs
         return out

@@ -108,6 +108,37 @@ def obs_variant_scenarios():
     return S
 
 
+def pending_obs_scenarios():
+    """Observation classes the oracle restates but the CUDA path does not offer yet: CentralNormDrEnv
+    (central.py:107-140 over variants.py:173-250) and CentralDrEnv (central.py:75-104 over variants.py:42-170) with its
+    env_config options.  Traces for the next round's kernels; tests/test_oracle_golden.py pins the oracle on them."""
+    S = []
+    W, H, gbs = rl.grid_layout(5)
+    vel = ['slow', 'fast', 0, 2.5] * 3
+    base = dict(kind='central', n_ue=12, bs_xy=gbs, map_wh=(W, H), velocities=vel, seed=29, reward='avg', steps=50,
+                action_seed=12, episodes=1)
+    S.append(dict(base, name='normdr_central_mixed', sharing='mixed', obs_variant='normdr'))
+    S.append(dict(base, name='normdr_central_max-cap', sharing='max-cap', obs_variant='normdr'))
+    S.append(dict(base, name='datarate_central_auto_all', sharing='mixed', obs_variant='datarate', util_func='step',
+                  obs_opts=dict(dr_cutoff='auto', sub_req_dr=True, curr_dr_obs=True, ues_at_bs_obs=True, dist_obs=True,
+                                next_dist_obs=True)))
+    S.append(dict(base, name='datarate_central_cutoff200', sharing='mixed', obs_variant='datarate',
+                  obs_opts=dict(dr_cutoff=200, sub_req_dr=False)))
+    # UniformMovement (util/movement.py:26-80): constant step, both components flip when the next point would not be
+    # strictly inside the map; mixed with RandomWaypoint UEs; long enough for several bounces
+    um = [('slow', 'slow'), ('fast', 'slow'), None, (3, -2), (0, 7.5), None, ('fast', 'fast'), (-4, 0)]
+    for kind in ('central', 'multi'):
+        S.append(dict(name=f'uniform_{kind}_avg', kind=kind, n_ue=8, bs_xy=gbs, map_wh=(W, H), sharing='mixed',
+                      velocities='slow', seed=31, reward='avg', steps=120, action_seed=13, episodes=2,
+                      uniform_moves=um))
+    # SeqMultiAgentMobileEnv (multi_ue/multi_agent.py:110-179): one UE acts per call; 6 UEs x 40 time steps
+    for reward in ('avg', 'min'):
+        S.append(dict(name=f'seq_multi_{reward}', kind='multi', n_ue=6, bs_xy=gbs, map_wh=(W, H), sharing='mixed',
+                      velocities=['slow', 'fast', 0, 2.5, 'slow', 'fast'], seed=37, reward=reward, steps=240,
+                      action_seed=14, episodes=1, sequential=True))
+    return S
+
+
 def brute_scenarios():
     """BruteForceAgent (deepcomp/agent/brute_force.py:59-94): all (M+1)^N joint actions tested with
     MobileEnv.test_ue_actions (single_ue/base.py:284-313) on the central env, the best one taken."""
@@ -207,7 +238,9 @@ def record(sc):
                        velocities=sc['velocities'], reward=sc['reward'], episode_length=sc['steps'],
                        init_pos=sc.get('init_pos'), max_ues=sc.get('max_ues'), ue_arrival=sc.get('ue_arrival'),
                        new_ue_interval=sc.get('new_ue_interval'), util_func=sc.get('util_func', 'log'),
-                       obs_norm=sc.get('obs_norm', 'rel'))
+                       obs_norm=sc.get('obs_norm', 'rel'), obs_variant=sc.get('obs_variant'),
+                       obs_opts=sc.get('obs_opts'), uniform_moves=sc.get('uniform_moves'),
+                       sequential=sc.get('sequential', False))
     pop = 'max_ues' in sc
     n_act = sc.get('max_ues', sc['n_ue'])                # length of the action vector (central.py:28)
     tr = rl.RefTrace(env, sc['kind'])
@@ -238,6 +271,10 @@ def record(sc):
             # base.py:371-381: done is None; multi_agent.py:97-102: dict of None incl. '__all__'
             if sc['kind'] == 'central':
                 assert s['done'] is None
+            elif sc.get('sequential'):
+                # multi_agent.py:134-141 wraps MultiAgentMobileEnv.done() (already a dict) under the two keys
+                assert '__all__' in s['done'] and len(s['done']) == 2
+                assert all(v is None for d in s['done'].values() for v in d.values())
             elif pop:
                 assert all(v is None for v in s['done'].values())
             else:
@@ -305,7 +342,7 @@ def main():
     if not only:
         np.savez_compressed(os.path.join(OUT_DIR, 'anchors.npz'), **anchors())
     for sc in scenarios() + policy_scenarios() + population_scenarios() + brute_scenarios() + utility_scenarios() + \
-            obs_variant_scenarios():
+            obs_variant_scenarios() + pending_obs_scenarios():
         if not sc['name'].startswith(only):
             continue
         data = record_brute(sc) if sc['name'].startswith('brute_') else record(sc)

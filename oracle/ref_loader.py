@@ -31,14 +31,16 @@ def _import_reference():
     from deepcomp.env.entities.map import Map
     from deepcomp.env.entities.station import Basestation
     from deepcomp.env.entities.user import User
-    from deepcomp.env.util.movement import RandomWaypoint
-    from deepcomp.env.multi_ue.central import CentralRelNormEnv, CentralMaxNormEnv
-    from deepcomp.env.multi_ue.multi_agent import MultiAgentMobileEnv
+    from deepcomp.env.util.movement import RandomWaypoint, UniformMovement
+    from deepcomp.env.multi_ue.central import CentralRelNormEnv, CentralMaxNormEnv, CentralNormDrEnv, CentralDrEnv
+    from deepcomp.env.multi_ue.multi_agent import MultiAgentMobileEnv, SeqMultiAgentMobileEnv
     from deepcomp.env.single_ue.variants import MaxNormEnv
     from shapely.geometry import Point
     return dict(Map=Map, Basestation=Basestation, User=User, RandomWaypoint=RandomWaypoint,
                 CentralRelNormEnv=CentralRelNormEnv, MultiAgentMobileEnv=MultiAgentMobileEnv, Point=Point,
-                CentralMaxNormEnv=CentralMaxNormEnv, MaxNormEnv=MaxNormEnv)
+                CentralMaxNormEnv=CentralMaxNormEnv, MaxNormEnv=MaxNormEnv, CentralNormDrEnv=CentralNormDrEnv,
+                CentralDrEnv=CentralDrEnv, UniformMovement=UniformMovement,
+                SeqMultiAgentMobileEnv=SeqMultiAgentMobileEnv)
 
 
 def sharing_for_bs(sharing, b):
@@ -58,7 +60,8 @@ def grid_layout(n_bs, pitch=100, border=10):
 
 def build_env(kind, n_ue, seed, bs_xy, map_wh, sharing='mixed', velocities='slow', reward='avg',
               episode_length=100, rand_episodes=False, init_pos=None, max_ues=None, ue_arrival=None,
-              new_ue_interval=None, util_func='log', obs_norm='rel'):
+              new_ue_interval=None, util_func='log', obs_norm='rel', obs_variant=None, obs_opts=None,
+              uniform_moves=None, sequential=False):
     """
     Build a reference env.
 
@@ -82,15 +85,31 @@ def build_env(kind, n_ue, seed, bs_xy, map_wh, sharing='mixed', velocities='slow
     ue_list = []
     for i in range(n_ue):
         px, py = ('random', 'random') if init_pos is None else init_pos[i]
-        ue_list.append(R['User'](str(i + 1), m, pos_x=px, pos_y=py,
-                                 movement=R['RandomWaypoint'](m, velocity=velocities[i]), util_func=util_func))
+        if uniform_moves is not None and uniform_moves[i] is not None:
+            mv = R['UniformMovement'](m, move_x=uniform_moves[i][0], move_y=uniform_moves[i][1])   # movement.py:26-80
+        else:
+            mv = R['RandomWaypoint'](m, velocity=velocities[i])
+        ue_list.append(R['User'](str(i + 1), m, pos_x=px, pos_y=py, movement=mv, util_func=util_func))
     env_config = {
         'episode_length': episode_length, 'seed': seed, 'map': m, 'bs_list': bs_list, 'ue_list': ue_list,
         'rand_episodes': rand_episodes, 'new_ue_interval': new_ue_interval, 'reward': reward, 'max_ues': max_ues,
         'ue_arrival': None if ue_arrival is None else {int(t): int(n) for t, n in ue_arrival.items()},
         'log_metrics': True, 'dashboard': False, 'ue_details': False,
     }
-    if obs_norm == 'max':
+    if sequential:
+        assert kind == 'multi' and obs_variant is None and obs_norm == 'rel'
+        return R['SeqMultiAgentMobileEnv'](env_config)           # multi_agent.py:110-179
+    if obs_variant is not None:
+        # CentralNormDrEnv (central.py:107-140) / CentralDrEnv (central.py:75-104, options read from env_config,
+        # variants.py:68-73); the reference has no multi-agent class with these observations
+        assert kind == 'central' and obs_variant in ('normdr', 'datarate')
+        if obs_variant == 'datarate':
+            opts = dict(dr_cutoff='auto', sub_req_dr=True, curr_dr_obs=False, ues_at_bs_obs=False, dist_obs=False,
+                        next_dist_obs=False)
+            opts.update(obs_opts or {})
+            env_config.update(opts)
+        cls = R['CentralNormDrEnv'] if obs_variant == 'normdr' else R['CentralDrEnv']
+    elif obs_norm == 'max':
         cls = R['CentralMaxNormEnv'] if kind == 'central' else \
             type('MultiAgentMaxNormEnv', (R['MultiAgentMobileEnv'], R['MaxNormEnv']), {})
     else:
@@ -139,13 +158,20 @@ class RefTrace:
 
     def movement(self):
         """velocity, waypoint x, waypoint y, pausing, curr_pause per UE"""
-        return np.array([[ue.movement.velocity, ue.movement.waypoint.x, ue.movement.waypoint.y,
+        return np.array([[ue.movement.move_x, ue.movement.move_y, -1.0, 0.0, 0.0] if hasattr(ue.movement, 'move_x') else
+                         [ue.movement.velocity, ue.movement.waypoint.x, ue.movement.waypoint.y,
                           float(ue.movement.pausing), ue.movement.curr_pause] for ue in self.env.ue_list],
                         dtype=np.float64)
 
     # ---- obs / reward flattening (RLlib Dict-flattening order = sorted keys) -------------
+    def _sequential(self):
+        return hasattr(self.env, 'ue_order_idx')
+
     def flat_obs(self, obs):
         e = self.env
+        if self._sequential():                  # SeqMultiAgentMobileEnv: the current UE's observation only
+            (o,) = obs.values()
+            return np.concatenate([np.asarray(o[k], dtype=np.float64).ravel() for k in sorted(o.keys())])
         if self.kind == 'central':
             return np.concatenate([np.asarray(obs[k], dtype=np.float64) for k in sorted(obs.keys())])
         rows = []
@@ -155,12 +181,17 @@ class RefTrace:
         return self._pad(np.stack(rows))
 
     def flat_reward(self, reward):
+        if self._sequential():
+            (r,) = reward.values()
+            return np.float64(r)
         if self.kind == 'central':
             return np.float64(reward)
         return self._pad(np.array([float(reward[ue.id]) for ue in self.env.ue_list], dtype=np.float64))
 
     def to_action(self, a):
         """a: int array [N] -> the action object the env class expects"""
+        if self._sequential():                  # only the current UE acts (multi_agent.py:21-30 skips the others)
+            return {self.env.curr_ue.id: int(a[self.env.ue_order_idx])}
         if self.kind == 'central':
             return np.asarray(a, dtype=np.int64)          # length max_ues; entries beyond the UEs present are ignored
         return {ue.id: int(a[i]) for i, ue in enumerate(self.env.ue_list)}
@@ -187,7 +218,10 @@ class RefTrace:
         return out
 
     def step(self, a):
+        self._lost = None
         obs, reward, done, info = self.env.step(self.to_action(a))
+        if self._lost is None:                  # a sequential sub-step without a move
+            self._lost = [0] * len(self.env.ue_list)
         self.last_obs = obs
         out = self.snapshot()
         out['obs'] = self.flat_obs(obs)
@@ -195,7 +229,11 @@ class RefTrace:
         out['lost_conn'] = self._pad(np.array(self._lost, dtype=np.int32))
         out['done'] = done
         out['info'] = info
-        if self.kind == 'multi':
+        if self._sequential():
+            # multi_agent.py:143-146 wraps MultiAgentMobileEnv.info() (already a dict per UE id) once more
+            (inner,) = info.values()
+            info0 = next(iter(inner.values()))
+        elif self.kind == 'multi':
             info0 = info[self.env.ue_list[0].id]
         else:
             info0 = info

@@ -5,8 +5,9 @@ import pytest
 from oracle import c_oracle
 from oracle import deepcomp_oracle as po
 
-from helpers import (GOLDEN_DIR, assert_close, assert_exact, brute_names, check_against_golden, golden_names, load_golden, obs_variant_names, oracle_kwargs, population_kwargs,
-                     population_names, utility_names)
+from helpers import (GOLDEN_DIR, assert_close, assert_exact, brute_names, check_against_golden, golden_names, load_golden, obs_variant_names, oracle_kwargs, pending_movement_names, pending_obs_names,
+                     pending_sequential_names,
+                     population_kwargs, population_names, utility_names)
 
 
 def test_anchor_known_answers():
@@ -109,3 +110,54 @@ def test_python_oracle_maxnorm_observation_matches_reference(name):
     n, m = cfg['n_ue'], len(cfg['bs_xy'])
     dr = z['reset_obs'][0][n * m:2 * n * m].reshape(n, m) if cfg['kind'] == 'central' else z['reset_obs'][0][:, m:2 * m]
     assert dr[11, 0] == 1.0 and (dr[10] < 0).all()
+
+
+@pytest.mark.parametrize('name', pending_obs_names())
+def test_python_oracle_normdr_and_datarate_observations_match_reference(name):
+    """CentralNormDrEnv (multi_ue/central.py:107-140, single_ue/variants.py:173-250) and CentralDrEnv (central.py:75-104,
+    variants.py:42-170, all of its env_config options): the shared rate a UE gets or would get from every BS
+    (station.py:204-220).  Oracle only -- the CUDA path does not offer these classes yet (DESIGN.md section 6e')."""
+    cfg, z = load_golden(name)
+    env = po.OracleEnv(**oracle_kwargs(cfg))
+    check_against_golden(env, cfg, z, exact_floats=True)
+    n, m = cfg['n_ue'], len(cfg['bs_xy'])
+    width = z['step_obs'].shape[1]
+    if cfg['obs_variant'] == 'normdr':
+        assert width == 2 * n * m + n                       # connected | dr | dr_total
+    elif cfg['obs_opts'].get('next_dist_obs'):
+        assert width == 5 * n * m + n                       # connected | dist | dr | dr_total | next_dist | ues_at_bs
+    else:
+        assert width == 2 * n * m
+
+
+@pytest.mark.parametrize('name', pending_movement_names())
+def test_python_oracle_uniform_movement_matches_reference(name):
+    """UniformMovement (util/movement.py:26-80) next to RandomWaypoint UEs: constant step, both components flip when the
+    next point would not be strictly inside the map; two episodes ('slow' / 'fast' steps are redrawn at the reset).
+    Oracle only -- the CUDA path does not offer this movement yet."""
+    cfg, z = load_golden(name)
+    env = po.OracleEnv(**oracle_kwargs(cfg))
+    check_against_golden(env, cfg, z, exact_floats=True)
+    mv = z['step_movement']                                     # [T, N, 5]: uniform UEs are (move_x, move_y, -1, 0, 0)
+    uni = [i for i, u in enumerate(cfg['uniform_moves']) if u is not None]
+    assert (mv[:, uni, 2] == -1).all()
+    # at least one bounce happened: the sign of some UE's step changed within an episode
+    assert any((np.sign(mv[:cfg['steps'], i, 0]) != np.sign(mv[0, i, 0])).any() or
+               (np.sign(mv[:cfg['steps'], i, 1]) != np.sign(mv[0, i, 1])).any() for i in uni)
+    W, H = cfg['map_wh']
+    pos = z['step_pos'][:, uni]
+    assert (pos[..., 0] > -21).all() and (pos[..., 0] < W + 21).all()
+
+
+@pytest.mark.parametrize('name', pending_sequential_names())
+def test_python_oracle_sequential_multi_agent_matches_reference(name):
+    """SeqMultiAgentMobileEnv (multi_ue/multi_agent.py:110-179): one UE acts per call, the UEs move and time advances
+    after the last one; observation row and multi-agent reward of the next UE.  Oracle only -- no CUDA path yet."""
+    cfg, z = load_golden(name)
+    env = po.OracleEnv(**oracle_kwargs(cfg))
+    check_against_golden(env, cfg, z, exact_floats=True)
+    n, m = cfg['n_ue'], len(cfg['bs_xy'])
+    assert z['step_obs'].shape == (cfg['steps'], 4 * m + 1) and z['step_reward'].shape == (cfg['steps'],)
+    assert z['step_time'][-1] == cfg['steps'] // n              # time advances once per round of the UEs
+    moved = np.flatnonzero(np.diff(np.concatenate([[0], z['step_time']])))
+    assert (moved % n == n - 1).all()
