@@ -16,6 +16,10 @@ GEOS ``sqrt(dx*dx+dy*dy)``, restated in ``_dist``.
 The restatement keeps the reference's per-object evaluation order (dict insertion order of
 ``ue.bs_dr``, list order of ``bs.conn_ues``) so that floating-point sums associate identically.
 All file:line citations are relative to /root/reference/deepcomp/.
+
+Beyond what the CUDA path offers today the oracle also restates (pinned on traces of the reference, kernels to follow):
+CentralNormDrEnv / CentralDrEnv observations (``obs_variant``), UniformMovement (``uniform_moves``) and
+SeqMultiAgentMobileEnv (``sequential``).
 """
 import math
 import random
