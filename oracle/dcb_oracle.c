@@ -26,6 +26,7 @@
 #define MIN_UTILITY (-20.0)
 #define MAX_UTILITY 20.0
 #define SNR_THRESHOLD 2e-8
+#define MAX_SNR_THRESHOLD 7e-6   /* MaxNormEnv.MAX_SNR_THRESHOLD, single_ue/variants.py:311 */
 #define BW 9e6
 #define NOISE 1e-9
 #define TX_POWER 30.0
@@ -118,6 +119,9 @@ void orc_rng_draws(long long seed, int n_raw, uint32_t *raw, int n_int, const in
 /* ------------------------------------------------------------------------------------------------ env */
 typedef struct orc_env {
     int kind, n_ue, n_bs, width, height, reward_agg, rand_episodes, pause_duration, border_buffer, has_seed;
+    int util_step;        /* User.util_func: 0 = 'log' (utility.py:36-54), 1 = 'step' (utility.py:23-33) */
+    double dr_req;        /* User.dr_req (user.py:17-30) */
+    int obs_maxnorm;      /* observation 'dr': 0 = RelNormEnv (variants.py:276-284), 1 = MaxNormEnv (variants.py:308-332) */
     long long seed;
     int time;
     double total_utility;
@@ -216,7 +220,8 @@ static void update_rates(orc_env *e) {
             e->link_rate[i * M + b] = r;
         }
         e->curr_dr[i] = total;
-        e->utility[i] = log_utility(total);
+        /* user.py:81-92: 'log' or 'step' (MAX_UTILITY at or above the required rate, else MIN_UTILITY) */
+        e->utility[i] = e->util_step ? (total >= e->dr_req ? MAX_UTILITY : MIN_UTILITY) : log_utility(total);
     }
 }
 
@@ -270,6 +275,11 @@ static void build_obs_reward(orc_env *e) {
         for (int b = 0; b < M; b++) {
             double conn = e->mask[i * M + b];
             double dr = mx == 0 ? 0 : e->snr[i * M + b] / mx;
+            if (e->obs_maxnorm) {
+                /* MaxNormEnv.get_ue_obs (variants.py:322-330): cap, subtract the required SNR, normalise */
+                double sn = e->snr[i * M + b] < MAX_SNR_THRESHOLD ? e->snr[i * M + b] : MAX_SNR_THRESHOLD;
+                dr = (sn - SNR_THRESHOLD) / (MAX_SNR_THRESHOLD - SNR_THRESHOLD);
+            }
             if (e->kind == KIND_CENTRAL) {
                 e->obs[i * M + b] = conn;
                 e->obs[N * M + i * M + b] = dr;
@@ -357,6 +367,11 @@ orc_env *orc_create(int kind, int n_ue, int n_bs, const double *bs_xy, int width
         mt_seed_int(&e->mrng[i], s);
     }
     return e;
+}
+
+/* per-env switches that leave the step itself untouched: User.util_func / dr_req and the observation normalisation */
+void orc_set_variants(orc_env *e, int util_step, double dr_req, int obs_maxnorm) {
+    e->util_step = util_step; e->dr_req = dr_req; e->obs_maxnorm = obs_maxnorm;
 }
 
 void orc_destroy(orc_env *e) {

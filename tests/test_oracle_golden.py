@@ -55,7 +55,7 @@ def test_python_oracle_bit_identical_to_reference(name):
     check_against_golden(env, cfg, z, exact_floats=exact)
 
 
-@pytest.mark.parametrize('name', golden_names())
+@pytest.mark.parametrize('name', golden_names() + utility_names() + obs_variant_names())
 def test_c_oracle_matches_reference(name):
     cfg, z = load_golden(name)
     env = c_oracle.COracleEnv(**oracle_kwargs(cfg))
