@@ -99,3 +99,32 @@ def test_spaces_contract():
     md = spaces.MultiDiscrete([4, 4, 4])
     assert md.contains(np.array([0, 3, 1])) and not md.contains(np.array([0, 4, 1]))
     assert md.shape == (3,)
+
+
+def test_fixed_point_utility_sums_of_the_fx_agg_experiment():
+    """Arithmetic of the -DDCB_FX_AGG experiment (dcb_step.cu), mirrored in numpy on the utilities of a
+    reference trace: a utility as a 2^-36 fixed-point number, split into a non-negative 20-bit low part and a signed
+    high part, each summed in int32 (native shared-memory atomics on the device) -- the sums stay inside int32 for 512
+    UEs per BS, are independent of the order, and come back within |C_b| * 2^-37 of the exact sum (1e-9 parity bar)."""
+    from helpers import load_golden
+    cfg, z = load_golden('grid10bs_50ue_multi')
+    util = z['step_utility'].astype(np.float64)                  # [T, N], values in [-20, 20]
+    mask = z['step_mask'].astype(bool)                           # [T, N, M]
+    fx = np.rint(util * 2.0 ** 36).astype(np.int64)
+    lo, hi = fx & 0xfffff, fx >> 20
+    assert (lo >= 0).all() and (lo < 2 ** 20).all() and (np.abs(hi) < 2 ** 21).all()
+    assert np.array_equal((hi << 20) + lo, fx)
+    worst = 0.0
+    for t in range(util.shape[0]):
+        for b in range(mask.shape[2]):
+            m = mask[t, :, b]
+            s_lo, s_hi = lo[t, m].astype(np.int32).sum(dtype=np.int32), hi[t, m].astype(np.int32).sum(dtype=np.int32)
+            got = float((np.int64(s_hi) << 20) + np.int64(s_lo)) * 2.0 ** -36
+            perm = np.random.default_rng(t * 16 + b).permutation(int(m.sum()))
+            assert (lo[t, m][perm].sum(), hi[t, m][perm].sum()) == (int(s_lo), int(s_hi))
+            want = float(np.sum(util[t, m]))
+            assert abs(got - want) <= m.sum() * 2.0 ** -37 + 1e-13
+            worst = max(worst, abs(got - want))
+    assert worst < 1e-9
+    # headroom: 512 UEs (the fused kernel's limit) at +-20 on one BS
+    assert 512 * (2 ** 20 - 1) < 2 ** 31 and 512 * (20 * 2 ** 16) < 2 ** 31
