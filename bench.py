@@ -30,6 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+REF_ENV_STEPS = 25      # env steps per worker and bench step of the reference arm
 METRIC = "env steps/sec (batched)"
 UNIT = "env-steps/s"
 
@@ -43,14 +44,23 @@ def grid_layout(n_bs, pitch=100, border=10):
     return width, height, [(border + pitch * (b % cols), border + pitch * (b // cols)) for b in range(n_bs)]
 
 
+def effective_fragment(args):
+    """steps per launch: a rollout fragment, never longer than the timed region or an episode"""
+    return max(1, min(args.fragment, args.steps, args.episode_length))
+
+
 def workload_config(args, n_gpus):
+    N, M, K = args.n_ue, args.n_bs, args.envs
+    obs_floats = K * (N * (4 * M + 1) if args.kind == 'multi' else 2 * N * M + N)
     return {
-        "workload": f"{args.n_ue} UE x {args.n_bs} BS x {args.envs} envs/GPU ({args.envs * n_gpus} total), "
+        "workload": f"{N} UE x {M} BS x {K} envs/GPU ({K * n_gpus} total), "
                     f"{'MultiAgentMobileEnv' if args.kind == 'multi' else 'CentralRelNormEnv'}, {args.sharing} "
                     f"sharing, slow RandomWaypoint, episode_length {args.episode_length}, reset every episode",
-        "kind": args.kind, "n_ue": args.n_ue, "n_bs": args.n_bs, "envs_per_gpu": args.envs,
-        "episode_length": args.episode_length, "fragment_steps": args.fragment, "base_seed": args.seed,
+        "kind": args.kind, "n_ue": N, "n_bs": M, "envs_per_gpu": K,
+        "episode_length": args.episode_length, "fragment_steps": effective_fragment(args), "base_seed": args.seed,
         "actions": "uniform int in [0, M], torch.Generator(seed=0), pre-generated on device",
+        "l2": (f"no flush needed: the {args.steps} timed steps stream {args.steps * obs_floats * 4 / 1e6:.0f} MB of "
+               f"observations + {args.steps * K * N * 4 / 1e6:.0f} MB of actions per GPU through a 126 MB L2; nothing is re-read"),
     }
 
 
@@ -128,10 +138,12 @@ def reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    # each step = every worker's env advancing once: bounded sample of the workload (one env per host core)
-    value, cores, elapsed = run_cpu_port(args, args.steps, min(args.warmup, 20), cores)
-    sample = (f"{cores} envs (one per host core) x {args.steps} steps of the same (N_UE={args.n_ue}, M_BS={args.n_bs}) "
-              f"workload, oracle port of the reference's Python env")
+    # each bench step = every worker's env advancing REF_ENV_STEPS times: a bounded sample of the workload (one env per
+    # host core) that is long enough for a stable number (20 steps -> 500 env steps per core, ~10 s)
+    n_env_steps = args.steps * REF_ENV_STEPS
+    value, cores, elapsed = run_cpu_port(args, n_env_steps, min(args.warmup, 20), cores)
+    sample = (f"{cores} envs (one per host core) x {n_env_steps} env steps ({REF_ENV_STEPS} per bench step) of the same "
+              f"(N_UE={args.n_ue}, M_BS={args.n_bs}) workload, oracle port of the reference's Python env, {elapsed:.1f} s")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -209,6 +221,36 @@ class ClockSampler:
         return out
 
 
+def pin_to_gpu_numa_node(gpu_index):
+    """
+    Run this rank (and allocate its pinned host buffers: first touch) on the NUMA node its GPU hangs off, so that the
+    device -> host copies of the e2e path do not cross the socket interconnect.  Best effort: silently does nothing
+    where sysfs does not say (single-node hosts report -1).
+    """
+    try:
+        out = subprocess.run(['nvidia-smi', '--query-gpu=pci.bus_id', '--format=csv,noheader', '-i', str(gpu_index)],
+                             capture_output=True, text=True, timeout=10).stdout.strip()
+        if len(out) < 12:
+            return None
+        bdf = out[-12:]                                            # 00000000:1B:00.0 -> 0000:1b:00.0
+        bdf = bdf.lower()
+        with open(f'/sys/bus/pci/devices/{bdf}/numa_node') as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f'/sys/devices/system/node/node{node}/cpulist') as f:
+            cpus = set()
+            for part in f.read().strip().split(','):
+                a, _, b = part.partition('-')
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def measured_peak_hbm():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     try:
@@ -246,23 +288,29 @@ def gpu_arm(args):
         # stdout carries exactly one JSON line, but NCCL writes its version banner to the C stdout whenever it pleases
         # (buffered, so it can surface long after communicator creation): file descriptor 1 points at stderr for the
         # whole run and the JSON line goes to the saved descriptor at the end
-        os.environ['NCCL_DEBUG'] = os.environ.get('DCB_NCCL_DEBUG', 'WARN')
         sys.stdout.flush()
         real_stdout = os.dup(1)
         os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=dev)
 
-    K, N, M, L, F = args.envs, args.n_ue, args.n_bs, args.episode_length, args.fragment
+    K, N, M, L = args.envs, args.n_ue, args.n_bs, args.episode_length
+    # steps per launch: a rollout fragment; never longer than the timed region itself
+    F = effective_fragment(args)
     W, H, bs = grid_layout(M)
+    pin_to_gpu_numa_node(local_rank)
     env = BatchedMobileEnv(num_envs=K, n_ue=N, bs_xy=bs, map_wh=(W, H), kind=args.kind, sharing=args.sharing,
                            velocities='slow', seed=args.seed, reward='avg', episode_length=L, device=dev,
                            first_env=rank * K)
-    total = args.warmup + args.steps
+    R = args.reps
+    per_rep = args.warmup + args.steps
+    preroll = args.preroll
+    total = preroll + R * per_rep
+    n_act = min(total, 4 * L + per_rep)                 # the action tensor is reused cyclically (it is input, not state)
     gen = torch.Generator(device=dev)
     gen.manual_seed(0 + rank)
-    actions = torch.randint(0, M + 1, (total, K, N), generator=gen, device=dev, dtype=torch.int32)
+    actions = torch.randint(0, M + 1, (n_act + F, K, N), generator=gen, device=dev, dtype=torch.int32)
 
-    # one fragment plan for warm-up + timed steps: (first step, n steps, reset before?)
+    # fragment plan of `count` steps starting at env time t_env: (offset into the action tensor, n steps, reset before?)
     def plan(first, count, t_env):
         out = []
         s = first
@@ -271,13 +319,16 @@ def gpu_arm(args):
             if reset:
                 t_env = 0
             n = min(F, L - t_env, first + count - s)
-            out.append((s, n, reset))
+            out.append((s % n_act, n, reset))
             s += n
             t_env += n
         return out, t_env
 
-    env.reset()
     bufs = {}
+    policy_spec = None
+    if args.policy:
+        policy_spec = {'3gpp': dict(kind='3gpp'), 'fullcomp': dict(kind='fullcomp'),
+                       'dynamic': dict(kind='dynamic', epsilon=0.5), 'random': dict(kind='random', seed=0)}[args.policy]
 
     def run(fragments, events=None):
         for (s, n, reset) in fragments:
@@ -294,59 +345,87 @@ def gpu_arm(args):
                 e1.record()
                 events.append((e0, e1, n))
 
-    warm, t_env = plan(0, args.warmup, 0)
-    timed, _ = plan(args.warmup, args.steps, t_env)
-    # allocate the per-fragment output buffers outside the timed region (one dry fragment per distinct length)
-    policy_spec = None
-    if args.policy:
-        policy_spec = {'3gpp': dict(kind='3gpp'), 'fullcomp': dict(kind='fullcomp'),
-                       'dynamic': dict(kind='dynamic', epsilon=0.5), 'random': dict(kind='random', seed=0)}[args.policy]
-    for n in sorted({n for _, n, _ in warm + timed}):
+    # the whole schedule up front: pre-roll, then R repetitions of [W warm-up steps (untimed), K timed steps]
+    pos, t_env = 0, 0
+    pre_plan, t_env = plan(pos, preroll, t_env)
+    pos += preroll
+    reps = []
+    for _ in range(R):
+        warm, t_env = plan(pos, args.warmup, t_env)
+        pos += args.warmup
+        timed, t_env = plan(pos, args.steps, t_env)
+        pos += args.steps
+        reps.append((warm, timed))
+    # per-fragment output buffers are allocated outside the timed region (one dry fragment per distinct length)
+    env.reset()
+    for n in sorted({n for _, n, _ in pre_plan + [f for w, t in reps for f in w + t]}):
         bufs[n] = (env.rollout(policy_spec, n, obs=True, info=False, return_actions=False) if args.policy
                    else env.step_many(actions[0:n], obs=True, info=False))
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.wait_started()
     env.reset()
-    run(warm)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
-    launches0 = env.launch_count
-    mark0 = sampler.mark() if sampler else 0
-    events = []
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(dev)
-    t_start.record()
-    run(timed, events)
-    t_end.record()
+    # ---- timed region.  Nothing below synchronises with the host until the last repetition is queued: the pre-roll keeps
+    # the GPU busy while the host runs ahead, so no launch latency sits between the recorded events (a K-step region of
+    # ~0.1 ms would otherwise mostly measure the Python -> ctypes -> cudaLaunchKernel path).
+    mark0 = sampler.mark() if sampler else 0
+    run(pre_plan)
+    rep_events = []
+    for warm, timed in reps:
+        run(warm)
+        events = []
+        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = env.launch_count
+        t_start.record()
+        run(timed, events)
+        t_end.record()
+        rep_events.append((t_start, t_end, events, env.launch_count - l0))
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     clocks = sampler.stop(mark0, sampler.mark()) if sampler else None
-    launches = env.launch_count - launches0
     env.check_errors()
-    elapsed_ms = t_start.elapsed_time(t_end)
-    kern_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in events)
-    kern_steps = sum(n for _, _, n in events)
+    rep_ms = [a.elapsed_time(b) for a, b, _, _ in rep_events]
+    rep_ms_all = list(rep_ms)
     if world > 1:
-        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
+        t = torch.tensor(rep_ms, device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)           # per repetition: the slowest rank
+        rep_ms_all = [float(x) for x in t.tolist()]
+    best = int(np.argmin(rep_ms_all))                       # best of R repetitions
+    elapsed_ms = rep_ms_all[best]
     value = world * K * args.steps / (elapsed_ms * 1e-3)
+    launches = rep_events[best][3]
 
-    # ---- roofline of the dominant kernel (dcb_step_kernel): algorithmic bytes / launch duration, this rank
+    # ---- roofline of the dominant kernel: algorithmic bytes / launch duration (CUDA events around every launch of the
+    # timed repetitions, on the launching stream), this rank
     peak, peak_src = measured_peak_hbm()
     bytes_per_env_step = env.algorithmic_bytes_per_env_step
+
+    def kernel_stats(ev):
+        ms = sum(e0.elapsed_time(e1) for e0, e1, _ in ev)
+        steps = sum(n for _, _, n in ev)
+        return ms, steps, len(ev)
+
+    kern_ms, kern_steps, n_kern = kernel_stats(rep_events[best][2])
+    all_ms, all_steps, all_n = kernel_stats([e for r in rep_events for e in r[2]])
     achieved = (bytes_per_env_step * K * kern_steps) / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+    achieved_all = (bytes_per_env_step * K * all_steps) / (all_ms * 1e-3) / 1e9 if all_ms > 0 else 0.0
+    steps_per_launch = kern_steps / max(n_kern, 1)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "kernel": env.kernel_name,
                 "algorithmic_bytes_per_env_step": bytes_per_env_step,
-                "kernel_share_of_step": kern_ms / elapsed_ms if elapsed_ms > 0 else None,
-                "avg_launch_ms": kern_ms / max(len(events), 1), "env_steps_per_launch": K * F}
+                "kernel_share_of_step": kern_ms / rep_ms[best] if rep_ms[best] > 0 else None,
+                "avg_launch_ms": kern_ms / max(n_kern, 1), "launches_timed": n_kern,
+                "env_steps_per_launch": K * steps_per_launch,
+                "frac_all_reps": achieved_all / peak, "avg_launch_ms_all_reps": all_ms / max(all_n, 1)}
     # measured DRAM bytes of one launch of this workload (ncu --set full capture, profiles/traffic.json), if one exists
+    # for THIS fragment length
     tr = os.path.join(ROOT, 'profiles', 'traffic.json')
-    wl_key = f"{args.kind}:{N}x{M}x{K}:F{F}"
+    wl_key = f"{args.kind}:{N}x{M}x{K}:F{int(round(steps_per_launch))}"
     if os.path.exists(tr):
         try:
             with open(tr) as f:
@@ -357,33 +436,81 @@ def gpu_arm(args):
         except Exception:  # noqa: BLE001
             pass
 
-    # ---- e2e: host actions -> H2D -> step -> D2H obs/reward/lost_conn, every step, through dcb_step_host
-    e2e_steps = min(args.steps, args.e2e_steps)
-    pb = env.pinned_buffers()
-    host_actions = actions[:e2e_steps].cpu().numpy()
+    # ---- e2e: host actions -> H2D -> steps -> D2H obs/reward/lost_conn, through the C-ABI host-buffer calls.
+    # (1) dcb_step_many_host: fragments of `e2e_fragment` steps, device -> host copies overlapped with the next chunk's
+    #     compute, one synchronise per fragment; (2) dcb_step_host: one synchronous round trip per step;
+    # (3) the PCIe ceiling of the same run: a plain cudaMemcpyAsync of one fragment's outputs to the same pinned buffers.
+    e2e_steps = max(args.e2e_steps, 1)
+    FE = max(1, min(args.e2e_fragment, L, e2e_steps))
+    e2e_steps = (e2e_steps + FE - 1) // FE * FE
+    fb = env.pinned_fragment_buffers(FE)
+    host_actions = actions[:min(e2e_steps, n_act)].cpu().numpy()
+
+    def e2e_pass(n_steps):
+        t_e = 0
+        for s in range(0, n_steps, FE):
+            if t_e >= L:
+                env.reset(); t_e = 0
+            np.copyto(fb['actions'].numpy(), host_actions[s % len(host_actions):][:FE])
+            env.step_many_host(fb)
+            t_e += FE
+
     env.reset()
-    for s in range(min(5, e2e_steps)):
-        env.step_host(host_actions[s])
+    e2e_pass(2 * FE)
     env.reset()
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    for s in range(e2e_steps):
-        if s > 0 and s % L == 0:
-            env.reset()
+    e2e_pass(e2e_steps)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    # per-step synchronous variant
+    sync_steps = min(e2e_steps, 100)
+    pb = env.pinned_buffers()
+    env.reset()
+    for s in range(3):
+        env.step_host(host_actions[s])
+    env.reset()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for s in range(sync_steps):
         np.copyto(pb['actions'].numpy(), host_actions[s])
         env.step_host(None)
     torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
+    sync_s = time.perf_counter() - t0
+    # PCIe ceiling: the same output bytes of one fragment, device -> pinned host, nothing else
+    dsrc = {k: torch.empty(fb[k].shape, dtype=fb[k].dtype, device=dev) for k in ('obs', 'reward', 'lost_conn')}
+    for _ in range(2):
+        for k in dsrc:
+            fb[k].copy_(dsrc[k], non_blocking=True)
+    torch.cuda.synchronize(dev)
     if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.barrier()
+    t0 = time.perf_counter()
+    n_copy = max(1, e2e_steps // FE)
+    for _ in range(n_copy):
+        for k in dsrc:
+            fb[k].copy_(dsrc[k], non_blocking=True)
+    torch.cuda.synchronize(dev)
+    copy_s = time.perf_counter() - t0
+    del dsrc
+    if world > 1:
+        t = torch.tensor([e2e_s, sync_s, copy_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+        e2e_s, sync_s, copy_s = [float(x) for x in t.tolist()]
+    d2h_step = int(fb['obs'][0].numel() * 4 + fb['reward'][0].numel() * 4 + fb['lost_conn'][0].numel())
+    ceiling = world * K * n_copy * FE / copy_s
     e2e = {"value": world * K * e2e_steps / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": int(pb['actions'].numel() * 4),
-           "d2h_bytes_per_step": int(pb['obs'].numel() * 4 + pb['reward'].numel() * 4 + pb['lost_conn'].numel()),
-           "steps": e2e_steps, "api": "BatchedMobileEnv.step_host -> dcb_step_host (pinned host buffers)"}
+           "h2d_bytes_per_step": int(fb['actions'][0].numel() * 4), "d2h_bytes_per_step": d2h_step,
+           "steps": e2e_steps, "fragment_steps": FE,
+           "api": "BatchedMobileEnv.step_many_host -> dcb_step_many_host (pinned host buffers, chunked D2H on a copy "
+                  "stream overlapping the next chunk's kernel, one synchronise per fragment)",
+           "pcie_ceiling": {"value": ceiling, "unit": UNIT, "d2h_GBps_per_gpu": d2h_step * n_copy * FE / copy_s / 1e9,
+                            "how": "cudaMemcpyAsync device -> the same pinned buffers, same bytes, no kernel"},
+           "frac_of_pcie_ceiling": (world * K * e2e_steps / e2e_s) / ceiling,
+           "per_step_sync": {"value": world * K * sync_steps / sync_s, "unit": UNIT, "steps": sync_steps,
+                             "api": "BatchedMobileEnv.step_host -> dcb_step_host (one H2D + step + D2H + synchronise per step)"}}
     env.check_errors()
 
     # ---- rollout hand-off (not in the timed region): NCCL all-gather of one fragment's rewards + obs slab
@@ -413,9 +540,10 @@ def gpu_arm(args):
         return
 
     cfg = workload_config(args, world)
-    cfg["l2"] = (f"no flush needed: each fragment streams {bufs[max(bufs)]['obs'].numel() * 4 / 1e6:.0f} MB of "
-                 f"observations + {F * K * N * 4 / 1e6:.0f} MB of actions through a 126 MB L2")
-    cfg["launch_geometry"] = env.launch_geometry
+    run_info = {"launch_geometry": env.launch_geometry,
+                "timing": (f"{preroll} pre-roll steps, then {R} x [{args.warmup} warm-up + {args.steps} timed steps] queued "
+                           f"back to back without a host synchronise (CUDA events on the launching stream); value = best "
+                           f"repetition, per repetition the slowest rank")}
     if args.policy:
         cfg["actions"] = f"on-device scripted policy '{args.policy}' (dcb_rollout), closed loop"
     line = {
@@ -423,6 +551,7 @@ def gpu_arm(args):
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "run": run_info, "rep_ms": rep_ms_all, "gpu_launches_all_reps": int(sum(r[3] for r in rep_events)),
     }
     if extra_native is not None:
         line["cpu_native_port"] = extra_native
@@ -450,7 +579,10 @@ def main():
     ap.add_argument('--episode-length', type=int, default=100)
     ap.add_argument('--fragment', type=int, default=100, help='steps per launch (rollout fragment)')
     ap.add_argument('--seed', type=int, default=1000)
-    ap.add_argument('--e2e-steps', type=int, default=200)
+    ap.add_argument('--e2e-steps', type=int, default=200, help='e2e sample, independent of --steps')
+    ap.add_argument('--e2e-fragment', type=int, default=25, help='steps per dcb_step_many_host call')
+    ap.add_argument('--reps', type=int, default=5, help='repetitions of the timed region (best is reported)')
+    ap.add_argument('--preroll', type=int, default=200, help='untimed steps queued ahead of the first repetition')
     ap.add_argument('--cpu-steps', type=int, default=300, help='steps per core for the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--policy', default=None, choices=['3gpp', 'fullcomp', 'dynamic', 'random'],

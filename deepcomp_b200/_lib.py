@@ -37,6 +37,12 @@ class DcbPolicy(ctypes.Structure):
                 ('seed', ctypes.c_uint64)]
 
 
+class DcbObsVariant(ctypes.Structure):
+    _fields_ = [('kind', ctypes.c_int32), ('dr_mode', ctypes.c_int32), ('dr_cutoff', ctypes.c_double),
+                ('curr_dr_obs', ctypes.c_int32), ('ues_at_bs_obs', ctypes.c_int32), ('dist_obs', ctypes.c_int32),
+                ('next_dist_obs', ctypes.c_int32)]
+
+
 class DcbStateHost(ctypes.Structure):
     _fields_ = [('pos', ctypes.c_void_p), ('mask', ctypes.c_void_p), ('ewma', ctypes.c_void_p),
                 ('movement', ctypes.c_void_p), ('time', ctypes.c_void_p)]
@@ -48,7 +54,7 @@ SYMBOLS = [
     'dcb_step_many', 'dcb_rollout', 'dcb_step_host', 'dcb_check_errors', 'dcb_get_state', 'dcb_set_state', 'dcb_obs_size',
     'dcb_reward_size', 'dcb_algorithmic_bytes_per_env_step', 'dcb_launch_count', 'dcb_launch_geometry',
     'dcb_kernel_name', 'dcb_set_active_ues', 'dcb_get_active_ues', 'dcb_population_event', 'dcb_get_ue_ids', 'dcb_num_joint_actions', 'dcb_test_actions', 'dcb_set_utility',
-    'dcb_set_obs_norm',
+    'dcb_set_obs_norm', 'dcb_step_many_host', 'dcb_step_no_move', 'dcb_set_uniform_movement', 'dcb_set_obs_variant', 'dcb_set_interference',
 ]
 
 DCB_ABI_VERSION = 1
@@ -89,9 +95,12 @@ def load():
     L.dcb_reset.argtypes = [vp, vp, i32, vp]
     L.dcb_observe.argtypes = [vp, ctypes.POINTER(DcbOutputs), vp]
     L.dcb_step.argtypes = [vp, vp, ctypes.POINTER(DcbOutputs), vp]
+    L.dcb_step_no_move.argtypes = [vp, vp, ctypes.POINTER(DcbOutputs), vp]
+    L.dcb_set_uniform_movement.argtypes = [vp, vp, vp]
     L.dcb_step_many.argtypes = [vp, vp, i32, ctypes.POINTER(DcbOutputs), vp]
     L.dcb_rollout.argtypes = [vp, ctypes.POINTER(DcbPolicy), i32, vp, ctypes.POINTER(DcbOutputs), vp]
     L.dcb_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.dcb_step_many_host.argtypes = [vp, vp, i32, vp, vp, vp, i32, vp]
     L.dcb_check_errors.argtypes = [vp, vp]
     L.dcb_get_state.argtypes = [vp, ctypes.POINTER(DcbStateHost)]
     L.dcb_set_state.argtypes = [vp, ctypes.POINTER(DcbStateHost)]
@@ -110,6 +119,8 @@ def load():
     L.dcb_get_ue_ids.argtypes = [vp, vp]
     L.dcb_set_utility.argtypes = [vp, i32, ctypes.c_double]
     L.dcb_set_obs_norm.argtypes = [vp, i32]
+    L.dcb_set_obs_variant.argtypes = [vp, ctypes.POINTER(DcbObsVariant)]
+    L.dcb_set_interference.argtypes = [vp, i32]
     L.dcb_num_joint_actions.argtypes = [vp]
     L.dcb_num_joint_actions.restype = i64
     L.dcb_test_actions.argtypes = [vp, i32, i64, i64, vp, vp]

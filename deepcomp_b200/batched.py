@@ -45,10 +45,13 @@ class BatchedMobileEnv:
     def __init__(self, num_envs, n_ue, bs_xy, map_wh, kind='multi', sharing='mixed', velocities='slow', seed=0,
                  seeds=None, reward='avg', episode_length=100, rand_episodes=False, auto_reset=False, init_pos=None,
                  pause_duration=2, border_buffer=10, device=None, first_env=0, max_ues=None, ue_arrival=None,
-                 new_ue_interval=None, util_func='log', dr_req=1, obs_norm='rel'):
+                 new_ue_interval=None, util_func='log', dr_req=1, obs_norm='rel', uniform_moves=None):
         """
         `obs_norm`: 'rel' = the observation entry 'dr' is snr / max snr (RelNormEnv, variants.py:276-284; default);
         'max' = (min(snr, 7e-6) - 2e-8) / (7e-6 - 2e-8) (MaxNormEnv, variants.py:308-332; CentralMaxNormEnv).
+
+        `uniform_moves`: None, or per UE None (RandomWaypoint) / (move_x, move_y) = UniformMovement (util/movement.py:26-80),
+        each component a number or 'slow' / 'fast' (drawn per reset from the UE's movement generator).
 
         Variable UE population (reference env_config keys of the same names, base.py:80-84, 429-443): `n_ue` UEs at
         reset, `max_ues` slots per env (every per-UE array has max_ues rows; rows of UEs that are not there read as
@@ -148,6 +151,26 @@ class BatchedMobileEnv:
         self.obs_norm = obs_norm
         if obs_norm == 'max':
             check(self._L.dcb_set_obs_norm(self._h, 1))
+        self.uniform_moves = None
+        if uniform_moves is not None and any(u is not None for u in uniform_moves):
+            if self._dynamic or self.num_ue_initial != self.n_ue:
+                raise NotImplementedError("UniformMovement UEs with a variable UE population")
+            if len(uniform_moves) != self.n_ue:
+                raise ValueError("need one uniform_moves entry (None or (move_x, move_y)) per UE")
+            kinds = np.zeros((self.n_ue, 2), dtype=np.int32)
+            vals = np.zeros((self.n_ue, 2), dtype=np.float64)
+            for i, u in enumerate(uniform_moves):
+                if u is None:
+                    continue
+                for c, m in enumerate(u):
+                    if m in ('slow', 'fast'):
+                        kinds[i, c] = 2 if m == 'slow' else 3           # movement.py:49-52: randint(1, 5) / randint(10, 20)
+                    else:
+                        kinds[i, c], vals[i, c] = 1, float(m)
+            check(self._L.dcb_set_uniform_movement(self._h, ctypes.c_void_p(kinds.ctypes.data),
+                                                   ctypes.c_void_p(vals.ctypes.data)))
+            self.uniform_moves = [None if u is None else tuple(u) for u in uniform_moves]
+        self._seq_idx = 0            # SeqMultiAgentMobileEnv.ue_order_idx (multi_agent.py:119; never reset)
 
     # ------------------------------------------------------------------ plumbing
     def close(self):
@@ -347,6 +370,37 @@ class BatchedMobileEnv:
             inf.update(curr_dr=t['curr_dr'], utility=t['utility'], sum_utility=t['sum_utility'])
         return t['obs'], t['reward'], None, inf
 
+    def step_sequential(self, action, info=True, debug=False):
+        """
+        SeqMultiAgentMobileEnv.step (multi_ue/multi_agent.py:149-179) for all K envs: only the CURRENT UE of the round
+        acts (`action`: int32 [K] on the device, or [K, N] of which the current UE's column is used); rates and rewards
+        are updated; after the last UE of the round the UEs move and time advances (a plain step), otherwise nothing
+        moves (dcb_step_no_move).  Returns the observation row and the reward of the NEXT UE: (obs [K, 4M+1],
+        reward [K], None, info) with info['ue_index'] = that UE's slot.
+        """
+        if self.kind != 'multi' or self._dynamic:
+            raise NotImplementedError("sequential stepping is SeqMultiAgentMobileEnv: multi-agent, fixed UE population")
+        K, N = self.num_envs, self.n_ue
+        cur = self._seq_idx
+        a = torch.zeros((K, N), dtype=torch.int32, device=self.device)
+        a[:, cur] = action if action.dim() == 1 else action[:, cur]
+        o, t = self._outputs(None, info=info or debug, debug=debug)
+        last_of_round = cur + 1 >= self.active_ues
+        if last_of_round:
+            self._t += 1
+            check(self._L.dcb_step(self._h, ctypes.c_void_p(a.data_ptr()), ctypes.byref(o), self._stream()))
+        else:
+            check(self._L.dcb_step_no_move(self._h, ctypes.c_void_p(a.data_ptr()), ctypes.byref(o), self._stream()))
+        self._seq_idx = 0 if last_of_round else cur + 1
+        nxt = self._seq_idx
+        if debug:
+            t['ue_index'] = nxt
+            return t
+        inf = {'lost_conn': t['lost_conn'], 'ue_index': nxt, 'moved': last_of_round}
+        if info:
+            inf.update(curr_dr=t['curr_dr'], utility=t['utility'], sum_utility=t['sum_utility'])
+        return t['obs'][:, nxt], t['reward'][:, nxt], None, inf
+
     def step_many(self, actions, obs=True, info=False, out=None):
         """
         T consecutive steps in one launch.  actions: int32 [T, K, N].  Returns dict of [T, ...] tensors
@@ -459,6 +513,31 @@ class BatchedMobileEnv:
                                     ctypes.c_void_p(pb['obs'].data_ptr()), ctypes.c_void_p(pb['reward'].data_ptr()),
                                     ctypes.c_void_p(pb['lost_conn'].data_ptr()), self._stream()))
         return pb['obs'], pb['reward'], None, {'lost_conn': pb['lost_conn']}
+
+    def pinned_fragment_buffers(self, T):
+        """Pinned host buffers for step_many_host: actions int32 [T,K,N], obs [T,K,...], reward [T,K,...], lost_conn."""
+        K, N = self.num_envs, self.n_ue
+        return dict(
+            actions=torch.empty((T, K, N), dtype=torch.int32).pin_memory(),
+            obs=torch.empty((T, K) + self.obs_shape, dtype=torch.float32).pin_memory(),
+            reward=torch.empty((T, K) + self.reward_shape, dtype=torch.float32).pin_memory(),
+            lost_conn=torch.empty((T, K, N), dtype=torch.uint8).pin_memory())
+
+    def step_many_host(self, bufs, T=None, chunk_steps=0):
+        """
+        T steps through HOST memory in one C-ABI call (dcb_step_many_host): `bufs` = pinned_fragment_buffers(T) with
+        bufs['actions'] filled in; the steps run in chunks whose device -> host copies overlap the next chunk's compute,
+        one synchronise at the end.  Returns (obs, reward, None, {'lost_conn'}) as [T, ...] host tensors.
+        """
+        if self._dynamic:
+            raise NotImplementedError("step_many_host with a variable UE population (use step_many with device tensors)")
+        T = int(bufs['actions'].shape[0]) if T is None else int(T)
+        self._t += T
+        check(self._L.dcb_step_many_host(self._h, ctypes.c_void_p(bufs['actions'].data_ptr()), T,
+                                         ctypes.c_void_p(bufs['obs'].data_ptr()),
+                                         ctypes.c_void_p(bufs['reward'].data_ptr()),
+                                         ctypes.c_void_p(bufs['lost_conn'].data_ptr()), int(chunk_steps), self._stream()))
+        return bufs['obs'][:T], bufs['reward'][:T], None, {'lost_conn': bufs['lost_conn'][:T]}
 
     # ------------------------------------------------------------------ state snapshots
     def get_state(self):

@@ -63,6 +63,31 @@ double threshold_d2(double c1, double c2) {
     return lo;
 }
 
+// Largest squared distance d2 with fl(sqrt(d2)) <= vel (movement.py:142-145 as one compare; see snap_threshold in
+// dcb_device.cuh -- sqrt is correctly rounded on both sides, so host and device agree bit for bit)
+double host_snap_threshold(double vel) {
+    if (!(vel > 0.0)) return 0.0;
+    double c = vel * vel;
+    while (sqrt(c) > vel) c = nextafter(c, 0.0);
+    while (sqrt(nextafter(c, INFINITY)) <= vel) c = nextafter(c, INFINITY);
+    return c;
+}
+
+// MathTables of dcb_math.cuh (inv, l2c, ex2, pwm, pwe: 5 x 16 doubles) followed by the snap thresholds of the drawn
+// velocities 0..15, built with the host libm once per handle
+void host_math_tables(double h, double c0, double *out) {
+    for (int j = 0; j < 16; j++) {
+        const double c = 1.0 + ((double)j + 0.5) / 16.0;
+        const double inv = 1.0 / c;
+        out[j] = inv;
+        out[16 + j] = -log2(inv);
+        out[32 + j] = exp2((double)j / 16.0);
+        out[48 + j] = pow(inv, h);
+        out[64 + j] = exp2(c0 - h * (double)j);
+        out[80 + j] = host_snap_threshold((double)j);
+    }
+}
+
 }  // namespace
 
 struct dcb_env {
@@ -74,7 +99,7 @@ struct dcb_env {
     bool wide = false;   // one CTA per env (dcb_wide.cu) instead of the fused kernel (dcb_step.cu)
     int64_t launches = 0;
     // device allocations
-    double *d_bs_xy = nullptr, *d_vel = nullptr, *d_init_xy = nullptr;
+    double *d_bs_xy = nullptr, *d_vel = nullptr, *d_init_xy = nullptr, *d_tabs = nullptr;
     int *d_sharing = nullptr;
     long long *d_seeds = nullptr;
     double2 *d_pos = nullptr, *d_init_pos = nullptr;
@@ -93,6 +118,10 @@ struct dcb_env {
     double *d_vel_u = nullptr;                           // velocity spec per env and slot (slots change owners)
     int32_t *d_env_ids = nullptr;
     int env_ids_cap = 0;
+    int32_t *d_uni_kind = nullptr;                       // UniformMovement (dcb_set_uniform_movement)
+    double *d_uni_val = nullptr;
+    std::vector<int32_t> h_uni_kind;
+    std::vector<double> h_uni_val;
     // scripted policies (dcb_rollout)
     unsigned long long *d_cluster = nullptr;
     int32_t *d_fixed = nullptr;
@@ -101,6 +130,14 @@ struct dcb_env {
     int32_t *d_h_actions = nullptr;
     float *d_h_obs = nullptr, *d_h_reward = nullptr;
     uint8_t *d_h_lost = nullptr;
+    // dcb_step_many_host: actions of the fragment, two chunk-sized staging sets, copy stream, events
+    int32_t *d_hm_actions = nullptr;
+    size_t hm_actions_cap = 0;
+    float *d_hm_obs[2] = {nullptr, nullptr}, *d_hm_reward[2] = {nullptr, nullptr};
+    uint8_t *d_hm_lost[2] = {nullptr, nullptr};
+    int hm_chunk_cap = 0;
+    cudaStream_t hm_copy_stream = nullptr;
+    cudaEvent_t hm_done[2] = {nullptr, nullptr}, hm_copied[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -145,9 +182,31 @@ int choose_envs_per_cta(int K, int N, int M, int kind, int num_sms, size_t smem_
     return best_e;
 }
 
+// Move a handle to the one-CTA-per-env kernel (observation variants and the interference extension live there only)
+int force_wide_kernel(dcb_env *env) {
+    if (env->wide) return DCB_OK;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, env->device));
+    const DevParams &p = env->p;
+    const WideLayout W = dcb_wide_layout(p.N, p.M, p.LC);
+    if ((size_t)W.total > prop.sharedMemPerBlockOptin)
+        return fail(DCB_ERR_UNSUPPORTED, "one env of %d UEs x %d BS needs %d B of shared memory on the wide kernel", p.N, p.M,
+                    W.total);
+    int threads = (p.N + 31) / 32 * 32;
+    if (threads < 128) threads = 128;
+    CU(dcb_wide_set_smem_limit(prop.sharedMemPerBlockOptin));
+    env->wide = true;
+    env->threads = threads;
+    env->grid = p.K;
+    env->smem = (size_t)W.total;
+    env->p.E = 1;
+    return DCB_OK;
+}
+
 int launch_step(dcb_env *env, const int32_t *d_actions, int T, const dcb_outputs *out, cudaStream_t s,
-                const PolicyParams *pol = nullptr, int32_t *d_actions_out = nullptr) {
+                const PolicyParams *pol = nullptr, int32_t *d_actions_out = nullptr, int flags = 0) {
     StepArgs a;
+    a.flags = flags;
     memset(&a.pol, 0, sizeof(a.pol));
     if (pol) a.pol = *pol;
     a.actions_out = d_actions_out;
@@ -177,6 +236,7 @@ const char *dcb_last_error(void) { return g_err; }
 
 int64_t dcb_obs_size(const dcb_env *env) {
     const int64_t N = env->p.N, M = env->p.M;
+    if (env->p.obs_var) return env->p.var_obs_size;
     return env->p.kind == DCB_KIND_CENTRAL ? 2 * N * M + N : N * (4 * M + 1);
 }
 
@@ -184,9 +244,9 @@ int64_t dcb_reward_size(const dcb_env *env) { return env->p.kind == DCB_KIND_CEN
 
 int64_t dcb_algorithmic_bytes_per_env_step(const dcb_env *env) {
     // state R+W per UE 56 + 8W (W = ceil(M/32) mask words), actions 4, obs f32, reward f32
+    // = N (60 + 8W) + 4 obs_size + 4 reward_size, which also covers the observation variants
     const int64_t N = env->p.N, M = env->p.M, W = (M + 31) / 32;
-    if (env->p.kind == DCB_KIND_CENTRAL) return N * (60 + 8 * W + 8 * M + 4) + 4;
-    return N * (64 + 8 * W + 16 * M + 4);
+    return N * (60 + 8 * W) + 4 * dcb_obs_size(env) + 4 * dcb_reward_size(env);
 }
 
 int64_t dcb_launch_count(const dcb_env *env) { return env->launches; }
@@ -206,7 +266,7 @@ int dcb_launch_geometry(const dcb_env *env, int32_t *envs_per_cta, int32_t *thre
 void dcb_destroy(dcb_env *env) {
     if (!env) return;
     DeviceGuard g(env->device);
-    cudaFree(env->d_bs_xy); cudaFree(env->d_vel); cudaFree(env->d_init_xy); cudaFree(env->d_sharing);
+    cudaFree(env->d_bs_xy); cudaFree(env->d_vel); cudaFree(env->d_init_xy); cudaFree(env->d_sharing); cudaFree(env->d_tabs);
     cudaFree(env->d_seeds); cudaFree(env->d_pos); cudaFree(env->d_init_pos); cudaFree(env->d_mv);
     cudaFree(env->d_mask); cudaFree(env->d_ewma); cudaFree(env->d_time); cudaFree(env->d_err);
     cudaFree(env->d_table); cudaFree(env->d_pos_skip); cudaFree(env->d_mv_skip); cudaFree(env->d_env_ids);
@@ -214,6 +274,14 @@ void dcb_destroy(dcb_env *env) {
     cudaFree(env->d_uid); cudaFree(env->d_map_draws); cudaFree(env->d_glob_draws);
     cudaFree(env->d_ue_seed); cudaFree(env->d_ue_pos_used); cudaFree(env->d_ue_mv_used); cudaFree(env->d_vel_u);
     cudaFree(env->d_h_actions); cudaFree(env->d_h_obs); cudaFree(env->d_h_reward); cudaFree(env->d_h_lost);
+    cudaFree(env->d_uni_kind); cudaFree(env->d_uni_val);
+    cudaFree(env->d_hm_actions);
+    for (int j = 0; j < 2; j++) {
+        cudaFree(env->d_hm_obs[j]); cudaFree(env->d_hm_reward[j]); cudaFree(env->d_hm_lost[j]);
+        if (env->hm_done[j]) cudaEventDestroy(env->hm_done[j]);
+        if (env->hm_copied[j]) cudaEventDestroy(env->hm_copied[j]);
+    }
+    if (env->hm_copy_stream) cudaStreamDestroy(env->hm_copy_stream);
     delete env;
 }
 
@@ -345,6 +413,7 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     ALLOC(env->d_seeds, K); ALLOC(env->d_pos, KN); ALLOC(env->d_init_pos, KN); ALLOC(env->d_mv, KN);
     ALLOC(env->d_mask, KN); ALLOC(env->d_ewma, KN); ALLOC(env->d_time, K); ALLOC(env->d_err, 1);
     ALLOC(env->d_table, KN * D);
+    ALLOC(env->d_tabs, 96);
     ALLOC(env->d_uid, KN); ALLOC(env->d_map_draws, K); ALLOC(env->d_glob_draws, K);
     if (cfg->rand_episodes) { ALLOC(env->d_pos_skip, K); ALLOC(env->d_mv_skip, KN); }
 #undef ALLOC
@@ -366,6 +435,7 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     DevParams &p = env->p;
     memset(&p, 0, sizeof(p));
     p.K = K; p.N = N; p.NA = N; p.M = M; p.kind = cfg->kind; p.reward = cfg->reward;
+    p.map_w = (double)cfg->map_width; p.map_h = (double)cfg->map_height;
     p.episode_length = cfg->episode_length; p.auto_reset = cfg->auto_reset; p.pause_duration = cfg->pause_duration;
     p.D = D; p.E = E; p.S = S; p.CS = CS; p.LC = LC;
     p.has_maxcap = has_maxcap; p.has_propfair = has_pf;
@@ -379,6 +449,12 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     // (1 + r)^(-h) = sum_k binom(-h, k) r^k
     p.pw[0] = 1.0;
     for (int k = 1; k < 10; k++) p.pw[k] = p.pw[k - 1] * (-p.snr_h - (double)(k - 1)) / (double)k;
+    {
+        double tabs[96];
+        host_math_tables(p.snr_h, p.snr_c0, tabs);
+        CU(cudaMemcpy(env->d_tabs, tabs, sizeof(tabs), cudaMemcpyHostToDevice));
+    }
+    p.tabs = env->d_tabs;
     p.bs_xy = env->d_bs_xy; p.sharing = env->d_sharing; p.vel_spec = env->d_vel;
     p.pos = env->d_pos; p.mv = env->d_mv; p.mask = env->d_mask; p.ewma = env->d_ewma; p.time = env->d_time;
     p.init_pos = env->d_init_pos; p.table = env->d_table; p.err = env->d_err;
@@ -394,7 +470,7 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     // initial tables + state (as after the first reset)
     GenArgs g;
     g.K = K; g.N = N; g.D = D; g.W = cfg->map_width; g.H = cfg->map_height; g.border_buffer = cfg->border_buffer;
-    g.seeds = env->d_seeds; g.vel_spec = env->d_vel; g.init_xy = env->d_init_xy;
+    g.seeds = env->d_seeds; g.vel_spec = env->d_vel; g.init_xy = env->d_init_xy; g.uni_kind = env->d_uni_kind;
     g.pos_skip = nullptr; g.mv_skip = nullptr; g.env_ids = nullptr; g.n_ids = 0;
     g.ue_seed = nullptr; g.ue_pos_skip = nullptr;
     g.init_pos = env->d_init_pos; g.table = env->d_table;
@@ -450,7 +526,7 @@ int dcb_reset(dcb_env *env, const int32_t *host_env_ids, int32_t n, void *stream
         GenArgs g;
         g.K = p.K; g.N = p.N; g.D = p.D; g.W = env->cfg.map_width; g.H = env->cfg.map_height;
         g.border_buffer = env->cfg.border_buffer;
-        g.seeds = env->d_seeds; g.vel_spec = env->d_vel; g.init_xy = env->d_init_xy;
+        g.seeds = env->d_seeds; g.vel_spec = env->d_vel; g.init_xy = env->d_init_xy; g.uni_kind = env->d_uni_kind;
         g.pos_skip = nullptr; g.mv_skip = env->d_ue_mv_used; g.env_ids = nullptr; g.n_ids = 0;
         g.ue_seed = env->d_ue_seed; g.ue_pos_skip = env->d_ue_pos_used;
         g.init_pos = env->d_init_pos; g.table = env->d_table;
@@ -468,7 +544,7 @@ int dcb_reset(dcb_env *env, const int32_t *host_env_ids, int32_t n, void *stream
         GenArgs g;
         g.K = p.K; g.N = p.N; g.D = p.D; g.W = env->cfg.map_width; g.H = env->cfg.map_height;
         g.border_buffer = env->cfg.border_buffer;
-        g.seeds = env->d_seeds; g.vel_spec = env->d_vel; g.init_xy = env->d_init_xy;
+        g.seeds = env->d_seeds; g.vel_spec = env->d_vel; g.init_xy = env->d_init_xy; g.uni_kind = env->d_uni_kind;
         g.pos_skip = env->d_pos_skip; g.mv_skip = env->d_mv_skip; g.env_ids = d_ids; g.n_ids = n;
         g.ue_seed = nullptr; g.ue_pos_skip = nullptr;
         g.init_pos = env->d_init_pos; g.table = env->d_table;
@@ -513,6 +589,65 @@ int dcb_set_obs_norm(dcb_env *env, int32_t kind) {
     return DCB_OK;
 }
 
+int dcb_set_obs_variant(dcb_env *env, const dcb_obs_variant *v) {
+    if (!env || !v) return fail(DCB_ERR_INVALID_ARG, "null argument");
+    DevParams &p = env->p;
+    if (v->kind == DCB_OBSVAR_NONE) {
+        p.obs_var = 0;
+        return DCB_OK;
+    }
+    if (v->kind != DCB_OBSVAR_NORMDR && v->kind != DCB_OBSVAR_DATARATE)
+        return fail(DCB_ERR_INVALID_ARG, "unknown observation variant %d", v->kind);
+    if (p.kind != DCB_KIND_CENTRAL)    // the reference has CentralNormDrEnv / CentralDrEnv (central.py:75-140) only
+        return fail(DCB_ERR_UNSUPPORTED, "the data-rate observation classes exist for the central env only");
+    if (p.obs_maxnorm) return fail(DCB_ERR_INVALID_ARG, "MaxNorm and a data-rate observation are different classes");
+    bool tot = true, ues = false, dist = false, next = false;
+    if (v->kind == DCB_OBSVAR_DATARATE) {
+        if (v->dr_mode < DCB_DR_AUTO || v->dr_mode > DCB_DR_PLAIN) return fail(DCB_ERR_INVALID_ARG, "bad dr_mode");
+        // variants.py:75-79
+        if (v->curr_dr_obs && v->dr_mode != DCB_DR_AUTO)
+            return fail(DCB_ERR_INVALID_ARG, "Enable all processing to add extra obs (curr_dr_obs needs dr_cutoff 'auto')");
+        if (v->next_dist_obs && !v->dist_obs)
+            return fail(DCB_ERR_INVALID_ARG, "Also enable 'dist_obs' when using 'next_dist_obs'");
+        if (v->dr_mode != DCB_DR_AUTO && !(p.dr_req < v->dr_cutoff))      // variants.py:87-88
+            return fail(DCB_ERR_INVALID_ARG, "dr_cutoff should be higher than max required dr. by UEs");
+        if (v->next_dist_obs && p.uni_kind)
+            return fail(DCB_ERR_UNSUPPORTED, "next_dist_obs needs RandomWaypoint UEs (step_towards_waypoint)");
+        tot = v->curr_dr_obs != 0; ues = v->ues_at_bs_obs != 0; dist = v->dist_obs != 0; next = v->next_dist_obs != 0;
+    }
+    DeviceGuard guard(env->device);
+    const int rc = force_wide_kernel(env);
+    if (rc != DCB_OK) return rc;
+    // alphabetical key order (gym.spaces.Dict sorts; central.py:33-44): connected, dist, dr, dr_total, next_dist, ues_at_bs
+    const int NM = p.N * p.M;
+    int o = 0;
+    p.vo_conn = o; o += NM;
+    p.vo_dist = dist ? o : -1; o += dist ? NM : 0;
+    p.vo_dr = o; o += NM;
+    p.vo_tot = tot ? o : -1; o += tot ? p.N : 0;
+    p.vo_next = next ? o : -1; o += next ? NM : 0;
+    p.vo_ues = ues ? o : -1; o += ues ? NM : 0;
+    p.var_obs_size = o;
+    p.obs_var = v->kind;
+    p.dr_mode = v->dr_mode;
+    p.dr_cutoff = v->dr_cutoff;
+    p.map_diag = sqrt((double)env->cfg.map_width * env->cfg.map_width + (double)env->cfg.map_height * env->cfg.map_height);
+    return DCB_OK;
+}
+
+int dcb_set_interference(dcb_env *env, int32_t on) {
+    if (!env) return fail(DCB_ERR_INVALID_ARG, "null handle");
+    if (!on) {
+        env->p.interference = 0;
+        return DCB_OK;
+    }
+    DeviceGuard guard(env->device);
+    const int rc = force_wide_kernel(env);
+    if (rc != DCB_OK) return rc;
+    env->p.interference = 1;
+    return DCB_OK;
+}
+
 int64_t dcb_num_joint_actions(const dcb_env *env) {
     if (!env) return 0;
     double n = pow((double)(env->p.M + 1), (double)env->p.NA);
@@ -524,6 +659,7 @@ int dcb_test_actions(dcb_env *env, int32_t env_index, int64_t first, int64_t cou
     const DevParams &p = env->p;
     if (env_index < 0 || env_index >= p.K) return fail(DCB_ERR_INVALID_ARG, "env %d outside [0, %d)", env_index, p.K);
     if (p.NA > 16) return fail(DCB_ERR_UNSUPPORTED, "brute force over %d UEs (at most 16)", p.NA);
+    if (p.interference) return fail(DCB_ERR_UNSUPPORTED, "brute force with the interference extension");
     const int64_t total = dcb_num_joint_actions(env);
     if (total < 0) return fail(DCB_ERR_UNSUPPORTED, "(%d + 1)^%d joint actions do not fit 63 bits", p.M, p.NA);
     if (first < 0 || count < 0 || first + count > total)
@@ -558,6 +694,7 @@ int dcb_population_event(dcb_env *env, int32_t n_add, int32_t n_remove, int32_t 
         return fail(DCB_ERR_INVALID_ARG, "%d UEs would exceed max_ues = %d (base.py:84)", p.NA - n_remove + n_add, p.N);
     if (env->cfg.rand_episodes)
         return fail(DCB_ERR_UNSUPPORTED, "variable UE population needs rand_episodes = 0 (streams restart at reset)");
+    if (env->p.uni_kind) return fail(DCB_ERR_UNSUPPORTED, "variable UE population with UniformMovement UEs");
     DeviceGuard guard(env->device);
     cudaStream_t s = (cudaStream_t)stream;
     if (!env->pop_used) {
@@ -600,6 +737,62 @@ int dcb_step(dcb_env *env, const int32_t *d_actions, const dcb_outputs *out, voi
     return launch_step(env, d_actions, 1, out, (cudaStream_t)stream);
 }
 
+int dcb_step_no_move(dcb_env *env, const int32_t *d_actions, const dcb_outputs *out, void *stream) {
+    if (!env || !d_actions) return fail(DCB_ERR_INVALID_ARG, "null argument");
+    DeviceGuard guard(env->device);
+    return launch_step(env, d_actions, 1, out, (cudaStream_t)stream, nullptr, nullptr, DCB_STEPF_NO_MOVE);
+}
+
+int dcb_set_uniform_movement(dcb_env *env, const int32_t *host_kind, const double *host_value) {
+    if (!env || !host_kind || !host_value) return fail(DCB_ERR_INVALID_ARG, "null argument");
+    const DevParams &p = env->p;
+    if (env->pop_used || p.NA < p.N)
+        return fail(DCB_ERR_UNSUPPORTED, "UniformMovement UEs with a variable UE population");
+    bool any = false;
+    for (int i = 0; i < p.N; i++) {
+        const int kx = host_kind[2 * i], ky = host_kind[2 * i + 1];
+        if (kx < 0 || kx > 3 || ky < 0 || ky > 3) return fail(DCB_ERR_INVALID_ARG, "uniform movement kind of UE %d", i);
+        if ((kx == 0) != (ky == 0))
+            return fail(DCB_ERR_INVALID_ARG, "UE %d: both components or none (UniformMovement has move_x and move_y)", i);
+        if ((kx == 1 && !isfinite(host_value[2 * i])) || (ky == 1 && !isfinite(host_value[2 * i + 1])))
+            return fail(DCB_ERR_INVALID_ARG, "UE %d: move_x / move_y must be finite numbers", i);
+        any |= kx != 0;
+    }
+    DeviceGuard guard(env->device);
+    CU(cudaDeviceSynchronize());
+    if (!env->d_uni_kind) {
+        CU(cudaMalloc((void **)&env->d_uni_kind, sizeof(int32_t) * 2 * p.N));
+        CU(cudaMalloc((void **)&env->d_uni_val, sizeof(double) * 2 * p.N));
+    }
+    CU(cudaMemcpy(env->d_uni_kind, host_kind, sizeof(int32_t) * 2 * p.N, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(env->d_uni_val, host_value, sizeof(double) * 2 * p.N, cudaMemcpyHostToDevice));
+    env->h_uni_kind.assign(host_kind, host_kind + 2 * p.N);
+    env->h_uni_val.assign(host_value, host_value + 2 * p.N);
+    env->p.uni_kind = any ? env->d_uni_kind : nullptr;
+    env->p.uni_val = any ? env->d_uni_val : nullptr;
+    // the draw sequences of those UEs' movement generators change: regenerate the tables and start over (as dcb_create)
+    if (env->cfg.rand_episodes) {
+        CU(cudaMemset(env->d_pos_skip, 0, sizeof(uint32_t) * p.K));
+        CU(cudaMemset(env->d_mv_skip, 0, sizeof(uint32_t) * (size_t)p.K * p.N));
+    }
+    GenArgs g;
+    g.K = p.K; g.N = p.N; g.D = p.D; g.W = env->cfg.map_width; g.H = env->cfg.map_height;
+    g.border_buffer = env->cfg.border_buffer;
+    g.seeds = env->d_seeds; g.vel_spec = env->d_vel; g.init_xy = env->d_init_xy; g.uni_kind = env->d_uni_kind;
+    g.pos_skip = nullptr; g.mv_skip = nullptr; g.env_ids = nullptr; g.n_ids = 0;
+    g.ue_seed = nullptr; g.ue_pos_skip = nullptr;
+    g.init_pos = env->d_init_pos; g.table = env->d_table;
+    ResetArgs r;
+    r.K = p.K; r.N = p.N; r.D = p.D; r.env_ids = nullptr; r.n_ids = 0; r.init_pos = env->d_init_pos;
+    r.table = env->d_table; r.pos = env->d_pos; r.mv = env->d_mv; r.mask = env->d_mask; r.ewma = env->d_ewma;
+    r.time = env->d_time; r.pos_skip = nullptr;
+    CU(dcb_launch_generate(g, 0));
+    CU(dcb_launch_reset(r, 0));
+    CU(cudaDeviceSynchronize());
+    env->launches += 2;
+    return DCB_OK;
+}
+
 int dcb_step_many(dcb_env *env, const int32_t *d_actions, int32_t T, const dcb_outputs *out, void *stream) {
     if (!env || !d_actions) return fail(DCB_ERR_INVALID_ARG, "null argument");
     if (T < 1) return fail(DCB_ERR_INVALID_ARG, "T must be >= 1");
@@ -613,6 +806,8 @@ int dcb_rollout(dcb_env *env, const dcb_policy *policy, int32_t T, int32_t *d_ac
     if (T < 1) return fail(DCB_ERR_INVALID_ARG, "T must be >= 1");
     if (policy->kind < DCB_POLICY_3GPP || policy->kind > DCB_POLICY_RANDOM)
         return fail(DCB_ERR_INVALID_ARG, "unknown policy kind %d", policy->kind);
+    if (env->p.obs_var || env->p.interference)
+        return fail(DCB_ERR_UNSUPPORTED, "the scripted device policies read the RelNorm observation of the SNR model");
     if (env->p.obs_maxnorm)   // the agents pick by 'dr' (heuristics.py:19-38,44-65,86-108); MaxNorm caps it at 7e-6
         return fail(DCB_ERR_UNSUPPORTED, "the scripted device policies read the RelNorm observation; this handle is MaxNorm");
     DeviceGuard guard(env->device);
@@ -684,6 +879,83 @@ int dcb_step_host(dcb_env *env, const int32_t *h_actions, float *h_obs, float *h
     return DCB_OK;
 }
 
+int dcb_step_many_host(dcb_env *env, const int32_t *h_actions, int32_t T, float *h_obs, float *h_reward,
+                       uint8_t *h_lost_conn, int32_t chunk_steps, void *stream) {
+    if (!env || !h_actions) return fail(DCB_ERR_INVALID_ARG, "null argument");
+    if (T < 1) return fail(DCB_ERR_INVALID_ARG, "T must be >= 1");
+    DeviceGuard guard(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const DevParams &p = env->p;
+    const size_t KN = (size_t)p.K * p.N;
+    const size_t n_obs = (size_t)p.K * dcb_obs_size(env), n_rew = (size_t)p.K * dcb_reward_size(env);
+    const size_t step_bytes = n_obs * 4 + n_rew * 4 + KN;
+    int C = chunk_steps > 0 ? chunk_steps : (int)((16u << 20) / step_bytes);
+    if (C < 1) C = 1;
+    if (C > T) C = T;
+    if (!env->hm_copy_stream) {
+        CU(cudaStreamCreateWithFlags(&env->hm_copy_stream, cudaStreamNonBlocking));
+        for (int j = 0; j < 2; j++) {
+            CU(cudaEventCreateWithFlags(&env->hm_done[j], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&env->hm_copied[j], cudaEventDisableTiming));
+        }
+    }
+    if ((size_t)T * KN > env->hm_actions_cap) {
+        CU(cudaStreamSynchronize(s));
+        cudaFree(env->d_hm_actions);
+        env->d_hm_actions = nullptr;
+        env->hm_actions_cap = 0;
+        CU(cudaMalloc((void **)&env->d_hm_actions, sizeof(int32_t) * (size_t)T * KN));
+        env->hm_actions_cap = (size_t)T * KN;
+    }
+    if (C > env->hm_chunk_cap) {
+        CU(cudaStreamSynchronize(s));
+        CU(cudaStreamSynchronize(env->hm_copy_stream));
+        for (int j = 0; j < 2; j++) {
+            cudaFree(env->d_hm_obs[j]); cudaFree(env->d_hm_reward[j]); cudaFree(env->d_hm_lost[j]);
+            env->d_hm_obs[j] = nullptr; env->d_hm_reward[j] = nullptr; env->d_hm_lost[j] = nullptr;
+        }
+        env->hm_chunk_cap = 0;
+        for (int j = 0; j < 2; j++) {
+            CU(cudaMalloc((void **)&env->d_hm_obs[j], sizeof(float) * n_obs * C));
+            CU(cudaMalloc((void **)&env->d_hm_reward[j], sizeof(float) * n_rew * C));
+            CU(cudaMalloc((void **)&env->d_hm_lost[j], KN * C));
+        }
+        env->hm_chunk_cap = C;
+    }
+    CU(cudaMemcpyAsync(env->d_hm_actions, h_actions, sizeof(int32_t) * (size_t)T * KN, cudaMemcpyHostToDevice, s));
+    int chunk = 0;
+    for (int t0 = 0; t0 < T; t0 += C, chunk++) {
+        const int n = T - t0 < C ? T - t0 : C;
+        const int j = chunk & 1;
+        // staging set j is free once the copies of chunk - 2 have left it
+        if (chunk >= 2) CU(cudaStreamWaitEvent(s, env->hm_copied[j], 0));
+        dcb_outputs o;
+        memset(&o, 0, sizeof(o));
+        if (h_obs) { o.obs = env->d_hm_obs[j]; o.obs_stride = (int64_t)n_obs; }
+        if (h_reward) { o.reward = env->d_hm_reward[j]; o.reward_stride = (int64_t)n_rew; }
+        if (h_lost_conn) { o.lost_conn = env->d_hm_lost[j]; o.lost_conn_stride = (int64_t)KN; }
+        const int rc = launch_step(env, env->d_hm_actions + (size_t)t0 * KN, n, &o, s);
+        if (rc != DCB_OK) return rc;
+        CU(cudaEventRecord(env->hm_done[j], s));
+        CU(cudaStreamWaitEvent(env->hm_copy_stream, env->hm_done[j], 0));
+        if (h_obs)
+            CU(cudaMemcpyAsync(h_obs + (size_t)t0 * n_obs, env->d_hm_obs[j], sizeof(float) * n_obs * n,
+                               cudaMemcpyDeviceToHost, env->hm_copy_stream));
+        if (h_reward)
+            CU(cudaMemcpyAsync(h_reward + (size_t)t0 * n_rew, env->d_hm_reward[j], sizeof(float) * n_rew * n,
+                               cudaMemcpyDeviceToHost, env->hm_copy_stream));
+        if (h_lost_conn)
+            CU(cudaMemcpyAsync(h_lost_conn + (size_t)t0 * KN, env->d_hm_lost[j], KN * n, cudaMemcpyDeviceToHost,
+                               env->hm_copy_stream));
+        CU(cudaEventRecord(env->hm_copied[j], env->hm_copy_stream));
+    }
+    // the caller's stream is ordered behind the copies too (a later launch must not overwrite the staging sets early)
+    CU(cudaStreamWaitEvent(s, env->hm_copied[(chunk - 1) & 1], 0));
+    if (chunk >= 2) CU(cudaStreamWaitEvent(s, env->hm_copied[chunk & 1], 0));
+    CU(cudaStreamSynchronize(s));
+    return DCB_OK;
+}
+
 int dcb_check_errors(dcb_env *env, void *stream) {
     if (!env) return fail(DCB_ERR_INVALID_ARG, "null handle");
     DeviceGuard guard(env->device);
@@ -722,6 +994,15 @@ int dcb_get_state(dcb_env *env, dcb_state_host *st) {
         for (size_t u = 0; u < KN; u++) {
             const double vf = env->d_vel_u ? vel[u] : vel[u % p.N];
             double *m = st->movement + 5 * u;
+            if (env->p.uni_kind && env->h_uni_kind[2 * (u % p.N)]) {
+                // UniformMovement: move_x, move_y (current sign), -1, 0, 0
+                const size_t i = u % p.N;
+                double mx = env->h_uni_kind[2 * i] == 1 ? env->h_uni_val[2 * i] : (double)(mv[u].x & 0xffffu);
+                double my = env->h_uni_kind[2 * i + 1] == 1 ? env->h_uni_val[2 * i + 1] : (double)(mv[u].x >> 16);
+                if (mv[u].y & 0x8000u) { mx = -mx; my = -my; }
+                m[0] = mx; m[1] = my; m[2] = -1.0; m[3] = 0.0; m[4] = 0.0;
+                continue;
+            }
             m[0] = vf >= 0.0 ? vf : (double)(mv[u].y & 0xffu);
             m[1] = (double)(mv[u].x & 0xffffu);
             m[2] = (double)(mv[u].x >> 16);
@@ -748,6 +1029,7 @@ int dcb_set_state(dcb_env *env, const dcb_state_host *st) {
         CU(cudaMemcpy(mv.data(), env->d_mv, sizeof(uint2) * KN, cudaMemcpyDeviceToHost));
         for (size_t u = 0; u < KN; u++) {
             const double *m = st->movement + 5 * u;
+            if (env->p.uni_kind && env->h_uni_kind[2 * (u % p.N)]) continue;      // UniformMovement UEs keep their word
             const unsigned wx = (unsigned)m[1], wy = (unsigned)m[2];
             if (wx >= 16384u || wy >= 16384u) return fail(DCB_ERR_INVALID_ARG, "waypoint outside the map");
             const unsigned v = (unsigned)m[0] & 0xffu;

@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) dcb_brute_kernel(BruteArgs a) {
     unsigned long long *mask0 = reinterpret_cast<unsigned long long *>(ewma0 + N);   // [N] current links
     unsigned long long *inr = mask0 + N;                                          // [N] base stations in range
     int *share = reinterpret_cast<int *>(inr + N);                                // [M]
-    dcb_math_init(tab, threadIdx.x, p.snr_h, p.snr_c0);
+    dcb_math_init(tab, nullptr, threadIdx.x, blockDim.x, p.tabs);
     __syncthreads();
     const long long base = (long long)a.env * p.N;
     for (int i = threadIdx.x; i < N; i += blockDim.x) {

@@ -196,6 +196,24 @@ __device__ __forceinline__ void prefetch_table_entry(uint32_t *slot, const uint3
 }
 __device__ __forceinline__ void prefetch_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// UniformMovement.step (movement.py:66-80) for one UE: constant (move_x, move_y) per step; when the next point would not
+// be strictly inside the map (Point.within: a point on the border is outside) BOTH components flip sign and the step is
+// taken with the flipped vector, without a second check.  kx, ky: component kinds (DevParams::uni_kind), vx, vy: the fixed
+// numbers; drawn magnitudes and the flip bit live in the packed movement word.
+__device__ __forceinline__ void ue_move_uniform(const DevParams &p, int kx, int ky, double vx, double vy, double &x,
+                                                double &y, unsigned wxy, unsigned &vpt) {
+    double mx = kx == 1 ? vx : (double)(wxy & 0xffffu);
+    double my = ky == 1 ? vy : (double)(wxy >> 16);
+    if (vpt & 0x8000u) { mx = -mx; my = -my; }
+    double nx = x + mx, ny = y + my;
+    if (!(0.0 < nx && nx < p.map_w && 0.0 < ny && ny < p.map_h)) {
+        vpt ^= 0x8000u;
+        mx = -mx; my = -my;
+        nx = x + mx; ny = y + my;
+    }
+    x = nx; y = ny;
+}
+
 template <bool PREFETCH>
 __device__ __forceinline__ void ue_move(const DevParams &p, long long u, double vfix, double vfix_thr, const double *vthr,
                                         double &x, double &y, unsigned &wxy, unsigned &vpt, uint32_t *next_slot) {

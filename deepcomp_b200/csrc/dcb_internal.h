@@ -26,6 +26,8 @@
 //   vel    : drawn velocity 1..10 for 'slow'/'fast' UEs (movement.py:112-115); unused for fixed-velocity UEs
 //   pause  : bit 7 = RandomWaypoint.pausing, bits 0..6 = curr_pause (movement.py:101-102)
 //   tidx   : next unread entry of this UE's waypoint table
+// UniformMovement UEs reuse the word: wx, wy = the drawn |move_x|, |move_y| ('slow' / 'fast' components), bit 7 of pause
+// = "both components have flipped sign" (movement.py:76-78), tidx stays 1
 // Packed waypoint-table entry (4 bytes): wx | wy << 14 | vel << 28
 
 struct DevParams {
@@ -40,13 +42,28 @@ struct DevParams {
     int util_step;       // 0: log utility (utility.py:36-54); 1: step utility (utility.py:23-33) at dr_req
     double dr_req;       // User.dr_req (user.py:17-30)
     int obs_maxnorm;     // observation 'dr': 0 = snr / max snr (variants.py:276-284); 1 = MaxNormEnv (variants.py:308-332)
+    // data-rate observation classes (dcb_set_obs_variant; wide kernel, central layout): segment offsets in floats within an
+    // env's observation, -1 = key absent; order = alphabetical keys (central.py:31-57)
+    int obs_var;         // dcb_obs_variant_kind
+    int dr_mode;         // dcb_dr_mode
+    double dr_cutoff;
+    double map_diag;     // Map.diagonal (map.py:26)
+    int vo_conn, vo_dist, vo_dr, vo_tot, vo_next, vo_ues;
+    int var_obs_size;    // floats per env of the variant observation
+    int interference;    // extension: SINR instead of SNR (dcb_set_interference)
     int LC;              // wide kernel: link slots per UE (bound on the base stations any point can be in range of)
     double thr_d2;       // largest squared distance that is still in range (snr > 2e-8, station.py:224)
     double c1, c2;       // Okumura-Hata constants (station.py:112-114)
     double snr_c0, snr_h; // snr(d) = 2^(snr_c0 - snr_h * log2(d^2)): the same model folded for the fast path
     double pw[10];       // binomial series of (1 + r)^(-snr_h): coefficients of r^0 .. r^9 (dcb_snr_inrange)
+    const double *tabs;  // [80 + 16] MathTables (dcb_math.cuh) + snap thresholds of the drawn velocities 0..15, host-built
     const double *bs_xy; // [M][2]
     const int *sharing;  // [M]
+    // UniformMovement UEs (util/movement.py:26-80): per slot and component 0 = none (RandomWaypoint), 1 = fixed number
+    // (uni_val), 2 = 'slow' randint(1, 5), 3 = 'fast' randint(10, 20) drawn per reset (table entry 0); NULL = no such UE
+    const int32_t *uni_kind; // [N][2]
+    const double *uni_val;   // [N][2]
+    double map_w, map_h;     // Map.width / height (map.py:20-21): UniformMovement bounces off the border
     const double *vel_spec;  // [N] velocity spec per slot (the same in every env) ...
     const double *vel_u;     // ... or [K*N] per env and slot once UEs have changed slots (variable population), else NULL
     // state slabs, flat UE index u = k*N + i
@@ -65,9 +82,6 @@ struct SmemLayout {
     int off_tab, off_stage, off_x, off_fac_pre, off_fac_post, off_hx, off_hy,
         off_hmask, off_hutil, off_hrb, off_hdr, off_hlost, off_bsx, off_bsy, off_vel,
         off_arg_pre, off_arg_post, off_bits, off_share, off_links, off_vthr, off_wagg, off_snext;
-#ifdef DCB_FX_AGG
-    int off_fxagg;   // experiment: per-(env, BS) fixed-point utility sums, [3][E*M][2] int32 (lo, hi)
-#endif
     int nbits;   // words per bitset
     int links_per_warp;   // capacity (entries) of one physics warp's link list
     int wagg_pairs;       // (env, BS) pairs one observer warp aggregates for itself: the envs its 32 rows touch x M
@@ -120,9 +134,6 @@ __host__ __device__ inline SmemLayout dcb_smem_layout(int kind, int N, int M, in
     L.wagg_pairs = ((31 / N + 2) * M + 1) & ~1;
     L.wagg_stride = align16(L.wagg_pairs * 28);
     L.off_wagg = o;     o += ((EN + 31) / 32) * L.wagg_stride;
-#ifdef DCB_FX_AGG
-    L.off_fxagg = o;    o += align16(3 * EM * 2 * 4);
-#endif
     L.total = o;
     return L;
 }
@@ -131,7 +142,8 @@ __host__ __device__ inline SmemLayout dcb_smem_layout(int kind, int N, int M, in
 struct WideLayout {
     int off_tab, off_bsxy, off_share, off_vthr, off_xs, off_sx, off_sy, off_smask, off_su, off_srb, off_sew, off_smv,
         off_bits, off_fac,
-        off_arg, off_cnt, off_usum, off_umin, off_fues, off_futil, off_env;
+        off_arg, off_cnt, off_usum, off_umin, off_fues, off_futil, off_env,
+        off_sdr, off_ssum, off_lsum, off_lbest, off_lcnt;   // general instance: curr_dr / interference sum per UE, raw link aggregates per BS
     int total;
 };
 
@@ -160,6 +172,11 @@ __host__ __device__ inline WideLayout dcb_wide_layout(int N, int M, int LC) {
     L.off_cnt = o;   o += align16(M * 4);
     L.off_fues = o;  o += align16(M * 4);
     L.off_futil = o; o += align16(M * 4);
+    L.off_sdr = o;   o += align16(N * 8);
+    L.off_ssum = o;  o += align16(N * 8);
+    L.off_lsum = o;  o += align16(M * 8);
+    L.off_lbest = o; o += align16(M * 8);
+    L.off_lcnt = o;  o += align16(M * 4);
     L.total = o;
     return L;
 }
@@ -176,6 +193,10 @@ struct PolicyParams {
     unsigned long long seed;           // RandomAgent
 };
 
+// StepArgs::flags
+#define DCB_STEPF_NO_MOVE 1   // apply actions, rates, rewards, observation -- no movement, link drop, EWMA update or time
+                              // increment (SeqMultiAgentMobileEnv between the UEs of one round, multi_agent.py:149-179)
+
 struct StepArgs {
     DevParams p;
     SmemLayout L;
@@ -184,6 +205,7 @@ struct StepArgs {
     int T;                   // 0 = observe only
     int threads;             // CTA size of the launch
     PolicyParams pol;
+    int flags;               // DCB_STEPF_*
     int32_t *actions_out;    // [T][K][N] actions the policy took, or NULL
     dcb_outputs out;
 };
@@ -192,6 +214,7 @@ struct GenArgs {
     int K, N, D, W, H, border_buffer;
     const long long *seeds;     // [K]
     const double *vel_spec;     // [N]
+    const int32_t *uni_kind;    // [N][2] UniformMovement components (DevParams::uni_kind) or NULL
     const double *init_xy;      // [N][2]
     const uint32_t *pos_skip;   // [K] reset_pos() calls already consumed per env (rand_episodes) or NULL
     const uint32_t *mv_skip;    // [K*N] movement.reset() calls already consumed per UE or NULL
@@ -251,6 +274,12 @@ struct ReseedArgs {
     uint32_t *ue_pos_used;      // [K*N] ... reset_pos() draws since that seeding
     uint32_t *ue_mv_used;       // [K*N] ... movement.reset() draws since that seeding
 };
+// The general (PAD) template instances carry everything that is not the measured fixed-population RelNorm path: padding
+// slots, observation variants, UniformMovement, ...
+__host__ inline bool dcb_step_needs_general(const DevParams &p, int flags) {
+    return p.NA < p.N || p.obs_maxnorm || p.uni_kind || (flags & DCB_STEPF_NO_MOVE);
+}
+
 cudaError_t dcb_launch_pop_reseed(const ReseedArgs &a, cudaStream_t s);
 cudaError_t dcb_launch_pop_seed_init(long long *ue_seed, uint32_t *pos_used, uint32_t *mv_used, const long long *seeds,
                                      int K, int N, cudaStream_t s);

@@ -3,7 +3,7 @@
 //
 // Table-driven log2 / exp2 with 16-entry tables: a 16 x 8-byte table is exactly one row of the 32 shared-memory
 // banks, so ANY per-lane index pattern is conflict-free (equal indices broadcast).  The tables are built once per
-// CTA with the libm routines (dcb_math_init) and live in shared memory.
+// handle with the host libm (dcb_create) and live in shared memory (dcb_math_init copies them in).
 //
 //   log2(x)   x = 2^e * m, j = top 4 mantissa bits, c_j = 1 + (j + 1/2)/16, r = m * INV[j] - 1, |r| <= 1/32
 //             log2(x) = e + L2C[j] + log2(1 + r),   L2C[j] = -log2(INV[j]) with INV[j] = fl(1/c_j)   (consistent)
@@ -27,16 +27,15 @@ struct MathTables {
     double pwe[16];   // 2^(c0 - h e)        for binary exponents e = 0..15     (dcb_snr_inrange)
 };
 
-// call from the first 16 threads of the CTA, then __syncthreads(); h, c0: snr(d) = 2^(c0 - h log2(d^2))
-__device__ __forceinline__ void dcb_math_init(MathTables *t, int tid, double h, double c0) {
-    if (tid < 16) {
-        const double c = 1.0 + ((double)tid + 0.5) / 16.0;
-        const double inv = 1.0 / c;
-        t->inv[tid] = inv;
-        t->l2c[tid] = -log2(inv);
-        t->ex2[tid] = exp2((double)tid / 16.0);
-        t->pwm[tid] = pow(inv, h);
-        t->pwe[tid] = exp2(c0 - h * (double)tid);
+// The tables are built once per handle on the host (dcb_create: host libm, dcb_host_math_tables) and copied into shared
+// memory by the first 80 threads of the CTA, then __syncthreads(): no libm call in any kernel prologue.
+#define DCB_MATH_TABLE_DOUBLES 80
+#define DCB_VTHR_DOUBLES 16      // snap thresholds of the drawn velocities 0..15 follow the math tables in the host block
+__device__ __forceinline__ void dcb_math_init(MathTables *t, double *vthr, int tid, int nthreads, const double *src) {
+    for (int j = tid; j < DCB_MATH_TABLE_DOUBLES + DCB_VTHR_DOUBLES; j += nthreads) {
+        const double v = src[j];
+        if (j < DCB_MATH_TABLE_DOUBLES) reinterpret_cast<double *>(t)[j] = v;
+        else if (vthr) vthr[j - DCB_MATH_TABLE_DOUBLES] = v;
     }
 }
 

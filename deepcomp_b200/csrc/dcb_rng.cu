@@ -108,7 +108,15 @@ __global__ void __launch_bounds__(128) dcb_generate_kernel(GenArgs a) {
     const double vs = a.vel_spec[i];
     const uint32_t skip = a.mv_skip ? a.mv_skip[u] : 0u;
     uint32_t *row = a.table + u * a.D;
+    const int ukx = a.uni_kind ? a.uni_kind[2 * i] : 0, uky = a.uni_kind ? a.uni_kind[2 * i + 1] : 0;
     for (uint32_t e = 0; e < skip + (uint32_t)a.D; e++) {
+        if (ukx) {
+            // UniformMovement.reset (movement.py:47-64): move_x, then move_y; 'slow' = randint(1, 5), 'fast' = randint(10, 20)
+            const int mx = ukx == 2 ? mt_randint(g, 1, 5) : (ukx == 3 ? mt_randint(g, 10, 20) : 0);
+            const int my = uky == 2 ? mt_randint(g, 1, 5) : (uky == 3 ? mt_randint(g, 10, 20) : 0);
+            if (e >= skip) row[e - skip] = (uint32_t)mx | ((uint32_t)my << 14);
+            continue;
+        }
         int v = 0;
         if (vs == DCB_VELOCITY_SLOW) v = mt_randint(g, 1, 3);
         else if (vs == DCB_VELOCITY_FAST) v = mt_randint(g, 5, 10);

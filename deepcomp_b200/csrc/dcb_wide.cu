@@ -41,11 +41,21 @@ struct WideSmem {
     double *usum, *umin;   // [M]
     float *f_ues, *f_util; // [M]
     double *env_red;   // [2] per-env reward / utility sum
+    // general instance (EXT): data-rate observation classes and the interference extension
+    double *sdr;       // [N] curr_dr after the move (user.py:64-69)
+    double *ssum;      // [N] sum over all BS of the SNR at the UE's position (interference extension)
+    double *lsum, *lbest;  // [M] raw link aggregates of the current masks: sum of link values, largest unshared rate
+    int *lcnt;         // [M] ... number of linked UEs
 };
+
+// Signal quality of one UE-BS pair: SNR (station.py:122-127) or, with the interference extension, SINR =
+// snr_b / (1 + sum_{b' != b} snr_b') with `tot` = the sum over ALL base stations at the UE's position
+__device__ __forceinline__ double pair_sinr(double snr, double tot) { return snr / (1.0 + (tot - snr)); }
 
 __device__ __forceinline__ int rank_of(u64 mask, int b) { return __popcll(mask & (((u64)1 << b) - 1)); }
 
 // per-BS reduction over the linked UEs: count, sum of link values, first arg-max -> sharing factor (one warp per BS)
+template <bool EXT>
 __device__ __forceinline__ void wide_reduce_links(const WideSmem &S, int N, int M, int NW, int LC, bool want_arg,
                                                   int warp, int lane, int nwarps) {
     for (int b = warp; b < M; b += nwarps) {
@@ -75,8 +85,36 @@ __device__ __forceinline__ void wide_reduce_links(const WideSmem &S, int N, int 
         if (lane == 0) {
             S.fac[b] = share_factor(S.share[b], c, s);
             S.arg[b] = a0;
+            if (EXT) { S.lcnt[b] = c; S.lsum[b] = s; S.lbest[b] = best; }
         }
     }
+}
+
+// Interference extension: sum over all base stations of the SNR at every UE's current position (S.sx, S.sy) -- one warp
+// per UE, lanes over the base stations (two passes cover M <= 64), folded with warp shuffles.
+__device__ __forceinline__ void wide_interference_sums(const WideSmem &S, const DevParams &p, int NA, int M, int warp,
+                                                       int lane, int nwarps) {
+    const int b0 = lane, b1 = lane + 32;
+    const bool ok0 = b0 < M, ok1 = b1 < M;
+    const double2 bs0 = ok0 ? S.bsxy[b0] : make_double2(0.0, 0.0), bs1 = ok1 ? S.bsxy[b1] : make_double2(0.0, 0.0);
+    for (int r = warp; r < NA; r += nwarps) {
+        const double rx = S.sx[r], ry = S.sy[r];
+        double v = ok0 ? snr_of_d2(p, S.tab, dist2(bs0, rx, ry)) : 0.0;
+        if (ok1) v += snr_of_d2(p, S.tab, dist2(bs1, rx, ry));
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) S.ssum[r] = v;
+    }
+}
+
+// The position one step closer to the waypoint (RandomWaypoint.step_towards_waypoint, movement.py:132-156), the UE itself
+// is not moved: for the 'next_dist' observation (variants.py:166-169)
+__device__ __forceinline__ void step_towards_waypoint(double x, double y, double wx, double wy, double vel, double &nx,
+                                                      double &ny) {
+    const double vx = wx - x, vy = wy - y;
+    if (sqrt(vx * vx + vy * vy) <= vel) { nx = wx; ny = wy; return; }
+    const double norm = sqrt(fma(vy, vy, vx * vx));
+    nx = x + vel * (vx / norm);
+    ny = y + vel * (vy / norm);
 }
 
 // per-BS utility aggregates for the observation / multi-agent reward (one warp per BS)
@@ -128,7 +166,9 @@ __device__ __forceinline__ double warp_min(double v) {
 }
 
 // PAD: the envs have padding slots (NA < N, variable UE population)
-template <bool PAD>
+// EXT: the general instance -- data-rate observation classes (dcb_set_obs_variant), the interference extension
+// (dcb_set_interference), UniformMovement UEs, the no-move launch mode; the plain instances compile without them
+template <bool PAD, bool EXT>
 __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const DevParams &p = a.p;
@@ -157,7 +197,13 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
     S.f_ues = reinterpret_cast<float *>(smem + L.off_fues);
     S.f_util = reinterpret_cast<float *>(smem + L.off_futil);
     S.env_red = reinterpret_cast<double *>(smem + L.off_env);
+    S.sdr = reinterpret_cast<double *>(smem + L.off_sdr);
+    S.ssum = reinterpret_cast<double *>(smem + L.off_ssum);
+    S.lsum = reinterpret_cast<double *>(smem + L.off_lsum);
+    S.lbest = reinterpret_cast<double *>(smem + L.off_lbest);
+    S.lcnt = reinterpret_cast<int *>(smem + L.off_lcnt);
     const MathTables *tab = S.tab;
+    const bool interf = EXT && p.interference;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = a.threads >> 5;   // a.threads == blockDim.x
     const int k = blockIdx.x;
@@ -167,18 +213,18 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
     const long long u = (long long)k * N + i;
     const bool central = p.kind == DCB_KIND_CENTRAL;
     const int OW = obs_width(p.kind, M);
-    const size_t per_env = central ? (size_t)(2 * N * M + N) : (size_t)N * OW;
+    const size_t per_env = (EXT && p.obs_var) ? (size_t)p.var_obs_size
+                                              : (central ? (size_t)(2 * N * M + N) : (size_t)N * OW);
     const int T = a.T;
     const int n_iter = T > 0 ? T : 1;
     const float hr = (float)(p.snr_h - 1.5);
 
-    dcb_math_init(S.tab, tid, p.snr_h, p.snr_c0);
+    dcb_math_init(S.tab, S.vthr, tid, blockDim.x, p.tabs);
     for (int b = tid; b < M; b += blockDim.x) {
         S.bsxy[b] = make_double2(p.bs_xy[2 * b], p.bs_xy[2 * b + 1]);
         S.share[b] = p.sharing[b];
     }
     for (int j = tid; j < M * NW; j += blockDim.x) S.bits[j] = 0u;
-    if (tid >= 32 && tid < 48) S.vthr[tid - 32] = snap_threshold((double)(tid - 32));
 
     // ---- per-UE state: global slabs -> shared memory for the launch.  A UE's thread pulls it into registers for the
     // per-UE phases of a step only, so the row-parallel phase (most of the instructions) has the registers to itself
@@ -192,8 +238,30 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
     }
     const double vfix = valid ? (p.vel_u ? p.vel_u[u] : p.vel_spec[i]) : 0.0;
     const double vfix_thr = vfix >= 0.0 ? snap_threshold(vfix) : 0.0;
+    // UniformMovement UEs (movement.py:26-80) and the no-move launch mode (DCB_STEPF_NO_MOVE)
+    int ukx = 0, uky = 0;
+    double uvx = 0.0, uvy = 0.0;
+    if (EXT && p.uni_kind && valid) {
+        ukx = p.uni_kind[2 * i]; uky = p.uni_kind[2 * i + 1];
+        uvx = p.uni_val[2 * i]; uvy = p.uni_val[2 * i + 1];
+    }
+    const bool no_move = EXT && (a.flags & DCB_STEPF_NO_MOVE) != 0;
     double *Xrow = S.Xs + (size_t)i * LC;
     __syncthreads();
+    if (interf) {
+        // the SNR sums at the positions the launch starts from; every step refreshes them after its move
+        wide_interference_sums(S, p, NA, M, warp, lane, nwarps);
+        __syncthreads();
+    }
+    // in range (can_connect, station.py:222-226) and unshared rate (station.py:129-138) of one pair, SNR or SINR based
+    auto in_range = [&](double d2, double tot) -> bool {
+        if (interf) return pair_sinr(snr_of_d2(p, tab, d2), tot) > DCB_SNR_THRESHOLD;
+        return d2 <= p.thr_d2;
+    };
+    auto unshared_rate = [&](double d2, double tot) -> double {
+        if (interf) return DCB_BW * dcb_log2_1p(tab, pair_sinr(snr_of_d2(p, tab, d2), tot));
+        return rate_of_d2(p, tab, d2);
+    };
 
     for (int step = 0; step < n_iter; step++) {
         const bool last = step == n_iter - 1;
@@ -215,6 +283,12 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                     mask = 0; ewma = 0.0;
                 }
                 tk = 0;
+                if (interf) {               // the SNR sums follow the UEs to their initial positions (CTA-uniform branch)
+                    if (valid) { S.sx[i] = x; S.sy[i] = y; }
+                    __syncthreads();
+                    wide_interference_sums(S, p, NA, M, warp, lane, nwarps);
+                    __syncthreads();
+                }
             }
             if (valid) {
                 // ---- apply_ue_actions (base.py:247-282) -> User.connect_to_bs(disconnect=True) (user.py:190-229)
@@ -231,7 +305,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                     const int b = act - 1;
                     const u64 bit = (u64)1 << b;
                     if (mask & bit) mask &= ~bit;
-                    else if (dist2(S.bsxy[b], x, y) <= p.thr_d2) mask |= bit;   // can_connect, station.py:222-226
+                    else if (in_range(dist2(S.bsxy[b], x, y), interf ? S.ssum[i] : 0.0)) mask |= bit;   // can_connect, station.py:222-226
                 }
                 if (__popcll(mask) > LC) {          // cannot happen on a reachable state (LC bounds the BS in range)
                     atomicOr(p.err, DCB_ERRBIT_LINKS);
@@ -240,15 +314,16 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                 // ---- link values at the pre-move position (station.py:129-150)
                 const double iee = dcb_rcp(ewma + DCB_EPSILON);
                 int slot = 0;
+                const double tot0 = interf ? S.ssum[i] : 0.0;
                 for (u64 m = mask; m; m &= m - 1, slot++) {
                     const int b = __ffsll((long long)m) - 1;
-                    Xrow[slot] = link_value(S.share[b], rate_of_d2(p, tab, dist2(S.bsxy[b], x, y)), iee);
+                    Xrow[slot] = link_value(S.share[b], unshared_rate(dist2(S.bsxy[b], x, y), tot0), iee);
                     atomicOr(&S.bits[b * NW + (i >> 5)], 1u << (i & 31));
                 }
                 S.smask[i] = mask;
             }
             __syncthreads();
-            wide_reduce_links(S, N, M, NW, LC, p.has_maxcap, warp, lane, nwarps);
+            wide_reduce_links<EXT>(S, N, M, NW, LC, p.has_maxcap, warp, lane, nwarps);
             __syncthreads();
             for (int j = tid; j < M * NW; j += blockDim.x) S.bits[j] = 0u;
             if (valid) {
@@ -265,27 +340,41 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                 }
                 rb = ue_utility(p, tab, dr0) * (1.0 / DCB_MAX_UTILITY);
                 // ---- User.move (user.py:159-173), check_bs_connection (user.py:175-188), update_ewma_dr (user.py:148-157)
-                ue_move<false>(p, u, vfix, vfix_thr, S.vthr, x, y, wxy, vpt, nullptr);
+                if (!no_move) {
+                    if (ukx) ue_move_uniform(p, ukx, uky, uvx, uvy, x, y, wxy, vpt);
+                    else ue_move<false>(p, u, vfix, vfix_thr, S.vthr, x, y, wxy, vpt, nullptr);
+                }
+            }
+            if (interf && !no_move) {
+                // the SINR at the new positions needs the SNR sums there before any link can be judged
+                if (valid) { S.sx[i] = x; S.sy[i] = y; }
+                __syncthreads();
+                wide_interference_sums(S, p, NA, M, warp, lane, nwarps);
+                __syncthreads();
+            }
+            if (valid && !no_move) {
+                const double tot1 = interf ? S.ssum[i] : 0.0;
                 double keep = 0.0;
-                slot = 0;
+                int slot = 0;
                 for (u64 m = mask; m; m &= m - 1, slot++) {
                     const int b = __ffsll((long long)m) - 1;
-                    if (dist2(S.bsxy[b], x, y) <= p.thr_d2) keep += Xrow[slot];
+                    if (in_range(dist2(S.bsxy[b], x, y), tot1)) keep += Xrow[slot];
                     else { mask &= ~((u64)1 << b); lost++; }
                 }
                 ewma = 0.9 * keep + (1 - 0.9) * ewma;
             }
-            tk += 1;                                                                   // base.py:454
+            if (!no_move) tk += 1;                                                     // base.py:454
             __syncthreads();      // bits cleared, slots of the pre-move pass consumed
         }
         // ---- link values at the new position for update_ue_drs_rewards(update_only=True) (base.py:451)
         if (valid) {
             const double iee = dcb_rcp(ewma + DCB_EPSILON);
+            const double tot1 = interf ? S.ssum[i] : 0.0;
             int slot = 0;
             for (u64 m = mask; m; m &= m - 1, slot++) {
                 const int b = __ffsll((long long)m) - 1;
                 if (slot < LC) {
-                    Xrow[slot] = link_value(S.share[b], rate_of_d2(p, tab, dist2(S.bsxy[b], x, y)), iee);
+                    Xrow[slot] = link_value(S.share[b], unshared_rate(dist2(S.bsxy[b], x, y), tot1), iee);
                     atomicOr(&S.bits[b * NW + (i >> 5)], 1u << (i & 31));
                 } else {
                     atomicOr(p.err, DCB_ERRBIT_LINKS);     // observe-only launch on an injected state with too many links
@@ -298,7 +387,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
             S.smv[i] = make_uint2(wxy, vpt);
         }
         __syncthreads();
-        wide_reduce_links(S, N, M, NW, LC, p.has_maxcap, warp, lane, nwarps);
+        wide_reduce_links<EXT>(S, N, M, NW, LC, p.has_maxcap, warp, lane, nwarps);
         __syncthreads();
         if (valid) {
             // ---- post-move rates -> utility (user.py:76-92)
@@ -313,6 +402,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
             util = ue_utility(p, tab, dr);
             S.su[i] = util;
             S.srb[i] = rb;
+            if (EXT) S.sdr[i] = dr;
             // ---- per-UE info outputs (base.py:383-411)
             if (a.out.curr_dr) a.out.curr_dr[(size_t)step * a.out.curr_dr_stride + u] = (float)dr;
             if (a.out.utility) a.out.utility[(size_t)step * a.out.utility_stride + u] = (float)util;
@@ -375,6 +465,21 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
             if (PAD && r >= NA) {
                 // ---- padding slot (no UE there: max_ues > num_ue): zeros, as central.py:46-55 pads the observation
                 const long long ru = kN + r;
+                if (EXT && p.obs_var) {
+                    const int offs[5] = {p.vo_conn, p.vo_dist, p.vo_dr, p.vo_next, p.vo_ues};
+                    double *dbg_env = (last && a.out.dbg_obs) ? a.out.dbg_obs + (size_t)k * per_env : nullptr;
+                    for (int sgm = 0; sgm < 5; sgm++) {
+                        if (offs[sgm] < 0) continue;
+                        for (int b = lane; b < M; b += 32) {
+                            if (obs_env) obs_env[(size_t)offs[sgm] + (size_t)r * M + b] = 0.0f;
+                            if (dbg_env) dbg_env[(size_t)offs[sgm] + (size_t)r * M + b] = 0.0;
+                        }
+                    }
+                    if (lane == 0 && p.vo_tot >= 0) {
+                        if (obs_env) obs_env[(size_t)p.vo_tot + r] = 0.0f;
+                        if (dbg_env) dbg_env[(size_t)p.vo_tot + r] = 0.0;
+                    }
+                } else
                 if (obs_lane) {
                     float *o = obs_lane + r * row_stride_f;
                     if (central) {
@@ -396,7 +501,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                     if (last && a.out.dbg_curr_dr) a.out.dbg_curr_dr[ru] = 0.0;
                     if (last && a.out.dbg_utility) a.out.dbg_utility[ru] = 0.0;
                 }
-                if (last && a.out.dbg_obs) {
+                if (last && a.out.dbg_obs && !(EXT && p.obs_var)) {
                     if (central) {
                         double *drow = a.out.dbg_obs + (size_t)k * (2 * N * M + N);
                         if (ok0) { drow[r * M + b0] = 0.0; drow[N * M + r * M + b0] = 0.0; }
@@ -417,6 +522,154 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
             const u64 rmask = S.smask[r];
             const double d20 = ok0 ? dist2(bs0, rx, ry) : CUDART_INF;
             const double d21 = ok1 ? dist2(bs1, rx, ry) : CUDART_INF;
+            if (EXT && (p.obs_var || interf)) {
+                // ---- general instance: SINR-based quantities (interference extension) and / or the data-rate observation
+                // classes (NormDrMobileEnv / DatarateMobileEnv.get_ue_obs, variants.py:127-250; central layout)
+                const double tot = interf ? S.ssum[r] : 0.0;
+                const double q0 = ok0 ? (interf ? pair_sinr(snr_of_d2(p, tab, d20), tot) : snr_of_d2(p, tab, d20)) : 0.0;
+                const double q1 = ok1 ? (interf ? pair_sinr(snr_of_d2(p, tab, d21), tot) : snr_of_d2(p, tab, d21)) : 0.0;
+                const bool r0in = ok0 && (interf ? q0 > DCB_SNR_THRESHOLD : d20 <= p.thr_d2);
+                const bool r1in = ok1 && (interf ? q1 > DCB_SNR_THRESHOLD : d21 <= p.thr_d2);
+                const unsigned in0 = __ballot_sync(0xffffffffu, r0in), in1 = __ballot_sync(0xffffffffu, r1in);
+                const bool cb0 = ((unsigned)rmask >> lane) & 1u, cb1 = ((unsigned)(rmask >> 32) >> lane) & 1u;
+                const double un = rutil * (1.0 / DCB_MAX_UTILITY);
+                const long long ru = kN + r;
+                double *dbg_env = (last && a.out.dbg_obs) ? a.out.dbg_obs + (size_t)k * per_env : nullptr;
+                if (p.obs_var) {
+                    const double ew = S.sew[r], ee = ew + DCB_EPSILON, iee = dcb_rcp(ee);
+                    const double req = p.dr_req;
+                    double nx = rx, ny = ry;
+                    if (p.vo_next >= 0) {
+                        const uint2 mv = S.smv[r];
+                        const double vf = p.vel_u ? p.vel_u[ru] : p.vel_spec[r];
+                        step_towards_waypoint(rx, ry, (double)(mv.x & 0xffffu), (double)(mv.x >> 16),
+                                              vf >= 0.0 ? vf : (double)(mv.y & 0xffu), nx, ny);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const int b = q ? b1 : b0;
+                        if (b >= M) continue;
+                        const double d2 = q ? d21 : d20, qual = q ? q1 : q0;
+                        const bool inr = q ? r1in : r0in, conn = q ? cb1 : cb0;
+                        // Basestation.data_rate (station.py:204-220): the shared rate this UE gets, or would get if it were
+                        // counted in (data_rate_shared adds it temporarily, station.py:164-168, 197-201)
+                        double rate = 0.0;
+                        if (inr) {
+                            const int model = S.share[b];
+                            const double r0 = DCB_BW * dcb_log2_1p(tab, qual);
+                            if (conn) {
+                                rate = shared_rate(model, link_value(model, r0, iee), S.fac[b], S.arg[b], r, ee);
+                            } else {
+                                const int c = S.lcnt[b];
+                                const double sm = S.lsum[b];
+                                if (model == DCB_SHARE_RESOURCE_FAIR) rate = r0 / (double)(c + 1);
+                                else if (model == DCB_SHARE_RATE_FAIR) rate = 1.0 / (sm + 1.0 / r0);
+                                else if (model == DCB_SHARE_MAX_CAP) rate = (c == 0 || r0 > S.lbest[b]) ? r0 : 0.0;
+                                else { const double pr = r0 / ee; rate = pr / (sm + pr + DCB_EPSILON) * r0; }
+                            }
+                        }
+                        double dro;
+                        if (p.obs_var == DCB_OBSVAR_NORMDR) dro = fmin(rate, 100.0) / 100.0;             // variants.py:213-221
+                        else if (p.dr_mode == DCB_DR_AUTO) dro = fmin(rate - req, req) / req;           // variants.py:131-141
+                        else if (p.dr_mode == DCB_DR_SUB_REQ) dro = fmin(rate - req, p.dr_cutoff);
+                        else dro = fmin(rate, p.dr_cutoff);
+                        const size_t e = (size_t)r * M + b;
+                        const double vals[5] = {conn ? 1.0 : 0.0, sqrt(d2) / p.map_diag, dro,
+                                                sqrt(dist2(q ? bs1 : bs0, nx, ny)) / p.map_diag, (double)S.lcnt[b]};
+                        const int offs[5] = {p.vo_conn, p.vo_dist, p.vo_dr, p.vo_next, p.vo_ues};
+#pragma unroll
+                        for (int sgm = 0; sgm < 5; sgm++) {
+                            if (offs[sgm] < 0) continue;
+                            if (obs_env) obs_env[(size_t)offs[sgm] + e] = (float)vals[sgm];
+                            if (dbg_env) dbg_env[(size_t)offs[sgm] + e] = vals[sgm];
+                        }
+                    }
+                    if (lane == 0 && p.vo_tot >= 0) {
+                        const double cd = S.sdr[r];
+                        const double tot_o = p.obs_var == DCB_OBSVAR_NORMDR ? fmin(cd, 100.0) / 100.0
+                                                                            : fmin(cd - req, req) / req;   // variants.py:147-152, 222
+                        if (obs_env) obs_env[(size_t)p.vo_tot + r] = (float)tot_o;
+                        if (dbg_env) dbg_env[(size_t)p.vo_tot + r] = tot_o;
+                    }
+                } else {
+                    // RelNorm / MaxNorm observation on the SINR (variants.py:276-284, 308-332)
+                    double qmax = q0 > q1 ? q0 : q1;
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const double o = __shfl_xor_sync(0xffffffffu, qmax, off);
+                        qmax = o > qmax ? o : qmax;
+                    }
+                    const double inv_max = qmax > 0.0 ? 1.0 / qmax : 0.0;
+                    const float dr0 = p.obs_maxnorm ? max_norm_snr(q0) : (float)(q0 * inv_max);
+                    const float dr1 = p.obs_maxnorm ? max_norm_snr(q1) : (float)(q1 * inv_max);
+                    const float c0 = cb0 ? 1.0f : 0.0f, c1 = cb1 ? 1.0f : 0.0f;
+                    if (obs_lane) {
+                        float *o = obs_lane + r * row_stride_f;
+                        if (central) {
+                            if (ok0) { o[0] = c0; o[seg1] = dr0; }
+                            if (ok1) { o[32] = c1; o[seg1 + 32] = dr1; }
+                            if (lane == 0) obs_env[(size_t)2 * N * M + r] = (float)un;
+                        } else {
+                            if (ok0) { o[0] = c0; o[seg1] = dr0; o[seg2] = fu0; o[seg3] = fa0; }
+                            if (ok1) { o[32] = c1; o[seg1 + 32] = dr1; o[seg2 + 32] = fu1; o[seg3 + 32] = fa1; }
+                            if (lane == 0) o[4 * M] = (float)un;
+                        }
+                    }
+                    if (dbg_env) {
+                        if (central) {
+                            if (ok0) { dbg_env[r * M + b0] = (double)c0; dbg_env[N * M + r * M + b0] = (double)dr0; }
+                            if (ok1) { dbg_env[r * M + b1] = (double)c1; dbg_env[N * M + r * M + b1] = (double)dr1; }
+                            if (lane == 0) dbg_env[2 * N * M + r] = un;
+                        } else {
+                            double *drow = dbg_env + (size_t)r * OW;
+#pragma unroll
+                            for (int q = 0; q < 2; q++) {
+                                const int b = q ? b1 : b0;
+                                if (b < M) {
+                                    const int c = S.cnt_obs[b];
+                                    drow[b] = (double)(q ? c1 : c0);
+                                    drow[M + b] = (double)(q ? dr1 : dr0);
+                                    drow[2 * M + b] = (double)c / (double)NA;
+                                    drow[3 * M + b] = (c > 0 ? S.usum[b] / (double)c : 0.0) / DCB_MAX_UTILITY;
+                                }
+                            }
+                            if (lane == 0) drow[4 * M] = un;
+                        }
+                    }
+                }
+                if (last && a.out.dbg_snr) {
+                    if (ok0) a.out.dbg_snr[ru * M + b0] = q0;
+                    if (ok1) a.out.dbg_snr[ru * M + b1] = q1;
+                }
+                if (!central && T > 0) {
+                    // ---- multi_agent.py:39-95 on the POST-move state (as below, with the SINR-based in-range set)
+                    double agg = rutil;
+                    if (in0 | in1) {
+                        const bool i0 = (in0 >> lane) & 1u, i1 = (in1 >> lane) & 1u;
+                        if (p.reward == DCB_REWARD_AVG) {
+                            int nn = (i0 ? cn0 : 0) + (i1 ? cn1 : 0);
+                            double tt = (i0 ? us0 : 0.0) + (i1 ? us1 : 0.0);
+                            for (int off = 16; off > 0; off >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, off);
+                            tt = warp_sum(tt);
+                            if (nn > 0) agg = (rmask == 0 ? tt + rutil : tt) * dcb_rcp((double)(rmask == 0 ? nn + 1 : nn));
+                        } else if (p.reward == DCB_REWARD_SUM) {
+                            double sacc = 0.0;
+                            for (int j = lane; j < NA; j += 32)
+                                if (S.smask[j] & rmask) sacc += S.srb[j];
+                            agg = warp_sum(sacc);
+                        } else {
+                            double mn = i0 ? um0 : CUDART_INF;
+                            if (i1) mn = um1 < mn ? um1 : mn;
+                            mn = warp_min(mn);
+                            agg = mn < agg ? mn : agg;
+                        }
+                    }
+                    if (lane == 0) {
+                        if (reward_env) reward_env[r] = (float)agg;
+                        if (dbg_reward_env) dbg_reward_env[r] = agg;
+                    }
+                }
+                continue;
+            }
             const float f0 = (float)d20, f1 = (float)d21;
             float d2minf = fminf(f0, f1);
             for (int off = 16; off > 0; off >>= 1) d2minf = fminf(d2minf, __shfl_xor_sync(0xffffffffu, d2minf, off));
@@ -532,14 +785,27 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
 }  // namespace
 
 cudaError_t dcb_wide_set_smem_limit(size_t smem) {
-    cudaError_t e = cudaFuncSetAttribute(dcb_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(dcb_wide_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(dcb_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(dcb_wide_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(dcb_wide_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(dcb_wide_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     return e;
 }
 
 cudaError_t dcb_launch_wide(const StepArgs &a, int threads, int grid, size_t smem, cudaStream_t s) {
-    if (a.p.NA < a.p.N) dcb_wide_kernel<true><<<grid, threads, smem, s>>>(a);
-    else dcb_wide_kernel<false><<<grid, threads, smem, s>>>(a);
+    // the general instance (EXT) carries the data-rate observation classes, the interference extension, UniformMovement
+    // UEs and the no-move mode; the plain instances -- the measured path -- compile without them
+    const bool ext = a.p.obs_var || a.p.interference || a.p.uni_kind || (a.flags & DCB_STEPF_NO_MOVE);
+    const bool pad = a.p.NA < a.p.N;
+    if (ext) {
+        if (pad) dcb_wide_kernel<true, true><<<grid, threads, smem, s>>>(a);
+        else dcb_wide_kernel<false, true><<<grid, threads, smem, s>>>(a);
+    } else {
+        if (pad) dcb_wide_kernel<true, false><<<grid, threads, smem, s>>>(a);
+        else dcb_wide_kernel<false, false><<<grid, threads, smem, s>>>(a);
+    }
     return cudaGetLastError();
 }

@@ -59,6 +59,17 @@ class RandomWaypoint:
         return f"RandomWaypoint({self.init_velocity})"
 
 
+class UniformMovement:
+    """util/movement.py:26-45: move_x / move_y per step, numbers or 'slow' / 'fast'; bounces off the map border"""
+
+    def __init__(self, map, move_x=0, move_y=0):
+        self.map, self.init_move_x, self.init_move_y = map, move_x, move_y
+        self.move_x = self.move_y = None
+
+    def __str__(self):
+        return f"UniformMovement({self.move_x}, {self.move_y})"
+
+
 class User:
     """entities/user.py:12-50"""
 

@@ -40,18 +40,25 @@ def _parse_env_config(env_config):
                 curr += arrival
                 max_ues = max(max_ues, curr)
     assert max_ues >= len(ue_list)                                                        # base.py:84
-    velocities, init_pos, pauses, borders, utils = [], [], set(), set(), set()
+    velocities, init_pos, pauses, borders, utils, uniform = [], [], set(), set(), set(), []
     for ue in ue_list:
         if getattr(ue, 'util_func', 'log') not in ('log', 'step'):
             raise NotImplementedError(f"Utility function {ue.util_func} not implemented!")   # user.py:92
         utils.add((getattr(ue, 'util_func', 'log'), getattr(ue, 'dr_req', 1)))
         mv = ue.movement
-        if not hasattr(mv, 'init_velocity'):
-            raise NotImplementedError("only RandomWaypoint movement is in scope (movement.py:82-181)")
-        velocities.append(mv.init_velocity)
         init_pos.append((ue.init_pos_x, ue.init_pos_y))
+        if hasattr(mv, 'init_move_x'):                       # UniformMovement (movement.py:26-80)
+            uniform.append((mv.init_move_x, mv.init_move_y))
+            velocities.append(0)
+            continue
+        if not hasattr(mv, 'init_velocity'):
+            raise NotImplementedError("movement must be a RandomWaypoint or a UniformMovement (movement.py:26-181)")
+        uniform.append(None)
+        velocities.append(mv.init_velocity)
         pauses.add(mv.pause_duration)
         borders.add(mv.border_buffer)
+    if not pauses:
+        pauses, borders = {2}, {10}                          # only UniformMovement UEs: the RandomWaypoint defaults
     if len(pauses) != 1 or len(borders) != 1:
         raise NotImplementedError("per-UE pause_duration / border_buffer are not supported")
     if len(utils) != 1:
@@ -62,7 +69,8 @@ def _parse_env_config(env_config):
                 velocities=velocities, init_pos=init_pos, pause_duration=pauses.pop(), border_buffer=borders.pop(),
                 episode_length=env_config['episode_length'], rand_episodes=bool(env_config['rand_episodes']),
                 max_ues=int(max_ues), ue_arrival=env_config['ue_arrival'], new_ue_interval=env_config['new_ue_interval'],
-                util_func=util_func, dr_req=dr_req)
+                util_func=util_func, dr_req=dr_req,
+                uniform_moves=uniform if any(u is not None for u in uniform) else None)
 
 
 class _MobileEnvFacade:
@@ -116,7 +124,7 @@ class _MobileEnvFacade:
             episode_length=sc['episode_length'], rand_episodes=sc['rand_episodes'], init_pos=sc['init_pos'],
             pause_duration=sc['pause_duration'], border_buffer=sc['border_buffer'], device=self._device,
             max_ues=sc['max_ues'], ue_arrival=sc['ue_arrival'], new_ue_interval=sc['new_ue_interval'],
-            util_func=sc['util_func'], dr_req=sc['dr_req'], obs_norm=self._obs_norm)
+            util_func=sc['util_func'], dr_req=sc['dr_req'], obs_norm=self._obs_norm, uniform_moves=sc['uniform_moves'])
 
     # ---- MobileEnv attributes
     @property
@@ -326,6 +334,60 @@ class MultiAgentMobileEnv(_MobileEnvFacade):
         rewards = {ue.id: float(reward[i]) for i, ue in enumerate(self.ue_list)}         # multi_agent.py:39-95
         info = self._info(curr_dr, utility, sum_utility)
         return self.obs, rewards, self.done(), {ue.id: info for ue in self.ue_list}      # multi_agent.py:104-107
+
+
+class SeqMultiAgentMobileEnv(MultiAgentMobileEnv):
+    """
+    All agents observe and act one after the other within a time step; the UEs move and time advances after the last one
+    (reference multi_agent.py:110-179).  Every return value holds the CURRENT UE only.  As in the reference, `done` and
+    `info` nest the parent's per-UE dicts under the current UE's id (multi_agent.py:130-143 call the parent's methods,
+    which already return dicts keyed by UE id), and `ue_order_idx` survives reset().
+    """
+
+    def __init__(self, env_config):
+        super().__init__(env_config)
+        self.ue_order = self.ue_list
+        self.ue_order_idx = 0
+        self.curr_ue = self.ue_order[self.ue_order_idx]
+        self._last_info = None
+
+    def _curr_obs(self, row):
+        m = self.num_bs
+        return {self.curr_ue.id: {'connected': [int(v) for v in row[:m]], 'dr': [float(v) for v in row[m:2 * m]],
+                                  'utility': [float(row[4 * m])], 'ues_at_bs': [float(v) for v in row[2 * m:3 * m]],
+                                  'util_at_bs': [float(v) for v in row[3 * m:4 * m]]}}
+
+    def reset(self):
+        self.time = 0
+        self._reset_ue_list()
+        packed = self._batch.reset()[0].cpu().numpy()
+        self.curr_ue = self.ue_order[self.ue_order_idx]
+        self.obs = self._curr_obs(packed[self.ue_order_idx])
+        return self.obs
+
+    def done(self):
+        done = super().done()
+        return {self.curr_ue.id: done, '__all__': done}
+
+    def step(self, action):
+        a = 0
+        if self.curr_ue.id in action:                                   # multi_agent.py:21-30
+            a = int(action[self.curr_ue.id])
+            assert self.action_space.contains(a), f"Action {a} does not fit action space {self.action_space}"
+        dev = self._batch.device
+        row, reward, _, info = self._batch.step_sequential(torch.as_tensor([a], dtype=torch.int32, device=dev), info=True)
+        if info['moved']:
+            self.time += 1
+        self.ue_order_idx = info['ue_index']
+        self.curr_ue = self.ue_order[self.ue_order_idx]
+        curr_dr, utility = info['curr_dr'][0].cpu().numpy(), info['utility'][0].cpu().numpy()
+        sum_utility = float(info['sum_utility'][0])
+        self.last_lost_conn = info['lost_conn'][0].cpu().numpy()
+        self._sync_entities(curr_dr, utility)
+        self.obs = self._curr_obs(row[0].cpu().numpy())
+        base_info = self._info(curr_dr, utility, sum_utility)
+        return (self.obs, {self.curr_ue.id: float(reward[0])}, self.done(),
+                {self.curr_ue.id: {ue.id: base_info for ue in self.ue_list}})
 
 
 def get_env_class(env_type):

@@ -199,11 +199,65 @@ int dcb_set_utility(dcb_env *env, int32_t kind, double dr_req);
 typedef enum dcb_obs_norm { DCB_OBS_RELNORM = 0, DCB_OBS_MAXNORM = 1 } dcb_obs_norm;
 int dcb_set_obs_norm(dcb_env *env, int32_t kind);
 
+/*
+ * The data-rate observation classes (one setting per handle, central kind only -- the reference has CentralNormDrEnv and
+ * CentralDrEnv, multi_ue/central.py:75-140): every UE observes the SHARED rate it gets, or would get if it connected, from
+ * every BS (Basestation.data_rate, station.py:204-220: 0 out of range; a UE that is not connected is counted in
+ * temporarily) instead of the normalised SNR.
+ *   DCB_OBSVAR_NORMDR   NormDrMobileEnv.get_ue_obs (single_ue/variants.py:198-250): dr = min(rate, 100) / 100,
+ *                       dr_total = min(curr_dr, 100) / 100.
+ *   DCB_OBSVAR_DATARATE DatarateMobileEnv.get_ue_obs (single_ue/variants.py:127-170) with its env_config options:
+ *                       dr_mode AUTO min(rate - req, req) / req | SUB_REQ min(rate - req, dr_cutoff) | PLAIN
+ *                       min(rate, dr_cutoff); curr_dr_obs adds dr_total = min(curr_dr - req, req) / req; ues_at_bs_obs the
+ *                       number of UEs linked to each BS (per UE, not normalised); dist_obs the UE-BS distances / map
+ *                       diagonal; next_dist_obs the same after the UE's next step towards its waypoint (movement.py:132-156).
+ *                       req = dcb_set_utility's dr_req.
+ * Layout: the keys present, in alphabetical order (connected, dist, dr, dr_total, next_dist, ues_at_bs), each as one
+ * segment [N][M] (dr_total: [N]) -- central.py:31-57.  dcb_obs_size changes accordingly.  Handles with such an observation
+ * run on the one-CTA-per-env kernel (dcb_wide.cu) whatever their shape.  Call before the first dcb_observe / dcb_step.
+ */
+typedef enum dcb_obs_variant_kind { DCB_OBSVAR_NONE = 0, DCB_OBSVAR_NORMDR = 1, DCB_OBSVAR_DATARATE = 2 } dcb_obs_variant_kind;
+typedef enum dcb_dr_mode { DCB_DR_AUTO = 0, DCB_DR_SUB_REQ = 1, DCB_DR_PLAIN = 2 } dcb_dr_mode;
+typedef struct dcb_obs_variant {
+    int32_t kind;          /* dcb_obs_variant_kind */
+    int32_t dr_mode;       /* dcb_dr_mode (DATARATE) */
+    double dr_cutoff;      /* DATARATE, dr_mode != AUTO */
+    int32_t curr_dr_obs, ues_at_bs_obs, dist_obs, next_dist_obs;   /* DATARATE options (variants.py:56-79) */
+} dcb_obs_variant;
+int dcb_set_obs_variant(dcb_env *env, const dcb_obs_variant *variant);
+
+/*
+ * Interference extension (NOT in the reference, which is SNR only: station.py:122-127, docs/model.md:15-19; named by
+ * BASELINE.json's north star and config 4): with interference on, the signal quality of link (i, b) is
+ *   SINR(i, b) = P(i, b) / (noise + sum_{b' != b} P(i, b')),  P = received power (station.py:116-120),
+ * i.e. snr_b / (1 + sum_{b' != b} snr_b') in units of the noise floor, and it replaces the SNR everywhere the SNR is
+ * used: can_connect (SINR > 2e-8), the unshared rate bw log2(1 + SINR), the observation entry 'dr' (SINR / max SINR).
+ * The per-UE sum over the base stations is a warp-shuffle reduction over BS lanes.  Runs on the one-CTA-per-env kernel.
+ * Not parity-graded against the reference; its only oracle is the restatement in oracle/dcb_oracle.c.  Default off.
+ */
+int dcb_set_interference(dcb_env *env, int32_t on);
+
 /* get_obs() of the current state (central.py:31-57 / multi_agent.py:32-37) without stepping; reward is not written */
 int dcb_observe(dcb_env *env, const dcb_outputs *out, void *stream);
 
 /* MobileEnv.step (base.py:413-466) for all K envs: d_actions int32 [K][N] on the device */
 int dcb_step(dcb_env *env, const int32_t *d_actions, const dcb_outputs *out, void *stream);
+
+/*
+ * A step WITHOUT the movement half: actions are applied, rates / rewards / observation are updated, but no UE moves, no
+ * link is dropped, the EWMA rates and the env time stay.  SeqMultiAgentMobileEnv (multi_ue/multi_agent.py:110-179) calls
+ * this for every UE of a round but the last (whose call is a plain dcb_step with that UE's action alone).
+ */
+int dcb_step_no_move(dcb_env *env, const int32_t *d_actions, const dcb_outputs *out, void *stream);
+
+/*
+ * UniformMovement UEs (util/movement.py:26-80): UE i moves by (move_x, move_y) every step and bounces off the map border
+ * (both components flip when the next point would not be strictly inside the map).  host_kind int32 [N][2] per UE and
+ * component: 0 = this UE keeps its RandomWaypoint (both components 0), 1 = the number in host_value [N][2], 2 = 'slow'
+ * (randint(1, 5) from the UE's movement generator at every reset), 3 = 'fast' (randint(10, 20)).  Regenerates the RNG
+ * tables and resets the batch (synchronous): call it right after dcb_create.  Not with a variable UE population.
+ */
+int dcb_set_uniform_movement(dcb_env *env, const int32_t *host_kind, const double *host_value);
 
 /* T consecutive steps in ONE launch (state stays on chip between steps): d_actions int32 [T][K][N] */
 int dcb_step_many(dcb_env *env, const int32_t *d_actions, int32_t T, const dcb_outputs *out, void *stream);
@@ -223,6 +277,17 @@ int dcb_rollout(dcb_env *env, const dcb_policy *policy, int32_t T, int32_t *d_ac
  */
 int dcb_step_host(dcb_env *env, const int32_t *h_actions, float *h_obs, float *h_reward, uint8_t *h_lost_conn,
                   void *stream);
+
+/*
+ * T consecutive steps through host memory, pipelined: h_actions int32 [T][K][N] go to the device in one copy; the steps
+ * run in chunks (a few steps per launch, dcb_step_many) into two device staging buffers, and while chunk c+1 computes,
+ * chunk c's obs / reward / lost_conn travel to h_obs [T][...] / h_reward [T][...] / h_lost_conn [T][K][N] on a second
+ * (library-owned) copy stream.  ONE stream synchronise at the end: the call returns when every output is in host memory.
+ * PCIe-bound for every shape (the device produces 8.4 MB of observations per 5.6 us step at the headline shape), so
+ * pinned host buffers are required for the overlap; NULL outputs are skipped.  chunk_steps <= 0 picks ~16 MB chunks.
+ */
+int dcb_step_many_host(dcb_env *env, const int32_t *h_actions, int32_t T, float *h_obs, float *h_reward,
+                       uint8_t *h_lost_conn, int32_t chunk_steps, void *stream);
 
 /* Sticky device-side error flags (action range, table exhaustion) since the last call; synchronises the stream. */
 int dcb_check_errors(dcb_env *env, void *stream);

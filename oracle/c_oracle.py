@@ -47,6 +47,8 @@ def lib():
         L.orc_reward_size.argtypes = [ctypes.c_void_p]
         L.orc_get.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 13
         L.orc_batch_run.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ip, ctypes.c_int, ctypes.c_int]
+        L.orc_batch_trace.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ip, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.orc_rng_draws.argtypes = [ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ip, ip, ip]
         L.orc_max_threads.restype = ctypes.c_int
         _lib = L
@@ -161,3 +163,21 @@ def batch_run(envs, actions, nthreads=0):
     assert K == len(envs)
     arr = (ctypes.c_void_p * K)(*[e.h for e in envs])
     L.orc_batch_run(arr, K, _iptr(a), T, nthreads)
+
+
+def batch_trace(envs, actions, pos_every, nthreads=0):
+    """As batch_run, returning per step the connection bitmasks uint64 [T, K, N], the lost-link counts uint8 [T, K, N],
+    the rewards float64 [T, K, R], and the positions after every `pos_every`-th step float64 [T // pos_every, K, N, 2]."""
+    L = lib()
+    a = np.ascontiguousarray(actions, dtype=np.int32)
+    T, K, N = a.shape
+    assert K == len(envs)
+    R = envs[0].reward_size
+    mask = np.zeros((T, K, N), dtype=np.uint64)
+    lost = np.zeros((T, K, N), dtype=np.uint8)
+    rew = np.zeros((T, K, R), dtype=np.float64)
+    pos = np.zeros((T // pos_every, K, N, 2), dtype=np.float64)
+    arr = (ctypes.c_void_p * K)(*[e.h for e in envs])
+    L.orc_batch_trace(arr, K, _iptr(a), T, nthreads, mask.ctypes.data, lost.ctypes.data, rew.ctypes.data,
+                      pos.ctypes.data, pos_every)
+    return mask, lost, rew, pos

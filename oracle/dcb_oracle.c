@@ -492,6 +492,37 @@ void orc_batch_run(orc_env **envs, int K, const int *actions, int T, int nthread
     }
 }
 
+/* As orc_batch_run, recording what the soak tests compare bit for bit: the connection mask of every UE after every step
+ * (bit b = linked to BS b, [T][K][N]), the links each UE lost through movement ([T][K][N]), the step rewards
+ * ([T][K][R]) and the positions after every `pos_every`-th step ([T / pos_every][K][N][2]).  NULL outputs are skipped. */
+void orc_batch_trace(orc_env **envs, int K, const int *actions, int T, int nthreads, uint64_t *mask_out,
+                     uint8_t *lost_out, double *reward_out, double *pos_out, int pos_every) {
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+    (void)nthreads;
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < K; k++) {
+        orc_env *e = envs[k];
+        const int N = e->n_ue, M = e->n_bs, R = orc_reward_size(e);
+        for (int t = 0; t < T; t++) {
+            orc_step(e, actions + ((size_t)t * K + k) * N);
+            const size_t row = ((size_t)t * K + k) * N;
+            for (int i = 0; i < N; i++) {
+                if (mask_out) {
+                    uint64_t m = 0;
+                    for (int b = 0; b < M; b++) m |= (uint64_t)(e->mask[i * M + b] != 0) << b;
+                    mask_out[row + i] = m;
+                }
+                if (lost_out) lost_out[row + i] = (uint8_t)e->lost_conn[i];
+            }
+            if (reward_out) memcpy(reward_out + ((size_t)t * K + k) * R, e->reward, sizeof(double) * R);
+            if (pos_out && pos_every > 0 && (t + 1) % pos_every == 0)
+                memcpy(pos_out + (((size_t)((t + 1) / pos_every - 1) * K + k) * N) * 2, e->pos, sizeof(double) * 2 * N);
+        }
+    }
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

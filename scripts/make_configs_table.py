@@ -21,7 +21,7 @@ with open(f'{P}/{T}_configs.md', 'w') as f:
     f.write('| workload | kernel | geometry (envs/CTA, threads, smem, grid) | env-steps/s | us / batched step | B / env-step | '
             'achieved GB/s | frac of measured 6554.2 GB/s | e2e env-steps/s |\n|---|---|---|---|---|---|---|---|---|\n')
     for label, d in rows:
-        g, r = d['config']['launch_geometry'], d['roofline']
+        g, r = d['run']['launch_geometry'], d['roofline']
         f.write(f"| {label} | {r['kernel']} | {g['envs_per_cta']}, {g['threads']}, {g['smem_bytes']}, {g['grid']} | "
                 f"{d['value']:.3e} | {1e3 * d['ms_per_step']:.2f} | {r['algorithmic_bytes_per_env_step']} | "
                 f"{r['achieved']:.0f} | {100 * r['frac']:.1f} % | {d['e2e']['value']:.3e} |\n")

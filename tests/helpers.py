@@ -31,18 +31,17 @@ def golden_names():
 
 
 def pending_obs_names():
-    """traces of observation classes the oracle restates but the CUDA path does not offer yet (CentralNormDrEnv,
-    CentralDrEnv): oracle tests only"""
+    """traces of the data-rate observation classes (CentralNormDrEnv, CentralDrEnv: central.py:75-140)"""
     return [n for n in _names() if n.startswith(('normdr_', 'datarate_'))]
 
 
 def pending_sequential_names():
-    """traces of SeqMultiAgentMobileEnv (multi_ue/multi_agent.py:110-179): restated by the oracle, no CUDA path yet"""
+    """traces of SeqMultiAgentMobileEnv (multi_ue/multi_agent.py:110-179)"""
     return [n for n in _names() if n.startswith('seq_')]
 
 
 def pending_movement_names():
-    """traces with UniformMovement UEs (util/movement.py:26-80): restated by the oracle, not offered by the CUDA path yet"""
+    """traces with UniformMovement UEs (util/movement.py:26-80), mixed with RandomWaypoint UEs, two episodes"""
     return [n for n in _names() if n.startswith('uniform_')]
 
 

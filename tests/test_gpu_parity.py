@@ -6,7 +6,8 @@ import torch
 from oracle import c_oracle
 
 from helpers import (assert_close, assert_exact, golden_names, load_golden, obs_variant_names, oracle_kwargs,
-                     population_kwargs, population_names, utility_names)
+                     pending_movement_names, pending_obs_names, pending_sequential_names, population_kwargs,
+                     population_names, utility_names)
 
 pytestmark = pytest.mark.gpu
 
@@ -70,7 +71,7 @@ def compare_step(env, dbg, want, k, what, step=True, num_ue=None):
 
 
 @pytest.mark.parametrize('wide', [False, True], ids=['fused', 'wide'])
-@pytest.mark.parametrize('name', golden_names() + utility_names() + obs_variant_names())
+@pytest.mark.parametrize('name', golden_names() + utility_names() + obs_variant_names() + pending_movement_names())
 def test_cuda_step_matches_reference_golden(name, wide, monkeypatch):
     """K=1, one launch per step, every recorded array of the reference trace; through the fused kernel (dcb_step.cu)
     and through the one-CTA-per-env kernel for large envs (dcb_wide.cu, forced here for the small golden shapes)."""
@@ -121,6 +122,55 @@ def test_cuda_variable_population_matches_reference_golden(name, wide, monkeypat
             compare_step(env, dbg, {k: z['step_' + k][t] for k in step_keys}, 0, f'{name}.step[{t}]',
                          num_ue=env.active_ues)
             t += 1
+    env.check_errors()
+
+
+@pytest.mark.parametrize('wide', [False, True], ids=['fused', 'wide'])
+@pytest.mark.parametrize('name', pending_sequential_names())
+def test_cuda_sequential_env_matches_reference_golden(name, wide, monkeypatch):
+    """SeqMultiAgentMobileEnv (multi_agent.py:110-179): one UE acts per call, nothing moves until the last UE of the round
+    has acted (dcb_step_no_move), the call returns the NEXT UE's observation row and reward -- every recorded array of the
+    reference's trace, two envs in lockstep, through both kernels."""
+    if wide:
+        monkeypatch.setenv('DCB_FORCE_WIDE', '1')
+    cfg, z = load_golden(name)
+    kw = oracle_kwargs(cfg)
+    assert kw.pop('sequential')
+    env = make_env(kw, num_envs=2, seeds=[cfg['seed'], cfg['seed']])
+    n_ue, n_bs = cfg['n_ue'], len(cfg['bs_xy'])
+    dbg = env.reset(debug=True)
+    nxt = 0
+    for k in range(2):
+        want = {key: z['reset_' + key][0] for key in ('pos', 'mask', 'movement', 'ewma', 'snr', 'link_rates', 'curr_dr',
+                                                      'utility')}
+        want['obs'] = dbg['dbg_obs'][k].cpu().numpy()                  # the trace holds the current UE's row only ...
+        compare_step(env, dbg, want, k, f'{name}.reset', step=False)
+        assert_close(dbg['dbg_obs'][k, nxt].cpu().numpy(), z['reset_obs'][0], f'{name}.reset.obs', RTOL_DR, 1e-30)
+    for t in range(cfg['steps']):
+        a = torch.as_tensor(np.stack([z['actions'][t]] * 2).astype(np.int32), device='cuda')
+        dbg = env.step_sequential(a, debug=True)
+        nxt = dbg['ue_index']
+        st = env.get_state()
+        for k in range(2):
+            what = f'{name}.step[{t}].env{k}'
+            assert_exact(st['pos'][k], z['step_pos'][t], what + '.pos')
+            assert_exact(env.mask_matrix(st['mask'])[k], z['step_mask'][t], what + '.mask')
+            assert_exact(st['movement'][k], z['step_movement'][t], what + '.movement')
+            assert st['time'][k] == z['step_time'][t]
+            assert_exact(dbg['lost_conn'][k].cpu().numpy().astype(np.int32), z['step_lost_conn'][t], what + '.lost_conn')
+            assert_close(st['ewma'][k], z['step_ewma'][t], what + '.ewma', RTOL, ATOL)
+            assert_close(dbg['dbg_snr'][k].cpu().numpy(), z['step_snr'][t], what + '.snr', RTOL, 0)
+            assert_close(dbg['dbg_link_rate'][k].cpu().numpy(), z['step_link_rates'][t], what + '.link_rates', RTOL, ATOL)
+            assert_close(dbg['dbg_curr_dr'][k].cpu().numpy(), z['step_curr_dr'][t], what + '.curr_dr', RTOL, ATOL)
+            assert_close(dbg['dbg_utility'][k].cpu().numpy(), z['step_utility'][t], what + '.utility', RTOL, ATOL)
+            assert_close(dbg['dbg_sum_utility'][k].cpu().numpy(), z['step_sum_utility'][t], what + '.sum_utility', RTOL, ATOL)
+            w_rest, w_dr = split_dr(z['step_obs'][t][None, :], 1, n_bs)
+            g_rest, g_dr = split_dr(dbg['dbg_obs'][k, nxt].cpu().numpy()[None, :], 1, n_bs)
+            assert_close(g_rest, w_rest, what + '.obs64', RTOL, ATOL)
+            assert_close(g_dr, w_dr, what + '.obs64.dr', RTOL_DR, 1e-30)
+            assert_close(dbg['obs'][k, nxt].cpu().numpy(), z['step_obs'][t], what + '.obs32', RTOL32, ATOL32)
+            assert_close(dbg['dbg_reward'][k, nxt].cpu().numpy(), z['step_reward'][t], what + '.reward64', RTOL, ATOL)
+            assert_close(dbg['reward'][k, nxt].cpu().numpy(), z['step_reward'][t], what + '.reward32', RTOL32, ATOL32)
     env.check_errors()
 
 

@@ -1,0 +1,162 @@
+"""GPU: parity soak at the benched shapes and adversarial UE placements (hard part a).
+
+The connection mask is `snr > 2e-8` (station.py:10, 222-226), i.e. distance < 68.92488308058006 m; the CUDA path takes
+the decision as one fp64 compare of the squared distance against a host-computed threshold.  These
+tests (i) replay >= 1e8 UE x BS pair-steps through both kernels against the C oracle and assert ZERO mismatches in
+masks, lost-connection counts and positions, and (ii) put UEs a few ulps either side of the threshold distance, on top of
+a base station, within a metre of one, and on the map border, against the golden-pinned Python oracle.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from oracle.deepcomp_oracle import OracleEnv, grid_layout
+
+from helpers import assert_close, assert_exact
+
+pytestmark = pytest.mark.gpu
+
+THRESHOLD_DISTANCE = 68.92488308058006       # largest distance with snr > 2e-8 (SURVEY.md section 8c anchors)
+
+
+def _soak(n_ue, n_bs, K, episodes, L, frag, kind='multi', force_wide=False, monkeypatch=None):
+    """K envs x episodes x L steps in fragments of `frag` steps: masks (from the observation's `connected` entries) and
+    lost links of EVERY step and env, positions / masks / pause state after every fragment, all bit-exact; rewards to
+    float32 rounding.  Returns the number of UE x BS pair-steps compared."""
+    from deepcomp_b200 import BatchedMobileEnv, env_seeds
+    if force_wide:
+        monkeypatch.setenv('DCB_FORCE_WIDE', '1')
+    W, H, bs = grid_layout(n_bs)
+    seeds = env_seeds(1000, K, n_ue)
+    kw = dict(kind=kind, n_ue=n_ue, bs_xy=bs, map_wh=(W, H), sharing='mixed', velocities='slow', reward='avg',
+              episode_length=L)
+    env = BatchedMobileEnv(num_envs=K, seeds=seeds, **kw)
+    orcs = [c_oracle.COracleEnv(seed=int(s), **kw) for s in seeds]
+    rng = np.random.default_rng(2024)
+    bits = np.arange(n_bs, dtype=np.uint64)
+    mismatches = 0
+    pair_steps = 0
+    for ep in range(episodes):
+        env.reset()
+        for o in orcs:
+            o.L.orc_reset(o.h)
+        acts = rng.integers(0, n_bs + 1, (L, K, n_ue)).astype(np.int32)
+        want_mask, want_lost, want_rew, want_pos = c_oracle.batch_trace(orcs, acts, frag)
+        a_dev = torch.as_tensor(acts, device='cuda')
+        for f0 in range(0, L, frag):
+            out = env.step_many(a_dev[f0:f0 + frag].contiguous())
+            obs = out['obs'].cpu().numpy()
+            if kind == 'multi':
+                conn = obs[..., :n_bs]                                        # [frag, K, N, M]
+            else:
+                conn = obs[..., :n_ue * n_bs].reshape(frag, K, n_ue, n_bs)
+            want_conn = ((want_mask[f0:f0 + frag, ..., None] >> bits) & np.uint64(1)).astype(np.float32)
+            mismatches += int((conn != want_conn).sum())
+            mismatches += int((out['lost_conn'].cpu().numpy() != want_lost[f0:f0 + frag]).sum())
+            st = env.get_state()
+            mismatches += int((st['pos'] != want_pos[f0 // frag]).sum())
+            mismatches += int((st['mask'] != want_mask[f0 + frag - 1]).sum())
+            rew = out['reward'].cpu().numpy().reshape(frag, K, -1)
+            assert_close(rew, want_rew[f0:f0 + frag], f'ep{ep}.reward[{f0}:{f0 + frag}]', 2e-6, 1e-6)
+            pair_steps += frag * K * n_ue * n_bs
+    env.check_errors()
+    print(f"soak ({n_ue} UE x {n_bs} BS x {K} envs, {kind}, {env.kernel_name}): {pair_steps:.3e} pair-steps, "
+          f"{mismatches} mismatches")
+    assert mismatches == 0
+    return pair_steps
+
+
+def test_soak_headline_shape_zero_mismatches():
+    """(50, 10, 1024) x 200 steps (two episodes, reset in between) on the fused kernel at the benched geometry:
+    1.02e8 pair-steps, every env and step."""
+    assert _soak(50, 10, 1024, episodes=2, L=100, frag=20) >= 1e8
+
+
+def test_soak_central_and_wide_kernel(monkeypatch):
+    """the central layout at the headline shape and BASELINE config 4's shape (1000 UE x 50 BS) on the wide kernel"""
+    n = _soak(50, 10, 256, episodes=1, L=100, frag=25, kind='central')
+    n += _soak(1000, 50, 8, episodes=1, L=20, frag=5)
+    n += _soak(50, 10, 64, episodes=1, L=100, frag=20, force_wide=True, monkeypatch=monkeypatch)
+    assert n >= 2e7
+
+
+def _ulps(x, k):
+    for _ in range(abs(k)):
+        x = math.nextafter(x, math.inf if k > 0 else -math.inf)
+    return x
+
+
+def _adversarial_scenario():
+    """Static UEs (velocity 0: RandomWaypoint never moves them, movement.py:132-156) at hand-picked distances from BS 0 at
+    the origin, so that distance = sqrt(d*d + 0) = d exactly: the threshold distance +- {0, 1, 2, 8} ulps, d in
+    {0, 1e-9, 0.5, 0.999, 1.001} m (the near-BS branches of the SNR evaluation), the map corners / borders, and the same
+    offsets along the diagonal (both coordinates non-zero)."""
+    W, H = 200, 150
+    bs = [(0.0, 0.0), (200.0, 150.0), (100.0, 75.0)]
+    pts = []
+    for k in (-8, -2, -1, 0, 1, 2, 8):
+        d = _ulps(THRESHOLD_DISTANCE, k)
+        pts.append((d, 0.0))
+        pts.append((0.0, d))
+        pts.append((200.0 - d, 150.0))                       # from BS 1; 200 - d rounds: whatever it is, both sides agree
+        c = d / math.sqrt(2.0)
+        pts.append((_ulps(c, k), c))                         # diagonal from BS 0
+        pts.append((100.0 + c, 75.0 - c))                    # diagonal from BS 2
+    for d in (0.0, 1e-9, 0.5, 0.999, 1.001, 1.0):
+        pts.append((d, 0.0))
+        pts.append((100.0 + d, 75.0))
+        pts.append((200.0, 150.0 - d))
+    pts += [(0.0, 150.0), (200.0, 0.0), (200.0, 75.0), (0.0, 75.0), (100.0, 0.0), (100.0, 150.0), (100.0, 75.0)]
+    return W, H, bs, pts
+
+
+@pytest.mark.parametrize('wide', [False, True], ids=['fused', 'wide'])
+@pytest.mark.parametrize('kind', ['central', 'multi'])
+def test_adversarial_positions_match_the_python_oracle(kind, wide, monkeypatch):
+    """Every UE tries to connect to every BS in turn (and toggles back): masks bit-exact, SNR / rates / utilities /
+    observation within the usual tolerances, through both kernels, against the Python oracle (bit-identical to the
+    reference on the golden traces).  station.py:10,122-127,222-226; variants.py:276-284."""
+    from deepcomp_b200 import BatchedMobileEnv
+    if wide:
+        monkeypatch.setenv('DCB_FORCE_WIDE', '1')
+    W, H, bs, pts = _adversarial_scenario()
+    n_ue, n_bs = len(pts), len(bs)
+    kw = dict(kind=kind, n_ue=n_ue, bs_xy=bs, map_wh=(W, H), sharing='mixed', velocities=[0] * n_ue, reward='avg',
+              episode_length=20, init_pos=pts)
+    orc = OracleEnv(seed=5, **kw)
+    env = BatchedMobileEnv(num_envs=2, seeds=[5, 5], **kw)
+    want = orc.reset_trace()
+    dbg = env.reset(debug=True)
+    assert_exact(env.get_state()['pos'][0], want['pos'], 'reset.pos')
+    n_in_range = 0
+    for t in range(2 * n_bs + 2):
+        a = np.full(n_ue, (t % n_bs) + 1, dtype=np.int32)
+        want = orc.step(a)
+        dbg = env.step(torch.as_tensor(np.stack([a, a]), device='cuda'), debug=True)
+        st = env.get_state()
+        for k in range(2):
+            assert_exact(st['pos'][k], want['pos'], f'step[{t}].pos')
+            assert_exact(env.mask_matrix(st['mask'])[k], want['mask'], f'step[{t}].mask')
+            assert_exact(dbg['lost_conn'][k].cpu().numpy().astype(np.int32), want['lost_conn'], f'step[{t}].lost_conn')
+            # snr at d = 0 is 10^((30 - c1 + 16 c2) / 10) / 1e-9 ~ 1e48: relative tolerance only
+            assert_close(dbg['dbg_snr'][k].cpu().numpy(), want['snr'], f'step[{t}].snr', 1e-9, 0)
+            assert_close(dbg['dbg_link_rate'][k].cpu().numpy(), want['link_rates'], f'step[{t}].link_rates', 1e-9, 1e-9)
+            assert_close(dbg['dbg_curr_dr'][k].cpu().numpy(), want['curr_dr'], f'step[{t}].curr_dr', 1e-9, 1e-9)
+            assert_close(dbg['dbg_utility'][k].cpu().numpy(), want['utility'], f'step[{t}].utility', 1e-9, 1e-9)
+            assert_close(dbg['dbg_reward'][k].cpu().numpy(), want['reward'], f'step[{t}].reward', 1e-9, 1e-9)
+            assert_close(dbg['obs'][k].cpu().numpy(), want['obs'], f'step[{t}].obs', 2e-6, 1e-6)
+        n_in_range += int(want['mask'].sum())
+    # the scenario must actually straddle the threshold: UEs exactly at it connect, UEs one ulp beyond do not
+    thr_ue = pts.index((THRESHOLD_DISTANCE, 0.0))
+    out_ue = pts.index((_ulps(THRESHOLD_DISTANCE, 1), 0.0))
+    a = np.zeros(n_ue, dtype=np.int32)
+    a[thr_ue] = a[out_ue] = 1
+    orc2 = OracleEnv(seed=5, **kw)
+    orc2.reset_trace()
+    w = orc2.step(a)
+    assert w['mask'][thr_ue, 0] == 1 and w['mask'][out_ue, 0] == 0
+    assert n_in_range > 0
+    env.check_errors()
