@@ -54,7 +54,7 @@ SYMBOLS = [
     'dcb_step_many', 'dcb_rollout', 'dcb_step_host', 'dcb_check_errors', 'dcb_get_state', 'dcb_set_state', 'dcb_obs_size',
     'dcb_reward_size', 'dcb_algorithmic_bytes_per_env_step', 'dcb_launch_count', 'dcb_launch_geometry',
     'dcb_kernel_name', 'dcb_set_active_ues', 'dcb_get_active_ues', 'dcb_population_event', 'dcb_get_ue_ids', 'dcb_num_joint_actions', 'dcb_test_actions', 'dcb_set_utility',
-    'dcb_set_obs_norm', 'dcb_step_many_host', 'dcb_step_no_move', 'dcb_set_uniform_movement', 'dcb_set_obs_variant', 'dcb_set_interference',
+    'dcb_set_obs_norm', 'dcb_step_many_host', 'dcb_step_no_move', 'dcb_set_uniform_movement', 'dcb_set_obs_variant', 'dcb_set_interference', 'dcb_extend_waypoints',
 ]
 
 DCB_ABI_VERSION = 1
@@ -101,6 +101,7 @@ def load():
     L.dcb_rollout.argtypes = [vp, ctypes.POINTER(DcbPolicy), i32, vp, ctypes.POINTER(DcbOutputs), vp]
     L.dcb_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     L.dcb_step_many_host.argtypes = [vp, vp, i32, vp, vp, vp, i32, vp]
+    L.dcb_extend_waypoints.argtypes = [vp, vp]
     L.dcb_check_errors.argtypes = [vp, vp]
     L.dcb_get_state.argtypes = [vp, ctypes.POINTER(DcbStateHost)]
     L.dcb_set_state.argtypes = [vp, ctypes.POINTER(DcbStateHost)]

@@ -1,8 +1,10 @@
 """Baseline agents of the reference (deepcomp/agent/heuristics.py, deepcomp/agent/dummy.py) in two forms.
 
-* Host form: the same classes, constructor arguments and ``compute_action`` signatures as the reference, operating on
-  the obs dicts the facades in ``deepcomp_b200.env`` return -- so the reference's evaluation loop
-  (``Simulation.apply_action_multi_agent``, deepcomp/util/simulation.py:351-380) runs unchanged.
+* Host / tensor form: the same classes and constructor arguments as the reference; the decision rules are written over
+  whole observation batches (``compute_actions(obs [..., N, 4M+1]) -> int32 [..., N]``, torch ops on whichever device
+  the observations live on), and the reference's per-UE ``compute_action(obs_dict, policy_id)`` is a thin wrapper -- so
+  the reference's evaluation loop (``Simulation.apply_action_multi_agent``, deepcomp/util/simulation.py:351-380) runs
+  unchanged on the facades of ``deepcomp_b200.env``.
 * Device form: ``agent.device_policy(batch)`` describes the same decision rule to the CUDA step kernel, which then
   drives all K envs for a whole fragment without a host round trip (``BatchedMobileEnv.rollout``): the physics warps
   evaluate the rule from the state they already hold ("highest dr" = "smallest distance", "dr >= eps * best" as a
@@ -11,6 +13,7 @@
 import random
 
 import numpy as np
+import torch
 
 POLICY_KIND = {'3gpp': 1, 'fullcomp': 2, 'dynamic': 3, 'static': 4, 'fixed': 5, 'random': 6}
 
@@ -35,52 +38,76 @@ class CentralAgent:
         raise NotImplementedError("This needs to be implemented in the child class")
 
 
-class Heuristic3GPP(MultiAgent):
-    """Always at most one BS: the one with the highest SNR (heuristics.py:13-38)."""
+def _split(obs, n_bs=None):
+    """(connected, dr) as bool / float tensors [..., M] from a packed multi-agent observation [..., 4M+1] (the layout of
+    BatchedMobileEnv: connected | dr | ues_at_bs | util_at_bs | utility) or from one of the facades' obs dicts"""
+    if isinstance(obs, dict):
+        return torch.as_tensor(np.asarray(obs['connected'])) > 0, torch.as_tensor(np.asarray(obs['dr'], dtype=np.float64))
+    obs = torch.as_tensor(obs)
+    m = (obs.shape[-1] - 1) // 4 if n_bs is None else n_bs
+    return obs[..., :m] > 0, obs[..., m:2 * m]
+
+
+def _first_true(mask):
+    """index of the first True along the last axis (0 where there is none)"""
+    return torch.argmax(mask.to(torch.int8), dim=-1)
+
+
+def _argmax_first(x):
+    """np.argmax semantics (first maximum) along the last axis"""
+    return _first_true(x == x.max(dim=-1, keepdim=True).values)
+
+
+def _pick_in_set(conn, dr, selected):
+    """Common tail of DynamicSelection / StaticClustering for a whole batch (heuristics.py:93-108, 177-187): leave the
+    first connected BS outside the set; else join the strongest BS of the set that is not connected yet; else no-op."""
+    leave = conn & ~selected
+    want = selected & ~conn
+    strongest = _argmax_first(torch.where(want, dr, torch.full_like(dr, -float('inf'))))
+    act = torch.where(want.any(dim=-1), strongest + 1, torch.zeros_like(strongest))
+    return torch.where(leave.any(dim=-1), _first_true(leave) + 1, act).to(torch.int32)
+
+
+class _BatchedHeuristic(MultiAgent):
+    """
+    The per-UE decision rules evaluated for ALL UEs of ALL envs at once: ``compute_actions(obs)`` takes the packed
+    observation tensor of BatchedMobileEnv ([..., N, 4M+1], host or device) and returns int32 actions [..., N];
+    ``compute_action(obs, policy_id)`` is the reference's per-UE signature (one obs dict) on top of it.
+    """
+
+    def compute_actions(self, obs, n_bs=None):
+        raise NotImplementedError
 
     def compute_action(self, obs, policy_id=None):
-        best_bs = int(np.argmax(obs['dr']))
-        if obs['connected'][best_bs]:
-            return 0
-        if sum(obs['connected']) > 0:
-            return list(obs['connected']).index(1) + 1
-        return best_bs + 1
+        return int(self.compute_actions(obs))
+
+
+class Heuristic3GPP(_BatchedHeuristic):
+    """At most one BS, the one with the highest SNR; leave any other BS first (heuristics.py:13-38)."""
+
+    def compute_actions(self, obs, n_bs=None):
+        conn, dr = _split(obs, n_bs)
+        best = _argmax_first(dr)
+        at_best = torch.gather(conn, -1, best.unsqueeze(-1)).squeeze(-1)
+        act = torch.where(conn.any(dim=-1), _first_true(conn) + 1, best + 1)
+        return torch.where(at_best, torch.zeros_like(act), act).to(torch.int32)
 
     def device_policy(self, batch=None):
         return dict(kind='3gpp')
 
 
-class FullCoMP(MultiAgent):
-    """Greedily connect to all BS, strongest first (heuristics.py:41-65)."""
+class FullCoMP(_BatchedHeuristic):
+    """Connect to every BS, strongest first (heuristics.py:41-65)."""
 
-    def compute_action(self, obs, policy_id=None):
-        disconn_bs = [idx for idx, conn in enumerate(obs['connected']) if not conn]
-        if len(disconn_bs) == 0:
-            return 0
-        best_bs = disconn_bs[0]
-        best_dr = obs['dr'][best_bs]
-        for bs in disconn_bs:
-            if obs['dr'][bs] > best_dr:
-                best_bs, best_dr = bs, obs['dr'][bs]
-        return best_bs + 1
+    def compute_actions(self, obs, n_bs=None):
+        conn, dr = _split(obs, n_bs)
+        return _pick_in_set(conn, dr, torch.ones_like(conn))
 
     def device_policy(self, batch=None):
         return dict(kind='fullcomp')
 
 
-def _select_within(obs, selected):
-    """Common tail of DynamicSelection / StaticClustering (heuristics.py:93-108, 177-187)."""
-    connected = [idx for idx, conn in enumerate(obs['connected']) if conn]
-    for bs in connected:
-        if bs not in selected:
-            return bs + 1
-    for bs in sorted(selected, key=lambda idx: obs['dr'][idx], reverse=True):
-        if not obs['connected'][bs]:
-            return bs + 1
-    return 0
-
-
-class DynamicSelection(MultiAgent):
+class DynamicSelection(_BatchedHeuristic):
     """Strongest BS and all BS within epsilon * SNR of it (heuristics.py:68-108)."""
 
     def __init__(self, epsilon):
@@ -88,15 +115,15 @@ class DynamicSelection(MultiAgent):
         assert 0 <= epsilon <= 1, f"Scaling factor epsilon must be within [0,1] but is {epsilon}."   # cli.py:100
         self.epsilon = epsilon
 
-    def compute_action(self, obs, policy_id=None):
-        threshold = max(obs['dr']) * self.epsilon
-        return _select_within(obs, [idx for idx, snr in enumerate(obs['dr']) if snr >= threshold])
+    def compute_actions(self, obs, n_bs=None):
+        conn, dr = _split(obs, n_bs)
+        return _pick_in_set(conn, dr, dr >= dr.max(dim=-1, keepdim=True).values * self.epsilon)
 
     def device_policy(self, batch=None):
         return dict(kind='dynamic', epsilon=float(self.epsilon))
 
 
-class StaticClustering(MultiAgent):
+class StaticClustering(_BatchedHeuristic):
     """Static, non-overlapping clusters of `cluster_size` closest cells (heuristics.py:111-187)."""
 
     def __init__(self, cluster_size, bs_list, seed=None, clusters=None):
@@ -131,8 +158,13 @@ class StaticClustering(MultiAgent):
             clusters[b] = set(curr)
         return clusters
 
-    def compute_action(self, obs, policy_id=None):
-        return _select_within(obs, sorted(self.clusters[int(np.argmax(obs['dr']))]))
+    def compute_actions(self, obs, n_bs=None):
+        conn, dr = _split(obs, n_bs)
+        m = conn.shape[-1]
+        member = torch.zeros((m, m), dtype=torch.bool, device=conn.device)      # member[b, c]: c is in the cluster of b
+        for b, cluster in self.clusters.items():
+            member[b, sorted(cluster)] = True
+        return _pick_in_set(conn, dr, member[_argmax_first(dr)])
 
     def cluster_masks(self):
         m = np.zeros(len(self.bs_list), dtype=np.uint64)

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import DcbConfig, DcbOutputs, DcbPolicy, DcbStateHost, check
+from ._lib import DcbConfig, DcbObsVariant, DcbOutputs, DcbPolicy, DcbStateHost, check
 
 KIND = {'central': 0, 'multi': 1}
 REWARD = {'avg': 0, 'sum': 1, 'min': 2}
@@ -45,10 +45,16 @@ class BatchedMobileEnv:
     def __init__(self, num_envs, n_ue, bs_xy, map_wh, kind='multi', sharing='mixed', velocities='slow', seed=0,
                  seeds=None, reward='avg', episode_length=100, rand_episodes=False, auto_reset=False, init_pos=None,
                  pause_duration=2, border_buffer=10, device=None, first_env=0, max_ues=None, ue_arrival=None,
-                 new_ue_interval=None, util_func='log', dr_req=1, obs_norm='rel', uniform_moves=None):
+                 new_ue_interval=None, util_func='log', dr_req=1, obs_norm='rel', uniform_moves=None,
+                 obs_variant=None, obs_opts=None, interference=False):
         """
         `obs_norm`: 'rel' = the observation entry 'dr' is snr / max snr (RelNormEnv, variants.py:276-284; default);
         'max' = (min(snr, 7e-6) - 2e-8) / (7e-6 - 2e-8) (MaxNormEnv, variants.py:308-332; CentralMaxNormEnv).
+
+        `obs_variant`: None, 'normdr' (CentralNormDrEnv, central.py:107-140) or 'datarate' (CentralDrEnv, central.py:75-104)
+        with `obs_opts` = the reference's env_config keys dr_cutoff ('auto' or a number), sub_req_dr, curr_dr_obs,
+        ues_at_bs_obs, dist_obs, next_dist_obs (variants.py:56-79); central kind only.
+        `interference`: extension, not in the reference (SNR only): SINR = P_b / (noise + sum of the other P_b').
 
         `uniform_moves`: None, or per UE None (RandomWaypoint) / (move_x, move_y) = UniformMovement (util/movement.py:26-80),
         each component a number or 'slow' / 'fast' (drawn per reset from the UE's movement generator).
@@ -80,6 +86,7 @@ class BatchedMobileEnv:
         if self._dynamic and (rand_episodes or auto_reset):
             raise NotImplementedError("variable UE population needs rand_episodes=False and auto_reset=False")
         self._t = 0                                          # MobileEnv.time of the lockstep batch (events key on it)
+        self._table_steps = 0                                # steps taken since the waypoint tables were (re)generated
         if not isinstance(velocities, (list, tuple, np.ndarray)):
             velocities = [velocities] * int(n_ue)
         velocities = list(velocities) + ['slow'] * (n_slots - len(velocities))   # add_new_ue(velocity='slow')
@@ -170,6 +177,44 @@ class BatchedMobileEnv:
             check(self._L.dcb_set_uniform_movement(self._h, ctypes.c_void_p(kinds.ctypes.data),
                                                    ctypes.c_void_p(vals.ctypes.data)))
             self.uniform_moves = [None if u is None else tuple(u) for u in uniform_moves]
+        self.obs_variant, self.obs_opts = obs_variant, None
+        if obs_variant is not None:
+            if obs_variant not in ('normdr', 'datarate'):
+                raise ValueError(f"obs_variant must be None, 'normdr' or 'datarate', got {obs_variant!r}")
+            if kind != 'central':
+                raise NotImplementedError("the data-rate observation classes exist for the central env only "
+                                          "(CentralNormDrEnv / CentralDrEnv, central.py:75-140)")
+            o = dict(dr_cutoff='auto', sub_req_dr=True, curr_dr_obs=False, ues_at_bs_obs=False, dist_obs=False,
+                     next_dist_obs=False)
+            o.update(obs_opts or {})
+            v = DcbObsVariant(kind=1 if obs_variant == 'normdr' else 2)
+            if obs_variant == 'datarate':
+                # variants.py:75-79
+                assert not (o['dr_cutoff'] == 'auto' and not o['sub_req_dr']), "For dr_cutoff auto, sub_req_dr must be True."
+                assert (not o['curr_dr_obs']) or (o['dr_cutoff'] == 'auto' and o['sub_req_dr']), \
+                    "Enable all processing to add extra obs"
+                assert o['dist_obs'] or not o['next_dist_obs'], "Also enable 'dist_obs' when using 'next_dist_obs'"
+                v.dr_mode = 0 if o['dr_cutoff'] == 'auto' else (1 if o['sub_req_dr'] else 2)
+                v.dr_cutoff = 0.0 if o['dr_cutoff'] == 'auto' else float(o['dr_cutoff'])
+                v.curr_dr_obs, v.ues_at_bs_obs = int(bool(o['curr_dr_obs'])), int(bool(o['ues_at_bs_obs']))
+                v.dist_obs, v.next_dist_obs = int(bool(o['dist_obs'])), int(bool(o['next_dist_obs']))
+                if util_func == 'log':          # the required rate enters the observation even with the log utility
+                    check(self._L.dcb_set_utility(self._h, 0, float(dr_req)))
+            check(self._L.dcb_set_obs_variant(self._h, ctypes.byref(v)))
+            self.obs_opts = o
+            self.obs_size = int(self._L.dcb_obs_size(self._h))
+            self.obs_shape = (self.obs_size,)
+            n, m = self.n_ue, self.n_bs
+            if obs_variant == 'normdr':
+                self.obs_keys = [('connected', n * m), ('dr', n * m), ('dr_total', n)]
+            else:
+                self.obs_keys = [('connected', n * m)] + ([('dist', n * m)] if o['dist_obs'] else []) + [('dr', n * m)] + \
+                    ([('dr_total', n)] if o['curr_dr_obs'] else []) + ([('next_dist', n * m)] if o['next_dist_obs'] else []) + \
+                    ([('ues_at_bs', n * m)] if o['ues_at_bs_obs'] else [])
+            assert sum(w for _, w in self.obs_keys) == self.obs_size
+        self.interference = bool(interference)
+        if self.interference:
+            check(self._L.dcb_set_interference(self._h, 1))
         self._seq_idx = 0            # SeqMultiAgentMobileEnv.ue_order_idx (multi_agent.py:119; never reset)
 
     # ------------------------------------------------------------------ plumbing
@@ -273,6 +318,12 @@ class BatchedMobileEnv:
     def split_obs(self, obs):
         """Packed observation -> dict of views keyed like the reference's obs dicts (variants.py:302-303)."""
         M, N = self.n_bs, self.n_ue
+        if self.obs_variant is not None:
+            out, o = {}, 0
+            for key, w in self.obs_keys:
+                out[key] = obs[..., o:o + w]
+                o += w
+            return out
         if self.kind == 'central':
             nm = N * M
             return {'connected': obs[..., :nm], 'dr': obs[..., nm:2 * nm], 'utility': obs[..., 2 * nm:]}
@@ -332,11 +383,31 @@ class BatchedMobileEnv:
                                                    self._stream()))
         return actions
 
+    def _before_steps(self, T):
+        """
+        Continuous stepping (the reference's --cont-train / soft_horizon: no reset at episode_length, `done` is never set,
+        base.py:371-381): the pre-drawn waypoint tables cover episode_length steps, so before a launch would run past them
+        the per-UE random streams are continued on the device (dcb_extend_waypoints).
+        """
+        if self.auto_reset:                # the envs reset themselves on the device when their time is up
+            return
+        if self._table_steps + T <= self.episode_length:
+            self._table_steps += T
+            return
+        if T > self.episode_length:
+            raise ValueError(f"a fragment of {T} steps is longer than episode_length = {self.episode_length}")
+        if self._dynamic or self.num_ue_initial != self.n_ue:
+            raise NotImplementedError("stepping past episode_length without reset() with a variable UE population")
+        check(self._L.dcb_extend_waypoints(self._h, self._stream()))
+        self._table_steps = T
+
     def reset(self, env_ids=None, debug=False):
         """MobileEnv.reset (base.py:169-189) for all envs or the listed ones; returns the observation of ALL envs."""
         if self._dynamic and env_ids is not None:
             raise NotImplementedError("a batch with a variable UE population resets as a whole (lockstep)")
         self._t = 0
+        if env_ids is None:
+            self._table_steps = 0
         if env_ids is None:
             check(self._L.dcb_reset(self._h, None, 0, self._stream()))
         else:
@@ -358,6 +429,7 @@ class BatchedMobileEnv:
     def step(self, actions, info=True, debug=False):
         """MobileEnv.step (base.py:413-466) for all K envs.  actions: int32 [K, N] on the device."""
         self._check_actions(actions)
+        self._before_steps(1)
         if self._dynamic:
             actions = self._population_events(self._t, actions)
         self._t += 1
@@ -387,6 +459,7 @@ class BatchedMobileEnv:
         o, t = self._outputs(None, info=info or debug, debug=debug)
         last_of_round = cur + 1 >= self.active_ues
         if last_of_round:
+            self._before_steps(1)
             self._t += 1
             check(self._L.dcb_step(self._h, ctypes.c_void_p(a.data_ptr()), ctypes.byref(o), self._stream()))
         else:
@@ -423,13 +496,19 @@ class BatchedMobileEnv:
                     t1 += 1
                 acts = actions[t0:t1] if a0.data_ptr() == actions[t0].data_ptr() else \
                     torch.cat([a0[None], actions[t0 + 1:t1]]).contiguous()
+                self._before_steps(t1 - t0)
                 check(self._L.dcb_step_many(self._h, ctypes.c_void_p(acts.data_ptr()), t1 - t0,
                                             ctypes.byref(self._offset_outputs(o, t0)), self._stream()))
                 self._t += t1 - t0
                 t0 = t1
             return t
         self._t += T
-        check(self._L.dcb_step_many(self._h, ctypes.c_void_p(actions.data_ptr()), T, ctypes.byref(o), self._stream()))
+        L = T if self.auto_reset else self.episode_length
+        for t0 in range(0, T, L):                       # fragments longer than an episode: one launch per <= L steps
+            n = min(L, T - t0)
+            self._before_steps(n)
+            check(self._L.dcb_step_many(self._h, ctypes.c_void_p(actions[t0:t0 + n].data_ptr()), n,
+                                        ctypes.byref(o if t0 == 0 else self._offset_outputs(o, t0)), self._stream()))
         return t
 
     def _has_event(self, t):
@@ -456,6 +535,7 @@ class BatchedMobileEnv:
         from .agents import POLICY_KIND
         if self._dynamic:
             raise NotImplementedError("device-side policies with a variable UE population")
+        self._before_steps(int(T))
         self._t += T
         spec = policy.device_policy(self) if hasattr(policy, 'device_policy') else dict(policy)
         pol = DcbPolicy(kind=POLICY_KIND[spec['kind']], noop_interval=int(spec.get('noop_interval', 0)),
@@ -503,12 +583,20 @@ class BatchedMobileEnv:
         stream synchronise -- all inside the C-ABI call dcb_step_host.  `actions`: None (already written into
         pinned_buffers()['actions']) or an int array [K, N].
         """
-        if self._dynamic:
-            raise NotImplementedError("step_host with a variable UE population (use step with device tensors)")
-        self._t += 1
         pb = self.pinned_buffers()
         if actions is not None:
             pb['actions'].copy_(torch.as_tensor(np.asarray(actions, dtype=np.int32)))
+        if self._dynamic:
+            # arrivals / departures edit the action buffer on the device (base.py:429-443): host -> device, events + step,
+            # device -> the same pinned buffers
+            obs, rew, _, info = self.step(pb['actions'].to(self.device, non_blocking=True), info=False)
+            pb['obs'].copy_(obs, non_blocking=True)
+            pb['reward'].copy_(rew, non_blocking=True)
+            pb['lost_conn'].copy_(info['lost_conn'], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            return pb['obs'], pb['reward'], None, {'lost_conn': pb['lost_conn']}
+        self._before_steps(1)
+        self._t += 1
         check(self._L.dcb_step_host(self._h, ctypes.c_void_p(pb['actions'].data_ptr()),
                                     ctypes.c_void_p(pb['obs'].data_ptr()), ctypes.c_void_p(pb['reward'].data_ptr()),
                                     ctypes.c_void_p(pb['lost_conn'].data_ptr()), self._stream()))
@@ -532,6 +620,7 @@ class BatchedMobileEnv:
         if self._dynamic:
             raise NotImplementedError("step_many_host with a variable UE population (use step_many with device tensors)")
         T = int(bufs['actions'].shape[0]) if T is None else int(T)
+        self._before_steps(T)
         self._t += T
         check(self._L.dcb_step_many_host(self._h, ctypes.c_void_p(bufs['actions'].data_ptr()), T,
                                          ctypes.c_void_p(bufs['obs'].data_ptr()),

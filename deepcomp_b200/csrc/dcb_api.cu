@@ -112,6 +112,7 @@ struct dcb_env {
     int32_t *d_uid = nullptr;
     uint32_t *d_map_draws = nullptr, *d_glob_draws = nullptr;
     int na_reset = 0;        // UEs present after a reset (the original ue_list, base.py:176-182)
+    bool table_shifted = false;   // dcb_extend_waypoints moved some table rows past the start of their streams
     bool pop_used = false;   // the population has changed at least once: resets go through the re-seeding path from then on
     long long *d_ue_seed = nullptr;                      // per original UE: seed / draws consumed since that seeding
     uint32_t *d_ue_pos_used = nullptr, *d_ue_mv_used = nullptr;
@@ -538,6 +539,21 @@ int dcb_reset(dcb_env *env, const int32_t *host_env_ids, int32_t n, void *stream
         env->launches += 4;
     }
     env->p.NA = env->na_reset;
+    if (env->table_shifted && !env->cfg.rand_episodes && !env->pop_used) {
+        // the episode restarts the seeded streams (base.py:171-173): bring the table rows of the envs that reset back to
+        // the first draws
+        CU(dcb_launch_table_cursor(p.K, p.N, d_ids, n, env->d_mv, env->d_mv_skip, 1, s));
+        GenArgs g;
+        g.K = p.K; g.N = p.N; g.D = p.D; g.W = env->cfg.map_width; g.H = env->cfg.map_height;
+        g.border_buffer = env->cfg.border_buffer;
+        g.seeds = env->d_seeds; g.vel_spec = env->d_vel; g.init_xy = env->d_init_xy; g.uni_kind = env->d_uni_kind;
+        g.pos_skip = nullptr; g.mv_skip = nullptr; g.env_ids = d_ids; g.n_ids = n;
+        g.ue_seed = nullptr; g.ue_pos_skip = nullptr;
+        g.init_pos = env->d_init_pos; g.table = env->d_table;
+        CU(dcb_launch_generate(g, s));
+        env->launches += 2;
+        if (!host_env_ids) env->table_shifted = false;
+    }
     if (env->cfg.rand_episodes) {
         // base.py:171-173: no re-seed -> continue every UE's stream where the last episode left it
         CU(dcb_launch_advance_skip(p.K, p.N, d_ids, n, env->d_mv, env->d_mv_skip, env->d_pos_skip, s));
@@ -558,6 +574,36 @@ int dcb_reset(dcb_env *env, const int32_t *host_env_ids, int32_t n, void *stream
     CU(dcb_launch_reset(r, s));
     env->launches++;
     if (host_env_ids) CU(cudaStreamSynchronize(s));   // the id list is reused by the next partial reset
+    return DCB_OK;
+}
+
+int dcb_extend_waypoints(dcb_env *env, void *stream) {
+    if (!env) return fail(DCB_ERR_INVALID_ARG, "null handle");
+    if (env->cfg.auto_reset)
+        return fail(DCB_ERR_UNSUPPORTED, "auto_reset replays the seeded episode from the start of the table; it cannot be "
+                                         "combined with continuous stepping");
+    if (env->pop_used || env->p.NA < env->p.N)
+        return fail(DCB_ERR_UNSUPPORTED, "continuous stepping past episode_length with a variable UE population");
+    DeviceGuard guard(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const DevParams &p = env->p;
+    if (!env->d_mv_skip) {
+        CU(cudaMalloc((void **)&env->d_mv_skip, sizeof(uint32_t) * (size_t)p.K * p.N));
+        CU(cudaMemsetAsync(env->d_mv_skip, 0, sizeof(uint32_t) * (size_t)p.K * p.N, s));
+    }
+    CU(dcb_launch_table_cursor(p.K, p.N, nullptr, 0, env->d_mv, env->d_mv_skip, 0, s));
+    GenArgs g;
+    g.K = p.K; g.N = p.N; g.D = p.D; g.W = env->cfg.map_width; g.H = env->cfg.map_height;
+    g.border_buffer = env->cfg.border_buffer;
+    g.seeds = env->d_seeds; g.vel_spec = env->d_vel; g.init_xy = env->d_init_xy; g.uni_kind = env->d_uni_kind;
+    // (rand_episodes: the initial positions are re-derived for the episodes completed so far and overwritten by the next
+    // reset anyway)
+    g.pos_skip = env->cfg.rand_episodes ? env->d_pos_skip : nullptr; g.mv_skip = env->d_mv_skip;
+    g.env_ids = nullptr; g.n_ids = 0; g.ue_seed = nullptr; g.ue_pos_skip = nullptr;
+    g.init_pos = env->d_init_pos; g.table = env->d_table;
+    CU(dcb_launch_generate(g, s));
+    env->launches += 2;
+    env->table_shifted = true;
     return DCB_OK;
 }
 

@@ -162,7 +162,9 @@ __device__ __forceinline__ int policy_action(const PolicyParams &q, mask_t mask,
         return best_free + 1;                            // -1 + 1 = 0 = noop when linked to every BS
     mask_t selected = 0;
     if (q.kind == DCB_POLICY_DYNAMIC) {                  // heuristics.py:86-108: strongest BS and all within eps of it
-        const double thr = d2min * q.gain;
+        // epsilon = 0 selects every BS (heuristics.py:86-91: threshold 0); gain = inf there, and inf * 0 would be NaN for a
+        // UE sitting exactly on a BS
+        const double thr = isinf(q.gain) ? CUDART_INF : d2min * q.gain;
         for (int b = 0; b < M; b++)
             if (dist2(bsxy[b], x, y) <= thr) selected |= (mask_t)1 << b;
     } else {                                             // heuristics.py:169-187: the static cluster of the strongest BS

@@ -143,7 +143,7 @@ struct WideLayout {
     int off_tab, off_bsxy, off_share, off_vthr, off_xs, off_sx, off_sy, off_smask, off_su, off_srb, off_sew, off_smv,
         off_bits, off_fac,
         off_arg, off_cnt, off_usum, off_umin, off_fues, off_futil, off_env,
-        off_sdr, off_ssum, off_lsum, off_lbest, off_lcnt;   // general instance: curr_dr / interference sum per UE, raw link aggregates per BS
+        off_sdr, off_ssum, off_smax, off_sbmax, off_lsum, off_lbest, off_lcnt;   // general instance: curr_dr / interference sum per UE, raw link aggregates per BS
     int total;
 };
 
@@ -174,6 +174,8 @@ __host__ __device__ inline WideLayout dcb_wide_layout(int N, int M, int LC) {
     L.off_futil = o; o += align16(M * 4);
     L.off_sdr = o;   o += align16(N * 8);
     L.off_ssum = o;  o += align16(N * 8);
+    L.off_smax = o;  o += align16(N * 8);
+    L.off_sbmax = o; o += align16(N * 4);
     L.off_lsum = o;  o += align16(M * 8);
     L.off_lbest = o; o += align16(M * 8);
     L.off_lcnt = o;  o += align16(M * 4);
@@ -301,6 +303,8 @@ cudaError_t dcb_launch_iota_uid(int32_t *uid, int K, int N, cudaStream_t s);
 cudaError_t dcb_launch_reset(const ResetArgs &a, cudaStream_t s);
 cudaError_t dcb_launch_advance_skip(int K, int N, const int32_t *env_ids, int n_ids, const uint2 *mv,
                                     uint32_t *mv_skip, const uint32_t *pos_skip, cudaStream_t s);
+cudaError_t dcb_launch_table_cursor(int K, int N, const int32_t *env_ids, int n_ids, uint2 *mv, uint32_t *mv_skip, int mode,
+                                    cudaStream_t s);
 cudaError_t dcb_launch_step(const StepArgs &a, int threads, int grid, size_t smem, cudaStream_t s);
 cudaError_t dcb_step_set_smem_limit(int threads, int n_bs, size_t smem);
 cudaError_t dcb_launch_wide(const StepArgs &a, int threads, int grid, size_t smem, cudaStream_t s);

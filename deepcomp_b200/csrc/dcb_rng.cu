@@ -318,6 +318,32 @@ cudaError_t dcb_launch_advance_skip(int K, int N, const int32_t *env_ids, int n_
     return cudaGetLastError();
 }
 
+// Continuous stepping past episode_length (the reference's --cont-train / soft_horizon: `done` is never set, base.py:371-381):
+// the table row of UE u moves on to the entries from its cursor onwards.  mode 0: mv_skip[u] += cursor, cursor = 0 (then
+// regenerate with mv_skip); mode 1: mv_skip[u] = 0 for the listed envs (a reset goes back to the start of the stream).
+__global__ void __launch_bounds__(256) dcb_table_cursor_kernel(int K, int N, const int32_t *env_ids, int n_ids, uint2 *mv,
+                                                               uint32_t *mv_skip, int mode) {
+    const long long n_env = env_ids ? n_ids : K;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_env * N) return;
+    const int k = env_ids ? env_ids[t / N] : (int)(t / N);
+    const long long u = (long long)k * N + (t % N);
+    if (mode == 0) {
+        mv_skip[u] += mv[u].y >> 16;
+        mv[u].y &= 0xffffu;
+    } else {
+        mv_skip[u] = 0u;
+    }
+}
+
+cudaError_t dcb_launch_table_cursor(int K, int N, const int32_t *env_ids, int n_ids, uint2 *mv, uint32_t *mv_skip, int mode,
+                                    cudaStream_t s) {
+    const long long n = (long long)(env_ids ? n_ids : K) * N;
+    if (n == 0) return cudaSuccess;
+    dcb_table_cursor_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(K, N, env_ids, n_ids, mv, mv_skip, mode);
+    return cudaGetLastError();
+}
+
 cudaError_t dcb_launch_generate(const GenArgs &a, cudaStream_t s) {
     const long long n = (long long)(a.env_ids ? a.n_ids : a.K) * a.N;
     if (n == 0) return cudaSuccess;

@@ -43,14 +43,23 @@ struct WideSmem {
     double *env_red;   // [2] per-env reward / utility sum
     // general instance (EXT): data-rate observation classes and the interference extension
     double *sdr;       // [N] curr_dr after the move (user.py:64-69)
-    double *ssum;      // [N] sum over all BS of the SNR at the UE's position (interference extension)
+    // interference extension, per UE at its current position: the largest SNR over the base stations, which BS that is, and
+    // the sum of all the OTHER base stations' SNR (kept apart: a UE on top of a BS has snr ~ 1e52 there, which would absorb
+    // the rest of the sum)
+    double *ssum;      // [N] sum of the SNR over all BS but the strongest
+    double *smax;      // [N] SNR of the strongest BS
+    int *sbmax;        // [N] index of the strongest BS
     double *lsum, *lbest;  // [M] raw link aggregates of the current masks: sum of link values, largest unshared rate
     int *lcnt;         // [M] ... number of linked UEs
 };
 
 // Signal quality of one UE-BS pair: SNR (station.py:122-127) or, with the interference extension, SINR =
 // snr_b / (1 + sum_{b' != b} snr_b') with `tot` = the sum over ALL base stations at the UE's position
-__device__ __forceinline__ double pair_sinr(double snr, double tot) { return snr / (1.0 + (tot - snr)); }
+struct UeInterference { double rest, smax; int bmax; };
+__device__ __forceinline__ double pair_sinr(double snr, int b, const UeInterference &u) {
+    const double others = b == u.bmax ? u.rest : (u.rest - snr) + u.smax;
+    return snr / (1.0 + others);
+}
 
 __device__ __forceinline__ int rank_of(u64 mask, int b) { return __popcll(mask & (((u64)1 << b) - 1)); }
 
@@ -99,10 +108,20 @@ __device__ __forceinline__ void wide_interference_sums(const WideSmem &S, const 
     const double2 bs0 = ok0 ? S.bsxy[b0] : make_double2(0.0, 0.0), bs1 = ok1 ? S.bsxy[b1] : make_double2(0.0, 0.0);
     for (int r = warp; r < NA; r += nwarps) {
         const double rx = S.sx[r], ry = S.sy[r];
-        double v = ok0 ? snr_of_d2(p, S.tab, dist2(bs0, rx, ry)) : 0.0;
-        if (ok1) v += snr_of_d2(p, S.tab, dist2(bs1, rx, ry));
+        const double v0 = ok0 ? snr_of_d2(p, S.tab, dist2(bs0, rx, ry)) : 0.0;
+        const double v1 = ok1 ? snr_of_d2(p, S.tab, dist2(bs1, rx, ry)) : 0.0;
+        // strongest BS (first index on ties), then the sum of the others
+        double mx = v0;
+        int bm = b0;
+        if (v1 > mx) { mx = v1; bm = b1; }
+        for (int off = 16; off > 0; off >>= 1) {
+            const double om = __shfl_xor_sync(0xffffffffu, mx, off);
+            const int ob = __shfl_xor_sync(0xffffffffu, bm, off);
+            if (om > mx || (om == mx && ob < bm)) { mx = om; bm = ob; }
+        }
+        double v = (b0 == bm ? 0.0 : v0) + (b1 == bm ? 0.0 : v1);
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        if (lane == 0) S.ssum[r] = v;
+        if (lane == 0) { S.ssum[r] = v; S.smax[r] = mx; S.sbmax[r] = bm; }
     }
 }
 
@@ -199,6 +218,8 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
     S.env_red = reinterpret_cast<double *>(smem + L.off_env);
     S.sdr = reinterpret_cast<double *>(smem + L.off_sdr);
     S.ssum = reinterpret_cast<double *>(smem + L.off_ssum);
+    S.smax = reinterpret_cast<double *>(smem + L.off_smax);
+    S.sbmax = reinterpret_cast<int *>(smem + L.off_sbmax);
     S.lsum = reinterpret_cast<double *>(smem + L.off_lsum);
     S.lbest = reinterpret_cast<double *>(smem + L.off_lbest);
     S.lcnt = reinterpret_cast<int *>(smem + L.off_lcnt);
@@ -254,12 +275,18 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
         __syncthreads();
     }
     // in range (can_connect, station.py:222-226) and unshared rate (station.py:129-138) of one pair, SNR or SINR based
-    auto in_range = [&](double d2, double tot) -> bool {
-        if (interf) return pair_sinr(snr_of_d2(p, tab, d2), tot) > DCB_SNR_THRESHOLD;
+    auto ue_interf = [&](int r) -> UeInterference {
+        UeInterference q;
+        q.rest = 0.0; q.smax = 0.0; q.bmax = -1;
+        if (interf) { q.rest = S.ssum[r]; q.smax = S.smax[r]; q.bmax = S.sbmax[r]; }
+        return q;
+    };
+    auto in_range = [&](double d2, int b, const UeInterference &q) -> bool {
+        if (interf) return pair_sinr(snr_of_d2(p, tab, d2), b, q) > DCB_SNR_THRESHOLD;
         return d2 <= p.thr_d2;
     };
-    auto unshared_rate = [&](double d2, double tot) -> double {
-        if (interf) return DCB_BW * dcb_log2_1p(tab, pair_sinr(snr_of_d2(p, tab, d2), tot));
+    auto unshared_rate = [&](double d2, int b, const UeInterference &q) -> double {
+        if (interf) return DCB_BW * dcb_log2_1p(tab, pair_sinr(snr_of_d2(p, tab, d2), b, q));
         return rate_of_d2(p, tab, d2);
     };
 
@@ -305,7 +332,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                     const int b = act - 1;
                     const u64 bit = (u64)1 << b;
                     if (mask & bit) mask &= ~bit;
-                    else if (in_range(dist2(S.bsxy[b], x, y), interf ? S.ssum[i] : 0.0)) mask |= bit;   // can_connect, station.py:222-226
+                    else if (in_range(dist2(S.bsxy[b], x, y), b, ue_interf(i))) mask |= bit;   // can_connect, station.py:222-226
                 }
                 if (__popcll(mask) > LC) {          // cannot happen on a reachable state (LC bounds the BS in range)
                     atomicOr(p.err, DCB_ERRBIT_LINKS);
@@ -314,10 +341,10 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                 // ---- link values at the pre-move position (station.py:129-150)
                 const double iee = dcb_rcp(ewma + DCB_EPSILON);
                 int slot = 0;
-                const double tot0 = interf ? S.ssum[i] : 0.0;
+                const UeInterference tot0 = ue_interf(i);
                 for (u64 m = mask; m; m &= m - 1, slot++) {
                     const int b = __ffsll((long long)m) - 1;
-                    Xrow[slot] = link_value(S.share[b], unshared_rate(dist2(S.bsxy[b], x, y), tot0), iee);
+                    Xrow[slot] = link_value(S.share[b], unshared_rate(dist2(S.bsxy[b], x, y), b, tot0), iee);
                     atomicOr(&S.bits[b * NW + (i >> 5)], 1u << (i & 31));
                 }
                 S.smask[i] = mask;
@@ -353,12 +380,12 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                 __syncthreads();
             }
             if (valid && !no_move) {
-                const double tot1 = interf ? S.ssum[i] : 0.0;
+                const UeInterference tot1 = ue_interf(i);
                 double keep = 0.0;
                 int slot = 0;
                 for (u64 m = mask; m; m &= m - 1, slot++) {
                     const int b = __ffsll((long long)m) - 1;
-                    if (in_range(dist2(S.bsxy[b], x, y), tot1)) keep += Xrow[slot];
+                    if (in_range(dist2(S.bsxy[b], x, y), b, tot1)) keep += Xrow[slot];
                     else { mask &= ~((u64)1 << b); lost++; }
                 }
                 ewma = 0.9 * keep + (1 - 0.9) * ewma;
@@ -369,12 +396,12 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
         // ---- link values at the new position for update_ue_drs_rewards(update_only=True) (base.py:451)
         if (valid) {
             const double iee = dcb_rcp(ewma + DCB_EPSILON);
-            const double tot1 = interf ? S.ssum[i] : 0.0;
+            const UeInterference tot1 = ue_interf(i);
             int slot = 0;
             for (u64 m = mask; m; m &= m - 1, slot++) {
                 const int b = __ffsll((long long)m) - 1;
                 if (slot < LC) {
-                    Xrow[slot] = link_value(S.share[b], unshared_rate(dist2(S.bsxy[b], x, y), tot1), iee);
+                    Xrow[slot] = link_value(S.share[b], unshared_rate(dist2(S.bsxy[b], x, y), b, tot1), iee);
                     atomicOr(&S.bits[b * NW + (i >> 5)], 1u << (i & 31));
                 } else {
                     atomicOr(p.err, DCB_ERRBIT_LINKS);     // observe-only launch on an injected state with too many links
@@ -525,9 +552,9 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
             if (EXT && (p.obs_var || interf)) {
                 // ---- general instance: SINR-based quantities (interference extension) and / or the data-rate observation
                 // classes (NormDrMobileEnv / DatarateMobileEnv.get_ue_obs, variants.py:127-250; central layout)
-                const double tot = interf ? S.ssum[r] : 0.0;
-                const double q0 = ok0 ? (interf ? pair_sinr(snr_of_d2(p, tab, d20), tot) : snr_of_d2(p, tab, d20)) : 0.0;
-                const double q1 = ok1 ? (interf ? pair_sinr(snr_of_d2(p, tab, d21), tot) : snr_of_d2(p, tab, d21)) : 0.0;
+                const UeInterference tot = ue_interf(r);
+                const double q0 = ok0 ? (interf ? pair_sinr(snr_of_d2(p, tab, d20), b0, tot) : snr_of_d2(p, tab, d20)) : 0.0;
+                const double q1 = ok1 ? (interf ? pair_sinr(snr_of_d2(p, tab, d21), b1, tot) : snr_of_d2(p, tab, d21)) : 0.0;
                 const bool r0in = ok0 && (interf ? q0 > DCB_SNR_THRESHOLD : d20 <= p.thr_d2);
                 const bool r1in = ok1 && (interf ? q1 > DCB_SNR_THRESHOLD : d21 <= p.thr_d2);
                 const unsigned in0 = __ballot_sync(0xffffffffu, r0in), in1 = __ballot_sync(0xffffffffu, r1in);

@@ -78,6 +78,10 @@ class _MobileEnvFacade:
     metadata = {'render.modes': ['human']}
     _kind = None
     _obs_norm = 'rel'           # 'dr' normalisation: RelNormEnv (variants.py:276-284) / 'max' = MaxNormEnv (:308-332)
+    _obs_variant = None         # 'normdr' / 'datarate': the data-rate observation classes (variants.py:42-250)
+
+    def _obs_options(self):
+        return None
 
     def __init__(self, env_config):
         self.env_config = env_config
@@ -124,7 +128,8 @@ class _MobileEnvFacade:
             episode_length=sc['episode_length'], rand_episodes=sc['rand_episodes'], init_pos=sc['init_pos'],
             pause_duration=sc['pause_duration'], border_buffer=sc['border_buffer'], device=self._device,
             max_ues=sc['max_ues'], ue_arrival=sc['ue_arrival'], new_ue_interval=sc['new_ue_interval'],
-            util_func=sc['util_func'], dr_req=sc['dr_req'], obs_norm=self._obs_norm, uniform_moves=sc['uniform_moves'])
+            util_func=sc['util_func'], dr_req=sc['dr_req'], obs_norm=self._obs_norm, uniform_moves=sc['uniform_moves'],
+            obs_variant=self._obs_variant, obs_opts=self._obs_options(), interference=bool(self.env_config.get('interference', False)))
 
     # ---- MobileEnv attributes
     @property
@@ -136,10 +141,29 @@ class _MobileEnvFacade:
         return len(self.ue_list)
 
     def get_max_num_ue(self):
-        return self.num_ue
+        """base.py:191-209: the maximum number of UEs within an episode"""
+        max_ues = self.num_ue
+        if self.new_ue_interval is not None:
+            # "eps_length - 1 because time is increased before checking done and t=eps_length is never reached"
+            max_ues = self.num_ue + int((self.episode_length - 1) / self.new_ue_interval)
+        if self.ue_arrival is not None:
+            curr_ues = max_ues
+            for arrival in self.ue_arrival.values():
+                curr_ues += arrival
+                if curr_ues > max_ues:
+                    max_ues = curr_ues
+        return max_ues
 
     def get_num_diff_ues(self):
-        return self.num_ue
+        """base.py:211-225: the number of DIFFERENT UEs over an episode (env_setup.py:295 makes one policy per UE of it)"""
+        max_ues = self.get_max_num_ue()
+        if self.ue_arrival is None:
+            return max_ues
+        num_diff_ues = self.num_ue
+        for arrival in self.ue_arrival.values():
+            if arrival > 0:
+                num_diff_ues += arrival
+        return num_diff_ues
 
     def seed(self, seed=None):
         """
@@ -217,6 +241,7 @@ class _MobileEnvFacade:
 
     def _step_batch(self, per_ue_actions):
         obs, reward, _, info = self._batch.step(self._device_actions(per_ue_actions), info=True)
+        self._batch.check_errors()     # device-side flags (action range, waypoint table) raise here, not silently diverge
         if self._batch._dynamic:
             self._sync_ue_list()
         self.time += 1
@@ -283,6 +308,62 @@ class CentralMaxNormEnv(CentralRelNormEnv):
             'dr': spaces.Box(low=-1, high=1, shape=(n * m,)),
             'utility': spaces.Box(low=-1, high=1, shape=(n,)),
         })
+
+
+class _CentralVariantEnv(CentralRelNormEnv):
+    """central env whose observation is one of the data-rate classes: a dict of the keys present, each a Python list"""
+
+    def _obs_dict(self, flat):
+        out, o = {}, 0
+        for key, w in self._batch.obs_keys:
+            vals = flat[o:o + w]
+            out[key] = [int(v) for v in vals] if key in ('connected', 'ues_at_bs') else [float(v) for v in vals]
+            o += w
+        return out
+
+
+class CentralNormDrEnv(_CentralVariantEnv):
+    """Reference central.py:107-140 over NormDrMobileEnv (variants.py:173-250): every UE observes the shared rate it gets
+    or would get from every BS, cut at 100 and normalised; `dr_total` is its current total rate."""
+    _obs_variant = 'normdr'
+
+    def __init__(self, env_config):
+        super().__init__(env_config)
+        n, m = self.max_ues, self.num_bs
+        self.dr_cutoff = 100
+        self.observation_space = spaces.Dict({                                          # central.py:120-131
+            'dr': spaces.Box(low=0, high=1, shape=(n * m,)),
+            'connected': spaces.MultiBinary(n * m),
+            'dr_total': spaces.Box(low=0, high=1, shape=(n,)),
+        })
+
+
+class CentralDrEnv(_CentralVariantEnv):
+    """Reference central.py:75-104 over DatarateMobileEnv (variants.py:42-170); extra env_config keys: dr_cutoff ('auto' or
+    a number), sub_req_dr, curr_dr_obs, ues_at_bs_obs, dist_obs, next_dist_obs."""
+    _obs_variant = 'datarate'
+
+    def _obs_options(self):
+        ec = self.env_config
+        return {k: ec[k] for k in ('dr_cutoff', 'sub_req_dr', 'curr_dr_obs', 'ues_at_bs_obs', 'dist_obs', 'next_dist_obs')}
+
+    def __init__(self, env_config):
+        super().__init__(env_config)
+        n, m = self.max_ues, self.num_bs
+        o = self._batch.obs_opts
+        self.dr_cutoff, self.sub_req_dr = o['dr_cutoff'], o['sub_req_dr']
+        self.curr_dr_obs, self.ues_at_bs_obs = o['curr_dr_obs'], o['ues_at_bs_obs']
+        self.dist_obs, self.next_dist_obs = o['dist_obs'], o['next_dist_obs']
+        obs_space = {'dr': spaces.Box(low=-1, high=1, shape=(n * m,)), 'connected': spaces.MultiBinary(n * m)}   # central.py:88-92
+        if self.curr_dr_obs:
+            obs_space['dr_total'] = spaces.Box(low=-1, high=1, shape=(n,))
+        if self.ues_at_bs_obs:
+            obs_space['ues_at_bs'] = spaces.MultiDiscrete([n + 1 for _ in range(m)])
+        if self.dist_obs:
+            obs_space['dist'] = spaces.Box(low=0, high=1, shape=(n * m,))
+        if self.next_dist_obs:
+            obs_space['next_dist'] = spaces.Box(low=0, high=1, shape=(n * m,))
+        self.observation_space = spaces.Dict(obs_space)
 
 
 class MultiAgentMobileEnv(_MobileEnvFacade):

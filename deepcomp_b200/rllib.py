@@ -28,13 +28,13 @@ class _BatchAdapter:
         scenario = dict(scenario)
         scenario['kind'] = self.kind
         self.batch = BatchedMobileEnv(num_envs=num_envs, **scenario)
-        if self.batch._dynamic:
-            # agent ids differ per env once UEs arrive / leave (per-env draws of who leaves): use the K = 1 classes of
-            # deepcomp_b200.env, which track them, or BatchedMobileEnv with ue_ids() directly
-            raise NotImplementedError("batch adapters with a variable UE population")
+        # variable UE population (base.py:429-443, 592-617): the batch steps in lockstep, but WHO leaves is drawn per env,
+        # so the agent ids per slot differ between envs -- they are read back from the device after every event
+        self.dynamic = self.batch._dynamic
         self.num_envs = num_envs
         self.n_ue, self.n_bs = self.batch.n_ue, self.batch.n_bs
         self.agent_ids = [str(i + 1) for i in range(self.n_ue)]
+        self._ids = None            # dynamic: int array [K, active_ues] of User.id per slot
         self._obs = None
         # 'dr' is Box(0, 1) for the RelNorm observation, Box(-1, 1) for MaxNorm (variants.py:259, 313-317)
         self._dr_low = -1 if self.batch.obs_norm == 'max' else 0
@@ -47,6 +47,16 @@ class _BatchAdapter:
         m = self.n_bs
         return {'connected': row[:m].astype(np.int8), 'dr': row[m:2 * m], 'ues_at_bs': row[2 * m:3 * m],
                 'util_at_bs': row[3 * m:4 * m], 'utility': row[4 * m:]}
+
+    def _refresh_ids(self):
+        if self.dynamic:
+            self._ids = self.batch.ue_ids()
+
+    def _agents_of(self, k):
+        """agent ids (multi_agent.py:21-37: the UE ids as strings) of the UEs present in env k, in slot order"""
+        if not self.dynamic:
+            return self.agent_ids
+        return [str(int(i)) for i in self._ids[k]]
 
     def _info(self, k, info):
         return {'time': int(self._time[k]),
@@ -75,6 +85,8 @@ class CentralVectorEnv(_BatchAdapter):
         return [self._central_obs(obs[k]) for k in range(self.num_envs)]
 
     def reset_at(self, index=0):
+        if self.dynamic:
+            raise NotImplementedError("a batch with a variable UE population resets as a whole (vector_reset)")
         obs = self.batch.reset(env_ids=[index]).cpu().numpy()
         self._time[index] = 0
         self._obs = obs
@@ -111,12 +123,13 @@ class MultiAgentBaseEnv(_BatchAdapter):
         self._time = np.zeros(num_envs, dtype=np.int64)
         self._pending = None
         obs = self.batch.reset().cpu().numpy()
+        self._refresh_ids()
         self._pending = (self._obs_dicts(obs), {k: {} for k in range(num_envs)},
                          {k: {'__all__': None} for k in range(num_envs)}, {k: {} for k in range(num_envs)})
 
     def _obs_dicts(self, obs, only=None):
         ks = range(self.num_envs) if only is None else only
-        return {k: {aid: self._agent_obs(obs[k, i]) for i, aid in enumerate(self.agent_ids)} for k in ks}
+        return {k: {aid: self._agent_obs(obs[k, i]) for i, aid in enumerate(self._agents_of(k))} for k in ks}
 
     def poll(self):
         """-> (obs, rewards, dones, infos, off_policy_actions), each {env_id: {agent_id: value}}"""
@@ -129,22 +142,32 @@ class MultiAgentBaseEnv(_BatchAdapter):
         (multi_agent.py:21-30)"""
         a = np.zeros((self.num_envs, self.n_ue), dtype=np.int32)
         for k, acts in action_dict.items():
-            for aid, v in acts.items():
-                a[k, int(aid) - 1] = int(v)
+            if self.dynamic:
+                slot = {int(i): j for j, i in enumerate(self._ids[k])}
+                for aid, v in acts.items():
+                    if int(aid) in slot:                 # a UE that is not in the list does nothing (multi_agent.py:21-30)
+                        a[k, slot[int(aid)]] = int(v)
+            else:
+                for aid, v in acts.items():
+                    a[k, int(aid) - 1] = int(v)
         obs, rew, _, info = self.batch.step(torch.as_tensor(a, device=self.batch.device))
+        self._refresh_ids()                              # arrivals / departures of this step are in the returned dicts
         self.batch.check_errors()
         obs, rew = obs.cpu().numpy(), rew.cpu().numpy()
         info = {k: v.cpu().numpy() for k, v in info.items()}
         self._time += 1
         K = self.num_envs
-        rewards = {k: {aid: float(rew[k, i]) for i, aid in enumerate(self.agent_ids)} for k in range(K)}
-        dones = {k: dict({aid: None for aid in self.agent_ids}, __all__=None) for k in range(K)}
-        infos = {k: {aid: self._info(k, info) for aid in self.agent_ids} for k in range(K)}
+        rewards = {k: {aid: float(rew[k, i]) for i, aid in enumerate(self._agents_of(k))} for k in range(K)}
+        dones = {k: dict({aid: None for aid in self._agents_of(k)}, __all__=None) for k in range(K)}
+        infos = {k: {aid: self._info(k, info) for aid in self._agents_of(k)} for k in range(K)}
         self._pending = (self._obs_dicts(obs), rewards, dones, infos)
 
     def try_reset(self, env_id=None):
+        if self.dynamic and env_id is not None:
+            raise NotImplementedError("a batch with a variable UE population resets as a whole (try_reset(None))")
         ids = None if env_id is None else [env_id]
         obs = self.batch.reset(env_ids=ids).cpu().numpy()
+        self._refresh_ids()
         if env_id is None:
             self._time[:] = 0
             return self._obs_dicts(obs)

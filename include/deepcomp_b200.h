@@ -45,7 +45,7 @@ typedef enum dcb_status {
     DCB_ERR_UNSUPPORTED = -2,   /* shape outside what the kernels handle (see dcb_create) */
     DCB_ERR_CUDA = -3,
     DCB_ERR_ACTION_RANGE = -4,  /* an action outside [0, M] was seen on the device (base.py:238, central.py:61) */
-    DCB_ERR_TABLE_EXHAUSTED = -5 /* waypoint table ran dry: call dcb_reset or dcb_refill_waypoints */
+    DCB_ERR_TABLE_EXHAUSTED = -5 /* waypoint table ran dry: call dcb_reset or dcb_extend_waypoints in time */
 } dcb_status;
 
 /* deepcomp/util/env_setup.py:23-37: 'central' -> CentralRelNormEnv, 'multi' -> MultiAgentMobileEnv */
@@ -92,7 +92,9 @@ typedef struct dcb_config {
     int32_t map_height;
     int32_t episode_length;  /* env_config['episode_length']; sizes the waypoint table */
     int32_t rand_episodes;   /* env_config['rand_episodes'] (base.py:171-173): 0 = re-seed on every reset */
-    int32_t auto_reset;      /* 1: an env whose time reached episode_length resets before its next step */
+    int32_t auto_reset;      /* 1: an env whose time reached episode_length resets at the top of its next step (a benchmark
+                                convenience: the observation returned AT the boundary is the old episode's last one, the
+                                reset state itself is never observed -- learners should call dcb_reset + dcb_observe) */
     int32_t pause_duration;  /* RandomWaypoint(pause_duration=2) movement.py:87 */
     int32_t border_buffer;   /* RandomWaypoint(border_buffer=10) movement.py:87 */
     const double *host_bs_xy;     /* [M][2] BS positions (Basestation.pos) */
@@ -153,6 +155,15 @@ void dcb_destroy(dcb_env *env);
  * env_ids.  Re-seeds when rand_episodes == 0.  Follow with dcb_observe to get the first observation.
  */
 int dcb_reset(dcb_env *env, const int32_t *host_env_ids, int32_t n, void *stream);
+
+/*
+ * Continuous stepping past episode_length without a reset (the reference's --cont-train / soft_horizon; `done` is never
+ * set, base.py:371-381).  The pre-drawn waypoint table of a UE covers episode_length steps from the last dcb_reset /
+ * dcb_extend_waypoints; this call moves every UE's table row on to the draws from its cursor onwards (the per-UE MT19937
+ * streams simply continue, as random.Random does in the reference).  Call it at least every episode_length steps when not
+ * resetting (BatchedMobileEnv does).  Not with auto_reset or a variable UE population.  Asynchronous on `stream`.
+ */
+int dcb_extend_waypoints(dcb_env *env, void *stream);
 
 /*
  * Variable UE population (base.py:80-84 `max_ues`, central.py:46-55 zero padding): of the n_ue = max_ues slots of every

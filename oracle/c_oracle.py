@@ -41,6 +41,7 @@ def lib():
                                  ctypes.c_int]
         L.orc_destroy.argtypes = [ctypes.c_void_p]
         L.orc_set_variants.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int]
+        L.orc_set_interference.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.orc_reset.argtypes = [ctypes.c_void_p]
         L.orc_step.argtypes = [ctypes.c_void_p, ip]
         L.orc_obs_size.argtypes = [ctypes.c_void_p]
@@ -103,7 +104,8 @@ class COracleEnv:
 
     def __init__(self, kind, n_ue, bs_xy, map_wh, sharing='mixed', velocities='slow', seed=None, reward='avg',
                  episode_length=100, rand_episodes=False, init_pos=None, pause_duration=2, border_buffer=10,
-                 util_func='log', dr_req=1, obs_norm='rel'):
+                 util_func='log', dr_req=1, obs_norm='rel', interference=False):
+        """`interference`: EXTENSION, not in the reference (SNR only) -- this restatement is its only oracle."""
         assert util_func in ('log', 'step') and obs_norm in ('rel', 'max')
         self.L = lib()
         self.kind, self.n_ue, self.n_bs = kind, n_ue, len(bs_xy)
@@ -119,6 +121,8 @@ class COracleEnv:
         self.reward_size = self.L.orc_reward_size(self.h)
         if util_func != 'log' or obs_norm != 'rel':
             self.L.orc_set_variants(self.h, int(util_func == 'step'), float(dr_req), int(obs_norm == 'max'))
+        if interference:
+            self.L.orc_set_interference(self.h, 1)
 
     def __del__(self):
         try:

@@ -119,6 +119,8 @@ void orc_rng_draws(long long seed, int n_raw, uint32_t *raw, int n_int, const in
 /* ------------------------------------------------------------------------------------------------ env */
 typedef struct orc_env {
     int kind, n_ue, n_bs, width, height, reward_agg, rand_episodes, pause_duration, border_buffer, has_seed;
+    int interference;     /* EXTENSION (not in the reference, which is SNR only: station.py:122-127, docs/model.md:15-19):
+                             every use of the SNR sees SINR_b = snr_b / (1 + sum_{b' != b} snr_b') instead */
     int util_step;        /* User.util_func: 0 = 'log' (utility.py:36-54), 1 = 'step' (utility.py:23-33) */
     double dr_req;        /* User.dr_req (user.py:17-30) */
     int obs_maxnorm;      /* observation 'dr': 0 = RelNormEnv (variants.py:276-284), 1 = MaxNormEnv (variants.py:308-332) */
@@ -176,11 +178,26 @@ int orc_obs_size(const orc_env *e) {
 }
 int orc_reward_size(const orc_env *e) { return e->kind == KIND_CENTRAL ? 1 : e->n_ue; }
 
+/* signal quality of UE i at its current position towards every BS: SNR (station.py:122-127) or, with the interference
+ * extension, SINR = P_b / (noise + sum of the other BS' received powers) = snr_b / (1 + sum_{b' != b} snr_b') */
+static void ue_quality(const orc_env *e, int i, double *out) {
+    const int M = e->n_bs;
+    for (int b = 0; b < M; b++)
+        out[b] = snr_of_distance(e, dist(e->bs_xy[2 * b], e->bs_xy[2 * b + 1], e->pos[2 * i], e->pos[2 * i + 1]));
+    if (e->interference) {
+        double snr[64];
+        memcpy(snr, out, sizeof(double) * M);
+        for (int b = 0; b < M; b++) {
+            double others = 0;
+            for (int c = 0; c < M; c++)
+                if (c != b) others += snr[c];
+            out[b] = snr[b] / (1.0 + others);
+        }
+    }
+}
+
 static void compute_snr(orc_env *e) {
-    for (int i = 0; i < e->n_ue; i++)
-        for (int b = 0; b < e->n_bs; b++)
-            e->snr[i * e->n_bs + b] =
-                snr_of_distance(e, dist(e->bs_xy[2 * b], e->bs_xy[2 * b + 1], e->pos[2 * i], e->pos[2 * i + 1]));
+    for (int i = 0; i < e->n_ue; i++) ue_quality(e, i, e->snr + (size_t)i * e->n_bs);
 }
 
 /* station.py:129-220 over all connected links, user.py:143-146, 64-92; needs e->snr at the current positions */
@@ -374,6 +391,9 @@ void orc_set_variants(orc_env *e, int util_step, double dr_req, int obs_maxnorm)
     e->util_step = util_step; e->dr_req = dr_req; e->obs_maxnorm = obs_maxnorm;
 }
 
+/* interference extension on / off (takes effect with the next reset / step) */
+void orc_set_interference(orc_env *e, int on) { e->interference = on; }
+
 void orc_destroy(orc_env *e) {
     if (!e) return;
     free(e->bs_xy); free(e->sharing); free(e->vel_spec); free(e->init_xy); free(e->rng); free(e->mrng);
@@ -436,9 +456,11 @@ void orc_step(orc_env *e, const int *actions) {
         movement_step(e, i);
         int lost = 0;
         double dr = 0;
+        double q[64];
+        ue_quality(e, i, q);
         for (int b = 0; b < M; b++) {
             if (!e->mask[i * M + b]) continue;
-            double s = snr_of_distance(e, dist(e->bs_xy[2 * b], e->bs_xy[2 * b + 1], e->pos[2 * i], e->pos[2 * i + 1]));
+            double s = q[b];
             if (!(s > SNR_THRESHOLD)) { e->mask[i * M + b] = 0; lost++; }
             else dr += e->link_rate[i * M + b];
         }

@@ -1,4 +1,4 @@
-"""Instruction / stall-sample share per `// [region:NAME]` block of dcb_step.cu from an .ncu-rep.
+"""Instruction / stall-sample share per `// [region:NAME]` block of dcb_step_body.cuh from an .ncu-rep.
 
     python scripts/ncu_regions.py gpurun_out/prof.ncu-rep 'dcb_step_kernelILi768'
 """
@@ -23,7 +23,7 @@ def main():
     with contextlib.redirect_stdout(buf):
         h.main()
     lines = buf.getvalue().splitlines()
-    src = open(os.path.join(ROOT, 'deepcomp_b200', 'csrc', 'dcb_step.cu')).read().splitlines()
+    src = open(os.path.join(ROOT, 'deepcomp_b200', 'csrc', 'dcb_step_body.cuh')).read().splitlines()
     marks = [(i + 1, m.group(1)) for i, l in enumerate(src) for m in [re.search(r'\[region:([^\]]+)\]', l)] if m]
     agg = {}
     for ln in lines[1:]:
@@ -32,7 +32,7 @@ def main():
             continue
         pi, ps, f, l = float(m.group(1)), float(m.group(2)), m.group(3), int(m.group(4))
         key = f
-        if f == 'dcb_step.cu':
+        if f == 'dcb_step_body.cuh':
             key = 'layout'
             for start, name in marks:
                 if l >= start:

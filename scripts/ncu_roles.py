@@ -4,7 +4,7 @@ instructions per warp and step, the heaviest source lines and the stall-sample s
     python scripts/ncu_roles.py gpurun_out/prof.ncu-rep deepcomp_b200/libdeepcomp_b200.so 'dcb_step_kernelILi704ELb1' [T] [warps_per_group] [ctas]
 
 Roles are told apart by SASS address: everything after the first instruction attributed to the `[region:O.setup]`
-block of dcb_step.cu belongs to the observers, the shared prologue is reported on its own.
+block of dcb_step_body.cuh belongs to the observers, the shared prologue is reported on its own.
 """
 import csv
 import os
@@ -30,11 +30,11 @@ def main():
     ii, si = hdr.index('Instructions Executed'), hdr.index('# Samples')
     inst = [(int(r[ii]), int(r[si]), r[1]) for r in rows[h + 1:] if len(r) == len(hdr)]
     sl = H.sass_lines(lib, pat)
-    src = open(os.path.join(os.path.dirname(HERE), 'deepcomp_b200', 'csrc', 'dcb_step.cu')).read().splitlines()
+    src = open(os.path.join(os.path.dirname(HERE), 'deepcomp_b200', 'csrc', 'dcb_step_body.cuh')).read().splitlines()
     marks = [(i + 1, m.group(1)) for i, l in enumerate(src) for m in [re.search(r'\[region:([^\]]+)\]', l)] if m]
 
     def region(f, l):
-        if f != 'dcb_step.cu':
+        if f != 'dcb_step_body.cuh':
             return None
         key = None
         for start, name in marks:
@@ -60,7 +60,7 @@ def main():
               f'{n / (ctas * wpg * T):.0f} warp-instr per warp and step')
         for (f, l), (ni, sm) in sorted(lines[role].items(), key=lambda kv: -kv[1][0])[:int(os.environ.get('TOP', 25))]:
             text = ''
-            if f == 'dcb_step.cu' and l <= len(src):
+            if f == 'dcb_step_body.cuh' and l <= len(src):
                 text = src[l - 1].strip()[:90]
             print(f'   {ni / (ctas * wpg * T):6.1f}/ws {100 * sm / all_s:5.1f}% smp  {f}:{l}  {text}')
 

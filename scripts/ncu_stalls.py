@@ -23,11 +23,11 @@ def main():
     cols = [i for i, c in enumerate(hdr) if c.startswith('stall_') and 'Not Issued' not in c]
     body = [r for r in rows[h + 1:] if len(r) == len(hdr)]
     sl = H.sass_lines(lib, pat)
-    src = open(os.path.join(os.path.dirname(HERE), 'deepcomp_b200', 'csrc', 'dcb_step.cu')).read().splitlines()
+    src = open(os.path.join(os.path.dirname(HERE), 'deepcomp_b200', 'csrc', 'dcb_step_body.cuh')).read().splitlines()
     marks = [(i + 1, m.group(1)) for i, l in enumerate(src) for m in [re.search(r'\[region:([^\]]+)\]', l)] if m]
 
     def region(f, l):
-        if f != 'dcb_step.cu':
+        if f != 'dcb_step_body.cuh':
             return None
         key = None
         for start, name in marks:

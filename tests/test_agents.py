@@ -51,6 +51,17 @@ def test_host_agents_reproduce_reference_actions(name):
             t += 1
 
 
+@pytest.mark.parametrize('name', [n for n in POLICY_CASES if 'fixed' not in n])
+def test_batched_agents_reproduce_reference_actions(name):
+    """compute_actions over the packed observation of all UEs (and of a stack of steps) at once == the reference's agents"""
+    cfg, z = load_golden(name)
+    agent = make_agent(cfg)
+    obs = np.concatenate([z['reset_obs'][:1], z['step_obs'][:cfg['steps'] - 1]])       # obs seen before each action
+    got = agent.compute_actions(obs).numpy()
+    assert np.array_equal(got, z['actions'][:cfg['steps']])
+    assert np.array_equal(agent.compute_actions(obs[3]).numpy(), z['actions'][3])
+
+
 @pytest.mark.parametrize('name', [n for n in POLICY_CASES if 'static' in n])
 def test_static_clusters_match_reference(name):
     """build_clusters (heuristics.py:132-167) with the same seeded random.Random picks the same clusters"""

@@ -127,6 +127,36 @@ def test_gym_facades_with_arriving_and_departing_ues(name):
     env.close()
 
 
+@pytest.mark.parametrize('name', ['normdr_central_mixed', 'datarate_central_auto_all', 'datarate_central_cutoff200'])
+def test_central_datarate_facades_replay_reference_traces(name):
+    """CentralNormDrEnv / CentralDrEnv (central.py:75-140) with the reference's env_config keys and obs dict keys"""
+    from deepcomp_b200.env import CentralDrEnv, CentralNormDrEnv
+    from deepcomp_b200.entities import User
+    cfg, z = load_golden(name)
+    ec = _env_config_from_golden(cfg)
+    if cfg.get('util_func'):
+        ec['ue_list'] = [User(u.id, u.map, u.init_pos_x, u.init_pos_y, u.movement, util_func=cfg['util_func']) for u in ec['ue_list']]
+    cls = CentralNormDrEnv
+    if cfg['obs_variant'] == 'datarate':
+        cls = CentralDrEnv
+        opts = dict(dr_cutoff='auto', sub_req_dr=True, curr_dr_obs=False, ues_at_bs_obs=False, dist_obs=False,
+                    next_dist_obs=False)
+        opts.update(cfg['obs_opts'])
+        ec.update(opts)
+    env = cls(ec)
+    obs = env.reset()
+    flat = np.concatenate([np.asarray(obs[k], dtype=np.float64) for k in sorted(obs)])
+    assert_close(flat, z['reset_obs'][0], 'reset obs', 2e-6, 1e-6)
+    assert set(obs) == set(env.observation_space.spaces)
+    for t in range(cfg['steps']):
+        obs, reward, done, info = env.step(z['actions'][t].astype(np.int64))
+        flat = np.concatenate([np.asarray(obs[k], dtype=np.float64) for k in sorted(obs)])
+        assert_close(flat, z['step_obs'][t], f'obs[{t}]', 2e-6, 1e-6)
+        assert_close(reward, z['step_reward'][t], f'reward[{t}]', 2e-6, 1e-6)
+        assert done is None
+    env.close()
+
+
 def test_central_maxnorm_facade_replays_reference_trace():
     """CentralMaxNormEnv (multi_ue/central.py:155-164 over MaxNormEnv, single_ue/variants.py:308-332): same step, the
     observation entry 'dr' is the capped, threshold-shifted SNR -- Box(-1, 1), negative where the BS is out of range."""
@@ -285,13 +315,62 @@ def test_auto_reset_replays_the_seeded_episode():
 
 
 def test_stepping_past_the_waypoint_table_is_reported():
+    """the raw C-ABI path (no host bookkeeping): a launch that runs past the pre-drawn waypoints sets the sticky flag"""
+    import ctypes
     from deepcomp_b200 import BatchedMobileEnv
     sc = _scenario(6, 2, episode_length=4, velocities='fast')
     sc['map_wh'], sc['bs_xy'] = (120, 120), [(30, 30), (90, 90)]
     env = BatchedMobileEnv(num_envs=3, kind='multi', seed=0, **sc)
     env.reset()
-    env.step_many(torch.zeros((400, 3, 6), dtype=torch.int32, device='cuda'), obs=False)
+    a = torch.zeros((400, 3, 6), dtype=torch.int32, device='cuda')
+    assert env._L.dcb_step_many(env._h, ctypes.c_void_p(a.data_ptr()), 400, None, env._stream()) == 0
     with pytest.raises(RuntimeError, match='waypoints'):
+        env.check_errors()
+
+
+@pytest.mark.parametrize('wide', [False, True], ids=['fused', 'wide'])
+@pytest.mark.parametrize('rand_episodes', [False, True])
+def test_continuous_stepping_past_episode_length_matches_the_oracle(rand_episodes, wide, monkeypatch):
+    """--cont-train / soft_horizon in the reference: no reset at episode_length, `done` is never set (base.py:371-381),
+    every UE's random.Random simply keeps drawing.  The waypoint tables are extended on the device
+    (dcb_extend_waypoints); positions / masks / movement state stay bit-exact for 10 episode lengths, single steps and
+    fragments, and a later reset() restarts (or, with rand_episodes, continues) the streams like the oracle."""
+    from deepcomp_b200 import BatchedMobileEnv, env_seeds
+    if wide:
+        monkeypatch.setenv('DCB_FORCE_WIDE', '1')
+    K, N, M, L = 3, 6, 2, 12
+    sc = _scenario(N, M, episode_length=L, velocities='fast')
+    sc['map_wh'], sc['bs_xy'] = (120, 120), [(30, 30), (90, 90)]
+    seeds = env_seeds(5, K, N)
+    env = BatchedMobileEnv(num_envs=K, kind='multi', seeds=seeds, rand_episodes=rand_episodes, **sc)
+    orcs = [c_oracle.COracleEnv('multi', seed=int(sd), rand_episodes=rand_episodes, **sc) for sd in seeds]
+    rng = np.random.default_rng(3)
+
+    def check(what):
+        st = env.get_state()
+        for k, o in enumerate(orcs):
+            w = o._trace(True)
+            assert_exact(st['pos'][k], w['pos'], what + '.pos')
+            assert_exact(env.mask_matrix(st['mask'])[k], w['mask'], what + '.mask')
+            assert_exact(st['movement'][k], w['movement'], what + '.movement')
+
+    for episode in range(2):
+        env.reset()
+        for o in orcs:
+            o.reset_trace()
+        for t in range(5 * L):                                         # single steps
+            a = rng.integers(0, M + 1, (K, N)).astype(np.int32)
+            obs, rew, _, info = env.step(torch.as_tensor(a, device='cuda'))
+            for k, o in enumerate(orcs):
+                w = o.step(a[k])
+                assert_close(rew[k].cpu().numpy(), w['reward'], f'ep{episode}.reward[{t}]', 2e-6, 1e-6)
+            check(f'ep{episode}.step[{t}]')
+        a = rng.integers(0, M + 1, (5 * L, K, N)).astype(np.int32)     # one fragment request of 5 episode lengths
+        env.step_many(torch.as_tensor(a, device='cuda'))
+        for k, o in enumerate(orcs):
+            for t in range(5 * L):
+                o.step(a[t, k])
+        check(f'ep{episode}.fragment')
         env.check_errors()
 
 
@@ -396,6 +475,83 @@ def test_rllib_vector_and_base_env_adapters():
         assert_close([rew[k][aid] for aid in b.agent_ids], w['reward'], 'ma reward', 2e-6, 1e-6)
         assert dones[k]['__all__'] is None
     b.stop()
+
+
+@pytest.mark.parametrize('name', ['pop_largeupdown_multi_avg', 'pop_3up2down_central_sum'])
+def test_rllib_adapters_with_arriving_and_departing_ues(name):
+    """Variable UE population through the batch adapters (base.py:429-443, 592-617; multi_agent.py:21-37): the batch steps
+    in lockstep, but which UE leaves is drawn per env, so every env has its own agent-id map -- checked per env against
+    the Python oracle (bit-identical to the reference on the pop_* traces; env 0 IS the reference's trace)."""
+    from oracle.deepcomp_oracle import OracleEnv
+    from deepcomp_b200.rllib import CentralVectorEnv, MultiAgentBaseEnv
+    from helpers import population_kwargs
+    cfg, z = load_golden(name)
+    kw = dict(helpers_oracle_kwargs(cfg), **population_kwargs(cfg))
+    kind, seed = kw.pop('kind'), kw.pop('seed')
+    K, S, M = 3, cfg['max_ues'], len(cfg['bs_xy'])
+    seeds = [seed, seed + 100000, seed + 200000]
+    orcs = [OracleEnv(kind, seed=sd, **kw) for sd in seeds]
+    wants = [o.reset_trace() for o in orcs]
+    if kind == 'central':
+        v = CentralVectorEnv(K, seeds=seeds, **kw)
+        obs = v.vector_reset()
+        for t in range(cfg['steps']):
+            a = np.stack([z['actions'][t]] * K)
+            obs, rew, dones, infos = v.vector_step(list(a))
+            for k, o in enumerate(orcs):
+                w = o.step(a[k])
+                got = np.concatenate([obs[k][key] for key in sorted(obs[k])])
+                assert_close(got, w['obs'], f'obs[{t}].env{k}', 2e-6, 1e-6)
+                assert_close(rew[k], w['reward'], f'reward[{t}].env{k}', 2e-6, 1e-5)
+            assert_close(np.concatenate([obs[0][key] for key in sorted(obs[0])]), z['step_obs'][t], 'trace', 2e-6, 1e-6)
+        with pytest.raises(NotImplementedError):
+            v.reset_at(1)
+        v.close()
+        return
+    b = MultiAgentBaseEnv(K, seeds=seeds, **kw)
+    obs, _, _, _, _ = b.poll()
+    differ = False
+    for t in range(cfg['steps']):
+        ids_before = [[ue.id for ue in o.ues] for o in orcs]
+        for k in range(K):
+            assert list(obs[k]) == ids_before[k], (t, k)
+        a = z['actions'][t]
+        b.send_actions({k: {aid: int(a[i]) for i, aid in enumerate(ids_before[k])} for k in range(K)})
+        obs, rew, dones, infos, _ = b.poll()
+        for k, o in enumerate(orcs):
+            w = o.step(a)
+            ids = [ue.id for ue in o.ues]
+            assert list(obs[k]) == list(rew[k]) == ids and set(dones[k]) == set(ids) | {'__all__'}
+            got = np.zeros((S, 4 * M + 1))
+            r = np.zeros(S)
+            for i, aid in enumerate(ids):
+                got[i] = np.concatenate([obs[k][aid][key] for key in sorted(obs[k][aid])])
+                r[i] = rew[k][aid]
+            assert_close(got, w['obs'], f'obs[{t}].env{k}', 2e-6, 1e-6)
+            assert_close(r, w['reward'], f'reward[{t}].env{k}', 2e-6, 1e-5)
+            assert infos[k][ids[0]]['time'] == t + 1
+        differ |= [ue.id for ue in orcs[0].ues] != [ue.id for ue in orcs[1].ues]
+    assert differ                     # the envs drew different departures: their agent-id maps really are per env
+    with pytest.raises(NotImplementedError):
+        b.try_reset(1)
+    obs = b.try_reset()
+    assert list(obs[2]) == [str(i + 1) for i in range(cfg['n_ue'])]
+    b.stop()
+
+
+def test_step_host_with_a_variable_population_equals_device_step():
+    from deepcomp_b200 import BatchedMobileEnv
+    W, H, bs = grid_layout(5)
+    kw = dict(num_envs=4, n_ue=3, max_ues=8, bs_xy=bs, map_wh=(W, H), kind='multi', seed=11, episode_length=30,
+              ue_arrival={2: 2, 5: -1, 9: 3, 12: -2})
+    a, b = BatchedMobileEnv(**kw), BatchedMobileEnv(**kw)
+    a.reset(); b.reset()
+    acts = _actions(20, 4, 8, 5, seed=2)
+    for t in range(20):
+        ho, hr, _, hi = a.step_host(acts[t].cpu().numpy())
+        do, dr, _, di = b.step(acts[t])
+        assert torch.equal(ho, do.cpu()) and torch.equal(hr, dr.cpu()) and torch.equal(hi['lost_conn'], di['lost_conn'].cpu())
+    assert a.active_ues == b.active_ues == 5
 
 
 # ------------------------------------------------------------------------------------------------ full-size properties

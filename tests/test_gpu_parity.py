@@ -53,15 +53,20 @@ def compare_step(env, dbg, want, k, what, step=True, num_ue=None):
     assert_close(dbg['dbg_curr_dr'][k].cpu().numpy(), want['curr_dr'], f'{what}.curr_dr', RTOL, ATOL)
     assert_close(dbg['dbg_utility'][k].cpu().numpy(), want['utility'], f'{what}.utility', RTOL, ATOL)
     n_ue, n_bs = want['mask'].shape
-    # MaxNormEnv's 'dr' (variants.py:308-332) crosses zero at the connection threshold: absolute floor there
-    dr_atol = 1e-9 if env.obs_norm == 'max' else 1e-30
-    w_rest, w_dr = split_dr(want['obs'], n_ue, n_bs)
-    g_rest, g_dr = split_dr(dbg['dbg_obs'][k].cpu().numpy(), n_ue, n_bs)
-    assert_close(g_rest, w_rest, f'{what}.obs64', RTOL, ATOL)
-    assert_close(g_dr, w_dr, f'{what}.obs64.dr', RTOL_DR, dr_atol)
-    g_rest, g_dr = split_dr(dbg['obs'][k].cpu().numpy(), n_ue, n_bs)
-    assert_close(g_rest, w_rest, f'{what}.obs32', RTOL32, ATOL32)
-    assert_close(g_dr, w_dr, f'{what}.obs32.dr', RTOL_DR, dr_atol)
+    if env.obs_variant is not None:
+        # data-rate observation classes: every entry is fp64 on the device (tap) and rounded once (production output)
+        assert_close(dbg['dbg_obs'][k].cpu().numpy(), want['obs'], f'{what}.obs64', RTOL, ATOL)
+        assert_close(dbg['obs'][k].cpu().numpy(), want['obs'], f'{what}.obs32', RTOL32, ATOL32)
+    else:
+        # MaxNormEnv's 'dr' (variants.py:308-332) crosses zero at the connection threshold: absolute floor there
+        dr_atol = 1e-9 if env.obs_norm == 'max' else 1e-30
+        w_rest, w_dr = split_dr(want['obs'], n_ue, n_bs)
+        g_rest, g_dr = split_dr(dbg['dbg_obs'][k].cpu().numpy(), n_ue, n_bs)
+        assert_close(g_rest, w_rest, f'{what}.obs64', RTOL, ATOL)
+        assert_close(g_dr, w_dr, f'{what}.obs64.dr', RTOL_DR, dr_atol)
+        g_rest, g_dr = split_dr(dbg['obs'][k].cpu().numpy(), n_ue, n_bs)
+        assert_close(g_rest, w_rest, f'{what}.obs32', RTOL32, ATOL32)
+        assert_close(g_dr, w_dr, f'{what}.obs32.dr', RTOL_DR, dr_atol)
     if step:
         assert_exact(dbg['lost_conn'][k].cpu().numpy().astype(np.int32), want['lost_conn'], f'{what}.lost_conn')
         assert st['time'][k] == want['time']
@@ -121,6 +126,31 @@ def test_cuda_variable_population_matches_reference_golden(name, wide, monkeypat
             assert env.active_ues == int(z['step_num_ue'][t]), (name, t)
             compare_step(env, dbg, {k: z['step_' + k][t] for k in step_keys}, 0, f'{name}.step[{t}]',
                          num_ue=env.active_ues)
+            t += 1
+    env.check_errors()
+
+
+@pytest.mark.parametrize('name', pending_obs_names())
+def test_cuda_datarate_observation_classes_match_reference_golden(name):
+    """CentralNormDrEnv / CentralDrEnv (central.py:75-140, variants.py:42-250): the shared rate every UE gets or would get
+    from every BS, all env_config options of the data-rate class (auto / numeric cut-off, required-rate subtraction, total
+    rate, UEs per BS, distances now and after the next step), every recorded array of the reference's traces.  These
+    handles run on the one-CTA-per-env kernel whatever their shape."""
+    cfg, z = load_golden(name)
+    env = make_env(oracle_kwargs(cfg))
+    assert env.kernel_name == 'dcb_wide_kernel' and env.obs_size == z['step_obs'].shape[1]
+    t = 0
+    for ep in range(cfg['episodes']):
+        dbg = env.reset(debug=True)
+        want = {k: z['reset_' + k][ep] for k in ('pos', 'mask', 'movement', 'ewma', 'snr', 'link_rates', 'curr_dr',
+                                                 'utility', 'obs')}
+        compare_step(env, dbg, want, 0, f'{name}.reset[{ep}]', step=False)
+        for _ in range(cfg['steps']):
+            a = torch.as_tensor(z['actions'][t][None, :].astype(np.int32), device='cuda')
+            dbg = env.step(a, debug=True)
+            want = {k: z['step_' + k][t] for k in ('pos', 'mask', 'movement', 'ewma', 'snr', 'link_rates', 'curr_dr',
+                                                   'utility', 'obs', 'lost_conn', 'time', 'reward', 'sum_utility')}
+            compare_step(env, dbg, want, 0, f'{name}.step[{t}]')
             t += 1
     env.check_errors()
 
@@ -246,6 +276,46 @@ def test_wide_kernel_matches_c_oracle(kind, n_ue, n_bs, K, steps, force, monkeyp
         dbg = env.step(torch.as_tensor(a, device='cuda'), debug=True)
         for k, o in enumerate(orcs):
             compare_step(env, dbg, o.step(a[k]), k, f'step[{t}].env{k}')
+    env.check_errors()
+
+
+@pytest.mark.parametrize('kind', ['central', 'multi'])
+@pytest.mark.parametrize('n_ue,n_bs,K,near', [(20, 10, 3, False), (12, 5, 2, True), (300, 40, 2, False)])
+def test_interference_extension_matches_c_restatement(kind, n_ue, n_bs, K, near):
+    """EXTENSION, not parity-graded against the reference (which is SNR only, station.py:122-127): SINR_b = snr_b / (1 +
+    sum of the other base stations' snr) everywhere the SNR is used -- against its only oracle, the C restatement.
+    `near`: some UEs sit on top of / within a metre of a base station, where the interference term is not ~1e-8 but
+    dominates every other link of that UE."""
+    from deepcomp_b200 import env_seeds
+    W, H, bs = c_oracle_grid(n_bs)
+    seeds = env_seeds(77, K, n_ue)
+    init_pos = None
+    velocities = 'slow'
+    if near:
+        init_pos = [(bs[0][0], bs[0][1]), (bs[1][0] + 0.25, bs[1][1]), (bs[2][0], bs[2][1] - 0.9)] + \
+            [('random', 'random')] * (n_ue - 3)
+        velocities = [0, 0, 0] + ['slow'] * (n_ue - 3)
+    kw = dict(kind=kind, n_ue=n_ue, bs_xy=bs, map_wh=(W, H), sharing='mixed', velocities=velocities, reward='avg',
+              episode_length=30, init_pos=init_pos)
+    env = make_env(dict(kw, seed=0), num_envs=K, seeds=seeds, interference=True)
+    assert env.kernel_name == 'dcb_wide_kernel'
+    orcs = [c_oracle.COracleEnv(seed=int(s), interference=True, **kw) for s in seeds]
+    plain = c_oracle.COracleEnv(seed=int(seeds[0]), **kw)
+    dbg = env.reset(debug=True)
+    for k, o in enumerate(orcs):
+        compare_step(env, dbg, o.reset_trace(), k, f'reset.env{k}', step=False)
+    plain.reset_trace()
+    rng = np.random.default_rng(6)
+    differs = 0.0
+    for t in range(30):
+        a = rng.integers(0, n_bs + 1, (K, n_ue)).astype(np.int32)
+        dbg = env.step(torch.as_tensor(a, device='cuda'), debug=True)
+        for k, o in enumerate(orcs):
+            w = o.step(a[k])
+            compare_step(env, dbg, w, k, f'step[{t}].env{k}')
+            if k == 0:
+                differs = max(differs, float(np.max(np.abs(w['snr'] / plain.step(a[0])['snr'] - 1.0))))
+    assert differs > 1e-9          # the extension is not a no-op: the SINR differs from the SNR beyond the parity bar
     env.check_errors()
 
 
