@@ -130,17 +130,27 @@ __device__ __forceinline__ void reduce_links(int tid, int gsize, const double *X
                 c0 += __popc(wa);
                 c1 += __popc(wb);
                 unsigned both = wa | wb;
+                const int ibase = (w << 5) + sh;
                 while (both) {
+                    // two UEs per trip: both loads are in flight before the (ordered) accumulation
                     const int j = __ffs(both) - 1;
                     both &= both - 1;
-                    const int i = (w << 5) + sh + j;
-                    const double v = col[i * MS];
+                    const bool two = both != 0u;
+                    const int j2 = two ? __ffs(both) - 1 : j;
+                    both &= both - 1;
+                    const double v = col[(ibase + j) * MS];
+                    const double v2 = col[(ibase + j2) * MS];
                     const bool ina = (wa >> j) & 1u, inb = (wb >> j) & 1u;
+                    const bool ina2 = two && ((wa >> j2) & 1u), inb2 = two && ((wb >> j2) & 1u);
                     if (ina) s0 += v;
                     if (inb) s1 += v;
+                    if (ina2) s0 += v2;
+                    if (inb2) s1 += v2;
                     if (want_arg) {               // max-cap only (station.py:184): first arg-max
-                        if (ina && v > b0) { b0 = v; a0 = i; }
-                        if (inb && v > b1) { b1 = v; a1 = i; }
+                        if (ina && v > b0) { b0 = v; a0 = ibase + j; }
+                        if (inb && v > b1) { b1 = v; a1 = ibase + j; }
+                        if (ina2 && v2 > b0) { b0 = v2; a0 = ibase + j2; }
+                        if (inb2 && v2 > b1) { b1 = v2; a1 = ibase + j2; }
                     }
                 }
             }
@@ -227,7 +237,9 @@ __device__ __forceinline__ double warp_reduce_env(int lane, const double *v, int
 // PAD: the general instance -- the envs may have padding slots (NA < N, variable UE population) and the observation may be
 // a per-handle variant (MaxNorm); the common fixed-population RelNorm case compiles without the extra compares, the
 // padding branch of the observers and the variant branch
-template <int MAXT, bool M32, bool PAD>
+// CENTRAL: observation / reward layout of the central agent (central.py:31-73) instead of the per-UE multi-agent one
+// (multi_agent.py:32-95) -- a compile-time choice: it selects offsets, store paths and reward code all over the observers
+template <int MAXT, bool M32, bool PAD, bool CENTRAL>
 __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
     using mask_t = typename MaskType<M32>::type;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -273,8 +285,8 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
     const bool valid = PAD ? (in_cta && i < NA) : in_cta;
     const int k = env0 + le;
     const long long u = (long long)k * N + i;
-    const bool central = p.kind == DCB_KIND_CENTRAL;
-    const int OW = obs_width(p.kind, M);
+    constexpr bool central = CENTRAL;
+    const int OW = central ? 2 * M + 1 : 4 * M + 1;
     const int T = a.T;
     const int n_iter = T > 0 ? T : 1;
 
@@ -331,6 +343,9 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
         double rb_next = 0.0;     // the next step's reward before the move (base.py:446)
         // ... which only the central reward (central.py:65-73) and the multi-agent 'sum' reward (multi_agent.py:79-86) read
         const bool need_rb = central || p.reward == DCB_REWARD_SUM;
+        // this UE's action of the current step (running pointer: no 64-bit index arithmetic per step)
+        const size_t act_stride = (size_t)p.K * N;
+        const int32_t *act_row = a.actions ? a.actions + u : nullptr;
         bool any_fresh = true;    // some env of this CTA starts the step without inherited aggregates (CTA-uniform)
         int rot = 0;              // step % 3: the post-move UE bitsets rotate over three buffers (see the clear below)
 
@@ -344,7 +359,8 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
             int lost = 0;
             // next step's action: issued now so that the global-load latency hides behind this step's work
             int act_next = 0;
-            if (valid && T > 0 && !last && !a.pol.kind) act_next = a.actions[(size_t)(step + 1) * p.K * N + u];
+            if (valid && T > 0 && !last && !a.pol.kind) act_next = act_row[act_stride];
+            act_row += act_stride;                     // -> actions of step + 1
 // [region:P.top+fresh]
             // the observers must be done with this parity's hand-off buffers (step - 2)
             if (step >= 2) bar_sync(BAR_EMPTY + par, 2 * G);
@@ -370,7 +386,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                                 act = policy_action<mask_t>(a.pol, mask, x, y, bsxy, M, i, a.pol.call0 + step, u);
                                 if (a.actions_out) a.actions_out[(size_t)step * p.K * N + u] = act;
                             } else {
-                                act = a.actions[(size_t)step * p.K * N + u];
+                                act = *(act_row - act_stride);          // act_row already points at step + 1
                             }
                             if (act < 0 || act > M) {
                                 atomicOr(p.err, DCB_ERRBIT_ACTION);
@@ -608,12 +624,21 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
         const bool want_env_rew = central && T > 0;
         const bool want_env_sumu = a.out.sum_utility || a.out.dbg_sum_utility;
         int orot = 0;                                 // step % 3 (the physics warps' rotating post bitsets)
+        // production outputs of the current step as running pointers (no 64-bit index arithmetic per step)
+        float *obs_step = a.out.obs ? a.out.obs + (size_t)env0 * per_env : nullptr;
+        float *rew_step = a.out.reward ? a.out.reward + (central ? (long long)k : u) : nullptr;
+        uint8_t *lost_step = a.out.lost_conn ? a.out.lost_conn + u : nullptr;
 
         for (int step = 0; step < n_iter; step++) {
             const bool last = step == n_iter - 1;
             const int par = step & 1;
             const int hbase = par * EN;
-            float *dst = a.out.obs ? a.out.obs + (size_t)step * a.out.obs_stride + (size_t)env0 * per_env : nullptr;
+            float *dst = obs_step;
+            float *rew_dst = rew_step;
+            uint8_t *lost_dst = lost_step;
+            if (obs_step) obs_step += a.out.obs_stride;
+            if (rew_step) rew_step += a.out.reward_stride;
+            if (lost_step) lost_step += a.out.lost_conn_stride;
             const unsigned mis = (unsigned)((size_t)dst & 15);
             float *tile = stage + (mis >> 2);
             float *row_conn = tile + row_off;
@@ -735,13 +760,13 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                     if (last && a.out.dbg_sum_utility) a.out.dbg_sum_utility[k] = env_sumu_v;
                 }
                 if (T > 0) {
-                    if (a.out.lost_conn) a.out.lost_conn[(size_t)step * a.out.lost_conn_stride + u] = (uint8_t)hlost[h];
+                    if (lost_dst) *lost_dst = (uint8_t)hlost[h];
                     if (central) {
                         if (i == 0) {
                             // central.py:65-73 over the PRE-move rewards
                             double r = env_rew_v;
                             if (p.reward == DCB_REWARD_AVG) r = r / (double)NA;
-                            if (a.out.reward) a.out.reward[(size_t)step * a.out.reward_stride + k] = (float)r;
+                            if (rew_dst) *rew_dst = (float)r;
                             if (last && a.out.dbg_reward) a.out.dbg_reward[k] = r;
                         }
                     } else {
@@ -769,7 +794,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                                 }
                             }
                         }
-                        if (a.out.reward) a.out.reward[(size_t)step * a.out.reward_stride + u] = (float)agg;
+                        if (rew_dst) *rew_dst = (float)agg;
                         if (last && a.out.dbg_reward) a.out.dbg_reward[u] = agg;
                     }
                 }
@@ -785,8 +810,8 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                 if (a.out.curr_dr) a.out.curr_dr[(size_t)step * a.out.curr_dr_stride + u] = 0.0f;
                 if (a.out.utility) a.out.utility[(size_t)step * a.out.utility_stride + u] = 0.0f;
                 if (T > 0) {
-                    if (a.out.lost_conn) a.out.lost_conn[(size_t)step * a.out.lost_conn_stride + u] = 0;
-                    if (!central && a.out.reward) a.out.reward[(size_t)step * a.out.reward_stride + u] = 0.0f;
+                    if (lost_dst) *lost_dst = 0;
+                    if (!central && rew_dst) *rew_dst = 0.0f;
                 }
                 if (last) {
                     if (a.out.dbg_curr_dr) a.out.dbg_curr_dr[u] = 0.0;
@@ -868,9 +893,9 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
 // this file; the classes compile in parallel).  Register budget per class so that one CTA of that size (three of the
 // smallest) is always resident: 65536 registers / (warps rounded up to a multiple of 4 x 32), in the allocation granule
 // of 8 registers per thread (88 registers x 704 threads does not launch: warps are allocated in fours).
-template <bool M32, bool PAD>
+template <bool M32, bool PAD, bool CENTRAL>
 __global__ void __maxnreg__(DCB_STEP_REGS) DCB_STEP_KERNEL_NAME(const __grid_constant__ StepArgs a) {
-    dcb_step_body<DCB_STEP_CLASS, M32, PAD>(a);
+    dcb_step_body<DCB_STEP_CLASS, M32, PAD, CENTRAL>(a);
 }
 
 }  // namespace
@@ -884,34 +909,41 @@ extern "C" int dcb_trace_read_cta(long long *out) {
 }
 #endif
 
-#define DCB_DISPATCH(m32, pad, EXPR)                                                                \
+#define DCB_DISPATCH3(M32V, PADV, central, EXPR)                                                    \
+    do {                                                                                            \
+        if (central) { auto kern = DCB_STEP_KERNEL_NAME<M32V, PADV, true>; EXPR; }                  \
+        else { auto kern = DCB_STEP_KERNEL_NAME<M32V, PADV, false>; EXPR; }                         \
+    } while (0)
+#define DCB_DISPATCH(m32, pad, central, EXPR)                                                       \
     do {                                                                                            \
         if (m32) {                                                                                  \
-            if (pad) { auto kern = DCB_STEP_KERNEL_NAME<true, true>; EXPR; }                        \
-            else { auto kern = DCB_STEP_KERNEL_NAME<true, false>; EXPR; }                           \
+            if (pad) DCB_DISPATCH3(true, true, central, EXPR);                                      \
+            else DCB_DISPATCH3(true, false, central, EXPR);                                         \
         } else {                                                                                    \
-            if (pad) { auto kern = DCB_STEP_KERNEL_NAME<false, true>; EXPR; }                       \
-            else { auto kern = DCB_STEP_KERNEL_NAME<false, false>; EXPR; }                          \
+            if (pad) DCB_DISPATCH3(false, true, central, EXPR);                                     \
+            else DCB_DISPATCH3(false, false, central, EXPR);                                        \
         }                                                                                           \
     } while (0)
 
 cudaError_t DCB_STEP_CLASS_FN(set_smem)(int n_bs, size_t smem) {
     cudaError_t e = cudaSuccess;
-    for (int pad = 0; pad < 2 && e == cudaSuccess; pad++)
-        DCB_DISPATCH(n_bs <= 32, pad, e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int v = 0; v < 4 && e == cudaSuccess; v++)
+        DCB_DISPATCH(n_bs <= 32, v & 1, v >> 1,
+                     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return e;
 }
 
 int DCB_STEP_CLASS_FN(regs)(int n_bs) {
     cudaFuncAttributes at;
     cudaError_t e = cudaSuccess;
-    DCB_DISPATCH(n_bs <= 32, false, e = cudaFuncGetAttributes(&at, kern));
+    DCB_DISPATCH(n_bs <= 32, false, false, e = cudaFuncGetAttributes(&at, kern));
     return e == cudaSuccess ? at.numRegs : 128;
 }
 
 cudaError_t DCB_STEP_CLASS_FN(launch)(const StepArgs &a, int threads, int grid, size_t smem, cudaStream_t s) {
     // the general instance (PAD) also carries the per-handle variants; the fixed-population RelNorm case -- the measured
     // path -- compiles without them
-    DCB_DISPATCH(a.p.M <= 32, dcb_step_needs_general(a.p, a.flags), (kern<<<grid, threads, smem, s>>>(a)));
+    DCB_DISPATCH(a.p.M <= 32, dcb_step_needs_general(a.p, a.flags), a.p.kind == DCB_KIND_CENTRAL,
+                 (kern<<<grid, threads, smem, s>>>(a)));
     return cudaGetLastError();
 }
