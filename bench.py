@@ -44,14 +44,21 @@ def grid_layout(n_bs, pitch=100, border=10):
     return width, height, [(border + pitch * (b % cols), border + pitch * (b // cols)) for b in range(n_bs)]
 
 
+def obs_floats_per_step(args):
+    N, M, K = args.n_ue, args.n_bs, args.envs
+    return K * (N * (4 * M + 1) if args.kind == 'multi' else 2 * N * M + N)
+
+
 def effective_fragment(args):
-    """steps per launch: a rollout fragment, never longer than the timed region or an episode"""
-    return max(1, min(args.fragment, args.steps, args.episode_length))
+    """steps per launch: a rollout fragment, never longer than the timed region or an episode, and small enough for
+    its observation buffer to stay under 24 GiB (large env batches)"""
+    by_memory = max(1, int((24 << 30) // (obs_floats_per_step(args) * 4)))
+    return max(1, min(args.fragment, args.steps, args.episode_length, by_memory))
 
 
 def workload_config(args, n_gpus):
     N, M, K = args.n_ue, args.n_bs, args.envs
-    obs_floats = K * (N * (4 * M + 1) if args.kind == 'multi' else 2 * N * M + N)
+    obs_floats = obs_floats_per_step(args)
     return {
         "workload": f"{N} UE x {M} BS x {K} envs/GPU ({K * n_gpus} total), "
                     f"{'MultiAgentMobileEnv' if args.kind == 'multi' else 'CentralRelNormEnv'}, {args.sharing} "
@@ -146,7 +153,7 @@ def reference_arm(args):
               f"(N_UE={args.n_ue}, M_BS={args.n_bs}) workload, oracle port of the reference's Python env, {elapsed:.1f} s")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -300,7 +307,7 @@ def gpu_arm(args):
     pin_to_gpu_numa_node(local_rank)
     env = BatchedMobileEnv(num_envs=K, n_ue=N, bs_xy=bs, map_wh=(W, H), kind=args.kind, sharing=args.sharing,
                            velocities='slow', seed=args.seed, reward='avg', episode_length=L, device=dev,
-                           first_env=rank * K)
+                           first_env=rank * K, interference=args.interference)
     R = args.reps
     per_rep = args.warmup + args.steps
     preroll = args.preroll
@@ -441,7 +448,7 @@ def gpu_arm(args):
     #     compute, one synchronise per fragment; (2) dcb_step_host: one synchronous round trip per step;
     # (3) the PCIe ceiling of the same run: a plain cudaMemcpyAsync of one fragment's outputs to the same pinned buffers.
     e2e_steps = max(args.e2e_steps, 1)
-    FE = max(1, min(args.e2e_fragment, L, e2e_steps))
+    FE = max(1, min(args.e2e_fragment, L, e2e_steps, int((1 << 30) // (obs_floats_per_step(args) * 4)) or 1))
     e2e_steps = (e2e_steps + FE - 1) // FE * FE
     fb = env.pinned_fragment_buffers(FE)
     host_actions = actions[:min(e2e_steps, n_act)].cpu().numpy()
@@ -546,9 +553,12 @@ def gpu_arm(args):
                            f"repetition, per repetition the slowest rank")}
     if args.policy:
         cfg["actions"] = f"on-device scripted policy '{args.policy}' (dcb_rollout), closed loop"
+    if args.interference:
+        cfg["interference"] = ("EXTENSION, not parity-graded: SINR = P_b / (noise + sum of the other base stations' received "
+                               "power) instead of the reference's SNR (station.py:122-127); oracle = oracle/dcb_oracle.c")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "run": run_info, "rep_ms": rep_ms_all, "gpu_launches_all_reps": int(sum(r[3] for r in rep_events)),
@@ -574,6 +584,8 @@ def main():
     ap.add_argument('--n-ue', type=int, default=50)
     ap.add_argument('--n-bs', type=int, default=10)
     ap.add_argument('--envs', type=int, default=1024, help='envs per GPU (weak scaling)')
+    ap.add_argument('--total-envs', type=int, default=None,
+                    help='strong scaling: this many envs in total, split evenly over the GPUs (overrides --envs)')
     ap.add_argument('--kind', default='multi', choices=['multi', 'central'])
     ap.add_argument('--sharing', default='mixed')
     ap.add_argument('--episode-length', type=int, default=100)
@@ -585,11 +597,18 @@ def main():
     ap.add_argument('--preroll', type=int, default=200, help='untimed steps queued ahead of the first repetition')
     ap.add_argument('--cpu-steps', type=int, default=300, help='steps per core for the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--interference', action='store_true',
+                    help='EXTENSION, not in the reference and not parity-graded: SINR with the per-UE interference sum '
+                         '(BASELINE.json configs[3]); runs on the one-CTA-per-env kernel')
     ap.add_argument('--policy', default=None, choices=['3gpp', 'fullcomp', 'dynamic', 'random'],
                     help='drive the envs with an on-device baseline policy instead of pre-generated random actions')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    args.scaling = 'weak'
+    if args.total_envs is not None:
+        args.envs = max(1, args.total_envs // max(1, args.gpus))
+        args.scaling = 'strong' 
     if args.impl == 'reference':
         reference_arm(args)
     else:

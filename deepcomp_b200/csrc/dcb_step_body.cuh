@@ -197,15 +197,33 @@ __device__ __forceinline__ void warp_reduce_utility(int lane, const unsigned *bi
         const double *sue = su + le * N;
         double s = 0.0, mn = DCB_MAX_UTILITY;
         int c = 0;
-        for (int w = 0; w < NW; w++) {
-            unsigned wa = pb[w];
-            c += __popc(wa);
-            while (wa) {
-                const int j = __ffs(wa) - 1;
-                wa &= wa - 1;
-                const double uu = sue[(w << 5) + j];
-                s += uu;
-                if (want_min) mn = uu < mn ? uu : mn;
+        if (want_min) {
+            for (int w = 0; w < NW; w++) {
+                unsigned wa = pb[w];
+                c += __popc(wa);
+                while (wa) {
+                    const int j = __ffs(wa) - 1;
+                    wa &= wa - 1;
+                    const double uu = sue[(w << 5) + j];
+                    s += uu;
+                    mn = uu < mn ? uu : mn;
+                }
+            }
+        } else {
+            for (int w = 0; w < NW; w++) {
+                unsigned wa = pb[w];
+                c += __popc(wa);
+                while (wa) {
+                    // two UEs per trip: both loads in flight before the (ordered) additions
+                    const int j = __ffs(wa) - 1;
+                    wa &= wa - 1;
+                    const bool two = wa != 0u;
+                    const int j2 = two ? __ffs(wa) - 1 : j;
+                    wa &= wa - 1;
+                    const double uu = sue[(w << 5) + j], uu2 = sue[(w << 5) + j2];
+                    s += uu;
+                    if (two) s += uu2;
+                }
             }
         }
         cnt[q] = c;

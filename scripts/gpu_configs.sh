@@ -7,6 +7,7 @@ run() { name=$1; shift; timeout 600 python bench.py --no-cpu-baseline "$@" > gpu
 run cfg3 --n-ue 200 --n-bs 20 --envs 512 --fragment 50 --steps 1000 --warmup 100 --e2e-steps 10
 run cfg4 --n-ue 1000 --n-bs 50 --envs 1024 --fragment 10 --steps 100 --warmup 20 --e2e-steps 3
 run cfg4c --n-ue 1000 --n-bs 50 --envs 1024 --fragment 10 --steps 100 --warmup 20 --e2e-steps 3 --kind central
-for k in 256 4096 16384 65536; do
-  run k$k --envs $k --fragment 25 --steps $(( k > 8192 ? 200 : 2000 )) --warmup $(( k > 8192 ? 50 : 200 )) --e2e-steps 3
-done
+# config 4 with the interference extension (SINR; not in the reference, not parity-graded)
+run cfg4i --n-ue 1000 --n-bs 50 --envs 1024 --fragment 10 --steps 100 --warmup 20 --e2e-steps 3 --interference
+run cfg3c --n-ue 200 --n-bs 20 --envs 512 --fragment 50 --steps 1000 --warmup 100 --e2e-steps 10 --kind central
+run central --kind central --steps 3000 --warmup 300 --e2e-steps 50
