@@ -304,7 +304,7 @@ def gpu_arm(args):
     # steps per launch: a rollout fragment; never longer than the timed region itself
     F = effective_fragment(args)
     W, H, bs = grid_layout(M)
-    pin_to_gpu_numa_node(local_rank)
+    numa_node = pin_to_gpu_numa_node(local_rank)
     env = BatchedMobileEnv(num_envs=K, n_ue=N, bs_xy=bs, map_wh=(W, H), kind=args.kind, sharing=args.sharing,
                            velocities='slow', seed=args.seed, reward='avg', episode_length=L, device=dev,
                            first_env=rank * K, interference=args.interference)
@@ -337,20 +337,28 @@ def gpu_arm(args):
         policy_spec = {'3gpp': dict(kind='3gpp'), 'fullcomp': dict(kind='fullcomp'),
                        'dynamic': dict(kind='dynamic', epsilon=0.5), 'random': dict(kind='random', seed=0)}[args.policy]
 
-    def run(fragments, events=None):
+    def run(fragments, events=None, first=None):
+        """events: list that receives (start event, end event, n steps) per step-kernel launch.  The events form a chain --
+        the end of one launch is the start of the next (`first` = the repetition's own start event), a reset in between
+        gets its own marker -- so a K-step region of one launch carries two event records, not four."""
+        last = first
         for (s, n, reset) in fragments:
             if reset:
                 env.reset()          # MobileEnv.reset incl. the first observation, as the reference loop does
-            if events is not None:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
+                last = None
+            if events is not None and last is None:
+                last = torch.cuda.Event(enable_timing=True)
+                last.record()
             if args.policy:
                 env.rollout(policy_spec, n, out=bufs[n])          # closed loop on the device, no actions tensor
             else:
                 env.step_many(actions[s:s + n], out=bufs[n])
             if events is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
                 e1.record()
-                events.append((e0, e1, n))
+                events.append((last, e1, n))
+                last = e1
+        return last
 
     # the whole schedule up front: pre-roll, then R repetitions of [W warm-up steps (untimed), K timed steps]
     pos, t_env = 0, 0
@@ -385,11 +393,10 @@ def gpu_arm(args):
     for warm, timed in reps:
         run(warm)
         events = []
-        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_start = torch.cuda.Event(enable_timing=True)
         l0 = env.launch_count
         t_start.record()
-        run(timed, events)
-        t_end.record()
+        t_end = run(timed, events, first=t_start)       # the end event of the last timed launch closes the region
         rep_events.append((t_start, t_end, events, env.launch_count - l0))
     torch.cuda.synchronize(dev)
     if world > 1:
@@ -451,15 +458,18 @@ def gpu_arm(args):
     FE = max(1, min(args.e2e_fragment, L, e2e_steps, int((1 << 30) // (obs_floats_per_step(args) * 4)) or 1))
     e2e_steps = (e2e_steps + FE - 1) // FE * FE
     fb = env.pinned_fragment_buffers(FE)
-    host_actions = actions[:min(e2e_steps, n_act)].cpu().numpy()
+    # the action log lives in pinned host memory (the caller's buffer is handed to the C ABI as it is)
+    n_host = (min(e2e_steps, n_act) // FE) * FE or FE
+    host_actions_t = actions[:n_host].cpu().pin_memory()
+    host_actions = host_actions_t.numpy()
 
     def e2e_pass(n_steps):
         t_e = 0
         for s in range(0, n_steps, FE):
             if t_e >= L:
                 env.reset(); t_e = 0
-            np.copyto(fb['actions'].numpy(), host_actions[s % len(host_actions):][:FE])
-            env.step_many_host(fb)
+            o = s % n_host
+            env.step_many_host(fb, actions=host_actions_t[o:o + FE])
             t_e += FE
 
     env.reset()
@@ -477,12 +487,12 @@ def gpu_arm(args):
     pb = env.pinned_buffers()
     env.reset()
     for s in range(3):
-        env.step_host(host_actions[s])
+        env.step_host(host_actions[s % n_host])
     env.reset()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     for s in range(sync_steps):
-        np.copyto(pb['actions'].numpy(), host_actions[s])
+        np.copyto(pb["actions"].numpy(), host_actions[s % n_host])
         env.step_host(None)
     torch.cuda.synchronize(dev)
     sync_s = time.perf_counter() - t0
@@ -516,6 +526,7 @@ def gpu_arm(args):
            "pcie_ceiling": {"value": ceiling, "unit": UNIT, "d2h_GBps_per_gpu": d2h_step * n_copy * FE / copy_s / 1e9,
                             "how": "cudaMemcpyAsync device -> the same pinned buffers, same bytes, no kernel"},
            "frac_of_pcie_ceiling": (world * K * e2e_steps / e2e_s) / ceiling,
+           "host_numa_node_rank0": numa_node,
            "per_step_sync": {"value": world * K * sync_steps / sync_s, "unit": UNIT, "steps": sync_steps,
                              "api": "BatchedMobileEnv.step_host -> dcb_step_host (one H2D + step + D2H + synchronise per step)"}}
     env.check_errors()

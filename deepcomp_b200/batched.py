@@ -611,18 +611,22 @@ class BatchedMobileEnv:
             reward=torch.empty((T, K) + self.reward_shape, dtype=torch.float32).pin_memory(),
             lost_conn=torch.empty((T, K, N), dtype=torch.uint8).pin_memory())
 
-    def step_many_host(self, bufs, T=None, chunk_steps=0):
+    def step_many_host(self, bufs, T=None, chunk_steps=0, actions=None):
         """
         T steps through HOST memory in one C-ABI call (dcb_step_many_host): `bufs` = pinned_fragment_buffers(T) with
-        bufs['actions'] filled in; the steps run in chunks whose device -> host copies overlap the next chunk's compute,
-        one synchronise at the end.  Returns (obs, reward, None, {'lost_conn'}) as [T, ...] host tensors.
+        bufs['actions'] filled in (or `actions`: any pinned int32 host tensor [T, K, N], e.g. a slice of a larger action
+        log); the steps run in chunks whose device -> host copies overlap the next chunk's compute, one synchronise at the
+        end.  Returns (obs, reward, None, {'lost_conn'}) as [T, ...] host tensors.
         """
         if self._dynamic:
             raise NotImplementedError("step_many_host with a variable UE population (use step_many with device tensors)")
-        T = int(bufs['actions'].shape[0]) if T is None else int(T)
+        acts = bufs['actions'] if actions is None else actions
+        if not (acts.dtype == torch.int32 and acts.is_contiguous() and not acts.is_cuda):
+            raise ValueError("actions must be a contiguous int32 host tensor [T, K, N]")
+        T = int(acts.shape[0]) if T is None else int(T)
         self._before_steps(T)
         self._t += T
-        check(self._L.dcb_step_many_host(self._h, ctypes.c_void_p(bufs['actions'].data_ptr()), T,
+        check(self._L.dcb_step_many_host(self._h, ctypes.c_void_p(acts.data_ptr()), T,
                                          ctypes.c_void_p(bufs['obs'].data_ptr()),
                                          ctypes.c_void_p(bufs['reward'].data_ptr()),
                                          ctypes.c_void_p(bufs['lost_conn'].data_ptr()), int(chunk_steps), self._stream()))

@@ -935,7 +935,10 @@ int dcb_step_many_host(dcb_env *env, const int32_t *h_actions, int32_t T, float 
     const size_t KN = (size_t)p.K * p.N;
     const size_t n_obs = (size_t)p.K * dcb_obs_size(env), n_rew = (size_t)p.K * dcb_reward_size(env);
     const size_t step_bytes = n_obs * 4 + n_rew * 4 + KN;
-    int C = chunk_steps > 0 ? chunk_steps : (int)((16u << 20) / step_bytes);
+    // default: ~64 MB chunks (the two small copies per chunk -- reward, lost_conn -- then cost a few per cent of the chunk's
+    // transfer time), but at least three chunks per call so that only the first chunk's kernel is exposed
+    int C = chunk_steps > 0 ? chunk_steps : (int)((64u << 20) / step_bytes);
+    if (chunk_steps <= 0 && C > (T + 2) / 3) C = (T + 2) / 3;
     if (C < 1) C = 1;
     if (C > T) C = T;
     if (!env->hm_copy_stream) {

@@ -353,6 +353,18 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
             wide_reduce_links<EXT>(S, N, M, NW, LC, p.has_maxcap, warp, lane, nwarps);
             __syncthreads();
             for (int j = tid; j < M * NW; j += blockDim.x) S.bits[j] = 0u;
+            // check_bs_connection (user.py:175-188) + update_ewma_dr (user.py:148-157) at the new position
+            auto drop_links = [&]() {
+                const UeInterference tot1 = ue_interf(i);
+                double keep = 0.0;
+                int slot = 0;
+                for (u64 m = mask; m; m &= m - 1, slot++) {
+                    const int b = __ffsll((long long)m) - 1;
+                    if (in_range(dist2(S.bsxy[b], x, y), b, tot1)) keep += Xrow[slot];
+                    else { mask &= ~((u64)1 << b); lost++; }
+                }
+                ewma = 0.9 * keep + (1 - 0.9) * ewma;
+            };
             if (valid) {
                 // ---- update_ue_drs_rewards (base.py:315-335): shared rate of every connected link -> ue.bs_dr cache
                 // (back into the slots), calc_reward (base.py:158-167; penalties are identically 0, base.py:257)
@@ -370,6 +382,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                 if (!no_move) {
                     if (ukx) ue_move_uniform(p, ukx, uky, uvx, uvy, x, y, wxy, vpt);
                     else ue_move<false>(p, u, vfix, vfix_thr, S.vthr, x, y, wxy, vpt, nullptr);
+                    if (!interf) drop_links();          // (same basic block as the move in the plain instances)
                 }
             }
             if (interf && !no_move) {
@@ -378,17 +391,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                 __syncthreads();
                 wide_interference_sums(S, p, NA, M, warp, lane, nwarps);
                 __syncthreads();
-            }
-            if (valid && !no_move) {
-                const UeInterference tot1 = ue_interf(i);
-                double keep = 0.0;
-                int slot = 0;
-                for (u64 m = mask; m; m &= m - 1, slot++) {
-                    const int b = __ffsll((long long)m) - 1;
-                    if (in_range(dist2(S.bsxy[b], x, y), b, tot1)) keep += Xrow[slot];
-                    else { mask &= ~((u64)1 << b); lost++; }
-                }
-                ewma = 0.9 * keep + (1 - 0.9) * ewma;
+                if (valid) drop_links();
             }
             if (!no_move) tk += 1;                                                     // base.py:454
             __syncthreads();      // bits cleared, slots of the pre-move pass consumed
@@ -474,10 +477,11 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
         const double2 bs0 = ok0 ? S.bsxy[b0] : make_double2(0.0, 0.0), bs1 = ok1 ? S.bsxy[b1] : make_double2(0.0, 0.0);
         float fu0 = 0.0f, fu1 = 0.0f, fa0 = 0.0f, fa1 = 0.0f;
         int cn0 = 0, cn1 = 0;
-        double us0 = 0.0, us1 = 0.0, um0 = CUDART_INF, um1 = CUDART_INF;
+        double us0 = 0.0, us1 = 0.0;
         if (!central) {
-            if (ok0) { fu0 = S.f_ues[b0]; fa0 = S.f_util[b0]; cn0 = S.cnt_obs[b0]; us0 = S.usum[b0]; um0 = S.umin[b0]; }
-            if (ok1) { fu1 = S.f_ues[b1]; fa1 = S.f_util[b1]; cn1 = S.cnt_obs[b1]; us1 = S.usum[b1]; um1 = S.umin[b1]; }
+            // (the per-BS minima of the 'min' reward are read where they are used: four registers less across the row loop)
+            if (ok0) { fu0 = S.f_ues[b0]; fa0 = S.f_util[b0]; cn0 = S.cnt_obs[b0]; us0 = S.usum[b0]; }
+            if (ok1) { fu1 = S.f_ues[b1]; fa1 = S.f_util[b1]; cn1 = S.cnt_obs[b1]; us1 = S.usum[b1]; }
         }
         // this lane's output cursor: column b0 of the env's first row; the four (multi) / two (central) segments of a
         // row are fixed byte offsets from it, the second pass (b1 = b0 + 32) is +128 bytes on the same addresses
@@ -684,8 +688,8 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                                 if (S.smask[j] & rmask) sacc += S.srb[j];
                             agg = warp_sum(sacc);
                         } else {
-                            double mn = i0 ? um0 : CUDART_INF;
-                            if (i1) mn = um1 < mn ? um1 : mn;
+                            double mn = i0 ? S.umin[b0] : CUDART_INF;
+                            if (i1) { const double um1 = S.umin[b1]; mn = um1 < mn ? um1 : mn; }
                             mn = warp_min(mn);
                             agg = mn < agg ? mn : agg;
                         }
@@ -782,8 +786,8 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                         agg = warp_sum(s);
                     } else {
                         const bool i0 = (in0 >> lane) & 1u, i1 = (in1 >> lane) & 1u;
-                        double mn = i0 ? um0 : CUDART_INF;
-                        if (i1) mn = um1 < mn ? um1 : mn;
+                        double mn = i0 ? S.umin[b0] : CUDART_INF;
+                        if (i1) { const double um1 = S.umin[b1]; mn = um1 < mn ? um1 : mn; }
                         mn = warp_min(mn);
                         agg = mn < agg ? mn : agg;
                     }

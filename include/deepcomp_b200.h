@@ -295,7 +295,8 @@ int dcb_step_host(dcb_env *env, const int32_t *h_actions, float *h_obs, float *h
  * chunk c's obs / reward / lost_conn travel to h_obs [T][...] / h_reward [T][...] / h_lost_conn [T][K][N] on a second
  * (library-owned) copy stream.  ONE stream synchronise at the end: the call returns when every output is in host memory.
  * PCIe-bound for every shape (the device produces 8.4 MB of observations per 5.6 us step at the headline shape), so
- * pinned host buffers are required for the overlap; NULL outputs are skipped.  chunk_steps <= 0 picks ~16 MB chunks.
+ * pinned host buffers are required for the overlap; NULL outputs are skipped.  chunk_steps <= 0 picks ~64 MB chunks (at
+ * least three per call).
  */
 int dcb_step_many_host(dcb_env *env, const int32_t *h_actions, int32_t T, float *h_obs, float *h_reward,
                        uint8_t *h_lost_conn, int32_t chunk_steps, void *stream);

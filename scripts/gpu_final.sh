@@ -15,7 +15,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --c
 # wide kernel at config 4
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:dcb_step_kernel -s 5 -c 1 -o $O/prof_$TAG -f \
     python bench.py --steps 300 --warmup 100 --reps 1 --no-cpu-baseline --e2e-steps 3 > $O/ncu_full_$TAG.log 2>&1
-timeout 600 ncu --set full --clock-control none -k regex:dcb_step_kernel -s 14 -c 1 -o $O/prof_f20_$TAG -f \
+timeout 600 ncu --set full --clock-control none -k regex:dcb_step_kernel -s 6 -c 8 -o $O/prof_f20_$TAG -f \
     python bench.py --steps 20 --warmup 5 --reps 2 --no-cpu-baseline --e2e-steps 3 > $O/ncu_full_f20_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:dcb_wide_kernel -s 4 -c 1 -o $O/prof_wide_$TAG -f \
     python bench.py --n-ue 1000 --n-bs 50 --envs 1024 --fragment 4 --steps 12 --warmup 4 --reps 1 --no-cpu-baseline --e2e-steps 1 > $O/ncu_wide_$TAG.log 2>&1

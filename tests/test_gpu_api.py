@@ -434,6 +434,31 @@ def test_step_host_equals_device_step():
         assert torch.equal(ho, do.cpu()) and torch.equal(hr, dr.cpu()) and torch.equal(hi['lost_conn'], di['lost_conn'].cpu())
 
 
+@pytest.mark.parametrize('chunk', [0, 1, 3, 40])
+def test_step_many_host_equals_device_fragment(chunk):
+    """dcb_step_many_host (chunked launches, device -> host copies on a second stream overlapping the next chunk) returns
+    exactly what one device fragment returns, for any chunk length, call after call (the staging sets are reused)"""
+    from deepcomp_b200 import BatchedMobileEnv
+    K, N, M, T = 24, 50, 10, 17
+    a = BatchedMobileEnv(num_envs=K, kind='multi', seed=9, **_scenario())
+    b = BatchedMobileEnv(num_envs=K, kind='multi', seed=9, **_scenario())
+    a.reset(); b.reset()
+    fb = a.pinned_fragment_buffers(T)
+    for call in range(3):
+        acts = _actions(T, K, N, M, seed=call)
+        fb['actions'].copy_(acts.cpu())
+        ho, hr, _, hi = a.step_many_host(fb, chunk_steps=chunk)
+        d = b.step_many(acts)
+        assert torch.equal(ho, d['obs'].cpu()) and torch.equal(hr, d['reward'].cpu())
+        assert torch.equal(hi['lost_conn'], d['lost_conn'].cpu())
+    log = _actions(2 * T, K, N, M, seed=7).cpu().pin_memory()          # a caller-owned pinned action log, used in place
+    ho, hr, _, hi = a.step_many_host(fb, actions=log[T:])
+    d = b.step_many(log[T:].cuda())
+    assert torch.equal(ho, d['obs'].cpu()) and torch.equal(hr, d['reward'].cpu())
+    sa, sb = a.get_state(), b.get_state()
+    assert np.array_equal(sa['pos'], sb['pos']) and np.array_equal(sa['mask'], sb['mask'])
+
+
 # ------------------------------------------------------------------------------------------------ RLlib adapters
 def test_rllib_vector_and_base_env_adapters():
     from deepcomp_b200.rllib import CentralVectorEnv, MultiAgentBaseEnv

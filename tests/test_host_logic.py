@@ -128,3 +128,21 @@ def test_fixed_point_utility_sums_of_the_fx_agg_experiment():
     assert worst < 1e-9
     # headroom: 512 UEs (the fused kernel's limit) at +-20 on one BS
     assert 512 * (2 ** 20 - 1) < 2 ** 31 and 512 * (20 * 2 ** 16) < 2 ** 31
+
+
+def test_bench_arms_share_one_workload_config():
+    """bench.py: the GPU arm and the reference arm print the same `config`; fragments never exceed the timed region, an
+    episode, or the memory clamp; --total-envs splits the batch (strong scaling)"""
+    import argparse
+    import bench
+    args = argparse.Namespace(n_ue=50, n_bs=10, envs=1024, kind='multi', sharing='mixed', episode_length=100, fragment=100,
+                              steps=20, seed=1000)
+    assert bench.effective_fragment(args) == 20
+    cfg = bench.workload_config(args, 8)
+    assert cfg == bench.workload_config(args, 8) and '8192 total' in cfg['workload'] and cfg['fragment_steps'] == 20
+    assert 'l2' in cfg and '168 MB' in cfg['l2']
+    args.steps, args.envs = 5000, 65536 * 16
+    assert 1 <= bench.effective_fragment(args) < 100          # observation buffer of one fragment stays under the clamp
+    args.envs, args.kind = 1024, 'central'
+    assert bench.effective_fragment(args) == 100
+    assert bench.obs_floats_per_step(args) == 1024 * (2 * 50 * 10 + 50)
