@@ -100,6 +100,7 @@ struct dcb_env {
     int64_t launches = 0;
     // device allocations
     double *d_bs_xy = nullptr, *d_vel = nullptr, *d_init_xy = nullptr, *d_tabs = nullptr;
+    uint16_t *d_pair_order = nullptr;
     int *d_sharing = nullptr;
     long long *d_seeds = nullptr;
     double2 *d_pos = nullptr, *d_init_pos = nullptr;
@@ -267,7 +268,7 @@ int dcb_launch_geometry(const dcb_env *env, int32_t *envs_per_cta, int32_t *thre
 void dcb_destroy(dcb_env *env) {
     if (!env) return;
     DeviceGuard g(env->device);
-    cudaFree(env->d_bs_xy); cudaFree(env->d_vel); cudaFree(env->d_init_xy); cudaFree(env->d_sharing); cudaFree(env->d_tabs);
+    cudaFree(env->d_bs_xy); cudaFree(env->d_vel); cudaFree(env->d_init_xy); cudaFree(env->d_sharing); cudaFree(env->d_tabs); cudaFree(env->d_pair_order);
     cudaFree(env->d_seeds); cudaFree(env->d_pos); cudaFree(env->d_init_pos); cudaFree(env->d_mv);
     cudaFree(env->d_mask); cudaFree(env->d_ewma); cudaFree(env->d_time); cudaFree(env->d_err);
     cudaFree(env->d_table); cudaFree(env->d_pos_skip); cudaFree(env->d_mv_skip); cudaFree(env->d_env_ids);
@@ -415,6 +416,7 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     ALLOC(env->d_mask, KN); ALLOC(env->d_ewma, KN); ALLOC(env->d_time, K); ALLOC(env->d_err, 1);
     ALLOC(env->d_table, KN * D);
     ALLOC(env->d_tabs, 96);
+    ALLOC(env->d_pair_order, (size_t)E * M);
     ALLOC(env->d_uid, KN); ALLOC(env->d_map_draws, K); ALLOC(env->d_glob_draws, K);
     if (cfg->rand_episodes) { ALLOC(env->d_pos_skip, K); ALLOC(env->d_mv_skip, KN); }
 #undef ALLOC
@@ -456,6 +458,17 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
         CU(cudaMemcpy(env->d_tabs, tabs, sizeof(tabs), cudaMemcpyHostToDevice));
     }
     p.tabs = env->d_tabs;
+    {
+        // reducer order of a CTA's (env, BS) pairs: resource-fair base stations first (their factor is a bit count, no
+        // walk over the link values), then the others, each group env-major
+        std::vector<uint16_t> order;
+        for (int pass = 0; pass < 2; pass++)
+            for (int le = 0; le < E; le++)
+                for (int b = 0; b < M; b++)
+                    if ((cfg->host_sharing[b] == DCB_SHARE_RESOURCE_FAIR) == (pass == 0)) order.push_back((uint16_t)(le * M + b));
+        CU(cudaMemcpy(env->d_pair_order, order.data(), sizeof(uint16_t) * order.size(), cudaMemcpyHostToDevice));
+    }
+    p.pair_order = env->d_pair_order;
     p.bs_xy = env->d_bs_xy; p.sharing = env->d_sharing; p.vel_spec = env->d_vel;
     p.pos = env->d_pos; p.mv = env->d_mv; p.mask = env->d_mask; p.ewma = env->d_ewma; p.time = env->d_time;
     p.init_pos = env->d_init_pos; p.table = env->d_table; p.err = env->d_err;

@@ -56,6 +56,8 @@ struct DevParams {
     double c1, c2;       // Okumura-Hata constants (station.py:112-114)
     double snr_c0, snr_h; // snr(d) = 2^(snr_c0 - snr_h * log2(d^2)): the same model folded for the fast path
     double pw[10];       // binomial series of (1 + r)^(-snr_h): coefficients of r^0 .. r^9 (dcb_snr_inrange)
+    const uint16_t *pair_order;  // [E*M] the (env, BS) pairs of a CTA ordered by sharing model (resource-fair pairs first:
+                                 // their reduction is a bit count), so that a reducer warp works on one model
     const double *tabs;  // [80 + 16] MathTables (dcb_math.cuh) + snap thresholds of the drawn velocities 0..15, host-built
     const double *bs_xy; // [M][2]
     const int *sharing;  // [M]
@@ -81,7 +83,7 @@ struct DevParams {
 struct SmemLayout {
     int off_tab, off_stage, off_x, off_fac_pre, off_fac_post, off_hx, off_hy,
         off_hmask, off_hutil, off_hrb, off_hdr, off_hlost, off_bsx, off_bsy, off_vel,
-        off_arg_pre, off_arg_post, off_bits, off_share, off_links, off_vthr, off_wagg, off_snext;
+        off_arg_pre, off_arg_post, off_bits, off_share, off_links, off_vthr, off_wagg, off_snext, off_porder;
     int nbits;   // words per bitset
     int links_per_warp;   // capacity (entries) of one physics warp's link list
     int wagg_pairs;       // (env, BS) pairs one observer warp aggregates for itself: the envs its 32 rows touch x M
@@ -129,6 +131,7 @@ __host__ __device__ inline SmemLayout dcb_smem_layout(int kind, int N, int M, in
     L.off_links = o;    o += align16(((EN + 31) / 32) * L.links_per_warp * 2);
     L.off_vthr = o;     o += align16(16 * 8);                        // snap thresholds for drawn velocities 0..15
     L.off_snext = o;    o += align16(EN * 4);                        // per UE: prefetched waypoint-table entry
+    L.off_porder = o;   o += align16(EM * 2);                        // (env, BS) pairs in the reducer's order (by sharing model)
     // per observer warp: utility aggregates of the (env, BS) pairs its rows need -- usum, umin (double), cnt (int),
     // f_ues, f_util (float) -- computed by the warp itself so that observer warps never synchronise with each other
     L.wagg_pairs = ((31 / N + 2) * M + 1) & ~1;

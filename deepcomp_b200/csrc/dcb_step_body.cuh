@@ -103,23 +103,28 @@ __device__ __forceinline__ bool bar_or(int id, int n, bool pred) {
 // or, when there are more lanes than words, a 16- / 8-bit piece of one (CS = log2 chunks per word); fixed
 // combination order -> deterministic.
 __device__ __forceinline__ void reduce_links(int tid, int gsize, const double *X, const unsigned *bits_a,
-                                             const unsigned *bits_b, int N, int M, int MS, int n_env, int S, int CS,
-                                             bool want_arg, const int *share, double *fac_a, int *arg_a,
-                                             double *fac_b, int *arg_b) {
+                                             const unsigned *bits_b, int N, int M, int MS, int n_env, int n_pairs,
+                                             const unsigned short *porder, int S, int CS, bool want_arg, const int *share,
+                                             double *fac_a, int *arg_a, double *fac_b, int *arg_b) {
     const int R = n_env * M;
     const int NW = (N + 31) >> 5;
     const int ls = 31 - __clz(S);                 // S is a power of two
     const int ppp = gsize >> ls;
     const int seg = tid & (S - 1);
     const float inv_m = 1.0f / (float)M;
-    for (int base = 0; base < R; base += ppp) {
-        const int pair = base + (tid >> ls);
-        const bool ok = pair < R;
+    for (int base = 0; base < n_pairs; base += ppp) {
+        // pairs are taken in the order of `porder`: resource-fair pairs first, so that (almost) every warp works on one
+        // sharing model -- and the warps of the resource-fair pairs only count bits
+        const int slot = base + (tid >> ls);
+        const int pair = slot < n_pairs ? (int)porder[slot] : R;
+        const bool ok = pair < R;                 // (a CTA at the end of the batch holds fewer than E envs)
         int c0 = 0, c1 = 0, a0 = 0x7fffffff, a1 = 0x7fffffff, model = 0;
         double s0 = 0.0, s1 = 0.0, b0 = 0.0, b1 = 0.0;
+        bool walk = false;
         if (ok) {
             const int le = __float2int_rz(((float)pair + 0.5f) * inv_m), b = pair - le * M;   // exact: pair < 2^16
             model = share[b];
+            walk = want_arg || model != DCB_SHARE_RESOURCE_FAIR;
             const double *col = X + (size_t)(le * N) * MS + b;
             const int cb = 32 >> CS;                                   // bits per chunk
             const unsigned cmask = 0xffffffffu >> (32 - cb);
@@ -129,7 +134,7 @@ __device__ __forceinline__ void reduce_links(int tid, int gsize, const double *X
                 const unsigned wb = (bits_b[pair * NW + w] >> sh) & cmask;
                 c0 += __popc(wa);
                 c1 += __popc(wb);
-                unsigned both = wa | wb;
+                unsigned both = walk ? (wa | wb) : 0u;
                 const int ibase = (w << 5) + sh;
                 while (both) {
                     // two UEs per trip: both loads are in flight before the (ordered) accumulation
@@ -155,11 +160,14 @@ __device__ __forceinline__ void reduce_links(int tid, int gsize, const double *X
                 }
             }
         }
+        const bool any_walk = __any_sync(0xffffffffu, walk);           // warp-uniform: sums only where some lane has one
         for (int off = S >> 1; off > 0; off >>= 1) {
             c0 += __shfl_xor_sync(0xffffffffu, c0, off);
             c1 += __shfl_xor_sync(0xffffffffu, c1, off);
-            s0 += __shfl_xor_sync(0xffffffffu, s0, off);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+            if (any_walk) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+            }
             if (want_arg) {
                 double ob = __shfl_xor_sync(0xffffffffu, b0, off);
                 int oi = __shfl_xor_sync(0xffffffffu, a0, off);
@@ -289,6 +297,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
     unsigned short *links = reinterpret_cast<unsigned short *>(smem + L.off_links);
     double *vthr = reinterpret_cast<double *>(smem + L.off_vthr);
     uint32_t *snext = reinterpret_cast<uint32_t *>(smem + L.off_snext);
+    unsigned short *porder = reinterpret_cast<unsigned short *>(smem + L.off_porder);
 
     const int G = blockDim.x >> 1;                  // threads per warp group
     const bool is_obs = (int)threadIdx.x >= G;
@@ -314,6 +323,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
         share[b] = p.sharing[b];
     }
     for (int j = threadIdx.x; j < N; j += blockDim.x) velspec[j] = p.vel_spec[j];
+    for (int j = threadIdx.x; j < E * M; j += blockDim.x) porder[j] = p.pair_order[j];
     for (int j = threadIdx.x; j < 6 * L.nbits; j += blockDim.x) bits_post3[j] = 0u;
     __syncthreads();
 
@@ -425,7 +435,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                         }
                     }
                     bar_sync(BAR_PHYS, G);
-                    reduce_links(t, G, X, bits_fresh, bits_fresh, N, M, MS, n_env, S, p.CS, p.has_maxcap, share, fac_post,
+                    reduce_links(t, G, X, bits_fresh, bits_fresh, N, M, MS, n_env, E * M, porder, S, p.CS, p.has_maxcap, share, fac_post,
                                  arg_post, fac_pre, arg_pre);
                     bar_sync(BAR_PHYS, G);
                     for (int j = t; j < L.nbits; j += G) bits_fresh[j] = 0u;
@@ -548,7 +558,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
             DCB_TRACE_PT(0, 3);
             any_fresh = bar_or(BAR_PHYS, G, valid && T > 0 && p.auto_reset && tk >= p.episode_length);
             DCB_TRACE_PT(0, 4);
-            reduce_links(t, G, X, bits_post, bits_pre, N, M, MS, n_env, S, p.CS, p.has_maxcap, share, fac_post, arg_post,
+            reduce_links(t, G, X, bits_post, bits_pre, N, M, MS, n_env, E * M, porder, S, p.CS, p.has_maxcap, share, fac_post, arg_post,
                          fac_pre, arg_pre);
             bar_sync(BAR_PHYS, G);
             DCB_TRACE_PT(0, 5);
