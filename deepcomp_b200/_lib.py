@@ -34,7 +34,7 @@ class DcbOutputs(ctypes.Structure):
 class DcbPolicy(ctypes.Structure):
     _fields_ = [('kind', ctypes.c_int32), ('noop_interval', ctypes.c_int32), ('epsilon', ctypes.c_double),
                 ('host_cluster_masks', ctypes.c_void_p), ('host_fixed_action', ctypes.c_void_p),
-                ('seed', ctypes.c_uint64)]
+                ('seed', ctypes.c_uint64), ('calls_before', ctypes.c_int64)]
 
 
 class DcbObsVariant(ctypes.Structure):

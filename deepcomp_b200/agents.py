@@ -201,6 +201,7 @@ class FixedAgent(CentralAgent):
         super().__init__()
         self.action, self.noop_interval, self.num_vec_envs = action, noop_interval, num_vec_envs
         self.noop_counter = noop_interval
+        self.device_calls = 0          # steps this agent has driven on the device (phase of its no-op interval)
 
     def compute_action(self, observation):
         if self.noop_counter < self.noop_interval:
@@ -215,7 +216,7 @@ class FixedAgent(CentralAgent):
 
     def device_policy(self, batch=None):
         return dict(kind='fixed', fixed_action=np.asarray(self.action, dtype=np.int32),
-                    noop_interval=int(self.noop_interval))
+                    noop_interval=int(self.noop_interval), calls_before=int(self.device_calls))
 
 
 class BruteForceAgent(CentralAgent):

@@ -539,7 +539,10 @@ class BatchedMobileEnv:
         self._t += T
         spec = policy.device_policy(self) if hasattr(policy, 'device_policy') else dict(policy)
         pol = DcbPolicy(kind=POLICY_KIND[spec['kind']], noop_interval=int(spec.get('noop_interval', 0)),
-                        epsilon=float(spec.get('epsilon', 0.0)), seed=int(spec.get('seed', 0)))
+                        epsilon=float(spec.get('epsilon', 0.0)), seed=int(spec.get('seed', 0)),
+                        calls_before=int(spec.get('calls_before', -1)))
+        if hasattr(policy, 'device_calls'):          # the agent keeps its own call count (not the handle)
+            policy.device_calls += int(T)
         keep = []
         if spec['kind'] == 'static':
             cm = np.ascontiguousarray(np.asarray(spec['cluster_masks'], dtype=np.uint64))

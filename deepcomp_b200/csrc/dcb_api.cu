@@ -875,7 +875,7 @@ int dcb_rollout(dcb_env *env, const dcb_policy *policy, int32_t T, int32_t *d_ac
     PolicyParams q;
     memset(&q, 0, sizeof(q));
     q.kind = policy->kind;
-    q.call0 = env->policy_calls;
+    q.call0 = policy->calls_before >= 0 ? policy->calls_before : env->policy_calls;
     q.seed = policy->seed;
     if (policy->kind == DCB_POLICY_DYNAMIC) {
         // heuristics.py:86-91: selected = {b: snr_b >= epsilon * best_snr}; snr ~ (d^2)^-h  =>  d2_b <= d2min * epsilon^(-1/h)

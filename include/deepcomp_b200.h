@@ -74,6 +74,9 @@ typedef struct dcb_policy {
     const uint64_t *host_cluster_masks; /* STATIC: [M] bitmask of the cluster each BS belongs to (heuristics.py:127-167) */
     const int32_t *host_fixed_action;   /* FIXED: [N] action per UE */
     uint64_t seed;                      /* RANDOM */
+    int64_t calls_before;               /* compute_action calls THIS agent has made before the rollout (FIXED: phase of the
+                                           no-op interval, dummy.py:37-45; RANDOM: position in its stream); < 0 = use the
+                                           handle's running count of rollout steps (one agent per handle) */
 } dcb_policy;
 
 /* Velocity spec of a UE's RandomWaypoint (movement.py:112-117): a number >= 0 is used as is */

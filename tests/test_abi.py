@@ -37,7 +37,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.DcbConfig) == 14 * 4 + 5 * 8
     assert ctypes.sizeof(_lib.DcbOutputs) == 6 * 8 + 6 * 8 + 7 * 8
     assert ctypes.sizeof(_lib.DcbStateHost) == 5 * 8
-    assert ctypes.sizeof(_lib.DcbPolicy) == 2 * 4 + 8 + 2 * 8 + 8
+    assert ctypes.sizeof(_lib.DcbPolicy) == 2 * 4 + 8 + 2 * 8 + 8 + 8
     assert ctypes.sizeof(_lib.DcbObsVariant) == 2 * 4 + 8 + 4 * 4
 
 

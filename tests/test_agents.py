@@ -76,3 +76,4 @@ def test_device_policy_specs():
         agents.DynamicSelection(1.5)                                   # cli.py:100
     spec = agents.FixedAgent([1, 0, 2], noop_interval=3).device_policy()
     assert spec['kind'] == 'fixed' and spec['noop_interval'] == 3 and spec['fixed_action'].tolist() == [1, 0, 2]
+    assert spec['calls_before'] == 0
