@@ -122,6 +122,7 @@ struct dcb_env {
     int env_ids_cap = 0;
     int32_t *d_uni_kind = nullptr;                       // UniformMovement (dcb_set_uniform_movement)
     double *d_uni_val = nullptr;
+    std::vector<int> h_sharing;                          // sharing model per BS (host copy)
     std::vector<int32_t> h_uni_kind;
     std::vector<double> h_uni_val;
     // scripted policies (dcb_rollout)
@@ -147,14 +148,14 @@ namespace {
 // Envs per CTA.  The fused kernel wants every CTA resident at once (one wave), few idle lanes in the last warp of
 // each group, an even spread over the SMs, and -- when the batch is large enough to need several waves -- as many
 // resident warps as registers and shared memory allow.
-int choose_envs_per_cta(int K, int N, int M, int kind, int num_sms, size_t smem_cap) {
+int choose_envs_per_cta(int K, int N, int M, int kind, int num_sms, size_t smem_cap, int var = 0) {
     const char *ov = getenv("DCB_ENVS_PER_CTA");
     if (ov && atoi(ov) > 0) return atoi(ov);
     int best_e = 1;
     double best_score = -1.0;
     const int max_group = N <= 256 ? 384 : 512;     // threads per warp group; the CTA has two groups
     for (int E = 1; E * N <= max_group && E <= K; E++) {
-        const size_t sm = dcb_step_smem_bytes(kind, N, M, E);
+        const size_t sm = dcb_step_smem_bytes(kind, N, M, E, var);
         if (sm > smem_cap) break;
         const int group = (E * N + 31) / 32 * 32;
         const int threads = 2 * group;
@@ -182,6 +183,46 @@ int choose_envs_per_cta(int K, int N, int M, int kind, int num_sms, size_t smem_
         if (score > best_score) { best_score = score; best_e = E; }
     }
     return best_e;
+}
+
+// Launch geometry of the fused kernel for this handle: envs per CTA, threads, grid, shared memory, reducer lanes, and the
+// reducer's pair order.  var: the handle observes a data-rate class (larger shared-memory layout).  p.sharing holds the
+// sharing models on the device; host_sharing the same on the host.
+int configure_fused(dcb_env *env, const int *host_sharing, int var) {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, env->device));
+    const size_t smem_cap = prop.sharedMemPerBlockOptin;
+    DevParams &p = env->p;
+    const int K = p.K, N = p.N, M = p.M;
+    const int E = choose_envs_per_cta(K, N, M, p.kind, prop.multiProcessorCount, smem_cap, var);
+    if (E * N > 512 || dcb_step_smem_bytes(p.kind, N, M, E, var) > smem_cap)
+        return fail(DCB_ERR_INVALID_ARG, "%d envs per CTA do not fit the fused kernel (%zu B of shared memory)", E,
+                    dcb_step_smem_bytes(p.kind, N, M, E, var));
+    const int group = (E * N + 31) / 32 * 32;      // threads per warp group (physics / observers)
+    env->threads = 2 * group;
+    env->grid = (K + E - 1) / E;
+    env->smem = dcb_step_smem_bytes(p.kind, N, M, E, var);
+    // reducer lanes per (env, BS) pair: one per 32-UE bitset word, power of two, while the pairs still fit the CTA
+    // (more lanes than words: the words are cut into 16- or 8-bit chunks)
+    int S = 1, CS = 0;
+    const int NW = (N + 31) / 32;
+    while (S < 4 * NW && S * 2 <= 32 && E * M * S * 2 <= group) S *= 2;
+    if (const char *ov = getenv("DCB_REDUCE_LANES")) {       // experiments: 1, 2, 4, 8, ...
+        const int v = atoi(ov);
+        if (v >= 1 && v <= 32 && (v & (v - 1)) == 0 && v <= 4 * NW) S = v;
+    }
+    while ((NW << CS) < S && CS < 2) CS++;
+    p.E = E; p.S = S; p.CS = CS;
+    // reducer order of a CTA's (env, BS) pairs: resource-fair base stations first (their factor is a bit count, no walk
+    // over the link values), then the others, each group env-major
+    std::vector<uint16_t> order;
+    for (int pass = 0; pass < 2; pass++)
+        for (int le = 0; le < E; le++)
+            for (int b = 0; b < M; b++)
+                if ((host_sharing[b] == DCB_SHARE_RESOURCE_FAIR) == (pass == 0)) order.push_back((uint16_t)(le * M + b));
+    CU(cudaMemcpy(env->d_pair_order, order.data(), sizeof(uint16_t) * order.size(), cudaMemcpyHostToDevice));
+    CU(dcb_step_set_smem_limit(env->threads, M, smem_cap));
+    return DCB_OK;
 }
 
 // Move a handle to the one-CTA-per-env kernel (observation variants and the interference extension live there only)
@@ -213,7 +254,7 @@ int launch_step(dcb_env *env, const int32_t *d_actions, int T, const dcb_outputs
     if (pol) a.pol = *pol;
     a.actions_out = d_actions_out;
     a.p = env->p;
-    a.L = dcb_smem_layout(env->p.kind, env->p.N, env->p.M, env->p.E);
+    a.L = dcb_smem_layout(env->p.kind, env->p.N, env->p.M, env->p.E, env->p.obs_var != 0 && !env->wide);
     a.W = dcb_wide_layout(env->p.N, env->p.M, env->p.LC);
     a.actions = d_actions;
     a.T = T;
@@ -363,7 +404,6 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
         }
         if (c > LC) LC = c;
     }
-    int E = 1, group = 0;
     if (env->wide) {
         const WideLayout W = dcb_wide_layout(N, M, LC);
         if ((size_t)W.total > smem_cap) {
@@ -376,28 +416,7 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
         env->threads = threads;
         env->grid = K;
         env->smem = (size_t)W.total;
-        group = threads;
-    } else {
-        E = choose_envs_per_cta(K, N, M, cfg->kind, prop.multiProcessorCount, smem_cap);
-        if (E * N > 512 || dcb_step_smem_bytes(cfg->kind, N, M, E) > smem_cap) {
-            delete env;
-            return fail(DCB_ERR_INVALID_ARG, "DCB_ENVS_PER_CTA = %d does not fit", E);
-        }
-        group = (E * N + 31) / 32 * 32;      // threads per warp group (physics / observers)
-        env->threads = 2 * group;
-        env->grid = (K + E - 1) / E;
-        env->smem = dcb_step_smem_bytes(cfg->kind, N, M, E);
     }
-    // reducer lanes per (env, BS) pair: one per 32-UE bitset word, power of two, while the pairs still fit the CTA
-    // (more lanes than words: the words are cut into 16- or 8-bit chunks)
-    int S = 1, CS = 0;
-    const int NW = (N + 31) / 32;
-    while (S < 4 * NW && S * 2 <= 32 && E * M * S * 2 <= group) S *= 2;
-    if (const char *ov = getenv("DCB_REDUCE_LANES")) {       // experiments: 1, 2, 4, 8, ...
-        const int v = atoi(ov);
-        if (v >= 1 && v <= 32 && (v & (v - 1)) == 0 && v <= 4 * NW) S = v;
-    }
-    while ((NW << CS) < S && CS < 2) CS++;
 
     const size_t KN = (size_t)K * N;
     // pause_duration + 1 steps is the shortest possible redraw cycle (movement.py:168-181); +2 = entry 0 and slack
@@ -416,7 +435,7 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     ALLOC(env->d_mask, KN); ALLOC(env->d_ewma, KN); ALLOC(env->d_time, K); ALLOC(env->d_err, 1);
     ALLOC(env->d_table, KN * D);
     ALLOC(env->d_tabs, 96);
-    ALLOC(env->d_pair_order, (size_t)E * M);
+    ALLOC(env->d_pair_order, (size_t)(512 / N + 1) * M);
     ALLOC(env->d_uid, KN); ALLOC(env->d_map_draws, K); ALLOC(env->d_glob_draws, K);
     if (cfg->rand_episodes) { ALLOC(env->d_pos_skip, K); ALLOC(env->d_mv_skip, KN); }
 #undef ALLOC
@@ -440,7 +459,7 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     p.K = K; p.N = N; p.NA = N; p.M = M; p.kind = cfg->kind; p.reward = cfg->reward;
     p.map_w = (double)cfg->map_width; p.map_h = (double)cfg->map_height;
     p.episode_length = cfg->episode_length; p.auto_reset = cfg->auto_reset; p.pause_duration = cfg->pause_duration;
-    p.D = D; p.E = E; p.S = S; p.CS = CS; p.LC = LC;
+    p.D = D; p.E = 1; p.S = 1; p.CS = 0; p.LC = LC;
     p.has_maxcap = has_maxcap; p.has_propfair = has_pf;
     p.util_step = 0; p.dr_req = 1.0;
     p.obs_maxnorm = 0;
@@ -458,16 +477,6 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
         CU(cudaMemcpy(env->d_tabs, tabs, sizeof(tabs), cudaMemcpyHostToDevice));
     }
     p.tabs = env->d_tabs;
-    {
-        // reducer order of a CTA's (env, BS) pairs: resource-fair base stations first (their factor is a bit count, no
-        // walk over the link values), then the others, each group env-major
-        std::vector<uint16_t> order;
-        for (int pass = 0; pass < 2; pass++)
-            for (int le = 0; le < E; le++)
-                for (int b = 0; b < M; b++)
-                    if ((cfg->host_sharing[b] == DCB_SHARE_RESOURCE_FAIR) == (pass == 0)) order.push_back((uint16_t)(le * M + b));
-        CU(cudaMemcpy(env->d_pair_order, order.data(), sizeof(uint16_t) * order.size(), cudaMemcpyHostToDevice));
-    }
     p.pair_order = env->d_pair_order;
     p.bs_xy = env->d_bs_xy; p.sharing = env->d_sharing; p.vel_spec = env->d_vel;
     p.pos = env->d_pos; p.mv = env->d_mv; p.mask = env->d_mask; p.ewma = env->d_ewma; p.time = env->d_time;
@@ -475,10 +484,20 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
 
     // the attribute is per kernel, not per handle: always raise it to the device limit so that a later, smaller handle
     // of the same kernel class cannot lower it under an earlier one
-    cudaError_t e = env->wide ? dcb_wide_set_smem_limit(smem_cap) : dcb_step_set_smem_limit(env->threads, M, smem_cap);
-    if (e != cudaSuccess) {
-        dcb_destroy(env);
-        return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", env->smem, cudaGetErrorString(e));
+    env->h_sharing.assign(cfg->host_sharing, cfg->host_sharing + M);
+    cudaError_t e = cudaSuccess;
+    if (env->wide) {
+        e = dcb_wide_set_smem_limit(smem_cap);
+        if (e != cudaSuccess) {
+            dcb_destroy(env);
+            return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", env->smem, cudaGetErrorString(e));
+        }
+    } else {
+        const int rc = configure_fused(env, env->h_sharing.data(), 0);
+        if (rc != DCB_OK) {
+            dcb_destroy(env);
+            return rc;
+        }
     }
 
     // initial tables + state (as after the first reset)
@@ -675,8 +694,15 @@ int dcb_set_obs_variant(dcb_env *env, const dcb_obs_variant *v) {
         tot = v->curr_dr_obs != 0; ues = v->ues_at_bs_obs != 0; dist = v->dist_obs != 0; next = v->next_dist_obs != 0;
     }
     DeviceGuard guard(env->device);
-    const int rc = force_wide_kernel(env);
-    if (rc != DCB_OK) return rc;
+    if (!env->wide) {
+        // the fused kernel keeps this step's per-(env, BS) aggregates for its observers: a larger shared-memory layout,
+        // possibly fewer envs per CTA; envs that do not fit go to the one-CTA-per-env kernel
+        CU(cudaDeviceSynchronize());
+        if (dcb_step_smem_bytes(p.kind, p.N, p.M, 1, 1) > 227u * 1024u || configure_fused(env, env->h_sharing.data(), 1) != DCB_OK) {
+            const int rc = force_wide_kernel(env);
+            if (rc != DCB_OK) return rc;
+        }
+    }
     // alphabetical key order (gym.spaces.Dict sorts; central.py:33-44): connected, dist, dr, dr_total, next_dist, ues_at_bs
     const int NM = p.N * p.M;
     int o = 0;

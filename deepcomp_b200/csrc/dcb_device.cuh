@@ -87,6 +87,40 @@ __device__ __forceinline__ double shared_rate(int model, double v, double fac, i
     return v * fac * (v * ewma_eps);                                                            // :194-195, r0 = v (ewma + eps)
 }
 
+// Basestation.data_rate (station.py:204-220) for a UE that is in range of the BS but NOT connected to it: data_rate_shared
+// counts it in temporarily (station.py:164-168, 197-201).  r0 = its unshared rate, ee = its ewma + EPSILON; cnt / sum / best
+// = the raw aggregates of the UEs that are connected (count, sum of the link values of link_value(), largest unshared rate)
+__device__ __forceinline__ double rate_if_added(int model, double r0, double ee, int cnt, double sum, double best) {
+    if (model == DCB_SHARE_RESOURCE_FAIR) return r0 / (double)(cnt + 1);                        // :173
+    if (model == DCB_SHARE_RATE_FAIR) return 1.0 / (sum + 1.0 / r0);                            // :178-180
+    if (model == DCB_SHARE_MAX_CAP) return (cnt == 0 || r0 > best) ? r0 : 0.0;                  // :184-187 (first arg-max)
+    const double pr = r0 / ee;                                                                  // :150, 194-195
+    return pr / (sum + pr + DCB_EPSILON) * r0;
+}
+
+// The 'dr' / 'dr_total' entries of the data-rate observation classes from a rate (variants.py:131-152, 213-222)
+__device__ __forceinline__ double obs_dr_entry(const DevParams &p, double rate) {
+    if (p.obs_var == DCB_OBSVAR_NORMDR) return fmin(rate, 100.0) / 100.0;
+    if (p.dr_mode == DCB_DR_AUTO) return fmin(rate - p.dr_req, p.dr_req) / p.dr_req;
+    if (p.dr_mode == DCB_DR_SUB_REQ) return fmin(rate - p.dr_req, p.dr_cutoff);
+    return fmin(rate, p.dr_cutoff);
+}
+__device__ __forceinline__ double obs_dr_total(const DevParams &p, double curr_dr) {
+    if (p.obs_var == DCB_OBSVAR_NORMDR) return fmin(curr_dr, 100.0) / 100.0;
+    return fmin(curr_dr - p.dr_req, p.dr_req) / p.dr_req;
+}
+
+// The position one step closer to the waypoint (RandomWaypoint.step_towards_waypoint, movement.py:132-156), the UE itself
+// is not moved: for the 'next_dist' observation (variants.py:166-169)
+__device__ __forceinline__ void step_towards_waypoint(double x, double y, double wx, double wy, double vel, double &nx,
+                                                      double &ny) {
+    const double vx = wx - x, vy = wy - y;
+    if (sqrt(vx * vx + vy * vy) <= vel) { nx = wx; ny = wy; return; }
+    const double norm = sqrt(fma(vy, vy, vx * vx));
+    nx = x + vel * (vx / norm);
+    ny = y + vel * (vy / norm);
+}
+
 // Largest squared distance d2 with fl(sqrt(d2)) <= vel: `curr_pos.distance(waypoint) <= velocity` (movement.py:142-145)
 // becomes one compare.  fl(sqrt) is monotone, so the set is a down-set and the boundary sits within a few ulps of vel^2.
 __device__ __noinline__ double snap_threshold(double vel) {

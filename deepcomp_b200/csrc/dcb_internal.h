@@ -83,7 +83,8 @@ struct DevParams {
 struct SmemLayout {
     int off_tab, off_stage, off_x, off_fac_pre, off_fac_post, off_hx, off_hy,
         off_hmask, off_hutil, off_hrb, off_hdr, off_hlost, off_bsx, off_bsy, off_vel,
-        off_arg_pre, off_arg_post, off_bits, off_share, off_links, off_vthr, off_wagg, off_snext, off_porder;
+        off_arg_pre, off_arg_post, off_bits, off_share, off_links, off_vthr, off_wagg, off_snext, off_porder,
+        off_vfac, off_varg, off_rcnt, off_rsum, off_rbest, off_hewma, off_hmv;   // data-rate observation classes (var)
     int nbits;   // words per bitset
     int links_per_warp;   // capacity (entries) of one physics warp's link list
     int wagg_pairs;       // (env, BS) pairs one observer warp aggregates for itself: the envs its 32 rows touch x M
@@ -99,7 +100,9 @@ __host__ __device__ inline int obs_width(int kind, int M) { return kind == DCB_K
 // phase (consecutive UEs, same BS) hit 16 different bank pairs.
 __host__ __device__ inline int row_stride(int M) { return M | 1; }
 
-__host__ __device__ inline SmemLayout dcb_smem_layout(int kind, int N, int M, int E) {
+// var: the handle observes a data-rate class (dcb_set_obs_variant): the observers -- one step behind the physics warps -- then
+// need that step's per-(env, BS) aggregates and a little more per-UE state, double-buffered by step parity
+__host__ __device__ inline SmemLayout dcb_smem_layout(int kind, int N, int M, int E, int var = 0) {
     SmemLayout L;
     const int EN = E * N, EM = E * M;
     int o = 0;
@@ -137,6 +140,16 @@ __host__ __device__ inline SmemLayout dcb_smem_layout(int kind, int N, int M, in
     L.wagg_pairs = ((31 / N + 2) * M + 1) & ~1;
     L.wagg_stride = align16(L.wagg_pairs * 28);
     L.off_wagg = o;     o += ((EN + 31) / 32) * L.wagg_stride;
+    L.off_vfac = L.off_varg = L.off_rcnt = L.off_rsum = L.off_rbest = L.off_hewma = L.off_hmv = 0;
+    if (var) {
+        L.off_vfac = o;  o += align16(2 * EM * 8);     // sharing factors / arg-max of the current masks, per parity
+        L.off_rsum = o;  o += align16(2 * EM * 8);     // raw sums of the link values
+        L.off_rbest = o; o += align16(2 * EM * 8);     // largest unshared rate (max-cap)
+        L.off_varg = o;  o += align16(2 * EM * 4);
+        L.off_rcnt = o;  o += align16(2 * EM * 4);     // linked UEs
+        L.off_hewma = o; o += align16(2 * EN * 8);     // hand-off: EWMA rate, packed movement word
+        L.off_hmv = o;   o += align16(2 * EN * 8);
+    }
     L.total = o;
     return L;
 }
@@ -282,7 +295,7 @@ struct ReseedArgs {
 // The general (PAD) template instances carry everything that is not the measured fixed-population RelNorm path: padding
 // slots, observation variants, UniformMovement, ...
 __host__ inline bool dcb_step_needs_general(const DevParams &p, int flags) {
-    return p.NA < p.N || p.obs_maxnorm || p.uni_kind || (flags & DCB_STEPF_NO_MOVE);
+    return p.NA < p.N || p.obs_maxnorm || p.obs_var || p.uni_kind || (flags & DCB_STEPF_NO_MOVE);
 }
 
 cudaError_t dcb_launch_pop_reseed(const ReseedArgs &a, cudaStream_t s);
@@ -312,5 +325,5 @@ cudaError_t dcb_launch_step(const StepArgs &a, int threads, int grid, size_t sme
 cudaError_t dcb_step_set_smem_limit(int threads, int n_bs, size_t smem);
 cudaError_t dcb_launch_wide(const StepArgs &a, int threads, int grid, size_t smem, cudaStream_t s);
 cudaError_t dcb_wide_set_smem_limit(size_t smem);
-size_t dcb_step_smem_bytes(int kind, int N, int M, int E);
+size_t dcb_step_smem_bytes(int kind, int N, int M, int E, int var = 0);
 int dcb_step_regs_per_thread(int threads, int n_bs);

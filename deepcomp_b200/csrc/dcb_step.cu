@@ -18,7 +18,7 @@ DCB_DECLARE_CLASS(1024)
      : (threads) <= 704 ? dcb_step_704_##f(__VA_ARGS__)                          \
      : (threads) <= 768 ? dcb_step_768_##f(__VA_ARGS__) : dcb_step_1024_##f(__VA_ARGS__))
 
-size_t dcb_step_smem_bytes(int kind, int N, int M, int E) { return (size_t)dcb_smem_layout(kind, N, M, E).total; }
+size_t dcb_step_smem_bytes(int kind, int N, int M, int E, int var) { return (size_t)dcb_smem_layout(kind, N, M, E, var).total; }
 
 cudaError_t dcb_step_set_smem_limit(int threads, int n_bs, size_t smem) { return DCB_BY_CLASS(threads, set_smem, n_bs, smem); }
 

@@ -105,7 +105,8 @@ __device__ __forceinline__ bool bar_or(int id, int n, bool pred) {
 __device__ __forceinline__ void reduce_links(int tid, int gsize, const double *X, const unsigned *bits_a,
                                              const unsigned *bits_b, int N, int M, int MS, int n_env, int n_pairs,
                                              const unsigned short *porder, int S, int CS, bool want_arg, const int *share,
-                                             double *fac_a, int *arg_a, double *fac_b, int *arg_b) {
+                                             double *fac_a, int *arg_a, double *fac_b, int *arg_b, int *raw_cnt = nullptr,
+                                             double *raw_sum = nullptr, double *raw_best = nullptr) {
     const int R = n_env * M;
     const int NW = (N + 31) >> 5;
     const int ls = 31 - __clz(S);                 // S is a power of two
@@ -181,6 +182,7 @@ __device__ __forceinline__ void reduce_links(int tid, int gsize, const double *X
             fac_a[pair] = share_factor(model, c0, s0);
             fac_b[pair] = share_factor(model, c1, s1);
             if (want_arg) { arg_a[pair] = a0; arg_b[pair] = a1; }
+            if (raw_cnt) { raw_cnt[pair] = c0; raw_sum[pair] = s0; raw_best[pair] = b0; }   // data-rate observation classes
         }
     }
 }
@@ -298,6 +300,16 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
     double *vthr = reinterpret_cast<double *>(smem + L.off_vthr);
     uint32_t *snext = reinterpret_cast<uint32_t *>(smem + L.off_snext);
     unsigned short *porder = reinterpret_cast<unsigned short *>(smem + L.off_porder);
+    // general instance, data-rate observation classes (dcb_set_obs_variant): per step parity, for the observers
+    const bool obs_var = PAD && p.obs_var != 0;
+    const int EMv = E * M;
+    double *vfac = reinterpret_cast<double *>(smem + L.off_vfac);
+    double *rsum = reinterpret_cast<double *>(smem + L.off_rsum);
+    double *rbest = reinterpret_cast<double *>(smem + L.off_rbest);
+    int *varg = reinterpret_cast<int *>(smem + L.off_varg);
+    int *rcnt = reinterpret_cast<int *>(smem + L.off_rcnt);
+    double *hewma = reinterpret_cast<double *>(smem + L.off_hewma);
+    uint2 *hmv = reinterpret_cast<uint2 *>(smem + L.off_hmv);
 
     const int G = blockDim.x >> 1;                  // threads per warp group
     const bool is_obs = (int)threadIdx.x >= G;
@@ -559,8 +571,10 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
             any_fresh = bar_or(BAR_PHYS, G, valid && T > 0 && p.auto_reset && tk >= p.episode_length);
             DCB_TRACE_PT(0, 4);
             reduce_links(t, G, X, bits_post, bits_pre, N, M, MS, n_env, E * M, porder, S, p.CS, p.has_maxcap, share, fac_post, arg_post,
-                         fac_pre, arg_pre);
+                         fac_pre, arg_pre, obs_var ? rcnt + par * EMv : nullptr, rsum + par * EMv, rbest + par * EMv);
             bar_sync(BAR_PHYS, G);
+            if (obs_var)       // the observers read this step's factors one step later: a copy per parity
+                for (int j = t; j < EMv; j += G) { vfac[par * EMv + j] = fac_post[j]; varg[par * EMv + j] = arg_post[j]; }
             DCB_TRACE_PT(0, 5);
             // bits_pre of this parity is consumed; its next use is two steps (>= 2 group barriers) away.  The post
             // bitsets of step - 2 were read by the observers, who are done with that step (EMPTY wait above); that
@@ -595,6 +609,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                 hx[h] = x; hy[h] = y; hmask[h] = mask;
                 hutil[h] = util;
                 hrb[h] = rb; hdr[h] = dr; hlost[h] = lost;
+                if (obs_var) { hewma[h] = ewma; hmv[h] = make_uint2(wxy, vpt); }
             }
             bar_arrive(BAR_FULL + par, 2 * G);
             DCB_TRACE_PT(0, 7);
@@ -630,7 +645,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
         // aligned addresses and sizes; the CTA's span of the observation buffer starts at an arbitrary multiple of 4
         // bytes, so the tile is built in shared memory at the same offset modulo 16 and the (< 16 byte) head and tail
         // are written with scalar stores.
-        const size_t per_env = central ? (size_t)(2 * N * M + N) : (size_t)N * OW;
+        const size_t per_env = obs_var ? (size_t)p.var_obs_size : (central ? (size_t)(2 * N * M + N) : (size_t)N * OW);
         const unsigned tile_bytes = (unsigned)(per_env * n_env * 4);
         // multi: a warp's 32 rows are one contiguous span of 128 * OW bytes (a multiple of 16 from the tile start), so
         // every warp stores its own span and the observer warps never wait for each other
@@ -703,9 +718,52 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                 const double x = hx[h], y = hy[h], util = hutil[h], dr = hdr[h];
                 const mask_t mask = (mask_t)hmask[h];
 // [region:O.dense]
+                mask_t inrange = 0;
+                if (obs_var) {
+                    // ---- data-rate observation classes (general instance, central layout; NormDrMobileEnv /
+                    // DatarateMobileEnv.get_ue_obs, variants.py:127-250): per BS the shared rate this UE gets or would get
+                    // (station.py:204-220), from this step's per-(env, BS) aggregates (kept per parity by the physics
+                    // warps); written straight to the observation buffer, one segment per key (central.py:31-57)
+                    const double ee = hewma[h] + DCB_EPSILON, iee = dcb_rcp(ee);
+                    float *oenv = dst ? dst + (size_t)le * per_env : nullptr;
+                    double *denv = (last && a.out.dbg_obs) ? a.out.dbg_obs + (size_t)k * per_env : nullptr;
+                    double nx = x, ny = y;
+                    if (p.vo_next >= 0) {
+                        const uint2 mv = hmv[h];
+                        const double vf = p.vel_u ? p.vel_u[u] : velspec[i];
+                        step_towards_waypoint(x, y, (double)(mv.x & 0xffffu), (double)(mv.x >> 16),
+                                              vf >= 0.0 ? vf : (double)(mv.y & 0xffu), nx, ny);
+                    }
+                    const int offs[5] = {p.vo_conn, p.vo_dist, p.vo_dr, p.vo_next, p.vo_ues};
+                    for (int b = 0; b < M; b++) {
+                        const double d2 = dist2(bsxy[b], x, y);
+                        const bool conn = (mask >> b) & 1;
+                        const int pr = par * EMv + le * M + b;
+                        double rate = 0.0;
+                        if (d2 <= p.thr_d2) {
+                            const int model = share[b];
+                            const double r0 = rate_of_d2(p, tab, d2);
+                            rate = conn ? shared_rate(model, link_value(model, r0, iee), vfac[pr], varg[pr], i, ee)
+                                        : rate_if_added(model, r0, ee, rcnt[pr], rsum[pr], rbest[pr]);
+                        }
+                        const double vals[5] = {conn ? 1.0 : 0.0, sqrt(d2) / p.map_diag, obs_dr_entry(p, rate),
+                                                sqrt(dist2(bsxy[b], nx, ny)) / p.map_diag, (double)rcnt[pr]};
+                        const size_t e = (size_t)i * M + b;
+                        for (int sgm = 0; sgm < 5; sgm++) {
+                            if (offs[sgm] < 0) continue;
+                            if (oenv) oenv[(size_t)offs[sgm] + e] = (float)vals[sgm];
+                            if (denv) denv[(size_t)offs[sgm] + e] = vals[sgm];
+                        }
+                        if (last && a.out.dbg_snr) a.out.dbg_snr[u * M + b] = snr_of_d2(p, tab, d2);
+                    }
+                    if (p.vo_tot >= 0) {
+                        const double tot_o = obs_dr_total(p, dr);
+                        if (oenv) oenv[(size_t)p.vo_tot + i] = (float)tot_o;
+                        if (denv) denv[(size_t)p.vo_tot + i] = tot_o;
+                    }
+                } else {
                 // ---- dense pass A: squared distances (fp64, exact range decision multi_agent.py:60 /
                 // station.py:222-226), parked in the tile as float for pass B
-                mask_t inrange = 0;
                 float d2minf = CUDART_INF_F;
                 DCB_UNROLL(DCB_OBS_UNROLL)
                 for (int b = 0; b < M; b++) {
@@ -775,6 +833,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                         for (int b = 0; b < M; b++)
                             a.out.dbg_snr[u * M + b] = snr_of_d2(p, tab, dist2(bsxy[b], x, y));
                 }
+                }
                 DCB_TRACE_PT(1, 3);
 // [region:O.outputs+reward]
                 // ---- per-UE outputs and rewards -> global
@@ -826,6 +885,31 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                         if (last && a.out.dbg_reward) a.out.dbg_reward[u] = agg;
                     }
                 }
+            } else if (PAD && in_cta && obs_var) {
+                // ---- padding slot under a data-rate observation class: zeros in every segment (central.py:46-55)
+                float *oenv = dst ? dst + (size_t)le * per_env : nullptr;
+                double *denv = (last && a.out.dbg_obs) ? a.out.dbg_obs + (size_t)k * per_env : nullptr;
+                const int offs[5] = {p.vo_conn, p.vo_dist, p.vo_dr, p.vo_next, p.vo_ues};
+                for (int sgm = 0; sgm < 5; sgm++) {
+                    if (offs[sgm] < 0) continue;
+                    for (int b = 0; b < M; b++) {
+                        if (oenv) oenv[(size_t)offs[sgm] + (size_t)i * M + b] = 0.0f;
+                        if (denv) denv[(size_t)offs[sgm] + (size_t)i * M + b] = 0.0;
+                    }
+                }
+                if (p.vo_tot >= 0) {
+                    if (oenv) oenv[(size_t)p.vo_tot + i] = 0.0f;
+                    if (denv) denv[(size_t)p.vo_tot + i] = 0.0;
+                }
+                if (a.out.curr_dr) a.out.curr_dr[(size_t)step * a.out.curr_dr_stride + u] = 0.0f;
+                if (a.out.utility) a.out.utility[(size_t)step * a.out.utility_stride + u] = 0.0f;
+                if (T > 0 && lost_dst) *lost_dst = 0;
+                if (last) {
+                    if (a.out.dbg_curr_dr) a.out.dbg_curr_dr[u] = 0.0;
+                    if (a.out.dbg_utility) a.out.dbg_utility[u] = 0.0;
+                    if (a.out.dbg_snr)
+                        for (int b = 0; b < M; b++) a.out.dbg_snr[u * M + b] = 0.0;
+                }
             } else if (PAD && in_cta) {
                 // ---- padding slot (no UE there: max_ues > num_ue): zeros, as central.py:46-55 pads the observation
                 for (int b = 0; b < M; b++) {
@@ -864,7 +948,9 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
             // ---- obs tile -> global observation buffer (contiguous span of this CTA): generic-proxy writes of the
             // tile -> visible to the async proxy; then an elected thread issues the bulk copy (TMA, UBLKCP); its read
             // completion is awaited before the tile is rewritten next step
-            if (dst && warp_store) {
+            if (obs_var) {
+                // (data-rate observation classes: the rows went straight to the observation buffer)
+            } else if (dst && warp_store) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (wrows > 0) {

@@ -125,17 +125,6 @@ __device__ __forceinline__ void wide_interference_sums(const WideSmem &S, const 
     }
 }
 
-// The position one step closer to the waypoint (RandomWaypoint.step_towards_waypoint, movement.py:132-156), the UE itself
-// is not moved: for the 'next_dist' observation (variants.py:166-169)
-__device__ __forceinline__ void step_towards_waypoint(double x, double y, double wx, double wy, double vel, double &nx,
-                                                      double &ny) {
-    const double vx = wx - x, vy = wy - y;
-    if (sqrt(vx * vx + vy * vy) <= vel) { nx = wx; ny = wy; return; }
-    const double norm = sqrt(fma(vy, vy, vx * vx));
-    nx = x + vel * (vx / norm);
-    ny = y + vel * (vy / norm);
-}
-
 // per-BS utility aggregates for the observation / multi-agent reward (one warp per BS)
 __device__ __forceinline__ void wide_reduce_utility(const WideSmem &S, int NA, int M, int NW, bool want_min, int warp,
                                                     int lane, int nwarps) {
@@ -568,7 +557,6 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                 double *dbg_env = (last && a.out.dbg_obs) ? a.out.dbg_obs + (size_t)k * per_env : nullptr;
                 if (p.obs_var) {
                     const double ew = S.sew[r], ee = ew + DCB_EPSILON, iee = dcb_rcp(ee);
-                    const double req = p.dr_req;
                     double nx = rx, ny = ry;
                     if (p.vo_next >= 0) {
                         const uint2 mv = S.smv[r];
@@ -591,19 +579,10 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                             if (conn) {
                                 rate = shared_rate(model, link_value(model, r0, iee), S.fac[b], S.arg[b], r, ee);
                             } else {
-                                const int c = S.lcnt[b];
-                                const double sm = S.lsum[b];
-                                if (model == DCB_SHARE_RESOURCE_FAIR) rate = r0 / (double)(c + 1);
-                                else if (model == DCB_SHARE_RATE_FAIR) rate = 1.0 / (sm + 1.0 / r0);
-                                else if (model == DCB_SHARE_MAX_CAP) rate = (c == 0 || r0 > S.lbest[b]) ? r0 : 0.0;
-                                else { const double pr = r0 / ee; rate = pr / (sm + pr + DCB_EPSILON) * r0; }
+                                rate = rate_if_added(model, r0, ee, S.lcnt[b], S.lsum[b], S.lbest[b]);
                             }
                         }
-                        double dro;
-                        if (p.obs_var == DCB_OBSVAR_NORMDR) dro = fmin(rate, 100.0) / 100.0;             // variants.py:213-221
-                        else if (p.dr_mode == DCB_DR_AUTO) dro = fmin(rate - req, req) / req;           // variants.py:131-141
-                        else if (p.dr_mode == DCB_DR_SUB_REQ) dro = fmin(rate - req, p.dr_cutoff);
-                        else dro = fmin(rate, p.dr_cutoff);
+                        const double dro = obs_dr_entry(p, rate);                                       // variants.py:131-141, 213-221
                         const size_t e = (size_t)r * M + b;
                         const double vals[5] = {conn ? 1.0 : 0.0, sqrt(d2) / p.map_diag, dro,
                                                 sqrt(dist2(q ? bs1 : bs0, nx, ny)) / p.map_diag, (double)S.lcnt[b]};
@@ -617,8 +596,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                     }
                     if (lane == 0 && p.vo_tot >= 0) {
                         const double cd = S.sdr[r];
-                        const double tot_o = p.obs_var == DCB_OBSVAR_NORMDR ? fmin(cd, 100.0) / 100.0
-                                                                            : fmin(cd - req, req) / req;   // variants.py:147-152, 222
+                        const double tot_o = obs_dr_total(p, cd);                                       // variants.py:147-152, 222
                         if (obs_env) obs_env[(size_t)p.vo_tot + r] = (float)tot_o;
                         if (dbg_env) dbg_env[(size_t)p.vo_tot + r] = tot_o;
                     }

@@ -227,8 +227,9 @@ int dcb_set_obs_norm(dcb_env *env, int32_t kind);
  *                       diagonal; next_dist_obs the same after the UE's next step towards its waypoint (movement.py:132-156).
  *                       req = dcb_set_utility's dr_req.
  * Layout: the keys present, in alphabetical order (connected, dist, dr, dr_total, next_dist, ues_at_bs), each as one
- * segment [N][M] (dr_total: [N]) -- central.py:31-57.  dcb_obs_size changes accordingly.  Handles with such an observation
- * run on the one-CTA-per-env kernel (dcb_wide.cu) whatever their shape.  Call before the first dcb_observe / dcb_step.
+ * segment [N][M] (dr_total: [N]) -- central.py:31-57.  dcb_obs_size changes accordingly; the launch geometry is chosen
+ * again (the fused kernel keeps a step's per-BS aggregates per step parity for its observers).  Call before the first
+ * dcb_observe / dcb_step.
  */
 typedef enum dcb_obs_variant_kind { DCB_OBSVAR_NONE = 0, DCB_OBSVAR_NORMDR = 1, DCB_OBSVAR_DATARATE = 2 } dcb_obs_variant_kind;
 typedef enum dcb_dr_mode { DCB_DR_AUTO = 0, DCB_DR_SUB_REQ = 1, DCB_DR_PLAIN = 2 } dcb_dr_mode;

@@ -130,15 +130,19 @@ def test_cuda_variable_population_matches_reference_golden(name, wide, monkeypat
     env.check_errors()
 
 
+@pytest.mark.parametrize('wide', [False, True], ids=['fused', 'wide'])
 @pytest.mark.parametrize('name', pending_obs_names())
-def test_cuda_datarate_observation_classes_match_reference_golden(name):
+def test_cuda_datarate_observation_classes_match_reference_golden(name, wide, monkeypatch):
     """CentralNormDrEnv / CentralDrEnv (central.py:75-140, variants.py:42-250): the shared rate every UE gets or would get
     from every BS, all env_config options of the data-rate class (auto / numeric cut-off, required-rate subtraction, total
     rate, UEs per BS, distances now and after the next step), every recorded array of the reference's traces.  These
-    handles run on the one-CTA-per-env kernel whatever their shape."""
+    fused kernel's observers run one step behind the physics warps, which keep that step's per-(env, BS) aggregates for
+    them per step parity."""
+    if wide:
+        monkeypatch.setenv('DCB_FORCE_WIDE', '1')
     cfg, z = load_golden(name)
     env = make_env(oracle_kwargs(cfg))
-    assert env.kernel_name == 'dcb_wide_kernel' and env.obs_size == z['step_obs'].shape[1]
+    assert env.kernel_name == ('dcb_wide_kernel' if wide else 'dcb_step_kernel') and env.obs_size == z['step_obs'].shape[1]
     t = 0
     for ep in range(cfg['episodes']):
         dbg = env.reset(debug=True)
@@ -152,6 +156,36 @@ def test_cuda_datarate_observation_classes_match_reference_golden(name):
                                                    'utility', 'obs', 'lost_conn', 'time', 'reward', 'sum_utility')}
             compare_step(env, dbg, want, 0, f'{name}.step[{t}]')
             t += 1
+    env.check_errors()
+
+
+@pytest.mark.parametrize('variant,opts', [('normdr', None), ('datarate', dict(dr_cutoff='auto', sub_req_dr=True,
+                                          curr_dr_obs=True, ues_at_bs_obs=True, dist_obs=True, next_dist_obs=True))])
+def test_datarate_observation_fragments_match_the_python_oracle(variant, opts):
+    """the data-rate observation classes on a K-env batch in multi-step fragments (the pipelined path of the fused kernel:
+    observers one step behind, aggregates per step parity), every step of every env against the Python oracle"""
+    from oracle.deepcomp_oracle import OracleEnv
+    from deepcomp_b200 import BatchedMobileEnv, env_seeds
+    K, N, M, T = 9, 20, 7, 24
+    W, H, bs = c_oracle_grid(M)
+    seeds = env_seeds(3, K, N)
+    kw = dict(kind='central', n_ue=N, bs_xy=bs, map_wh=(W, H), sharing=['resource-fair', 'rate-fair', 'proportional-fair',
+              'max-cap', 'rate-fair', 'proportional-fair', 'max-cap'], velocities='slow', reward='avg', episode_length=T,
+              obs_variant=variant, obs_opts=opts)
+    env = BatchedMobileEnv(num_envs=K, seeds=seeds, **kw)
+    assert env.kernel_name == 'dcb_step_kernel'
+    orcs = [OracleEnv(seed=int(sd), **kw) for sd in seeds]
+    obs0 = env.reset().cpu().numpy()
+    for k, o in enumerate(orcs):
+        assert_close(obs0[k], o.reset_trace()['obs'], f'reset.env{k}', RTOL32, ATOL32)
+    a = np.random.default_rng(4).integers(0, M + 1, (T, K, N)).astype(np.int32)
+    out = env.step_many(torch.as_tensor(a, device='cuda'))
+    obs, rew = out['obs'].cpu().numpy(), out['reward'].cpu().numpy()
+    for k, o in enumerate(orcs):
+        for t in range(T):
+            w = o.step(a[t, k])
+            assert_close(obs[t, k], w['obs'], f'obs[{t}].env{k}', RTOL32, ATOL32)
+            assert_close(rew[t, k], w['reward'], f'reward[{t}].env{k}', RTOL32, ATOL32)
     env.check_errors()
 
 
