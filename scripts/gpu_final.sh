@@ -26,3 +26,5 @@ timeout 900 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_a
 DCB_FORCE_WIDE=1 timeout 900 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_api.py tests/test_gpu_parity.py -q -x -k "step_many or auto_reset or interference" > $O/racecheck_wide_$TAG.log 2>&1; tail -3 $O/racecheck_wide_$TAG.log
 bash scripts/gpu_configs.sh $TAG
 ls $O | head -80
+# build + smoke entry point of the driver
+timeout 600 python __graft_entry__.py > $O/graft_entry_$TAG.log 2>&1; tail -2 $O/graft_entry_$TAG.log
