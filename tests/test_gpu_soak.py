@@ -160,3 +160,49 @@ def test_adversarial_positions_match_the_python_oracle(kind, wide, monkeypatch):
     assert w['mask'][thr_ue, 0] == 1 and w['mask'][out_ue, 0] == 0
     assert n_in_range > 0
     env.check_errors()
+
+
+@pytest.mark.parametrize('case', range(12))
+def test_random_shapes_sharing_and_rewards_match_c_oracle(case):
+    """Seeded random scenarios -- shape (1..130 UEs, 1..40 BS, 1..40 envs: every CTA-size class, several bitset words,
+    partially filled last CTAs), per-BS sharing models incl. max-cap, reward aggregation, layout, velocity mix, fragments
+    of random length -- every step of every env against the C oracle: masks / lost links / positions bit-exact,
+    observations and rewards to float32 rounding."""
+    from deepcomp_b200 import BatchedMobileEnv, env_seeds
+    rng = np.random.default_rng(1000 + case)
+    n_ue, n_bs, K = int(rng.integers(1, 131)), int(rng.integers(1, 41)), int(rng.integers(1, 41))
+    kind = ['central', 'multi'][int(rng.integers(0, 2))]
+    reward = ['avg', 'sum', 'min'][int(rng.integers(0, 3))]
+    models = ['resource-fair', 'rate-fair', 'proportional-fair', 'max-cap']
+    sharing = [models[int(j)] for j in rng.integers(0, 4, n_bs)] if rng.random() < 0.7 else 'mixed'
+    velocities = [['slow', 'fast', 0, 2.5, 7][int(j)] for j in rng.integers(0, 5, n_ue)]
+    W, H, bs = grid_layout(n_bs)
+    T = 30
+    seeds = env_seeds(77 + case, K, n_ue)
+    kw = dict(kind=kind, n_ue=n_ue, bs_xy=bs, map_wh=(W, H), sharing=sharing, velocities=velocities, reward=reward,
+              episode_length=T)
+    env = BatchedMobileEnv(num_envs=K, seeds=seeds, **kw)
+    orcs = [c_oracle.COracleEnv(seed=int(sd), **kw) for sd in seeds]
+    obs0 = env.reset().cpu().numpy()
+    for k, o in enumerate(orcs):
+        assert_close(obs0[k], o.reset_trace()['obs'], f'case{case}.reset.env{k}', 2e-6, 1e-6)
+    acts = rng.integers(0, n_bs + 1, (T, K, n_ue)).astype(np.int32)
+    t = 0
+    while t < T:
+        n = int(min(T - t, rng.integers(1, 9)))
+        out = env.step_many(torch.as_tensor(acts[t:t + n], device='cuda'))
+        obs, rew, lost = out['obs'].cpu().numpy(), out['reward'].cpu().numpy(), out['lost_conn'].cpu().numpy()
+        st = None
+        for j in range(n):
+            for k, o in enumerate(orcs):
+                w = o.step(acts[t + j, k])
+                what = f'case{case} ({n_ue},{n_bs},{K},{kind},{reward}).step[{t + j}].env{k}'
+                assert_exact(lost[j, k].astype(np.int32), w['lost_conn'], what + '.lost_conn')
+                assert_close(obs[j, k], w['obs'], what + '.obs', 2e-6, 1e-6)
+                assert_close(rew[j, k], w['reward'], what + '.reward', 2e-6, 1e-5)
+                if j == n - 1:
+                    st = st or env.get_state()
+                    assert_exact(st['pos'][k], w['pos'], what + '.pos')
+                    assert_exact(env.mask_matrix(st['mask'])[k], w['mask'], what + '.mask')
+        t += n
+    env.check_errors()
