@@ -176,7 +176,9 @@ __device__ __forceinline__ double warp_min(double v) {
 // PAD: the envs have padding slots (NA < N, variable UE population)
 // EXT: the general instance -- data-rate observation classes (dcb_set_obs_variant), the interference extension
 // (dcb_set_interference), UniformMovement UEs, the no-move launch mode; the plain instances compile without them
-template <bool PAD, bool EXT>
+// CENTRAL: observation / reward layout of the central agent instead of the per-UE multi-agent one (compile-time, as in
+// the fused kernel: it selects store patterns and the reward code of every row)
+template <bool PAD, bool EXT, bool CENTRAL>
 __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const DevParams &p = a.p;
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
     const bool valid = tid < NA;
     const int i = valid ? tid : 0;
     const long long u = (long long)k * N + i;
-    const bool central = p.kind == DCB_KIND_CENTRAL;
+    constexpr bool central = CENTRAL;
     const int OW = obs_width(p.kind, M);
     const size_t per_env = (EXT && p.obs_var) ? (size_t)p.var_obs_size
                                               : (central ? (size_t)(2 * N * M + N) : (size_t)N * OW);
@@ -793,14 +795,22 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
 
 }  // namespace
 
+#define DCB_WIDE_DISPATCH(pad, ext, central, EXPR)                                                  \
+    do {                                                                                            \
+        if (central) {                                                                              \
+            if (ext) { if (pad) { auto kern = dcb_wide_kernel<true, true, true>; EXPR; } else { auto kern = dcb_wide_kernel<false, true, true>; EXPR; } }     \
+            else { if (pad) { auto kern = dcb_wide_kernel<true, false, true>; EXPR; } else { auto kern = dcb_wide_kernel<false, false, true>; EXPR; } }      \
+        } else {                                                                                    \
+            if (ext) { if (pad) { auto kern = dcb_wide_kernel<true, true, false>; EXPR; } else { auto kern = dcb_wide_kernel<false, true, false>; EXPR; } }   \
+            else { if (pad) { auto kern = dcb_wide_kernel<true, false, false>; EXPR; } else { auto kern = dcb_wide_kernel<false, false, false>; EXPR; } }    \
+        }                                                                                           \
+    } while (0)
+
 cudaError_t dcb_wide_set_smem_limit(size_t smem) {
-    cudaError_t e = cudaFuncSetAttribute(dcb_wide_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(dcb_wide_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(dcb_wide_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(dcb_wide_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaSuccess;
+    for (int v = 0; v < 8 && e == cudaSuccess; v++)
+        DCB_WIDE_DISPATCH(v & 1, (v >> 1) & 1, v >> 2,
+                          e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return e;
 }
 
@@ -809,12 +819,6 @@ cudaError_t dcb_launch_wide(const StepArgs &a, int threads, int grid, size_t sme
     // UEs and the no-move mode; the plain instances -- the measured path -- compile without them
     const bool ext = a.p.obs_var || a.p.interference || a.p.uni_kind || (a.flags & DCB_STEPF_NO_MOVE);
     const bool pad = a.p.NA < a.p.N;
-    if (ext) {
-        if (pad) dcb_wide_kernel<true, true><<<grid, threads, smem, s>>>(a);
-        else dcb_wide_kernel<false, true><<<grid, threads, smem, s>>>(a);
-    } else {
-        if (pad) dcb_wide_kernel<true, false><<<grid, threads, smem, s>>>(a);
-        else dcb_wide_kernel<false, false><<<grid, threads, smem, s>>>(a);
-    }
+    DCB_WIDE_DISPATCH(pad, ext, a.p.kind == DCB_KIND_CENTRAL, (kern<<<grid, threads, smem, s>>>(a)));
     return cudaGetLastError();
 }
