@@ -468,6 +468,7 @@ int dcb_create(const dcb_config *cfg, dcb_env **out) {
     p.thr_d2 = thr_d2;
     p.snr_c0 = log2(10.0) * (DCB_TX_POWER - p.c1) / 10.0 - log2(DCB_NOISE);
     p.snr_h = p.c2 / 20.0;
+    p.snr_hr = (float)(p.snr_h - 1.5);
     // (1 + r)^(-h) = sum_k binom(-h, k) r^k
     p.pw[0] = 1.0;
     for (int k = 1; k < 10; k++) p.pw[k] = p.pw[k - 1] * (-p.snr_h - (double)(k - 1)) / (double)k;

@@ -52,6 +52,7 @@ struct DevParams {
     int var_obs_size;    // floats per env of the variant observation
     int interference;    // extension: SINR instead of SNR (dcb_set_interference)
     int LC;              // wide kernel: link slots per UE (bound on the base stations any point can be in range of)
+    float snr_hr;        // (float)(snr_h - 1.5): exponent left over by norm_snr_f32 (dcb_device.cuh), host-computed
     double thr_d2;       // largest squared distance that is still in range (snr > 2e-8, station.py:224)
     double c1, c2;       // Okumura-Hata constants (station.py:112-114)
     double snr_c0, snr_h; // snr(d) = 2^(snr_c0 - snr_h * log2(d^2)): the same model folded for the fast path
@@ -156,7 +157,7 @@ __host__ __device__ inline SmemLayout dcb_smem_layout(int kind, int N, int M, in
 
 // ---- shared-memory layout of the wide-env kernel (dcb_wide.cu: one CTA per env)
 struct WideLayout {
-    int off_tab, off_bsxy, off_share, off_vthr, off_xs, off_sx, off_sy, off_smask, off_su, off_srb, off_sew, off_smv,
+    int off_tab, off_bsxy, off_share, off_vthr, off_xs, off_rec, off_sew, off_smv,
         off_bits, off_fac,
         off_arg, off_cnt, off_usum, off_umin, off_fues, off_futil, off_env,
         off_sdr, off_ssum, off_smax, off_sbmax, off_lsum, off_lbest, off_lcnt;   // general instance: curr_dr / interference sum per UE, raw link aggregates per BS
@@ -171,11 +172,7 @@ __host__ __device__ inline WideLayout dcb_wide_layout(int N, int M, int LC) {
     L.off_bsxy = o;  o += align16(M * 16);
     L.off_vthr = o;  o += align16(16 * 8);
     L.off_xs = o;    o += align16(N * LC * 8);
-    L.off_sx = o;    o += align16(N * 8);
-    L.off_sy = o;    o += align16(N * 8);
-    L.off_smask = o; o += align16(N * 8);
-    L.off_su = o;    o += align16(N * 8);
-    L.off_srb = o;   o += align16(N * 8);
+    L.off_rec = o;   o += align16(N * 48);                   // per UE: position, utility, mask, in-range set, reward (UeRec)
     L.off_sew = o;   o += align16(N * 8);
     L.off_smv = o;   o += align16(N * 8);
     L.off_fac = o;   o += align16(M * 8);

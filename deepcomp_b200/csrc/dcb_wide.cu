@@ -22,16 +22,23 @@ namespace {
 
 typedef unsigned long long u64;
 
+// What the row and reward phases need of a UE, in one 48-byte record (16-byte loads / one store at ONE address per row
+// instead of six arrays with an address each)
+struct __align__(16) UeRec {
+    double x, y;       // position after the move
+    double util;       // utility after the move
+    u64 mask;          // linked base stations
+    u64 inr;           // base stations in range (bit b), left by the row phase for the reward phase
+    double rb;         // reward before the move
+};
+
 struct WideSmem {
     MathTables *tab;
     double2 *bsxy;
     int *share;
     double *vthr;
     double *Xs;        // [N][LC] link values / cached shared rates
-    double *sx, *sy;   // [N] positions after the move
-    u64 *smask;        // [N]
-    double *su;        // [N] utility after the move
-    double *srb;       // [N] reward before the move
+    UeRec *rec;        // [N] position / utility after the move, link mask, in-range set, reward before the move
     double *sew;       // [N] EWMA rate
     uint2 *smv;        // [N] packed movement state
     unsigned *bits;    // [M][NW] UEs linked to each BS
@@ -77,7 +84,7 @@ __device__ __forceinline__ void wide_reduce_links(const WideSmem &S, int N, int 
                 const int j = __ffs(wa) - 1;
                 wa &= wa - 1;
                 const int i = (w << 5) + j;
-                const double v = S.Xs[(size_t)i * LC + rank_of(S.smask[i], b)];
+                const double v = S.Xs[(size_t)i * LC + rank_of(S.rec[i].mask, b)];
                 s += v;
                 if (want_arg && v > best) { best = v; a0 = i; }      // station.py:184: first arg-max
             }
@@ -107,7 +114,7 @@ __device__ __forceinline__ void wide_interference_sums(const WideSmem &S, const 
     const bool ok0 = b0 < M, ok1 = b1 < M;
     const double2 bs0 = ok0 ? S.bsxy[b0] : make_double2(0.0, 0.0), bs1 = ok1 ? S.bsxy[b1] : make_double2(0.0, 0.0);
     for (int r = warp; r < NA; r += nwarps) {
-        const double rx = S.sx[r], ry = S.sy[r];
+        const double rx = S.rec[r].x, ry = S.rec[r].y;
         const double v0 = ok0 ? snr_of_d2(p, S.tab, dist2(bs0, rx, ry)) : 0.0;
         const double v1 = ok1 ? snr_of_d2(p, S.tab, dist2(bs1, rx, ry)) : 0.0;
         // strongest BS (first index on ties), then the sum of the others
@@ -138,7 +145,7 @@ __device__ __forceinline__ void wide_reduce_utility(const WideSmem &S, int NA, i
             while (wa) {
                 const int j = __ffs(wa) - 1;
                 wa &= wa - 1;
-                const double uu = S.su[(w << 5) + j];
+                const double uu = S.rec[(w << 5) + j].util;
                 s += uu;
                 if (want_min) mn = uu < mn ? uu : mn;
             }
@@ -191,11 +198,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
     S.share = reinterpret_cast<int *>(smem + L.off_share);
     S.vthr = reinterpret_cast<double *>(smem + L.off_vthr);
     S.Xs = reinterpret_cast<double *>(smem + L.off_xs);
-    S.sx = reinterpret_cast<double *>(smem + L.off_sx);
-    S.sy = reinterpret_cast<double *>(smem + L.off_sy);
-    S.smask = reinterpret_cast<u64 *>(smem + L.off_smask);
-    S.su = reinterpret_cast<double *>(smem + L.off_su);
-    S.srb = reinterpret_cast<double *>(smem + L.off_srb);
+    S.rec = reinterpret_cast<UeRec *>(smem + L.off_rec);
     S.sew = reinterpret_cast<double *>(smem + L.off_sew);
     S.smv = reinterpret_cast<uint2 *>(smem + L.off_smv);
     S.bits = reinterpret_cast<unsigned *>(smem + L.off_bits);
@@ -224,12 +227,12 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
     const int i = valid ? tid : 0;
     const long long u = (long long)k * N + i;
     constexpr bool central = CENTRAL;
-    const int OW = obs_width(p.kind, M);
+    const int OW = obs_width(central ? DCB_KIND_CENTRAL : DCB_KIND_MULTI, M);
     const size_t per_env = (EXT && p.obs_var) ? (size_t)p.var_obs_size
                                               : (central ? (size_t)(2 * N * M + N) : (size_t)N * OW);
     const int T = a.T;
     const int n_iter = T > 0 ? T : 1;
-    const float hr = (float)(p.snr_h - 1.5);
+    const float hr = p.snr_hr;
 
     dcb_math_init(S.tab, S.vthr, tid, blockDim.x, p.tabs);
     for (int b = tid; b < M; b += blockDim.x) {
@@ -243,9 +246,9 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
     int tk = p.time[k];
     if (valid) {
         const double2 ps = p.pos[u];
-        S.sx[i] = ps.x; S.sy[i] = ps.y;
+        S.rec[i].x = ps.x; S.rec[i].y = ps.y;
         S.smv[i] = p.mv[u];
-        S.smask[i] = p.mask[u];
+        S.rec[i].mask = p.mask[u];
         S.sew[i] = p.ewma[u];
     }
     const double vfix = valid ? (p.vel_u ? p.vel_u[u] : p.vel_spec[i]) : 0.0;
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
         u64 mask = 0;
         unsigned wxy = 0, vpt = 0;
         if (valid) {
-            x = S.sx[i]; y = S.sy[i]; ewma = S.sew[i]; mask = S.smask[i];
+            x = S.rec[i].x; y = S.rec[i].y; ewma = S.sew[i]; mask = S.rec[i].mask;
             const uint2 mv = S.smv[i];
             wxy = mv.x; vpt = mv.y;
         }
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                 }
                 tk = 0;
                 if (interf) {               // the SNR sums follow the UEs to their initial positions (CTA-uniform branch)
-                    if (valid) { S.sx[i] = x; S.sy[i] = y; }
+                    if (valid) { S.rec[i].x = x; S.rec[i].y = y; }
                     __syncthreads();
                     wide_interference_sums(S, p, NA, M, warp, lane, nwarps);
                     __syncthreads();
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                     Xrow[slot] = link_value(S.share[b], unshared_rate(dist2(S.bsxy[b], x, y), b, tot0), iee);
                     atomicOr(&S.bits[b * NW + (i >> 5)], 1u << (i & 31));
                 }
-                S.smask[i] = mask;
+                S.rec[i].mask = mask;
             }
             __syncthreads();
             wide_reduce_links<EXT>(S, N, M, NW, LC, p.has_maxcap, warp, lane, nwarps);
@@ -378,7 +381,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
             }
             if (interf && !no_move) {
                 // the SINR at the new positions needs the SNR sums there before any link can be judged
-                if (valid) { S.sx[i] = x; S.sy[i] = y; }
+                if (valid) { S.rec[i].x = x; S.rec[i].y = y; }
                 __syncthreads();
                 wide_interference_sums(S, p, NA, M, warp, lane, nwarps);
                 __syncthreads();
@@ -402,8 +405,8 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                     mask &= ~((u64)1 << b);
                 }
             }
-            S.smask[i] = mask;
-            S.sx[i] = x; S.sy[i] = y;
+            S.rec[i].mask = mask;
+            S.rec[i].x = x; S.rec[i].y = y;
             S.sew[i] = ewma;
             S.smv[i] = make_uint2(wxy, vpt);
         }
@@ -421,8 +424,8 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                 dr += r;
             }
             util = ue_utility(p, tab, dr);
-            S.su[i] = util;
-            S.srb[i] = rb;
+            S.rec[i].util = util;
+            S.rec[i].rb = rb;
             if (EXT) S.sdr[i] = dr;
             // ---- per-UE info outputs (base.py:383-411)
             if (a.out.curr_dr) a.out.curr_dr[(size_t)step * a.out.curr_dr_stride + u] = (float)dr;
@@ -437,8 +440,8 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
             // per-env sums: utility (base.py:402) and the central reward over the PRE-move rewards (central.py:65-73)
             double s_u = 0.0, s_r = p.reward == DCB_REWARD_MIN ? CUDART_INF : 0.0;
             for (int j = lane; j < NA; j += 32) {
-                s_u += S.su[j];
-                const double r = S.srb[j];
+                s_u += S.rec[j].util;
+                const double r = S.rec[j].rb;
                 s_r = p.reward == DCB_REWARD_MIN ? (r < s_r ? r : s_r) : s_r + r;
             }
             s_u = warp_sum(s_u);
@@ -467,23 +470,26 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
         const bool ok0 = b0 < M, ok1 = b1 < M;
         const double2 bs0 = ok0 ? S.bsxy[b0] : make_double2(0.0, 0.0), bs1 = ok1 ? S.bsxy[b1] : make_double2(0.0, 0.0);
         float fu0 = 0.0f, fu1 = 0.0f, fa0 = 0.0f, fa1 = 0.0f;
-        int cn0 = 0, cn1 = 0;
-        double us0 = 0.0, us1 = 0.0;
         if (!central) {
-            // (the per-BS minima of the 'min' reward are read where they are used: four registers less across the row loop)
-            if (ok0) { fu0 = S.f_ues[b0]; fa0 = S.f_util[b0]; cn0 = S.cnt_obs[b0]; us0 = S.usum[b0]; }
-            if (ok1) { fu1 = S.f_ues[b1]; fa1 = S.f_util[b1]; cn1 = S.cnt_obs[b1]; us1 = S.usum[b1]; }
+            if (ok0) { fu0 = S.f_ues[b0]; fa0 = S.f_util[b0]; }
+            if (ok1) { fu1 = S.f_ues[b1]; fa1 = S.f_util[b1]; }
         }
-        // this lane's output cursor: column b0 of the env's first row; the four (multi) / two (central) segments of a
-        // row are fixed byte offsets from it, the second pass (b1 = b0 + 32) is +128 bytes on the same addresses
-        float *obs_lane = obs_env ? obs_env + b0 : nullptr;
+        const unsigned lanebit = 1u << lane;
+        // this lane's output cursor: column b0 of the row the warp is at, advanced by nwarps rows per trip; the four
+        // (multi) / two (central) segments of a row are fixed offsets from it, the second pass (b1 = b0 + 32) is +128
+        // bytes on the same addresses
         const int seg1 = central ? N * M : M, seg2 = 2 * M, seg3 = 3 * M;      // in floats
         const int row_stride_f = central ? M : OW;
+        float *o = obs_env + b0 + warp * row_stride_f;                // (never dereferenced when obs_env is NULL)
+        const int o_step = nwarps * row_stride_f;
         const long long kN = (long long)k * N;
-        float *reward_env = (a.out.reward && !central && T > 0)
-                                ? a.out.reward + (size_t)step * a.out.reward_stride + kN : nullptr;
-        double *dbg_reward_env = (last && a.out.dbg_reward && !central && T > 0) ? a.out.dbg_reward + kN : nullptr;
-        for (int r = warp; r < N; r += nwarps) {
+        // the per-UE rewards of the multi-agent env are NOT computed here: the row phase leaves the in-range set of every
+        // UE in its record and a thread per UE folds the per-BS aggregates over it afterwards (one warp instruction serves 32
+        // UEs there, against 15 shuffles per row here)
+        const bool want_reward = !central && T > 0;
+        float *reward_env = (a.out.reward && want_reward) ? a.out.reward + (size_t)step * a.out.reward_stride + kN : nullptr;
+        double *dbg_reward_env = (last && a.out.dbg_reward && want_reward) ? a.out.dbg_reward + kN : nullptr;
+        for (int r = warp; r < N; r += nwarps, o += o_step) {
             if (PAD && r >= NA) {
                 // ---- padding slot (no UE there: max_ues > num_ue): zeros, as central.py:46-55 pads the observation
                 const long long ru = kN + r;
@@ -502,8 +508,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                         if (dbg_env) dbg_env[(size_t)p.vo_tot + r] = 0.0;
                     }
                 } else
-                if (obs_lane) {
-                    float *o = obs_lane + r * row_stride_f;
+                if (obs_env) {
                     if (central) {
                         if (ok0) { o[0] = 0.0f; o[seg1] = 0.0f; }
                         if (ok1) { o[32] = 0.0f; o[seg1 + 32] = 0.0f; }
@@ -540,8 +545,9 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                 }
                 continue;
             }
-            const double rx = S.sx[r], ry = S.sy[r], rutil = S.su[r];
-            const u64 rmask = S.smask[r];
+            const UeRec *rp = S.rec + r;
+            const double rx = rp->x, ry = rp->y, rutil = rp->util;
+            const u64 rmask = rp->mask;
             const double d20 = ok0 ? dist2(bs0, rx, ry) : CUDART_INF;
             const double d21 = ok1 ? dist2(bs1, rx, ry) : CUDART_INF;
             if (EXT && (p.obs_var || interf)) {
@@ -613,8 +619,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                     const float dr0 = p.obs_maxnorm ? max_norm_snr(q0) : (float)(q0 * inv_max);
                     const float dr1 = p.obs_maxnorm ? max_norm_snr(q1) : (float)(q1 * inv_max);
                     const float c0 = cb0 ? 1.0f : 0.0f, c1 = cb1 ? 1.0f : 0.0f;
-                    if (obs_lane) {
-                        float *o = obs_lane + r * row_stride_f;
+                    if (obs_env) {
                         if (central) {
                             if (ok0) { o[0] = c0; o[seg1] = dr0; }
                             if (ok1) { o[32] = c1; o[seg1 + 32] = dr1; }
@@ -651,44 +656,19 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                     if (ok0) a.out.dbg_snr[ru * M + b0] = q0;
                     if (ok1) a.out.dbg_snr[ru * M + b1] = q1;
                 }
-                if (!central && T > 0) {
-                    // ---- multi_agent.py:39-95 on the POST-move state (as below, with the SINR-based in-range set)
-                    double agg = rutil;
-                    if (in0 | in1) {
-                        const bool i0 = (in0 >> lane) & 1u, i1 = (in1 >> lane) & 1u;
-                        if (p.reward == DCB_REWARD_AVG) {
-                            int nn = (i0 ? cn0 : 0) + (i1 ? cn1 : 0);
-                            double tt = (i0 ? us0 : 0.0) + (i1 ? us1 : 0.0);
-                            for (int off = 16; off > 0; off >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, off);
-                            tt = warp_sum(tt);
-                            if (nn > 0) agg = (rmask == 0 ? tt + rutil : tt) * dcb_rcp((double)(rmask == 0 ? nn + 1 : nn));
-                        } else if (p.reward == DCB_REWARD_SUM) {
-                            double sacc = 0.0;
-                            for (int j = lane; j < NA; j += 32)
-                                if (S.smask[j] & rmask) sacc += S.srb[j];
-                            agg = warp_sum(sacc);
-                        } else {
-                            double mn = i0 ? S.umin[b0] : CUDART_INF;
-                            if (i1) { const double um1 = S.umin[b1]; mn = um1 < mn ? um1 : mn; }
-                            mn = warp_min(mn);
-                            agg = mn < agg ? mn : agg;
-                        }
-                    }
-                    if (lane == 0) {
-                        if (reward_env) reward_env[r] = (float)agg;
-                        if (dbg_reward_env) dbg_reward_env[r] = agg;
-                    }
-                }
+                if (want_reward) S.rec[r].inr = ((u64)in1 << 32) | in0;     // SINR-based in-range set for the reward phase
                 continue;
             }
             const float f0 = (float)d20, f1 = (float)d21;
-            float d2minf = fminf(f0, f1);
-            for (int off = 16; off > 0; off >>= 1) d2minf = fminf(d2minf, __shfl_xor_sync(0xffffffffu, d2minf, off));
+            // closest BS: squared distances are >= +0 (or +inf on the lanes past M), so their fp32 bit patterns order like
+            // unsigned integers and ONE redux.sync replaces a five-level shuffle ladder
+            const float d2minf = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(fminf(f0, f1))));
             // in-range set (multi_agent.py:60 / station.py:222-226): exact fp64 decision, gathered by ballot
             const unsigned in0 = __ballot_sync(0xffffffffu, ok0 && d20 <= p.thr_d2);
             const unsigned in1 = __ballot_sync(0xffffffffu, ok1 && d21 <= p.thr_d2);
+            if (want_reward) S.rec[r].inr = ((u64)in1 << 32) | in0;   // (every lane stores the same word)
             float dr0, dr1;
-            if (p.obs_maxnorm) {         // MaxNormEnv (variants.py:308-332): per-handle variant
+            if (EXT && p.obs_maxnorm) {  // MaxNormEnv (variants.py:308-332): per-handle variant, general instance only
                 dr0 = ok0 ? max_norm_snr(snr_of_d2_general(p.snr_c0, p.snr_h, tab, d20)) : 0.0f;
                 dr1 = ok1 ? max_norm_snr(snr_of_d2_general(p.snr_c0, p.snr_h, tab, d21)) : 0.0f;
             } else if (d2minf >= 1e-6f) {       // 'dr' = snr_b / max_b snr_b (variants.py:276-284) = (d2min / d2_b)^h in fp32
@@ -702,19 +682,20 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                 dr1 = ok1 ? (float)(snr_of_d2(p, tab, d21) * inv_max) : 0.0f;
             }
             // 'connected' (variants.py:272): bit b0 of the low word / bit b0 of the high word (b1 = b0 + 32)
-            const float c0 = (((unsigned)rmask >> lane) & 1u) ? 1.0f : 0.0f;
-            const float c1 = (((unsigned)(rmask >> 32) >> lane) & 1u) ? 1.0f : 0.0f;
+            const float c0 = ((unsigned)rmask & lanebit) ? 1.0f : 0.0f;
+            const float c1 = ((unsigned)(rmask >> 32) & lanebit) ? 1.0f : 0.0f;
             const double un = rutil * (1.0 / DCB_MAX_UTILITY);                              // variants.py:287
             const long long ru = kN + r;
-            if (obs_lane) {
-                float *o = obs_lane + r * row_stride_f;
+            if (obs_env) {
                 if (central) {
-                    if (ok0) { o[0] = c0; o[seg1] = dr0; }
-                    if (ok1) { o[32] = c1; o[seg1 + 32] = dr1; }
+                    float *o1 = o + seg1;
+                    if (ok0) { o[0] = c0; o1[0] = dr0; }
+                    if (ok1) { o[32] = c1; o1[32] = dr1; }
                     if (lane == 0) obs_env[(size_t)2 * N * M + r] = (float)un;
                 } else {
-                    if (ok0) { o[0] = c0; o[seg1] = dr0; o[seg2] = fu0; o[seg3] = fa0; }
-                    if (ok1) { o[32] = c1; o[seg1 + 32] = dr1; o[seg2 + 32] = fu1; o[seg3 + 32] = fa1; }
+                    float *o1 = o + seg1, *o2 = o + seg2, *o3 = o + seg3;
+                    if (ok0) { o[0] = c0; o1[0] = dr0; o2[0] = fu0; o3[0] = fa0; }
+                    if (ok1) { o[32] = c1; o1[32] = dr1; o2[32] = fu1; o3[32] = fa1; }
                     if (lane == 0) o[4 * M] = (float)un;
                 }
             }
@@ -747,46 +728,54 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                     if (ok1) a.out.dbg_snr[ru * M + b1] = snr_of_d2(p, tab, d21);
                 }
             }
-            if (!central && T > 0) {
-                // ---- multi_agent.py:39-95 on the POST-move state
-                double agg = rutil;
-                if (in0 | in1) {
+        }
+        __syncthreads();      // rows done: records / aggregates may be overwritten by the next step
+        if (want_reward) {
+            // ---- per-UE reward of the multi-agent env (multi_agent.py:39-95 -> user.py:231-260) on the POST-move state: a
+            // thread per UE folds the per-BS aggregates over the base stations in range of it (UeRec::inr, left by the row phase)
+            if (valid) {
+                const UeRec me = S.rec[i];
+                const u64 inm = me.inr;
+                double agg = me.util;
+                if (inm) {
                     if (p.reward == DCB_REWARD_AVG) {
-                        const bool i0 = (in0 >> lane) & 1u, i1 = (in1 >> lane) & 1u;
-                        int nn = (i0 ? cn0 : 0) + (i1 ? cn1 : 0);
-                        double tot = (i0 ? us0 : 0.0) + (i1 ? us1 : 0.0);
-                        for (int off = 16; off > 0; off >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, off);
-                        tot = warp_sum(tot);
-                        if (nn > 0) agg = (rmask == 0 ? tot + rutil : tot) * dcb_rcp((double)(rmask == 0 ? nn + 1 : nn));
+                        int nn = 0;
+                        double tot = 0.0;
+                        for (u64 m = inm; m; m &= m - 1) {
+                            const int b = __ffsll((long long)m) - 1;
+                            nn += S.cnt_obs[b];
+                            tot += S.usum[b];
+                        }
+                        if (nn > 0) agg = (me.mask == 0 ? tot + me.util : tot) * dcb_rcp((double)(me.mask == 0 ? nn + 1 : nn));
                     } else if (p.reward == DCB_REWARD_SUM) {
                         // user.py:238-244: UEs sharing any BS with this UE; their PRE-move rewards
                         double s = 0.0;
-                        for (int j = lane; j < NA; j += 32)
-                            if (S.smask[j] & rmask) s += S.srb[j];
-                        agg = warp_sum(s);
+                        for (int j = 0; j < NA; j++)
+                            if (S.rec[j].mask & me.mask) s += S.rec[j].rb;
+                        agg = s;
                     } else {
-                        const bool i0 = (in0 >> lane) & 1u, i1 = (in1 >> lane) & 1u;
-                        double mn = i0 ? S.umin[b0] : CUDART_INF;
-                        if (i1) { const double um1 = S.umin[b1]; mn = um1 < mn ? um1 : mn; }
-                        mn = warp_min(mn);
+                        double mn = CUDART_INF;
+                        for (u64 m = inm; m; m &= m - 1) {
+                            const double um = S.umin[__ffsll((long long)m) - 1];
+                            mn = um < mn ? um : mn;
+                        }
                         agg = mn < agg ? mn : agg;
                     }
                 }
-                if (lane == 0) {
-                    if (reward_env) reward_env[r] = (float)agg;
-                    if (dbg_reward_env) dbg_reward_env[r] = agg;
-                }
+                if (reward_env) reward_env[i] = (float)agg;
+                if (dbg_reward_env) dbg_reward_env[i] = agg;
             }
+            // the 'sum' reward reads the other UEs' masks, which their threads rewrite at the top of the next step
+            if (p.reward == DCB_REWARD_SUM) __syncthreads();
         }
-        __syncthreads();      // rows done: sx / su / smask / aggregates may be overwritten by the next step
     }
 
     // ---- shared memory -> state slabs
     if (T > 0) {
         if (valid) {
-            p.pos[u] = make_double2(S.sx[i], S.sy[i]);
+            p.pos[u] = make_double2(S.rec[i].x, S.rec[i].y);
             p.mv[u] = S.smv[i];
-            p.mask[u] = S.smask[i];
+            p.mask[u] = S.rec[i].mask;
             p.ewma[u] = S.sew[i];
         }
         if (tid == 0) p.time[k] = tk;
@@ -817,7 +806,7 @@ cudaError_t dcb_wide_set_smem_limit(size_t smem) {
 cudaError_t dcb_launch_wide(const StepArgs &a, int threads, int grid, size_t smem, cudaStream_t s) {
     // the general instance (EXT) carries the data-rate observation classes, the interference extension, UniformMovement
     // UEs and the no-move mode; the plain instances -- the measured path -- compile without them
-    const bool ext = a.p.obs_var || a.p.interference || a.p.uni_kind || (a.flags & DCB_STEPF_NO_MOVE);
+    const bool ext = a.p.obs_var || a.p.interference || a.p.uni_kind || a.p.obs_maxnorm || (a.flags & DCB_STEPF_NO_MOVE);
     const bool pad = a.p.NA < a.p.N;
     DCB_WIDE_DISPATCH(pad, ext, a.p.kind == DCB_KIND_CENTRAL, (kern<<<grid, threads, smem, s>>>(a)));
     return cudaGetLastError();
