@@ -133,12 +133,14 @@ struct dcb_env {
     int32_t *d_h_actions = nullptr;
     float *d_h_obs = nullptr, *d_h_reward = nullptr;
     uint8_t *d_h_lost = nullptr;
+    size_t h_obs_cap = 0;    // floats d_h_obs holds (the observation size can grow: dcb_set_obs_variant)
     // dcb_step_many_host: actions of the fragment, two chunk-sized staging sets, copy stream, events
     int32_t *d_hm_actions = nullptr;
     size_t hm_actions_cap = 0;
     float *d_hm_obs[2] = {nullptr, nullptr}, *d_hm_reward[2] = {nullptr, nullptr};
     uint8_t *d_hm_lost[2] = {nullptr, nullptr};
     int hm_chunk_cap = 0;
+    size_t hm_obs_cap = 0;   // floats per step the two staging sets were sized for
     cudaStream_t hm_copy_stream = nullptr;
     cudaEvent_t hm_done[2] = {nullptr, nullptr}, hm_copied[2] = {nullptr, nullptr};
 };
@@ -664,6 +666,8 @@ int dcb_set_obs_norm(dcb_env *env, int32_t kind) {
     if (!env) return fail(DCB_ERR_INVALID_ARG, "null handle");
     if (kind != DCB_OBS_RELNORM && kind != DCB_OBS_MAXNORM)
         return fail(DCB_ERR_INVALID_ARG, "unknown observation normalisation %d", kind);
+    if (kind == DCB_OBS_MAXNORM && env->p.obs_var)
+        return fail(DCB_ERR_INVALID_ARG, "MaxNorm and a data-rate observation are different classes");
     env->p.obs_maxnorm = kind == DCB_OBS_MAXNORM;
     return DCB_OK;
 }
@@ -946,9 +950,16 @@ int dcb_step_host(dcb_env *env, const int32_t *h_actions, float *h_obs, float *h
     const size_t n_obs = (size_t)p.K * dcb_obs_size(env), n_rew = (size_t)p.K * dcb_reward_size(env);
     if (!env->d_h_actions) {
         CU(cudaMalloc((void **)&env->d_h_actions, sizeof(int32_t) * KN));
-        CU(cudaMalloc((void **)&env->d_h_obs, sizeof(float) * n_obs));
         CU(cudaMalloc((void **)&env->d_h_reward, sizeof(float) * n_rew));
         CU(cudaMalloc((void **)&env->d_h_lost, KN));
+    }
+    if (n_obs > env->h_obs_cap) {      // first call, or the observation grew since (dcb_set_obs_variant)
+        CU(cudaStreamSynchronize(s));
+        cudaFree(env->d_h_obs);
+        env->d_h_obs = nullptr;
+        env->h_obs_cap = 0;
+        CU(cudaMalloc((void **)&env->d_h_obs, sizeof(float) * n_obs));
+        env->h_obs_cap = n_obs;
     }
     CU(cudaMemcpyAsync(env->d_h_actions, h_actions, sizeof(int32_t) * KN, cudaMemcpyHostToDevice, s));
     dcb_outputs o;
@@ -996,20 +1007,23 @@ int dcb_step_many_host(dcb_env *env, const int32_t *h_actions, int32_t T, float 
         CU(cudaMalloc((void **)&env->d_hm_actions, sizeof(int32_t) * (size_t)T * KN));
         env->hm_actions_cap = (size_t)T * KN;
     }
-    if (C > env->hm_chunk_cap) {
+    if (C > env->hm_chunk_cap || n_obs > env->hm_obs_cap) {
         CU(cudaStreamSynchronize(s));
         CU(cudaStreamSynchronize(env->hm_copy_stream));
         for (int j = 0; j < 2; j++) {
             cudaFree(env->d_hm_obs[j]); cudaFree(env->d_hm_reward[j]); cudaFree(env->d_hm_lost[j]);
             env->d_hm_obs[j] = nullptr; env->d_hm_reward[j] = nullptr; env->d_hm_lost[j] = nullptr;
         }
+        const int cap = C > env->hm_chunk_cap ? C : env->hm_chunk_cap;
         env->hm_chunk_cap = 0;
+        env->hm_obs_cap = 0;
         for (int j = 0; j < 2; j++) {
-            CU(cudaMalloc((void **)&env->d_hm_obs[j], sizeof(float) * n_obs * C));
-            CU(cudaMalloc((void **)&env->d_hm_reward[j], sizeof(float) * n_rew * C));
-            CU(cudaMalloc((void **)&env->d_hm_lost[j], KN * C));
+            CU(cudaMalloc((void **)&env->d_hm_obs[j], sizeof(float) * n_obs * cap));
+            CU(cudaMalloc((void **)&env->d_hm_reward[j], sizeof(float) * n_rew * cap));
+            CU(cudaMalloc((void **)&env->d_hm_lost[j], KN * cap));
         }
-        env->hm_chunk_cap = C;
+        env->hm_chunk_cap = cap;
+        env->hm_obs_cap = n_obs;
     }
     CU(cudaMemcpyAsync(env->d_hm_actions, h_actions, sizeof(int32_t) * (size_t)T * KN, cudaMemcpyHostToDevice, s));
     int chunk = 0;

@@ -459,6 +459,43 @@ def test_step_many_host_equals_device_fragment(chunk):
     assert np.array_equal(sa['pos'], sb['pos']) and np.array_equal(sa['mask'], sb['mask'])
 
 
+def test_host_staging_follows_a_later_observation_variant():
+    """dcb_step_host / dcb_step_many_host size their device staging for the observation of the first call; a handle that
+    is switched to a wider observation class afterwards (plain C ABI: dcb_set_obs_variant) must get larger staging sets,
+    and return what a handle built with the variant returns"""
+    import ctypes
+    from deepcomp_b200 import BatchedMobileEnv
+    from deepcomp_b200._lib import DcbObsVariant, check
+    K, N, M, T = 6, 12, 5, 7
+    opts = dict(dr_cutoff='auto', sub_req_dr=True, curr_dr_obs=True, ues_at_bs_obs=True, dist_obs=True, next_dist_obs=True)
+    a = BatchedMobileEnv(num_envs=K, kind='central', seed=4, **_scenario(N, M))
+    b = BatchedMobileEnv(num_envs=K, kind='central', seed=4, obs_variant='datarate', obs_opts=opts, **_scenario(N, M))
+    a.reset(); b.reset()
+    acts = _actions(2 + T, K, N, M, seed=3)
+    a.step_host(acts[0].cpu().numpy())                         # staging sized for 2NM + N floats per env
+    fa = a.pinned_fragment_buffers(1)
+    fa['actions'].copy_(acts[1:2].cpu())
+    a.step_many_host(fa, chunk_steps=1)
+    for t in range(2):
+        b.step(acts[t])
+    # the same switch BatchedMobileEnv makes at construction, on the live handle
+    check(a._L.dcb_set_utility(a._h, 0, 1.0))
+    v = DcbObsVariant(kind=2, dr_mode=0, dr_cutoff=0.0, curr_dr_obs=1, ues_at_bs_obs=1, dist_obs=1, next_dist_obs=1)
+    check(a._L.dcb_set_obs_variant(a._h, ctypes.byref(v)))
+    a.obs_variant, a.obs_opts, a.obs_keys = b.obs_variant, b.obs_opts, b.obs_keys
+    a.obs_size = int(a._L.dcb_obs_size(a._h))
+    a.obs_shape, a._pinned = (a.obs_size,), None
+    assert a.obs_size == b.obs_size == 5 * N * M + N > 2 * N * M + N
+    ho, hr, _, _ = a.step_host(acts[2].cpu().numpy())
+    do, dr, _, _ = b.step(acts[2])
+    assert torch.equal(ho, do.cpu()) and torch.equal(hr, dr.cpu())
+    fa = a.pinned_fragment_buffers(T - 1)
+    fa['actions'].copy_(acts[3:].cpu())
+    ho, hr, _, _ = a.step_many_host(fa, chunk_steps=1)          # chunk length unchanged, observation wider
+    d = b.step_many(acts[3:].contiguous())
+    assert torch.equal(ho, d['obs'].cpu()) and torch.equal(hr, d['reward'].cpu())
+
+
 # ------------------------------------------------------------------------------------------------ RLlib adapters
 def test_rllib_vector_and_base_env_adapters():
     from deepcomp_b200.rllib import CentralVectorEnv, MultiAgentBaseEnv
