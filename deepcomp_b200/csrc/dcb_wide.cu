@@ -61,11 +61,24 @@ struct WideSmem {
 };
 
 // Signal quality of one UE-BS pair: SNR (station.py:122-127) or, with the interference extension, SINR =
-// snr_b / (1 + sum_{b' != b} snr_b') with `tot` = the sum over ALL base stations at the UE's position
+// snr_b / (1 + sum_{b' != b} snr_b'), from the per-UE triple (sum over all BS but the strongest, the strongest, which one).
+// The reciprocal is dcb_rcp (<= 1 ulp, a quarter of the instructions of an IEEE division); every place that judges or
+// uses a link goes through this one function, so the in-range decisions of all phases agree bit for bit.
 struct UeInterference { double rest, smax; int bmax; };
 __device__ __forceinline__ double pair_sinr(double snr, int b, const UeInterference &u) {
     const double others = b == u.bmax ? u.rest : (u.rest - snr) + u.smax;
-    return snr / (1.0 + others);
+    return snr * dcb_rcp(1.0 + others);
+}
+
+// SNR of ANY pair of the map for the interference pass, where most pairs are far beyond the connection range: the table
+// form of dcb_snr_inrange takes the binary exponent of d^2 modulo 16, so exponents 16..31 (256 m <= d < 65 km) are the
+// entries of 0..15 times k16 = 2^(-16 h) -- no log2 / exp2 round trip and no divergent call for a far base station.
+__device__ __forceinline__ double snr_of_d2_anywhere(const DevParams &p, const MathTables *tab, double k16, double d2) {
+    if (d2 >= 1.0 && d2 < 4294967296.0) {
+        const double s = dcb_snr_inrange(tab, p.pw, d2);
+        return d2 < DCB_FAR_D2 ? s : s * k16;
+    }
+    return snr_of_d2_general(p.snr_c0, p.snr_h, tab, d2);
 }
 
 __device__ __forceinline__ int rank_of(u64 mask, int b) { return __popcll(mask & (((u64)1 << b) - 1)); }
@@ -103,32 +116,6 @@ __device__ __forceinline__ void wide_reduce_links(const WideSmem &S, int N, int 
             S.arg[b] = a0;
             if (EXT) { S.lcnt[b] = c; S.lsum[b] = s; S.lbest[b] = best; }
         }
-    }
-}
-
-// Interference extension: sum over all base stations of the SNR at every UE's current position (S.sx, S.sy) -- one warp
-// per UE, lanes over the base stations (two passes cover M <= 64), folded with warp shuffles.
-__device__ __forceinline__ void wide_interference_sums(const WideSmem &S, const DevParams &p, int NA, int M, int warp,
-                                                       int lane, int nwarps) {
-    const int b0 = lane, b1 = lane + 32;
-    const bool ok0 = b0 < M, ok1 = b1 < M;
-    const double2 bs0 = ok0 ? S.bsxy[b0] : make_double2(0.0, 0.0), bs1 = ok1 ? S.bsxy[b1] : make_double2(0.0, 0.0);
-    for (int r = warp; r < NA; r += nwarps) {
-        const double rx = S.rec[r].x, ry = S.rec[r].y;
-        const double v0 = ok0 ? snr_of_d2(p, S.tab, dist2(bs0, rx, ry)) : 0.0;
-        const double v1 = ok1 ? snr_of_d2(p, S.tab, dist2(bs1, rx, ry)) : 0.0;
-        // strongest BS (first index on ties), then the sum of the others
-        double mx = v0;
-        int bm = b0;
-        if (v1 > mx) { mx = v1; bm = b1; }
-        for (int off = 16; off > 0; off >>= 1) {
-            const double om = __shfl_xor_sync(0xffffffffu, mx, off);
-            const int ob = __shfl_xor_sync(0xffffffffu, bm, off);
-            if (om > mx || (om == mx && ob < bm)) { mx = om; bm = ob; }
-        }
-        double v = (b0 == bm ? 0.0 : v0) + (b1 == bm ? 0.0 : v1);
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        if (lane == 0) { S.ssum[r] = v; S.smax[r] = mx; S.sbmax[r] = bm; }
     }
 }
 
@@ -263,9 +250,82 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
     const bool no_move = EXT && (a.flags & DCB_STEPF_NO_MOVE) != 0;
     double *Xrow = S.Xs + (size_t)i * LC;
     __syncthreads();
+    // Interference extension, the pass over ALL pairs of the env at the UEs' current positions (S.rec[].x / y): one warp per
+    // UE row, lanes over the base stations (two passes cover M <= 64).  The SNR of every BS, the strongest BS (first index
+    // on ties) and the sum of the OTHERS by warp shuffles -> S.ssum / smax / sbmax, which every later judgement of a link of
+    // that UE reads.  With `emit` (the positions are those of this step's observation) the same pass finishes everything
+    // that depends on the positions alone, so that no pair is evaluated twice per step: the SINR of every pair, the
+    // in-range set for the reward phase (UeRec::inr), and the observation entry 'dr' = SINR_b / max SINR (variants.py:276-284;
+    // MaxNorm: variants.py:322-330) -- written straight to the row's 'dr' segment of the observation buffer; the row phase
+    // adds the other segments.  The data-rate observation classes need the per-BS aggregates of the step as well and keep
+    // their own row phase.
+    const double k16 = interf ? dcb_exp2(tab, -16.0 * p.snr_h) : 1.0;
+    auto interference_pass = [&](bool emit, int step, bool last) {
+        const int b0 = lane, b1 = lane + 32;
+        const bool ok0 = b0 < M, ok1 = b1 < M;
+        const double2 bs0 = ok0 ? S.bsxy[b0] : make_double2(0.0, 0.0), bs1 = ok1 ? S.bsxy[b1] : make_double2(0.0, 0.0);
+        emit = emit && !p.obs_var;
+        float *obs_env = (emit && a.out.obs) ? a.out.obs + (size_t)step * a.out.obs_stride + (size_t)k * per_env : nullptr;
+        double *dbg_env = (emit && last && a.out.dbg_obs) ? a.out.dbg_obs + (size_t)k * per_env : nullptr;
+        double *dbg_snr = (emit && last && a.out.dbg_snr) ? a.out.dbg_snr + (size_t)k * N * M : nullptr;
+        const bool want_inr = emit && !central && T > 0;
+        // 'dr' segment of row r: central [N*M + r*M + b], multi [r*OW + M + b]
+        const int dr_row = central ? M : OW, dr_off = central ? N * M : M;
+        for (int r = warp; r < NA; r += nwarps) {
+            const double rx = S.rec[r].x, ry = S.rec[r].y;
+            const double v0 = ok0 ? snr_of_d2_anywhere(p, tab, k16, dist2(bs0, rx, ry)) : 0.0;
+            const double v1 = ok1 ? snr_of_d2_anywhere(p, tab, k16, dist2(bs1, rx, ry)) : 0.0;
+            double mx = v0;
+            int bm = b0;
+            if (v1 > mx) { mx = v1; bm = b1; }
+            for (int off = 16; off > 0; off >>= 1) {
+                const double om = __shfl_xor_sync(0xffffffffu, mx, off);
+                const int ob = __shfl_xor_sync(0xffffffffu, bm, off);
+                if (om > mx || (om == mx && ob < bm)) { mx = om; bm = ob; }
+            }
+            double v = (b0 == bm ? 0.0 : v0) + (b1 == bm ? 0.0 : v1);
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (lane == 0) { S.ssum[r] = v; S.smax[r] = mx; S.sbmax[r] = bm; }
+            if (!emit) continue;
+            UeInterference tot;
+            tot.rest = v; tot.smax = mx; tot.bmax = bm;
+            const double q0 = ok0 ? pair_sinr(v0, b0, tot) : 0.0, q1 = ok1 ? pair_sinr(v1, b1, tot) : 0.0;
+            if (want_inr) {
+                const unsigned in0 = __ballot_sync(0xffffffffu, q0 > DCB_SNR_THRESHOLD);
+                const unsigned in1 = __ballot_sync(0xffffffffu, q1 > DCB_SNR_THRESHOLD);
+                if (lane == 0) S.rec[r].inr = ((u64)in1 << 32) | in0;
+            }
+            float dr0, dr1;
+            if (p.obs_maxnorm) {
+                dr0 = max_norm_snr(q0); dr1 = max_norm_snr(q1);
+            } else {
+                double qmax = q0 > q1 ? q0 : q1;
+                for (int off = 16; off > 0; off >>= 1) {
+                    const double o = __shfl_xor_sync(0xffffffffu, qmax, off);
+                    qmax = o > qmax ? o : qmax;
+                }
+                const double inv_max = qmax > 0.0 ? 1.0 / qmax : 0.0;
+                dr0 = (float)(q0 * inv_max); dr1 = (float)(q1 * inv_max);
+            }
+            const size_t e0 = (size_t)r * dr_row + dr_off + b0;
+            if (obs_env) {
+                if (ok0) obs_env[e0] = dr0;
+                if (ok1) obs_env[e0 + 32] = dr1;
+            }
+            if (dbg_env) {
+                if (ok0) dbg_env[e0] = (double)dr0;
+                if (ok1) dbg_env[e0 + 32] = (double)dr1;
+            }
+            if (dbg_snr) {
+                if (ok0) dbg_snr[(size_t)r * M + b0] = q0;
+                if (ok1) dbg_snr[(size_t)r * M + b1] = q1;
+            }
+        }
+    };
     if (interf) {
-        // the SNR sums at the positions the launch starts from; every step refreshes them after its move
-        wide_interference_sums(S, p, NA, M, warp, lane, nwarps);
+        // the sums at the positions the launch starts from (an observe-only launch: that is its observation); every step
+        // refreshes them after its move
+        interference_pass(T == 0, 0, true);
         __syncthreads();
     }
     // in range (can_connect, station.py:222-226) and unshared rate (station.py:129-138) of one pair, SNR or SINR based
@@ -276,11 +336,11 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
         return q;
     };
     auto in_range = [&](double d2, int b, const UeInterference &q) -> bool {
-        if (interf) return pair_sinr(snr_of_d2(p, tab, d2), b, q) > DCB_SNR_THRESHOLD;
+        if (interf) return pair_sinr(snr_of_d2_anywhere(p, tab, k16, d2), b, q) > DCB_SNR_THRESHOLD;
         return d2 <= p.thr_d2;
     };
     auto unshared_rate = [&](double d2, int b, const UeInterference &q) -> double {
-        if (interf) return DCB_BW * dcb_log2_1p(tab, pair_sinr(snr_of_d2(p, tab, d2), b, q));
+        if (interf) return DCB_BW * dcb_log2_1p(tab, pair_sinr(snr_of_d2_anywhere(p, tab, k16, d2), b, q));
         return rate_of_d2(p, tab, d2);
     };
 
@@ -307,7 +367,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                 if (interf) {               // the SNR sums follow the UEs to their initial positions (CTA-uniform branch)
                     if (valid) { S.rec[i].x = x; S.rec[i].y = y; }
                     __syncthreads();
-                    wide_interference_sums(S, p, NA, M, warp, lane, nwarps);
+                    interference_pass(false, step, last);
                     __syncthreads();
                 }
             }
@@ -379,13 +439,15 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
                     if (!interf) drop_links();          // (same basic block as the move in the plain instances)
                 }
             }
-            if (interf && !no_move) {
-                // the SINR at the new positions needs the SNR sums there before any link can be judged
-                if (valid) { S.rec[i].x = x; S.rec[i].y = y; }
+            if (interf) {
+                // the SINR at the new positions needs the SNR sums there before any link can be judged; these are the
+                // positions of the step's observation, so the pass emits what depends on them alone (no-move mode: the
+                // positions stay, the pass only emits)
+                if (valid && !no_move) { S.rec[i].x = x; S.rec[i].y = y; }
                 __syncthreads();
-                wide_interference_sums(S, p, NA, M, warp, lane, nwarps);
+                interference_pass(true, step, last);
                 __syncthreads();
-                if (valid) drop_links();
+                if (valid && !no_move) drop_links();
             }
             if (!no_move) tk += 1;                                                     // base.py:454
             __syncthreads();      // bits cleared, slots of the pre-move pass consumed
@@ -548,109 +610,104 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
             const UeRec *rp = S.rec + r;
             const double rx = rp->x, ry = rp->y, rutil = rp->util;
             const u64 rmask = rp->mask;
+            if (EXT && interf && !p.obs_var) {
+                // ---- interference extension with the RelNorm / MaxNorm observation: the row's 'dr' entries, its in-range set
+                // and the SINR taps were written by this step's interference pass (they depend on the positions alone);
+                // what is left are the segments that depend on the links
+                const float c0 = ((unsigned)rmask & lanebit) ? 1.0f : 0.0f;
+                const float c1 = ((unsigned)(rmask >> 32) & lanebit) ? 1.0f : 0.0f;
+                const double un = rutil * (1.0 / DCB_MAX_UTILITY);
+                if (obs_env) {
+                    if (central) {
+                        if (ok0) o[0] = c0;
+                        if (ok1) o[32] = c1;
+                        if (lane == 0) obs_env[(size_t)2 * N * M + r] = (float)un;
+                    } else {
+                        if (ok0) { o[0] = c0; o[seg2] = fu0; o[seg3] = fa0; }
+                        if (ok1) { o[32] = c1; o[seg2 + 32] = fu1; o[seg3 + 32] = fa1; }
+                        if (lane == 0) o[4 * M] = (float)un;
+                    }
+                }
+                if (last && a.out.dbg_obs) {
+                    double *dbg_env = a.out.dbg_obs + (size_t)k * per_env;
+                    if (central) {
+                        if (ok0) dbg_env[r * M + b0] = (double)c0;
+                        if (ok1) dbg_env[r * M + b1] = (double)c1;
+                        if (lane == 0) dbg_env[2 * N * M + r] = un;
+                    } else {
+                        double *drow = dbg_env + (size_t)r * OW;
+#pragma unroll
+                        for (int q = 0; q < 2; q++) {
+                            const int b = q ? b1 : b0;
+                            if (b < M) {
+                                const int c = S.cnt_obs[b];
+                                drow[b] = (double)(q ? c1 : c0);
+                                drow[2 * M + b] = (double)c / (double)NA;
+                                drow[3 * M + b] = (c > 0 ? S.usum[b] / (double)c : 0.0) / DCB_MAX_UTILITY;
+                            }
+                        }
+                        if (lane == 0) drow[4 * M] = un;
+                    }
+                }
+                continue;
+            }
             const double d20 = ok0 ? dist2(bs0, rx, ry) : CUDART_INF;
             const double d21 = ok1 ? dist2(bs1, rx, ry) : CUDART_INF;
-            if (EXT && (p.obs_var || interf)) {
-                // ---- general instance: SINR-based quantities (interference extension) and / or the data-rate observation
-                // classes (NormDrMobileEnv / DatarateMobileEnv.get_ue_obs, variants.py:127-250; central layout)
+            if (EXT && p.obs_var) {
+                // ---- general instance: the data-rate observation classes (NormDrMobileEnv / DatarateMobileEnv.get_ue_obs,
+                // variants.py:127-250; central layout), on the SNR or -- interference extension -- the SINR
                 const UeInterference tot = ue_interf(r);
-                const double q0 = ok0 ? (interf ? pair_sinr(snr_of_d2(p, tab, d20), b0, tot) : snr_of_d2(p, tab, d20)) : 0.0;
-                const double q1 = ok1 ? (interf ? pair_sinr(snr_of_d2(p, tab, d21), b1, tot) : snr_of_d2(p, tab, d21)) : 0.0;
+                const double q0 = ok0 ? (interf ? pair_sinr(snr_of_d2_anywhere(p, tab, k16, d20), b0, tot) : snr_of_d2(p, tab, d20)) : 0.0;
+                const double q1 = ok1 ? (interf ? pair_sinr(snr_of_d2_anywhere(p, tab, k16, d21), b1, tot) : snr_of_d2(p, tab, d21)) : 0.0;
                 const bool r0in = ok0 && (interf ? q0 > DCB_SNR_THRESHOLD : d20 <= p.thr_d2);
                 const bool r1in = ok1 && (interf ? q1 > DCB_SNR_THRESHOLD : d21 <= p.thr_d2);
                 const unsigned in0 = __ballot_sync(0xffffffffu, r0in), in1 = __ballot_sync(0xffffffffu, r1in);
                 const bool cb0 = ((unsigned)rmask >> lane) & 1u, cb1 = ((unsigned)(rmask >> 32) >> lane) & 1u;
-                const double un = rutil * (1.0 / DCB_MAX_UTILITY);
                 const long long ru = kN + r;
                 double *dbg_env = (last && a.out.dbg_obs) ? a.out.dbg_obs + (size_t)k * per_env : nullptr;
-                if (p.obs_var) {
-                    const double ew = S.sew[r], ee = ew + DCB_EPSILON, iee = dcb_rcp(ee);
-                    double nx = rx, ny = ry;
-                    if (p.vo_next >= 0) {
-                        const uint2 mv = S.smv[r];
-                        const double vf = p.vel_u ? p.vel_u[ru] : p.vel_spec[r];
-                        step_towards_waypoint(rx, ry, (double)(mv.x & 0xffffu), (double)(mv.x >> 16),
-                                              vf >= 0.0 ? vf : (double)(mv.y & 0xffu), nx, ny);
-                    }
+                const double ew = S.sew[r], ee = ew + DCB_EPSILON, iee = dcb_rcp(ee);
+                double nx = rx, ny = ry;
+                if (p.vo_next >= 0) {
+                    const uint2 mv = S.smv[r];
+                    const double vf = p.vel_u ? p.vel_u[ru] : p.vel_spec[r];
+                    step_towards_waypoint(rx, ry, (double)(mv.x & 0xffffu), (double)(mv.x >> 16),
+                                          vf >= 0.0 ? vf : (double)(mv.y & 0xffu), nx, ny);
+                }
 #pragma unroll
-                    for (int q = 0; q < 2; q++) {
-                        const int b = q ? b1 : b0;
-                        if (b >= M) continue;
-                        const double d2 = q ? d21 : d20, qual = q ? q1 : q0;
-                        const bool inr = q ? r1in : r0in, conn = q ? cb1 : cb0;
-                        // Basestation.data_rate (station.py:204-220): the shared rate this UE gets, or would get if it were
-                        // counted in (data_rate_shared adds it temporarily, station.py:164-168, 197-201)
-                        double rate = 0.0;
-                        if (inr) {
-                            const int model = S.share[b];
-                            const double r0 = DCB_BW * dcb_log2_1p(tab, qual);
-                            if (conn) {
-                                rate = shared_rate(model, link_value(model, r0, iee), S.fac[b], S.arg[b], r, ee);
-                            } else {
-                                rate = rate_if_added(model, r0, ee, S.lcnt[b], S.lsum[b], S.lbest[b]);
-                            }
-                        }
-                        const double dro = obs_dr_entry(p, rate);                                       // variants.py:131-141, 213-221
-                        const size_t e = (size_t)r * M + b;
-                        const double vals[5] = {conn ? 1.0 : 0.0, sqrt(d2) / p.map_diag, dro,
-                                                sqrt(dist2(q ? bs1 : bs0, nx, ny)) / p.map_diag, (double)S.lcnt[b]};
-                        const int offs[5] = {p.vo_conn, p.vo_dist, p.vo_dr, p.vo_next, p.vo_ues};
-#pragma unroll
-                        for (int sgm = 0; sgm < 5; sgm++) {
-                            if (offs[sgm] < 0) continue;
-                            if (obs_env) obs_env[(size_t)offs[sgm] + e] = (float)vals[sgm];
-                            if (dbg_env) dbg_env[(size_t)offs[sgm] + e] = vals[sgm];
-                        }
-                    }
-                    if (lane == 0 && p.vo_tot >= 0) {
-                        const double cd = S.sdr[r];
-                        const double tot_o = obs_dr_total(p, cd);                                       // variants.py:147-152, 222
-                        if (obs_env) obs_env[(size_t)p.vo_tot + r] = (float)tot_o;
-                        if (dbg_env) dbg_env[(size_t)p.vo_tot + r] = tot_o;
-                    }
-                } else {
-                    // RelNorm / MaxNorm observation on the SINR (variants.py:276-284, 308-332)
-                    double qmax = q0 > q1 ? q0 : q1;
-                    for (int off = 16; off > 0; off >>= 1) {
-                        const double o = __shfl_xor_sync(0xffffffffu, qmax, off);
-                        qmax = o > qmax ? o : qmax;
-                    }
-                    const double inv_max = qmax > 0.0 ? 1.0 / qmax : 0.0;
-                    const float dr0 = p.obs_maxnorm ? max_norm_snr(q0) : (float)(q0 * inv_max);
-                    const float dr1 = p.obs_maxnorm ? max_norm_snr(q1) : (float)(q1 * inv_max);
-                    const float c0 = cb0 ? 1.0f : 0.0f, c1 = cb1 ? 1.0f : 0.0f;
-                    if (obs_env) {
-                        if (central) {
-                            if (ok0) { o[0] = c0; o[seg1] = dr0; }
-                            if (ok1) { o[32] = c1; o[seg1 + 32] = dr1; }
-                            if (lane == 0) obs_env[(size_t)2 * N * M + r] = (float)un;
+                for (int q = 0; q < 2; q++) {
+                    const int b = q ? b1 : b0;
+                    if (b >= M) continue;
+                    const double d2 = q ? d21 : d20, qual = q ? q1 : q0;
+                    const bool inr = q ? r1in : r0in, conn = q ? cb1 : cb0;
+                    // Basestation.data_rate (station.py:204-220): the shared rate this UE gets, or would get if it were
+                    // counted in (data_rate_shared adds it temporarily, station.py:164-168, 197-201)
+                    double rate = 0.0;
+                    if (inr) {
+                        const int model = S.share[b];
+                        const double r0 = DCB_BW * dcb_log2_1p(tab, qual);
+                        if (conn) {
+                            rate = shared_rate(model, link_value(model, r0, iee), S.fac[b], S.arg[b], r, ee);
                         } else {
-                            if (ok0) { o[0] = c0; o[seg1] = dr0; o[seg2] = fu0; o[seg3] = fa0; }
-                            if (ok1) { o[32] = c1; o[seg1 + 32] = dr1; o[seg2 + 32] = fu1; o[seg3 + 32] = fa1; }
-                            if (lane == 0) o[4 * M] = (float)un;
+                            rate = rate_if_added(model, r0, ee, S.lcnt[b], S.lsum[b], S.lbest[b]);
                         }
                     }
-                    if (dbg_env) {
-                        if (central) {
-                            if (ok0) { dbg_env[r * M + b0] = (double)c0; dbg_env[N * M + r * M + b0] = (double)dr0; }
-                            if (ok1) { dbg_env[r * M + b1] = (double)c1; dbg_env[N * M + r * M + b1] = (double)dr1; }
-                            if (lane == 0) dbg_env[2 * N * M + r] = un;
-                        } else {
-                            double *drow = dbg_env + (size_t)r * OW;
+                    const double dro = obs_dr_entry(p, rate);                                       // variants.py:131-141, 213-221
+                    const size_t e = (size_t)r * M + b;
+                    const double vals[5] = {conn ? 1.0 : 0.0, sqrt(d2) / p.map_diag, dro,
+                                            sqrt(dist2(q ? bs1 : bs0, nx, ny)) / p.map_diag, (double)S.lcnt[b]};
+                    const int offs[5] = {p.vo_conn, p.vo_dist, p.vo_dr, p.vo_next, p.vo_ues};
 #pragma unroll
-                            for (int q = 0; q < 2; q++) {
-                                const int b = q ? b1 : b0;
-                                if (b < M) {
-                                    const int c = S.cnt_obs[b];
-                                    drow[b] = (double)(q ? c1 : c0);
-                                    drow[M + b] = (double)(q ? dr1 : dr0);
-                                    drow[2 * M + b] = (double)c / (double)NA;
-                                    drow[3 * M + b] = (c > 0 ? S.usum[b] / (double)c : 0.0) / DCB_MAX_UTILITY;
-                                }
-                            }
-                            if (lane == 0) drow[4 * M] = un;
-                        }
+                    for (int sgm = 0; sgm < 5; sgm++) {
+                        if (offs[sgm] < 0) continue;
+                        if (obs_env) obs_env[(size_t)offs[sgm] + e] = (float)vals[sgm];
+                        if (dbg_env) dbg_env[(size_t)offs[sgm] + e] = vals[sgm];
                     }
+                }
+                if (lane == 0 && p.vo_tot >= 0) {
+                    const double cd = S.sdr[r];
+                    const double tot_o = obs_dr_total(p, cd);                                       // variants.py:147-152, 222
+                    if (obs_env) obs_env[(size_t)p.vo_tot + r] = (float)tot_o;
+                    if (dbg_env) dbg_env[(size_t)p.vo_tot + r] = tot_o;
                 }
                 if (last && a.out.dbg_snr) {
                     if (ok0) a.out.dbg_snr[ru * M + b0] = q0;

@@ -353,6 +353,33 @@ def test_interference_extension_matches_c_restatement(kind, n_ue, n_bs, K, near)
     env.check_errors()
 
 
+@pytest.mark.parametrize('kind,reward', [('central', 'avg'), ('multi', 'avg'), ('multi', 'min'), ('multi', 'sum')])
+def test_interference_fragment_equals_single_steps(kind, reward):
+    """Interference extension: T fused steps in one launch == T single-step launches (the per-step interference pass writes
+    the 'dr' segment of each step's observation; the row phase the rest), with an on-device episode reset in between; an
+    observe-only launch returns the observation the last step returned."""
+    from deepcomp_b200 import BatchedMobileEnv, env_seeds
+    n_ue, n_bs, K, T = 70, 36, 3, 20
+    W, H, bs = c_oracle_grid(n_bs)
+    kw = dict(num_envs=K, n_ue=n_ue, bs_xy=bs, map_wh=(W, H), kind=kind, reward=reward, seeds=env_seeds(11, K, n_ue),
+              episode_length=8, auto_reset=True, interference=True)
+    a = torch.randint(0, n_bs + 1, (T, K, n_ue), dtype=torch.int32, device='cuda',
+                      generator=torch.Generator('cuda').manual_seed(5))
+    e1, e2 = BatchedMobileEnv(**kw), BatchedMobileEnv(**kw)
+    e1.reset(); e2.reset()
+    f = e1.step_many(a)
+    for t in range(T):
+        obs, rew, _, info = e2.step(a[t])
+        assert torch.equal(obs, f['obs'][t]) and torch.equal(rew, f['reward'][t]), t
+        assert torch.equal(info['lost_conn'], f['lost_conn'][t]), t
+    assert torch.equal(e1.observe(), f['obs'][T - 1]) and torch.equal(e2.observe(), f['obs'][T - 1])
+    assert float(f['obs'].abs().sum()) > 0 and bool(torch.isfinite(f['obs']).all())
+    s1, s2 = e1.get_state(), e2.get_state()
+    for key in ('pos', 'mask', 'ewma', 'movement', 'time'):
+        assert np.array_equal(s1[key], s2[key]), key
+    e1.check_errors(); e2.check_errors()
+
+
 def test_wide_fragment_equals_single_steps():
     """T fused steps in one launch of the wide kernel == T single-step launches (state carried in registers vs slabs),
     with an on-device episode reset in the middle."""
