@@ -155,6 +155,14 @@ __device__ __forceinline__ void wide_reduce_utility(const WideSmem &S, int NA, i
     }
 }
 
+// max over the warp of NON-NEGATIVE doubles: their bit patterns order like unsigned integers, so two redux.sync (high
+// words, then the low words of the lanes that hold the largest high word) replace a five-level shuffle ladder
+__device__ __forceinline__ double warp_max_nonneg(double v) {
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return __hiloint2double((int)mh, (int)ml);
+}
 __device__ __forceinline__ double warp_sum(double v) {
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     return v;
@@ -275,14 +283,11 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
             const double rx = S.rec[r].x, ry = S.rec[r].y;
             const double v0 = ok0 ? snr_of_d2_anywhere(p, tab, k16, dist2(bs0, rx, ry)) : 0.0;
             const double v1 = ok1 ? snr_of_d2_anywhere(p, tab, k16, dist2(bs1, rx, ry)) : 0.0;
-            double mx = v0;
-            int bm = b0;
-            if (v1 > mx) { mx = v1; bm = b1; }
-            for (int off = 16; off > 0; off >>= 1) {
-                const double om = __shfl_xor_sync(0xffffffffu, mx, off);
-                const int ob = __shfl_xor_sync(0xffffffffu, bm, off);
-                if (om > mx || (om == mx && ob < bm)) { mx = om; bm = ob; }
-            }
+            // the strongest BS, first index on ties: the SNR is positive (0 on the lanes past M), so the maximum is two
+            // redux.sync on the bit patterns and its owner the first set bit of two ballots
+            const double mx = warp_max_nonneg(v1 > v0 ? v1 : v0);
+            const unsigned eq0 = __ballot_sync(0xffffffffu, v0 == mx), eq1 = __ballot_sync(0xffffffffu, v1 == mx);
+            const int bm = eq0 ? __ffs(eq0) - 1 : 31 + __ffs(eq1);
             double v = (b0 == bm ? 0.0 : v0) + (b1 == bm ? 0.0 : v1);
             for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
             if (lane == 0) { S.ssum[r] = v; S.smax[r] = mx; S.sbmax[r] = bm; }
@@ -299,11 +304,7 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
             if (p.obs_maxnorm) {
                 dr0 = max_norm_snr(q0); dr1 = max_norm_snr(q1);
             } else {
-                double qmax = q0 > q1 ? q0 : q1;
-                for (int off = 16; off > 0; off >>= 1) {
-                    const double o = __shfl_xor_sync(0xffffffffu, qmax, off);
-                    qmax = o > qmax ? o : qmax;
-                }
+                const double qmax = warp_max_nonneg(q0 > q1 ? q0 : q1);
                 const double inv_max = qmax > 0.0 ? 1.0 / qmax : 0.0;
                 dr0 = (float)(q0 * inv_max); dr1 = (float)(q1 * inv_max);
             }
