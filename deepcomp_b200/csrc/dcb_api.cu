@@ -734,6 +734,7 @@ int dcb_set_interference(dcb_env *env, int32_t on) {
     DeviceGuard guard(env->device);
     const int rc = force_wide_kernel(env);
     if (rc != DCB_OK) return rc;
+    CU(dcb_wide_upload_interference_constants(env->p.pw, env->p.snr_c0, env->p.snr_h));
     env->p.interference = 1;
     return DCB_OK;
 }

@@ -322,5 +322,7 @@ cudaError_t dcb_launch_step(const StepArgs &a, int threads, int grid, size_t sme
 cudaError_t dcb_step_set_smem_limit(int threads, int n_bs, size_t smem);
 cudaError_t dcb_launch_wide(const StepArgs &a, int threads, int grid, size_t smem, cudaStream_t s);
 cudaError_t dcb_wide_set_smem_limit(size_t smem);
+// radio constants of the interference pass -> constant memory of the current device (dcb_wide.cu)
+cudaError_t dcb_wide_upload_interference_constants(const double *pw10, double snr_c0, double snr_h);
 size_t dcb_step_smem_bytes(int kind, int N, int M, int E, int var = 0);
 int dcb_step_regs_per_thread(int threads, int n_bs);

@@ -73,12 +73,16 @@ __device__ __forceinline__ double pair_sinr(double snr, int b, const UeInterfere
 // SNR of ANY pair of the map for the interference pass, where most pairs are far beyond the connection range: the table
 // form of dcb_snr_inrange takes the binary exponent of d^2 modulo 16, so exponents 16..31 (256 m <= d < 65 km) are the
 // entries of 0..15 times k16 = 2^(-16 h) -- no log2 / exp2 round trip and no divergent call for a far base station.
-__device__ __forceinline__ double snr_of_d2_anywhere(const DevParams &p, const MathTables *tab, double k16, double d2) {
+__device__ __forceinline__ double snr_of_d2_anywhere(const double *pw, double c0, double h, const MathTables *tab, double k16,
+                                                     double d2) {
     if (d2 >= 1.0 && d2 < 4294967296.0) {
-        const double s = dcb_snr_inrange(tab, p.pw, d2);
+        const double s = dcb_snr_inrange(tab, pw, d2);
         return d2 < DCB_FAR_D2 ? s : s * k16;
     }
-    return snr_of_d2_general(p.snr_c0, p.snr_h, tab, d2);
+    return snr_of_d2_general(c0, h, tab, d2);
+}
+__device__ __forceinline__ double snr_of_d2_anywhere(const DevParams &p, const MathTables *tab, double k16, double d2) {
+    return snr_of_d2_anywhere(p.pw, p.snr_c0, p.snr_h, tab, k16, d2);
 }
 
 __device__ __forceinline__ int rank_of(u64 mask, int b) { return __popcll(mask & (((u64)1 << b) - 1)); }
@@ -175,6 +179,96 @@ __device__ __forceinline__ double warp_min(double v) {
     return v;
 }
 
+// ------------------------------------------------------------------------------------------------ interference pass
+// Interference extension, the pass over ALL pairs of the env at the UEs' current positions (UeRec::x / y): one warp per UE
+// row, lanes over the base stations (two passes cover M <= 64).  The SNR of every BS, the strongest BS (first index on
+// ties) and the sum of the OTHERS -> ssum / smax / sbmax, which every later judgement of a link of that UE reads.  With
+// `emit` (the positions are those of this step's observation) the same pass finishes everything that depends on the
+// positions alone, so that no pair is evaluated twice per step: the SINR of every pair, the in-range set for the reward
+// phase (UeRec::inr), and the observation entry 'dr' = SINR_b / max SINR (variants.py:276-284; MaxNorm: variants.py:322-330)
+// -- written straight to the row's 'dr' segment of the observation buffer; the row phase adds the other segments.  The
+// data-rate observation classes need the per-BS aggregates of the step as well and keep their own row phase.
+//
+// A function of its own, NOT inlined: inside the 1024-thread kernel (64 registers) the row loop shared its registers with
+// everything else that is live across a step, and 15 % of its instructions re-read %tid and re-derived shared-memory
+// addresses (ncu source view, profiles/r02_wide_interf_hotlines.txt).  The radio constants it needs come from constant
+// memory, as instruction operands -- like DevParams in the kernel: pw[0..9] (binomial series of dcb_snr_inrange), snr_c0,
+// snr_h; the same for every handle (dcb_create derives them from the reference's constants), uploaded by
+// dcb_wide_upload_interference_constants.
+__constant__ double c_interf[12];
+
+struct InterfPass {
+    int off_tab, off_bsxy, off_rec, off_ssum, off_smax, off_sbmax;   // shared-memory offsets (WideLayout)
+    int NA, M, nwarps;
+    int dr_row, dr_off;          // the 'dr' entry of (row r, BS b) is element r * dr_row + dr_off + b of the env's observation
+    int emit, want_inr, maxnorm;
+    double k16;                  // 2^(-16 h), snr_of_d2_anywhere
+    float *obs_env;              // this step's observation of the env, or NULL
+    double *dbg_env, *dbg_snr;   // fp64 taps of the launch's last step, or NULL
+};
+
+__device__ __noinline__ void wide_interference_pass(const InterfPass q) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const MathTables *tab = reinterpret_cast<const MathTables *>(smem + q.off_tab);
+    const double2 *bsxy = reinterpret_cast<const double2 *>(smem + q.off_bsxy);
+    UeRec *rec = reinterpret_cast<UeRec *>(smem + q.off_rec);
+    double *ssum = reinterpret_cast<double *>(smem + q.off_ssum);
+    double *smax = reinterpret_cast<double *>(smem + q.off_smax);
+    int *sbmax = reinterpret_cast<int *>(smem + q.off_sbmax);
+    // (volatile: read once and kept, where ptxas would re-read %tid and mask it at every use in the row loop)
+    unsigned lane_u;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_u));
+    const int lane = (int)lane_u, warp = threadIdx.x >> 5;
+    const int M = q.M;
+    const int b0 = lane, b1 = lane + 32;
+    const bool ok0 = b0 < M, ok1 = b1 < M;
+    const double2 bs0 = ok0 ? bsxy[b0] : make_double2(0.0, 0.0), bs1 = ok1 ? bsxy[b1] : make_double2(0.0, 0.0);
+    const double k16 = q.k16;
+    float *const obs_env = q.obs_env;
+    double *const dbg_env = q.dbg_env, *const dbg_snr = q.dbg_snr;
+    for (int r = warp; r < q.NA; r += q.nwarps) {
+        const double rx = rec[r].x, ry = rec[r].y;
+        const double v0 = ok0 ? snr_of_d2_anywhere(c_interf, c_interf[10], c_interf[11], tab, k16, dist2(bs0, rx, ry)) : 0.0;
+        const double v1 = ok1 ? snr_of_d2_anywhere(c_interf, c_interf[10], c_interf[11], tab, k16, dist2(bs1, rx, ry)) : 0.0;
+        // the strongest BS, first index on ties: the SNR is positive (0 on the lanes past M), so the maximum is two
+        // redux.sync on the bit patterns and its owner the first set bit of two ballots
+        const double mx = warp_max_nonneg(v1 > v0 ? v1 : v0);
+        const unsigned eq0 = __ballot_sync(0xffffffffu, v0 == mx), eq1 = __ballot_sync(0xffffffffu, v1 == mx);
+        const int bm = eq0 ? __ffs(eq0) - 1 : 31 + __ffs(eq1);
+        const double v = warp_sum((b0 == bm ? 0.0 : v0) + (b1 == bm ? 0.0 : v1));
+        if (lane == 0) { ssum[r] = v; smax[r] = mx; sbmax[r] = bm; }
+        if (!q.emit) continue;
+        UeInterference tot;
+        tot.rest = v; tot.smax = mx; tot.bmax = bm;
+        const double q0 = ok0 ? pair_sinr(v0, b0, tot) : 0.0, q1 = ok1 ? pair_sinr(v1, b1, tot) : 0.0;
+        if (q.want_inr) {
+            const unsigned in0 = __ballot_sync(0xffffffffu, q0 > DCB_SNR_THRESHOLD);
+            const unsigned in1 = __ballot_sync(0xffffffffu, q1 > DCB_SNR_THRESHOLD);
+            if (lane == 0) rec[r].inr = ((u64)in1 << 32) | in0;
+        }
+        float dr0, dr1;
+        if (q.maxnorm) {
+            dr0 = max_norm_snr(q0); dr1 = max_norm_snr(q1);
+        } else {
+            const double inv_max = dcb_rcp(warp_max_nonneg(q0 > q1 ? q0 : q1));   // (some SINR is > 0: M >= 1)
+            dr0 = (float)(q0 * inv_max); dr1 = (float)(q1 * inv_max);
+        }
+        const size_t e0 = (size_t)r * q.dr_row + q.dr_off + b0;
+        if (obs_env) {
+            if (ok0) obs_env[e0] = dr0;
+            if (ok1) obs_env[e0 + 32] = dr1;
+        }
+        if (dbg_env) {
+            if (ok0) dbg_env[e0] = (double)dr0;
+            if (ok1) dbg_env[e0 + 32] = (double)dr1;
+        }
+        if (dbg_snr) {
+            if (ok0) dbg_snr[(size_t)r * M + b0] = q0;
+            if (ok1) dbg_snr[(size_t)r * M + b1] = q1;
+        }
+    }
+}
+
 // PAD: the envs have padding slots (NA < N, variable UE population)
 // EXT: the general instance -- data-rate observation classes (dcb_set_obs_variant), the interference extension
 // (dcb_set_interference), UniformMovement UEs, the no-move launch mode; the plain instances compile without them
@@ -258,70 +352,21 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
     const bool no_move = EXT && (a.flags & DCB_STEPF_NO_MOVE) != 0;
     double *Xrow = S.Xs + (size_t)i * LC;
     __syncthreads();
-    // Interference extension, the pass over ALL pairs of the env at the UEs' current positions (S.rec[].x / y): one warp per
-    // UE row, lanes over the base stations (two passes cover M <= 64).  The SNR of every BS, the strongest BS (first index
-    // on ties) and the sum of the OTHERS by warp shuffles -> S.ssum / smax / sbmax, which every later judgement of a link of
-    // that UE reads.  With `emit` (the positions are those of this step's observation) the same pass finishes everything
-    // that depends on the positions alone, so that no pair is evaluated twice per step: the SINR of every pair, the
-    // in-range set for the reward phase (UeRec::inr), and the observation entry 'dr' = SINR_b / max SINR (variants.py:276-284;
-    // MaxNorm: variants.py:322-330) -- written straight to the row's 'dr' segment of the observation buffer; the row phase
-    // adds the other segments.  The data-rate observation classes need the per-BS aggregates of the step as well and keep
-    // their own row phase.
+    // interference extension: the pass over all pairs of the env (wide_interference_pass above)
     const double k16 = interf ? dcb_exp2(tab, -16.0 * p.snr_h) : 1.0;
     auto interference_pass = [&](bool emit, int step, bool last) {
-        const int b0 = lane, b1 = lane + 32;
-        const bool ok0 = b0 < M, ok1 = b1 < M;
-        const double2 bs0 = ok0 ? S.bsxy[b0] : make_double2(0.0, 0.0), bs1 = ok1 ? S.bsxy[b1] : make_double2(0.0, 0.0);
+        InterfPass q;
+        q.off_tab = L.off_tab; q.off_bsxy = L.off_bsxy; q.off_rec = L.off_rec;
+        q.off_ssum = L.off_ssum; q.off_smax = L.off_smax; q.off_sbmax = L.off_sbmax;
+        q.NA = NA; q.M = M; q.nwarps = nwarps;
+        q.dr_row = central ? M : OW; q.dr_off = central ? N * M : M;
         emit = emit && !p.obs_var;
-        float *obs_env = (emit && a.out.obs) ? a.out.obs + (size_t)step * a.out.obs_stride + (size_t)k * per_env : nullptr;
-        double *dbg_env = (emit && last && a.out.dbg_obs) ? a.out.dbg_obs + (size_t)k * per_env : nullptr;
-        double *dbg_snr = (emit && last && a.out.dbg_snr) ? a.out.dbg_snr + (size_t)k * N * M : nullptr;
-        const bool want_inr = emit && !central && T > 0;
-        // 'dr' segment of row r: central [N*M + r*M + b], multi [r*OW + M + b]
-        const int dr_row = central ? M : OW, dr_off = central ? N * M : M;
-        for (int r = warp; r < NA; r += nwarps) {
-            const double rx = S.rec[r].x, ry = S.rec[r].y;
-            const double v0 = ok0 ? snr_of_d2_anywhere(p, tab, k16, dist2(bs0, rx, ry)) : 0.0;
-            const double v1 = ok1 ? snr_of_d2_anywhere(p, tab, k16, dist2(bs1, rx, ry)) : 0.0;
-            // the strongest BS, first index on ties: the SNR is positive (0 on the lanes past M), so the maximum is two
-            // redux.sync on the bit patterns and its owner the first set bit of two ballots
-            const double mx = warp_max_nonneg(v1 > v0 ? v1 : v0);
-            const unsigned eq0 = __ballot_sync(0xffffffffu, v0 == mx), eq1 = __ballot_sync(0xffffffffu, v1 == mx);
-            const int bm = eq0 ? __ffs(eq0) - 1 : 31 + __ffs(eq1);
-            double v = (b0 == bm ? 0.0 : v0) + (b1 == bm ? 0.0 : v1);
-            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-            if (lane == 0) { S.ssum[r] = v; S.smax[r] = mx; S.sbmax[r] = bm; }
-            if (!emit) continue;
-            UeInterference tot;
-            tot.rest = v; tot.smax = mx; tot.bmax = bm;
-            const double q0 = ok0 ? pair_sinr(v0, b0, tot) : 0.0, q1 = ok1 ? pair_sinr(v1, b1, tot) : 0.0;
-            if (want_inr) {
-                const unsigned in0 = __ballot_sync(0xffffffffu, q0 > DCB_SNR_THRESHOLD);
-                const unsigned in1 = __ballot_sync(0xffffffffu, q1 > DCB_SNR_THRESHOLD);
-                if (lane == 0) S.rec[r].inr = ((u64)in1 << 32) | in0;
-            }
-            float dr0, dr1;
-            if (p.obs_maxnorm) {
-                dr0 = max_norm_snr(q0); dr1 = max_norm_snr(q1);
-            } else {
-                const double qmax = warp_max_nonneg(q0 > q1 ? q0 : q1);
-                const double inv_max = qmax > 0.0 ? 1.0 / qmax : 0.0;
-                dr0 = (float)(q0 * inv_max); dr1 = (float)(q1 * inv_max);
-            }
-            const size_t e0 = (size_t)r * dr_row + dr_off + b0;
-            if (obs_env) {
-                if (ok0) obs_env[e0] = dr0;
-                if (ok1) obs_env[e0 + 32] = dr1;
-            }
-            if (dbg_env) {
-                if (ok0) dbg_env[e0] = (double)dr0;
-                if (ok1) dbg_env[e0 + 32] = (double)dr1;
-            }
-            if (dbg_snr) {
-                if (ok0) dbg_snr[(size_t)r * M + b0] = q0;
-                if (ok1) dbg_snr[(size_t)r * M + b1] = q1;
-            }
-        }
+        q.emit = emit; q.want_inr = emit && !central && T > 0; q.maxnorm = p.obs_maxnorm;
+        q.k16 = k16;
+        q.obs_env = (emit && a.out.obs) ? a.out.obs + (size_t)step * a.out.obs_stride + (size_t)k * per_env : nullptr;
+        q.dbg_env = (emit && last && a.out.dbg_obs) ? a.out.dbg_obs + (size_t)k * per_env : nullptr;
+        q.dbg_snr = (emit && last && a.out.dbg_snr) ? a.out.dbg_snr + (size_t)k * N * M : nullptr;
+        wide_interference_pass(q);
     };
     if (interf) {
         // the sums at the positions the launch starts from (an observe-only launch: that is its observation); every step
@@ -852,6 +897,14 @@ __global__ void __launch_bounds__(1024, 1) dcb_wide_kernel(const __grid_constant
             else { if (pad) { auto kern = dcb_wide_kernel<true, false, false>; EXPR; } else { auto kern = dcb_wide_kernel<false, false, false>; EXPR; } }    \
         }                                                                                           \
     } while (0)
+
+cudaError_t dcb_wide_upload_interference_constants(const double *pw10, double snr_c0, double snr_h) {
+    double v[12];
+    for (int j = 0; j < 10; j++) v[j] = pw10[j];
+    v[10] = snr_c0;
+    v[11] = snr_h;
+    return cudaMemcpyToSymbol(c_interf, v, sizeof(v));
+}
 
 cudaError_t dcb_wide_set_smem_limit(size_t smem) {
     cudaError_t e = cudaSuccess;
