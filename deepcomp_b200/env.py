@@ -457,6 +457,7 @@ class SeqMultiAgentMobileEnv(MultiAgentMobileEnv):
             assert self.action_space.contains(a), f"Action {a} does not fit action space {self.action_space}"
         dev = self._batch.device
         row, reward, _, info = self._batch.step_sequential(torch.as_tensor([a], dtype=torch.int32, device=dev), info=True)
+        self._batch.check_errors()     # device-side flags raise here, as in _step_batch
         if info['moved']:
             self.time += 1
         self.ue_order_idx = info['ue_index']

@@ -161,3 +161,47 @@ def test_python_oracle_sequential_multi_agent_matches_reference(name):
     assert z['step_time'][-1] == cfg['steps'] // n              # time advances once per round of the UEs
     moved = np.flatnonzero(np.diff(np.concatenate([[0], z['step_time']])))
     assert (moved % n == n - 1).all()
+
+
+@pytest.mark.parametrize('kind', ['central', 'multi'])
+def test_c_oracle_interference_extension_against_a_numpy_restatement(kind):
+    """The interference extension has no counterpart in the reference (SNR only, station.py:122-127); its oracle is the C
+    restatement.  Pin that restatement from a second side: numpy straight from the formula of docs/model.md with the
+    interference term added -- SINR_b = P_b / (noise + sum of the other P_b') -- on the positions of the C trace, incl. a UE on
+    top of a BS; and everything that follows from it in one step (in-range set, masks after the drop, unshared rates)."""
+    from oracle.deepcomp_oracle import grid_layout
+    n_ue, n_bs = 14, 9
+    W, H, bs = grid_layout(n_bs)
+    init_pos = [(bs[0][0], bs[0][1]), (bs[4][0] + 0.5, bs[4][1])] + [('random', 'random')] * (n_ue - 2)
+    velocities = [0, 0] + ['slow'] * (n_ue - 2)
+    kw = dict(kind=kind, n_ue=n_ue, bs_xy=bs, map_wh=(W, H), sharing='resource-fair', velocities=velocities, reward='avg',
+              episode_length=30, init_pos=init_pos, seed=5)
+    env = c_oracle.COracleEnv(interference=True, **kw)
+    plain = c_oracle.COracleEnv(**kw)
+    env.reset_trace(); plain.reset_trace()
+    bsa = np.asarray(bs, dtype=np.float64)
+    # station.py:26-30, 110-127 with numpy's own log10 / power
+    ch = 0.8 + (1.1 * np.log10(2500.0) - 0.7) * 1.5 - 1.56 * np.log10(2500.0)
+    c1 = 69.55 + 26.16 * np.log10(2500.0) - 13.82 * np.log10(50.0) - ch
+    c2 = 44.9 - 6.55 * np.log10(50.0)
+    rng = np.random.default_rng(2)
+    saw_difference = 0.0
+    for t in range(25):
+        a = rng.integers(0, n_bs + 1, n_ue).astype(np.int32)
+        w, p = env.step(a), plain.step(a)
+        d = np.sqrt(((w['pos'][:, None, :] - bsa[None, :, :]) ** 2).sum(-1))
+        power = 10.0 ** ((30.0 - (c1 + c2 * np.log10(d + 1e-16))) / 10.0)               # received power [mW]
+        noise = 1e-9
+        # (the others summed explicitly: `total - own` cancels catastrophically for a UE on top of a BS)
+        others = np.stack([np.delete(power, b, axis=1).sum(1) for b in range(n_bs)], axis=1)
+        sinr = power / (noise + others)
+        np.testing.assert_allclose(w['snr'], sinr, rtol=1e-9, atol=0)
+        # links exist only where the SINR clears the threshold, and a linked pair's unshared rate is bw log2(1 + SINR);
+        # with resource-fair sharing the shared rate is that over the number of UEs at the BS (station.py:129-138, 173)
+        assert not np.any(w['mask'].astype(bool) & ~(sinr > 2e-8))
+        cnt = w['mask'].sum(0)
+        exp_rate = np.where(w['mask'].astype(bool), 9e6 * np.log2(1.0 + sinr) / np.maximum(cnt, 1)[None, :], 0.0)
+        np.testing.assert_allclose(w['link_rates'], exp_rate, rtol=1e-9, atol=0)
+        assert np.array_equal(w['pos'], p['pos'])                                        # movement does not see the radio model
+        saw_difference = max(saw_difference, float(np.max(np.abs(w['snr'] / p['snr'] - 1.0))))
+    assert saw_difference > 1e-9
