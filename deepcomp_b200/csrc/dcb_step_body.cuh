@@ -329,6 +329,21 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
     const int T = a.T;
     const int n_iter = T > 0 ? T : 1;
 
+    // the physics threads' state and first action: issued ahead of the table / parameter loads of the prologue, so that a
+    // launch pays ONE global-memory latency before its first step instead of three in a row (tables, state, action)
+    double2 ld_ps = make_double2(0.0, 0.0);
+    uint2 ld_mv = make_uint2(0u, 0u);
+    unsigned long long ld_mask = 0;
+    double ld_ewma = 0.0;
+    int ld_tk = 0, ld_act = 0;
+    if (!is_obs && valid) {
+        ld_ps = p.pos[u];
+        ld_mv = p.mv[u];
+        ld_mask = p.mask[u];
+        ld_ewma = p.ewma[u];
+        ld_tk = p.time[k];
+        if (T > 0 && a.actions) ld_act = a.actions[u];
+    }
     dcb_math_init(tab, vthr, threadIdx.x, blockDim.x, p.tabs);
     for (int b = threadIdx.x; b < M; b += blockDim.x) {
         bsxy[b] = make_double2(p.bs_xy[2 * b], p.bs_xy[2 * b + 1]);
@@ -349,15 +364,11 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
         mask_t mask = 0;
         unsigned wxy = 0, vpt = 0;
         int tk = 0;
-        if (valid) {
-            const double2 ps = p.pos[u];
-            x = ps.x; y = ps.y;
-            const uint2 mv = p.mv[u];
-            wxy = mv.x; vpt = mv.y;
-            mask = (mask_t)p.mask[u];
-            ewma = p.ewma[u];
-            tk = p.time[k];
-        }
+        x = ld_ps.x; y = ld_ps.y;
+        wxy = ld_mv.x; vpt = ld_mv.y;
+        mask = (mask_t)ld_mask;
+        ewma = ld_ewma;
+        tk = ld_tk;
         // the waypoint-table entry under the cursor, fetched ahead of its use (ue_move)
         uint32_t *next_slot = snext + t;
         if (valid && (int)(vpt >> 16) < p.D) prefetch_table_entry(next_slot, p.table + u * p.D + (vpt >> 16));
@@ -426,7 +437,9 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
                                 act = policy_action<mask_t>(a.pol, mask, x, y, bsxy, M, i, a.pol.call0 + step, u);
                                 if (a.actions_out) a.actions_out[(size_t)step * p.K * N + u] = act;
                             } else {
-                                act = *(act_row - act_stride);          // act_row already points at step + 1
+                                // (the launch's first action came in with the state; a later fresh step -- an on-device
+                                // episode reset -- reads its own)
+                                act = step == 0 ? ld_act : *(act_row - act_stride);
                             }
                             if (act < 0 || act > M) {
                                 atomicOr(p.err, DCB_ERRBIT_ACTION);
@@ -615,11 +628,7 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
             DCB_TRACE_PT(0, 7);
         }
 // [region:P.drain+store]
-        // drain: the observers' last (up to two) EMPTY arrivals
-        if (n_iter >= 2) bar_sync(BAR_EMPTY + (n_iter & 1), 2 * G);
-        bar_sync(BAR_EMPTY + ((n_iter - 1) & 1), 2 * G);
-
-        // ---- registers -> state slabs
+        // ---- registers -> state slabs, while the observers are still busy with the last step (they never read the slabs)
         if (valid && T > 0) {
             p.pos[u] = make_double2(x, y);
             p.mv[u] = make_uint2(wxy, vpt);
@@ -627,6 +636,10 @@ __device__ __forceinline__ void dcb_step_body(const StepArgs &a) {
             p.ewma[u] = ewma;
             if (i == 0) p.time[k] = tk;
         }
+        // drain: the observers' last (up to two) EMPTY arrivals
+        if (n_iter >= 2) bar_sync(BAR_EMPTY + (n_iter & 1), 2 * G);
+        bar_sync(BAR_EMPTY + ((n_iter - 1) & 1), 2 * G);
+
 #ifdef DCB_TRACE_ON
         if (threadIdx.x == 0 && blockIdx.x < 4096) {
             dcb_trace_cta[3 * blockIdx.x + 1] = dcb_globaltimer();
