@@ -45,7 +45,15 @@ __device__ __forceinline__ void dcb_math_init(MathTables *t, double *vthr, int t
 // 1/x for a positive normal x, <= 1 ulp
 __device__ __forceinline__ double dcb_rcp(double x) {
     double y;
+#ifdef __CUDA_ARCH__
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#else
+    // host compilation of this header (tests/native/dcb_math_host.cpp: the table math checked on the CPU): a seed of the
+    // same ~20-bit quality, so that the two Newton steps below are exercised as on the device
+    int ex_;
+    const double m_ = frexp(x, &ex_);
+    y = ldexp((double)(1.0f / (float)m_), -ex_);
+#endif
     double e = fma(-x, y, 1.0);
     y = fma(y, e, y);
     e = fma(-x, y, 1.0);
