@@ -70,3 +70,59 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', txt, flags=re.M), f
                 assert 'dcb_oracle' not in txt, f
+
+
+def _sass_of(cubin_name, tmp):
+    """SASS of one cubin of the built library (cuobjdump -xelf / -sass), split by function"""
+    import shutil
+    import subprocess
+    if not shutil.which('cuobjdump'):
+        pytest.skip('cuobjdump not found')
+    subprocess.check_call(['cuobjdump', '-xelf', cubin_name, os.path.abspath(_lib.lib_path())], cwd=tmp,
+                          stdout=subprocess.DEVNULL)
+    txt = subprocess.run(['cuobjdump', '-sass', os.path.join(tmp, cubin_name)], capture_output=True, text=True).stdout
+    funcs, name = {}, None
+    for ln in txt.splitlines():
+        m = re.match(r'\s*Function : (\S+)', ln)
+        if m:
+            name = m.group(1)
+            funcs[name] = []
+        elif name and re.match(r'\s+/\*[0-9a-f]{4,}\*/', ln):
+            funcs[name].append(ln.split('*/', 1)[1].strip())
+    assert funcs, f'no functions in {cubin_name}'
+    return funcs
+
+
+def _count(lines, mnemonic):
+    return sum(1 for ln in lines if re.search(r'(^|\s)' + mnemonic + r'\b', ln))
+
+
+def test_built_kernels_are_sm100a_and_use_the_instructions_the_design_names(tmp_path):
+    """Static evidence from the shipped binary (no GPU): every cubin targets sm_100a, the fused step kernel's measured
+    instance sends its observation tile with the TMA bulk store (UBLKCP.G.S), prefetches the waypoint table with LDGSTS,
+    synchronises its two warp groups with named barriers and computes in fp64; nothing uses TMA tensor loads (the pair tile
+    never exists in HBM); the wide kernel reduces with redux.sync / shuffles and its interference pass is a function of
+    its own.  (profiles/r02_sass_tma_excerpt.txt is the human-readable form.)"""
+    import subprocess
+    elfs = subprocess.run(['cuobjdump', '-lelf', os.path.abspath(_lib.lib_path())], capture_output=True, text=True).stdout
+    names = re.findall(r'ELF file\s+\d+:\s+(\S+)', elfs)
+    assert names and all(n.endswith('.sm_100a.cubin') for n in names), names
+    fused = _sass_of('dcb_step_k704.sm_100a.cubin', str(tmp_path))
+    head = [f for f in fused if 'dcb_step_kernel_704ILb1ELb0ELb0' in f]          # <M32, !PAD, !CENTRAL>: the headline instance
+    assert len(head) == 1, list(fused)
+    k = fused[head[0]]
+    assert _count(k, r'UBLKCP\.G\.S') >= 1 and _count(k, r'LDGSTS\S*') >= 1
+    assert _count(k, r'BAR\.SYNC\S*') + _count(k, r'BAR\.ARV\S*') + _count(k, r'BAR\.RED\S*') >= 10
+    assert _count(k, r'DFMA') > 200 and _count(k, r'MUFU\.\S+') > 10
+    assert _count(k, r'UTMALDG\S*') == 0 and not any('wgmma' in ln.lower() or 'HMMA' in ln for ln in k)
+    assert _count(k, r'STL\S*') + _count(k, r'LDL\S*') <= 24, 'the measured instance spills more than a few words'
+    wide = _sass_of('dcb_wide.sm_100a.cubin', str(tmp_path))
+    plain = [f for f in wide if 'dcb_wide_kernelILb0ELb0ELb0' in f]
+    assert len(plain) == 1
+    w = wide[plain[0]]
+    assert _count(w, r'CREDUX\S*') + _count(w, r'REDUX\S*') >= 1 and _count(w, r'SHFL\S*') >= 10 and _count(w, r'VOTE\S*') >= 2
+    # the interference pass is a function of its own in each of the four general (EXT) instances, and in no other
+    syms = subprocess.run(['cuobjdump', '-symbols', os.path.join(str(tmp_path), 'dcb_wide.sm_100a.cubin')],
+                          capture_output=True, text=True).stdout
+    owners = re.findall(r'dcb_wide_kernelILb([01])ELb([01])ELb([01])EEEv8StepArgs\$\S*wide_interference_pass', syms)
+    assert sorted(owners) == sorted((p, '1', c) for p in '01' for c in '01'), owners
