@@ -10,7 +10,8 @@ vector interfaces:
   env: observations / rewards / dones / infos are ``{env_id: {agent_id: ...}}`` dicts, agent ids are "1".."N"
   (env_setup.py:148-160).
 
-Both keep obs as numpy views of one pinned-host copy per step; per-env Python dicts are only built at this boundary.
+Both keep obs as numpy views of ONE host copy of the batch per step; per-env Python dicts are only built at this boundary
+(for host-buffer stepping without dicts use ``BatchedMobileEnv.step_host`` / ``step_many_host`` with pinned buffers).
 Episode ends follow the reference: ``done`` is never set by the env (base.py:371-381); RLlib's ``horizon`` calls
 ``reset_at`` / ``try_reset``.
 """
