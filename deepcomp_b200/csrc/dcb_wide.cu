@@ -11,6 +11,9 @@
 //   * per-row phase  -- one warp per UE row of the observation, lanes over the base stations: squared distances, the
 //     closest BS by a shuffle min-reduction, the in-range set by ballot, normalised SNR, and the row leaves as coalesced
 //     128-byte segments straight to the observation buffer (no staging tile: one env's observation is up to 804 KB).
+//   * interference extension (general instance only) -- one more row-parallel phase right after the move: the SNR of every
+//     pair of the env, per-UE interference sum, and what of the observation depends on the positions alone
+//     (wide_interference_pass).
 // A UE's link values live in a compact per-UE slot list (slot = rank of the BS in the UE's mask) instead of the dense
 // [N][M] matrix of the fused kernel; the slot capacity LC is the largest number of base stations any point of the map
 // can be in range of (host-computed bound, dcb_api.cu).
